@@ -1,0 +1,139 @@
+/*
+ * mbe_b200.h - C-ABI of the B200-native batched IMBE/AMBE decoder (libmbe_b200.so).
+ *
+ * Drop-in boundary for the decode-and-synthesis hot path of arancormonk/mbelib-neo v2.0.0.  Every entry
+ * point is the batched form of one family of calls in the reference's public header
+ * (/root/reference/include/mbelib-neo/mbelib.h, cited per function below): element [s][f] of a batch has
+ * exactly the per-call semantics of the reference function applied to stream s's state, frames in order.
+ *
+ * Conventions
+ *   - plain C, no CUDA/torch types: device pointers are `void*`/typed pointers into device memory,
+ *     CUDA streams are passed as `void*` (a cudaStream_t; NULL = the context's own stream).
+ *   - codec ids: MBE_B200_IMBE7200X4400 (P25 Phase 1, char[8][23]), MBE_B200_IMBE7100X4400
+ *     (ProVoice, char[7][24]), MBE_B200_AMBE3600X2400 (D-STAR, char[4][24]),
+ *     MBE_B200_AMBE3600X2450 (DMR/NXDN AMBE+2, char[4][24]).
+ *   - hard frames: one byte per bit (0/1), laid out [stream][frame][rows*cols] exactly like the
+ *     reference's `char fr[R][C]`; soft frames: `mbe_soft_bit` pairs {bit, reliability}
+ *     (mbelib.h:148-151), i.e. 2 bytes per bit, same order.
+ *   - PCM: int16 [stream][frame][160] (8 kHz, 20 ms) and/or float [stream][frame][160] in the
+ *     reference's float scale (mbelib.h:16-20).
+ *   - per-frame status: `mbe_b200_result` = the reference's mbe_process_result (mbelib.h:180-191) plus
+ *     the call's return value (`status`: >= 0 total corrected errors, MBE_STATUS_INVALID_ARGUMENT (-1),
+ *     MBE_STATUS_INVALID_BITS (-2)).  A frame with negative status leaves the stream state untouched
+ *     and produces silence.
+ *   - per-stream state lives on the device: the reference's caller-owned triplet cur_mp / prev_mp /
+ *     prev_mp_enhanced (3 x 2604 bytes, `struct mbe_parameters` layout, mbelib.h:88-137) plus the
+ *     reference's thread-local RNG state (comfort-noise LCG48 and unvoiced cold-start seed,
+ *     src/core/mbe_adaptive.c:29-30, src/core/mbe_unvoiced_fft.c:29-30) made per-stream.
+ *   - every function returns 0 on success or a negative MBE_B200_E_* code; mbe_b200_last_error()
+ *     gives the text.  There is NO CPU fallback: without a CUDA device create() fails.
+ */
+#ifndef MBE_B200_H
+#define MBE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBE_B200_API __attribute__((visibility("default")))
+
+enum {
+    MBE_B200_IMBE7200X4400 = 0,
+    MBE_B200_IMBE7100X4400 = 1,
+    MBE_B200_AMBE3600X2400 = 2,
+    MBE_B200_AMBE3600X2450 = 3
+};
+
+#define MBE_B200_SAMPLES_PER_FRAME 160
+#define MBE_B200_PARMS_BYTES       2604 /* sizeof(mbe_parms) */
+
+/* call-level error codes */
+#define MBE_B200_E_ARG    (-1) /* bad argument (NULL pointer, range, codec id) */
+#define MBE_B200_E_CUDA   (-2) /* CUDA runtime error, see mbe_b200_last_error() */
+#define MBE_B200_E_NOGPU  (-3) /* no usable CUDA device - the product has no CPU path */
+
+/* per-frame result: return value + mbe_process_result (mbelib.h:180-191; flags mbelib.h:153-166) */
+typedef struct mbe_b200_result {
+    int32_t status;           /* what the reference call would have returned */
+    int32_t c0_errors;
+    int32_t protected_errors;
+    int32_t c4_errors;
+    int32_t total_errors;
+    uint32_t flags;           /* MBE_PROCESS_FLAG_* bit values of the reference */
+} mbe_b200_result;
+
+typedef struct mbe_b200_ctx mbe_b200_ctx;
+
+/* ---- context: owns device tables, the per-stream state pool and staging buffers ---------------- */
+MBE_B200_API int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams);
+MBE_B200_API void mbe_b200_destroy(mbe_b200_ctx* ctx);
+MBE_B200_API const char* mbe_b200_last_error(const mbe_b200_ctx* ctx); /* ctx may be NULL: last create() error */
+MBE_B200_API const char* mbe_b200_version(void);
+MBE_B200_API int mbe_b200_geometry(int codec, int* frame_bits, int* param_bits); /* 184/168/96/96, 88/88/49/49 */
+/* kernel launches issued by this context so far (bench.py reports it as gpu_launches) */
+MBE_B200_API long long mbe_b200_launch_count(const mbe_b200_ctx* ctx);
+
+/* ---- stream state ---------------------------------------------------------------------------
+ * init_streams == per stream: mbe_setThreadRngSeed(seed) (mbelib.h:596; seeds==NULL: fresh-thread
+ * default RNG state) followed by mbe_initMbeParms (mbelib.h:615).
+ * export/import move [count][3] mbe_parms blobs {cur_mp, prev_mp, prev_mp_enhanced} to/from host
+ * memory byte-for-byte; export_rng/import_rng move the per-stream RNG words
+ * {comfort_seed48 lo, hi, unvoiced seed, override flag}. */
+MBE_B200_API int mbe_b200_init_streams(mbe_b200_ctx* ctx, int first_stream, int count, const uint32_t* seeds);
+MBE_B200_API int mbe_b200_export_state(mbe_b200_ctx* ctx, int first_stream, int count, void* parms_triplets);
+MBE_B200_API int mbe_b200_import_state(mbe_b200_ctx* ctx, int first_stream, int count, const void* parms_triplets);
+MBE_B200_API int mbe_b200_export_rng(mbe_b200_ctx* ctx, int first_stream, int count, uint32_t* rng_words4);
+MBE_B200_API int mbe_b200_import_rng(mbe_b200_ctx* ctx, int first_stream, int count, const uint32_t* rng_words4);
+
+/* ---- the hot path: frames -> PCM ---------------------------------------------------------------
+ * Batched mbe_process<Codec>Frame / Framef / SoftFrame / SoftFramef
+ * (mbelib.h:352-373, 429-447, 505-523, 564-582).  Streams first_stream .. first_stream+n_streams-1 each
+ * consume n_frames consecutive frames.  Any of pcm / pcmf / results / bits may be NULL.
+ *   _dev : all pointers are device pointers; the launch is asynchronous on `cuda_stream`.
+ *   host : pointers are host memory (pinned or pageable); H2D copy, kernel and D2H copy run on the
+ *          context's stream and the call returns when the results are in host memory. */
+MBE_B200_API int mbe_b200_process_frames_dev(mbe_b200_ctx* ctx, int codec, int soft, int first_stream, int n_streams,
+                                             int n_frames, const uint8_t* d_frames, int16_t* d_pcm, float* d_pcmf,
+                                             mbe_b200_result* d_results, uint8_t* d_bits, void* cuda_stream);
+MBE_B200_API int mbe_b200_process_frames(mbe_b200_ctx* ctx, int codec, int soft, int first_stream, int n_streams,
+                                         int n_frames, const uint8_t* frames, int16_t* pcm, float* pcmf,
+                                         mbe_b200_result* results, uint8_t* bits);
+
+/* ---- stage-split entry points ----------------------------------------------------------------
+ * decode_frames: batched mbe_decode<Codec>[Soft]Frame (mbelib.h:315,323,395,403,471,479,545,553):
+ *   ECC + PN de-scrambling only; stateless; n = number of frames; bits [n][param_bits] one byte per bit.
+ * process_data : batched mbe_process<Codec>Data / Dataf (mbelib.h:335-342, 415-419, 491-495): parameter
+ *   bits -> PCM with the stream state; `results` is IN/OUT like the reference's result pointer (context
+ *   flags C0_VALID/C4_VALID and counters in, status flags out); results==NULL means "no decode context"
+ *   (the reference's result==NULL rules). IMBE 7100 uses the IMBE 4400 parameter layout (mbelib.h:545). */
+MBE_B200_API int mbe_b200_decode_frames_dev(mbe_b200_ctx* ctx, int codec, int soft, int n, const uint8_t* d_frames,
+                                            uint8_t* d_bits, mbe_b200_result* d_results, void* cuda_stream);
+MBE_B200_API int mbe_b200_decode_frames(mbe_b200_ctx* ctx, int codec, int soft, int n, const uint8_t* frames,
+                                        uint8_t* bits, mbe_b200_result* results);
+MBE_B200_API int mbe_b200_process_data_dev(mbe_b200_ctx* ctx, int codec, int first_stream, int n_streams, int n_frames,
+                                           const uint8_t* d_bits, mbe_b200_result* d_results_inout, int16_t* d_pcm,
+                                           float* d_pcmf, void* cuda_stream);
+MBE_B200_API int mbe_b200_process_data(mbe_b200_ctx* ctx, int codec, int first_stream, int n_streams, int n_frames,
+                                       const uint8_t* bits, mbe_b200_result* results_inout, int16_t* pcm, float* pcmf);
+
+/* ---- synthesis-only entry points --------------------------------------------------------------
+ * synthesize_speech: batched mbe_synthesizeSpeechf / mbe_synthesizeSpeech (mbelib.h:652,662): element i
+ *   synthesises one frame from host parameter sets cur[i], prev[i] (mbe_parms blobs, updated in place
+ *   like the reference does) with RNG state as after mbe_setThreadRngSeed(seeds[i]) (seeds NULL: default).
+ * floattoshort: batched mbe_floattoshort (mbelib.h:675), n_frames x 160 samples. */
+MBE_B200_API int mbe_b200_synthesize_speech(mbe_b200_ctx* ctx, int n, void* cur_parms, void* prev_parms,
+                                            const uint32_t* seeds, float* pcmf, int16_t* pcm);
+MBE_B200_API int mbe_b200_floattoshort(mbe_b200_ctx* ctx, int n_frames, const float* in, int16_t* out);
+MBE_B200_API int mbe_b200_floattoshort_dev(mbe_b200_ctx* ctx, int n_frames, const float* d_in, int16_t* d_out,
+                                           void* cuda_stream);
+
+/* block until everything queued on the context's stream has finished */
+MBE_B200_API int mbe_b200_synchronize(mbe_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBE_B200_H */

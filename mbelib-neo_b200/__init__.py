@@ -1,0 +1,211 @@
+"""mbelib-neo_b200 - B200-native batched IMBE/AMBE decoder.
+
+The product is the C-ABI shared library `libmbe_b200.so` (CUDA kernels for sm_100a + a plain-C host API,
+see include/mbe_b200.h).  This package is the thin Python mirror of that ABI used by the tests and by
+bench.py: it loads the library with ctypes and forwards numpy host arrays or raw device pointers.  It
+contains no decoding logic and no CPU fallback - if the library or a CUDA device is missing, it raises.
+
+Because the directory name contains a hyphen (it mirrors the reference's project name), import it through
+`__graft_entry__.load_package()` (or put the repo root on sys.path and use importlib as that helper does).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmbe_b200.so")
+
+IMBE7200X4400, IMBE7100X4400, AMBE3600X2400, AMBE3600X2450 = 0, 1, 2, 3
+CODEC_BY_NAME = {"imbe7200x4400": 0, "imbe7100x4400": 1, "ambe3600x2400": 2, "ambe3600x2450": 3}
+FRAME_BITS = {0: 184, 1: 168, 2: 96, 3: 96}
+PARAM_BITS = {0: 88, 1: 88, 2: 49, 3: 49}
+SAMPLES = 160
+PARMS_BYTES = 2604
+
+# same field order as mbe_b200_result in include/mbe_b200.h
+RESULT_DTYPE = np.dtype([("status", "<i4"), ("c0_errors", "<i4"), ("protected_errors", "<i4"), ("c4_errors", "<i4"),
+                         ("total_errors", "<i4"), ("flags", "<u4")])
+
+_EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b200_version", "mbe_b200_geometry",
+            "mbe_b200_launch_count", "mbe_b200_init_streams", "mbe_b200_export_state", "mbe_b200_import_state",
+            "mbe_b200_export_rng", "mbe_b200_import_rng", "mbe_b200_process_frames_dev", "mbe_b200_process_frames",
+            "mbe_b200_decode_frames_dev", "mbe_b200_decode_frames", "mbe_b200_process_data_dev",
+            "mbe_b200_process_data", "mbe_b200_synthesize_speech", "mbe_b200_floattoshort",
+            "mbe_b200_floattoshort_dev", "mbe_b200_synchronize"]
+
+_lib = None
+
+
+class MbeB200Error(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    return list(_EXPORTS)
+
+
+def load_library():
+    """dlopen libmbe_b200.so (no CUDA call is made until a context is created)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MbeB200Error("libmbe_b200.so is not built - run `python mbelib-neo_b200/build.py` "
+                               "(there is no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        lib.mbe_b200_create.argtypes = [ctypes.POINTER(vp), ci, ci]
+        lib.mbe_b200_destroy.argtypes = [vp]
+        lib.mbe_b200_destroy.restype = None
+        lib.mbe_b200_last_error.argtypes = [vp]
+        lib.mbe_b200_last_error.restype = ctypes.c_char_p
+        lib.mbe_b200_version.restype = ctypes.c_char_p
+        lib.mbe_b200_launch_count.argtypes = [vp]
+        lib.mbe_b200_launch_count.restype = ctypes.c_longlong
+        lib.mbe_b200_geometry.argtypes = [ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        lib.mbe_b200_init_streams.argtypes = [vp, ci, ci, vp]
+        for n in ("export_state", "import_state", "export_rng", "import_rng"):
+            getattr(lib, "mbe_b200_" + n).argtypes = [vp, ci, ci, vp]
+        lib.mbe_b200_process_frames_dev.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
+        lib.mbe_b200_process_frames.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp]
+        lib.mbe_b200_decode_frames_dev.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp]
+        lib.mbe_b200_decode_frames.argtypes = [vp, ci, ci, ci, vp, vp, vp]
+        lib.mbe_b200_process_data_dev.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]
+        lib.mbe_b200_process_data.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, vp]
+        lib.mbe_b200_synthesize_speech.argtypes = [vp, ci, vp, vp, vp, vp, vp]
+        lib.mbe_b200_floattoshort.argtypes = [vp, ci, vp, vp]
+        lib.mbe_b200_floattoshort_dev.argtypes = [vp, ci, vp, vp, vp]
+        lib.mbe_b200_synchronize.argtypes = [vp]
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Decoder:
+    """One context = one GPU + a pool of `max_streams` device-resident voice-stream states."""
+
+    def __init__(self, max_streams, device=0):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p()
+        rc = self.lib.mbe_b200_create(ctypes.byref(self.h), int(device), int(max_streams))
+        if rc != 0:
+            raise MbeB200Error("mbe_b200_create failed (%d): %s" % (rc, self.lib.mbe_b200_last_error(None).decode()))
+        self.max_streams = int(max_streams)
+        self.device = int(device)
+
+    def close(self):
+        if self.h:
+            self.lib.mbe_b200_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise MbeB200Error("%s failed (%d): %s" % (what, rc, self.lib.mbe_b200_last_error(self.h).decode()))
+
+    @property
+    def launches(self):
+        return int(self.lib.mbe_b200_launch_count(self.h))
+
+    # ---- state ----
+    def init_streams(self, first=0, count=None, seeds=None):
+        count = self.max_streams - first if count is None else count
+        if seeds is not None:
+            seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+            assert seeds.size == count
+        self._check(self.lib.mbe_b200_init_streams(self.h, first, count, _p(seeds)), "init_streams")
+
+    def export_state(self, first=0, count=None):
+        count = self.max_streams - first if count is None else count
+        out = np.zeros((count, 3, PARMS_BYTES), np.uint8)
+        self._check(self.lib.mbe_b200_export_state(self.h, first, count, _p(out)), "export_state")
+        return out
+
+    def import_state(self, blobs, first=0):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(-1, 3, PARMS_BYTES)
+        self._check(self.lib.mbe_b200_import_state(self.h, first, blobs.shape[0], _p(blobs)), "import_state")
+
+    def export_rng(self, first=0, count=None):
+        count = self.max_streams - first if count is None else count
+        out = np.zeros((count, 4), np.uint32)
+        self._check(self.lib.mbe_b200_export_rng(self.h, first, count, _p(out)), "export_rng")
+        return out
+
+    def import_rng(self, words, first=0):
+        words = np.ascontiguousarray(words, dtype=np.uint32).reshape(-1, 4)
+        self._check(self.lib.mbe_b200_import_rng(self.h, first, words.shape[0], _p(words)), "import_rng")
+
+    # ---- hot path, host buffers ----
+    def process_frames(self, codec, frames, soft=False, first_stream=0, want_float=False, want_bits=True,
+                       want_results=True, out_pcm=None):
+        """frames: uint8 [S][F][bits] (hard) or [S][F][bits][2] (soft). Returns dict of numpy arrays."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        S, F = frames.shape[0], frames.shape[1]
+        pcm = out_pcm if out_pcm is not None else np.zeros((S, F, SAMPLES), np.int16)
+        pcmf = np.zeros((S, F, SAMPLES), np.float32) if want_float else None
+        res = np.zeros((S, F), RESULT_DTYPE) if want_results else None
+        bits = np.zeros((S, F, PARAM_BITS[codec]), np.uint8) if want_bits else None
+        self._check(self.lib.mbe_b200_process_frames(self.h, codec, int(bool(soft)), first_stream, S, F, _p(frames),
+                                                     _p(pcm), _p(pcmf), _p(res), _p(bits)), "process_frames")
+        return dict(pcm=pcm, pcmf=pcmf, results=res, bits=bits)
+
+    def process_frames_dev(self, codec, soft, first_stream, n_streams, n_frames, d_frames, d_pcm, d_pcmf=0,
+                           d_results=0, d_bits=0, cuda_stream=0):
+        """All pointers are raw device addresses (ints); asynchronous on `cuda_stream`."""
+        self._check(self.lib.mbe_b200_process_frames_dev(self.h, codec, int(bool(soft)), first_stream, n_streams,
+                                                         n_frames, _p(d_frames), _p(d_pcm or None), _p(d_pcmf or None),
+                                                         _p(d_results or None), _p(d_bits or None),
+                                                         _p(cuda_stream or None)), "process_frames_dev")
+
+    def decode_frames(self, codec, frames, soft=False):
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        n = frames.size // (FRAME_BITS[codec] * (2 if soft else 1))
+        bits = np.zeros((n, PARAM_BITS[codec]), np.uint8)
+        res = np.zeros(n, RESULT_DTYPE)
+        self._check(self.lib.mbe_b200_decode_frames(self.h, codec, int(bool(soft)), n, _p(frames), _p(bits), _p(res)),
+                    "decode_frames")
+        return bits, res
+
+    def process_data(self, codec, bits, results=None, first_stream=0, want_float=False):
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        S, F = bits.shape[0], bits.shape[1]
+        pcm = np.zeros((S, F, SAMPLES), np.int16)
+        pcmf = np.zeros((S, F, SAMPLES), np.float32) if want_float else None
+        if results is not None:
+            results = np.ascontiguousarray(results, dtype=RESULT_DTYPE).reshape(S, F).copy()
+        self._check(self.lib.mbe_b200_process_data(self.h, codec, first_stream, S, F, _p(bits), _p(results), _p(pcm),
+                                                   _p(pcmf)), "process_data")
+        return dict(pcm=pcm, pcmf=pcmf, results=results)
+
+    def synthesize_speech(self, cur, prev, seeds=None):
+        """cur/prev: uint8 [n][2604] mbe_parms blobs, updated in place. Returns (pcmf, pcm)."""
+        n = cur.shape[0]
+        assert cur.flags["C_CONTIGUOUS"] and prev.flags["C_CONTIGUOUS"] and cur.dtype == np.uint8
+        pcmf = np.zeros((n, SAMPLES), np.float32)
+        pcm = np.zeros((n, SAMPLES), np.int16)
+        if seeds is not None:
+            seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        self._check(self.lib.mbe_b200_synthesize_speech(self.h, n, _p(cur), _p(prev), _p(seeds), _p(pcmf), _p(pcm)),
+                    "synthesize_speech")
+        return pcmf, pcm
+
+    def floattoshort(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, SAMPLES)
+        out = np.zeros(x.shape, np.int16)
+        self._check(self.lib.mbe_b200_floattoshort(self.h, x.shape[0], _p(x), _p(out)), "floattoshort")
+        return out
+
+    def synchronize(self):
+        self._check(self.lib.mbe_b200_synchronize(self.h), "synchronize")

@@ -1,0 +1,45 @@
+"""Builds libmbe_b200.so (CUDA kernels + C-ABI) in-tree for sm_100a with nvcc.
+
+    python mbelib-neo_b200/build.py [--force]
+
+nvcc cross-compiles without a GPU; the resulting .so is git-ignored but travels to the GPU box."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libmbe_b200.so")
+SOURCES = ["mbe_b200.cu"]
+DEPS = ["mbe_b200.cu", "mbe_common.cuh", "mbe_frontend.cuh", "mbe_parms.cuh", "mbe_synth.cuh", "mbe_libm.cuh",
+        "mbe_tables.inc", "mbe_exp2_tab.inc", os.path.join("..", "..", "include", "mbe_b200.h")]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-fmad=false",            # the reference's float arithmetic is unfused; FMAs are spelled out where glibc has them
+    "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2",
+    "-shared",
+]
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,1390 @@
+// libmbe_b200.so - B200 (sm_100a) batched IMBE/AMBE decoder: stream kernel, per-frame state machines,
+// host-side context and the C-ABI declared in include/mbe_b200.h.
+//
+// Execution model: one warp owns one voice stream for the whole launch and walks its frames in order
+// (inter-frame prediction, oscillator phases, WOLA tail and noise generator make frames of a stream
+// strictly sequential); the three mbe_parms structs of the stream stay in shared memory between
+// frames and touch HBM once per launch.  Parallelism is streams x (harmonics | samples | codewords).
+// No tensor cores (no dense contraction in this path), no collectives (streams are independent).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "mbe_common.cuh"
+
+// ---- codec tables: device copy + host copy (host copy is only used to derive DevTables) ----------
+#define MBE_TBL __device__ const
+#include "mbe_tables.inc"
+#undef MBE_TBL
+#define MBE_EXP2_TAB_QUAL __device__ const
+#include "mbe_exp2_tab.inc"
+#define d_exp2_tab mbe_exp2_tab
+namespace hosttab {
+#define MBE_TBL static const
+#include "mbe_tables.inc"
+#undef MBE_TBL
+}  // namespace hosttab
+
+#include "mbe_frontend.cuh"
+#include "mbe_parms.cuh"
+#include "mbe_synth.cuh"
+
+namespace mbe {
+
+constexpr int WARPS_PER_BLOCK = 7;
+
+struct BlockTables {
+    float tw[256];
+};
+
+constexpr unsigned FLAG_SOFT = 0x0001u, FLAG_C0 = 0x0002u, FLAG_C4 = 0x0004u, FLAG_TONE = 0x0010u,
+                   FLAG_ERASURE = 0x0020u, FLAG_REPEAT = 0x0040u, FLAG_MUTE = 0x0080u;
+constexpr unsigned CONTEXT_FLAGS = FLAG_SOFT | FLAG_C0 | FLAG_C4;
+constexpr unsigned STATUS_FLAGS = FLAG_TONE | FLAG_ERASURE | FLAG_REPEAT | FLAG_MUTE;
+
+struct FrameCtx {
+    int total, c0, c0v, c4, c4v;
+    unsigned flags;  // context flags in, status flags accumulate
+};
+
+// src/internal/mbe_result.h:44-97
+__device__ __forceinline__ int resolve_total_errors(int c0, int prot, int c4, int total_in, unsigned flags, int* total) {
+    auto ok = [](int c) { return c >= 0 && c <= 184; };
+    if ((flags & ~(CONTEXT_FLAGS | STATUS_FLAGS)) != 0u) {
+        return -1;
+    }
+    if (!ok(c0) || !ok(prot) || !ok(c4) || !ok(total_in)) {
+        return -1;
+    }
+    if (c0 > 184 - prot) {
+        return -1;
+    }
+    const int comp = c0 + prot;
+    if (!ok(comp)) {
+        return -1;
+    }
+    const int t = (total_in == 0 && comp != 0) ? comp : total_in;
+    const bool c0v = (flags & FLAG_C0) != 0u, c4v = (flags & FLAG_C4) != 0u;
+    if (!((comp == 0 || t == comp) && (!c0v || t >= c0) && (!c4v || t >= c4))) {
+        return -1;
+    }
+    *total = t;
+    return 0;
+}
+
+// the enhance + synthesise + state hand-over sandwich shared by all voice frames
+// (imbe7200x4400.c:842-856, ambe3600x2450.c:785-799)
+__device__ __forceinline__ void voice_frame(float acc[5], WarpWS& ws, StreamRng& rng, const DevTables* T,
+                                            const float* tw, int lane) {
+    copy_parms(&ws.prev, &ws.cur, lane);
+    const float rm0 = spectral_enhance(ws.cur, lane);
+    synthesize_speech(acc, ws, rng, T, tw, 1, rm0, lane);
+    __syncwarp();
+    copy_parms(&ws.enh, &ws.cur, lane);
+}
+
+// ---- IMBE 4400 frame state machine (imbe7200x4400.c:780-888) --------------------------------------
+__device__ __forceinline__ void process_imbe(float acc[5], FrameCtx& fc, const unsigned dw[3], WarpWS& ws,
+                                             StreamRng& rng, const DevTables* T, const float* tw, int lane) {
+    Parms& cur = ws.cur;
+    Parms& prev = ws.prev;
+    const float rate = (0.95f * prev.errorRate) + (0.000365f * (float)fc.total);
+    __syncwarp();
+    if (lane == 0) {
+        cur.errorCount4 = fc.c4v ? fc.c4 : 0;
+        cur.mutingThreshold = 0.0875f;
+        cur.errorCountTotal = fc.total;
+        cur.errorRate = rate;
+    }
+    __syncwarp();
+    const int bad = decode_imbe(dw, ws, T, lane);
+    __syncwarp();
+    const float thr = 10.0f + (40.0f * rate);
+    bool repeat;
+    if (bad == 1) {
+        repeat = true;
+    } else if (fc.c0v) {
+        repeat = (fc.c0 >= 2) && ((float)fc.total >= thr);
+    } else {
+        repeat = fc.total > 5;
+    }
+    if (!repeat) {
+        if (lane == 0) {
+            cur.repeatCount = 0;
+        }
+    } else {
+        if (prev.repeatCount > 3) {
+            // headroom exhausted: default voice model, continuity state kept (imbe7200x4400.c:56-81)
+            for (int l = lane; l <= 56; l += 32) {
+                cur.Vl[l] = 0;
+                cur.Ml[l] = 1.0f;
+                cur.log2Ml[l] = 0.0f;
+            }
+            if (lane == 0) {
+                cur.swn = 0;
+                cur.tonePhase = 0;
+                cur.w0 = T->imbe_default_w0;
+                cur.L = T->imbe_default_L;
+                cur.K = 12;
+                cur.gamma = 0.0f;
+                cur.repeatCount = 0;
+                cur.localEnergy = 75000.0f;
+                cur.amplitudeThreshold = 20480;
+                cur.mutingThreshold = 0.0875f;
+            }
+        } else {
+            copy_parms(&ws.cur, &ws.prev, lane);
+            if (lane == 0) {
+                cur.repeatCount = cur.repeatCount + 1;
+            }
+        }
+        fc.flags |= FLAG_REPEAT;
+    }
+    __syncwarp();
+    const bool muted = (cur.repeatCount >= 4) || (cur.errorRate > cur.mutingThreshold);
+    voice_frame(acc, ws, rng, T, tw, lane);
+    if (muted) {
+        fc.flags |= FLAG_MUTE;
+    }
+}
+
+// ---- AMBE helpers (ambe_common.c:191-271) ----------------------------------------------------------
+__device__ __forceinline__ void init_ambe(WarpWS& ws, const DevTables* T, int lane) {
+    init_all(ws, T->ambe_default_w0, 15, 0, 0.096f, lane);
+}
+
+__device__ __forceinline__ void set_erasure_model(Parms& mp, const Parms& src, int lane) {
+    for (int l = lane; l <= 56; l += 32) {
+        mp.Ml[l] = 1.0f;
+        mp.Vl[l] = 0;
+        mp.log2Ml[l] = 0.0f;
+        mp.PHIl[l] = src.PHIl[l];
+        mp.PSIl[l] = src.PSIl[l];
+    }
+    for (int i = lane; i < 96; i += 32) {
+        mp.noiseOverlap[i] = src.noiseOverlap[i];
+    }
+    for (int i = lane; i < 256; i += 32) {
+        mp.previousUw[i] = src.previousUw[i];
+    }
+    if (lane == 0) {
+        mp.swn = 0;
+        mp.tonePhase = 0;
+        mp.w0 = 0.0f;
+        mp.L = 9;
+        mp.K = 0;
+        mp.gamma = 0.0f;
+        mp.localEnergy = 75000.0f;
+        mp.amplitudeThreshold = 20480;
+        mp.noiseSeed = src.noiseSeed;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void prepare_ambe(const FrameCtx& fc, WarpWS& ws, const DevTables* T, int lane) {
+    if (fabsf(ws.prev.mutingThreshold - 0.096f) > 1e-6f) {
+        __syncwarp();
+        init_ambe(ws, T, lane);  // first AMBE frame after a generic init
+    }
+    const float rate = (0.95f * ws.prev.errorRate) + (0.001064f * (float)fc.total);
+    __syncwarp();
+    if (lane == 0) {
+        ws.cur.mutingThreshold = 0.096f;
+        ws.cur.errorCountTotal = fc.total;
+        ws.cur.errorCount4 = 0;
+        ws.cur.errorRate = rate;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void ambe_voice_or_mute(float acc[5], FrameCtx& fc, WarpWS& ws, StreamRng& rng,
+                                                   const DevTables* T, const float* tw, int lane) {
+    if (ws.cur.repeatCount < 4) {
+        voice_frame(acc, ws, rng, T, tw, lane);
+        return;
+    }
+    fc.flags |= FLAG_MUTE;
+    comfort_noise(acc, rng, T, lane);
+    __syncwarp();
+    init_ambe(ws, T, lane);
+}
+
+__device__ __forceinline__ void ambe_repeat(WarpWS& ws, FrameCtx& fc, int lane) {
+    copy_parms(&ws.cur, &ws.prev, lane);
+    if (lane == 0) {
+        ws.cur.repeatCount = ws.cur.repeatCount + 1;
+    }
+    fc.flags |= FLAG_REPEAT;
+    __syncwarp();
+}
+
+// ---- AMBE+2 3600x2450 (ambe3600x2450.c:716-877) -----------------------------------------------------
+__device__ __forceinline__ void process_ambe2450(float acc[5], FrameCtx& fc, const unsigned dw[3], WarpWS& ws,
+                                                 StreamRng& rng, const DevTables* T, const float* tw,
+                                                 uint32_t* spill, int lane) {
+    prepare_ambe(fc, ws, T, lane);
+    const int bad = decode_ambe2450(dw, ws, T, fc.total, lane);
+    __syncwarp();
+    if (bad == 2) {
+        fc.flags |= FLAG_ERASURE;
+        if (lane == 0) {
+            ws.cur.repeatCount = 0;
+        }
+        set_erasure_model(ws.cur, ws.prev, lane);
+    } else if (bad == 7) {
+        fc.flags |= FLAG_TONE;
+        if (lane == 0) {
+            ws.cur.repeatCount = 0;
+        }
+    } else {
+        const bool repeat = fc.c0v ? ((fc.c0 >= 4) || ((fc.c0 >= 2) && (fc.total >= 6))) : (fc.total > 3);
+        if (repeat) {
+            ambe_repeat(ws, fc, lane);
+        } else if (lane == 0) {
+            ws.cur.repeatCount = 0;
+        }
+    }
+    __syncwarp();
+
+    if (bad == 0) {
+        ambe_voice_or_mute(acc, fc, ws, rng, T, tw, lane);
+    } else if (bad == 7) {
+        unsigned u0 = 0, u1 = 0, u3 = 0;
+        for (int i = 0; i < 12; ++i) {
+            u0 = (u0 << 1) | getbit(dw, i);
+        }
+        for (int i = 12; i < 24; ++i) {
+            u1 = (u1 << 1) | getbit(dw, i);
+        }
+        for (int i = 35; i < 49; ++i) {
+            u3 = (u3 << 1) | getbit(dw, i);
+        }
+        const int id1 = (int)((u1 & 0xfffu) >> 4);
+        float f1, f2;
+        if (tone_freqs(id1, &f1, &f2)) {
+            const int AD = (int)(((u0 & 0x3fu) << 1) + ((u3 >> 4) & 1u));
+            render_tone(acc, ws.cur, f1, f2, AD, lane);
+        } else if (!(ws.prev.repeatCount >= 4)) {
+            // invalid tone id: replay the last voice model while advancing synthesis state
+            // (ambe3600x2450.c:808-816).  ws.cur is parked in the stream's HBM slot meanwhile.
+            uint32_t* cw = reinterpret_cast<uint32_t*>(&ws.cur);
+            for (int i = lane; i < PARMS_WORDS; i += 32) {
+                spill[i] = cw[i];
+            }
+            __syncwarp();
+            copy_parms(&ws.cur, &ws.enh, lane);
+            synthesize_speech(acc, ws, rng, T, tw, 0, 0.0f, lane);
+            __syncwarp();
+            copy_parms(&ws.enh, &ws.cur, lane);
+            for (int i = lane; i < PARMS_WORDS; i += 32) {
+                cw[i] = spill[i];
+            }
+            __syncwarp();
+        } else {
+            comfort_noise(acc, rng, T, lane);
+            __syncwarp();
+            init_ambe(ws, T, lane);
+        }
+    } else if (bad == 2) {
+        comfort_noise(acc, rng, T, lane);
+        __syncwarp();
+        copy_parms(&ws.prev, &ws.cur, lane);
+        copy_parms(&ws.enh, &ws.cur, lane);
+    } else {
+        comfort_noise(acc, rng, T, lane);
+        __syncwarp();
+        init_ambe(ws, T, lane);
+    }
+}
+
+// ---- AMBE 3600x2400 (ambe3600x2400.c:629-762) --------------------------------------------------------
+__device__ __forceinline__ void process_ambe2400(float acc[5], FrameCtx& fc, const unsigned dw[3], WarpWS& ws,
+                                                 StreamRng& rng, const DevTables* T, const float* tw, int lane) {
+    prepare_ambe(fc, ws, T, lane);
+    const int bad = decode_ambe2400(dw, ws, T, lane);
+    __syncwarp();
+    const bool clean_tone = (bad >= 7) && (bad <= 122) && (fc.c0 < 2) && (fc.total < 3);
+    if (bad == 3) {
+        fc.flags |= FLAG_TONE;
+        if (lane == 0) {
+            ws.cur.repeatCount = 0;
+        }
+    } else if (clean_tone) {
+        // state untouched
+    } else if (fc.total > 3) {
+        ambe_repeat(ws, fc, lane);
+    } else if (lane == 0) {
+        ws.cur.repeatCount = 0;
+    }
+    __syncwarp();
+
+    if (clean_tone) {
+        float f1 = 0.0f;
+        if (bad >= 7 && bad <= 122) {
+            f1 = 31.25f * (float)bad;
+        }
+        render_tone(acc, ws.cur, f1, f1, 103, lane);
+        copy_parms(&ws.prev, &ws.cur, lane);
+    } else if (bad == 0) {
+        ambe_voice_or_mute(acc, fc, ws, rng, T, tw, lane);
+    } else {
+        comfort_noise(acc, rng, T, lane);
+        __syncwarp();
+        init_ambe(ws, T, lane);
+    }
+}
+
+// =====================================================================================================
+// The stream kernel
+// =====================================================================================================
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) mbe_stream_kernel(const LaunchArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BlockTables* bt = reinterpret_cast<BlockTables*>(smem_raw);
+    WarpWS* wsa = reinterpret_cast<WarpWS*>(smem_raw + sizeof(BlockTables));
+    const DevTables* T = A.tab;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        bt->tw[i] = T->tw[i];
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (s >= A.n_streams) {
+        return;
+    }
+    WarpWS& ws = wsa[warp];
+    const float* tw = bt->tw;
+    StreamRng rng;
+    uint32_t* gs = nullptr;
+    uint32_t* wsw = reinterpret_cast<uint32_t*>(&ws);  // cur, prev, enh are the first 3*651 words
+
+    if (A.mode == MODE_SYNTH) {
+        const uint32_t* gc = A.synth_cur + (size_t)s * PARMS_WORDS;
+        const uint32_t* gp = A.synth_prev + (size_t)s * PARMS_WORDS;
+        uint32_t* c = reinterpret_cast<uint32_t*>(&ws.cur);
+        uint32_t* e = reinterpret_cast<uint32_t*>(&ws.enh);
+        for (int i = lane; i < PARMS_WORDS; i += 32) {
+            c[i] = gc[i];
+            e[i] = gp[i];
+        }
+        // RNG as after mbe_setThreadRngSeed(seed) (mbelib.c:173-181); no seeds: fresh-thread defaults
+        if (A.synth_seeds) {
+            unsigned seed = A.synth_seeds[s];
+            if (seed == 0u) {
+                seed = 0x6d25357bu;
+            }
+            rng.comfort = (((unsigned long long)seed) ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1ULL);
+            rng.uv_seed = seed % 53125u;
+            rng.uv_override = 1;
+        } else {
+            rng.comfort = (0x12345678ULL ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1ULL);
+            rng.uv_seed = 3147u;
+            rng.uv_override = 0;
+        }
+        __syncwarp();
+        float acc[5];
+        synthesize_speech(acc, ws, rng, T, tw, 0, 0.0f, lane);
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < 5; ++ch) {
+            const size_t o = (size_t)s * NS + 32 * ch + lane;
+            if (A.pcmf) {
+                A.pcmf[o] = acc[ch];
+            }
+            if (A.pcm) {
+                A.pcm[o] = float_to_short(acc[ch]);
+            }
+        }
+        uint32_t* oc = A.synth_cur + (size_t)s * PARMS_WORDS;
+        uint32_t* op = A.synth_prev + (size_t)s * PARMS_WORDS;
+        for (int i = lane; i < PARMS_WORDS; i += 32) {
+            oc[i] = c[i];
+            op[i] = e[i];
+        }
+        return;
+    }
+
+    const int stream = A.first_stream + s;
+    gs = A.state + (size_t)stream * STATE_WORDS;
+    for (int i = lane; i < 3 * PARMS_WORDS; i += 32) {
+        wsw[i] = gs[i];
+    }
+    rng.comfort = (unsigned long long)gs[3 * PARMS_WORDS] | ((unsigned long long)gs[3 * PARMS_WORDS + 1] << 32);
+    rng.uv_seed = gs[3 * PARMS_WORDS + 2];
+    rng.uv_override = gs[3 * PARMS_WORDS + 3];
+    __syncwarp();
+
+    const int codec = A.codec;
+    const int fbits = (codec == MBE_B200_IMBE7200X4400) ? 184 : (codec == MBE_B200_IMBE7100X4400 ? 168 : 96);
+    const int pbits = (codec <= MBE_B200_IMBE7100X4400) ? 88 : 49;
+    const size_t fstride = (A.mode == MODE_DATA) ? (size_t)pbits : (size_t)fbits * (A.soft ? 2u : 1u);
+
+    for (int f = 0; f < A.n_frames; ++f) {
+        const size_t idx = (size_t)s * A.n_frames + f;
+        const uint8_t* fr = A.frames + idx * fstride;
+        unsigned dw[3];
+        FrameCtx fc;
+        int status;
+        mbe_b200_result rout;
+        rout.c0_errors = rout.protected_errors = rout.c4_errors = rout.total_errors = 0;
+        rout.flags = 0;
+
+        if (A.mode == MODE_FRAMES) {
+            FrontResult R = front_end(codec, A.soft, fr, dw, ws.rel, reinterpret_cast<unsigned short*>(ws.u.tile),
+                                      ws.rowbits, T, lane);
+            status = R.status;
+            fc.total = R.c0 + R.prot;
+            fc.c0 = R.c0;
+            fc.c0v = 1;
+            fc.c4 = R.c4;
+            fc.c4v = (R.flags & FLAG_C4) ? 1 : 0;
+            fc.flags = R.flags;
+        } else {
+            // parameter bits from memory + optional decode context (mbe_process<Codec>Data semantics)
+            bool bad = false;
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                const int i = 32 * w + lane;
+                unsigned b = 0;
+                if (i < pbits) {
+                    const unsigned v = fr[i];
+                    bad |= (v > 1u);
+                    b = v & 1u;
+                }
+                dw[w] = __ballot_sync(FULL, b);
+            }
+            int c0 = 0, prot = 0, c4 = 0, tin = 0;
+            unsigned fl = 0;
+            if (A.results) {
+                const mbe_b200_result rin = A.results[idx];
+                c0 = rin.c0_errors;
+                prot = rin.protected_errors;
+                c4 = rin.c4_errors;
+                tin = rin.total_errors;
+                fl = rin.flags;
+                rout = rin;
+            }
+            int total = 0;
+            status = resolve_total_errors(c0, prot, c4, tin, fl, &total);
+            if (status == 0 && __any_sync(FULL, bad)) {
+                status = -2;
+            }
+            fc.flags = fl & CONTEXT_FLAGS;
+            fc.c0v = (fl & FLAG_C0) ? 1 : 0;
+            fc.c4v = (fl & FLAG_C4) ? 1 : 0;
+            fc.c0 = fc.c0v ? c0 : 0;
+            fc.c4 = fc.c4v ? c4 : 0;
+            fc.total = total;
+        }
+
+        float acc[5];
+#pragma unroll
+        for (int ch = 0; ch < 5; ++ch) {
+            acc[ch] = 0.0f;
+        }
+        if (status >= 0) {
+            if (codec <= MBE_B200_IMBE7100X4400) {
+                process_imbe(acc, fc, dw, ws, rng, T, tw, lane);
+            } else if (codec == MBE_B200_AMBE3600X2400) {
+                process_ambe2400(acc, fc, dw, ws, rng, T, tw, lane);
+            } else {
+                process_ambe2450(acc, fc, dw, ws, rng, T, tw, gs, lane);
+            }
+            status = fc.total;
+            rout.c0_errors = fc.c0;
+            rout.c4_errors = fc.c4;
+            rout.total_errors = fc.total;
+            rout.protected_errors = fc.total - fc.c0;
+            rout.flags = fc.flags;
+        }
+        __syncwarp();
+
+#pragma unroll
+        for (int ch = 0; ch < 5; ++ch) {
+            const size_t o = idx * NS + 32 * ch + lane;
+            if (A.pcmf) {
+                A.pcmf[o] = acc[ch];
+            }
+            if (A.pcm) {
+                A.pcm[o] = float_to_short(acc[ch]);
+            }
+        }
+        if (A.results && lane == 0) {
+            rout.status = status;
+            A.results[idx] = rout;
+        }
+        if (A.bits && A.mode == MODE_FRAMES) {
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                const int i = 32 * w + lane;
+                if (i < pbits) {
+                    A.bits[idx * pbits + i] = (uint8_t)((dw[w] >> lane) & 1u);
+                }
+            }
+        }
+    }
+
+    __syncwarp();
+    for (int i = lane; i < 3 * PARMS_WORDS; i += 32) {
+        gs[i] = wsw[i];
+    }
+    if (lane == 0) {
+        gs[3 * PARMS_WORDS] = (uint32_t)(rng.comfort & 0xffffffffULL);
+        gs[3 * PARMS_WORDS + 1] = (uint32_t)(rng.comfort >> 32);
+        gs[3 * PARMS_WORDS + 2] = rng.uv_seed;
+        gs[3 * PARMS_WORDS + 3] = rng.uv_override;
+    }
+}
+
+// stateless ECC-only kernel: one warp per frame (batched mbe_decode<Codec>[Soft]Frame)
+__global__ void __launch_bounds__(256) mbe_decode_kernel(int codec, int soft, int n, const uint8_t* __restrict__ frames,
+                                                         uint8_t* __restrict__ bits, mbe_b200_result* __restrict__ results,
+                                                         const DevTables* T) {
+    __shared__ unsigned char rel[8][8 * 24];
+    __shared__ unsigned short cost[8][640];
+    __shared__ unsigned rows[8][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= n) {
+        return;
+    }
+    const int fbits = (codec == MBE_B200_IMBE7200X4400) ? 184 : (codec == MBE_B200_IMBE7100X4400 ? 168 : 96);
+    const int pbits = (codec <= MBE_B200_IMBE7100X4400) ? 88 : 49;
+    unsigned dw[3];
+    FrontResult R = front_end(codec, soft, frames + (size_t)i * fbits * (soft ? 2 : 1), dw, rel[warp], cost[warp],
+                              rows[warp], T, lane);
+    if (bits && R.status >= 0) {
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            const int b = 32 * w + lane;
+            if (b < pbits) {
+                bits[(size_t)i * pbits + b] = (uint8_t)((dw[w] >> lane) & 1u);
+            }
+        }
+    }
+    if (results && lane == 0) {
+        mbe_b200_result r;
+        r.status = R.status;
+        r.c0_errors = R.c0;
+        r.protected_errors = R.prot;
+        r.c4_errors = R.c4;
+        r.total_errors = R.status >= 0 ? R.c0 + R.prot : 0;
+        r.flags = R.flags;
+        results[i] = r;
+    }
+}
+
+__global__ void mbe_floattoshort_kernel(size_t n, const float* __restrict__ in, int16_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        out[i] = float_to_short(in[i]);
+    }
+}
+
+// per stream: mbe_setThreadRngSeed(seed) + mbe_initMbeParms (mbelib.c:173-181,367-410)
+__global__ void mbe_init_streams_kernel(uint32_t* state, int first, int count, const uint32_t* seeds, float w0, int L) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= count) {
+        return;
+    }
+    uint32_t* gs = state + (size_t)(first + warp) * STATE_WORDS;
+    Parms* p = reinterpret_cast<Parms*>(gs);
+    for (int k = 0; k < 3; ++k) {
+        fill_default(p + k, w0, L, 12, 0.0875f, lane);
+    }
+    if (lane == 0) {
+        unsigned long long comfort;
+        unsigned uvs, ovr;
+        if (seeds) {
+            unsigned seed = seeds[warp];
+            if (seed == 0u) {
+                seed = 0x6d25357bu;
+            }
+            comfort = (((unsigned long long)seed) ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1ULL);
+            uvs = seed % 53125u;
+            ovr = 1;
+        } else {
+            comfort = (0x12345678ULL ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1ULL);
+            uvs = 3147u;
+            ovr = 0;
+        }
+        gs[3 * PARMS_WORDS] = (uint32_t)(comfort & 0xffffffffULL);
+        gs[3 * PARMS_WORDS + 1] = (uint32_t)(comfort >> 32);
+        gs[3 * PARMS_WORDS + 2] = uvs;
+        gs[3 * PARMS_WORDS + 3] = ovr;
+    }
+}
+
+// gather/scatter between the interleaved HBM state pool and dense [count][3][651] / [count][4] buffers
+__global__ void mbe_state_xfer_kernel(uint32_t* state, int first, int count, uint32_t* dense, int words, int offset,
+                                      int to_dense) {
+    const size_t total = (size_t)count * words;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t s = i / words, w = i % words;
+        uint32_t* g = state + (size_t)(first + s) * STATE_WORDS + offset + w;
+        if (to_dense) {
+            dense[i] = *g;
+        } else {
+            *g = dense[i];
+        }
+    }
+}
+
+}  // namespace mbe
+
+// =====================================================================================================
+// Host side
+// =====================================================================================================
+using namespace mbe;
+
+struct mbe_b200_ctx {
+    int device;
+    int max_streams;
+    uint32_t* d_state;
+    DevTables* d_tab;
+    cudaStream_t stream;
+    // staging for the host-pointer entry points (grown on demand)
+    void* d_in;
+    size_t d_in_cap;
+    void* d_out[4];
+    size_t d_out_cap[4];
+    long long launches;
+    float imbe_default_w0;
+    int imbe_default_L;
+    char err[256];
+};
+
+static char g_create_err[256] = "";
+
+static int fail(mbe_b200_ctx* ctx, int code, const char* what, cudaError_t ce) {
+    char* dst = ctx ? ctx->err : g_create_err;
+    if (ce != cudaSuccess) {
+        snprintf(dst, 256, "%s: %s", what, cudaGetErrorString(ce));
+    } else {
+        snprintf(dst, 256, "%s", what);
+    }
+    return code;
+}
+
+#define CU(call)                                                 \
+    do {                                                         \
+        cudaError_t _e = (call);                                 \
+        if (_e != cudaSuccess) {                                 \
+            return fail(ctx, MBE_B200_E_CUDA, #call, _e);        \
+        }                                                        \
+    } while (0)
+
+static void build_tables(DevTables* t) {
+    memset(t, 0, sizeof(*t));
+    // DCT cosine tables.  The reference's Release build (gcc -O3) constant-folds the 6x6 gain table, so
+    // those entries are correctly rounded cosines ((float)cos((double)x) reproduces all 36); the 8x8 and
+    // per-block tables come from glibc's cosf at run time (imbe7200x4400.c:97-111, ambe3600x2450.c:60-74).
+    for (int m = 1; m <= 6; ++m) {
+        for (int i = 1; i <= 6; ++i) {
+            float arg = (M_PI * (float)(m - 1) * ((float)i - 0.5f)) / 6.0f;
+            t->ri6[(m - 1) * 6 + (i - 1)] = (float)cos((double)arg);
+        }
+    }
+    for (int m = 1; m <= 8; ++m) {
+        for (int i = 1; i <= 8; ++i) {
+            t->ri8[(m - 1) * 8 + (i - 1)] = cosf((M_PI * (float)(m - 1) * ((float)i - 0.5f)) / 8.0f);
+        }
+    }
+    int off = 0;
+    for (int ji = 1; ji <= 17; ++ji) {
+        t->blk_off[ji] = off;
+        for (int j = 1; j <= ji; ++j) {
+            for (int k = 1; k <= ji; ++k) {
+                t->blk[off + (j - 1) * ji + (k - 1)] = cosf((M_PI * (float)(k - 1) * ((float)j - 0.5f)) / (float)ji);
+            }
+        }
+        off += ji * ji;
+    }
+    // FFTPACK twiddles, N = 256, factors 4x4x4x4 (pffft.c:1231-1262)
+    {
+        const int n = 256;
+        float argh = (2 * M_PI) / n;
+        int is = 0, l1 = 1;
+        for (int pass = 1; pass <= 3; ++pass) {
+            int l2 = l1 * 4, ido = n / l2, ld = 0;
+            for (int j = 1; j <= 3; ++j) {
+                int i = is, fi = 0;
+                ld += l1;
+                float argld = ld * argh;
+                for (int ii = 3; ii <= ido; ii += 2) {
+                    i += 2;
+                    fi += 1;
+                    // C semantics: double cos/sin of the float product (C++ would pick the float overload)
+                    t->tw[i - 2] = (float)cos((double)(fi * argld));
+                    t->tw[i - 1] = (float)sin((double)(fi * argld));
+                }
+                is += ido;
+            }
+            l1 = l2;
+        }
+    }
+    // b0 -> (w0, L, K)  (imbe7200x4400.c:117-154, imbe7100x4400.c:392-402)
+    for (int b0 = 0; b0 < 256; ++b0) {
+        float w0 = ((float)(4 * M_PI) / (float)((float)b0 + 39.5));
+        int L = (int)(0.9254 * (int)((M_PI / w0) + 0.25));
+        int K = (L < 37) ? (int)((float)(L + 2) / (float)3) : 12;
+        t->imbe_w0[b0] = w0;
+        t->imbe_K[b0] = (unsigned char)K;
+        t->imbe_Kv[b0] = (unsigned char)K;
+        t->imbe_L[b0] = (b0 <= 207 && L >= 9 && L <= 56) ? (unsigned char)L : 0;
+    }
+    for (int b0 = 0; b0 < 120; ++b0) {
+        t->a2450_w0[b0] = hosttab::t_a2450_f0[b0] * (float)2 * M_PI;
+    }
+    t->a2450_f0_silence = (float)M_PI / 32.0f;
+    t->a2450_w0_silence = t->a2450_f0_silence * (float)(2.0 * M_PI);
+    for (int b0 = 0; b0 < 126; ++b0) {
+        float f0 = exp2f(-4.311767578125f - (2.1336e-2f * ((float)b0 + 0.5f)));
+        t->a2400_f0[b0] = f0;
+        t->a2400_w0[b0] = f0 * (float)2 * M_PI;
+    }
+    t->a2400_w0_silence = ((float)2 * M_PI) / (float)32;
+    t->imbe_default_w0 = (float)((4.0 * M_PI) / (134.0 + 39.5));
+    t->imbe_default_L = (int)(0.9254 * (int)((M_PI / t->imbe_default_w0) + 0.25));
+    t->ambe_default_w0 = (float)((M_PI / 32.0) * (2.0 * M_PI));
+    for (int L = 1; L <= 56; ++L) {
+        t->log2_int[L] = log2f((float)L);
+    }
+    t->ambe_rconst = ((float)1 / ((float)2 * M_SQRT2));
+    // LCG jump-ahead coefficients
+    {
+        unsigned a = 1, c = 0;
+        for (int k = 0; k < 116; ++k) {
+            t->pnA[k] = (unsigned short)a;
+            t->pnC[k] = (unsigned short)c;
+            c = (173u * c + 13849u) & 0xffffu;
+            a = (173u * a) & 0xffffu;
+        }
+    }
+    {
+        unsigned long long a = 1, c = 0;
+        for (int k = 0; k <= 160; ++k) {
+            t->uvA[k] = (unsigned)a;
+            t->uvC[k] = (unsigned)c;
+            c = (171ull * c + 11213ull) % 53125ull;
+            a = (171ull * a) % 53125ull;
+        }
+    }
+    {
+        const unsigned long long M = (1ULL << 48) - 1ULL, MUL = 0x5DEECE66DULL, ADD = 0xBULL;
+        unsigned long long a = 1, c = 0;
+        for (int k = 0; k <= 160; ++k) {
+            t->cnA[k] = a;
+            t->cnC[k] = c;
+            c = (MUL * c + ADD) & M;
+            a = (MUL * a) & M;
+        }
+    }
+    // Golay(23,12)
+    for (int v = 0; v < 64; ++v) {
+        unsigned hi = 0, lo = 0;
+        for (int i = 0; i < 6; ++i) {
+            if (v & (0x20 >> i)) {
+                hi ^= hosttab::t_golay_gen[i];      // data bits 11..6
+                lo ^= hosttab::t_golay_gen[6 + i];  // data bits 5..0
+            }
+        }
+        t->golay_par_hi[v] = (unsigned short)hi;
+        t->golay_par_lo[v] = (unsigned short)lo;
+    }
+    for (unsigned d = 0; d < 4096; ++d) {
+        t->golay_cw[d] = (d << 11) | (unsigned)(t->golay_par_hi[d >> 6] ^ t->golay_par_lo[d & 63]);
+    }
+    memcpy(t->golay_fix, hosttab::t_golay_fix, sizeof(t->golay_fix));
+    // Hamming(15,11), standard and IMBE-7100 layouts (ecc_const.c:17-19, ecc.c:133-136)
+    {
+        const unsigned short rows[2][4] = {{0x7f08, 0x78e4, 0x66d2, 0x55b1}, {0x7ac8, 0x3d64, 0x1eb2, 0x7591}};
+        const int dpos[2][11] = {{2, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14}, {4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14}};
+        const int ppos[2][4] = {{0, 1, 3, 7}, {0, 1, 2, 3}};
+        for (int v = 0; v < 2; ++v) {
+            for (int i = 0; i < 4; ++i) {
+                t->ham_rows[v][i] = rows[v][i];
+            }
+            for (int syn = 0; syn < 16; ++syn) {
+                unsigned flip = 0;
+                for (int b = 0; b < 15 && !flip && syn; ++b) {
+                    int col = 0;
+                    for (int i = 0; i < 4; ++i) {
+                        col |= ((rows[v][i] >> b) & 1) << i;
+                    }
+                    if (col == syn) {
+                        flip = 1u << b;
+                    }
+                }
+                t->ham_flip[v][syn] = (unsigned short)flip;
+            }
+            for (unsigned d = 0; d < 2048; ++d) {
+                unsigned cw = 0;
+                for (int i = 0; i < 11; ++i) {
+                    cw |= ((d >> i) & 1u) << dpos[v][i];
+                }
+                int found = 0;
+                for (int p = 0; p < 16 && !found; ++p) {
+                    unsigned c = cw;
+                    for (int i = 0; i < 4; ++i) {
+                        c |= (unsigned)((p >> i) & 1) << ppos[v][i];
+                    }
+                    int syn = 0;
+                    for (int i = 0; i < 4; ++i) {
+                        syn |= (__builtin_popcount(c & rows[v][i]) & 1) << i;
+                    }
+                    if (syn == 0) {
+                        cw = c;
+                        found = 1;
+                    }
+                }
+                t->ham_cw[v][d] = (unsigned short)cw;
+            }
+        }
+    }
+    // windows (mbe_unvoiced_fft.c:159-176)
+    for (int i = 0; i < 256; ++i) {
+        int n = i - 128;
+        t->uvwin[i] = (n >= -105 && n <= 105) ? hosttab::t_win_unvoiced[n + 105] : 0.0f;
+    }
+    for (int n = 0; n < 160; ++n) {
+        float wp = (n <= 105) ? hosttab::t_win_unvoiced[n + 105] : 0.0f;
+        int m = n - 160;
+        float wc = (m >= -105) ? hosttab::t_win_unvoiced[m + 105] : 0.0f;
+        t->wola_wp[n] = wp;
+        t->wola_wc[n] = wc;
+        float wp2 = wp * wp, wc2 = wc * wc;
+        t->wola_den[n] = wp2 + wc2;
+    }
+    for (int i = 0; i < 321; ++i) {
+        t->voiced_win[i] = hosttab::t_win_voiced[i];
+    }
+}
+
+static size_t stream_kernel_smem(void) { return sizeof(BlockTables) + (size_t)WARPS_PER_BLOCK * sizeof(WarpWS); }
+
+extern "C" {
+
+const char* mbe_b200_version(void) { return "mbe_b200 0.1.0 (sm_100a)"; }
+
+const char* mbe_b200_last_error(const mbe_b200_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+long long mbe_b200_launch_count(const mbe_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mbe_b200_geometry(int codec, int* frame_bits, int* param_bits) {
+    if (codec < 0 || codec > 3) {
+        return MBE_B200_E_ARG;
+    }
+    if (frame_bits) {
+        *frame_bits = codec == 0 ? 184 : (codec == 1 ? 168 : 96);
+    }
+    if (param_bits) {
+        *param_bits = codec <= 1 ? 88 : 49;
+    }
+    return 0;
+}
+
+int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams) {
+    mbe_b200_ctx* ctx = nullptr;
+    if (!out || max_streams < 1) {
+        return fail(nullptr, MBE_B200_E_ARG, "mbe_b200_create: bad argument", cudaSuccess);
+    }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0) {
+        return fail(nullptr, MBE_B200_E_NOGPU, "mbe_b200_create: no CUDA device (this library has no CPU path)", ce);
+    }
+    if (device_ordinal < 0 || device_ordinal >= ndev) {
+        return fail(nullptr, MBE_B200_E_ARG, "mbe_b200_create: device ordinal out of range", cudaSuccess);
+    }
+    ctx = (mbe_b200_ctx*)calloc(1, sizeof(*ctx));
+    if (!ctx) {
+        return fail(nullptr, MBE_B200_E_ARG, "mbe_b200_create: out of host memory", cudaSuccess);
+    }
+    ctx->device = device_ordinal;
+    ctx->max_streams = max_streams;
+    DevTables* ht = (DevTables*)malloc(sizeof(DevTables));
+    build_tables(ht);
+    ctx->imbe_default_w0 = ht->imbe_default_w0;
+    ctx->imbe_default_L = ht->imbe_default_L;
+#define CUC(call)                                                                  \
+    do {                                                                           \
+        cudaError_t _e = (call);                                                   \
+        if (_e != cudaSuccess) {                                                   \
+            fail(nullptr, MBE_B200_E_CUDA, #call, _e);                             \
+            free(ht);                                                              \
+            mbe_b200_destroy(ctx);                                                 \
+            return MBE_B200_E_CUDA;                                                \
+        }                                                                          \
+    } while (0)
+    CUC(cudaSetDevice(device_ordinal));
+    CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUC(cudaMalloc(&ctx->d_tab, sizeof(DevTables)));
+    CUC(cudaMemcpy(ctx->d_tab, ht, sizeof(DevTables), cudaMemcpyHostToDevice));
+    CUC(cudaMalloc(&ctx->d_state, (size_t)max_streams * STATE_WORDS * sizeof(uint32_t)));
+    CUC(cudaFuncSetAttribute(mbe_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_kernel_smem()));
+#undef CUC
+    free(ht);
+    *out = ctx;
+    int rc = mbe_b200_init_streams(ctx, 0, max_streams, nullptr);
+    if (rc < 0) {
+        snprintf(g_create_err, sizeof(g_create_err), "%s", ctx->err);
+        mbe_b200_destroy(ctx);
+        *out = nullptr;
+        return rc;
+    }
+    return 0;
+}
+
+void mbe_b200_destroy(mbe_b200_ctx* ctx) {
+    if (!ctx) {
+        return;
+    }
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    cudaFree(ctx->d_state);
+    cudaFree(ctx->d_tab);
+    cudaFree(ctx->d_in);
+    for (int i = 0; i < 4; ++i) {
+        cudaFree(ctx->d_out[i]);
+    }
+    free(ctx);
+}
+
+int mbe_b200_synchronize(mbe_b200_ctx* ctx) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int check_range(mbe_b200_ctx* ctx, int first, int count) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    if (first < 0 || count < 0 || first > ctx->max_streams - count) {
+        return fail(ctx, MBE_B200_E_ARG, "stream range outside the context's pool", cudaSuccess);
+    }
+    return 0;
+}
+
+int mbe_b200_init_streams(mbe_b200_ctx* ctx, int first, int count, const uint32_t* seeds) {
+    int rc = check_range(ctx, first, count);
+    if (rc < 0 || count == 0) {
+        return rc;
+    }
+    CU(cudaSetDevice(ctx->device));
+    uint32_t* d_seeds = nullptr;
+    if (seeds) {
+        CU(cudaMalloc(&d_seeds, (size_t)count * sizeof(uint32_t)));
+        CU(cudaMemcpyAsync(d_seeds, seeds, (size_t)count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int threads = 256, wpb = threads / 32;
+    mbe_init_streams_kernel<<<(count + wpb - 1) / wpb, threads, 0, ctx->stream>>>(ctx->d_state, first, count, d_seeds,
+                                                                                    ctx->imbe_default_w0,
+                                                                                    ctx->imbe_default_L);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (d_seeds) {
+        cudaFree(d_seeds);
+    }
+    return 0;
+}
+
+static int state_xfer(mbe_b200_ctx* ctx, int first, int count, void* host, int words, int offset, int to_host) {
+    int rc = check_range(ctx, first, count);
+    if (rc < 0 || count == 0) {
+        return rc;
+    }
+    if (!host) {
+        return fail(ctx, MBE_B200_E_ARG, "NULL host buffer", cudaSuccess);
+    }
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)count * words * sizeof(uint32_t);
+    uint32_t* dense = nullptr;
+    CU(cudaMalloc(&dense, bytes));
+    if (!to_host) {
+        CU(cudaMemcpyAsync(dense, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    mbe_state_xfer_kernel<<<1024, 256, 0, ctx->stream>>>(ctx->d_state, first, count, dense, words, offset, to_host);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (to_host) {
+        CU(cudaMemcpyAsync(host, dense, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dense);
+    return 0;
+}
+
+int mbe_b200_export_state(mbe_b200_ctx* ctx, int first, int count, void* parms_triplets) {
+    return state_xfer(ctx, first, count, parms_triplets, 3 * PARMS_WORDS, 0, 1);
+}
+int mbe_b200_import_state(mbe_b200_ctx* ctx, int first, int count, const void* parms_triplets) {
+    return state_xfer(ctx, first, count, const_cast<void*>(parms_triplets), 3 * PARMS_WORDS, 0, 0);
+}
+int mbe_b200_export_rng(mbe_b200_ctx* ctx, int first, int count, uint32_t* rng_words4) {
+    return state_xfer(ctx, first, count, rng_words4, RNG_WORDS, 3 * PARMS_WORDS, 1);
+}
+int mbe_b200_import_rng(mbe_b200_ctx* ctx, int first, int count, const uint32_t* rng_words4) {
+    return state_xfer(ctx, first, count, const_cast<uint32_t*>(rng_words4), RNG_WORDS, 3 * PARMS_WORDS, 0);
+}
+
+static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a, cudaStream_t st) {
+    const int blocks = (a.n_streams + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    mbe_stream_kernel<<<blocks, WARPS_PER_BLOCK * 32, stream_kernel_smem(), st>>>(a);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbe_b200_process_frames_dev(mbe_b200_ctx* ctx, int codec, int soft, int first_stream, int n_streams, int n_frames,
+                                const uint8_t* d_frames, int16_t* d_pcm, float* d_pcmf, mbe_b200_result* d_results,
+                                uint8_t* d_bits, void* cuda_stream) {
+    int rc = check_range(ctx, first_stream, n_streams);
+    if (rc < 0) {
+        return rc;
+    }
+    if (codec < 0 || codec > 3 || n_frames < 0 || !d_frames) {
+        return fail(ctx, MBE_B200_E_ARG, "process_frames: bad argument", cudaSuccess);
+    }
+    if (n_streams == 0 || n_frames == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    LaunchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.codec = codec;
+    a.soft = soft ? 1 : 0;
+    a.mode = MODE_FRAMES;
+    a.first_stream = first_stream;
+    a.n_streams = n_streams;
+    a.n_frames = n_frames;
+    a.frames = d_frames;
+    a.pcm = d_pcm;
+    a.pcmf = d_pcmf;
+    a.results = d_results;
+    a.bits = d_bits;
+    a.state = ctx->d_state;
+    a.tab = ctx->d_tab;
+    return launch_stream_kernel(ctx, a, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream);
+}
+
+int mbe_b200_process_data_dev(mbe_b200_ctx* ctx, int codec, int first_stream, int n_streams, int n_frames,
+                              const uint8_t* d_bits, mbe_b200_result* d_results_inout, int16_t* d_pcm, float* d_pcmf,
+                              void* cuda_stream) {
+    int rc = check_range(ctx, first_stream, n_streams);
+    if (rc < 0) {
+        return rc;
+    }
+    if (codec < 0 || codec > 3 || n_frames < 0 || !d_bits) {
+        return fail(ctx, MBE_B200_E_ARG, "process_data: bad argument", cudaSuccess);
+    }
+    if (n_streams == 0 || n_frames == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    LaunchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.codec = codec;
+    a.mode = MODE_DATA;
+    a.first_stream = first_stream;
+    a.n_streams = n_streams;
+    a.n_frames = n_frames;
+    a.frames = d_bits;
+    a.pcm = d_pcm;
+    a.pcmf = d_pcmf;
+    a.results = d_results_inout;
+    a.state = ctx->d_state;
+    a.tab = ctx->d_tab;
+    return launch_stream_kernel(ctx, a, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream);
+}
+
+int mbe_b200_decode_frames_dev(mbe_b200_ctx* ctx, int codec, int soft, int n, const uint8_t* d_frames, uint8_t* d_bits,
+                               mbe_b200_result* d_results, void* cuda_stream) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    if (codec < 0 || codec > 3 || n < 0 || !d_frames) {
+        return fail(ctx, MBE_B200_E_ARG, "decode_frames: bad argument", cudaSuccess);
+    }
+    if (n == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    mbe_decode_kernel<<<(n + 7) / 8, 256, 0, st>>>(codec, soft ? 1 : 0, n, d_frames, d_bits, d_results, ctx->d_tab);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbe_b200_floattoshort_dev(mbe_b200_ctx* ctx, int n_frames, const float* d_in, int16_t* d_out, void* cuda_stream) {
+    if (!ctx || n_frames < 0 || !d_in || !d_out) {
+        return ctx ? fail(ctx, MBE_B200_E_ARG, "floattoshort: bad argument", cudaSuccess) : MBE_B200_E_ARG;
+    }
+    if (n_frames == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const size_t n = (size_t)n_frames * NS;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) {
+        blocks = 148 * 16;
+    }
+    mbe_floattoshort_kernel<<<blocks, 256, 0, st>>>(n, d_in, d_out);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---- host-pointer variants: stage through device buffers owned by the context ---------------------
+static int ensure(mbe_b200_ctx* ctx, void** p, size_t* cap, size_t need) {
+    if (need <= *cap) {
+        return 0;
+    }
+    if (*p) {
+        CU(cudaFree(*p));
+        *p = nullptr;
+        *cap = 0;
+    }
+    CU(cudaMalloc(p, need));
+    *cap = need;
+    return 0;
+}
+
+int mbe_b200_process_frames(mbe_b200_ctx* ctx, int codec, int soft, int first_stream, int n_streams, int n_frames,
+                            const uint8_t* frames, int16_t* pcm, float* pcmf, mbe_b200_result* results, uint8_t* bits) {
+    int rc = check_range(ctx, first_stream, n_streams);
+    if (rc < 0) {
+        return rc;
+    }
+    if (codec < 0 || codec > 3 || n_frames < 0 || !frames) {
+        return fail(ctx, MBE_B200_E_ARG, "process_frames: bad argument", cudaSuccess);
+    }
+    const size_t nf = (size_t)n_streams * n_frames;
+    if (nf == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    int fb, pb;
+    mbe_b200_geometry(codec, &fb, &pb);
+    const size_t in_bytes = nf * fb * (soft ? 2 : 1);
+    const size_t ob[4] = {pcm ? nf * NS * sizeof(int16_t) : 0, pcmf ? nf * NS * sizeof(float) : 0,
+                          results ? nf * sizeof(mbe_b200_result) : 0, bits ? nf * pb : 0};
+    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, in_bytes)) < 0) {
+        return rc;
+    }
+    for (int i = 0; i < 4; ++i) {
+        if (ob[i] && (rc = ensure(ctx, &ctx->d_out[i], &ctx->d_out_cap[i], ob[i])) < 0) {
+            return rc;
+        }
+    }
+    CU(cudaMemcpyAsync(ctx->d_in, frames, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = mbe_b200_process_frames_dev(ctx, codec, soft, first_stream, n_streams, n_frames, (const uint8_t*)ctx->d_in,
+                                     pcm ? (int16_t*)ctx->d_out[0] : nullptr, pcmf ? (float*)ctx->d_out[1] : nullptr,
+                                     results ? (mbe_b200_result*)ctx->d_out[2] : nullptr,
+                                     bits ? (uint8_t*)ctx->d_out[3] : nullptr, ctx->stream);
+    if (rc < 0) {
+        return rc;
+    }
+    void* host[4] = {pcm, pcmf, results, bits};
+    for (int i = 0; i < 4; ++i) {
+        if (ob[i]) {
+            CU(cudaMemcpyAsync(host[i], ctx->d_out[i], ob[i], cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mbe_b200_process_data(mbe_b200_ctx* ctx, int codec, int first_stream, int n_streams, int n_frames,
+                          const uint8_t* bits, mbe_b200_result* results_inout, int16_t* pcm, float* pcmf) {
+    int rc = check_range(ctx, first_stream, n_streams);
+    if (rc < 0) {
+        return rc;
+    }
+    if (codec < 0 || codec > 3 || n_frames < 0 || !bits) {
+        return fail(ctx, MBE_B200_E_ARG, "process_data: bad argument", cudaSuccess);
+    }
+    const size_t nf = (size_t)n_streams * n_frames;
+    if (nf == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    int fb, pb;
+    mbe_b200_geometry(codec, &fb, &pb);
+    const size_t in_bytes = nf * pb;
+    const size_t ob[3] = {pcm ? nf * NS * sizeof(int16_t) : 0, pcmf ? nf * NS * sizeof(float) : 0,
+                          results_inout ? nf * sizeof(mbe_b200_result) : 0};
+    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, in_bytes)) < 0) {
+        return rc;
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (ob[i] && (rc = ensure(ctx, &ctx->d_out[i], &ctx->d_out_cap[i], ob[i])) < 0) {
+            return rc;
+        }
+    }
+    CU(cudaMemcpyAsync(ctx->d_in, bits, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (results_inout) {
+        CU(cudaMemcpyAsync(ctx->d_out[2], results_inout, ob[2], cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = mbe_b200_process_data_dev(ctx, codec, first_stream, n_streams, n_frames, (const uint8_t*)ctx->d_in,
+                                   results_inout ? (mbe_b200_result*)ctx->d_out[2] : nullptr,
+                                   pcm ? (int16_t*)ctx->d_out[0] : nullptr, pcmf ? (float*)ctx->d_out[1] : nullptr,
+                                   ctx->stream);
+    if (rc < 0) {
+        return rc;
+    }
+    void* host[3] = {pcm, pcmf, results_inout};
+    for (int i = 0; i < 3; ++i) {
+        if (ob[i]) {
+            CU(cudaMemcpyAsync(host[i], ctx->d_out[i], ob[i], cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mbe_b200_decode_frames(mbe_b200_ctx* ctx, int codec, int soft, int n, const uint8_t* frames, uint8_t* bits,
+                           mbe_b200_result* results) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    if (codec < 0 || codec > 3 || n < 0 || !frames) {
+        return fail(ctx, MBE_B200_E_ARG, "decode_frames: bad argument", cudaSuccess);
+    }
+    if (n == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    int fb, pb, rc;
+    mbe_b200_geometry(codec, &fb, &pb);
+    const size_t in_bytes = (size_t)n * fb * (soft ? 2 : 1);
+    const size_t bb = bits ? (size_t)n * pb : 0, rb = results ? (size_t)n * sizeof(mbe_b200_result) : 0;
+    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, in_bytes)) < 0) {
+        return rc;
+    }
+    if (bb && (rc = ensure(ctx, &ctx->d_out[3], &ctx->d_out_cap[3], bb)) < 0) {
+        return rc;
+    }
+    if (rb && (rc = ensure(ctx, &ctx->d_out[2], &ctx->d_out_cap[2], rb)) < 0) {
+        return rc;
+    }
+    CU(cudaMemcpyAsync(ctx->d_in, frames, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bb) {
+        CU(cudaMemsetAsync(ctx->d_out[3], 0, bb, ctx->stream));
+    }
+    rc = mbe_b200_decode_frames_dev(ctx, codec, soft, n, (const uint8_t*)ctx->d_in, bb ? (uint8_t*)ctx->d_out[3] : nullptr,
+                                    rb ? (mbe_b200_result*)ctx->d_out[2] : nullptr, ctx->stream);
+    if (rc < 0) {
+        return rc;
+    }
+    if (bb) {
+        CU(cudaMemcpyAsync(bits, ctx->d_out[3], bb, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (rb) {
+        CU(cudaMemcpyAsync(results, ctx->d_out[2], rb, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mbe_b200_synthesize_speech(mbe_b200_ctx* ctx, int n, void* cur_parms, void* prev_parms, const uint32_t* seeds,
+                               float* pcmf, int16_t* pcm) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    if (n < 0 || !cur_parms || !prev_parms) {
+        return fail(ctx, MBE_B200_E_ARG, "synthesize_speech: bad argument", cudaSuccess);
+    }
+    if (n == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    const size_t pbytes = (size_t)n * sizeof(Parms);
+    int rc;
+    // d_in: [cur | prev | seeds]
+    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, 2 * pbytes + (size_t)n * 4)) < 0) {
+        return rc;
+    }
+    uint8_t* base = (uint8_t*)ctx->d_in;
+    CU(cudaMemcpyAsync(base, cur_parms, pbytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(base + pbytes, prev_parms, pbytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (seeds) {
+        CU(cudaMemcpyAsync(base + 2 * pbytes, seeds, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const size_t ob[2] = {pcm ? (size_t)n * NS * sizeof(int16_t) : 0, pcmf ? (size_t)n * NS * sizeof(float) : 0};
+    for (int i = 0; i < 2; ++i) {
+        if (ob[i] && (rc = ensure(ctx, &ctx->d_out[i], &ctx->d_out_cap[i], ob[i])) < 0) {
+            return rc;
+        }
+    }
+    LaunchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = MODE_SYNTH;
+    a.n_streams = n;
+    a.n_frames = 1;
+    a.pcm = pcm ? (int16_t*)ctx->d_out[0] : nullptr;
+    a.pcmf = pcmf ? (float*)ctx->d_out[1] : nullptr;
+    a.tab = ctx->d_tab;
+    a.synth_cur = (uint32_t*)base;
+    a.synth_prev = (uint32_t*)(base + pbytes);
+    a.synth_seeds = seeds ? (const uint32_t*)(base + 2 * pbytes) : nullptr;
+    if ((rc = launch_stream_kernel(ctx, a, ctx->stream)) < 0) {
+        return rc;
+    }
+    CU(cudaMemcpyAsync(cur_parms, base, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(prev_parms, base + pbytes, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pcm) {
+        CU(cudaMemcpyAsync(pcm, ctx->d_out[0], ob[0], cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (pcmf) {
+        CU(cudaMemcpyAsync(pcmf, ctx->d_out[1], ob[1], cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mbe_b200_floattoshort(mbe_b200_ctx* ctx, int n_frames, const float* in, int16_t* out) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    if (n_frames < 0 || !in || !out) {
+        return fail(ctx, MBE_B200_E_ARG, "floattoshort: bad argument", cudaSuccess);
+    }
+    if (n_frames == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)n_frames * NS;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, n * sizeof(float))) < 0) {
+        return rc;
+    }
+    if ((rc = ensure(ctx, &ctx->d_out[0], &ctx->d_out_cap[0], n * sizeof(int16_t))) < 0) {
+        return rc;
+    }
+    CU(cudaMemcpyAsync(ctx->d_in, in, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = mbe_b200_floattoshort_dev(ctx, n_frames, (const float*)ctx->d_in, (int16_t*)ctx->d_out[0], ctx->stream)) < 0) {
+        return rc;
+    }
+    CU(cudaMemcpyAsync(out, ctx->d_out[0], n * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

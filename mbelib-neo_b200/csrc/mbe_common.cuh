@@ -1,0 +1,131 @@
+// Shared declarations for the B200 IMBE/AMBE decoder kernels: state layout, lookup tables that are
+// filled on the host at context creation, per-warp shared-memory workspace.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mbe_b200.h"
+
+namespace mbe {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int NS = 160;     // samples per frame
+constexpr int NFFT = 256;   // unvoiced FFT length
+constexpr int MAXL = 56;    // max harmonics
+
+// Device image of the reference's `struct mbe_parameters` (include/mbelib-neo/mbelib.h:88-137).
+// Byte-identical layout: it is the import/export format of the C-ABI.
+struct Parms {
+    float w0;
+    int L;
+    int K;
+    int Vl[57];
+    float Ml[57];
+    float log2Ml[57];
+    float PHIl[57];
+    float PSIl[57];
+    float gamma;
+    uint32_t tonePhase;
+    int swn;
+    float localEnergy;
+    int amplitudeThreshold;
+    float errorRate;
+    int errorCountTotal;
+    int errorCount4;
+    int repeatCount;
+    float mutingThreshold;
+    float previousUw[256];
+    float noiseSeed;
+    float noiseOverlap[96];
+};
+static_assert(sizeof(Parms) == MBE_B200_PARMS_BYTES, "mbe_parms layout");
+constexpr int PARMS_WORDS = sizeof(Parms) / 4;            // 651
+constexpr int RNG_WORDS = 4;                              // comfort lo, comfort hi, uv seed, uv override
+constexpr int STATE_WORDS = 3 * PARMS_WORDS + RNG_WORDS;  // per stream in HBM: cur, prev, enh, rng (7828 B)
+
+// Tables computed on the host when a context is created (host libm = the reference's libm) and kept
+// in HBM; hot ones are staged into shared memory per block.
+struct DevTables {
+    // DCT cosines (src/imbe/imbe7200x4400.c:97-111, src/ambe/ambe3600x2450.c:60-74)
+    float ri6[36];      // [m-1][i-1]
+    float ri8[64];
+    float blk[1785];    // packed [ji][j][k]: blk_off[ji] + (j-1)*ji + (k-1), ji = 1..17
+    int blk_off[18];
+    // FFTPACK twiddles for N=256 (src/external/pffft/pffft.c:1231-1262)
+    float tw[256];
+    // b0 -> model tables
+    float imbe_w0[256];
+    unsigned char imbe_L[256];   // 0 = invalid (b0 > 207 or L out of 9..56)
+    unsigned char imbe_K[256];   // K as mbe_convertImbe7100to7200 computes it (no validity check)
+    unsigned char imbe_Kv[256];  // K for valid b0
+    float a2450_w0[120];
+    float a2450_w0_silence;
+    float a2450_f0_silence;
+    float a2400_f0[126];
+    float a2400_w0[126];
+    float a2400_w0_silence;
+    float imbe_default_w0;
+    int imbe_default_L;
+    float ambe_default_w0;
+    float log2_int[57];          // log2f((float)L)
+    float ambe_rconst;           // (float)(1/(2*sqrt(2)))
+    // LCG jump-ahead tables: x_k = (A[k]*x_0 + C[k]) mod m
+    unsigned short pnA[116], pnC[116];  // PN de-scrambler, mod 65536
+    unsigned uvA[161], uvC[161];        // unvoiced noise, mod 53125
+    unsigned long long cnA[161], cnC[161];  // comfort noise, mod 2^48
+    // ECC
+    unsigned short golay_par_hi[64], golay_par_lo[64];
+    unsigned golay_cw[4096];            // all codewords, index = 12 data bits
+    unsigned short ham_cw[2][2048];     // all Hamming(15,11) codewords in the reference's enumeration order
+    unsigned short ham_rows[2][4];
+    unsigned short ham_flip[2][16];
+    // windows
+    float uvwin[256];                   // 211-pt trapezoid centred at 128
+    float wola_wp[160], wola_wc[160], wola_den[160];
+    float voiced_win[324];
+    unsigned short golay_fix[2048];
+};
+
+// mode of the stream kernel
+enum { MODE_FRAMES = 0, MODE_DATA = 1, MODE_SYNTH = 2 };
+
+struct LaunchArgs {
+    int codec, soft, mode;
+    int first_stream, n_streams, n_frames;
+    const uint8_t* frames;      // MODE_FRAMES: channel frames; MODE_DATA: parameter bits
+    int16_t* pcm;
+    float* pcmf;
+    mbe_b200_result* results;
+    uint8_t* bits;
+    uint32_t* state;            // [max_streams][STATE_WORDS]
+    const DevTables* tab;
+    // MODE_SYNTH: cur/prev parameter blobs in device memory, [n][651] words each, updated in place
+    uint32_t* synth_cur;
+    uint32_t* synth_prev;
+    const uint32_t* synth_seeds;
+};
+
+constexpr int TILE_STRIDE = 36;   // floats per sample row of the oscillator tile (32 components + pad)
+
+// Per-warp shared-memory workspace: one warp owns one stream for the whole launch.
+struct __align__(16) WarpWS {
+    Parms cur, prev, enh;                 // 7812 B
+    float noise[NFFT];                    // white-noise buffer of the frame (phases + unvoiced)
+    union {
+        float tile[32 * TILE_STRIDE];     // voiced bank: [sample][component]
+        struct {
+            float a[NFFT];
+            float b[NFFT];
+            float scale[132];
+        } fft;
+    } u;
+    float gain[112];                      // per-component 2*Ml
+    float tmp[128];                       // scratch: per-harmonic terms [1..56], DCT coefficients [64+l]
+    float Tl[60];
+    int field[58];                        // IMBE quantiser words b1..bL+1
+    unsigned rowbits[8];
+    unsigned char comp[112];              // component descriptor: harmonic << 2 | kind
+    unsigned char rel[8 * 24];            // soft-bit reliabilities of the frame
+};
+
+}  // namespace mbe

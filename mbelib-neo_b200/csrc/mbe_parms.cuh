@@ -1,0 +1,465 @@
+// Parameter dequantisation on one warp: parameter bits -> w0, L, K, Vl[], log2Ml[], Ml[] using the
+// previous frame (replaces src/imbe/imbe7200x4400.c:117-354,589-630, src/ambe/ambe3600x2450.c:176-621,
+// src/ambe/ambe3600x2400.c:164-546).  Lanes run over harmonics; sums whose order matters for
+// rounding are kept in index order (per-harmonic terms are computed in parallel, then added serially).
+#pragma once
+#include "mbe_common.cuh"
+#include "mbe_frontend.cuh"
+#include "mbe_libm.cuh"
+
+namespace mbe {
+
+// codec tables (device copies of mbe_tables.inc) are declared in mbe_b200.cu before this header
+__device__ __forceinline__ float pow2i(int e) {  // exact 2^e for -126 <= e <= 127 (exp2f of an integer)
+    return __int_as_float((127 + e) << 23);
+}
+
+__device__ __forceinline__ unsigned pick(const unsigned dw[3], const unsigned char* idx, int n) {
+    unsigned v = 0;
+    for (int i = 0; i < n; ++i) {
+        v = (v << 1) | getbit(dw, idx[i]);
+    }
+    return v;
+}
+
+// log-magnitude prediction + exp2 (imbe7200x4400.c:294-354 / ambe3600x2450.c:389-459).
+//   ambe = 0: rho = rho_imbe, clamp interpolation indices to 0..56, no gain term
+//   ambe = 1: rho = 0.65, add BigGamma, unvoiced magnitudes scaled by unvc
+__device__ __forceinline__ void predict_magnitudes(WarpWS& ws, const DevTables* T, int ambe, float rho, float unvc,
+                                                   int lane) {
+    Parms& cur = ws.cur;
+    Parms& prev = ws.prev;
+    const int cur_L = cur.L;  // already within 9..56
+    int prev_L = prev.L;
+    prev_L = prev_L < 1 ? 1 : (prev_L > 56 ? 56 : prev_L);
+    if (cur_L > prev_L) {
+        const float m = prev.Ml[prev_L], lg = prev.log2Ml[prev_L];
+        for (int l = prev_L + 1 + lane; l <= cur_L; l += 32) {
+            prev.Ml[l] = m;
+            prev.log2Ml[l] = lg;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        prev.log2Ml[0] = prev.log2Ml[1];
+        prev.Ml[0] = prev.Ml[1];
+    }
+    __syncwarp();
+    const float* P = prev.log2Ml;  // P[57] aliases PHIl[0], exactly as in the reference's struct
+    const float ratio = (float)prev_L / (float)cur_L;
+    float dl[2], pa[2], pb[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        int l = 1 + lane + 32 * r;
+        dl[r] = 0.f;
+        pa[r] = 0.f;
+        pb[r] = 0.f;
+        if (l <= cur_L) {
+            float fk = ratio * (float)l;
+            int ik = (int)fk;
+            int up;
+            if (!ambe) {
+                ik = ik < 0 ? 0 : (ik > 56 ? 56 : ik);
+                up = ik + 1 > 56 ? 56 : ik + 1;
+            } else {
+                up = ik + 1;
+            }
+            dl[r] = fk - (float)ik;
+            pa[r] = P[ik];
+            pb[r] = P[up];
+            ws.tmp[l] = (((float)1 - dl[r]) * pa[r]) + (dl[r] * pb[r]);
+        }
+    }
+    __syncwarp();
+    float acc = 0.f;
+    for (int l = 1; l <= cur_L; ++l) {
+        acc = acc + ws.tmp[l];
+    }
+    acc = ((rho / (float)cur_L) * acc);
+    float big_gamma = 0.f;
+    if (ambe) {
+        float s42 = 0.f;
+        for (int l = 1; l <= cur_L; ++l) {
+            s42 += ws.Tl[l];
+        }
+        s42 = s42 / (float)cur_L;
+        big_gamma = cur.gamma - (0.5f * T->log2_int[cur_L]) - s42;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        int l = 1 + lane + 32 * r;
+        if (l <= cur_L) {
+            float c1 = (rho * ((float)1 - dl[r]) * pa[r]);
+            float c2 = (rho * dl[r] * pb[r]);
+            float lg;
+            if (ambe) {
+                lg = ws.Tl[l] + c1 + c2 - acc + big_gamma;
+            } else {
+                lg = ws.Tl[l] + c1 + c2 - acc;
+            }
+            cur.log2Ml[l] = lg;
+            float m = mbelibm::exp2f_glibc(lg, d_exp2_tab);
+            if (ambe && cur.Vl[l] != 1) {
+                m = unvc * m;
+            }
+            cur.Ml[l] = m;
+        }
+    }
+    __syncwarp();
+}
+
+// per-block inverse DCT: ws.tmp[64 + l] holds the DCT coefficients flattened by harmonic index,
+// blocklen[0..nblk-1] the block sizes.  Writes ws.Tl[1..L].
+__device__ __forceinline__ void block_idct(WarpWS& ws, const DevTables* T, const int* blocklen, int nblk, int L, int lane) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        int l = 1 + lane + 32 * r;
+        if (l <= L) {
+            int start = 0, ji = 1;
+            for (int i = 0; i < nblk; ++i) {
+                ji = blocklen[i];
+                if (l <= start + ji) {
+                    break;
+                }
+                start += ji;
+            }
+            const int j = l - start;
+            const float* cs = T->blk + T->blk_off[ji] + (j - 1) * ji;
+            float sum = 0.f;
+            for (int k = 1; k <= ji; ++k) {
+                float ak = (k == 1) ? 1.f : 2.f;
+                sum = sum + (ak * ws.tmp[64 + start + k] * cs[k - 1]);
+            }
+            ws.Tl[l] = sum;
+        }
+    }
+    __syncwarp();
+}
+
+// ---- IMBE 4400 ----  returns 0 (voice) or 1 (invalid fundamental -> repeat)
+__device__ __forceinline__ int decode_imbe(const unsigned dw[3], WarpWS& ws, const DevTables* T, int lane) {
+    Parms& cur = ws.cur;
+    unsigned b0 = 0;
+    {
+        const int idx[8] = {0, 1, 2, 3, 4, 5, 85, 86};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            b0 = (b0 << 1) | getbit(dw, idx[i]);
+        }
+    }
+    if (b0 > 207u) {
+        return 1;
+    }
+    const int L = (int)T->imbe_L[b0];
+    const int K = (int)T->imbe_Kv[b0];
+    if (lane == 0) {
+        cur.w0 = T->imbe_w0[b0];
+        cur.L = L;
+        cur.K = K;
+    }
+    const int L9 = L - 9;
+
+    // scatter bits 6..84 into the quantiser words b1..bL+1
+    for (int i = lane; i < 58; i += 32) {
+        ws.field[i] = 0;
+    }
+    __syncwarp();
+    {
+        const unsigned char* map = t_imbe_bitmap + L9 * 158;
+        for (int i = 6 + lane; i < 85; i += 32) {
+            if (getbit(dw, i)) {
+                atomicOr(&ws.field[map[2 * (i - 6)]], 1 << map[2 * (i - 6) + 1]);
+            }
+        }
+    }
+    __syncwarp();
+
+    // voiced/unvoiced decisions: one bit per band of three harmonics
+    {
+        const int vbits = ws.field[1];
+        for (int l = 1 + lane; l <= L; l += 32) {
+            int k = K - 1 - (l - 1) / 3;
+            k = k < 0 ? 0 : k;
+            cur.Vl[l] = (vbits >> k) & 1;
+        }
+    }
+    // gain vector -> ws.tmp[1..6]
+    if (lane < 6) {
+        float g;
+        if (lane == 0) {
+            g = t_imbe_gain0[ws.field[2] & 63];
+        } else {
+            const int nb = t_imbe_gain_bits[L9 * 5 + (lane - 1)];
+            const float step = t_imbe_gain_step[L9 * 5 + (lane - 1)];
+            const int bm = ws.field[lane + 2] & ((1 << nb) - 1);
+            g = (step * ((float)bm - pow2i(nb - 1) + 0.5f));
+        }
+        ws.tmp[1 + lane] = g;
+    }
+    __syncwarp();
+    // 6-point inverse DCT of the gains -> ws.tmp[9..14] = Ri[1..6]
+    if (lane < 6) {
+        float sum = 0.f;
+#pragma unroll
+        for (int m = 1; m <= 6; ++m) {
+            float am = (m == 1) ? 1.f : 2.f;
+            sum = sum + (am * ws.tmp[m] * T->ri6[(m - 1) * 6 + lane]);
+        }
+        ws.tmp[9 + lane] = sum;
+    }
+    __syncwarp();
+    // DCT coefficients flattened by harmonic: first of each block = Ri, rest = dequantised HOCs
+    int blen[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        blen[i] = t_imbe_blocklen[L9 * 6 + i];
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        int l = 1 + lane + 32 * r;
+        if (l <= L) {
+            int start = 0, blk = 0;  // block lengths are non-decreasing and sum to L
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                if (l > start + blen[i]) {
+                    start += blen[i];
+                    blk = i + 1;
+                }
+            }
+            blk = blk > 5 ? 5 : blk;
+            const int k = l - start;       // 1-based position inside block (blk+1)
+            float v;
+            if (k == 1) {
+                v = ws.tmp[9 + blk];
+            } else {
+                const int m = l - (blk + 1) + 7;  // quantiser word index
+                const int Bm = t_imbe_hoc_bits[L9 * 50 + (m - 8)];
+                if (Bm <= 0) {
+                    v = 0.f;
+                } else {
+                    const int bm = ws.field[m] & ((1 << Bm) - 1);
+                    v = ((t_imbe_hoc_step[Bm - 1] * t_imbe_hoc_sdev[k - 2]) * (((float)bm - pow2i(Bm - 1)) + 0.5f));
+                }
+            }
+            ws.tmp[64 + l] = v;
+        }
+    }
+    __syncwarp();
+    block_idct(ws, T, blen, 6, L, lane);
+
+    float rho;
+    if (L <= 15) {
+        rho = 0.4f;
+    } else if (L <= 24) {
+        rho = (0.03f * (float)L) - 0.05f;
+    } else {
+        rho = 0.7f;
+    }
+    predict_magnitudes(ws, T, 0, rho, 0.f, lane);
+    return 0;
+}
+
+// ---- AMBE common tail: PRBA -> Ri -> Cik -> Tl -> magnitudes ----
+struct AmbeBooks {
+    const float* prba24;
+    const float* prba58;
+    const float* hoc[4];
+    const unsigned char* blocklen;
+};
+
+__device__ __forceinline__ void ambe_tail(WarpWS& ws, const DevTables* T, const AmbeBooks& bk, int b3, int b4,
+                                          const int hocidx[4], float unvc, int lane) {
+    Parms& cur = ws.cur;
+    const int L = cur.L;
+    if (lane < 8) {
+        float g;
+        if (lane == 0) {
+            g = 0.f;
+        } else if (lane < 4) {
+            g = bk.prba24[b3 * 3 + (lane - 1)];
+        } else {
+            g = bk.prba58[b4 * 4 + (lane - 4)];
+        }
+        ws.tmp[1 + lane] = g;
+    }
+    __syncwarp();
+    if (lane < 8) {
+        float sum = 0.f;
+#pragma unroll
+        for (int m = 1; m <= 8; ++m) {
+            float am = (m == 1) ? 1.f : 2.f;
+            sum = sum + (am * ws.tmp[m] * T->ri8[(m - 1) * 8 + lane]);
+        }
+        ws.tmp[11 + lane] = sum;  // Ri[1..8] at tmp[11..18]
+    }
+    __syncwarp();
+    int blen[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        blen[i] = bk.blocklen[L * 4 + i];
+    }
+    const float rconst = T->ambe_rconst;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        int l = 1 + lane + 32 * r;
+        if (l <= L) {
+            int start = 0, blk = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (l > start + blen[i]) {
+                    start += blen[i];
+                    blk = i + 1;
+                }
+            }
+            blk = blk > 3 ? 3 : blk;
+            const int k = l - start;
+            const float ra = ws.tmp[11 + 2 * blk], rb2 = ws.tmp[12 + 2 * blk];
+            float v;
+            if (k == 1) {
+                v = 0.5f * (ra + rb2);
+            } else if (k == 2) {
+                v = rconst * (ra - rb2);
+            } else if (k <= 6) {
+                const float* h = (blk == 0) ? bk.hoc[0] : (blk == 1 ? bk.hoc[1] : (blk == 2 ? bk.hoc[2] : bk.hoc[3]));
+                const int hi = (blk == 0) ? hocidx[0] : (blk == 1 ? hocidx[1] : (blk == 2 ? hocidx[2] : hocidx[3]));
+                v = h[hi * 4 + (k - 3)];
+            } else {
+                v = 0.f;
+            }
+            ws.tmp[64 + l] = v;
+        }
+    }
+    __syncwarp();
+    block_idct(ws, T, blen, 4, L, lane);
+    predict_magnitudes(ws, T, 1, 0.65f, unvc, lane);
+}
+
+// ---- AMBE+2 3600x2450 ---- returns 0 voice | 2 erasure | 7 tone
+__device__ __forceinline__ int decode_ambe2450(const unsigned dw[3], WarpWS& ws, const DevTables* T, int total_errors,
+                                               int lane) {
+    Parms& cur = ws.cur;
+    unsigned u0 = 0, u1 = 0, u3 = 0;
+    for (int i = 0; i < 12; ++i) {
+        u0 = (u0 << 1) | getbit(dw, i);
+    }
+    for (int i = 12; i < 24; ++i) {
+        u1 = (u1 << 1) | getbit(dw, i);
+    }
+    for (int i = 35; i < 49; ++i) {
+        u3 = (u3 << 1) | getbit(dw, i);
+    }
+    const bool tone_ok = (((u0 >> 6) & 0x3fu) == 63u) && (((u3 & 0xfu) == 0u) || (((u1 >> 8) & 0xfu) == (u1 & 0xfu)));
+    if (tone_ok && total_errors < 6) {
+        return 7;
+    }
+    const unsigned char i_b0[7] = {0, 1, 2, 3, 37, 38, 39};
+    const unsigned char i_b1[5] = {4, 5, 6, 7, 35};
+    const unsigned char i_b2[5] = {8, 9, 10, 11, 36};
+    const unsigned char i_b3[9] = {12, 13, 14, 15, 16, 17, 18, 19, 40};
+    const unsigned char i_b4[7] = {20, 21, 22, 23, 41, 42, 43};
+    const unsigned char i_b5[5] = {24, 25, 26, 27, 44};
+    const unsigned char i_b6[4] = {28, 29, 30, 45};
+    const unsigned char i_b7[4] = {31, 32, 33, 46};
+    const unsigned char i_b8[3] = {34, 47, 48};
+    const int b0 = (int)pick(dw, i_b0, 7);
+    if (b0 >= 120 && b0 <= 123) {
+        return 2;
+    }
+    if (b0 == 126 || b0 == 127) {
+        return 2;
+    }
+    int L, silence = 0;
+    float f0, w0;
+    if (b0 == 124 || b0 == 125) {
+        silence = 1;
+        f0 = T->a2450_f0_silence;
+        w0 = T->a2450_w0_silence;
+        L = (b0 == 124) ? 15 : 14;
+    } else {
+        f0 = t_a2450_f0[b0];
+        w0 = T->a2450_w0[b0];
+        L = t_a2450_L[b0];
+    }
+    const float unvc = 0.2046f / sqrtf(w0);
+    const unsigned vmask = t_a2450_vuv[pick(dw, i_b1, 5)];
+    const float dg = t_a2450_dgain[pick(dw, i_b2, 5)];
+    for (int l = 1 + lane; l <= L; l += 32) {
+        if (silence) {
+            cur.Vl[l] = 0;
+        } else {
+            int jl = (int)((float)l * 16.0f * f0);
+            cur.Vl[l] = (int)((vmask >> jl) & 1u);
+        }
+    }
+    if (lane == 0) {
+        cur.w0 = w0;
+        cur.L = L;
+        cur.gamma = dg + (0.5f * ws.prev.gamma);
+    }
+    __syncwarp();
+    AmbeBooks bk = {t_a2450_prba24, t_a2450_prba58, {t_a2450_hoc5, t_a2450_hoc6, t_a2450_hoc7, t_a2450_hoc8},
+                    t_a2450_blocklen};
+    const int hocidx[4] = {(int)pick(dw, i_b5, 5), (int)pick(dw, i_b6, 4), (int)pick(dw, i_b7, 4), (int)pick(dw, i_b8, 3)};
+    ambe_tail(ws, T, bk, (int)pick(dw, i_b3, 9), (int)pick(dw, i_b4, 7), hocidx, unvc, lane);
+    return 0;
+}
+
+// ---- AMBE 3600x2400 ---- returns 0 voice | 3 tone/silence marker | 5..122 D-STAR tone index
+__device__ __forceinline__ int decode_ambe2400(const unsigned dw[3], WarpWS& ws, const DevTables* T, int lane) {
+    Parms& cur = ws.cur;
+    const unsigned char i_b0[7] = {0, 1, 2, 3, 4, 5, 48};
+    const unsigned char i_b1[4] = {38, 39, 40, 41};
+    const unsigned char i_b2[6] = {6, 7, 8, 9, 42, 43};
+    const unsigned char i_b3[9] = {10, 11, 12, 13, 14, 15, 16, 44, 45};
+    const unsigned char i_b4[7] = {17, 18, 19, 20, 21, 46, 47};
+    const unsigned char i_b5[4] = {22, 23, 25, 26};
+    const unsigned char i_b6[4] = {27, 28, 29, 30};
+    const unsigned char i_b7[4] = {31, 32, 33, 34};
+    const unsigned char i_b8[3] = {35, 36, 37};
+    const int b0 = (int)pick(dw, i_b0, 7);
+    if ((b0 & 0x7E) == 0x7E) {
+        // three remapped high bits (t7,t6,t5 tables of the reference folded into one) + five literal bits
+        const unsigned hi3 = (0x56732104u >> (4 * ((getbit(dw, 6) << 2) | (getbit(dw, 7) << 1) | getbit(dw, 8)))) & 7u;
+        const int tone = (int)((hi3 << 5) | (getbit(dw, 9) << 4) | (getbit(dw, 42) << 3) | (getbit(dw, 43) << 2)
+                               | (getbit(dw, 10) << 1) | getbit(dw, 11));
+        if (tone >= 5 && tone <= 122) {
+            return tone;
+        }
+        if (!(tone >= 128 && tone <= 163)) {
+            for (int l = 1 + lane; l <= 14; l += 32) {
+                cur.Vl[l] = 0;
+            }
+            if (lane == 0) {
+                cur.w0 = T->a2400_w0_silence;
+                cur.L = 14;
+            }
+            __syncwarp();
+        }
+        return 3;
+    }
+    const float f0 = T->a2400_f0[b0];
+    const float w0 = T->a2400_w0[b0];
+    const int L = t_a2400_L[b0];
+    const float unvc = 0.2046f / sqrtf(w0);
+    const unsigned vmask = t_a2400_vuv[pick(dw, i_b1, 4)];
+    const float dg = t_a2400_dgain[pick(dw, i_b2, 6)];
+    for (int l = 1 + lane; l <= L; l += 32) {
+        int jl = (int)((float)l * 16.0f * f0);
+        cur.Vl[l] = (int)((vmask >> jl) & 1u);
+    }
+    if (lane == 0) {
+        cur.w0 = w0;
+        cur.L = L;
+        cur.gamma = dg + (0.5f * ws.prev.gamma);
+    }
+    __syncwarp();
+    AmbeBooks bk = {t_a2400_prba24, t_a2400_prba58, {t_a2400_hoc5, t_a2400_hoc6, t_a2400_hoc7, t_a2400_hoc8},
+                    t_a2400_blocklen};
+    const int hocidx[4] = {(int)pick(dw, i_b5, 4), (int)pick(dw, i_b6, 4), (int)pick(dw, i_b7, 4),
+                           (int)(pick(dw, i_b8, 3) << 1)};
+    ambe_tail(ws, T, bk, (int)pick(dw, i_b3, 9), (int)pick(dw, i_b4, 7), hocidx, unvc, lane);
+    return 0;
+}
+
+}  // namespace mbe

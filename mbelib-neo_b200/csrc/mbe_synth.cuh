@@ -1,0 +1,790 @@
+// Speech synthesis on one warp: spectral enhancement, adaptive smoothing, noise sources, phase update,
+// voiced oscillator bank, FFT/WOLA unvoiced synthesis, tone synthesis, soft clip, float->int16.
+// Replaces src/core/mbelib.c:412-1132,1148-1177, src/core/mbe_adaptive.c:116-276,
+// src/core/mbe_unvoiced_fft.c:277-761 and the N=256 real radix-4 path of the vendored pffft
+// (src/external/pffft/pffft.c:749-926,1109-1196).
+//
+// The 160 output samples of a frame live in registers: lane i owns samples i, 32+i, ..., 128+i
+// (acc[0..4]).  Rounding-order rules that pin parity with the reference:
+//   * per sample, harmonics are added in order l = 1..maxl, previous-frame component before
+//     current-frame component (mbelib.c:310-317,1025-1039);
+//   * each oscillator is the reference's rotation recurrence, unfused:  c' = c*cd - s*sd,
+//     s' = s*cd + c*sd (mbelib.c:213-219), contribution (gain*W[n])*c (mbelib.c:262-265);
+//   * FFT butterflies follow FFTPACK radf4/radb4 operation order.
+#pragma once
+#include "mbe_common.cuh"
+#include "mbe_libm.cuh"
+
+namespace mbe {
+
+#define MBE_PI_F 3.14159274101257324f /* (float)M_PI */
+#define MBE_CLIP_F ((32767.0f * 0.95f) / 7.0f)
+
+__device__ __forceinline__ bool bands_ok(int L) { return L >= 1 && L <= MAXL; }
+
+__device__ __forceinline__ void copy_parms(Parms* dst, const Parms* src, int lane) {
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    for (int i = lane; i < PARMS_WORDS; i += 32) {
+        d[i] = s[i];
+    }
+    __syncwarp();
+}
+
+// default model of mbe_initMbeParms / mbe_initAmbeParms_common, written to all three structs
+__device__ __forceinline__ void fill_default(Parms* p, float w0, int L, int K, float mute_thr, int lane) {
+    for (int l = lane; l <= 56; l += 32) {
+        p->Ml[l] = 1.0f;
+        p->Vl[l] = 0;
+        p->log2Ml[l] = 0.0f;
+        p->PHIl[l] = 0.0f;
+        p->PSIl[l] = 0.0f;
+    }
+    for (int i = lane; i < 256; i += 32) {
+        p->previousUw[i] = 0.0f;
+    }
+    for (int i = lane; i < 96; i += 32) {
+        p->noiseOverlap[i] = 0.0f;
+    }
+    if (lane == 0) {
+        p->swn = 0;
+        p->tonePhase = 0;
+        p->w0 = w0;
+        p->L = L;
+        p->K = K;
+        p->gamma = 0.0f;
+        p->localEnergy = 75000.0f;
+        p->amplitudeThreshold = 20480;
+        p->errorRate = 0.0f;
+        p->errorCountTotal = 0;
+        p->errorCount4 = 0;
+        p->repeatCount = 0;
+        p->mutingThreshold = mute_thr;
+        p->noiseSeed = -1.0f;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void init_all(WarpWS& ws, float w0, int L, int K, float mute_thr, int lane) {
+    fill_default(&ws.prev, w0, L, K, mute_thr, lane);
+    copy_parms(&ws.cur, &ws.prev, lane);
+    copy_parms(&ws.enh, &ws.prev, lane);
+}
+
+struct StreamRng {
+    unsigned long long comfort;  // 48-bit LCG state
+    unsigned uv_seed;
+    unsigned uv_override;
+};
+
+// ---- spectral amplitude enhancement (mbelib.c:412-661); returns pre-enhancement Rm0 -------------
+__device__ __forceinline__ float spectral_enhance(Parms& cur, int lane) {
+    const int L = cur.L;
+    if (!bands_ok(L)) {
+        return 0.0f;
+    }
+    const float w0 = cur.w0;
+    float ss, cs;
+    mbelibm::sincosf_glibc(w0, &ss, &cs);
+    // serial: cos(l*w0) by rotation, Rm0 = sum M^2, Rm1 = sum M^2 cos, all in harmonic order
+    float c = 1.0f, s = 0.0f, Rm0 = 0.0f, Rm1 = 0.0f, cw0 = 0.0f, cw1 = 0.0f;
+    for (int l = 1; l <= L; ++l) {
+        float cn = (c * cs) - (s * ss);
+        float sn = (s * cs) + (c * ss);
+        c = cn;
+        s = sn;
+        if (l == lane + 1) {
+            cw0 = c;
+        }
+        if (l == lane + 33) {
+            cw1 = c;
+        }
+        const float m = cur.Ml[l];
+        const float m2 = m * m;
+        Rm0 += m2;
+        Rm1 += m2 * c;
+    }
+    const float R2m0 = Rm0 * Rm0;
+    const float R2m1 = Rm1 * Rm1;
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int l = 1 + lane + 32 * r;
+        if (l <= L) {
+            float M = cur.Ml[l];
+            if (M != 0.0f) {
+                const float cosw = r ? cw1 : cw0;
+                float W = sqrtf(M)
+                          * sqrtf(sqrtf(((0.96f * MBE_PI_F) * ((R2m0 + R2m1) - ((2.0f * Rm0) * Rm1 * cosw)))
+                                        / ((w0 * Rm0) * (R2m0 - R2m1))));
+                if ((8 * l) <= L) {
+                } else if (W > 1.2f) {
+                    M = 1.2f * M;
+                } else if (W < 0.5f) {
+                    M = 0.5f * M;
+                } else {
+                    M = W * M;
+                }
+                cur.Ml[l] = M;
+            }
+        }
+    }
+    __syncwarp();
+    float sum = 0.0f;
+    for (int l = 1; l <= L; ++l) {
+        float M = cur.Ml[l];
+        if (M < 0.0f) {
+            M = -M;
+        }
+        sum += M * M;
+    }
+    const float g = (sum == 0.0f) ? 1.0f : sqrtf(Rm0 / sum);
+    __syncwarp();
+    for (int l = 1 + lane; l <= L; l += 32) {
+        cur.Ml[l] = g * cur.Ml[l];
+    }
+    __syncwarp();
+    return Rm0;
+}
+
+// ---- adaptive smoothing, JMBE algorithms #111-116 (mbe_adaptive.c:151-276) -----------------------
+__device__ __forceinline__ void adaptive_smoothing(Parms& cur, const Parms& prev, int has_rm0, float rm0, int lane) {
+    if (!bands_ok(cur.L) || !bands_ok(prev.L)) {
+        return;
+    }
+    const int L = cur.L;
+    if (!has_rm0) {
+        rm0 = 0.0f;
+        for (int l = 1; l <= L; ++l) {
+            rm0 += cur.Ml[l] * cur.Ml[l];
+        }
+    }
+    const float rate = cur.errorRate;
+    const int etot = cur.errorCountTotal;
+    const int e4 = cur.errorCount4;
+    float pe = prev.localEnergy;
+    if (pe < 10000.0f) {
+        pe = 75000.0f;
+    }
+    float le = 0.95f * pe + 0.05f * rm0;
+    if (le < 10000.0f) {
+        le = 10000.0f;
+    }
+    float VM;
+    if (rate <= 0.005f && etot <= 4) {
+        VM = 3.40282346638528859812e+38f;
+    } else {
+        float x8 = sqrtf(sqrtf(sqrtf(le)));
+        float en = x8 * x8 * x8;
+        if (rate <= 0.0125f && e4 == 0) {
+            VM = (45.255f * en) / mbelibm::expf_glibc(277.26f * rate, d_exp2_tab);
+        } else {
+            VM = 1.414f * en;
+        }
+    }
+    int pt = prev.amplitudeThreshold;
+    if (pt <= 0) {
+        pt = 20480;
+    }
+    int Tm;
+    if (rate <= 0.005f && etot <= 6) {
+        Tm = 20480;
+    } else {
+        Tm = 6000 - (300 * etot) + pt;
+    }
+    __syncwarp();
+    for (int l = 1 + lane; l <= L; l += 32) {
+        if (cur.Ml[l] > VM) {
+            cur.Vl[l] = 1;
+        }
+    }
+    float Am = 0.0f;
+    for (int l = 1; l <= L; ++l) {
+        Am += cur.Ml[l];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        cur.localEnergy = le;
+        cur.amplitudeThreshold = Tm;
+    }
+    if (Am > (float)Tm && Am > 0.0f) {
+        const float sc = (float)Tm / Am;
+        for (int l = 1 + lane; l <= L; l += 32) {
+            cur.Ml[l] *= sc;
+        }
+    }
+    __syncwarp();
+}
+
+// ---- comfort noise (mbe_adaptive.c:116-131): java.util.Random-style LCG, jump-ahead per lane ------
+__device__ __forceinline__ void comfort_noise(float acc[5], StreamRng& rng, const DevTables* T, int lane) {
+    const float gain = (0.003f * 32767.0f) / 7.0f;
+    const unsigned long long mask = (1ULL << 48) - 1ULL;
+    const unsigned long long s0 = rng.comfort;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const int i = 32 * c + lane;
+        const unsigned long long st = (T->cnA[i + 1] * s0 + T->cnC[i + 1]) & mask;
+        const unsigned r24 = (unsigned)(st >> 24);
+        const float u = ((float)r24 / 16777216.0f) * 2.0f - 1.0f;
+        acc[c] = u * gain;
+    }
+    rng.comfort = (T->cnA[160] * s0 + T->cnC[160]) & mask;
+}
+
+// ---- white noise with overlap (mbe_unvoiced_fft.c:304-341) --------------------------------------
+__device__ __forceinline__ void make_noise(WarpWS& ws, StreamRng& rng, const DevTables* T, int lane) {
+    Parms& cur = ws.cur;
+    const float seed = cur.noiseSeed;
+    if (seed < 0.0f) {
+        for (int i = lane; i < NFFT; i += 32) {
+            ws.noise[i] = 0.0f;
+        }
+        for (int i = lane; i < 96; i += 32) {
+            cur.noiseOverlap[i] = 0.0f;
+        }
+        float ns;
+        if (rng.uv_override) {
+            ns = (float)rng.uv_seed;
+            rng.uv_override = 0;
+        } else {
+            ns = 3147.0f;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            cur.noiseSeed = ns;
+        }
+        __syncwarp();
+        return;
+    }
+    const unsigned st0 = ((unsigned)seed) % 53125u;
+    for (int i = lane; i < 96; i += 32) {
+        ws.noise[i] = cur.noiseOverlap[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const int i = 32 * c + lane;
+        const unsigned st = (T->uvA[i] * st0 + T->uvC[i]) % 53125u;
+        const float v = (float)st;
+        ws.noise[96 + i] = v;
+        if (i >= 64) {
+            cur.noiseOverlap[i - 64] = v;  // overlap <- buffer[160..255]
+        }
+    }
+    const unsigned stn = (T->uvA[160] * st0 + T->uvC[160]) % 53125u;
+    __syncwarp();
+    if (lane == 0) {
+        cur.noiseSeed = (float)stn;
+    }
+    __syncwarp();
+}
+
+// ---- 256-point real FFT: FFTPACK radix-4 passes, lanes over butterflies -------------------------
+__device__ __forceinline__ void rfft_fwd4(int ido, int l1, const float* in, float* out, const float* w1,
+                                          const float* w2, const float* w3, int lane) {
+#define FIN(i, k, j)  in[(i) + ido * ((k) + l1 * (j))]
+#define FOUT(i, j, k) out[(i) + ido * ((j) + 4 * (k))]
+    const float nhs2 = -0.70710678118654752440f;
+    for (int k = lane; k < l1; k += 32) {
+        float a0 = FIN(0, k, 0), a1 = FIN(0, k, 1), a2 = FIN(0, k, 2), a3 = FIN(0, k, 3);
+        float tr1 = a1 + a3;
+        float tr2 = a0 + a2;
+        FOUT(ido - 1, 1, k) = a0 - a2;
+        FOUT(0, 2, k) = a3 - a1;
+        FOUT(0, 0, k) = tr1 + tr2;
+        FOUT(ido - 1, 3, k) = tr2 - tr1;
+    }
+    if (ido >= 2) {
+        const int ni = ido / 2 - 1;
+        for (int it = lane; it < l1 * ni; it += 32) {
+            const int k = it / ni;
+            const int i = 2 + 2 * (it - k * ni);
+            const int ic = ido - i;
+            float cr2 = FIN(i - 1, k, 1), ci2 = FIN(i, k, 1);
+            float cr3 = FIN(i - 1, k, 2), ci3 = FIN(i, k, 2);
+            float cr4 = FIN(i - 1, k, 3), ci4 = FIN(i, k, 3);
+            float t;
+            t = cr2 * w1[i - 1];
+            cr2 = (cr2 * w1[i - 2]) + (ci2 * w1[i - 1]);
+            ci2 = (ci2 * w1[i - 2]) - t;
+            t = cr3 * w2[i - 1];
+            cr3 = (cr3 * w2[i - 2]) + (ci3 * w2[i - 1]);
+            ci3 = (ci3 * w2[i - 2]) - t;
+            t = cr4 * w3[i - 1];
+            cr4 = (cr4 * w3[i - 2]) + (ci4 * w3[i - 1]);
+            ci4 = (ci4 * w3[i - 2]) - t;
+            const float x0r = FIN(i - 1, k, 0), x0i = FIN(i, k, 0);
+            const float tr1 = cr2 + cr4, tr4 = cr4 - cr2;
+            const float tr2 = x0r + cr3, tr3 = x0r - cr3;
+            FOUT(i - 1, 0, k) = tr1 + tr2;
+            FOUT(ic - 1, 3, k) = tr2 - tr1;
+            const float ti1 = ci2 + ci4, ti4 = ci2 - ci4;
+            FOUT(i - 1, 2, k) = ti4 + tr3;
+            FOUT(ic - 1, 1, k) = tr3 - ti4;
+            const float ti2 = x0i + ci3, ti3 = x0i - ci3;
+            FOUT(i, 0, k) = ti1 + ti2;
+            FOUT(ic, 3, k) = ti1 - ti2;
+            FOUT(i, 2, k) = tr4 + ti3;
+            FOUT(ic, 1, k) = tr4 - ti3;
+        }
+        for (int k = lane; k < l1; k += 32) {
+            float a = FIN(ido - 1, k, 1), b = FIN(ido - 1, k, 3);
+            float c = FIN(ido - 1, k, 0), d = FIN(ido - 1, k, 2);
+            float ti1 = nhs2 * (a + b);
+            float tr1 = nhs2 * (b - a);
+            FOUT(ido - 1, 0, k) = tr1 + c;
+            FOUT(ido - 1, 2, k) = c - tr1;
+            FOUT(0, 1, k) = ti1 - d;
+            FOUT(0, 3, k) = ti1 + d;
+        }
+    }
+    __syncwarp();
+#undef FIN
+#undef FOUT
+}
+
+__device__ __forceinline__ void rfft_bwd4(int ido, int l1, const float* in, float* out, const float* w1,
+                                          const float* w2, const float* w3, int lane) {
+#define BIN(i, j, k)  in[(i) + ido * ((j) + 4 * (k))]
+#define BOUT(i, k, j) out[(i) + ido * ((k) + l1 * (j))]
+    const float nsq2 = -1.41421356237309504880f;
+    for (int k = lane; k < l1; k += 32) {
+        float a = BIN(0, 0, k), b = BIN(ido - 1, 3, k), c = BIN(0, 2, k), d = BIN(ido - 1, 1, k);
+        float tr3 = 2.f * d;
+        float tr2 = a + b;
+        float tr1 = a - b;
+        float tr4 = 2.f * c;
+        BOUT(0, k, 0) = tr2 + tr3;
+        BOUT(0, k, 2) = tr2 - tr3;
+        BOUT(0, k, 1) = tr1 - tr4;
+        BOUT(0, k, 3) = tr1 + tr4;
+    }
+    if (ido >= 2) {
+        const int ni = ido / 2 - 1;
+        for (int it = lane; it < l1 * ni; it += 32) {
+            const int k = it / ni;
+            const int i = 2 + 2 * (it - k * ni);
+            const int ic = ido - i;
+            float tr1 = BIN(i - 1, 0, k) - BIN(ic - 1, 3, k);
+            float tr2 = BIN(i - 1, 0, k) + BIN(ic - 1, 3, k);
+            float ti4 = BIN(i - 1, 2, k) - BIN(ic - 1, 1, k);
+            float tr3 = BIN(i - 1, 2, k) + BIN(ic - 1, 1, k);
+            BOUT(i - 1, k, 0) = tr2 + tr3;
+            float cr3 = tr2 - tr3;
+            float ti3 = BIN(i, 2, k) - BIN(ic, 1, k);
+            float tr4 = BIN(i, 2, k) + BIN(ic, 1, k);
+            float cr2 = tr1 - tr4;
+            float cr4 = tr1 + tr4;
+            float ti1 = BIN(i, 0, k) + BIN(ic, 3, k);
+            float ti2 = BIN(i, 0, k) - BIN(ic, 3, k);
+            BOUT(i, k, 0) = ti2 + ti3;
+            float ci3 = ti2 - ti3;
+            float ci2 = ti1 + ti4;
+            float ci4 = ti1 - ti4;
+            float t;
+            t = cr2 * w1[i - 1];
+            cr2 = (cr2 * w1[i - 2]) - (ci2 * w1[i - 1]);
+            ci2 = (ci2 * w1[i - 2]) + t;
+            BOUT(i - 1, k, 1) = cr2;
+            BOUT(i, k, 1) = ci2;
+            t = cr3 * w2[i - 1];
+            cr3 = (cr3 * w2[i - 2]) - (ci3 * w2[i - 1]);
+            ci3 = (ci3 * w2[i - 2]) + t;
+            BOUT(i - 1, k, 2) = cr3;
+            BOUT(i, k, 2) = ci3;
+            t = cr4 * w3[i - 1];
+            cr4 = (cr4 * w3[i - 2]) - (ci4 * w3[i - 1]);
+            ci4 = (ci4 * w3[i - 2]) + t;
+            BOUT(i - 1, k, 3) = cr4;
+            BOUT(i, k, 3) = ci4;
+        }
+        for (int k = lane; k < l1; k += 32) {
+            float c = BIN(ido - 1, 0, k), d = BIN(ido - 1, 2, k);
+            float a = BIN(0, 1, k), b = BIN(0, 3, k);
+            float tr1 = c - d;
+            float tr2 = c + d;
+            float ti1 = b + a;
+            float ti2 = b - a;
+            BOUT(ido - 1, k, 0) = tr2 + tr2;
+            BOUT(ido - 1, k, 1) = nsq2 * (ti1 - tr1);
+            BOUT(ido - 1, k, 2) = ti2 + ti2;
+            BOUT(ido - 1, k, 3) = nsq2 * (ti1 + tr1);
+        }
+    }
+    __syncwarp();
+#undef BIN
+#undef BOUT
+}
+
+// ---- unvoiced synthesis (mbe_unvoiced_fft.c:714-761); adds into acc[] and writes cur.previousUw --
+// Spectrum is kept in FFTPACK's native layout F[0]=DC, F[2b-1]=Re(b), F[2b]=Im(b), F[255]=Nyquist; the
+// reference's "ordered" layout is only a permutation of it, so no reorder pass is needed.
+__device__ __forceinline__ void unvoiced_synthesis(float acc[5], WarpWS& ws, const DevTables* T, const float* tw,
+                                                   int lane) {
+    Parms& cur = ws.cur;
+    const Parms& prev = ws.enh;
+    if (!bands_ok(cur.L) || !bands_ok(prev.L)) {
+        return;
+    }
+    float* A = ws.u.fft.a;
+    float* B = ws.u.fft.b;
+    float* scale = ws.u.fft.scale;
+    for (int i = lane; i < NFFT; i += 32) {
+        A[i] = ws.noise[i] * T->uvwin[i];
+    }
+    for (int i = lane; i < 129; i += 32) {
+        scale[i] = 0.0f;
+    }
+    __syncwarp();
+    rfft_fwd4(1, 64, A, B, tw + 252, tw + 253, tw + 254, lane);
+    rfft_fwd4(4, 16, B, A, tw + 240, tw + 244, tw + 248, lane);
+    rfft_fwd4(16, 4, A, B, tw + 192, tw + 208, tw + 224, lane);
+    rfft_fwd4(64, 1, B, A, tw + 0, tw + 64, tw + 128, lane);
+
+    const int L = cur.L;
+    const float mult = (256.0f / (2.0f * 3.14159265358979323846f)) * cur.w0;
+    for (int l = 1 + lane; l <= L; l += 32) {
+        int a = (int)ceilf((l - 0.5f) * mult);
+        int b = (int)ceilf((l + 0.5f) * mult);
+        if (a < 0) {
+            a = 0;
+        }
+        if (b > NFFT / 2) {
+            b = NFFT / 2;
+        }
+        if (cur.Vl[l] == 0 && b > a) {
+            float num = 0.0f;
+            int s = a;
+            if (s == 0) {
+                num += A[0] * A[0];
+                s = 1;
+            }
+            for (int bin = s; bin < b; ++bin) {
+                const float re = A[2 * bin - 1], im = A[2 * bin];
+                num += (re * re) + (im * im);
+            }
+            if (num > 1e-10f) {
+                const float sc = 146.17696f * cur.Ml[l] / sqrtf(num / (float)(b - a));
+                for (int bin = a; bin < b; ++bin) {
+                    scale[bin] = sc;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // per-bin scaling; bin 128 (Nyquist) is never covered by a band, so its scale stays 0
+    for (int i = lane; i < NFFT; i += 32) {
+        const int bin = (i == 0) ? 0 : ((i == NFFT - 1) ? NFFT / 2 : (i + 1) >> 1);
+        A[i] *= scale[bin];
+    }
+    __syncwarp();
+    rfft_bwd4(64, 1, A, B, tw + 0, tw + 64, tw + 128, lane);
+    rfft_bwd4(16, 4, B, A, tw + 192, tw + 208, tw + 224, lane);
+    rfft_bwd4(4, 16, A, B, tw + 240, tw + 244, tw + 248, lane);
+    rfft_bwd4(1, 64, B, A, tw + 252, tw + 253, tw + 254, lane);
+    const float inv = 1.0f / (float)NFFT;
+    for (int i = lane; i < NFFT; i += 32) {
+        A[i] *= inv;
+    }
+    __syncwarp();
+    // weighted overlap-add with the previous frame's inverse transform
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const int n = 32 * c + lane;
+        const float den = T->wola_den[n];
+        const float ps = (n + 128 < NFFT) ? prev.previousUw[n + 128] : 0.0f;
+        const float cs = (n - 32 >= 0) ? A[n - 32] : 0.0f;
+        if (den > 1e-10f) {
+            acc[c] += ((T->wola_wp[n] * ps) + (T->wola_wc[n] * cs)) / den;
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < NFFT; i += 32) {
+        cur.previousUw[i] = A[i];
+    }
+    __syncwarp();
+}
+
+// ---- voiced oscillator bank (mbelib.c:953-1040) --------------------------------------------------
+// kinds: 0 = previous-frame windowed component, 1 = current-frame windowed component,
+//        2 = phase/amplitude-interpolated harmonic (l < 8, both voiced, stable pitch)
+__device__ __forceinline__ void voiced_bank(float acc[5], WarpWS& ws, const DevTables* T, int maxl, int lane) {
+    const Parms& cur = ws.cur;
+    const Parms& prev = ws.enh;
+    const float cw0 = cur.w0, pw0 = prev.w0;
+    const bool stable = fabsf(cw0 - pw0) < (0.1f * cw0);
+
+    // ordered component list
+    int ncomp = 0;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int l = 1 + lane + 32 * r;
+        bool cv = false, pv = false;
+        if (l <= maxl) {
+            cv = (cur.Vl[l] == 1);
+            pv = (prev.Vl[l] == 1);
+        }
+        const bool interp = (l < 8) && cv && pv && stable;
+        const bool first = pv || interp;          // first slot of this harmonic
+        const bool second = cv && !interp;        // second slot
+        const unsigned mf = __ballot_sync(FULL, first);
+        const unsigned ms = __ballot_sync(FULL, second);
+        const unsigned lt = (1u << lane) - 1u;
+        int idx = ncomp + __popc(mf & lt) + __popc(ms & lt);
+        if (first) {
+            ws.comp[idx] = (unsigned char)((l << 2) | (interp ? 2 : 0));
+            ws.gain[idx] = 2.0f * prev.Ml[l];
+            idx++;
+        }
+        if (second) {
+            ws.comp[idx] = (unsigned char)((l << 2) | 1);
+            ws.gain[idx] = 2.0f * cur.Ml[l];
+        }
+        ncomp += __popc(mf) + __popc(ms);
+    }
+    __syncwarp();
+
+    const float* Wv = T->voiced_win;
+    float* tile = ws.u.tile;
+    for (int g0 = 0; g0 < ncomp; g0 += 32) {
+        const int cnt = min(32, ncomp - g0);
+        // oscillator owned by this lane
+        float c = 0.f, s = 0.f, cd = 0.f, sd = 0.f;
+        const bool osc = (lane < cnt) && ((ws.comp[g0 + lane] & 3) != 2);
+        if (osc) {
+            const int id = ws.comp[g0 + lane];
+            const int l = id >> 2;
+            float step, ph;
+            if ((id & 3) == 0) {
+                step = pw0 * (float)l;
+                ph = prev.PHIl[l];
+            } else {
+                step = cw0 * (float)l;
+                ph = cur.PHIl[l] - (step * (float)NS);
+            }
+            mbelibm::sincosf_glibc(step, &sd, &cd);
+            mbelibm::sincosf_glibc(ph, &s, &c);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 5; ++ch) {
+            if (osc) {
+#pragma unroll 8
+                for (int n = 0; n < 32; ++n) {
+                    tile[n * TILE_STRIDE + lane] = c;
+                    const float cn = (c * cd) - (s * sd);
+                    const float sn = (s * cd) + (c * sd);
+                    c = cn;
+                    s = sn;
+                }
+            }
+            __syncwarp();
+            const int n = 32 * ch + lane;
+            const float Wp = Wv[n + NS], Wc = Wv[n];
+            float a = acc[ch];
+            for (int j = 0; j < cnt; ++j) {
+                const int id = ws.comp[g0 + j];
+                const int kind = id & 3;
+                if (kind == 2) {
+                    const int l = id >> 2;
+                    const float pw0l = pw0 * (float)l;
+                    const float dphi = cur.PHIl[l] - prev.PHIl[l] - (((pw0 + cw0) * (float)(l * NS)) / 2.0f);
+                    const float dw = (1.0f / (float)NS)
+                                     * (dphi - (2.0f * MBE_PI_F * floorf((dphi + MBE_PI_F) / (2.0f * MBE_PI_F))));
+                    const float th = prev.PHIl[l] + ((pw0l + dw) * (float)n)
+                                     + (((cw0 - pw0) * (float)(l * n * n)) / (float)(2 * NS));
+                    const float am = prev.Ml[l] + (((float)n / (float)NS) * (cur.Ml[l] - prev.Ml[l]));
+                    a += 2.0f * am * mbelibm::cosf_glibc(th);
+                } else {
+                    const float gw = ws.gain[g0 + j] * (kind ? Wc : Wp);
+                    a += gw * tile[lane * TILE_STRIDE + j];
+                }
+            }
+            acc[ch] = a;
+            __syncwarp();
+        }
+    }
+}
+
+// ---- mbe_synthesizeSpeechCore (mbelib.c:1042-1105): cur = ws.cur, prev = ws.enh ------------------
+// returns with the 160 float samples in acc[]
+__device__ __forceinline__ void synthesize_speech(float acc[5], WarpWS& ws, StreamRng& rng, const DevTables* T,
+                                                  const float* tw, int has_rm0, float rm0, int lane) {
+    Parms& cur = ws.cur;
+    Parms& prev = ws.enh;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        acc[c] = 0.0f;
+    }
+    if (!bands_ok(cur.L) || !bands_ok(prev.L)) {
+        return;  // silence
+    }
+    adaptive_smoothing(cur, prev, has_rm0, rm0, lane);
+
+    const bool mute_on_rate = fabsf(cur.mutingThreshold - 0.096f) > 1e-6f;
+    if (cur.repeatCount >= 4 || (mute_on_rate && cur.errorRate > cur.mutingThreshold)) {
+        comfort_noise(acc, rng, T, lane);
+        return;
+    }
+    make_noise(ws, rng, T, lane);
+
+    // bands present in only one frame fade as zero-amplitude voiced bands (mbelib.c:912-929)
+    int maxl;
+    const int cL = cur.L, pL = prev.L;
+    if (cL > pL) {
+        maxl = cL;
+        for (int l = pL + 1 + lane; l <= maxl; l += 32) {
+            prev.Ml[l] = 0.0f;
+            prev.Vl[l] = 1;
+        }
+    } else {
+        maxl = pL;
+        for (int l = cL + 1 + lane; l <= maxl; l += 32) {
+            cur.Ml[l] = 0.0f;
+            cur.Vl[l] = 1;
+        }
+    }
+    __syncwarp();
+
+    // numUv counts index 0 as well (mbelib.c:902-910)
+    int numUv = 0;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int l = lane + 32 * r;
+        const bool uv = (l <= cL) && (cur.Vl[l] == 0);
+        numUv += __popc(__ballot_sync(FULL, uv));
+    }
+
+    // phase update for all 56 harmonics (mbelib.c:931-951)
+    const float cw0 = cur.w0, pw0 = prev.w0;
+    const float two_pi = 2.0f * MBE_PI_F;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int l = 1 + lane + 32 * r;
+        if (l <= 56) {
+            float wrapped = fmodf(prev.PSIl[l], two_pi);
+            if (wrapped < 0.0f) {
+                wrapped += two_pi;
+            }
+            prev.PSIl[l] = wrapped;
+            const float psi = wrapped + ((pw0 + cw0) * ((float)(l * NS) / 2.0f));
+            cur.PSIl[l] = psi;
+            if (l <= (cL / 4)) {
+                cur.PHIl[l] = psi;
+            } else {
+                const float pl = ((2.0f * MBE_PI_F / 53125.0f) * ws.noise[l]) - MBE_PI_F;
+                cur.PHIl[l] = psi + (((float)numUv * pl) / (float)cL);
+            }
+        }
+    }
+    __syncwarp();
+
+    voiced_bank(acc, ws, T, maxl, lane);
+    unvoiced_synthesis(acc, ws, T, tw, lane);
+
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        float v = acc[c];
+        if (v > MBE_CLIP_F) {
+            v = MBE_CLIP_F;
+        } else if (v < -MBE_CLIP_F) {
+            v = -MBE_CLIP_F;
+        }
+        acc[c] = v;
+    }
+}
+
+// ---- tone synthesis (mbelib.c:692-856, src/internal/mbe_tone.h) -----------------------------------
+__device__ __forceinline__ bool tone_freqs(int id, float* f1, float* f2) {
+    const unsigned short dual[36][2] = {
+        {1336, 941}, {1209, 697}, {1336, 697}, {1477, 697}, {1209, 770}, {1336, 770}, {1477, 770}, {1209, 852},
+        {1336, 852}, {1477, 852}, {1633, 697}, {1633, 770}, {1633, 852}, {1633, 941}, {1209, 941}, {1477, 941},
+        {1162, 820}, {1052, 606}, {1162, 606}, {1279, 606}, {1052, 672}, {1162, 672}, {1279, 672}, {1052, 743},
+        {1162, 743}, {1279, 743}, {1430, 606}, {1430, 672}, {1430, 743}, {1430, 820}, {1052, 820}, {1279, 820},
+        {440, 350},  {480, 440},  {620, 480},  {490, 350}};
+    *f1 = *f2 = 0.0f;
+    if (id == 5) {
+        *f1 = *f2 = 156.25f;
+        return true;
+    }
+    if (id == 6) {
+        *f1 = *f2 = 187.5f;
+        return true;
+    }
+    if (id >= 7 && id <= 122) {
+        *f1 = *f2 = 31.25f * (float)id;
+        return true;
+    }
+    if (id >= 128 && id <= 163) {
+        *f1 = (float)dual[id - 128][0];
+        *f2 = (float)dual[id - 128][1];
+        return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ unsigned tone_step(double hz) {
+    double st = (hz / 8000.0) * 4294967296.0;
+    return st <= 0.0 ? 0u : (unsigned)(st + 0.5);
+}
+
+__device__ __forceinline__ float tone_sample(unsigned phase) {
+    const double rad_per_tick = (2.0 * 3.14159265358979323846) / 4294967296.0;
+    float ang = (float)(((double)phase * rad_per_tick) - (3.14159265358979323846 / 2.0));
+    return mbelibm::sinf_glibc(ang);
+}
+
+__device__ __forceinline__ void render_tone(float acc[5], Parms& cur, float f1, float f2, int amp, int lane) {
+    if (f1 <= 0.0f) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            acc[c] = 0.0f;
+        }
+        return;
+    }
+    const bool dual = (f2 > 0.0f) && (fabsf(f2 - f1) > 1e-6f);
+    const float gain = (((amp < 0) ? 0.0f : (float)amp) / 127.0f) * MBE_CLIP_F;
+    const unsigned s1 = tone_step((double)f1);
+    const unsigned s2 = dual ? tone_step((double)f2) : 0u;
+    const unsigned p1 = (unsigned)cur.swn, p2 = cur.tonePhase;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const unsigned n1 = (unsigned)(32 * c + lane + 1);
+        const float a = tone_sample(p1 + n1 * s1);
+        if (dual) {
+            const float b = tone_sample(p2 + n1 * s2);
+            acc[c] = (0.5f * gain * a) + (0.5f * gain * b);
+        } else {
+            acc[c] = gain * a;
+        }
+    }
+    if (lane == 0) {
+        cur.swn = (int)(p1 + 160u * s1);
+        cur.tonePhase = p2 + 160u * s2;
+    }
+    __syncwarp();
+}
+
+// mbe_floattoshort (mbelib.c:1148-1177,1312-1320): x7, clip to 95 % full scale, truncate
+__device__ __forceinline__ short float_to_short(float x) {
+    const float maxa = 32767.0f * 0.95f;
+    const unsigned u = __float_as_uint(x);
+    const unsigned a = u & 0x7fffffffu;
+    float v;
+    if (a > 0x7f800000u) {
+        v = 0.0f;
+    } else if (a == 0x7f800000u) {
+        v = (u >> 31) ? -maxa : maxa;
+    } else {
+        v = 7.0f * x;
+        if (v > maxa) {
+            v = maxa;
+        } else if (v < -maxa) {
+            v = -maxa;
+        }
+    }
+    return (short)(int)v;
+}
+
+}  // namespace mbe

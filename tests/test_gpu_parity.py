@@ -1,0 +1,259 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI, libmbe_b200.so) against the CPU oracle on the
+same seeded inputs.  Bars (BASELINE.json north_star):
+  - ECC error counts, result flags and decoded parameter bits: bit-exact;
+  - int16 PCM: max |delta| <= 2 LSB and >= 99.99 % of samples exact (tolerance stated here);
+  - final mbe_parms triplets: integer fields exact, float fields compared bitwise and reported."""
+import numpy as np
+import pytest
+
+import mbe_testlib as T
+from __graft_entry__ import load_package
+
+pytestmark = pytest.mark.gpu
+
+PCM_MAX_LSB = 2
+PCM_EXACT_FRACTION = 0.9999
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return load_package()
+
+
+@pytest.fixture(scope="module")
+def dec(pkg):
+    d = pkg.Decoder(max_streams=4096, device=0)
+    yield d
+    d.close()
+
+
+def check_batch(dec, codec, soft, frames, seeds, strict_state=True):
+    S = frames.shape[0]
+    dec.init_streams(0, S, seeds)
+    got = dec.process_frames(codec, frames, soft=soft, want_float=True)
+    want = T.run_cpu(T.load_oracle().mbo_run, codec, soft, frames, seeds, n_threads=8)
+    res = got["results"]
+    assert np.array_equal(res["status"], want["results"][..., 0])
+    assert np.array_equal(got["bits"], want["bits"])
+    assert np.array_equal(res["c0_errors"], want["results"][..., 1])
+    assert np.array_equal(res["protected_errors"], want["results"][..., 2])
+    assert np.array_equal(res["c4_errors"], want["results"][..., 3])
+    assert np.array_equal(res["total_errors"], want["results"][..., 4])
+    assert np.array_equal(res["flags"].astype(np.int64), want["results"][..., 5].astype(np.int64) & 0xffffffff)
+    d = np.abs(got["pcm"].astype(np.int32) - want["pcm"].astype(np.int32))
+    exact = float((d == 0).mean())
+    assert d.max() <= PCM_MAX_LSB, "max |delta| = %d LSB" % d.max()
+    assert exact >= PCM_EXACT_FRACTION, "only %.6f of samples exact" % exact
+    st = dec.export_state(0, S)
+    state_equal = np.array_equal(st, want["state"])
+    if strict_state:
+        # integer fields of the final state must match exactly
+        for k in range(3):
+            for s in range(0, S, max(1, S // 16)):
+                a, b = T.parms_view(st[s, k]), T.parms_view(want["state"][s, k])
+                for name in ("L", "K", "repeatCount", "errorCountTotal", "errorCount4", "amplitudeThreshold", "swn"):
+                    assert a[name] == b[name], (name, s, k)
+                assert np.array_equal(a["Vl"], b["Vl"])
+    fexact = float((got["pcmf"].view(np.uint32) == want["pcmf"].view(np.uint32)).mean())
+    return dict(exact=exact, maxd=int(d.max()), float_exact=fexact, state_equal=state_equal)
+
+
+@pytest.mark.parametrize("codec", [0, 1, 2, 3])
+def test_random_hard_frames(dec, codec):
+    frames = T.random_hard_frames(codec, 512, 50, 100 + codec)
+    r = check_batch(dec, codec, 0, frames, T.stream_seeds(512))
+    print(T.CODEC_NAMES[codec], r)
+
+
+@pytest.mark.parametrize("codec", [0, 1, 2, 3])
+def test_random_soft_frames(dec, codec):
+    rng = np.random.default_rng(200 + codec)
+    n = 16 if codec < 2 else 64
+    bits = T.random_hard_frames(codec, n, 8, 210 + codec)
+    rel = rng.integers(0, 256, size=bits.shape, dtype=np.uint8)
+    r = check_batch(dec, codec, 1, np.stack([bits, rel], axis=-1), T.stream_seeds(n, 77))
+    print(T.CODEC_NAMES[codec], r)
+
+
+@pytest.mark.parametrize("codec,ber", [(3, 0.0), (3, 0.03), (2, 0.0), (2, 0.02), (0, 0.0), (0, 0.03)])
+def test_encoded_voice_frames(dec, codec, ber):
+    rng = np.random.default_rng(300 + codec + int(ber * 1000))
+    S, F = 64, 50
+    enc = T.encode_imbe7200_frame if codec == 0 else T.encode_ambe_frame
+    frames = np.zeros((S, F, T.FRAME_BITS[codec]), np.uint8)
+    for s in range(S):
+        for f in range(F):
+            p = rng.integers(0, 2, size=T.PARAM_BITS[codec], dtype=np.uint8)
+            if codec == 0:
+                p[0] = 0
+            frames[s, f] = enc(p).reshape(-1)
+    frames ^= (rng.random(frames.shape) < ber).astype(np.uint8)
+    r = check_batch(dec, codec, 0, frames, T.stream_seeds(S, 5))
+    print(T.CODEC_NAMES[codec], ber, r)
+
+
+def test_ambe2400_tones_and_unvoiced(dec):
+    rng = np.random.default_rng(4242)
+    S, F = 96, 40
+    frames = np.zeros((S, F, 96), np.uint8)
+    for s in range(S):
+        for f in range(F):
+            p = rng.integers(0, 2, size=49, dtype=np.uint8)
+            if (s + f // 5) % 3 == 0:
+                p[0:6] = 1
+            elif s % 2:
+                p[38:42] = 1
+            frames[s, f] = T.encode_ambe_frame(p).reshape(-1)
+    r = check_batch(dec, T.AMBE2400, 0, frames, T.stream_seeds(S, 9))
+    print(r)
+
+
+def test_ambe2450_tone_frames(dec):
+    rng = np.random.default_rng(777)
+    S, F = 64, 24
+    frames = np.zeros((S, F, 96), np.uint8)
+    for s in range(S):
+        for f in range(F):
+            p = rng.integers(0, 2, size=49, dtype=np.uint8)
+            if f % 4 == 1:
+                p[0:6] = 1
+                p[45:49] = 0
+                tid = int(rng.integers(0, 200))
+                p[12:20] = [(tid >> (7 - i)) & 1 for i in range(8)]
+            frames[s, f] = T.encode_ambe_frame(p).reshape(-1)
+    r = check_batch(dec, T.AMBE2450, 0, frames, T.stream_seeds(S, 3))
+    print(r)
+
+
+def test_soft_encoded_frames_with_flips(dec):
+    rng = np.random.default_rng(555)
+    for codec, S in ((0, 12), (3, 48)):
+        F = 10
+        enc = T.encode_imbe7200_frame if codec == 0 else T.encode_ambe_frame
+        hard = np.zeros((S, F, T.FRAME_BITS[codec]), np.uint8)
+        for s in range(S):
+            for f in range(F):
+                p = rng.integers(0, 2, size=T.PARAM_BITS[codec], dtype=np.uint8)
+                p[0] = 0
+                hard[s, f] = enc(p).reshape(-1)
+        soft = T.soften(hard, rng, flip_p=0.10)
+        r = check_batch(dec, codec, 1, soft, T.stream_seeds(S, 11))
+        print(T.CODEC_NAMES[codec], r)
+
+
+def test_invalid_bits_are_flagged_and_state_untouched(dec):
+    frames = T.random_hard_frames(3, 8, 4, 31)
+    frames[2, 1, 5] = 7            # not 0/1 -> MBE_STATUS_INVALID_BITS for that frame only
+    seeds = T.stream_seeds(8)
+    dec.init_streams(0, 8, seeds)
+    got = dec.process_frames(3, frames, want_float=True)
+    want = T.run_cpu(T.load_oracle().mbo_run, 3, 0, frames, seeds)
+    assert got["results"]["status"][2, 1] == -2
+    assert np.array_equal(got["results"]["status"], want["results"][..., 0])
+    assert (got["pcm"][2, 1] == 0).all()
+    d = np.abs(got["pcm"].astype(np.int32) - want["pcm"].astype(np.int32))
+    assert d.max() <= PCM_MAX_LSB
+
+
+def test_state_survives_split_launches(dec):
+    """50 frames in one launch == 5 launches of 10 frames (state round-trips through HBM)."""
+    frames = T.random_hard_frames(0, 64, 50, 909)
+    seeds = T.stream_seeds(64)
+    dec.init_streams(0, 64, seeds)
+    a = dec.process_frames(0, frames)
+    dec.init_streams(0, 64, seeds)
+    parts = [dec.process_frames(0, frames[:, i:i + 10])["pcm"] for i in range(0, 50, 10)]
+    assert np.array_equal(a["pcm"], np.concatenate(parts, axis=1))
+
+
+def test_export_import_roundtrip(dec):
+    frames = T.random_hard_frames(2, 32, 12, 77)
+    seeds = T.stream_seeds(32)
+    dec.init_streams(0, 32, seeds)
+    dec.process_frames(2, frames[:, :6])
+    st, rng = dec.export_state(0, 32), dec.export_rng(0, 32)
+    a = dec.process_frames(2, frames[:, 6:])["pcm"]
+    dec.import_state(st, 0)
+    dec.import_rng(rng, 0)
+    b = dec.process_frames(2, frames[:, 6:])["pcm"]
+    assert np.array_equal(a, b)
+
+
+def test_golden_pcm_fixture(dec):
+    """tests/test_golden_pcm.c of the reference: one synthetic frame through mbe_synthesizeSpeechf +
+    mbe_floattoshort; float hash 0x59741032 (scalar builds), int16 hash 0x4EDB8636."""
+    o = T.load_oracle()
+    cur = np.zeros((1, T.PARMS_BYTES), np.uint8)
+    prev = np.zeros((1, T.PARMS_BYTES), np.uint8)
+    enh = np.zeros((1, T.PARMS_BYTES), np.uint8)
+    o.mbo_init_parms(T._ptr(cur), T._ptr(prev), T._ptr(enh))
+    f, i = cur.view(np.float32).reshape(-1), cur.view(np.int32).reshape(-1)
+    f[0] = np.float32(0.105)
+    i[1] = 36
+    for l in range(1, 37):
+        i[3 + l] = 1 if l % 4 else 0
+        f[60 + l] = np.float32(0.035) + np.float32(0.0015) * np.float32(l)
+        f[174 + l] = np.float32(l) * np.float32(0.03)
+        f[231 + l] = np.float32(l) * np.float32(0.02)
+    prev[:] = cur
+    # a batch of identical fixtures: every element must give the golden output
+    n = 40
+    curs, prevs = np.repeat(cur, n, axis=0).copy(), np.repeat(prev, n, axis=0).copy()
+    pcmf, pcm = dec.synthesize_speech(curs, prevs, seeds=np.full(n, 0xC0FFEE, np.uint32))
+    for k in (0, n - 1):
+        assert T.fnv1a32(pcm[k].tobytes()) == 0x4EDB8636
+        assert T.fnv1a32(pcmf[k].tobytes()) == 0x59741032
+    assert (pcm == pcm[0]).all()
+
+
+def test_floattoshort_edges(dec):
+    """tests/test_floattoshort_parity.c: clip edges, NaN -> 0, +-Inf -> +-clip, truncation."""
+    x = np.zeros(160, np.float32)
+    edge = [0.0, -0.0, 1.0, -1.0, 4446.9, 4447.0, 4447.1, -4447.1, 1e9, -1e9, np.nan, np.inf, -np.inf, 0.14, -0.14,
+            4681.0, -4681.0, 123.456, -123.456, 0.999 / 7]
+    x[:len(edge)] = edge
+    rng = np.random.default_rng(5)
+    x[len(edge):] = rng.normal(0, 3000, 160 - len(edge)).astype(np.float32)
+    got = dec.floattoshort(x)[0]
+    want = np.zeros(160, np.int16)
+    T.load_oracle().mbo_float_to_short(T._ptr(x), T._ptr(want))
+    assert np.array_equal(got, want)
+
+
+def test_staged_decode_then_data_equals_frame_path(dec):
+    """mbe_decode*Frame followed by mbe_process*Data == mbe_process*Frame (README staged API)."""
+    for codec in (0, 3):
+        frames = T.random_hard_frames(codec, 48, 20, 1200 + codec)
+        seeds = T.stream_seeds(48)
+        dec.init_streams(0, 48, seeds)
+        a = dec.process_frames(codec, frames)
+        bits, res = dec.decode_frames(codec, frames)
+        assert np.array_equal(bits.reshape(48, 20, -1), a["bits"])
+        dec.init_streams(0, 48, seeds)
+        b = dec.process_data(codec, bits.reshape(48, 20, -1), results=res.reshape(48, 20))
+        assert np.array_equal(a["pcm"], b["pcm"])
+        assert np.array_equal(a["results"]["flags"], b["results"]["flags"])
+
+
+def test_process_data_without_context_uses_fallback_repeat_rules(dec):
+    """result == NULL semantics (T4): no C0 context -> total-error fallback; with zero errors no repeats."""
+    codec = 3
+    frames = T.random_hard_frames(codec, 16, 10, 5150)
+    bits, _ = dec.decode_frames(codec, frames)
+    seeds = T.stream_seeds(16)
+    dec.init_streams(0, 16, seeds)
+    got = dec.process_data(codec, bits.reshape(16, 10, -1), results=None)
+    o = T.load_oracle()
+    # oracle: per stream, mbo_process_data with result = NULL
+    import ctypes
+    for s in range(16):
+        cur = np.zeros(T.PARMS_BYTES, np.uint8); prev = cur.copy(); enh = cur.copy()
+        rng = np.zeros(16, np.uint8)
+        o.mbo_rng_default(T._ptr(rng)); o.mbo_rng_seed(T._ptr(rng), ctypes.c_uint32(int(seeds[s])))
+        o.mbo_init_parms(T._ptr(cur), T._ptr(prev), T._ptr(enh))
+        for f in range(10):
+            out = np.zeros(160, np.float32); sh = np.zeros(160, np.int16)
+            d = np.ascontiguousarray(bits.reshape(16, 10, -1)[s, f])
+            o.mbo_process_data(codec, T._ptr(out), None, T._ptr(d), T._ptr(cur), T._ptr(prev), T._ptr(enh), T._ptr(rng))
+            o.mbo_float_to_short(T._ptr(out), T._ptr(sh))
+            assert np.abs(sh.astype(np.int32) - got["pcm"][s, f].astype(np.int32)).max() <= PCM_MAX_LSB
