@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py - decoded 20 ms frames/s of the batched IMBE/AMBE decode+synthesis path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path (frame bits -> ECC -> parameter decode -> synthesis -> int16 PCM) over
+one batch: BASELINE.json configs[1], AMBE+2 3600x2450, 65,536 streams x 50 synthetic random-bit frames per
+GPU.  Streams are independent, so N GPUs run N disjoint stream shards with no collective on the data path
+("scaling": "weak"); torch.distributed is used only for the barrier and the max-over-ranks of the timings.
+
+Numbers in the JSON line:
+  value        frames/s, whole job, inputs resident in HBM, timed with CUDA events on the launching stream.
+  e2e          frames/s through the host-pointer C-ABI call (mbe_b200_process_frames): pinned HOST frame
+               bits in, int16 PCM + results in HOST memory out, copies inside the timed region.
+  roofline     HBM view of the stream kernel: algorithmic bytes per launch / mean launch time.
+  roofline_fp32  the bound that actually applies (FP32 issue): algorithmic FLOP per launch / launch time
+               against the non-fused FP32 issue peak (148 SM x 128 lanes x SM clock).
+  cpu_baseline the reference's own CPU build (oracle/_ref, dev-release flags) on the box's host cores,
+               bounded sample of the same workload.
+`--impl reference` times only that CPU arm.  The CUDA library is mandatory for the default arm: there is no
+CPU fallback in the product, and nothing under oracle/ is on the measured GPU path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CODEC_NAMES = {0: "imbe7200x4400", 1: "imbe7100x4400", 2: "ambe3600x2400", 3: "ambe3600x2450"}
+FRAME_BITS = {0: 184, 1: 168, 2: 96, 3: 96}
+# algorithmic FLOP per frame on iid random-bit frames (non-fused, mul = add = 1)
+FLOP_PER_FRAME = {0: 84e3, 1: 84e3, 2: 66e3, 3: 61e3}
+STATE_BYTES = 7828  # 3 x mbe_parms + 16 B RNG words per stream
+RESULT_BYTES = 24
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                d = json.load(f)
+            if "hbm_gbs" in d:
+                return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.stop = threading.Event()
+        self.th = None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w": round(max(pw), 1) if pw else None, "samples": len(self.rows)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_cpu_reference(codec, n_frames, steps, warmup, streams_per_thread):
+    """Times the reference's CPU implementation (oracle/_ref dev-release build; the oracle port if the compiled
+    reference is missing) on all host cores.  Returns (frames/s, info dict, seconds per step)."""
+    import mbe_testlib as T
+    cores = host_cores()
+    lib, kind, fn = None, "reference", None
+    if T.ref_available(fast=True):
+        lib = T.load_ref(fast=True)
+        fn = lib.ref_bench_run
+        flavour = "oracle/_ref/libmberef_fast.so (unmodified reference, dev-release flags: SIMD + fast-math + LTO)"
+    elif T.ref_available(fast=False):
+        lib = T.load_ref(fast=False)
+        fn = lib.ref_bench_run
+        flavour = "oracle/_ref/libmberef.so (unmodified reference, Release flags)"
+    else:
+        fn = T.load_oracle().mbo_run
+        kind = "port"
+        flavour = "oracle/libmbe_oracle.so (C restatement)"
+    S = min(cores * streams_per_thread, 65536)
+    frames = T.random_hard_frames(codec, S, n_frames, 0x2450)
+    seeds = T.stream_seeds(S)
+    pcm = np.zeros((S, n_frames, 160), np.int16)
+    res = np.zeros((S, n_frames, 6), np.int32)
+    times = []
+    for it in range(warmup + steps):
+        sec = fn(codec, 0, S, n_frames, T._ptr(frames), T._ptr(seeds), T._ptr(pcm), None, T._ptr(res), None, None, cores)
+        if it >= warmup:
+            times.append(sec)
+    sec = float(np.mean(times))
+    fps = S * n_frames / sec
+    info = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+            "sample": "%d streams x %d frames per step (%d per thread), %s, one stream per task over %d pthreads, %s" % (
+                S, n_frames, streams_per_thread, CODEC_NAMES[codec], cores, flavour),
+            "cpu_model": cpu_model(), "frames_per_s_per_core": fps / cores}
+    return fps, info, sec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--codec", default="ambe3600x2450", choices=list(CODEC_NAMES.values()))
+    ap.add_argument("--streams", type=int, default=65536, help="streams per GPU")
+    ap.add_argument("--frames", type=int, default=50, help="frames per stream per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    codec = {v: k for k, v in CODEC_NAMES.items()}[args.codec]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    S, F = args.streams, args.frames
+    workload = "%s hard-decision decode+synthesis, %d streams x %d synthetic random-bit frames per GPU" % (
+        CODEC_NAMES[codec], S, F)
+    config = {"workload": workload, "codec": CODEC_NAMES[codec], "streams_per_gpu": S, "frames_per_stream": F,
+              "sharding": "streams/%d, no collective" % world,
+              "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (S * F * (FRAME_BITS[codec] + 344) / 1e6)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        warm = max(1, min(args.warmup, 3))
+        fps, info, sec = run_cpu_reference(codec, F, args.steps, warm, streams_per_thread=1000)
+        line = {"impl": "reference", "metric": "decoded frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "realtime_channels": fps / 50.0, "cpu_baseline": info,
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)")
+    pkg = load_package()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    dec = pkg.Decoder(max_streams=S, device=local_rank)
+    seeds = (np.arange(S, dtype=np.uint64) + 0xC0FFEE + rank * S).astype(np.uint32)
+    dec.init_streams(0, S, seeds)
+
+    fb = FRAME_BITS[codec]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0x2450 + rank)
+    d_frames = torch.randint(0, 2, (S, F, fb), dtype=torch.uint8, device=dev, generator=gen)
+    d_pcm = torch.empty((S, F, 160), dtype=torch.int16, device=dev)
+    d_res = torch.empty((S, F, 6), dtype=torch.int32, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+
+    def step_dev():
+        dec.process_frames_dev(codec, 0, 0, S, F, d_frames.data_ptr(), d_pcm.data_ptr(), 0, d_res.data_ptr(), 0,
+                               stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm ----
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_dev()
+    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    l0 = dec.launches
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        with torch.cuda.stream(stream):
+            evs[0].record(stream)
+            for k in range(args.steps):
+                step_dev()
+                evs[k + 1].record(stream)
+        stream.synchronize()
+        barrier()
+    launches = dec.launches - l0
+    total_ms = max_over_ranks(evs[0].elapsed_time(evs[-1]))
+    per_launch_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    kern_ms = float(np.mean(per_launch_ms))
+    value = world * S * F * args.steps / (total_ms * 1e-3)
+    clocks = clk.summary()
+
+    # sanity: the PCM that came out is not silence and statuses are valid
+    chk = d_pcm[:64].abs().max().item()
+    st_min = int(d_res[:, :, 0].min().item())
+    if chk == 0 or st_min < 0:
+        raise SystemExit("bench.py: device path produced silence or error statuses (max |pcm| %d, min status %d)" % (chk, st_min))
+
+    # ---- end-to-end arm: host frames in, host PCM + results out, through the host-pointer C-ABI call ----
+    e2e = None
+    if not args.no_e2e:
+        h_frames = torch.empty((S, F, fb), dtype=torch.uint8, pin_memory=True)
+        h_frames.copy_(d_frames)
+        h_pcm = torch.empty((S, F, 160), dtype=torch.int16, pin_memory=True)
+        h_res = torch.empty((S, F, 6), dtype=torch.int32, pin_memory=True)
+        np_frames, np_pcm = h_frames.numpy(), h_pcm.numpy()
+        np_res = h_res.numpy().view(pkg.RESULT_DTYPE).reshape(S, F)
+        lib, h = dec.lib, dec.h
+        import ctypes
+
+        def step_host():
+            rc = lib.mbe_b200_process_frames(h, codec, 0, 0, S, F, np_frames.ctypes.data_as(ctypes.c_void_p),
+                                             np_pcm.ctypes.data_as(ctypes.c_void_p), None,
+                                             np_res.ctypes.data_as(ctypes.c_void_p), None)
+            if rc != 0:
+                raise SystemExit("mbe_b200_process_frames failed: %s" % lib.mbe_b200_last_error(h).decode())
+
+        for _ in range(max(1, min(args.warmup, 3))):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()          # returns when PCM + results are in host memory
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        e2e_s = max_over_ranks(t1 - t0)
+        barrier()
+        e2e = {"value": world * S * F * args.steps / e2e_s, "unit": "frames/s",
+               "h2d_bytes_per_step": int(S * F * fb), "d2h_bytes_per_step": int(S * F * (320 + RESULT_BYTES)),
+               "ms_per_step": e2e_s * 1e3 / args.steps,
+               "note": "mbe_b200_process_frames: pinned host bits in, int16 PCM + results to pinned host memory, "
+                       "wall clock around the blocking calls, max over ranks"}
+        if float(np.abs(np_pcm[:64]).max()) == 0:
+            raise SystemExit("bench.py: e2e path produced silence")
+
+    # ---- roofline of the stream kernel ----
+    hbm_peak, peak_src = measured_peaks()
+    alg_bytes = S * F * (fb + 320 + RESULT_BYTES) + 2 * S * STATE_BYTES
+    hbm_ach = alg_bytes / (kern_ms * 1e-3) / 1e9
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    fp32_issue_peak = 148 * 128 * sm_mhz * 1e6 / 1e12  # TFLOP/s, one non-fused op per lane per clock
+    flops = S * F * FLOP_PER_FRAME[codec]
+    fp32_ach = flops / (kern_ms * 1e-3) / 1e12
+    roofline = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "mbe_stream_kernel",
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms,
+                "note": "the kernel is FP32-issue bound, not HBM bound (no dense contraction, ~1 KB/frame); see roofline_fp32"}
+    roofline_fp32 = {"bound": "fp32-issue", "achieved": fp32_ach, "peak": fp32_issue_peak, "unit": "TFLOP/s",
+                     "frac": fp32_ach / fp32_issue_peak, "flop_per_frame": FLOP_PER_FRAME[codec],
+                     "peak_source": "148 SM x 128 FP32 lanes x %.0f MHz sampled SM clock, non-fused (mul and add issue "
+                                    "separately because parity forbids FMA contraction); FMA-counted peak is 2x" % sm_mhz}
+
+    line = {"metric": "decoded frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "realtime_channels": value / 50.0, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "roofline_fp32": roofline_fp32}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _, info, _ = run_cpu_reference(codec, F, 2, 1, streams_per_thread=1000)
+        line["cpu_baseline"] = info
+    dec.close()
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
