@@ -1,10 +1,14 @@
-// libmbe_b200.so - B200 (sm_100a) batched IMBE/AMBE decoder: stream kernel, per-frame state machines,
+// libmbe_b200.so - B200 (sm_100a) batched IMBE/AMBE decoder: stream kernels, per-frame state machines,
 // host-side context and the C-ABI declared in include/mbe_b200.h.
 //
 // Execution model: one warp owns one voice stream for the whole launch and walks its frames in order
 // (inter-frame prediction, oscillator phases, WOLA tail and noise generator make frames of a stream
 // strictly sequential); the three mbe_parms structs of the stream stay in shared memory between
 // frames and touch HBM once per launch.  Parallelism is streams x (harmonics | samples | codewords).
+// The stream kernel is a template over (codec, soft, mode): every instantiation carries only its own
+// front-end, parameter decoder and state machine, so the code a warp walks per frame stays small
+// (the first version was one 767 KB kernel and spent 64 % of its stall samples waiting for
+// instruction fetch - profiles/r01a_*).
 // No tensor cores (no dense contraction in this path), no collectives (streams are independent).
 #include <cuda_runtime.h>
 #include <math.h>
@@ -35,10 +39,6 @@ namespace mbe {
 
 constexpr int WARPS_PER_BLOCK = 7;
 
-struct BlockTables {
-    float tw[256];
-};
-
 constexpr unsigned FLAG_SOFT = 0x0001u, FLAG_C0 = 0x0002u, FLAG_C4 = 0x0004u, FLAG_TONE = 0x0010u,
                    FLAG_ERASURE = 0x0020u, FLAG_REPEAT = 0x0040u, FLAG_MUTE = 0x0080u;
 constexpr unsigned CONTEXT_FLAGS = FLAG_SOFT | FLAG_C0 | FLAG_C4;
@@ -47,6 +47,16 @@ constexpr unsigned STATUS_FLAGS = FLAG_TONE | FLAG_ERASURE | FLAG_REPEAT | FLAG_
 struct FrameCtx {
     int total, c0, c0v, c4, c4v;
     unsigned flags;  // context flags in, status flags accumulate
+};
+
+// What the frame's state machine decided to render; executed by ONE shared tail (render_frame) so that
+// the synthesis code exists once per kernel.
+enum { ACT_VOICE = 0, ACT_REPLAY, ACT_COMFORT_INIT, ACT_COMFORT_ERASURE, ACT_TONE };
+struct Action {
+    int kind;
+    float f1, f2;
+    int amp;
+    int keep_prev;  // ACT_TONE: prev_mp <- cur_mp afterwards (D-STAR clean tone)
 };
 
 // src/internal/mbe_result.h:44-97
@@ -74,20 +84,9 @@ __device__ __forceinline__ int resolve_total_errors(int c0, int prot, int c4, in
     return 0;
 }
 
-// the enhance + synthesise + state hand-over sandwich shared by all voice frames
-// (imbe7200x4400.c:842-856, ambe3600x2450.c:785-799)
-__device__ __forceinline__ void voice_frame(float acc[5], WarpWS& ws, StreamRng& rng, const DevTables* T,
-                                            const float* tw, int lane) {
-    copy_parms(&ws.prev, &ws.cur, lane);
-    const float rm0 = spectral_enhance(ws.cur, lane);
-    synthesize_speech(acc, ws, rng, T, tw, 1, rm0, lane);
-    __syncwarp();
-    copy_parms(&ws.enh, &ws.cur, lane);
-}
-
 // ---- IMBE 4400 frame state machine (imbe7200x4400.c:780-888) --------------------------------------
-__device__ __forceinline__ void process_imbe(float acc[5], FrameCtx& fc, const unsigned dw[3], WarpWS& ws,
-                                             StreamRng& rng, const DevTables* T, const float* tw, int lane) {
+__device__ __forceinline__ Action process_imbe(FrameCtx& fc, const unsigned dw[3], WarpWS& ws, const DevTables* T,
+                                               int lane) {
     Parms& cur = ws.cur;
     Parms& prev = ws.prev;
     const float rate = (0.95f * prev.errorRate) + (0.000365f * (float)fc.total);
@@ -143,11 +142,11 @@ __device__ __forceinline__ void process_imbe(float acc[5], FrameCtx& fc, const u
         fc.flags |= FLAG_REPEAT;
     }
     __syncwarp();
-    const bool muted = (cur.repeatCount >= 4) || (cur.errorRate > cur.mutingThreshold);
-    voice_frame(acc, ws, rng, T, tw, lane);
-    if (muted) {
+    if ((cur.repeatCount >= 4) || (cur.errorRate > cur.mutingThreshold)) {
         fc.flags |= FLAG_MUTE;
     }
+    Action a = {ACT_VOICE, 0.0f, 0.0f, 0, 0};
+    return a;
 }
 
 // ---- AMBE helpers (ambe_common.c:191-271) ----------------------------------------------------------
@@ -199,16 +198,12 @@ __device__ __forceinline__ void prepare_ambe(const FrameCtx& fc, WarpWS& ws, con
     __syncwarp();
 }
 
-__device__ __forceinline__ void ambe_voice_or_mute(float acc[5], FrameCtx& fc, WarpWS& ws, StreamRng& rng,
-                                                   const DevTables* T, const float* tw, int lane) {
+__device__ __forceinline__ int ambe_voice_or_mute(FrameCtx& fc, const WarpWS& ws) {
     if (ws.cur.repeatCount < 4) {
-        voice_frame(acc, ws, rng, T, tw, lane);
-        return;
+        return ACT_VOICE;
     }
     fc.flags |= FLAG_MUTE;
-    comfort_noise(acc, rng, T, lane);
-    __syncwarp();
-    init_ambe(ws, T, lane);
+    return ACT_COMFORT_INIT;
 }
 
 __device__ __forceinline__ void ambe_repeat(WarpWS& ws, FrameCtx& fc, int lane) {
@@ -221,9 +216,9 @@ __device__ __forceinline__ void ambe_repeat(WarpWS& ws, FrameCtx& fc, int lane) 
 }
 
 // ---- AMBE+2 3600x2450 (ambe3600x2450.c:716-877) -----------------------------------------------------
-__device__ __forceinline__ void process_ambe2450(float acc[5], FrameCtx& fc, const unsigned dw[3], WarpWS& ws,
-                                                 StreamRng& rng, const DevTables* T, const float* tw,
-                                                 uint32_t* spill, int lane) {
+__device__ __forceinline__ Action process_ambe2450(FrameCtx& fc, const unsigned dw[3], WarpWS& ws, const DevTables* T,
+                                                   int lane) {
+    Action act = {ACT_COMFORT_INIT, 0.0f, 0.0f, 0, 0};
     prepare_ambe(fc, ws, T, lane);
     const int bad = decode_ambe2450(dw, ws, T, fc.total, lane);
     __syncwarp();
@@ -249,7 +244,7 @@ __device__ __forceinline__ void process_ambe2450(float acc[5], FrameCtx& fc, con
     __syncwarp();
 
     if (bad == 0) {
-        ambe_voice_or_mute(acc, fc, ws, rng, T, tw, lane);
+        act.kind = ambe_voice_or_mute(fc, ws);
     } else if (bad == 7) {
         unsigned u0 = 0, u1 = 0, u3 = 0;
         for (int i = 0; i < 12; ++i) {
@@ -262,46 +257,24 @@ __device__ __forceinline__ void process_ambe2450(float acc[5], FrameCtx& fc, con
             u3 = (u3 << 1) | getbit(dw, i);
         }
         const int id1 = (int)((u1 & 0xfffu) >> 4);
-        float f1, f2;
-        if (tone_freqs(id1, &f1, &f2)) {
-            const int AD = (int)(((u0 & 0x3fu) << 1) + ((u3 >> 4) & 1u));
-            render_tone(acc, ws.cur, f1, f2, AD, lane);
+        if (tone_freqs(id1, &act.f1, &act.f2)) {
+            act.kind = ACT_TONE;
+            act.amp = (int)(((u0 & 0x3fu) << 1) + ((u3 >> 4) & 1u));
         } else if (!(ws.prev.repeatCount >= 4)) {
             // invalid tone id: replay the last voice model while advancing synthesis state
-            // (ambe3600x2450.c:808-816).  ws.cur is parked in the stream's HBM slot meanwhile.
-            uint32_t* cw = reinterpret_cast<uint32_t*>(&ws.cur);
-            for (int i = lane; i < PARMS_WORDS; i += 32) {
-                spill[i] = cw[i];
-            }
-            __syncwarp();
-            copy_parms(&ws.cur, &ws.enh, lane);
-            synthesize_speech(acc, ws, rng, T, tw, 0, 0.0f, lane);
-            __syncwarp();
-            copy_parms(&ws.enh, &ws.cur, lane);
-            for (int i = lane; i < PARMS_WORDS; i += 32) {
-                cw[i] = spill[i];
-            }
-            __syncwarp();
-        } else {
-            comfort_noise(acc, rng, T, lane);
-            __syncwarp();
-            init_ambe(ws, T, lane);
+            // (ambe3600x2450.c:808-816)
+            act.kind = ACT_REPLAY;
         }
     } else if (bad == 2) {
-        comfort_noise(acc, rng, T, lane);
-        __syncwarp();
-        copy_parms(&ws.prev, &ws.cur, lane);
-        copy_parms(&ws.enh, &ws.cur, lane);
-    } else {
-        comfort_noise(acc, rng, T, lane);
-        __syncwarp();
-        init_ambe(ws, T, lane);
+        act.kind = ACT_COMFORT_ERASURE;
     }
+    return act;
 }
 
 // ---- AMBE 3600x2400 (ambe3600x2400.c:629-762) --------------------------------------------------------
-__device__ __forceinline__ void process_ambe2400(float acc[5], FrameCtx& fc, const unsigned dw[3], WarpWS& ws,
-                                                 StreamRng& rng, const DevTables* T, const float* tw, int lane) {
+__device__ __forceinline__ Action process_ambe2400(FrameCtx& fc, const unsigned dw[3], WarpWS& ws, const DevTables* T,
+                                                   int lane) {
+    Action act = {ACT_COMFORT_INIT, 0.0f, 0.0f, 0, 0};
     prepare_ambe(fc, ws, T, lane);
     const int bad = decode_ambe2400(dw, ws, T, lane);
     __syncwarp();
@@ -321,33 +294,109 @@ __device__ __forceinline__ void process_ambe2400(float acc[5], FrameCtx& fc, con
     __syncwarp();
 
     if (clean_tone) {
-        float f1 = 0.0f;
-        if (bad >= 7 && bad <= 122) {
-            f1 = 31.25f * (float)bad;
-        }
-        render_tone(acc, ws.cur, f1, f1, 103, lane);
-        copy_parms(&ws.prev, &ws.cur, lane);
+        act.kind = ACT_TONE;
+        act.f1 = act.f2 = 31.25f * (float)bad;
+        act.amp = 103;
+        act.keep_prev = 1;
     } else if (bad == 0) {
-        ambe_voice_or_mute(acc, fc, ws, rng, T, tw, lane);
-    } else {
-        comfort_noise(acc, rng, T, lane);
-        __syncwarp();
-        init_ambe(ws, T, lane);
+        act.kind = ambe_voice_or_mute(fc, ws);
+    }
+    return act;
+}
+
+// ---- shared tail: render what the state machine decided, hand the state over ---------------------------
+// ACT_VOICE is the enhance + synthesise sandwich of imbe7200x4400.c:842-856 / ambe3600x2450.c:785-799;
+// `spill` is a 651-word HBM scratch (the stream's own state slot) used by the rare ACT_REPLAY.
+template <bool AMBE>
+__device__ __forceinline__ void render_frame(const Action& act, WarpWS& ws, const DevTables* T, const BlockTables* bt,
+                                             uint32_t* spill, int lane) {
+    int kind = act.kind;
+    if (!AMBE) {
+        kind = ACT_VOICE;
+    }
+    if (kind == ACT_VOICE || kind == ACT_REPLAY) {
+        float rm0 = 0.0f;
+        int has_rm0 = 0;
+        uint32_t* cw = reinterpret_cast<uint32_t*>(&ws.cur);
+        if (kind == ACT_VOICE) {
+            copy_parms(&ws.prev, &ws.cur, lane);
+            rm0 = spectral_enhance(ws.cur, lane);
+            has_rm0 = 1;
+        } else {
+            for (int i = lane; i < PARMS_WORDS; i += 32) {
+                spill[i] = cw[i];
+            }
+            __syncwarp();
+            copy_parms(&ws.cur, &ws.enh, lane);
+        }
+        synthesize_speech(ws, T, bt, has_rm0, rm0, lane);
+        copy_parms(&ws.enh, &ws.cur, lane);
+        if (AMBE && kind == ACT_REPLAY) {
+            for (int i = lane; i < PARMS_WORDS; i += 32) {
+                cw[i] = spill[i];
+            }
+            __syncwarp();
+        }
+        return;
+    }
+    if (AMBE) {
+        if (kind == ACT_TONE) {
+            render_tone(ws, act.f1, act.f2, act.amp, lane);
+            if (act.keep_prev) {
+                copy_parms(&ws.prev, &ws.cur, lane);
+            }
+            return;
+        }
+        comfort_noise(ws, T, lane);
+        if (kind == ACT_COMFORT_ERASURE) {
+            copy_parms(&ws.prev, &ws.cur, lane);
+            copy_parms(&ws.enh, &ws.cur, lane);
+        } else {
+            init_ambe(ws, T, lane);
+        }
+    }
+}
+
+__device__ __forceinline__ void load_block_tables(BlockTables* bt, const DevTables* T) {
+    for (int i = threadIdx.x; i < 324; i += blockDim.x) {
+        bt->voiced_win[i] = T->voiced_win[i];
+    }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        bt->tw[i] = T->tw[i];
+        bt->uvwin[i] = T->uvwin[i];
+    }
+    for (int i = threadIdx.x; i < 160; i += blockDim.x) {
+        bt->wola_wp[i] = T->wola_wp[i];
+        bt->wola_wc[i] = T->wola_wc[i];
+        bt->wola_den[i] = T->wola_den[i];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void store_pcm(const LaunchArgs& A, const WarpWS& ws, size_t frame_idx, int lane) {
+#pragma unroll
+    for (int ch = 0; ch < 5; ++ch) {
+        const size_t o = frame_idx * NS + 32 * ch + lane;
+        const float v = ws.out[32 * ch + lane];
+        if (A.pcmf) {
+            A.pcmf[o] = v;
+        }
+        if (A.pcm) {
+            A.pcm[o] = float_to_short(v);
+        }
     }
 }
 
 // =====================================================================================================
-// The stream kernel
+// The stream kernel: CODEC in {0..3}, SOFT in {0,1}, MODE in {MODE_FRAMES, MODE_DATA}
 // =====================================================================================================
+template <int CODEC, int SOFT, int MODE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) mbe_stream_kernel(const LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BlockTables* bt = reinterpret_cast<BlockTables*>(smem_raw);
     WarpWS* wsa = reinterpret_cast<WarpWS*>(smem_raw + sizeof(BlockTables));
     const DevTables* T = A.tab;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        bt->tw[i] = T->tw[i];
-    }
-    __syncthreads();
+    load_block_tables(bt, T);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -356,72 +405,25 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) mbe_stream_kernel(const 
         return;
     }
     WarpWS& ws = wsa[warp];
-    const float* tw = bt->tw;
-    StreamRng rng;
-    uint32_t* gs = nullptr;
-    uint32_t* wsw = reinterpret_cast<uint32_t*>(&ws);  // cur, prev, enh are the first 3*651 words
-
-    if (A.mode == MODE_SYNTH) {
-        const uint32_t* gc = A.synth_cur + (size_t)s * PARMS_WORDS;
-        const uint32_t* gp = A.synth_prev + (size_t)s * PARMS_WORDS;
-        uint32_t* c = reinterpret_cast<uint32_t*>(&ws.cur);
-        uint32_t* e = reinterpret_cast<uint32_t*>(&ws.enh);
-        for (int i = lane; i < PARMS_WORDS; i += 32) {
-            c[i] = gc[i];
-            e[i] = gp[i];
-        }
-        // RNG as after mbe_setThreadRngSeed(seed) (mbelib.c:173-181); no seeds: fresh-thread defaults
-        if (A.synth_seeds) {
-            unsigned seed = A.synth_seeds[s];
-            if (seed == 0u) {
-                seed = 0x6d25357bu;
-            }
-            rng.comfort = (((unsigned long long)seed) ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1ULL);
-            rng.uv_seed = seed % 53125u;
-            rng.uv_override = 1;
-        } else {
-            rng.comfort = (0x12345678ULL ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1ULL);
-            rng.uv_seed = 3147u;
-            rng.uv_override = 0;
-        }
-        __syncwarp();
-        float acc[5];
-        synthesize_speech(acc, ws, rng, T, tw, 0, 0.0f, lane);
-        __syncwarp();
-#pragma unroll
-        for (int ch = 0; ch < 5; ++ch) {
-            const size_t o = (size_t)s * NS + 32 * ch + lane;
-            if (A.pcmf) {
-                A.pcmf[o] = acc[ch];
-            }
-            if (A.pcm) {
-                A.pcm[o] = float_to_short(acc[ch]);
-            }
-        }
-        uint32_t* oc = A.synth_cur + (size_t)s * PARMS_WORDS;
-        uint32_t* op = A.synth_prev + (size_t)s * PARMS_WORDS;
-        for (int i = lane; i < PARMS_WORDS; i += 32) {
-            oc[i] = c[i];
-            op[i] = e[i];
-        }
-        return;
-    }
+    uint32_t* wsw = reinterpret_cast<uint32_t*>(&ws.cur);  // cur, prev, enh are contiguous: 3*651 words
+    constexpr bool AMBE = (CODEC >= MBE_B200_AMBE3600X2400);
+    constexpr int fbits = (CODEC == MBE_B200_IMBE7200X4400) ? 184 : (CODEC == MBE_B200_IMBE7100X4400 ? 168 : 96);
+    constexpr int pbits = AMBE ? 49 : 88;
+    constexpr size_t fstride = (MODE == MODE_DATA) ? (size_t)pbits : (size_t)fbits * (SOFT ? 2u : 1u);
 
     const int stream = A.first_stream + s;
-    gs = A.state + (size_t)stream * STATE_WORDS;
+    uint32_t* gs = A.state + (size_t)stream * STATE_WORDS;
     for (int i = lane; i < 3 * PARMS_WORDS; i += 32) {
         wsw[i] = gs[i];
     }
-    rng.comfort = (unsigned long long)gs[3 * PARMS_WORDS] | ((unsigned long long)gs[3 * PARMS_WORDS + 1] << 32);
-    rng.uv_seed = gs[3 * PARMS_WORDS + 2];
-    rng.uv_override = gs[3 * PARMS_WORDS + 3];
+    if (lane == 0) {
+        ws.rng.comfort = (unsigned long long)gs[3 * PARMS_WORDS] | ((unsigned long long)gs[3 * PARMS_WORDS + 1] << 32);
+        ws.rng.uv_seed = gs[3 * PARMS_WORDS + 2];
+        ws.rng.uv_override = gs[3 * PARMS_WORDS + 3];
+    }
     __syncwarp();
 
-    const int codec = A.codec;
-    const int fbits = (codec == MBE_B200_IMBE7200X4400) ? 184 : (codec == MBE_B200_IMBE7100X4400 ? 168 : 96);
-    const int pbits = (codec <= MBE_B200_IMBE7100X4400) ? 88 : 49;
-    const size_t fstride = (A.mode == MODE_DATA) ? (size_t)pbits : (size_t)fbits * (A.soft ? 2u : 1u);
-
+#pragma unroll 1
     for (int f = 0; f < A.n_frames; ++f) {
         const size_t idx = (size_t)s * A.n_frames + f;
         const uint8_t* fr = A.frames + idx * fstride;
@@ -432,9 +434,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) mbe_stream_kernel(const 
         rout.c0_errors = rout.protected_errors = rout.c4_errors = rout.total_errors = 0;
         rout.flags = 0;
 
-        if (A.mode == MODE_FRAMES) {
-            FrontResult R = front_end(codec, A.soft, fr, dw, ws.rel, reinterpret_cast<unsigned short*>(ws.u.tile),
-                                      ws.rowbits, T, lane);
+        if (MODE == MODE_FRAMES) {
+            FrontResult R = front_end(CODEC, SOFT, fr, dw, ws.rel, ws.u.dec.cost, ws.rowbits, T, lane);
             status = R.status;
             fc.total = R.c0 + R.prot;
             fc.c0 = R.c0;
@@ -480,43 +481,33 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) mbe_stream_kernel(const 
             fc.total = total;
         }
 
-        float acc[5];
-#pragma unroll
-        for (int ch = 0; ch < 5; ++ch) {
-            acc[ch] = 0.0f;
-        }
         if (status >= 0) {
-            if (codec <= MBE_B200_IMBE7100X4400) {
-                process_imbe(acc, fc, dw, ws, rng, T, tw, lane);
-            } else if (codec == MBE_B200_AMBE3600X2400) {
-                process_ambe2400(acc, fc, dw, ws, rng, T, tw, lane);
+            Action act;
+            if (!AMBE) {
+                act = process_imbe(fc, dw, ws, T, lane);
+            } else if (CODEC == MBE_B200_AMBE3600X2400) {
+                act = process_ambe2400(fc, dw, ws, T, lane);
             } else {
-                process_ambe2450(acc, fc, dw, ws, rng, T, tw, gs, lane);
+                act = process_ambe2450(fc, dw, ws, T, lane);
             }
+            render_frame<AMBE>(act, ws, T, bt, gs, lane);
             status = fc.total;
             rout.c0_errors = fc.c0;
             rout.c4_errors = fc.c4;
             rout.total_errors = fc.total;
             rout.protected_errors = fc.total - fc.c0;
             rout.flags = fc.flags;
+        } else {
+            zero_out(ws, lane);
         }
         __syncwarp();
 
-#pragma unroll
-        for (int ch = 0; ch < 5; ++ch) {
-            const size_t o = idx * NS + 32 * ch + lane;
-            if (A.pcmf) {
-                A.pcmf[o] = acc[ch];
-            }
-            if (A.pcm) {
-                A.pcm[o] = float_to_short(acc[ch]);
-            }
-        }
+        store_pcm(A, ws, idx, lane);
         if (A.results && lane == 0) {
             rout.status = status;
             A.results[idx] = rout;
         }
-        if (A.bits && A.mode == MODE_FRAMES) {
+        if (A.bits && MODE == MODE_FRAMES) {
 #pragma unroll
             for (int w = 0; w < 3; ++w) {
                 const int i = 32 * w + lane;
@@ -525,6 +516,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) mbe_stream_kernel(const 
                 }
             }
         }
+        __syncwarp();
     }
 
     __syncwarp();
@@ -532,30 +524,79 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) mbe_stream_kernel(const 
         gs[i] = wsw[i];
     }
     if (lane == 0) {
-        gs[3 * PARMS_WORDS] = (uint32_t)(rng.comfort & 0xffffffffULL);
-        gs[3 * PARMS_WORDS + 1] = (uint32_t)(rng.comfort >> 32);
-        gs[3 * PARMS_WORDS + 2] = rng.uv_seed;
-        gs[3 * PARMS_WORDS + 3] = rng.uv_override;
+        gs[3 * PARMS_WORDS] = (uint32_t)(ws.rng.comfort & 0xffffffffULL);
+        gs[3 * PARMS_WORDS + 1] = (uint32_t)(ws.rng.comfort >> 32);
+        gs[3 * PARMS_WORDS + 2] = ws.rng.uv_seed;
+        gs[3 * PARMS_WORDS + 3] = ws.rng.uv_override;
+    }
+}
+
+// batched mbe_synthesizeSpeech[f]: element s synthesises one frame from parameter blobs in device memory
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) mbe_synth_kernel(const LaunchArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BlockTables* bt = reinterpret_cast<BlockTables*>(smem_raw);
+    WarpWS* wsa = reinterpret_cast<WarpWS*>(smem_raw + sizeof(BlockTables));
+    const DevTables* T = A.tab;
+    load_block_tables(bt, T);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (s >= A.n_streams) {
+        return;
+    }
+    WarpWS& ws = wsa[warp];
+    uint32_t* gc = A.synth_cur + (size_t)s * PARMS_WORDS;
+    uint32_t* gp = A.synth_prev + (size_t)s * PARMS_WORDS;
+    uint32_t* c = reinterpret_cast<uint32_t*>(&ws.cur);
+    uint32_t* e = reinterpret_cast<uint32_t*>(&ws.enh);
+    for (int i = lane; i < PARMS_WORDS; i += 32) {
+        c[i] = gc[i];
+        e[i] = gp[i];
+    }
+    // RNG as after mbe_setThreadRngSeed(seed) (mbelib.c:173-181); no seeds: fresh-thread defaults
+    if (lane == 0) {
+        if (A.synth_seeds) {
+            unsigned seed = A.synth_seeds[s];
+            if (seed == 0u) {
+                seed = 0x6d25357bu;
+            }
+            ws.rng.comfort = (((unsigned long long)seed) ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1ULL);
+            ws.rng.uv_seed = seed % 53125u;
+            ws.rng.uv_override = 1;
+        } else {
+            ws.rng.comfort = (0x12345678ULL ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1ULL);
+            ws.rng.uv_seed = 3147u;
+            ws.rng.uv_override = 0;
+        }
+    }
+    __syncwarp();
+    synthesize_speech(ws, T, bt, 0, 0.0f, lane);
+    __syncwarp();
+    store_pcm(A, ws, (size_t)s, lane);
+    for (int i = lane; i < PARMS_WORDS; i += 32) {
+        gc[i] = c[i];
+        gp[i] = e[i];
     }
 }
 
 // stateless ECC-only kernel: one warp per frame (batched mbe_decode<Codec>[Soft]Frame)
-__global__ void __launch_bounds__(256) mbe_decode_kernel(int codec, int soft, int n, const uint8_t* __restrict__ frames,
+template <int CODEC, int SOFT>
+__global__ void __launch_bounds__(256) mbe_decode_kernel(int n, const uint8_t* __restrict__ frames,
                                                          uint8_t* __restrict__ bits, mbe_b200_result* __restrict__ results,
                                                          const DevTables* T) {
     __shared__ unsigned char rel[8][8 * 24];
-    __shared__ unsigned short cost[8][640];
+    __shared__ unsigned short cost[SOFT ? 8 : 1][640];
     __shared__ unsigned rows[8][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + warp;
     if (i >= n) {
         return;
     }
-    const int fbits = (codec == MBE_B200_IMBE7200X4400) ? 184 : (codec == MBE_B200_IMBE7100X4400 ? 168 : 96);
-    const int pbits = (codec <= MBE_B200_IMBE7100X4400) ? 88 : 49;
+    constexpr int fbits = (CODEC == MBE_B200_IMBE7200X4400) ? 184 : (CODEC == MBE_B200_IMBE7100X4400 ? 168 : 96);
+    constexpr int pbits = (CODEC <= MBE_B200_IMBE7100X4400) ? 88 : 49;
     unsigned dw[3];
-    FrontResult R = front_end(codec, soft, frames + (size_t)i * fbits * (soft ? 2 : 1), dw, rel[warp], cost[warp],
-                              rows[warp], T, lane);
+    FrontResult R = front_end(CODEC, SOFT, frames + (size_t)i * fbits * (SOFT ? 2 : 1), dw, rel[warp],
+                              cost[SOFT ? warp : 0], rows[warp], T, lane);
     if (bits && R.status >= 0) {
 #pragma unroll
         for (int w = 0; w < 3; ++w) {
@@ -868,6 +909,44 @@ static void build_tables(DevTables* t) {
 
 static size_t stream_kernel_smem(void) { return sizeof(BlockTables) + (size_t)WARPS_PER_BLOCK * sizeof(WarpWS); }
 
+typedef void (*StreamKernelFn)(const LaunchArgs);
+
+// one kernel image per (codec, soft) for channel frames; parameter-bit input (mbe_process<Codec>Data) has no
+// soft variant and IMBE 7100 shares the IMBE 4400 parameter layout
+static StreamKernelFn pick_stream_kernel(int codec, int soft, int mode) {
+    if (mode == MODE_DATA) {
+        switch (codec) {
+            case MBE_B200_AMBE3600X2400: return mbe_stream_kernel<MBE_B200_AMBE3600X2400, 0, MODE_DATA>;
+            case MBE_B200_AMBE3600X2450: return mbe_stream_kernel<MBE_B200_AMBE3600X2450, 0, MODE_DATA>;
+            default: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 0, MODE_DATA>;
+        }
+    }
+    switch (codec * 2 + (soft ? 1 : 0)) {
+        case 0: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 0, MODE_FRAMES>;
+        case 1: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 1, MODE_FRAMES>;
+        case 2: return mbe_stream_kernel<MBE_B200_IMBE7100X4400, 0, MODE_FRAMES>;
+        case 3: return mbe_stream_kernel<MBE_B200_IMBE7100X4400, 1, MODE_FRAMES>;
+        case 4: return mbe_stream_kernel<MBE_B200_AMBE3600X2400, 0, MODE_FRAMES>;
+        case 5: return mbe_stream_kernel<MBE_B200_AMBE3600X2400, 1, MODE_FRAMES>;
+        case 6: return mbe_stream_kernel<MBE_B200_AMBE3600X2450, 0, MODE_FRAMES>;
+        default: return mbe_stream_kernel<MBE_B200_AMBE3600X2450, 1, MODE_FRAMES>;
+    }
+}
+
+typedef void (*DecodeKernelFn)(int, const uint8_t*, uint8_t*, mbe_b200_result*, const DevTables*);
+static DecodeKernelFn pick_decode_kernel(int codec, int soft) {
+    switch (codec * 2 + (soft ? 1 : 0)) {
+        case 0: return mbe_decode_kernel<MBE_B200_IMBE7200X4400, 0>;
+        case 1: return mbe_decode_kernel<MBE_B200_IMBE7200X4400, 1>;
+        case 2: return mbe_decode_kernel<MBE_B200_IMBE7100X4400, 0>;
+        case 3: return mbe_decode_kernel<MBE_B200_IMBE7100X4400, 1>;
+        case 4: return mbe_decode_kernel<MBE_B200_AMBE3600X2400, 0>;
+        case 5: return mbe_decode_kernel<MBE_B200_AMBE3600X2400, 1>;
+        case 6: return mbe_decode_kernel<MBE_B200_AMBE3600X2450, 0>;
+        default: return mbe_decode_kernel<MBE_B200_AMBE3600X2450, 1>;
+    }
+}
+
 extern "C" {
 
 const char* mbe_b200_version(void) { return "mbe_b200 0.1.0 (sm_100a)"; }
@@ -928,7 +1007,15 @@ int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams) {
     CUC(cudaMalloc(&ctx->d_tab, sizeof(DevTables)));
     CUC(cudaMemcpy(ctx->d_tab, ht, sizeof(DevTables), cudaMemcpyHostToDevice));
     CUC(cudaMalloc(&ctx->d_state, (size_t)max_streams * STATE_WORDS * sizeof(uint32_t)));
-    CUC(cudaFuncSetAttribute(mbe_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_kernel_smem()));
+    for (int codec = 0; codec < 4; ++codec) {
+        for (int soft = 0; soft < 2; ++soft) {
+            for (int mode = 0; mode < 2; ++mode) {
+                CUC(cudaFuncSetAttribute(pick_stream_kernel(codec, soft, mode), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)stream_kernel_smem()));
+            }
+        }
+    }
+    CUC(cudaFuncSetAttribute(mbe_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_kernel_smem()));
 #undef CUC
     free(ht);
     *out = ctx;
@@ -1044,7 +1131,11 @@ int mbe_b200_import_rng(mbe_b200_ctx* ctx, int first, int count, const uint32_t*
 
 static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a, cudaStream_t st) {
     const int blocks = (a.n_streams + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    mbe_stream_kernel<<<blocks, WARPS_PER_BLOCK * 32, stream_kernel_smem(), st>>>(a);
+    if (a.mode == MODE_SYNTH) {
+        mbe_synth_kernel<<<blocks, WARPS_PER_BLOCK * 32, stream_kernel_smem(), st>>>(a);
+    } else {
+        pick_stream_kernel(a.codec, a.soft, a.mode)<<<blocks, WARPS_PER_BLOCK * 32, stream_kernel_smem(), st>>>(a);
+    }
     ctx->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -1125,7 +1216,7 @@ int mbe_b200_decode_frames_dev(mbe_b200_ctx* ctx, int codec, int soft, int n, co
     }
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    mbe_decode_kernel<<<(n + 7) / 8, 256, 0, st>>>(codec, soft ? 1 : 0, n, d_frames, d_bits, d_results, ctx->d_tab);
+    pick_decode_kernel(codec, soft)<<<(n + 7) / 8, 256, 0, st>>>(n, d_frames, d_bits, d_results, ctx->d_tab);
     ctx->launches++;
     CU(cudaGetLastError());
     return 0;

@@ -2,6 +2,7 @@
 // filled on the host at context creation, per-warp shared-memory workspace.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/mbe_b200.h"
@@ -107,25 +108,47 @@ struct LaunchArgs {
 
 constexpr int TILE_STRIDE = 36;   // floats per sample row of the oscillator tile (32 components + pad)
 
+// Tables every warp of a block reads with lane-varying indices on the synthesis path, staged into
+// shared memory once per block (5.3 KB).
+struct __align__(16) BlockTables {
+    float voiced_win[324];   // 321-pt voiced window Ws (mbelib_const.h), 16-byte aligned rows for LDS.128
+    float tw[256];           // FFTPACK twiddles
+    float uvwin[256];        // unvoiced analysis window, centred at 128
+    float wola_wp[160], wola_wc[160], wola_den[160];
+};
+
+// The reference's thread-local RNG state, per stream (mbe_adaptive.c:29-30, mbe_unvoiced_fft.c:29-30)
+struct StreamRng {
+    unsigned long long comfort;  // 48-bit comfort-noise LCG state
+    unsigned uv_seed;            // unvoiced cold-start seed override
+    unsigned uv_override;        // consumed by the first cold start
+};
+
 // Per-warp shared-memory workspace: one warp owns one stream for the whole launch.
 struct __align__(16) WarpWS {
-    Parms cur, prev, enh;                 // 7812 B
-    float noise[NFFT];                    // white-noise buffer of the frame (phases + unvoiced)
-    union {
-        float tile[32 * TILE_STRIDE];     // voiced bank: [sample][component]
+    StreamRng rng;
+    union __align__(16) {
+        float tile[32 * TILE_STRIDE];     // voiced bank: [sample][component], pre-weighted contributions
         struct {
-            float a[NFFT];
-            float b[NFFT];
-            float scale[132];
+            float b[NFFT];                // FFT pong buffer
+            float scale[132];             // per-bin unvoiced band scale
         } fft;
-    } u;
+        struct {                          // parameter decode scratch (dead before synthesis starts)
+            float tmp[128];               // per-harmonic terms [1..56], DCT coefficients [64+l]
+            float Tl[60];
+            int field[58];                // IMBE quantiser words b1..bL+1
+            unsigned short cost[640];     // soft-decision partial cost tables
+        } dec;
+    } u;                                  // 16-byte aligned: rows are read with LDS.128
+    float A[NFFT];                        // windowed white noise of the frame, then FFT ping buffer
+    float out[NS];                        // the frame's 160 float samples (lane i owns i, 32+i, ...)
     float gain[112];                      // per-component 2*Ml
-    float tmp[128];                       // scratch: per-harmonic terms [1..56], DCT coefficients [64+l]
-    float Tl[60];
-    int field[58];                        // IMBE quantiser words b1..bL+1
+    Parms cur, prev, enh;                 // 7812 B, contiguous
+    float nz[57];                         // white-noise samples 1..56 of the frame (phase randomisation)
     unsigned rowbits[8];
     unsigned char comp[112];              // component descriptor: harmonic << 2 | kind
     unsigned char rel[8 * 24];            // soft-bit reliabilities of the frame
 };
+static_assert(offsetof(WarpWS, u) % 16 == 0 && sizeof(WarpWS) % 16 == 0 && sizeof(BlockTables) % 16 == 0, "LDS.128 alignment");
 
 }  // namespace mbe

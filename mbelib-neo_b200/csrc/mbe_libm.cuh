@@ -84,15 +84,22 @@ struct SinCosCoef {
 
 MBE_HD uint32_t abstop12(float x) { return (f2u(x) >> 20) & 0x7ffu; }
 
-// 2/pi as overlapping 32-bit windows of its binary expansion (byte stride), for |x| >= 120.
+// 2/pi as overlapping 32-bit windows of its binary expansion (byte stride), for |x| >= 120:
+// window i covers bytes [i-3, i] of 0.A2F9836E 4E441529 FC2757D1 F534DDC0 DB629599 3C439041 ...
+#if defined(__CUDACC__)
+static __device__ const uint32_t k_inv_pio4_dev[24] = {
+    0xa2u,       0xa2f9u,     0xa2f983u,   0xa2f9836eu, 0xf9836e4eu, 0x836e4e44u, 0x6e4e4415u, 0x4e441529u,
+    0x441529fcu, 0x1529fc27u, 0x29fc2757u, 0xfc2757d1u, 0x2757d1f5u, 0x57d1f534u, 0xd1f534ddu, 0xf534ddc0u,
+    0x34ddc0dbu, 0xddc0db62u, 0xc0db6295u, 0xdb629599u, 0x6295993cu, 0x95993c43u, 0x993c4390u, 0x3c439041u};
+#endif
+
 MBE_HD uint32_t inv_pio4_word(int i) {
-    // hex digits of 2/pi: 0.A2F9836E 4E441529 FC2757D1 F534DDC0 DB629599 3C439041 ...
+#if defined(__CUDA_ARCH__)
+    return k_inv_pio4_dev[i];
+#else
     const uint64_t h0 = 0xA2F9836E4E441529ull, h1 = 0xFC2757D1F534DDC0ull, h2 = 0xDB6295993C439041ull;
-    // window i covers bytes [i-3, i] of the digit string (zero-extended to the left)
-    // build from a 24-byte big-endian string
-    int last = i;          // index of last byte in window
     uint32_t w = 0;
-    for (int b = last - 3; b <= last; ++b) {
+    for (int b = i - 3; b <= i; ++b) {
         uint32_t byte = 0;
         if (b >= 0) {
             uint64_t q = (b < 8) ? h0 : (b < 16 ? h1 : h2);
@@ -101,6 +108,7 @@ MBE_HD uint32_t inv_pio4_word(int i) {
         w = (w << 8) | byte;
     }
     return w;
+#endif
 }
 
 MBE_HD double reduce_fast(double x, int* np) {

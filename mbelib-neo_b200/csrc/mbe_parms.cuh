@@ -67,20 +67,20 @@ __device__ __forceinline__ void predict_magnitudes(WarpWS& ws, const DevTables* 
             dl[r] = fk - (float)ik;
             pa[r] = P[ik];
             pb[r] = P[up];
-            ws.tmp[l] = (((float)1 - dl[r]) * pa[r]) + (dl[r] * pb[r]);
+            ws.u.dec.tmp[l] = (((float)1 - dl[r]) * pa[r]) + (dl[r] * pb[r]);
         }
     }
     __syncwarp();
     float acc = 0.f;
     for (int l = 1; l <= cur_L; ++l) {
-        acc = acc + ws.tmp[l];
+        acc = acc + ws.u.dec.tmp[l];
     }
     acc = ((rho / (float)cur_L) * acc);
     float big_gamma = 0.f;
     if (ambe) {
         float s42 = 0.f;
         for (int l = 1; l <= cur_L; ++l) {
-            s42 += ws.Tl[l];
+            s42 += ws.u.dec.Tl[l];
         }
         s42 = s42 / (float)cur_L;
         big_gamma = cur.gamma - (0.5f * T->log2_int[cur_L]) - s42;
@@ -94,9 +94,9 @@ __device__ __forceinline__ void predict_magnitudes(WarpWS& ws, const DevTables* 
             float c2 = (rho * dl[r] * pb[r]);
             float lg;
             if (ambe) {
-                lg = ws.Tl[l] + c1 + c2 - acc + big_gamma;
+                lg = ws.u.dec.Tl[l] + c1 + c2 - acc + big_gamma;
             } else {
-                lg = ws.Tl[l] + c1 + c2 - acc;
+                lg = ws.u.dec.Tl[l] + c1 + c2 - acc;
             }
             cur.log2Ml[l] = lg;
             float m = mbelibm::exp2f_glibc(lg, d_exp2_tab);
@@ -109,8 +109,8 @@ __device__ __forceinline__ void predict_magnitudes(WarpWS& ws, const DevTables* 
     __syncwarp();
 }
 
-// per-block inverse DCT: ws.tmp[64 + l] holds the DCT coefficients flattened by harmonic index,
-// blocklen[0..nblk-1] the block sizes.  Writes ws.Tl[1..L].
+// per-block inverse DCT: ws.u.dec.tmp[64 + l] holds the DCT coefficients flattened by harmonic index,
+// blocklen[0..nblk-1] the block sizes.  Writes ws.u.dec.Tl[1..L].
 __device__ __forceinline__ void block_idct(WarpWS& ws, const DevTables* T, const int* blocklen, int nblk, int L, int lane) {
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -129,9 +129,9 @@ __device__ __forceinline__ void block_idct(WarpWS& ws, const DevTables* T, const
             float sum = 0.f;
             for (int k = 1; k <= ji; ++k) {
                 float ak = (k == 1) ? 1.f : 2.f;
-                sum = sum + (ak * ws.tmp[64 + start + k] * cs[k - 1]);
+                sum = sum + (ak * ws.u.dec.tmp[64 + start + k] * cs[k - 1]);
             }
-            ws.Tl[l] = sum;
+            ws.u.dec.Tl[l] = sum;
         }
     }
     __syncwarp();
@@ -162,14 +162,14 @@ __device__ __forceinline__ int decode_imbe(const unsigned dw[3], WarpWS& ws, con
 
     // scatter bits 6..84 into the quantiser words b1..bL+1
     for (int i = lane; i < 58; i += 32) {
-        ws.field[i] = 0;
+        ws.u.dec.field[i] = 0;
     }
     __syncwarp();
     {
         const unsigned char* map = t_imbe_bitmap + L9 * 158;
         for (int i = 6 + lane; i < 85; i += 32) {
             if (getbit(dw, i)) {
-                atomicOr(&ws.field[map[2 * (i - 6)]], 1 << map[2 * (i - 6) + 1]);
+                atomicOr(&ws.u.dec.field[map[2 * (i - 6)]], 1 << map[2 * (i - 6) + 1]);
             }
         }
     }
@@ -177,36 +177,36 @@ __device__ __forceinline__ int decode_imbe(const unsigned dw[3], WarpWS& ws, con
 
     // voiced/unvoiced decisions: one bit per band of three harmonics
     {
-        const int vbits = ws.field[1];
+        const int vbits = ws.u.dec.field[1];
         for (int l = 1 + lane; l <= L; l += 32) {
             int k = K - 1 - (l - 1) / 3;
             k = k < 0 ? 0 : k;
             cur.Vl[l] = (vbits >> k) & 1;
         }
     }
-    // gain vector -> ws.tmp[1..6]
+    // gain vector -> ws.u.dec.tmp[1..6]
     if (lane < 6) {
         float g;
         if (lane == 0) {
-            g = t_imbe_gain0[ws.field[2] & 63];
+            g = t_imbe_gain0[ws.u.dec.field[2] & 63];
         } else {
             const int nb = t_imbe_gain_bits[L9 * 5 + (lane - 1)];
             const float step = t_imbe_gain_step[L9 * 5 + (lane - 1)];
-            const int bm = ws.field[lane + 2] & ((1 << nb) - 1);
+            const int bm = ws.u.dec.field[lane + 2] & ((1 << nb) - 1);
             g = (step * ((float)bm - pow2i(nb - 1) + 0.5f));
         }
-        ws.tmp[1 + lane] = g;
+        ws.u.dec.tmp[1 + lane] = g;
     }
     __syncwarp();
-    // 6-point inverse DCT of the gains -> ws.tmp[9..14] = Ri[1..6]
+    // 6-point inverse DCT of the gains -> ws.u.dec.tmp[9..14] = Ri[1..6]
     if (lane < 6) {
         float sum = 0.f;
 #pragma unroll
         for (int m = 1; m <= 6; ++m) {
             float am = (m == 1) ? 1.f : 2.f;
-            sum = sum + (am * ws.tmp[m] * T->ri6[(m - 1) * 6 + lane]);
+            sum = sum + (am * ws.u.dec.tmp[m] * T->ri6[(m - 1) * 6 + lane]);
         }
-        ws.tmp[9 + lane] = sum;
+        ws.u.dec.tmp[9 + lane] = sum;
     }
     __syncwarp();
     // DCT coefficients flattened by harmonic: first of each block = Ri, rest = dequantised HOCs
@@ -231,18 +231,18 @@ __device__ __forceinline__ int decode_imbe(const unsigned dw[3], WarpWS& ws, con
             const int k = l - start;       // 1-based position inside block (blk+1)
             float v;
             if (k == 1) {
-                v = ws.tmp[9 + blk];
+                v = ws.u.dec.tmp[9 + blk];
             } else {
                 const int m = l - (blk + 1) + 7;  // quantiser word index
                 const int Bm = t_imbe_hoc_bits[L9 * 50 + (m - 8)];
                 if (Bm <= 0) {
                     v = 0.f;
                 } else {
-                    const int bm = ws.field[m] & ((1 << Bm) - 1);
+                    const int bm = ws.u.dec.field[m] & ((1 << Bm) - 1);
                     v = ((t_imbe_hoc_step[Bm - 1] * t_imbe_hoc_sdev[k - 2]) * (((float)bm - pow2i(Bm - 1)) + 0.5f));
                 }
             }
-            ws.tmp[64 + l] = v;
+            ws.u.dec.tmp[64 + l] = v;
         }
     }
     __syncwarp();
@@ -281,7 +281,7 @@ __device__ __forceinline__ void ambe_tail(WarpWS& ws, const DevTables* T, const 
         } else {
             g = bk.prba58[b4 * 4 + (lane - 4)];
         }
-        ws.tmp[1 + lane] = g;
+        ws.u.dec.tmp[1 + lane] = g;
     }
     __syncwarp();
     if (lane < 8) {
@@ -289,9 +289,9 @@ __device__ __forceinline__ void ambe_tail(WarpWS& ws, const DevTables* T, const 
 #pragma unroll
         for (int m = 1; m <= 8; ++m) {
             float am = (m == 1) ? 1.f : 2.f;
-            sum = sum + (am * ws.tmp[m] * T->ri8[(m - 1) * 8 + lane]);
+            sum = sum + (am * ws.u.dec.tmp[m] * T->ri8[(m - 1) * 8 + lane]);
         }
-        ws.tmp[11 + lane] = sum;  // Ri[1..8] at tmp[11..18]
+        ws.u.dec.tmp[11 + lane] = sum;  // Ri[1..8] at tmp[11..18]
     }
     __syncwarp();
     int blen[4];
@@ -314,7 +314,7 @@ __device__ __forceinline__ void ambe_tail(WarpWS& ws, const DevTables* T, const 
             }
             blk = blk > 3 ? 3 : blk;
             const int k = l - start;
-            const float ra = ws.tmp[11 + 2 * blk], rb2 = ws.tmp[12 + 2 * blk];
+            const float ra = ws.u.dec.tmp[11 + 2 * blk], rb2 = ws.u.dec.tmp[12 + 2 * blk];
             float v;
             if (k == 1) {
                 v = 0.5f * (ra + rb2);
@@ -327,7 +327,7 @@ __device__ __forceinline__ void ambe_tail(WarpWS& ws, const DevTables* T, const 
             } else {
                 v = 0.f;
             }
-            ws.tmp[64 + l] = v;
+            ws.u.dec.tmp[64 + l] = v;
         }
     }
     __syncwarp();

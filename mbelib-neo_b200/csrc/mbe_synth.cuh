@@ -4,8 +4,8 @@
 // src/core/mbe_unvoiced_fft.c:277-761 and the N=256 real radix-4 path of the vendored pffft
 // (src/external/pffft/pffft.c:749-926,1109-1196).
 //
-// The 160 output samples of a frame live in registers: lane i owns samples i, 32+i, ..., 128+i
-// (acc[0..4]).  Rounding-order rules that pin parity with the reference:
+// The 160 output samples of a frame live in the warp's shared-memory row ws.out: lane i owns samples
+// i, 32+i, ..., 128+i.  Rounding-order rules that pin parity with the reference:
 //   * per sample, harmonics are added in order l = 1..maxl, previous-frame component before
 //     current-frame component (mbelib.c:310-317,1025-1039);
 //   * each oscillator is the reference's rotation recurrence, unfused:  c' = c*cd - s*sd,
@@ -20,11 +20,22 @@ namespace mbe {
 #define MBE_PI_F 3.14159274101257324f /* (float)M_PI */
 #define MBE_CLIP_F ((32767.0f * 0.95f) / 7.0f)
 
+// The glibc-exact transcendental ports are large (double-precision kernels + Payne-Hanek style
+// reduction); they are kept out of line so each exists once per kernel image (instruction cache).
+__device__ __noinline__ float2 dev_sincosf(float y) {
+    float2 r;
+    mbelibm::sincosf_glibc(y, &r.x, &r.y);  // x = sin, y = cos
+    return r;
+}
+__device__ __noinline__ float dev_cosf(float y) { return mbelibm::cosf_glibc(y); }
+__device__ __noinline__ float dev_sinf(float y) { return mbelibm::sinf_glibc(y); }
+
 __device__ __forceinline__ bool bands_ok(int L) { return L >= 1 && L <= MAXL; }
 
 __device__ __forceinline__ void copy_parms(Parms* dst, const Parms* src, int lane) {
     uint32_t* d = reinterpret_cast<uint32_t*>(dst);
     const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll 4
     for (int i = lane; i < PARMS_WORDS; i += 32) {
         d[i] = s[i];
     }
@@ -65,17 +76,18 @@ __device__ __forceinline__ void fill_default(Parms* p, float w0, int L, int K, f
     __syncwarp();
 }
 
-__device__ __forceinline__ void init_all(WarpWS& ws, float w0, int L, int K, float mute_thr, int lane) {
+__device__ __noinline__ void init_all(WarpWS& ws, float w0, int L, int K, float mute_thr, int lane) {
     fill_default(&ws.prev, w0, L, K, mute_thr, lane);
     copy_parms(&ws.cur, &ws.prev, lane);
     copy_parms(&ws.enh, &ws.prev, lane);
 }
 
-struct StreamRng {
-    unsigned long long comfort;  // 48-bit LCG state
-    unsigned uv_seed;
-    unsigned uv_override;
-};
+__device__ __forceinline__ void zero_out(WarpWS& ws, int lane) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        ws.out[32 * c + lane] = 0.0f;
+    }
+}
 
 // ---- spectral amplitude enhancement (mbelib.c:412-661); returns pre-enhancement Rm0 -------------
 __device__ __forceinline__ float spectral_enhance(Parms& cur, int lane) {
@@ -84,10 +96,11 @@ __device__ __forceinline__ float spectral_enhance(Parms& cur, int lane) {
         return 0.0f;
     }
     const float w0 = cur.w0;
-    float ss, cs;
-    mbelibm::sincosf_glibc(w0, &ss, &cs);
+    const float2 sc = dev_sincosf(w0);
+    const float ss = sc.x, cs = sc.y;
     // serial: cos(l*w0) by rotation, Rm0 = sum M^2, Rm1 = sum M^2 cos, all in harmonic order
     float c = 1.0f, s = 0.0f, Rm0 = 0.0f, Rm1 = 0.0f, cw0 = 0.0f, cw1 = 0.0f;
+#pragma unroll 2
     for (int l = 1; l <= L; ++l) {
         float cn = (c * cs) - (s * ss);
         float sn = (s * cs) + (c * ss);
@@ -131,6 +144,7 @@ __device__ __forceinline__ float spectral_enhance(Parms& cur, int lane) {
     }
     __syncwarp();
     float sum = 0.0f;
+#pragma unroll 4
     for (int l = 1; l <= L; ++l) {
         float M = cur.Ml[l];
         if (M < 0.0f) {
@@ -199,6 +213,7 @@ __device__ __forceinline__ void adaptive_smoothing(Parms& cur, const Parms& prev
         }
     }
     float Am = 0.0f;
+#pragma unroll 4
     for (int l = 1; l <= L; ++l) {
         Am += cur.Ml[l];
     }
@@ -217,49 +232,59 @@ __device__ __forceinline__ void adaptive_smoothing(Parms& cur, const Parms& prev
 }
 
 // ---- comfort noise (mbe_adaptive.c:116-131): java.util.Random-style LCG, jump-ahead per lane ------
-__device__ __forceinline__ void comfort_noise(float acc[5], StreamRng& rng, const DevTables* T, int lane) {
+__device__ __noinline__ void comfort_noise(WarpWS& ws, const DevTables* T, int lane) {
     const float gain = (0.003f * 32767.0f) / 7.0f;
     const unsigned long long mask = (1ULL << 48) - 1ULL;
-    const unsigned long long s0 = rng.comfort;
-#pragma unroll
+    const unsigned long long s0 = ws.rng.comfort;
+    __syncwarp();
+#pragma unroll 1
     for (int c = 0; c < 5; ++c) {
         const int i = 32 * c + lane;
         const unsigned long long st = (T->cnA[i + 1] * s0 + T->cnC[i + 1]) & mask;
         const unsigned r24 = (unsigned)(st >> 24);
         const float u = ((float)r24 / 16777216.0f) * 2.0f - 1.0f;
-        acc[c] = u * gain;
+        ws.out[i] = u * gain;
     }
-    rng.comfort = (T->cnA[160] * s0 + T->cnC[160]) & mask;
+    if (lane == 0) {
+        ws.rng.comfort = (T->cnA[160] * s0 + T->cnC[160]) & mask;
+    }
+    __syncwarp();
 }
 
 // ---- white noise with overlap (mbe_unvoiced_fft.c:304-341) --------------------------------------
-__device__ __forceinline__ void make_noise(WarpWS& ws, StreamRng& rng, const DevTables* T, int lane) {
+// Writes the windowed buffer (noise * W256) straight into the FFT input ws.A and keeps the raw samples
+// 1..56 (the ones the phase update reads) in ws.nz.
+__device__ __forceinline__ void make_noise(WarpWS& ws, const DevTables* T, const BlockTables* bt, int lane) {
     Parms& cur = ws.cur;
     const float seed = cur.noiseSeed;
     if (seed < 0.0f) {
         for (int i = lane; i < NFFT; i += 32) {
-            ws.noise[i] = 0.0f;
+            ws.A[i] = 0.0f;  // 0 * window
+        }
+        for (int i = lane; i < 57; i += 32) {
+            ws.nz[i] = 0.0f;
         }
         for (int i = lane; i < 96; i += 32) {
             cur.noiseOverlap[i] = 0.0f;
         }
-        float ns;
-        if (rng.uv_override) {
-            ns = (float)rng.uv_seed;
-            rng.uv_override = 0;
-        } else {
-            ns = 3147.0f;
-        }
+        const float ns = ws.rng.uv_override ? (float)ws.rng.uv_seed : 3147.0f;
         __syncwarp();
         if (lane == 0) {
             cur.noiseSeed = ns;
+            ws.rng.uv_override = 0;  // the override is consumed by the first cold start only
         }
         __syncwarp();
         return;
     }
     const unsigned st0 = ((unsigned)seed) % 53125u;
-    for (int i = lane; i < 96; i += 32) {
-        ws.noise[i] = cur.noiseOverlap[i];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int i = 32 * r + lane;
+        const float v = cur.noiseOverlap[i];
+        ws.A[i] = v * bt->uvwin[i];
+        if (i < 57) {
+            ws.nz[i] = v;
+        }
     }
     __syncwarp();
 #pragma unroll
@@ -267,7 +292,7 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, StreamRng& rng, const Dev
         const int i = 32 * c + lane;
         const unsigned st = (T->uvA[i] * st0 + T->uvC[i]) % 53125u;
         const float v = (float)st;
-        ws.noise[96 + i] = v;
+        ws.A[96 + i] = v * bt->uvwin[96 + i];
         if (i >= 64) {
             cur.noiseOverlap[i - 64] = v;  // overlap <- buffer[160..255]
         }
@@ -281,11 +306,17 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, StreamRng& rng, const Dev
 }
 
 // ---- 256-point real FFT: FFTPACK radix-4 passes, lanes over butterflies -------------------------
-__device__ __forceinline__ void rfft_fwd4(int ido, int l1, const float* in, float* out, const float* w1,
-                                          const float* w2, const float* w3, int lane) {
+// One generic pass each way (kept out of line: 8 calls per frame share two code bodies).  `w` points
+// at the pass's first twiddle row; rows two and three follow at +ido and +2*ido.  `recip` =
+// ceil(65536 / (ido/2 - 1)) turns the flattened butterfly index into (k, i) without a division.
+__device__ __noinline__ void rfft_fwd_pass(int ido, int l1, unsigned recip, const float* __restrict__ in,
+                                           float* __restrict__ out, const float* __restrict__ w, int lane) {
 #define FIN(i, k, j)  in[(i) + ido * ((k) + l1 * (j))]
 #define FOUT(i, j, k) out[(i) + ido * ((j) + 4 * (k))]
     const float nhs2 = -0.70710678118654752440f;
+    const float* w1 = w;
+    const float* w2 = w + ido;
+    const float* w3 = w + 2 * ido;
     for (int k = lane; k < l1; k += 32) {
         float a0 = FIN(0, k, 0), a1 = FIN(0, k, 1), a2 = FIN(0, k, 2), a3 = FIN(0, k, 3);
         float tr1 = a1 + a3;
@@ -297,8 +328,9 @@ __device__ __forceinline__ void rfft_fwd4(int ido, int l1, const float* in, floa
     }
     if (ido >= 2) {
         const int ni = ido / 2 - 1;
-        for (int it = lane; it < l1 * ni; it += 32) {
-            const int k = it / ni;
+        const int it = lane;  // l1 * ni <= 31 for every pass of N = 256
+        if (it < l1 * ni) {
+            const int k = (int)(((unsigned)it * recip) >> 16);
             const int i = 2 + 2 * (it - k * ni);
             const int ic = ido - i;
             float cr2 = FIN(i - 1, k, 1), ci2 = FIN(i, k, 1);
@@ -328,7 +360,8 @@ __device__ __forceinline__ void rfft_fwd4(int ido, int l1, const float* in, floa
             FOUT(i, 2, k) = tr4 + ti3;
             FOUT(ic, 1, k) = tr4 - ti3;
         }
-        for (int k = lane; k < l1; k += 32) {
+        if (lane < l1) {
+            const int k = lane;
             float a = FIN(ido - 1, k, 1), b = FIN(ido - 1, k, 3);
             float c = FIN(ido - 1, k, 0), d = FIN(ido - 1, k, 2);
             float ti1 = nhs2 * (a + b);
@@ -344,11 +377,14 @@ __device__ __forceinline__ void rfft_fwd4(int ido, int l1, const float* in, floa
 #undef FOUT
 }
 
-__device__ __forceinline__ void rfft_bwd4(int ido, int l1, const float* in, float* out, const float* w1,
-                                          const float* w2, const float* w3, int lane) {
+__device__ __noinline__ void rfft_bwd_pass(int ido, int l1, unsigned recip, const float* __restrict__ in,
+                                           float* __restrict__ out, const float* __restrict__ w, int lane) {
 #define BIN(i, j, k)  in[(i) + ido * ((j) + 4 * (k))]
 #define BOUT(i, k, j) out[(i) + ido * ((k) + l1 * (j))]
     const float nsq2 = -1.41421356237309504880f;
+    const float* w1 = w;
+    const float* w2 = w + ido;
+    const float* w3 = w + 2 * ido;
     for (int k = lane; k < l1; k += 32) {
         float a = BIN(0, 0, k), b = BIN(ido - 1, 3, k), c = BIN(0, 2, k), d = BIN(ido - 1, 1, k);
         float tr3 = 2.f * d;
@@ -362,8 +398,9 @@ __device__ __forceinline__ void rfft_bwd4(int ido, int l1, const float* in, floa
     }
     if (ido >= 2) {
         const int ni = ido / 2 - 1;
-        for (int it = lane; it < l1 * ni; it += 32) {
-            const int k = it / ni;
+        const int it = lane;
+        if (it < l1 * ni) {
+            const int k = (int)(((unsigned)it * recip) >> 16);
             const int i = 2 + 2 * (it - k * ni);
             const int ic = ido - i;
             float tr1 = BIN(i - 1, 0, k) - BIN(ic - 1, 3, k);
@@ -399,7 +436,8 @@ __device__ __forceinline__ void rfft_bwd4(int ido, int l1, const float* in, floa
             BOUT(i - 1, k, 3) = cr4;
             BOUT(i, k, 3) = ci4;
         }
-        for (int k = lane; k < l1; k += 32) {
+        if (lane < l1) {
+            const int k = lane;
             float c = BIN(ido - 1, 0, k), d = BIN(ido - 1, 2, k);
             float a = BIN(0, 1, k), b = BIN(0, 3, k);
             float tr1 = c - d;
@@ -417,30 +455,28 @@ __device__ __forceinline__ void rfft_bwd4(int ido, int l1, const float* in, floa
 #undef BOUT
 }
 
-// ---- unvoiced synthesis (mbe_unvoiced_fft.c:714-761); adds into acc[] and writes cur.previousUw --
-// Spectrum is kept in FFTPACK's native layout F[0]=DC, F[2b-1]=Re(b), F[2b]=Im(b), F[255]=Nyquist; the
-// reference's "ordered" layout is only a permutation of it, so no reorder pass is needed.
-__device__ __forceinline__ void unvoiced_synthesis(float acc[5], WarpWS& ws, const DevTables* T, const float* tw,
-                                                   int lane) {
+// ---- unvoiced synthesis (mbe_unvoiced_fft.c:714-761); adds into ws.out and writes cur.previousUw --
+// ws.A holds the windowed noise on entry.  Spectrum is kept in FFTPACK's native layout F[0]=DC,
+// F[2b-1]=Re(b), F[2b]=Im(b), F[255]=Nyquist; the reference's "ordered" layout is only a permutation of
+// it, so no reorder pass is needed.
+__device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, const BlockTables* bt, int lane) {
     Parms& cur = ws.cur;
     const Parms& prev = ws.enh;
     if (!bands_ok(cur.L) || !bands_ok(prev.L)) {
         return;
     }
-    float* A = ws.u.fft.a;
+    float* A = ws.A;
     float* B = ws.u.fft.b;
     float* scale = ws.u.fft.scale;
-    for (int i = lane; i < NFFT; i += 32) {
-        A[i] = ws.noise[i] * T->uvwin[i];
-    }
+    const float* tw = bt->tw;
     for (int i = lane; i < 129; i += 32) {
         scale[i] = 0.0f;
     }
     __syncwarp();
-    rfft_fwd4(1, 64, A, B, tw + 252, tw + 253, tw + 254, lane);
-    rfft_fwd4(4, 16, B, A, tw + 240, tw + 244, tw + 248, lane);
-    rfft_fwd4(16, 4, A, B, tw + 192, tw + 208, tw + 224, lane);
-    rfft_fwd4(64, 1, B, A, tw + 0, tw + 64, tw + 128, lane);
+    rfft_fwd_pass(1, 64, 0u, A, B, tw + 252, lane);
+    rfft_fwd_pass(4, 16, 65536u, B, A, tw + 240, lane);
+    rfft_fwd_pass(16, 4, 9363u, A, B, tw + 192, lane);
+    rfft_fwd_pass(64, 1, 2115u, B, A, tw + 0, lane);
 
     const int L = cur.L;
     const float mult = (256.0f / (2.0f * 3.14159265358979323846f)) * cur.w0;
@@ -479,11 +515,12 @@ __device__ __forceinline__ void unvoiced_synthesis(float acc[5], WarpWS& ws, con
         A[i] *= scale[bin];
     }
     __syncwarp();
-    rfft_bwd4(64, 1, A, B, tw + 0, tw + 64, tw + 128, lane);
-    rfft_bwd4(16, 4, B, A, tw + 192, tw + 208, tw + 224, lane);
-    rfft_bwd4(4, 16, A, B, tw + 240, tw + 244, tw + 248, lane);
-    rfft_bwd4(1, 64, B, A, tw + 252, tw + 253, tw + 254, lane);
+    rfft_bwd_pass(64, 1, 2115u, A, B, tw + 0, lane);
+    rfft_bwd_pass(16, 4, 9363u, B, A, tw + 192, lane);
+    rfft_bwd_pass(4, 16, 65536u, A, B, tw + 240, lane);
+    rfft_bwd_pass(1, 64, 0u, B, A, tw + 252, lane);
     const float inv = 1.0f / (float)NFFT;
+    // scale by 1/N and hand the block to the state; the WOLA below reads this frame's samples back
     for (int i = lane; i < NFFT; i += 32) {
         A[i] *= inv;
     }
@@ -492,11 +529,11 @@ __device__ __forceinline__ void unvoiced_synthesis(float acc[5], WarpWS& ws, con
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
         const int n = 32 * c + lane;
-        const float den = T->wola_den[n];
+        const float den = bt->wola_den[n];
         const float ps = (n + 128 < NFFT) ? prev.previousUw[n + 128] : 0.0f;
         const float cs = (n - 32 >= 0) ? A[n - 32] : 0.0f;
         if (den > 1e-10f) {
-            acc[c] += ((T->wola_wp[n] * ps) + (T->wola_wc[n] * cs)) / den;
+            ws.out[n] += ((bt->wola_wp[n] * ps) + (bt->wola_wc[n] * cs)) / den;
         }
     }
     __syncwarp();
@@ -509,7 +546,13 @@ __device__ __forceinline__ void unvoiced_synthesis(float acc[5], WarpWS& ws, con
 // ---- voiced oscillator bank (mbelib.c:953-1040) --------------------------------------------------
 // kinds: 0 = previous-frame windowed component, 1 = current-frame windowed component,
 //        2 = phase/amplitude-interpolated harmonic (l < 8, both voiced, stable pitch)
-__device__ __forceinline__ void voiced_bank(float acc[5], WarpWS& ws, const DevTables* T, int maxl, int lane) {
+// Pass structure (32 components x 32 samples at a time):
+//   phase A  lane = component: runs its oscillator 32 steps and writes the finished contribution
+//            (gain*W[n])*cos into tile[n][component];
+//   phase B  lane = sample: adds the tile row in component order (LDS.128, four adds each).
+// Windowed components whose gain is exactly zero (the faded bands of mbelib.c:912-929) are dropped:
+// their contribution is +-0 and x + (+-0) == x for every accumulator value that can occur.
+__device__ __forceinline__ void voiced_bank(WarpWS& ws, const BlockTables* bt, int maxl, int lane) {
     const Parms& cur = ws.cur;
     const Parms& prev = ws.enh;
     const float cw0 = cur.w0, pw0 = prev.w0;
@@ -521,13 +564,23 @@ __device__ __forceinline__ void voiced_bank(float acc[5], WarpWS& ws, const DevT
     for (int r = 0; r < 2; ++r) {
         const int l = 1 + lane + 32 * r;
         bool cv = false, pv = false;
+        float gp = 0.0f, gc = 0.0f;
         if (l <= maxl) {
             cv = (cur.Vl[l] == 1);
             pv = (prev.Vl[l] == 1);
+            gp = 2.0f * prev.Ml[l];
+            gc = 2.0f * cur.Ml[l];
+            // keep zero-gain components whose phase is not finite (their product is NaN, not 0)
+            if (gp == 0.0f && !isfinite(prev.PHIl[l])) {
+                gp = __int_as_float(0x7fc00000);
+            }
+            if (gc == 0.0f && !isfinite(cur.PHIl[l])) {
+                gc = __int_as_float(0x7fc00000);
+            }
         }
         const bool interp = (l < 8) && cv && pv && stable;
-        const bool first = pv || interp;          // first slot of this harmonic
-        const bool second = cv && !interp;        // second slot
+        const bool first = interp || (pv && gp != 0.0f);   // first slot of this harmonic
+        const bool second = cv && !interp && gc != 0.0f;   // second slot
         const unsigned mf = __ballot_sync(FULL, first);
         const unsigned ms = __ballot_sync(FULL, second);
         const unsigned lt = (1u << lane) - 1u;
@@ -545,48 +598,64 @@ __device__ __forceinline__ void voiced_bank(float acc[5], WarpWS& ws, const DevT
     }
     __syncwarp();
 
-    const float* Wv = T->voiced_win;
     float* tile = ws.u.tile;
+#pragma unroll 1
     for (int g0 = 0; g0 < ncomp; g0 += 32) {
         const int cnt = min(32, ncomp - g0);
-        // oscillator owned by this lane
-        float c = 0.f, s = 0.f, cd = 0.f, sd = 0.f;
-        const bool osc = (lane < cnt) && ((ws.comp[g0 + lane] & 3) != 2);
-        if (osc) {
-            const int id = ws.comp[g0 + lane];
+        // oscillator owned by this lane; idle lanes and interpolated slots write zeros
+        float g = 0.f, c = 0.f, s = 0.f, cd = 0.f, sd = 0.f;
+        const float* Wb = bt->voiced_win;
+        int id = 0;
+        if (lane < cnt) {
+            id = ws.comp[g0 + lane];
+        }
+        const bool k2 = (lane < cnt) && ((id & 3) == 2);
+        if ((lane < cnt) && !k2) {
             const int l = id >> 2;
             float step, ph;
             if ((id & 3) == 0) {
                 step = pw0 * (float)l;
                 ph = prev.PHIl[l];
+                Wb = bt->voiced_win + NS;
             } else {
                 step = cw0 * (float)l;
                 ph = cur.PHIl[l] - (step * (float)NS);
             }
-            mbelibm::sincosf_glibc(step, &sd, &cd);
-            mbelibm::sincosf_glibc(ph, &s, &c);
+            g = ws.gain[g0 + lane];
+            const float2 d = dev_sincosf(step);
+            const float2 p = dev_sincosf(ph);
+            sd = d.x;
+            cd = d.y;
+            s = p.x;
+            c = p.y;
         }
-#pragma unroll
+        const unsigned k2mask = __ballot_sync(FULL, k2);
+        const int nq = (cnt + 3) >> 2;
+#pragma unroll 1
         for (int ch = 0; ch < 5; ++ch) {
-            if (osc) {
-#pragma unroll 8
-                for (int n = 0; n < 32; ++n) {
-                    tile[n * TILE_STRIDE + lane] = c;
+            const float* W = Wb + 32 * ch;
+            float* trow = tile + lane;
+#pragma unroll
+            for (int n4 = 0; n4 < 8; ++n4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(W + 4 * n4);
+                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    trow[(4 * n4 + k) * TILE_STRIDE] = (g * wv[k]) * c;
                     const float cn = (c * cd) - (s * sd);
                     const float sn = (s * cd) + (c * sd);
                     c = cn;
                     s = sn;
                 }
             }
-            __syncwarp();
             const int n = 32 * ch + lane;
-            const float Wp = Wv[n + NS], Wc = Wv[n];
-            float a = acc[ch];
-            for (int j = 0; j < cnt; ++j) {
-                const int id = ws.comp[g0 + j];
-                const int kind = id & 3;
-                if (kind == 2) {
-                    const int l = id >> 2;
+            if (k2mask) {
+                __syncwarp();
+                unsigned m = k2mask;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int l = ws.comp[g0 + j] >> 2;
                     const float pw0l = pw0 * (float)l;
                     const float dphi = cur.PHIl[l] - prev.PHIl[l] - (((pw0 + cw0) * (float)(l * NS)) / 2.0f);
                     const float dw = (1.0f / (float)NS)
@@ -594,39 +663,46 @@ __device__ __forceinline__ void voiced_bank(float acc[5], WarpWS& ws, const DevT
                     const float th = prev.PHIl[l] + ((pw0l + dw) * (float)n)
                                      + (((cw0 - pw0) * (float)(l * n * n)) / (float)(2 * NS));
                     const float am = prev.Ml[l] + (((float)n / (float)NS) * (cur.Ml[l] - prev.Ml[l]));
-                    a += 2.0f * am * mbelibm::cosf_glibc(th);
-                } else {
-                    const float gw = ws.gain[g0 + j] * (kind ? Wc : Wp);
-                    a += gw * tile[lane * TILE_STRIDE + j];
+                    tile[lane * TILE_STRIDE + j] = 2.0f * am * dev_cosf(th);
                 }
             }
-            acc[ch] = a;
+            __syncwarp();
+            float a = ws.out[n];
+            const float4* row = reinterpret_cast<const float4*>(tile + lane * TILE_STRIDE);
+#pragma unroll 2
+            for (int q = 0; q < nq; ++q) {
+                const float4 v = row[q];
+                a += v.x;
+                a += v.y;
+                a += v.z;
+                a += v.w;
+            }
+            ws.out[n] = a;
             __syncwarp();
         }
     }
 }
 
 // ---- mbe_synthesizeSpeechCore (mbelib.c:1042-1105): cur = ws.cur, prev = ws.enh ------------------
-// returns with the 160 float samples in acc[]
-__device__ __forceinline__ void synthesize_speech(float acc[5], WarpWS& ws, StreamRng& rng, const DevTables* T,
-                                                  const float* tw, int has_rm0, float rm0, int lane) {
+// leaves the 160 float samples in ws.out
+__device__ __noinline__ void synthesize_speech(WarpWS& ws, const DevTables* T, const BlockTables* bt, int has_rm0,
+                                               float rm0, int lane) {
     Parms& cur = ws.cur;
     Parms& prev = ws.enh;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        acc[c] = 0.0f;
-    }
+    zero_out(ws, lane);
     if (!bands_ok(cur.L) || !bands_ok(prev.L)) {
+        __syncwarp();
         return;  // silence
     }
     adaptive_smoothing(cur, prev, has_rm0, rm0, lane);
 
     const bool mute_on_rate = fabsf(cur.mutingThreshold - 0.096f) > 1e-6f;
     if (cur.repeatCount >= 4 || (mute_on_rate && cur.errorRate > cur.mutingThreshold)) {
-        comfort_noise(acc, rng, T, lane);
+        comfort_noise(ws, T, lane);
+        __syncwarp();
         return;
     }
-    make_noise(ws, rng, T, lane);
+    make_noise(ws, T, bt, lane);
 
     // bands present in only one frame fade as zero-amplitude voiced bands (mbelib.c:912-929)
     int maxl;
@@ -672,26 +748,27 @@ __device__ __forceinline__ void synthesize_speech(float acc[5], WarpWS& ws, Stre
             if (l <= (cL / 4)) {
                 cur.PHIl[l] = psi;
             } else {
-                const float pl = ((2.0f * MBE_PI_F / 53125.0f) * ws.noise[l]) - MBE_PI_F;
+                const float pl = ((2.0f * MBE_PI_F / 53125.0f) * ws.nz[l]) - MBE_PI_F;
                 cur.PHIl[l] = psi + (((float)numUv * pl) / (float)cL);
             }
         }
     }
     __syncwarp();
 
-    voiced_bank(acc, ws, T, maxl, lane);
-    unvoiced_synthesis(acc, ws, T, tw, lane);
+    voiced_bank(ws, bt, maxl, lane);
+    unvoiced_synthesis(ws, bt, lane);
 
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
-        float v = acc[c];
+        float v = ws.out[32 * c + lane];
         if (v > MBE_CLIP_F) {
             v = MBE_CLIP_F;
         } else if (v < -MBE_CLIP_F) {
             v = -MBE_CLIP_F;
         }
-        acc[c] = v;
+        ws.out[32 * c + lane] = v;
     }
+    __syncwarp();
 }
 
 // ---- tone synthesis (mbelib.c:692-856, src/internal/mbe_tone.h) -----------------------------------
@@ -731,15 +808,14 @@ __device__ __forceinline__ unsigned tone_step(double hz) {
 __device__ __forceinline__ float tone_sample(unsigned phase) {
     const double rad_per_tick = (2.0 * 3.14159265358979323846) / 4294967296.0;
     float ang = (float)(((double)phase * rad_per_tick) - (3.14159265358979323846 / 2.0));
-    return mbelibm::sinf_glibc(ang);
+    return dev_sinf(ang);
 }
 
-__device__ __forceinline__ void render_tone(float acc[5], Parms& cur, float f1, float f2, int amp, int lane) {
+__device__ __noinline__ void render_tone(WarpWS& ws, float f1, float f2, int amp, int lane) {
+    Parms& cur = ws.cur;
     if (f1 <= 0.0f) {
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            acc[c] = 0.0f;
-        }
+        zero_out(ws, lane);
+        __syncwarp();
         return;
     }
     const bool dual = (f2 > 0.0f) && (fabsf(f2 - f1) > 1e-6f);
@@ -748,15 +824,15 @@ __device__ __forceinline__ void render_tone(float acc[5], Parms& cur, float f1, 
     const unsigned s2 = dual ? tone_step((double)f2) : 0u;
     const unsigned p1 = (unsigned)cur.swn, p2 = cur.tonePhase;
     __syncwarp();
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < 5; ++c) {
         const unsigned n1 = (unsigned)(32 * c + lane + 1);
         const float a = tone_sample(p1 + n1 * s1);
         if (dual) {
             const float b = tone_sample(p2 + n1 * s2);
-            acc[c] = (0.5f * gain * a) + (0.5f * gain * b);
+            ws.out[32 * c + lane] = (0.5f * gain * a) + (0.5f * gain * b);
         } else {
-            acc[c] = gain * a;
+            ws.out[32 * c + lane] = gain * a;
         }
     }
     if (lane == 0) {
