@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmbe_b200.so")
+# MBE_B200_LIB lets a developer A/B an experimental build of the same library; default is the in-tree product build
+LIB_PATH = os.environ.get("MBE_B200_LIB") or os.path.join(_HERE, "libmbe_b200.so")
 
 IMBE7200X4400, IMBE7100X4400, AMBE3600X2400, AMBE3600X2450 = 0, 1, 2, 3
 CODEC_BY_NAME = {"imbe7200x4400": 0, "imbe7100x4400": 1, "ambe3600x2400": 2, "ambe3600x2450": 3}

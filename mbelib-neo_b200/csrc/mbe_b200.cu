@@ -37,6 +37,9 @@ namespace hosttab {
 
 namespace mbe {
 
+#ifndef MBE_FRAME_BARRIER
+#define MBE_FRAME_BARRIER 0
+#endif
 constexpr int WARPS_PER_BLOCK = 7;
 
 constexpr unsigned FLAG_SOFT = 0x0001u, FLAG_C0 = 0x0002u, FLAG_C4 = 0x0004u, FLAG_TONE = 0x0010u,
@@ -401,9 +404,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) mbe_stream_kernel(const 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int s = blockIdx.x * WARPS_PER_BLOCK + warp;
+#if MBE_FRAME_BARRIER
+    const bool live = s < A.n_streams;
+    if (!live) {
+        for (int f = 0; f < A.n_frames; ++f) {
+            __syncthreads();
+        }
+        return;
+    }
+#else
     if (s >= A.n_streams) {
         return;
     }
+#endif
     WarpWS& ws = wsa[warp];
     uint32_t* wsw = reinterpret_cast<uint32_t*>(&ws.cur);  // cur, prev, enh are contiguous: 3*651 words
     constexpr bool AMBE = (CODEC >= MBE_B200_AMBE3600X2400);
@@ -425,6 +438,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) mbe_stream_kernel(const 
 
 #pragma unroll 1
     for (int f = 0; f < A.n_frames; ++f) {
+#if MBE_FRAME_BARRIER
+        __syncthreads();  // keep the block's warps in the same code region (instruction cache)
+#endif
         const size_t idx = (size_t)s * A.n_frames + f;
         const uint8_t* fr = A.frames + idx * fstride;
         unsigned dw[3];

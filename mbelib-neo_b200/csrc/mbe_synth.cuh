@@ -17,6 +17,10 @@
 
 namespace mbe {
 
+#ifndef MBE_OSC_UNROLL
+#define MBE_OSC_UNROLL 2
+#endif
+constexpr int kOscUnroll = MBE_OSC_UNROLL;  // oscillator steps per loop body = 4 * kOscUnroll
 #define MBE_PI_F 3.14159274101257324f /* (float)M_PI */
 #define MBE_CLIP_F ((32767.0f * 0.95f) / 7.0f)
 
@@ -635,7 +639,7 @@ __device__ __forceinline__ void voiced_bank(WarpWS& ws, const BlockTables* bt, i
         for (int ch = 0; ch < 5; ++ch) {
             const float* W = Wb + 32 * ch;
             float* trow = tile + lane;
-#pragma unroll
+#pragma unroll(kOscUnroll)
             for (int n4 = 0; n4 < 8; ++n4) {
                 const float4 w4 = *reinterpret_cast<const float4*>(W + 4 * n4);
                 const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
