@@ -37,10 +37,6 @@ namespace hosttab {
 
 namespace mbe {
 
-#ifndef MBE_FRAME_BARRIER
-#define MBE_FRAME_BARRIER 0
-#endif
-constexpr int WARPS_PER_BLOCK = 7;
 
 constexpr unsigned FLAG_SOFT = 0x0001u, FLAG_C0 = 0x0002u, FLAG_C4 = 0x0004u, FLAG_TONE = 0x0010u,
                    FLAG_ERASURE = 0x0020u, FLAG_REPEAT = 0x0040u, FLAG_MUTE = 0x0080u;
@@ -88,10 +84,10 @@ __device__ __forceinline__ int resolve_total_errors(int c0, int prot, int c4, in
 }
 
 // ---- IMBE 4400 frame state machine (imbe7200x4400.c:780-888) --------------------------------------
-__device__ __forceinline__ Action process_imbe(FrameCtx& fc, const unsigned dw[3], WarpWS& ws, const DevTables* T,
-                                               int lane) {
+__device__ __forceinline__ Action process_imbe(FrameCtx& fc, const unsigned dw[3], WarpWS& ws, const StreamHome& home,
+                                               const DevTables* T, int lane) {
     Parms& cur = ws.cur;
-    Parms& prev = ws.prev;
+    ParmsSmall& prev = ws.prev;
     const float rate = (0.95f * prev.errorRate) + (0.000365f * (float)fc.total);
     __syncwarp();
     if (lane == 0) {
@@ -137,7 +133,7 @@ __device__ __forceinline__ Action process_imbe(FrameCtx& fc, const unsigned dw[3
                 cur.mutingThreshold = 0.0875f;
             }
         } else {
-            copy_parms(&ws.cur, &ws.prev, lane);
+            cur_from_prev(ws, home, lane);
             if (lane == 0) {
                 cur.repeatCount = cur.repeatCount + 1;
             }
@@ -153,11 +149,14 @@ __device__ __forceinline__ Action process_imbe(FrameCtx& fc, const unsigned dw[3
 }
 
 // ---- AMBE helpers (ambe_common.c:191-271) ----------------------------------------------------------
-__device__ __forceinline__ void init_ambe(WarpWS& ws, const DevTables* T, int lane) {
-    init_all(ws, T->ambe_default_w0, 15, 0, 0.096f, lane);
+__device__ __forceinline__ void init_ambe(WarpWS& ws, const StreamHome& home, const DevTables* T, int lane) {
+    init_all(ws, home.prev, home.enh, T->ambe_default_w0, 15, 0, 0.096f, lane);
 }
 
-__device__ __forceinline__ void set_erasure_model(Parms& mp, const Parms& src, int lane) {
+// erasure model built in cur_mp from prev_mp: phases, noise generator and WOLA tail carried over
+__device__ __forceinline__ void set_erasure_model(WarpWS& ws, const StreamHome& home, int lane) {
+    Parms& mp = ws.cur;
+    const ParmsSmall& src = ws.prev;
     for (int l = lane; l <= 56; l += 32) {
         mp.Ml[l] = 1.0f;
         mp.Vl[l] = 0;
@@ -165,12 +164,7 @@ __device__ __forceinline__ void set_erasure_model(Parms& mp, const Parms& src, i
         mp.PHIl[l] = src.PHIl[l];
         mp.PSIl[l] = src.PSIl[l];
     }
-    for (int i = lane; i < 96; i += 32) {
-        mp.noiseOverlap[i] = src.noiseOverlap[i];
-    }
-    for (int i = lane; i < 256; i += 32) {
-        mp.previousUw[i] = src.previousUw[i];
-    }
+    bulk_load(mp, home.prev, lane);
     if (lane == 0) {
         mp.swn = 0;
         mp.tonePhase = 0;
@@ -185,10 +179,11 @@ __device__ __forceinline__ void set_erasure_model(Parms& mp, const Parms& src, i
     __syncwarp();
 }
 
-__device__ __forceinline__ void prepare_ambe(const FrameCtx& fc, WarpWS& ws, const DevTables* T, int lane) {
+__device__ __forceinline__ void prepare_ambe(const FrameCtx& fc, WarpWS& ws, const StreamHome& home, const DevTables* T,
+                                             int lane) {
     if (fabsf(ws.prev.mutingThreshold - 0.096f) > 1e-6f) {
         __syncwarp();
-        init_ambe(ws, T, lane);  // first AMBE frame after a generic init
+        init_ambe(ws, home, T, lane);  // first AMBE frame after a generic init
     }
     const float rate = (0.95f * ws.prev.errorRate) + (0.001064f * (float)fc.total);
     __syncwarp();
@@ -209,8 +204,8 @@ __device__ __forceinline__ int ambe_voice_or_mute(FrameCtx& fc, const WarpWS& ws
     return ACT_COMFORT_INIT;
 }
 
-__device__ __forceinline__ void ambe_repeat(WarpWS& ws, FrameCtx& fc, int lane) {
-    copy_parms(&ws.cur, &ws.prev, lane);
+__device__ __forceinline__ void ambe_repeat(WarpWS& ws, const StreamHome& home, FrameCtx& fc, int lane) {
+    cur_from_prev(ws, home, lane);
     if (lane == 0) {
         ws.cur.repeatCount = ws.cur.repeatCount + 1;
     }
@@ -219,10 +214,10 @@ __device__ __forceinline__ void ambe_repeat(WarpWS& ws, FrameCtx& fc, int lane) 
 }
 
 // ---- AMBE+2 3600x2450 (ambe3600x2450.c:716-877) -----------------------------------------------------
-__device__ __forceinline__ Action process_ambe2450(FrameCtx& fc, const unsigned dw[3], WarpWS& ws, const DevTables* T,
-                                                   int lane) {
+__device__ __forceinline__ Action process_ambe2450(FrameCtx& fc, const unsigned dw[3], WarpWS& ws,
+                                                   const StreamHome& home, const DevTables* T, int lane) {
     Action act = {ACT_COMFORT_INIT, 0.0f, 0.0f, 0, 0};
-    prepare_ambe(fc, ws, T, lane);
+    prepare_ambe(fc, ws, home, T, lane);
     const int bad = decode_ambe2450(dw, ws, T, fc.total, lane);
     __syncwarp();
     if (bad == 2) {
@@ -230,7 +225,7 @@ __device__ __forceinline__ Action process_ambe2450(FrameCtx& fc, const unsigned 
         if (lane == 0) {
             ws.cur.repeatCount = 0;
         }
-        set_erasure_model(ws.cur, ws.prev, lane);
+        set_erasure_model(ws, home, lane);
     } else if (bad == 7) {
         fc.flags |= FLAG_TONE;
         if (lane == 0) {
@@ -239,7 +234,7 @@ __device__ __forceinline__ Action process_ambe2450(FrameCtx& fc, const unsigned 
     } else {
         const bool repeat = fc.c0v ? ((fc.c0 >= 4) || ((fc.c0 >= 2) && (fc.total >= 6))) : (fc.total > 3);
         if (repeat) {
-            ambe_repeat(ws, fc, lane);
+            ambe_repeat(ws, home, fc, lane);
         } else if (lane == 0) {
             ws.cur.repeatCount = 0;
         }
@@ -275,10 +270,10 @@ __device__ __forceinline__ Action process_ambe2450(FrameCtx& fc, const unsigned 
 }
 
 // ---- AMBE 3600x2400 (ambe3600x2400.c:629-762) --------------------------------------------------------
-__device__ __forceinline__ Action process_ambe2400(FrameCtx& fc, const unsigned dw[3], WarpWS& ws, const DevTables* T,
-                                                   int lane) {
+__device__ __forceinline__ Action process_ambe2400(FrameCtx& fc, const unsigned dw[3], WarpWS& ws,
+                                                   const StreamHome& home, const DevTables* T, int lane) {
     Action act = {ACT_COMFORT_INIT, 0.0f, 0.0f, 0, 0};
-    prepare_ambe(fc, ws, T, lane);
+    prepare_ambe(fc, ws, home, T, lane);
     const int bad = decode_ambe2400(dw, ws, T, lane);
     __syncwarp();
     const bool clean_tone = (bad >= 7) && (bad <= 122) && (fc.c0 < 2) && (fc.total < 3);
@@ -290,7 +285,7 @@ __device__ __forceinline__ Action process_ambe2400(FrameCtx& fc, const unsigned 
     } else if (clean_tone) {
         // state untouched
     } else if (fc.total > 3) {
-        ambe_repeat(ws, fc, lane);
+        ambe_repeat(ws, home, fc, lane);
     } else if (lane == 0) {
         ws.cur.repeatCount = 0;
     }
@@ -307,12 +302,16 @@ __device__ __forceinline__ Action process_ambe2400(FrameCtx& fc, const unsigned 
     return act;
 }
 
-// ---- shared tail: render what the state machine decided, hand the state over ---------------------------
-// ACT_VOICE is the enhance + synthesise sandwich of imbe7200x4400.c:842-856 / ambe3600x2450.c:785-799;
-// `spill` is a 651-word HBM scratch (the stream's own state slot) used by the rare ACT_REPLAY.
+// ---- rendering what the state machine decided ---------------------------------------------------------
+// A frame is rendered in three steps so that the voiced bank can be shared by the whole block:
+//   render_begin   per warp: non-voice actions completely (tone, comfort noise); for voice frames the
+//                  enhance + smoothing + phase + component-list part (imbe7200x4400.c:842-856,
+//                  ambe3600x2450.c:785-799).  Returns 1 if the frame goes through the bank.
+//   voiced_bank_block  all warps of the block together.
+//   render_end     per warp: unvoiced synthesis, clip, state hand-over.
 template <bool AMBE>
-__device__ __forceinline__ void render_frame(const Action& act, WarpWS& ws, const DevTables* T, const BlockTables* bt,
-                                             uint32_t* spill, int lane) {
+__device__ __forceinline__ int render_begin(const Action& act, WarpWS& ws, const StreamHome& home, const DevTables* T,
+                                            int lane) {
     int kind = act.kind;
     if (!AMBE) {
         kind = ACT_VOICE;
@@ -320,43 +319,57 @@ __device__ __forceinline__ void render_frame(const Action& act, WarpWS& ws, cons
     if (kind == ACT_VOICE || kind == ACT_REPLAY) {
         float rm0 = 0.0f;
         int has_rm0 = 0;
-        uint32_t* cw = reinterpret_cast<uint32_t*>(&ws.cur);
         if (kind == ACT_VOICE) {
-            copy_parms(&ws.prev, &ws.cur, lane);
+            prev_from_cur(ws, home, lane);
             rm0 = spectral_enhance(ws.cur, lane);
             has_rm0 = 1;
         } else {
+            // replay the last voice model (ambe3600x2450.c:808-816): cur_mp is parked in its HBM home
+            const uint32_t* cw = reinterpret_cast<const uint32_t*>(&ws.cur);
             for (int i = lane; i < PARMS_WORDS; i += 32) {
-                spill[i] = cw[i];
+                home.cur[i] = cw[i];
             }
             __syncwarp();
-            copy_parms(&ws.cur, &ws.enh, lane);
+            cur_from_enh(ws, home, lane);
         }
-        synthesize_speech(ws, T, bt, has_rm0, rm0, lane);
-        copy_parms(&ws.enh, &ws.cur, lane);
-        if (AMBE && kind == ACT_REPLAY) {
-            for (int i = lane; i < PARMS_WORDS; i += 32) {
-                cw[i] = spill[i];
-            }
-            __syncwarp();
-        }
-        return;
+        return synth_begin(ws, T, has_rm0, rm0, lane);
     }
     if (AMBE) {
         if (kind == ACT_TONE) {
             render_tone(ws, act.f1, act.f2, act.amp, lane);
             if (act.keep_prev) {
-                copy_parms(&ws.prev, &ws.cur, lane);
+                prev_from_cur(ws, home, lane);
             }
-            return;
+            return 0;
         }
         comfort_noise(ws, T, lane);
         if (kind == ACT_COMFORT_ERASURE) {
-            copy_parms(&ws.prev, &ws.cur, lane);
-            copy_parms(&ws.enh, &ws.cur, lane);
+            prev_from_cur(ws, home, lane);
+            enh_from_cur(ws, home, lane);
         } else {
-            init_ambe(ws, T, lane);
+            init_ambe(ws, home, T, lane);
         }
+    }
+    return 0;
+}
+
+template <bool AMBE>
+__device__ __forceinline__ void render_end(const Action& act, int go, WarpWS& ws, const StreamHome& home,
+                                           const DevTables* T, const BlockTables* bt, int lane) {
+    const int kind = AMBE ? act.kind : (int)ACT_VOICE;
+    if (kind != ACT_VOICE && kind != ACT_REPLAY) {
+        return;
+    }
+    if (go) {
+        synth_finish(ws, reinterpret_cast<const float*>(home.enh + UW_WORD), T, bt, lane);
+    }
+    enh_from_cur(ws, home, lane);
+    if (AMBE && kind == ACT_REPLAY) {
+        uint32_t* cw = reinterpret_cast<uint32_t*>(&ws.cur);
+        for (int i = lane; i < PARMS_WORDS; i += 32) {
+            cw[i] = home.cur[i];
+        }
+        __syncwarp();
     }
 }
 
@@ -390,156 +403,43 @@ __device__ __forceinline__ void store_pcm(const LaunchArgs& A, const WarpWS& ws,
     }
 }
 
-// =====================================================================================================
-// The stream kernel: CODEC in {0..3}, SOFT in {0,1}, MODE in {MODE_FRAMES, MODE_DATA}
-// =====================================================================================================
-template <int CODEC, int SOFT, int MODE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) mbe_stream_kernel(const LaunchArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    BlockTables* bt = reinterpret_cast<BlockTables*>(smem_raw);
-    WarpWS* wsa = reinterpret_cast<WarpWS*>(smem_raw + sizeof(BlockTables));
-    const DevTables* T = A.tab;
-    load_block_tables(bt, T);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * WARPS_PER_BLOCK + warp;
-#if MBE_FRAME_BARRIER
-    const bool live = s < A.n_streams;
-    if (!live) {
-        for (int f = 0; f < A.n_frames; ++f) {
-            __syncthreads();
-        }
-        return;
+// stream state: HBM slot <-> shared memory (cur complete, prev / enh without their bulk arrays)
+__device__ __forceinline__ void load_stream(WarpWS& ws, const uint32_t* gs, int lane) {
+    uint32_t* c = reinterpret_cast<uint32_t*>(&ws.cur);
+    uint32_t* p = reinterpret_cast<uint32_t*>(&ws.prev);
+    uint32_t* e = reinterpret_cast<uint32_t*>(&ws.enh);
+    for (int i = lane; i < PARMS_WORDS; i += 32) {
+        c[i] = gs[i];
     }
-#else
-    if (s >= A.n_streams) {
-        return;
-    }
-#endif
-    WarpWS& ws = wsa[warp];
-    uint32_t* wsw = reinterpret_cast<uint32_t*>(&ws.cur);  // cur, prev, enh are contiguous: 3*651 words
-    constexpr bool AMBE = (CODEC >= MBE_B200_AMBE3600X2400);
-    constexpr int fbits = (CODEC == MBE_B200_IMBE7200X4400) ? 184 : (CODEC == MBE_B200_IMBE7100X4400 ? 168 : 96);
-    constexpr int pbits = AMBE ? 49 : 88;
-    constexpr size_t fstride = (MODE == MODE_DATA) ? (size_t)pbits : (size_t)fbits * (SOFT ? 2u : 1u);
-
-    const int stream = A.first_stream + s;
-    uint32_t* gs = A.state + (size_t)stream * STATE_WORDS;
-    for (int i = lane; i < 3 * PARMS_WORDS; i += 32) {
-        wsw[i] = gs[i];
+    for (int i = lane; i < HEAD_WORDS; i += 32) {
+        p[i] = gs[PARMS_WORDS + i];
+        e[i] = gs[2 * PARMS_WORDS + i];
     }
     if (lane == 0) {
+        p[HEAD_WORDS] = gs[PARMS_WORDS + SEED_WORD];
+        e[HEAD_WORDS] = gs[2 * PARMS_WORDS + SEED_WORD];
         ws.rng.comfort = (unsigned long long)gs[3 * PARMS_WORDS] | ((unsigned long long)gs[3 * PARMS_WORDS + 1] << 32);
         ws.rng.uv_seed = gs[3 * PARMS_WORDS + 2];
         ws.rng.uv_override = gs[3 * PARMS_WORDS + 3];
     }
     __syncwarp();
+}
 
-#pragma unroll 1
-    for (int f = 0; f < A.n_frames; ++f) {
-#if MBE_FRAME_BARRIER
-        __syncthreads();  // keep the block's warps in the same code region (instruction cache)
-#endif
-        const size_t idx = (size_t)s * A.n_frames + f;
-        const uint8_t* fr = A.frames + idx * fstride;
-        unsigned dw[3];
-        FrameCtx fc;
-        int status;
-        mbe_b200_result rout;
-        rout.c0_errors = rout.protected_errors = rout.c4_errors = rout.total_errors = 0;
-        rout.flags = 0;
-
-        if (MODE == MODE_FRAMES) {
-            FrontResult R = front_end(CODEC, SOFT, fr, dw, ws.rel, ws.u.dec.cost, ws.rowbits, T, lane);
-            status = R.status;
-            fc.total = R.c0 + R.prot;
-            fc.c0 = R.c0;
-            fc.c0v = 1;
-            fc.c4 = R.c4;
-            fc.c4v = (R.flags & FLAG_C4) ? 1 : 0;
-            fc.flags = R.flags;
-        } else {
-            // parameter bits from memory + optional decode context (mbe_process<Codec>Data semantics)
-            bool bad = false;
-#pragma unroll
-            for (int w = 0; w < 3; ++w) {
-                const int i = 32 * w + lane;
-                unsigned b = 0;
-                if (i < pbits) {
-                    const unsigned v = fr[i];
-                    bad |= (v > 1u);
-                    b = v & 1u;
-                }
-                dw[w] = __ballot_sync(FULL, b);
-            }
-            int c0 = 0, prot = 0, c4 = 0, tin = 0;
-            unsigned fl = 0;
-            if (A.results) {
-                const mbe_b200_result rin = A.results[idx];
-                c0 = rin.c0_errors;
-                prot = rin.protected_errors;
-                c4 = rin.c4_errors;
-                tin = rin.total_errors;
-                fl = rin.flags;
-                rout = rin;
-            }
-            int total = 0;
-            status = resolve_total_errors(c0, prot, c4, tin, fl, &total);
-            if (status == 0 && __any_sync(FULL, bad)) {
-                status = -2;
-            }
-            fc.flags = fl & CONTEXT_FLAGS;
-            fc.c0v = (fl & FLAG_C0) ? 1 : 0;
-            fc.c4v = (fl & FLAG_C4) ? 1 : 0;
-            fc.c0 = fc.c0v ? c0 : 0;
-            fc.c4 = fc.c4v ? c4 : 0;
-            fc.total = total;
-        }
-
-        if (status >= 0) {
-            Action act;
-            if (!AMBE) {
-                act = process_imbe(fc, dw, ws, T, lane);
-            } else if (CODEC == MBE_B200_AMBE3600X2400) {
-                act = process_ambe2400(fc, dw, ws, T, lane);
-            } else {
-                act = process_ambe2450(fc, dw, ws, T, lane);
-            }
-            render_frame<AMBE>(act, ws, T, bt, gs, lane);
-            status = fc.total;
-            rout.c0_errors = fc.c0;
-            rout.c4_errors = fc.c4;
-            rout.total_errors = fc.total;
-            rout.protected_errors = fc.total - fc.c0;
-            rout.flags = fc.flags;
-        } else {
-            zero_out(ws, lane);
-        }
-        __syncwarp();
-
-        store_pcm(A, ws, idx, lane);
-        if (A.results && lane == 0) {
-            rout.status = status;
-            A.results[idx] = rout;
-        }
-        if (A.bits && MODE == MODE_FRAMES) {
-#pragma unroll
-            for (int w = 0; w < 3; ++w) {
-                const int i = 32 * w + lane;
-                if (i < pbits) {
-                    A.bits[idx * pbits + i] = (uint8_t)((dw[w] >> lane) & 1u);
-                }
-            }
-        }
-        __syncwarp();
-    }
-
+__device__ __forceinline__ void store_stream(const WarpWS& ws, uint32_t* gs, int lane) {
+    const uint32_t* c = reinterpret_cast<const uint32_t*>(&ws.cur);
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(&ws.prev);
+    const uint32_t* e = reinterpret_cast<const uint32_t*>(&ws.enh);
     __syncwarp();
-    for (int i = lane; i < 3 * PARMS_WORDS; i += 32) {
-        gs[i] = wsw[i];
+    for (int i = lane; i < PARMS_WORDS; i += 32) {
+        gs[i] = c[i];
+    }
+    for (int i = lane; i < HEAD_WORDS; i += 32) {
+        gs[PARMS_WORDS + i] = p[i];
+        gs[2 * PARMS_WORDS + i] = e[i];
     }
     if (lane == 0) {
+        gs[PARMS_WORDS + SEED_WORD] = p[HEAD_WORDS];
+        gs[2 * PARMS_WORDS + SEED_WORD] = e[HEAD_WORDS];
         gs[3 * PARMS_WORDS] = (uint32_t)(ws.rng.comfort & 0xffffffffULL);
         gs[3 * PARMS_WORDS + 1] = (uint32_t)(ws.rng.comfort >> 32);
         gs[3 * PARMS_WORDS + 2] = ws.rng.uv_seed;
@@ -547,51 +447,213 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) mbe_stream_kernel(const 
     }
 }
 
-// batched mbe_synthesizeSpeech[f]: element s synthesises one frame from parameter blobs in device memory
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) mbe_synth_kernel(const LaunchArgs A) {
+// =====================================================================================================
+// The stream kernel: CODEC in {0..3}, SOFT in {0,1}, MODE in {MODE_FRAMES, MODE_DATA}
+// One block = WARPS_PER_BLOCK streams walking their frames in lockstep (see WARPS_PER_BLOCK).
+// =====================================================================================================
+template <int CODEC, int SOFT, int MODE>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2) mbe_stream_kernel(const LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BlockTables* bt = reinterpret_cast<BlockTables*>(smem_raw);
     WarpWS* wsa = reinterpret_cast<WarpWS*>(smem_raw + sizeof(BlockTables));
+    BlockShared* bs = reinterpret_cast<BlockShared*>(smem_raw + sizeof(BlockTables) + WARPS_PER_BLOCK * sizeof(WarpWS));
+    const DevTables* T = A.tab;
+    load_block_tables(bt, T);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const bool live = s < A.n_streams;  // idle warps of the last block still take part in the bank
+    WarpWS& ws = wsa[warp];
+    constexpr bool AMBE = (CODEC >= MBE_B200_AMBE3600X2400);
+    constexpr int fbits = (CODEC == MBE_B200_IMBE7200X4400) ? 184 : (CODEC == MBE_B200_IMBE7100X4400 ? 168 : 96);
+    constexpr int pbits = AMBE ? 49 : 88;
+    constexpr size_t fstride = (MODE == MODE_DATA) ? (size_t)pbits : (size_t)fbits * (SOFT ? 2u : 1u);
+
+    uint32_t* gs = A.state + (size_t)(A.first_stream + (live ? s : 0)) * STATE_WORDS;
+    const StreamHome home = {gs, gs + PARMS_WORDS, gs + 2 * PARMS_WORDS};
+    if (live) {
+        load_stream(ws, gs, lane);
+    }
+
+#pragma unroll 1
+    for (int f = 0; f < A.n_frames; ++f) {
+        __syncthreads();  // frame boundary: tiles / counters of the previous frame are dead
+        const size_t idx = (size_t)s * A.n_frames + f;
+        unsigned dw[3] = {0u, 0u, 0u};
+        FrameCtx fc;
+        int status = -1, go = 0;
+        Action act = {ACT_COMFORT_INIT, 0.0f, 0.0f, 0, 0};
+        mbe_b200_result rout;
+        rout.c0_errors = rout.protected_errors = rout.c4_errors = rout.total_errors = 0;
+        rout.flags = 0;
+
+        if (live) {
+            const uint8_t* fr = A.frames + idx * fstride;
+            if (MODE == MODE_FRAMES) {
+                FrontResult R = front_end(CODEC, SOFT, fr, dw, ws.rel, ws.u.dec.cost, ws.rowbits, T, lane);
+                status = R.status;
+                fc.total = R.c0 + R.prot;
+                fc.c0 = R.c0;
+                fc.c0v = 1;
+                fc.c4 = R.c4;
+                fc.c4v = (R.flags & FLAG_C4) ? 1 : 0;
+                fc.flags = R.flags;
+            } else {
+                // parameter bits from memory + optional decode context (mbe_process<Codec>Data semantics)
+                bool bad = false;
+#pragma unroll
+                for (int w = 0; w < 3; ++w) {
+                    const int i = 32 * w + lane;
+                    unsigned b = 0;
+                    if (i < pbits) {
+                        const unsigned v = fr[i];
+                        bad |= (v > 1u);
+                        b = v & 1u;
+                    }
+                    dw[w] = __ballot_sync(FULL, b);
+                }
+                int c0 = 0, prot = 0, c4 = 0, tin = 0;
+                unsigned fl = 0;
+                if (A.results) {
+                    const mbe_b200_result rin = A.results[idx];
+                    c0 = rin.c0_errors;
+                    prot = rin.protected_errors;
+                    c4 = rin.c4_errors;
+                    tin = rin.total_errors;
+                    fl = rin.flags;
+                    rout = rin;
+                }
+                int total = 0;
+                status = resolve_total_errors(c0, prot, c4, tin, fl, &total);
+                if (status == 0 && __any_sync(FULL, bad)) {
+                    status = -2;
+                }
+                fc.flags = fl & CONTEXT_FLAGS;
+                fc.c0v = (fl & FLAG_C0) ? 1 : 0;
+                fc.c4v = (fl & FLAG_C4) ? 1 : 0;
+                fc.c0 = fc.c0v ? c0 : 0;
+                fc.c4 = fc.c4v ? c4 : 0;
+                fc.total = total;
+            }
+
+            if (status >= 0) {
+                if (!AMBE) {
+                    act = process_imbe(fc, dw, ws, home, T, lane);
+                } else if (CODEC == MBE_B200_AMBE3600X2400) {
+                    act = process_ambe2400(fc, dw, ws, home, T, lane);
+                } else {
+                    act = process_ambe2450(fc, dw, ws, home, T, lane);
+                }
+                go = render_begin<AMBE>(act, ws, home, T, lane);
+            } else {
+                zero_out(ws, lane);
+            }
+        }
+        if (lane == 0) {
+            bs->cnt[warp] = go ? ws.ncomp : 0;
+        }
+        __syncthreads();
+        voiced_bank_block(wsa, bs, bt, warp, lane);
+
+        if (live) {
+            if (status >= 0) {
+                render_end<AMBE>(act, go, ws, home, T, bt, lane);
+                status = fc.total;
+                rout.c0_errors = fc.c0;
+                rout.c4_errors = fc.c4;
+                rout.total_errors = fc.total;
+                rout.protected_errors = fc.total - fc.c0;
+                rout.flags = fc.flags;
+            }
+            __syncwarp();
+            store_pcm(A, ws, idx, lane);
+            if (A.results && lane == 0) {
+                rout.status = status;
+                A.results[idx] = rout;
+            }
+            if (A.bits && MODE == MODE_FRAMES) {
+#pragma unroll
+                for (int w = 0; w < 3; ++w) {
+                    const int i = 32 * w + lane;
+                    if (i < pbits) {
+                        A.bits[idx * pbits + i] = (uint8_t)((dw[w] >> lane) & 1u);
+                    }
+                }
+            }
+        }
+    }
+    if (live) {
+        store_stream(ws, gs, lane);
+    }
+}
+
+// batched mbe_synthesizeSpeech[f]: element s synthesises one frame from parameter blobs in device memory
+// (cur[s] -> ws.cur, prev[s] -> ws.enh; prev's previousUw is read in place, both are updated in place)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2) mbe_synth_kernel(const LaunchArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BlockTables* bt = reinterpret_cast<BlockTables*>(smem_raw);
+    WarpWS* wsa = reinterpret_cast<WarpWS*>(smem_raw + sizeof(BlockTables));
+    BlockShared* bs = reinterpret_cast<BlockShared*>(smem_raw + sizeof(BlockTables) + WARPS_PER_BLOCK * sizeof(WarpWS));
     const DevTables* T = A.tab;
     load_block_tables(bt, T);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int s = blockIdx.x * WARPS_PER_BLOCK + warp;
-    if (s >= A.n_streams) {
-        return;
-    }
+    const bool live = s < A.n_streams;
     WarpWS& ws = wsa[warp];
-    uint32_t* gc = A.synth_cur + (size_t)s * PARMS_WORDS;
-    uint32_t* gp = A.synth_prev + (size_t)s * PARMS_WORDS;
+    uint32_t* gc = A.synth_cur + (size_t)(live ? s : 0) * PARMS_WORDS;
+    uint32_t* gp = A.synth_prev + (size_t)(live ? s : 0) * PARMS_WORDS;
     uint32_t* c = reinterpret_cast<uint32_t*>(&ws.cur);
     uint32_t* e = reinterpret_cast<uint32_t*>(&ws.enh);
-    for (int i = lane; i < PARMS_WORDS; i += 32) {
-        c[i] = gc[i];
-        e[i] = gp[i];
-    }
-    // RNG as after mbe_setThreadRngSeed(seed) (mbelib.c:173-181); no seeds: fresh-thread defaults
-    if (lane == 0) {
-        if (A.synth_seeds) {
-            unsigned seed = A.synth_seeds[s];
-            if (seed == 0u) {
-                seed = 0x6d25357bu;
-            }
-            ws.rng.comfort = (((unsigned long long)seed) ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1ULL);
-            ws.rng.uv_seed = seed % 53125u;
-            ws.rng.uv_override = 1;
-        } else {
-            ws.rng.comfort = (0x12345678ULL ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1ULL);
-            ws.rng.uv_seed = 3147u;
-            ws.rng.uv_override = 0;
+    int go = 0;
+    if (live) {
+        for (int i = lane; i < PARMS_WORDS; i += 32) {
+            c[i] = gc[i];
         }
+        for (int i = lane; i < HEAD_WORDS; i += 32) {
+            e[i] = gp[i];
+        }
+        // RNG as after mbe_setThreadRngSeed(seed) (mbelib.c:173-181); no seeds: fresh-thread defaults
+        if (lane == 0) {
+            e[HEAD_WORDS] = gp[SEED_WORD];
+            if (A.synth_seeds) {
+                unsigned seed = A.synth_seeds[s];
+                if (seed == 0u) {
+                    seed = 0x6d25357bu;
+                }
+                ws.rng.comfort = (((unsigned long long)seed) ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1ULL);
+                ws.rng.uv_seed = seed % 53125u;
+                ws.rng.uv_override = 1;
+            } else {
+                ws.rng.comfort = (0x12345678ULL ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1ULL);
+                ws.rng.uv_seed = 3147u;
+                ws.rng.uv_override = 0;
+            }
+        }
+        __syncwarp();
+        go = synth_begin(ws, T, 0, 0.0f, lane);
     }
-    __syncwarp();
-    synthesize_speech(ws, T, bt, 0, 0.0f, lane);
-    __syncwarp();
-    store_pcm(A, ws, (size_t)s, lane);
-    for (int i = lane; i < PARMS_WORDS; i += 32) {
-        gc[i] = c[i];
-        gp[i] = e[i];
+    if (lane == 0) {
+        bs->cnt[warp] = go ? ws.ncomp : 0;
+    }
+    __syncthreads();
+    voiced_bank_block(wsa, bs, bt, warp, lane);
+    if (live) {
+        if (go) {
+            synth_finish(ws, reinterpret_cast<const float*>(gp + UW_WORD), T, bt, lane);
+        }
+        __syncwarp();
+        store_pcm(A, ws, (size_t)s, lane);
+        for (int i = lane; i < PARMS_WORDS; i += 32) {
+            gc[i] = c[i];
+        }
+        for (int i = lane; i < HEAD_WORDS; i += 32) {
+            gp[i] = e[i];
+        }
+        if (lane == 0) {
+            gp[SEED_WORD] = e[HEAD_WORDS];
+        }
     }
 }
 
@@ -923,7 +985,9 @@ static void build_tables(DevTables* t) {
     }
 }
 
-static size_t stream_kernel_smem(void) { return sizeof(BlockTables) + (size_t)WARPS_PER_BLOCK * sizeof(WarpWS); }
+static size_t stream_kernel_smem(void) {
+    return sizeof(BlockTables) + (size_t)WARPS_PER_BLOCK * sizeof(WarpWS) + sizeof(BlockShared);
+}
 
 typedef void (*StreamKernelFn)(const LaunchArgs);
 

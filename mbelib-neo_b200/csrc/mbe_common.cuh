@@ -40,6 +40,39 @@ struct Parms {
     float noiseOverlap[96];
 };
 static_assert(sizeof(Parms) == MBE_B200_PARMS_BYTES, "mbe_parms layout");
+
+// The same struct without its two bulk arrays: what the kernel keeps in shared memory for prev_mp and
+// prev_mp_enhanced (their previousUw / noiseOverlap stay in the stream's HBM slot and are only touched
+// by whole-struct copies and by the overlap-add).  Words 0..297 are laid out exactly like Parms.
+struct ParmsSmall {
+    float w0;
+    int L;
+    int K;
+    int Vl[57];
+    float Ml[57];
+    float log2Ml[57];
+    float PHIl[57];
+    float PSIl[57];
+    float gamma;
+    uint32_t tonePhase;
+    int swn;
+    float localEnergy;
+    int amplitudeThreshold;
+    float errorRate;
+    int errorCountTotal;
+    int errorCount4;
+    int repeatCount;
+    float mutingThreshold;
+    float noiseSeed;
+};
+constexpr int HEAD_WORDS = 298;       // w0 .. mutingThreshold
+constexpr int UW_WORD = 298;          // previousUw[256]
+constexpr int SEED_WORD = 554;        // noiseSeed
+constexpr int OVERLAP_WORD = 555;     // noiseOverlap[96]
+static_assert(sizeof(ParmsSmall) == (HEAD_WORDS + 1) * 4, "ParmsSmall layout");
+static_assert(offsetof(Parms, previousUw) == UW_WORD * 4 && offsetof(Parms, noiseSeed) == SEED_WORD * 4 &&
+                  offsetof(Parms, noiseOverlap) == OVERLAP_WORD * 4 && offsetof(Parms, mutingThreshold) == 297 * 4,
+              "mbe_parms offsets");
 constexpr int PARMS_WORDS = sizeof(Parms) / 4;            // 651
 constexpr int RNG_WORDS = 4;                              // comfort lo, comfort hi, uv seed, uv override
 constexpr int STATE_WORDS = 3 * PARMS_WORDS + RNG_WORDS;  // per stream in HBM: cur, prev, enh, rng (7828 B)
@@ -130,6 +163,7 @@ struct __align__(16) WarpWS {
     union __align__(16) {
         float tile[32 * TILE_STRIDE];     // voiced bank: [sample][component], pre-weighted contributions
         struct {
+            float a[NFFT];                // FFT ping buffer (windowed noise on entry)
             float b[NFFT];                // FFT pong buffer
             float scale[132];             // per-bin unvoiced band scale
         } fft;
@@ -140,15 +174,26 @@ struct __align__(16) WarpWS {
             unsigned short cost[640];     // soft-decision partial cost tables
         } dec;
     } u;                                  // 16-byte aligned: rows are read with LDS.128
-    float A[NFFT];                        // windowed white noise of the frame, then FFT ping buffer
     float out[NS];                        // the frame's 160 float samples (lane i owns i, 32+i, ...)
     float gain[112];                      // per-component 2*Ml
-    Parms cur, prev, enh;                 // 7812 B, contiguous
+    Parms cur;                            // cur_mp, complete
+    ParmsSmall prev, enh;                 // prev_mp / prev_mp_enhanced without their bulk arrays
     float nz[57];                         // white-noise samples 1..56 of the frame (phase randomisation)
     unsigned rowbits[8];
+    int ncomp;                            // oscillator components of this frame (0: no voiced synthesis)
+    unsigned k2mask;                      // list positions (< 32) of phase-interpolated harmonics
     unsigned char comp[112];              // component descriptor: harmonic << 2 | kind
     unsigned char rel[8 * 24];            // soft-bit reliabilities of the frame
 };
 static_assert(offsetof(WarpWS, u) % 16 == 0 && sizeof(WarpWS) % 16 == 0 && sizeof(BlockTables) % 16 == 0, "LDS.128 alignment");
+
+// Streams (= warps) per block.  The block walks its streams' frames in lockstep: per frame every warp
+// decodes its own stream, then the block pools the oscillator components of all its streams and
+// spreads them evenly over all lanes (voiced_bank_block), then every warp finishes its own stream.
+constexpr int WARPS_PER_BLOCK = 9;
+
+struct BlockShared {
+    int cnt[WARPS_PER_BLOCK + 3];         // per stream: component count of the current frame
+};
 
 }  // namespace mbe

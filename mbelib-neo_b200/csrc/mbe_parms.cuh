@@ -28,7 +28,7 @@ __device__ __forceinline__ unsigned pick(const unsigned dw[3], const unsigned ch
 __device__ __forceinline__ void predict_magnitudes(WarpWS& ws, const DevTables* T, int ambe, float rho, float unvc,
                                                    int lane) {
     Parms& cur = ws.cur;
-    Parms& prev = ws.prev;
+    ParmsSmall& prev = ws.prev;
     const int cur_L = cur.L;  // already within 9..56
     int prev_L = prev.L;
     prev_L = prev_L < 1 ? 1 : (prev_L > 56 ? 56 : prev_L);

@@ -36,30 +36,96 @@ __device__ __noinline__ float dev_sinf(float y) { return mbelibm::sinf_glibc(y);
 
 __device__ __forceinline__ bool bands_ok(int L) { return L >= 1 && L <= MAXL; }
 
-__device__ __forceinline__ void copy_parms(Parms* dst, const Parms* src, int lane) {
-    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
-#pragma unroll 4
-    for (int i = lane; i < PARMS_WORDS; i += 32) {
+// ---- whole-struct copies ---------------------------------------------------------------------------
+// cur_mp lives completely in shared memory; prev_mp / prev_mp_enhanced keep only their first 298 words
+// + noiseSeed there, their previousUw / noiseOverlap arrays stay in the stream's HBM slot (`g` below
+// points at that struct's 651-word image).  Array element i is always moved by lane i % 32, so a lane
+// only ever reads back global words it wrote itself.
+template <class D, class S>
+__device__ __forceinline__ void copy_small(D& dst, const S& src, int lane) {
+    uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&src);
+#pragma unroll 5
+    for (int i = lane; i < HEAD_WORDS; i += 32) {
         d[i] = s[i];
+    }
+    if (lane == 0) {
+        dst.noiseSeed = src.noiseSeed;
     }
     __syncwarp();
 }
 
-// default model of mbe_initMbeParms / mbe_initAmbeParms_common, written to all three structs
-__device__ __forceinline__ void fill_default(Parms* p, float w0, int L, int K, float mute_thr, int lane) {
+__device__ __forceinline__ void bulk_store(const Parms& c, uint32_t* g, int lane) {
+    const uint32_t* uw = reinterpret_cast<const uint32_t*>(c.previousUw);
+    const uint32_t* ov = reinterpret_cast<const uint32_t*>(c.noiseOverlap);
+#pragma unroll
+    for (int i = lane; i < 256; i += 32) {
+        g[UW_WORD + i] = uw[i];
+    }
+#pragma unroll
+    for (int i = lane; i < 96; i += 32) {
+        g[OVERLAP_WORD + i] = ov[i];
+    }
+}
+
+__device__ __forceinline__ void bulk_load(Parms& c, const uint32_t* g, int lane) {
+    uint32_t* uw = reinterpret_cast<uint32_t*>(c.previousUw);
+    uint32_t* ov = reinterpret_cast<uint32_t*>(c.noiseOverlap);
+#pragma unroll
+    for (int i = lane; i < 256; i += 32) {
+        uw[i] = g[UW_WORD + i];
+    }
+#pragma unroll
+    for (int i = lane; i < 96; i += 32) {
+        ov[i] = g[OVERLAP_WORD + i];
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void bulk_zero(uint32_t* g, int lane) {
+#pragma unroll
+    for (int i = lane; i < 256; i += 32) {
+        g[UW_WORD + i] = 0u;
+    }
+#pragma unroll
+    for (int i = lane; i < 96; i += 32) {
+        g[OVERLAP_WORD + i] = 0u;
+    }
+}
+
+// HBM homes of the stream's three structs
+struct StreamHome {
+    uint32_t* cur;
+    uint32_t* prev;
+    uint32_t* enh;
+};
+
+__device__ __forceinline__ void prev_from_cur(WarpWS& ws, const StreamHome& h, int lane) {
+    copy_small(ws.prev, ws.cur, lane);
+    bulk_store(ws.cur, h.prev, lane);
+}
+__device__ __forceinline__ void enh_from_cur(WarpWS& ws, const StreamHome& h, int lane) {
+    copy_small(ws.enh, ws.cur, lane);
+    bulk_store(ws.cur, h.enh, lane);
+}
+__device__ __forceinline__ void cur_from_prev(WarpWS& ws, const StreamHome& h, int lane) {
+    copy_small(ws.cur, ws.prev, lane);
+    bulk_load(ws.cur, h.prev, lane);
+}
+__device__ __forceinline__ void cur_from_enh(WarpWS& ws, const StreamHome& h, int lane) {
+    copy_small(ws.cur, ws.enh, lane);
+    bulk_load(ws.cur, h.enh, lane);
+}
+
+// default model of mbe_initMbeParms / mbe_initAmbeParms_common (head fields + noiseSeed)
+template <class P>
+__device__ __forceinline__ void fill_default_small(P* p, float w0, int L, int K, float mute_thr, int lane) {
     for (int l = lane; l <= 56; l += 32) {
         p->Ml[l] = 1.0f;
         p->Vl[l] = 0;
         p->log2Ml[l] = 0.0f;
         p->PHIl[l] = 0.0f;
         p->PSIl[l] = 0.0f;
-    }
-    for (int i = lane; i < 256; i += 32) {
-        p->previousUw[i] = 0.0f;
-    }
-    for (int i = lane; i < 96; i += 32) {
-        p->noiseOverlap[i] = 0.0f;
     }
     if (lane == 0) {
         p->swn = 0;
@@ -80,10 +146,24 @@ __device__ __forceinline__ void fill_default(Parms* p, float w0, int L, int K, f
     __syncwarp();
 }
 
-__device__ __noinline__ void init_all(WarpWS& ws, float w0, int L, int K, float mute_thr, int lane) {
-    fill_default(&ws.prev, w0, L, K, mute_thr, lane);
-    copy_parms(&ws.cur, &ws.prev, lane);
-    copy_parms(&ws.enh, &ws.prev, lane);
+__device__ __forceinline__ void fill_default(Parms* p, float w0, int L, int K, float mute_thr, int lane) {
+    fill_default_small(p, w0, L, K, mute_thr, lane);
+    for (int i = lane; i < 256; i += 32) {
+        p->previousUw[i] = 0.0f;
+    }
+    for (int i = lane; i < 96; i += 32) {
+        p->noiseOverlap[i] = 0.0f;
+    }
+    __syncwarp();
+}
+
+__device__ __noinline__ void init_all(WarpWS& ws, uint32_t* gprev, uint32_t* genh, float w0, int L, int K, float mute_thr,
+                                      int lane) {
+    fill_default(&ws.cur, w0, L, K, mute_thr, lane);
+    copy_small(ws.prev, ws.cur, lane);
+    copy_small(ws.enh, ws.cur, lane);
+    bulk_zero(gprev, lane);
+    bulk_zero(genh, lane);
 }
 
 __device__ __forceinline__ void zero_out(WarpWS& ws, int lane) {
@@ -166,7 +246,8 @@ __device__ __forceinline__ float spectral_enhance(Parms& cur, int lane) {
 }
 
 // ---- adaptive smoothing, JMBE algorithms #111-116 (mbe_adaptive.c:151-276) -----------------------
-__device__ __forceinline__ void adaptive_smoothing(Parms& cur, const Parms& prev, int has_rm0, float rm0, int lane) {
+__device__ __forceinline__ void adaptive_smoothing(Parms& cur, const ParmsSmall& prev, int has_rm0, float rm0,
+                                                   int lane) {
     if (!bands_ok(cur.L) || !bands_ok(prev.L)) {
         return;
     }
@@ -256,17 +337,26 @@ __device__ __noinline__ void comfort_noise(WarpWS& ws, const DevTables* T, int l
 }
 
 // ---- white noise with overlap (mbe_unvoiced_fft.c:304-341) --------------------------------------
-// Writes the windowed buffer (noise * W256) straight into the FFT input ws.A and keeps the raw samples
-// 1..56 (the ones the phase update reads) in ws.nz.
+// noise_peek: the raw samples 1..56 of the frame's buffer (what the phase update reads) come from the
+// overlap of the previous buffer, or are zero on a cold start; nothing is advanced yet.
+__device__ __forceinline__ void noise_peek(WarpWS& ws, int lane) {
+    const Parms& cur = ws.cur;
+    const bool cold = cur.noiseSeed < 0.0f;
+    for (int i = lane; i < 57; i += 32) {
+        ws.nz[i] = cold ? 0.0f : cur.noiseOverlap[i];
+    }
+    __syncwarp();
+}
+
+// make_noise: builds the frame's 256-sample buffer, advances the LCG / overlap state and writes the
+// WINDOWED buffer (noise * W256) straight into the FFT input.
 __device__ __forceinline__ void make_noise(WarpWS& ws, const DevTables* T, const BlockTables* bt, int lane) {
     Parms& cur = ws.cur;
+    float* A = ws.u.fft.a;
     const float seed = cur.noiseSeed;
     if (seed < 0.0f) {
         for (int i = lane; i < NFFT; i += 32) {
-            ws.A[i] = 0.0f;  // 0 * window
-        }
-        for (int i = lane; i < 57; i += 32) {
-            ws.nz[i] = 0.0f;
+            A[i] = 0.0f;  // 0 * window
         }
         for (int i = lane; i < 96; i += 32) {
             cur.noiseOverlap[i] = 0.0f;
@@ -284,11 +374,7 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, const DevTables* T, const
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const int i = 32 * r + lane;
-        const float v = cur.noiseOverlap[i];
-        ws.A[i] = v * bt->uvwin[i];
-        if (i < 57) {
-            ws.nz[i] = v;
-        }
+        A[i] = cur.noiseOverlap[i] * bt->uvwin[i];
     }
     __syncwarp();
 #pragma unroll
@@ -296,7 +382,7 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, const DevTables* T, const
         const int i = 32 * c + lane;
         const unsigned st = (T->uvA[i] * st0 + T->uvC[i]) % 53125u;
         const float v = (float)st;
-        ws.A[96 + i] = v * bt->uvwin[96 + i];
+        A[96 + i] = v * bt->uvwin[96 + i];
         if (i >= 64) {
             cur.noiseOverlap[i - 64] = v;  // overlap <- buffer[160..255]
         }
@@ -460,16 +546,13 @@ __device__ __noinline__ void rfft_bwd_pass(int ido, int l1, unsigned recip, cons
 }
 
 // ---- unvoiced synthesis (mbe_unvoiced_fft.c:714-761); adds into ws.out and writes cur.previousUw --
-// ws.A holds the windowed noise on entry.  Spectrum is kept in FFTPACK's native layout F[0]=DC,
+// ws.u.fft.a holds the windowed noise on entry; enh_uw = prev_mp_enhanced->previousUw in HBM.  Spectrum is kept in FFTPACK's native layout F[0]=DC,
 // F[2b-1]=Re(b), F[2b]=Im(b), F[255]=Nyquist; the reference's "ordered" layout is only a permutation of
 // it, so no reorder pass is needed.
-__device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, const BlockTables* bt, int lane) {
+__device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, const float* __restrict__ enh_uw,
+                                                   const BlockTables* bt, int lane) {
     Parms& cur = ws.cur;
-    const Parms& prev = ws.enh;
-    if (!bands_ok(cur.L) || !bands_ok(prev.L)) {
-        return;
-    }
-    float* A = ws.A;
+    float* A = ws.u.fft.a;
     float* B = ws.u.fft.b;
     float* scale = ws.u.fft.scale;
     const float* tw = bt->tw;
@@ -534,7 +617,7 @@ __device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, const BlockTables
     for (int c = 0; c < 5; ++c) {
         const int n = 32 * c + lane;
         const float den = bt->wola_den[n];
-        const float ps = (n + 128 < NFFT) ? prev.previousUw[n + 128] : 0.0f;
+        const float ps = (n + 128 < NFFT) ? enh_uw[n + 128] : 0.0f;
         const float cs = (n - 32 >= 0) ? A[n - 32] : 0.0f;
         if (den > 1e-10f) {
             ws.out[n] += ((bt->wola_wp[n] * ps) + (bt->wola_wc[n] * cs)) / den;
@@ -550,20 +633,17 @@ __device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, const BlockTables
 // ---- voiced oscillator bank (mbelib.c:953-1040) --------------------------------------------------
 // kinds: 0 = previous-frame windowed component, 1 = current-frame windowed component,
 //        2 = phase/amplitude-interpolated harmonic (l < 8, both voiced, stable pitch)
-// Pass structure (32 components x 32 samples at a time):
-//   phase A  lane = component: runs its oscillator 32 steps and writes the finished contribution
-//            (gain*W[n])*cos into tile[n][component];
-//   phase B  lane = sample: adds the tile row in component order (LDS.128, four adds each).
+//
+// build_components: the ordered component list of one stream (l ascending, previous before current).
 // Windowed components whose gain is exactly zero (the faded bands of mbelib.c:912-929) are dropped:
 // their contribution is +-0 and x + (+-0) == x for every accumulator value that can occur.
-__device__ __forceinline__ void voiced_bank(WarpWS& ws, const BlockTables* bt, int maxl, int lane) {
+__device__ __forceinline__ void build_components(WarpWS& ws, int maxl, int lane) {
     const Parms& cur = ws.cur;
-    const Parms& prev = ws.enh;
+    const ParmsSmall& prev = ws.enh;
     const float cw0 = cur.w0, pw0 = prev.w0;
     const bool stable = fabsf(cw0 - pw0) < (0.1f * cw0);
-
-    // ordered component list
     int ncomp = 0;
+    unsigned k2mask = 0;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int l = 1 + lane + 32 * r;
@@ -589,6 +669,10 @@ __device__ __forceinline__ void voiced_bank(WarpWS& ws, const BlockTables* bt, i
         const unsigned ms = __ballot_sync(FULL, second);
         const unsigned lt = (1u << lane) - 1u;
         int idx = ncomp + __popc(mf & lt) + __popc(ms & lt);
+        if (r == 0) {
+            // interpolated harmonics have l < 8, so their list positions are < 14
+            k2mask = __reduce_or_sync(FULL, interp ? (1u << idx) : 0u);
+        }
         if (first) {
             ws.comp[idx] = (unsigned char)((l << 2) | (interp ? 2 : 0));
             ws.gain[idx] = 2.0f * prev.Ml[l];
@@ -600,103 +684,163 @@ __device__ __forceinline__ void voiced_bank(WarpWS& ws, const BlockTables* bt, i
         }
         ncomp += __popc(mf) + __popc(ms);
     }
+    if (lane == 0) {
+        ws.ncomp = ncomp;
+        ws.k2mask = k2mask;
+    }
     __syncwarp();
+}
 
-    float* tile = ws.u.tile;
+// voiced_bank_block: ALL warps of the block call this once per frame (block barriers inside).
+// The component lists of the block's streams are laid end to end (each stream's start rounded up to a
+// multiple of four slots) and cut into passes of 32 slots; pass p of a round is run by warp p:
+//   phase A  lane = slot: the lane runs that component's oscillator 32 steps (the reference's unfused
+//            rotation recurrence) and writes the finished contribution (gain*W[n])*cos into its warp's
+//            tile[n][lane];
+//   phase B  lane = sample, warp = stream: adds its stream's slots in list order (LDS.128, four adds
+//            each) from whichever tiles they landed in.
+// So oscillator work is spread evenly over the block no matter how the components are distributed
+// over streams, and a stream's additions keep the reference's order.
+__device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared* bs, const BlockTables* bt, int warp,
+                                                  int lane) {
+    constexpr int W = WARPS_PER_BLOCK;
+    int off[W + 1];
+    off[0] = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        off[i + 1] = off[i] + ((bs->cnt[i] + 3) & ~3);
+    }
+    const int total = off[W];
+    if (total == 0) {
+        return;
+    }
+    WarpWS& me = wsa[warp];
+    int my_lo = 0, my_cnt = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        if (i == warp) {
+            my_lo = off[i];
+            my_cnt = bs->cnt[i];
+        }
+    }
+    const int my_hi = my_lo + ((my_cnt + 3) & ~3);
+    float* tile = me.u.tile;
+
 #pragma unroll 1
-    for (int g0 = 0; g0 < ncomp; g0 += 32) {
-        const int cnt = min(32, ncomp - g0);
-        // oscillator owned by this lane; idle lanes and interpolated slots write zeros
+    for (int base = 0; base < total; base += 32 * W) {
+        // ---- oscillator owned by this lane in this round (idle slots and interpolated ones write zeros)
+        const int k = base + 32 * warp + lane;
+        int owner = -1, j = 0;
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            if (k >= off[i] && k < off[i] + bs->cnt[i]) {
+                owner = i;
+                j = k - off[i];
+            }
+        }
         float g = 0.f, c = 0.f, s = 0.f, cd = 0.f, sd = 0.f;
         const float* Wb = bt->voiced_win;
-        int id = 0;
-        if (lane < cnt) {
-            id = ws.comp[g0 + lane];
-        }
-        const bool k2 = (lane < cnt) && ((id & 3) == 2);
-        if ((lane < cnt) && !k2) {
-            const int l = id >> 2;
-            float step, ph;
-            if ((id & 3) == 0) {
-                step = pw0 * (float)l;
-                ph = prev.PHIl[l];
-                Wb = bt->voiced_win + NS;
-            } else {
-                step = cw0 * (float)l;
-                ph = cur.PHIl[l] - (step * (float)NS);
+        if (owner >= 0) {
+            const WarpWS& o = wsa[owner];
+            const int id = o.comp[j];
+            if ((id & 3) != 2) {
+                const int l = id >> 2;
+                float step, ph;
+                if ((id & 3) == 0) {
+                    step = o.enh.w0 * (float)l;
+                    ph = o.enh.PHIl[l];
+                    Wb = bt->voiced_win + NS;
+                } else {
+                    step = o.cur.w0 * (float)l;
+                    ph = o.cur.PHIl[l] - (step * (float)NS);
+                }
+                g = o.gain[j];
+                const float2 d = dev_sincosf(step);
+                const float2 p = dev_sincosf(ph);
+                sd = d.x;
+                cd = d.y;
+                s = p.x;
+                c = p.y;
             }
-            g = ws.gain[g0 + lane];
-            const float2 d = dev_sincosf(step);
-            const float2 p = dev_sincosf(ph);
-            sd = d.x;
-            cd = d.y;
-            s = p.x;
-            c = p.y;
         }
-        const unsigned k2mask = __ballot_sync(FULL, k2);
-        const int nq = (cnt + 3) >> 2;
+        // this stream's slots inside the round, and its interpolated harmonics among them
+        const int lo = max(my_lo, base), hi = min(my_hi, base + 32 * W);
+        unsigned k2 = 0;
+        if (hi > lo && me.k2mask) {
+            const int sh = lo - my_lo;  // list position of the first slot of this round
+            k2 = (sh < 32) ? (me.k2mask >> sh) : 0u;
+            if (hi - lo < 32) {
+                k2 &= (1u << (hi - lo)) - 1u;  // the rest of the list belongs to the next round
+            }
+        }
 #pragma unroll 1
         for (int ch = 0; ch < 5; ++ch) {
-            const float* W = Wb + 32 * ch;
-            float* trow = tile + lane;
+            const float* Wc = Wb + 32 * ch;
+            float* tcol = tile + lane;
 #pragma unroll(kOscUnroll)
             for (int n4 = 0; n4 < 8; ++n4) {
-                const float4 w4 = *reinterpret_cast<const float4*>(W + 4 * n4);
+                const float4 w4 = *reinterpret_cast<const float4*>(Wc + 4 * n4);
                 const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    trow[(4 * n4 + k) * TILE_STRIDE] = (g * wv[k]) * c;
+                for (int q = 0; q < 4; ++q) {
+                    tcol[(4 * n4 + q) * TILE_STRIDE] = (g * wv[q]) * c;
                     const float cn = (c * cd) - (s * sd);
                     const float sn = (s * cd) + (c * sd);
                     c = cn;
                     s = sn;
                 }
             }
-            const int n = 32 * ch + lane;
-            if (k2mask) {
-                __syncwarp();
-                unsigned m = k2mask;
-                while (m) {
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int l = ws.comp[g0 + j] >> 2;
-                    const float pw0l = pw0 * (float)l;
-                    const float dphi = cur.PHIl[l] - prev.PHIl[l] - (((pw0 + cw0) * (float)(l * NS)) / 2.0f);
-                    const float dw = (1.0f / (float)NS)
-                                     * (dphi - (2.0f * MBE_PI_F * floorf((dphi + MBE_PI_F) / (2.0f * MBE_PI_F))));
-                    const float th = prev.PHIl[l] + ((pw0l + dw) * (float)n)
-                                     + (((cw0 - pw0) * (float)(l * n * n)) / (float)(2 * NS));
-                    const float am = prev.Ml[l] + (((float)n / (float)NS) * (cur.Ml[l] - prev.Ml[l]));
-                    tile[lane * TILE_STRIDE + j] = 2.0f * am * dev_cosf(th);
+            __syncthreads();
+            if (hi > lo) {
+                const int n = 32 * ch + lane;
+                if (k2) {
+                    const Parms& cur = me.cur;
+                    const ParmsSmall& prev = me.enh;
+                    const float cw0 = cur.w0, pw0 = prev.w0;
+                    unsigned m = k2;
+                    while (m) {
+                        const int jj = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int slot = lo + jj - base;  // slot index inside the round
+                        const int l = me.comp[lo - my_lo + jj] >> 2;
+                        const float pw0l = pw0 * (float)l;
+                        const float dphi = cur.PHIl[l] - prev.PHIl[l] - (((pw0 + cw0) * (float)(l * NS)) / 2.0f);
+                        const float dw = (1.0f / (float)NS)
+                                         * (dphi - (2.0f * MBE_PI_F * floorf((dphi + MBE_PI_F) / (2.0f * MBE_PI_F))));
+                        const float th = prev.PHIl[l] + ((pw0l + dw) * (float)n)
+                                         + (((cw0 - pw0) * (float)(l * n * n)) / (float)(2 * NS));
+                        const float am = prev.Ml[l] + (((float)n / (float)NS) * (cur.Ml[l] - prev.Ml[l]));
+                        wsa[slot >> 5].u.tile[lane * TILE_STRIDE + (slot & 31)] = 2.0f * am * dev_cosf(th);
+                    }
+                    __syncwarp();
                 }
-            }
-            __syncwarp();
-            float a = ws.out[n];
-            const float4* row = reinterpret_cast<const float4*>(tile + lane * TILE_STRIDE);
+                float a = me.out[n];
 #pragma unroll 2
-            for (int q = 0; q < nq; ++q) {
-                const float4 v = row[q];
-                a += v.x;
-                a += v.y;
-                a += v.z;
-                a += v.w;
+                for (int k4 = lo - base; k4 < hi - base; k4 += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(wsa[k4 >> 5].u.tile + lane * TILE_STRIDE + (k4 & 31));
+                    a += v.x;
+                    a += v.y;
+                    a += v.z;
+                    a += v.w;
+                }
+                me.out[n] = a;
             }
-            ws.out[n] = a;
-            __syncwarp();
+            __syncthreads();
         }
     }
 }
 
-// ---- mbe_synthesizeSpeechCore (mbelib.c:1042-1105): cur = ws.cur, prev = ws.enh ------------------
-// leaves the 160 float samples in ws.out
-__device__ __noinline__ void synthesize_speech(WarpWS& ws, const DevTables* T, const BlockTables* bt, int has_rm0,
-                                               float rm0, int lane) {
+// ---- mbe_synthesizeSpeechCore (mbelib.c:1042-1105), split around the block-cooperative voiced bank ----
+// cur = ws.cur, prev = ws.enh; the 160 float samples end up in ws.out.
+// synth_begin: everything up to the component list.  Returns 1 when the frame continues through
+// voiced_bank_block + synth_finish, 0 when it is already complete (silence or comfort noise).
+__device__ __noinline__ int synth_begin(WarpWS& ws, const DevTables* T, int has_rm0, float rm0, int lane) {
     Parms& cur = ws.cur;
-    Parms& prev = ws.enh;
+    ParmsSmall& prev = ws.enh;
     zero_out(ws, lane);
     if (!bands_ok(cur.L) || !bands_ok(prev.L)) {
         __syncwarp();
-        return;  // silence
+        return 0;  // silence
     }
     adaptive_smoothing(cur, prev, has_rm0, rm0, lane);
 
@@ -704,9 +848,9 @@ __device__ __noinline__ void synthesize_speech(WarpWS& ws, const DevTables* T, c
     if (cur.repeatCount >= 4 || (mute_on_rate && cur.errorRate > cur.mutingThreshold)) {
         comfort_noise(ws, T, lane);
         __syncwarp();
-        return;
+        return 0;
     }
-    make_noise(ws, T, bt, lane);
+    noise_peek(ws, lane);
 
     // bands present in only one frame fade as zero-amplitude voiced bands (mbelib.c:912-929)
     int maxl;
@@ -758,10 +902,15 @@ __device__ __noinline__ void synthesize_speech(WarpWS& ws, const DevTables* T, c
         }
     }
     __syncwarp();
+    build_components(ws, maxl, lane);
+    return 1;
+}
 
-    voiced_bank(ws, bt, maxl, lane);
-    unvoiced_synthesis(ws, bt, lane);
-
+// synth_finish: unvoiced FFT/WOLA synthesis on top of the voiced samples, then the soft clip.
+__device__ __noinline__ void synth_finish(WarpWS& ws, const float* __restrict__ enh_uw, const DevTables* T,
+                                          const BlockTables* bt, int lane) {
+    make_noise(ws, T, bt, lane);
+    unvoiced_synthesis(ws, enh_uw, bt, lane);
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
         float v = ws.out[32 * c + lane];
