@@ -761,12 +761,18 @@ __global__ void mbe_state_xfer_kernel(uint32_t* state, int first, int count, uin
 // =====================================================================================================
 using namespace mbe;
 
+// the host-pointer entry points cut a batch into up to MAX_CHUNKS stream ranges and pipeline them
+constexpr int MAX_CHUNKS = 32;
+
 struct mbe_b200_ctx {
     int device;
     int max_streams;
     uint32_t* d_state;
     DevTables* d_tab;
     cudaStream_t stream;
+    // host-pointer pipeline: copy-in stream, two alternating compute streams, copy-out stream, chunk events
+    cudaStream_t s_in, s_k[2], s_out;
+    cudaEvent_t ev_in[MAX_CHUNKS], ev_k[MAX_CHUNKS], ev_start;
     // staging for the host-pointer entry points (grown on demand)
     void* d_in;
     size_t d_in_cap;
@@ -1084,6 +1090,15 @@ int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams) {
     } while (0)
     CUC(cudaSetDevice(device_ordinal));
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->s_k[0], cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->s_k[1], cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+    for (int i = 0; i < MAX_CHUNKS; ++i) {
+        CUC(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+    }
     CUC(cudaMalloc(&ctx->d_tab, sizeof(DevTables)));
     CUC(cudaMemcpy(ctx->d_tab, ht, sizeof(DevTables), cudaMemcpyHostToDevice));
     CUC(cudaMalloc(&ctx->d_state, (size_t)max_streams * STATE_WORDS * sizeof(uint32_t)));
@@ -1117,6 +1132,24 @@ void mbe_b200_destroy(mbe_b200_ctx* ctx) {
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
+    }
+    cudaStream_t extra[4] = {ctx->s_in, ctx->s_k[0], ctx->s_k[1], ctx->s_out};
+    for (int i = 0; i < 4; ++i) {
+        if (extra[i]) {
+            cudaStreamSynchronize(extra[i]);
+            cudaStreamDestroy(extra[i]);
+        }
+    }
+    if (ctx->ev_start) {
+        cudaEventDestroy(ctx->ev_start);
+    }
+    for (int i = 0; i < MAX_CHUNKS; ++i) {
+        if (ctx->ev_in[i]) {
+            cudaEventDestroy(ctx->ev_in[i]);
+        }
+        if (ctx->ev_k[i]) {
+            cudaEventDestroy(ctx->ev_k[i]);
+        }
     }
     cudaFree(ctx->d_state);
     cudaFree(ctx->d_tab);
@@ -1337,6 +1370,22 @@ static int ensure(mbe_b200_ctx* ctx, void** p, size_t* cap, size_t need) {
     return 0;
 }
 
+// Streams per pipeline chunk: whole waves of the stream kernel (2 blocks per SM x 148 SMs x WARPS_PER_BLOCK
+// streams), about eight chunks per batch, so the first copy-in and the last copy-out are the only exposed
+// transfers.
+static int pipeline_chunk_streams(int n_streams) {
+    const int wave = 2 * 148 * WARPS_PER_BLOCK;
+    if (n_streams <= 2 * wave) {
+        return n_streams;
+    }
+    int chunk = (n_streams + 7) / 8;
+    chunk = ((chunk + wave - 1) / wave) * wave;
+    while ((n_streams + chunk - 1) / chunk > MAX_CHUNKS) {
+        chunk += wave;
+    }
+    return chunk;
+}
+
 int mbe_b200_process_frames(mbe_b200_ctx* ctx, int codec, int soft, int first_stream, int n_streams, int n_frames,
                             const uint8_t* frames, int16_t* pcm, float* pcmf, mbe_b200_result* results, uint8_t* bits) {
     int rc = check_range(ctx, first_stream, n_streams);
@@ -1353,32 +1402,54 @@ int mbe_b200_process_frames(mbe_b200_ctx* ctx, int codec, int soft, int first_st
     CU(cudaSetDevice(ctx->device));
     int fb, pb;
     mbe_b200_geometry(codec, &fb, &pb);
-    const size_t in_bytes = nf * fb * (soft ? 2 : 1);
-    const size_t ob[4] = {pcm ? nf * NS * sizeof(int16_t) : 0, pcmf ? nf * NS * sizeof(float) : 0,
-                          results ? nf * sizeof(mbe_b200_result) : 0, bits ? nf * pb : 0};
-    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, in_bytes)) < 0) {
+    const size_t in_per_frame = (size_t)fb * (soft ? 2 : 1);
+    const size_t per_frame[4] = {pcm ? NS * sizeof(int16_t) : 0, pcmf ? NS * sizeof(float) : 0,
+                                 results ? sizeof(mbe_b200_result) : 0, bits ? (size_t)pb : 0};
+    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, nf * in_per_frame)) < 0) {
         return rc;
     }
     for (int i = 0; i < 4; ++i) {
-        if (ob[i] && (rc = ensure(ctx, &ctx->d_out[i], &ctx->d_out_cap[i], ob[i])) < 0) {
+        if (per_frame[i] && (rc = ensure(ctx, &ctx->d_out[i], &ctx->d_out_cap[i], nf * per_frame[i])) < 0) {
             return rc;
         }
     }
-    CU(cudaMemcpyAsync(ctx->d_in, frames, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    rc = mbe_b200_process_frames_dev(ctx, codec, soft, first_stream, n_streams, n_frames, (const uint8_t*)ctx->d_in,
-                                     pcm ? (int16_t*)ctx->d_out[0] : nullptr, pcmf ? (float*)ctx->d_out[1] : nullptr,
-                                     results ? (mbe_b200_result*)ctx->d_out[2] : nullptr,
-                                     bits ? (uint8_t*)ctx->d_out[3] : nullptr, ctx->stream);
-    if (rc < 0) {
-        return rc;
-    }
+    // Pipeline over stream ranges: copy-in (s_in) -> kernel (two alternating compute streams, so the tail of
+    // one chunk overlaps the head of the next) -> copy-out (s_out).  Everything is ordered after what is
+    // already queued on the context's own stream; the call returns when the results are in host memory.
     void* host[4] = {pcm, pcmf, results, bits};
-    for (int i = 0; i < 4; ++i) {
-        if (ob[i]) {
-            CU(cudaMemcpyAsync(host[i], ctx->d_out[i], ob[i], cudaMemcpyDeviceToHost, ctx->stream));
+    const int chunk = pipeline_chunk_streams(n_streams);
+    CU(cudaEventRecord(ctx->ev_start, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
+    CU(cudaStreamWaitEvent(ctx->s_k[0], ctx->ev_start, 0));
+    CU(cudaStreamWaitEvent(ctx->s_k[1], ctx->ev_start, 0));
+    int c = 0;
+    for (int s0 = 0; s0 < n_streams; s0 += chunk, ++c) {
+        const int ns = (n_streams - s0 < chunk) ? (n_streams - s0) : chunk;
+        const size_t f0 = (size_t)s0 * n_frames, fn = (size_t)ns * n_frames;
+        cudaStream_t sk = ctx->s_k[c & 1];
+        CU(cudaMemcpyAsync((uint8_t*)ctx->d_in + f0 * in_per_frame, frames + f0 * in_per_frame, fn * in_per_frame,
+                           cudaMemcpyHostToDevice, ctx->s_in));
+        CU(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+        CU(cudaStreamWaitEvent(sk, ctx->ev_in[c], 0));
+        rc = mbe_b200_process_frames_dev(
+            ctx, codec, soft, first_stream + s0, ns, n_frames, (const uint8_t*)ctx->d_in + f0 * in_per_frame,
+            pcm ? (int16_t*)ctx->d_out[0] + f0 * NS : nullptr, pcmf ? (float*)ctx->d_out[1] + f0 * NS : nullptr,
+            results ? (mbe_b200_result*)ctx->d_out[2] + f0 : nullptr, bits ? (uint8_t*)ctx->d_out[3] + f0 * pb : nullptr, sk);
+        if (rc < 0) {
+            return rc;
+        }
+        CU(cudaEventRecord(ctx->ev_k[c], sk));
+        CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[c], 0));
+        for (int i = 0; i < 4; ++i) {
+            if (per_frame[i]) {
+                CU(cudaMemcpyAsync((uint8_t*)host[i] + f0 * per_frame[i], (uint8_t*)ctx->d_out[i] + f0 * per_frame[i],
+                                   fn * per_frame[i], cudaMemcpyDeviceToHost, ctx->s_out));
+            }
         }
     }
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->s_out));
+    CU(cudaStreamSynchronize(ctx->s_k[0]));
+    CU(cudaStreamSynchronize(ctx->s_k[1]));
     return 0;
 }
 
