@@ -130,6 +130,12 @@ MBE_B200_API int mbe_b200_floattoshort(mbe_b200_ctx* ctx, int n_frames, const fl
 MBE_B200_API int mbe_b200_floattoshort_dev(mbe_b200_ctx* ctx, int n_frames, const float* d_in, int16_t* d_out,
                                            void* cuda_stream);
 
+/* profiling aid: per-stage clock64() sums of the stream kernel; all zero unless the library was built with
+ * -DMBE_STAGE_TIMING=1.  out16[0..7] = {frame barrier, front-end + decode, enhance + synthesis
+ * setup, count barrier, voiced bank, unvoiced + hand-over, output stores, state store}, out16[8..13] = inside the bank
+ * {oscillator setup, phase A, interpolation, wait A, phase B, wait B}; reset != 0 clears the counters. */
+MBE_B200_API int mbe_b200_debug_stage_cycles(mbe_b200_ctx* ctx, unsigned long long* out16, int reset);
+
 /* block until everything queued on the context's stream has finished */
 MBE_B200_API int mbe_b200_synchronize(mbe_b200_ctx* ctx);
 

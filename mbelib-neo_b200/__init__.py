@@ -33,7 +33,7 @@ _EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b
             "mbe_b200_export_rng", "mbe_b200_import_rng", "mbe_b200_process_frames_dev", "mbe_b200_process_frames",
             "mbe_b200_decode_frames_dev", "mbe_b200_decode_frames", "mbe_b200_process_data_dev",
             "mbe_b200_process_data", "mbe_b200_synthesize_speech", "mbe_b200_floattoshort",
-            "mbe_b200_floattoshort_dev", "mbe_b200_synchronize"]
+            "mbe_b200_floattoshort_dev", "mbe_b200_synchronize", "mbe_b200_debug_stage_cycles"]
 
 _lib = None
 
@@ -77,6 +77,7 @@ def load_library():
         lib.mbe_b200_floattoshort.argtypes = [vp, ci, vp, vp]
         lib.mbe_b200_floattoshort_dev.argtypes = [vp, ci, vp, vp, vp]
         lib.mbe_b200_synchronize.argtypes = [vp]
+        lib.mbe_b200_debug_stage_cycles.argtypes = [vp, vp, ci]
         _lib = lib
     return _lib
 
@@ -206,6 +207,11 @@ class Decoder:
         x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, SAMPLES)
         out = np.zeros(x.shape, np.int16)
         self._check(self.lib.mbe_b200_floattoshort(self.h, x.shape[0], _p(x), _p(out)), "floattoshort")
+        return out
+
+    def debug_stage_cycles(self, reset=True):
+        out = np.zeros(16, np.uint64)
+        self._check(self.lib.mbe_b200_debug_stage_cycles(self.h, _p(out), int(reset)), "debug_stage_cycles")
         return out
 
     def synchronize(self):

@@ -37,7 +37,6 @@ namespace hosttab {
 
 namespace mbe {
 
-
 constexpr unsigned FLAG_SOFT = 0x0001u, FLAG_C0 = 0x0002u, FLAG_C4 = 0x0004u, FLAG_TONE = 0x0010u,
                    FLAG_ERASURE = 0x0020u, FLAG_REPEAT = 0x0040u, FLAG_MUTE = 0x0080u;
 constexpr unsigned CONTEXT_FLAGS = FLAG_SOFT | FLAG_C0 | FLAG_C4;
@@ -452,7 +451,7 @@ __device__ __forceinline__ void store_stream(const WarpWS& ws, uint32_t* gs, int
 // One block = WARPS_PER_BLOCK streams walking their frames in lockstep (see WARPS_PER_BLOCK).
 // =====================================================================================================
 template <int CODEC, int SOFT, int MODE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2) mbe_stream_kernel(const LaunchArgs A) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_stream_kernel(const LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BlockTables* bt = reinterpret_cast<BlockTables*>(smem_raw);
     WarpWS* wsa = reinterpret_cast<WarpWS*>(smem_raw + sizeof(BlockTables));
@@ -476,9 +475,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2) mbe_stream_kernel(con
         load_stream(ws, gs, lane);
     }
 
+    StageTimer tm;
+#if MBE_STAGE_TIMING
+    for (int i = 0; i < 16; ++i) {
+        tm.acc[i] = 0;
+    }
+    tm.last = clock64();
+#endif
 #pragma unroll 1
     for (int f = 0; f < A.n_frames; ++f) {
         __syncthreads();  // frame boundary: tiles / counters of the previous frame are dead
+        STAGE_T(0);
         const size_t idx = (size_t)s * A.n_frames + f;
         unsigned dw[3] = {0u, 0u, 0u};
         FrameCtx fc;
@@ -545,7 +552,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2) mbe_stream_kernel(con
                 } else {
                     act = process_ambe2450(fc, dw, ws, home, T, lane);
                 }
+                STAGE_T(1);
                 go = render_begin<AMBE>(act, ws, home, T, lane);
+                STAGE_T(2);
             } else {
                 zero_out(ws, lane);
             }
@@ -554,11 +563,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2) mbe_stream_kernel(con
             bs->cnt[warp] = go ? ws.ncomp : 0;
         }
         __syncthreads();
-        voiced_bank_block(wsa, bs, bt, warp, lane);
+        STAGE_T(3);
+        voiced_bank_block(wsa, bs, bt, tm, warp, lane);
+        STAGE_T(4);
 
         if (live) {
             if (status >= 0) {
                 render_end<AMBE>(act, go, ws, home, T, bt, lane);
+                STAGE_T(5);
                 status = fc.total;
                 rout.c0_errors = fc.c0;
                 rout.c4_errors = fc.c4;
@@ -582,15 +594,24 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2) mbe_stream_kernel(con
                 }
             }
         }
+        STAGE_T(6);
     }
     if (live) {
         store_stream(ws, gs, lane);
     }
+#if MBE_STAGE_TIMING
+    STAGE_T(7);
+    if (A.dbg && lane == 0 && live) {
+        for (int i = 0; i < 16; ++i) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(A.dbg) + i, (unsigned long long)tm.acc[i]);
+        }
+    }
+#endif
 }
 
 // batched mbe_synthesizeSpeech[f]: element s synthesises one frame from parameter blobs in device memory
 // (cur[s] -> ws.cur, prev[s] -> ws.enh; prev's previousUw is read in place, both are updated in place)
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2) mbe_synth_kernel(const LaunchArgs A) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_synth_kernel(const LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BlockTables* bt = reinterpret_cast<BlockTables*>(smem_raw);
     WarpWS* wsa = reinterpret_cast<WarpWS*>(smem_raw + sizeof(BlockTables));
@@ -638,7 +659,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2) mbe_synth_kernel(cons
         bs->cnt[warp] = go ? ws.ncomp : 0;
     }
     __syncthreads();
-    voiced_bank_block(wsa, bs, bt, warp, lane);
+    StageTimer tm;
+    voiced_bank_block(wsa, bs, bt, tm, warp, lane);
     if (live) {
         if (go) {
             synth_finish(ws, reinterpret_cast<const float*>(gp + UW_WORD), T, bt, lane);
@@ -779,6 +801,7 @@ struct mbe_b200_ctx {
     void* d_out[4];
     size_t d_out_cap[4];
     long long launches;
+    unsigned long long* d_dbg;  // 16 stage counters (MBE_STAGE_TIMING builds)
     float imbe_default_w0;
     int imbe_default_L;
     char err[256];
@@ -992,7 +1015,13 @@ static void build_tables(DevTables* t) {
 }
 
 static size_t stream_kernel_smem(void) {
-    return sizeof(BlockTables) + (size_t)WARPS_PER_BLOCK * sizeof(WarpWS) + sizeof(BlockShared);
+    // MBE_B200_PAD_SMEM (bytes) is a profiling knob: it lowers occupancy without touching the code
+    static long pad = -1;
+    if (pad < 0) {
+        const char* e = getenv("MBE_B200_PAD_SMEM");
+        pad = e ? atol(e) : 0;
+    }
+    return sizeof(BlockTables) + (size_t)WARPS_PER_BLOCK * sizeof(WarpWS) + sizeof(BlockShared) + (size_t)pad;
 }
 
 typedef void (*StreamKernelFn)(const LaunchArgs);
@@ -1102,6 +1131,8 @@ int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams) {
     CUC(cudaMalloc(&ctx->d_tab, sizeof(DevTables)));
     CUC(cudaMemcpy(ctx->d_tab, ht, sizeof(DevTables), cudaMemcpyHostToDevice));
     CUC(cudaMalloc(&ctx->d_state, (size_t)max_streams * STATE_WORDS * sizeof(uint32_t)));
+    CUC(cudaMalloc(&ctx->d_dbg, 16 * sizeof(unsigned long long)));
+    CUC(cudaMemset(ctx->d_dbg, 0, 16 * sizeof(unsigned long long)));
     for (int codec = 0; codec < 4; ++codec) {
         for (int soft = 0; soft < 2; ++soft) {
             for (int mode = 0; mode < 2; ++mode) {
@@ -1152,12 +1183,26 @@ void mbe_b200_destroy(mbe_b200_ctx* ctx) {
         }
     }
     cudaFree(ctx->d_state);
+    cudaFree(ctx->d_dbg);
     cudaFree(ctx->d_tab);
     cudaFree(ctx->d_in);
     for (int i = 0; i < 4; ++i) {
         cudaFree(ctx->d_out[i]);
     }
     free(ctx);
+}
+
+int mbe_b200_debug_stage_cycles(mbe_b200_ctx* ctx, unsigned long long* out16, int reset) {
+    if (!ctx || !out16) {
+        return MBE_B200_E_ARG;
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out16, ctx->d_dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) {
+        CU(cudaMemset(ctx->d_dbg, 0, 16 * sizeof(unsigned long long)));
+    }
+    return 0;
 }
 
 int mbe_b200_synchronize(mbe_b200_ctx* ctx) {
@@ -1283,6 +1328,7 @@ int mbe_b200_process_frames_dev(mbe_b200_ctx* ctx, int codec, int soft, int firs
     a.bits = d_bits;
     a.state = ctx->d_state;
     a.tab = ctx->d_tab;
+    a.dbg = ctx->d_dbg;
     return launch_stream_kernel(ctx, a, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream);
 }
 

@@ -137,6 +137,7 @@ struct LaunchArgs {
     uint32_t* synth_cur;
     uint32_t* synth_prev;
     const uint32_t* synth_seeds;
+    unsigned long long* dbg;    // MBE_STAGE_TIMING builds: 16 accumulated per-stage cycle counters
 };
 
 constexpr int TILE_STRIDE = 36;   // floats per sample row of the oscillator tile (32 components + pad)
@@ -149,6 +150,18 @@ struct __align__(16) BlockTables {
     float uvwin[256];        // unvoiced analysis window, centred at 128
     float wola_wp[160], wola_wc[160], wola_den[160];
 };
+
+// Streams (= warps) per block.  The block walks its streams' frames in lockstep: per frame every warp
+// decodes its own stream, then the block pools the oscillator components of all its streams and
+// spreads them evenly over all lanes (voiced_bank_block), then every warp finishes its own stream.
+#ifndef MBE_WPB
+#define MBE_WPB 9
+#endif
+#ifndef MBE_MINB
+#define MBE_MINB 2
+#endif
+constexpr int WARPS_PER_BLOCK = MBE_WPB;
+constexpr int MIN_BLOCKS_PER_SM = MBE_MINB;
 
 // The reference's thread-local RNG state, per stream (mbe_adaptive.c:29-30, mbe_unvoiced_fft.c:29-30)
 struct StreamRng {
@@ -181,19 +194,30 @@ struct __align__(16) WarpWS {
     float nz[57];                         // white-noise samples 1..56 of the frame (phase randomisation)
     unsigned rowbits[8];
     int ncomp;                            // oscillator components of this frame (0: no voiced synthesis)
+    int off[WARPS_PER_BLOCK + 3];         // this warp's copy of the block's slot offsets (prefix of padded counts)
     unsigned k2mask;                      // list positions (< 32) of phase-interpolated harmonics
     unsigned char comp[112];              // component descriptor: harmonic << 2 | kind
     unsigned char rel[8 * 24];            // soft-bit reliabilities of the frame
 };
 static_assert(offsetof(WarpWS, u) % 16 == 0 && sizeof(WarpWS) % 16 == 0 && sizeof(BlockTables) % 16 == 0, "LDS.128 alignment");
 
-// Streams (= warps) per block.  The block walks its streams' frames in lockstep: per frame every warp
-// decodes its own stream, then the block pools the oscillator components of all its streams and
-// spreads them evenly over all lanes (voiced_bank_block), then every warp finishes its own stream.
-constexpr int WARPS_PER_BLOCK = 9;
-
 struct BlockShared {
     int cnt[WARPS_PER_BLOCK + 3];         // per stream: component count of the current frame
 };
+
+// MBE_STAGE_TIMING=1 builds accumulate per-stage clock64() deltas per warp into LaunchArgs.dbg (profiling aid)
+#ifndef MBE_STAGE_TIMING
+#define MBE_STAGE_TIMING 0
+#endif
+#if MBE_STAGE_TIMING
+struct StageTimer {
+    long long acc[16];
+    long long last;
+};
+#define STAGE_T(i) do { const long long _t = clock64(); tm.acc[i] += _t - tm.last; tm.last = _t; } while (0)
+#else
+struct StageTimer {};
+#define STAGE_T(i) do { } while (0)
+#endif
 
 }  // namespace mbe

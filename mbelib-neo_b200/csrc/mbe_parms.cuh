@@ -14,11 +14,11 @@ __device__ __forceinline__ float pow2i(int e) {  // exact 2^e for -126 <= e <= 1
     return __int_as_float((127 + e) << 23);
 }
 
-__device__ __forceinline__ unsigned pick(const unsigned dw[3], const unsigned char* idx, int n) {
+// gather parameter bits (MSB first) at compile-time positions: the index lists fold into immediates
+template <int... IDX>
+__device__ __forceinline__ unsigned pick(const unsigned dw[3]) {
     unsigned v = 0;
-    for (int i = 0; i < n; ++i) {
-        v = (v << 1) | getbit(dw, idx[i]);
-    }
+    ((v = (v << 1) | ((dw[IDX >> 5] >> (IDX & 31)) & 1u)), ...);
     return v;
 }
 
@@ -353,16 +353,7 @@ __device__ __forceinline__ int decode_ambe2450(const unsigned dw[3], WarpWS& ws,
     if (tone_ok && total_errors < 6) {
         return 7;
     }
-    const unsigned char i_b0[7] = {0, 1, 2, 3, 37, 38, 39};
-    const unsigned char i_b1[5] = {4, 5, 6, 7, 35};
-    const unsigned char i_b2[5] = {8, 9, 10, 11, 36};
-    const unsigned char i_b3[9] = {12, 13, 14, 15, 16, 17, 18, 19, 40};
-    const unsigned char i_b4[7] = {20, 21, 22, 23, 41, 42, 43};
-    const unsigned char i_b5[5] = {24, 25, 26, 27, 44};
-    const unsigned char i_b6[4] = {28, 29, 30, 45};
-    const unsigned char i_b7[4] = {31, 32, 33, 46};
-    const unsigned char i_b8[3] = {34, 47, 48};
-    const int b0 = (int)pick(dw, i_b0, 7);
+    const int b0 = (int)pick<0, 1, 2, 3, 37, 38, 39>(dw);
     if (b0 >= 120 && b0 <= 123) {
         return 2;
     }
@@ -382,8 +373,8 @@ __device__ __forceinline__ int decode_ambe2450(const unsigned dw[3], WarpWS& ws,
         L = t_a2450_L[b0];
     }
     const float unvc = 0.2046f / sqrtf(w0);
-    const unsigned vmask = t_a2450_vuv[pick(dw, i_b1, 5)];
-    const float dg = t_a2450_dgain[pick(dw, i_b2, 5)];
+    const unsigned vmask = t_a2450_vuv[pick<4, 5, 6, 7, 35>(dw)];
+    const float dg = t_a2450_dgain[pick<8, 9, 10, 11, 36>(dw)];
     for (int l = 1 + lane; l <= L; l += 32) {
         if (silence) {
             cur.Vl[l] = 0;
@@ -400,24 +391,17 @@ __device__ __forceinline__ int decode_ambe2450(const unsigned dw[3], WarpWS& ws,
     __syncwarp();
     AmbeBooks bk = {t_a2450_prba24, t_a2450_prba58, {t_a2450_hoc5, t_a2450_hoc6, t_a2450_hoc7, t_a2450_hoc8},
                     t_a2450_blocklen};
-    const int hocidx[4] = {(int)pick(dw, i_b5, 5), (int)pick(dw, i_b6, 4), (int)pick(dw, i_b7, 4), (int)pick(dw, i_b8, 3)};
-    ambe_tail(ws, T, bk, (int)pick(dw, i_b3, 9), (int)pick(dw, i_b4, 7), hocidx, unvc, lane);
+    const int hocidx[4] = {(int)pick<24, 25, 26, 27, 44>(dw), (int)pick<28, 29, 30, 45>(dw), (int)pick<31, 32, 33, 46>(dw),
+                           (int)pick<34, 47, 48>(dw)};
+    ambe_tail(ws, T, bk, (int)pick<12, 13, 14, 15, 16, 17, 18, 19, 40>(dw), (int)pick<20, 21, 22, 23, 41, 42, 43>(dw), hocidx,
+              unvc, lane);
     return 0;
 }
 
 // ---- AMBE 3600x2400 ---- returns 0 voice | 3 tone/silence marker | 5..122 D-STAR tone index
 __device__ __forceinline__ int decode_ambe2400(const unsigned dw[3], WarpWS& ws, const DevTables* T, int lane) {
     Parms& cur = ws.cur;
-    const unsigned char i_b0[7] = {0, 1, 2, 3, 4, 5, 48};
-    const unsigned char i_b1[4] = {38, 39, 40, 41};
-    const unsigned char i_b2[6] = {6, 7, 8, 9, 42, 43};
-    const unsigned char i_b3[9] = {10, 11, 12, 13, 14, 15, 16, 44, 45};
-    const unsigned char i_b4[7] = {17, 18, 19, 20, 21, 46, 47};
-    const unsigned char i_b5[4] = {22, 23, 25, 26};
-    const unsigned char i_b6[4] = {27, 28, 29, 30};
-    const unsigned char i_b7[4] = {31, 32, 33, 34};
-    const unsigned char i_b8[3] = {35, 36, 37};
-    const int b0 = (int)pick(dw, i_b0, 7);
+    const int b0 = (int)pick<0, 1, 2, 3, 4, 5, 48>(dw);
     if ((b0 & 0x7E) == 0x7E) {
         // three remapped high bits (t7,t6,t5 tables of the reference folded into one) + five literal bits
         const unsigned hi3 = (0x56732104u >> (4 * ((getbit(dw, 6) << 2) | (getbit(dw, 7) << 1) | getbit(dw, 8)))) & 7u;
@@ -442,8 +426,8 @@ __device__ __forceinline__ int decode_ambe2400(const unsigned dw[3], WarpWS& ws,
     const float w0 = T->a2400_w0[b0];
     const int L = t_a2400_L[b0];
     const float unvc = 0.2046f / sqrtf(w0);
-    const unsigned vmask = t_a2400_vuv[pick(dw, i_b1, 4)];
-    const float dg = t_a2400_dgain[pick(dw, i_b2, 6)];
+    const unsigned vmask = t_a2400_vuv[pick<38, 39, 40, 41>(dw)];
+    const float dg = t_a2400_dgain[pick<6, 7, 8, 9, 42, 43>(dw)];
     for (int l = 1 + lane; l <= L; l += 32) {
         int jl = (int)((float)l * 16.0f * f0);
         cur.Vl[l] = (int)((vmask >> jl) & 1u);
@@ -456,9 +440,10 @@ __device__ __forceinline__ int decode_ambe2400(const unsigned dw[3], WarpWS& ws,
     __syncwarp();
     AmbeBooks bk = {t_a2400_prba24, t_a2400_prba58, {t_a2400_hoc5, t_a2400_hoc6, t_a2400_hoc7, t_a2400_hoc8},
                     t_a2400_blocklen};
-    const int hocidx[4] = {(int)pick(dw, i_b5, 4), (int)pick(dw, i_b6, 4), (int)pick(dw, i_b7, 4),
-                           (int)(pick(dw, i_b8, 3) << 1)};
-    ambe_tail(ws, T, bk, (int)pick(dw, i_b3, 9), (int)pick(dw, i_b4, 7), hocidx, unvc, lane);
+    const int hocidx[4] = {(int)pick<22, 23, 25, 26>(dw), (int)pick<27, 28, 29, 30>(dw), (int)pick<31, 32, 33, 34>(dw),
+                           (int)(pick<35, 36, 37>(dw) << 1)};
+    ambe_tail(ws, T, bk, (int)pick<10, 11, 12, 13, 14, 15, 16, 44, 45>(dw), (int)pick<17, 18, 19, 20, 21, 46, 47>(dw), hocidx,
+              unvc, lane);
     return 0;
 }
 

@@ -396,11 +396,12 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, const DevTables* T, const
 }
 
 // ---- 256-point real FFT: FFTPACK radix-4 passes, lanes over butterflies -------------------------
-// One generic pass each way (kept out of line: 8 calls per frame share two code bodies).  `w` points
-// at the pass's first twiddle row; rows two and three follow at +ido and +2*ido.  `recip` =
-// ceil(65536 / (ido/2 - 1)) turns the flattened butterfly index into (k, i) without a division.
-__device__ __noinline__ void rfft_fwd_pass(int ido, int l1, unsigned recip, const float* __restrict__ in,
-                                           float* __restrict__ out, const float* __restrict__ w, int lane) {
+// One pass template each way, instantiated for the four (ido, l1) shapes of N = 256 so that all index
+// arithmetic folds into immediates.  `w` points at the pass's first twiddle row; rows two and three
+// follow at +ido and +2*ido.
+template <int ido, int l1>
+__device__ __forceinline__ void rfft_fwd_pass(const float* __restrict__ in, float* __restrict__ out,
+                                              const float* __restrict__ w, int lane) {
 #define FIN(i, k, j)  in[(i) + ido * ((k) + l1 * (j))]
 #define FOUT(i, j, k) out[(i) + ido * ((j) + 4 * (k))]
     const float nhs2 = -0.70710678118654752440f;
@@ -417,10 +418,10 @@ __device__ __noinline__ void rfft_fwd_pass(int ido, int l1, unsigned recip, cons
         FOUT(ido - 1, 3, k) = tr2 - tr1;
     }
     if (ido >= 2) {
-        const int ni = ido / 2 - 1;
+        constexpr int ni = (ido / 2 - 1) > 0 ? (ido / 2 - 1) : 1;
         const int it = lane;  // l1 * ni <= 31 for every pass of N = 256
-        if (it < l1 * ni) {
-            const int k = (int)(((unsigned)it * recip) >> 16);
+        if (it < l1 * (ido / 2 - 1)) {
+            const int k = it / ni;  // compile-time divisor
             const int i = 2 + 2 * (it - k * ni);
             const int ic = ido - i;
             float cr2 = FIN(i - 1, k, 1), ci2 = FIN(i, k, 1);
@@ -467,8 +468,9 @@ __device__ __noinline__ void rfft_fwd_pass(int ido, int l1, unsigned recip, cons
 #undef FOUT
 }
 
-__device__ __noinline__ void rfft_bwd_pass(int ido, int l1, unsigned recip, const float* __restrict__ in,
-                                           float* __restrict__ out, const float* __restrict__ w, int lane) {
+template <int ido, int l1>
+__device__ __forceinline__ void rfft_bwd_pass(const float* __restrict__ in, float* __restrict__ out,
+                                              const float* __restrict__ w, int lane) {
 #define BIN(i, j, k)  in[(i) + ido * ((j) + 4 * (k))]
 #define BOUT(i, k, j) out[(i) + ido * ((k) + l1 * (j))]
     const float nsq2 = -1.41421356237309504880f;
@@ -487,10 +489,10 @@ __device__ __noinline__ void rfft_bwd_pass(int ido, int l1, unsigned recip, cons
         BOUT(0, k, 3) = tr1 + tr4;
     }
     if (ido >= 2) {
-        const int ni = ido / 2 - 1;
+        constexpr int ni = (ido / 2 - 1) > 0 ? (ido / 2 - 1) : 1;
         const int it = lane;
-        if (it < l1 * ni) {
-            const int k = (int)(((unsigned)it * recip) >> 16);
+        if (it < l1 * (ido / 2 - 1)) {
+            const int k = it / ni;  // compile-time divisor
             const int i = 2 + 2 * (it - k * ni);
             const int ic = ido - i;
             float tr1 = BIN(i - 1, 0, k) - BIN(ic - 1, 3, k);
@@ -545,6 +547,23 @@ __device__ __noinline__ void rfft_bwd_pass(int ido, int l1, unsigned recip, cons
 #undef BOUT
 }
 
+// the two 256-point transforms: four radix-4 passes each, ping-ponging between A and B; result in A
+__device__ __noinline__ void rfft256_forward(float* __restrict__ A, float* __restrict__ B, const float* __restrict__ tw,
+                                             int lane) {
+    rfft_fwd_pass<1, 64>(A, B, tw + 252, lane);
+    rfft_fwd_pass<4, 16>(B, A, tw + 240, lane);
+    rfft_fwd_pass<16, 4>(A, B, tw + 192, lane);
+    rfft_fwd_pass<64, 1>(B, A, tw + 0, lane);
+}
+
+__device__ __noinline__ void rfft256_backward(float* __restrict__ A, float* __restrict__ B, const float* __restrict__ tw,
+                                              int lane) {
+    rfft_bwd_pass<64, 1>(A, B, tw + 0, lane);
+    rfft_bwd_pass<16, 4>(B, A, tw + 192, lane);
+    rfft_bwd_pass<4, 16>(A, B, tw + 240, lane);
+    rfft_bwd_pass<1, 64>(B, A, tw + 252, lane);
+}
+
 // ---- unvoiced synthesis (mbe_unvoiced_fft.c:714-761); adds into ws.out and writes cur.previousUw --
 // ws.u.fft.a holds the windowed noise on entry; enh_uw = prev_mp_enhanced->previousUw in HBM.  Spectrum is kept in FFTPACK's native layout F[0]=DC,
 // F[2b-1]=Re(b), F[2b]=Im(b), F[255]=Nyquist; the reference's "ordered" layout is only a permutation of
@@ -560,10 +579,7 @@ __device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, const float* __re
         scale[i] = 0.0f;
     }
     __syncwarp();
-    rfft_fwd_pass(1, 64, 0u, A, B, tw + 252, lane);
-    rfft_fwd_pass(4, 16, 65536u, B, A, tw + 240, lane);
-    rfft_fwd_pass(16, 4, 9363u, A, B, tw + 192, lane);
-    rfft_fwd_pass(64, 1, 2115u, B, A, tw + 0, lane);
+    rfft256_forward(A, B, tw, lane);
 
     const int L = cur.L;
     const float mult = (256.0f / (2.0f * 3.14159265358979323846f)) * cur.w0;
@@ -602,10 +618,7 @@ __device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, const float* __re
         A[i] *= scale[bin];
     }
     __syncwarp();
-    rfft_bwd_pass(64, 1, 2115u, A, B, tw + 0, lane);
-    rfft_bwd_pass(16, 4, 9363u, B, A, tw + 192, lane);
-    rfft_bwd_pass(4, 16, 65536u, A, B, tw + 240, lane);
-    rfft_bwd_pass(1, 64, 0u, B, A, tw + 252, lane);
+    rfft256_backward(A, B, tw, lane);
     const float inv = 1.0f / (float)NFFT;
     // scale by 1/N and hand the block to the state; the WOLA below reads this frame's samples back
     for (int i = lane; i < NFFT; i += 32) {
@@ -691,38 +704,59 @@ __device__ __forceinline__ void build_components(WarpWS& ws, int maxl, int lane)
     __syncwarp();
 }
 
+// list positions (as a bit mask shifted to the round's first slot of that stream) of the interpolated
+// harmonics of stream `off .. off+cnt` that fall inside the round [base, base + round)
+__device__ __forceinline__ unsigned round_k2mask(unsigned k2mask, int off, int cnt, int base, int round) {
+    const int ilo = max(off, base), ihi = min(off + cnt, base + round);
+    const int sh = ilo - off;
+    if (ihi <= ilo || sh >= 32 || k2mask == 0u) {
+        return 0u;
+    }
+    unsigned m = k2mask >> sh;
+    if (ihi - ilo < 32) {
+        m &= (1u << (ihi - ilo)) - 1u;
+    }
+    return m;
+}
+
 // voiced_bank_block: ALL warps of the block call this once per frame (block barriers inside).
 // The component lists of the block's streams are laid end to end (each stream's start rounded up to a
 // multiple of four slots) and cut into passes of 32 slots; pass p of a round is run by warp p:
 //   phase A  lane = slot: the lane runs that component's oscillator 32 steps (the reference's unfused
 //            rotation recurrence) and writes the finished contribution (gain*W[n])*cos into its warp's
-//            tile[n][lane];
+//            tile[n][lane]; the phase-interpolated harmonics of the round (one cosf per sample) are
+//            dealt round-robin to all warps, lane = sample;
 //   phase B  lane = sample, warp = stream: adds its stream's slots in list order (LDS.128, four adds
 //            each) from whichever tiles they landed in.
 // So oscillator work is spread evenly over the block no matter how the components are distributed
 // over streams, and a stream's additions keep the reference's order.
-__device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared* bs, const BlockTables* bt, int warp,
-                                                  int lane) {
+__device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared* bs, const BlockTables* bt,
+                                                  StageTimer& tm, int warp, int lane) {
     constexpr int W = WARPS_PER_BLOCK;
-    int off[W + 1];
-    off[0] = 0;
+    WarpWS& me = wsa[warp];
+    // slot offsets: exclusive prefix of the counts, each rounded up to a multiple of four (every warp
+    // keeps its own copy in shared memory; lanes 0..W-1 scan)
+    {
+        const int padded = (lane < W) ? ((bs->cnt[lane] + 3) & ~3) : 0;
+        int incl = padded;
 #pragma unroll
-    for (int i = 0; i < W; ++i) {
-        off[i + 1] = off[i] + ((bs->cnt[i] + 3) & ~3);
+        for (int d = 1; d < 16; d <<= 1) {
+            const int up = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) {
+                incl += up;
+            }
+        }
+        if (lane <= W) {
+            me.off[lane] = incl - padded;  // lane W: total
+        }
+        __syncwarp();
     }
+    const int* off = me.off;
     const int total = off[W];
     if (total == 0) {
         return;
     }
-    WarpWS& me = wsa[warp];
-    int my_lo = 0, my_cnt = 0;
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-        if (i == warp) {
-            my_lo = off[i];
-            my_cnt = bs->cnt[i];
-        }
-    }
+    const int my_lo = off[warp], my_cnt = bs->cnt[warp];
     const int my_hi = my_lo + ((my_cnt + 3) & ~3);
     float* tile = me.u.tile;
 
@@ -740,10 +774,13 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
         }
         float g = 0.f, c = 0.f, s = 0.f, cd = 0.f, sd = 0.f;
         const float* Wb = bt->voiced_win;
+        bool k2lane = false;  // this lane's slot is an interpolated harmonic: written by whoever computes it
         if (owner >= 0) {
             const WarpWS& o = wsa[owner];
             const int id = o.comp[j];
-            if ((id & 3) != 2) {
+            if ((id & 3) == 2) {
+                k2lane = true;
+            } else {
                 const int l = id >> 2;
                 float step, ph;
                 if ((id & 3) == 0) {
@@ -763,57 +800,69 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
                 c = p.y;
             }
         }
-        // this stream's slots inside the round, and its interpolated harmonics among them
+        STAGE_T(8);  // offsets + oscillator start states
+        // this stream's slots inside the round
         const int lo = max(my_lo, base), hi = min(my_hi, base + 32 * W);
-        unsigned k2 = 0;
-        if (hi > lo && me.k2mask) {
-            const int sh = lo - my_lo;  // list position of the first slot of this round
-            k2 = (sh < 32) ? (me.k2mask >> sh) : 0u;
-            if (hi - lo < 32) {
-                k2 &= (1u << (hi - lo)) - 1u;  // the rest of the list belongs to the next round
-            }
+        // interpolated harmonics of the round: every warp walks the same enumeration and takes every W-th
+        int n_interp = 0;
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            n_interp += __popc(round_k2mask(wsa[i].k2mask, off[i], bs->cnt[i], base, 32 * W));
         }
+        const bool has_pass = (base + 32 * warp) < total;  // warps beyond the last slot skip phase A
 #pragma unroll 1
         for (int ch = 0; ch < 5; ++ch) {
             const float* Wc = Wb + 32 * ch;
             float* tcol = tile + lane;
 #pragma unroll(kOscUnroll)
-            for (int n4 = 0; n4 < 8; ++n4) {
+            for (int n4 = 0; has_pass && n4 < 8; ++n4) {
                 const float4 w4 = *reinterpret_cast<const float4*>(Wc + 4 * n4);
                 const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    tcol[(4 * n4 + q) * TILE_STRIDE] = (g * wv[q]) * c;
+                    if (!k2lane) {
+                        tcol[(4 * n4 + q) * TILE_STRIDE] = (g * wv[q]) * c;
+                    }
                     const float cn = (c * cd) - (s * sd);
                     const float sn = (s * cd) + (c * sd);
                     c = cn;
                     s = sn;
                 }
             }
-            __syncthreads();
-            if (hi > lo) {
+            STAGE_T(9);  // phase A
+            if (n_interp) {
                 const int n = 32 * ch + lane;
-                if (k2) {
-                    const Parms& cur = me.cur;
-                    const ParmsSmall& prev = me.enh;
-                    const float cw0 = cur.w0, pw0 = prev.w0;
-                    unsigned m = k2;
+                int t = 0;
+#pragma unroll 1
+                for (int i = 0; i < W; ++i) {
+                    unsigned m = round_k2mask(wsa[i].k2mask, off[i], bs->cnt[i], base, 32 * W);
+                    const int ilo = max(off[i], base);
                     while (m) {
                         const int jj = __ffs(m) - 1;
                         m &= m - 1;
-                        const int slot = lo + jj - base;  // slot index inside the round
-                        const int l = me.comp[lo - my_lo + jj] >> 2;
+                        if ((t++ % W) != warp) {
+                            continue;
+                        }
+                        const WarpWS& o = wsa[i];
+                        const int slot = ilo + jj - base;  // slot index inside the round
+                        const int l = o.comp[ilo - off[i] + jj] >> 2;
+                        const float cw0 = o.cur.w0, pw0 = o.enh.w0;
                         const float pw0l = pw0 * (float)l;
-                        const float dphi = cur.PHIl[l] - prev.PHIl[l] - (((pw0 + cw0) * (float)(l * NS)) / 2.0f);
+                        const float dphi = o.cur.PHIl[l] - o.enh.PHIl[l] - (((pw0 + cw0) * (float)(l * NS)) / 2.0f);
                         const float dw = (1.0f / (float)NS)
                                          * (dphi - (2.0f * MBE_PI_F * floorf((dphi + MBE_PI_F) / (2.0f * MBE_PI_F))));
-                        const float th = prev.PHIl[l] + ((pw0l + dw) * (float)n)
+                        const float th = o.enh.PHIl[l] + ((pw0l + dw) * (float)n)
                                          + (((cw0 - pw0) * (float)(l * n * n)) / (float)(2 * NS));
-                        const float am = prev.Ml[l] + (((float)n / (float)NS) * (cur.Ml[l] - prev.Ml[l]));
+                        const float am = o.enh.Ml[l] + (((float)n / (float)NS) * (o.cur.Ml[l] - o.enh.Ml[l]));
                         wsa[slot >> 5].u.tile[lane * TILE_STRIDE + (slot & 31)] = 2.0f * am * dev_cosf(th);
                     }
-                    __syncwarp();
                 }
+            }
+            STAGE_T(10);  // interpolated harmonics
+            __syncthreads();
+            STAGE_T(11);  // wait for phase A of the block
+            if (hi > lo) {
+                const int n = 32 * ch + lane;
                 float a = me.out[n];
 #pragma unroll 2
                 for (int k4 = lo - base; k4 < hi - base; k4 += 4) {
@@ -825,7 +874,9 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
                 }
                 me.out[n] = a;
             }
+            STAGE_T(12);  // phase B
             __syncthreads();
+            STAGE_T(13);  // wait for phase B of the block
         }
     }
 }
@@ -925,13 +976,15 @@ __device__ __noinline__ void synth_finish(WarpWS& ws, const float* __restrict__ 
 }
 
 // ---- tone synthesis (mbelib.c:692-856, src/internal/mbe_tone.h) -----------------------------------
+// dual-tone (DTMF / call-progress) frequency pairs for tone ids 128..163 (src/internal/mbe_tone.h)
+static __device__ const unsigned short k_dual_tones[36][2] = {
+    {1336, 941}, {1209, 697}, {1336, 697}, {1477, 697}, {1209, 770}, {1336, 770}, {1477, 770}, {1209, 852},
+    {1336, 852}, {1477, 852}, {1633, 697}, {1633, 770}, {1633, 852}, {1633, 941}, {1209, 941}, {1477, 941},
+    {1162, 820}, {1052, 606}, {1162, 606}, {1279, 606}, {1052, 672}, {1162, 672}, {1279, 672}, {1052, 743},
+    {1162, 743}, {1279, 743}, {1430, 606}, {1430, 672}, {1430, 743}, {1430, 820}, {1052, 820}, {1279, 820},
+    {440, 350},  {480, 440},  {620, 480},  {490, 350}};
+
 __device__ __forceinline__ bool tone_freqs(int id, float* f1, float* f2) {
-    const unsigned short dual[36][2] = {
-        {1336, 941}, {1209, 697}, {1336, 697}, {1477, 697}, {1209, 770}, {1336, 770}, {1477, 770}, {1209, 852},
-        {1336, 852}, {1477, 852}, {1633, 697}, {1633, 770}, {1633, 852}, {1633, 941}, {1209, 941}, {1477, 941},
-        {1162, 820}, {1052, 606}, {1162, 606}, {1279, 606}, {1052, 672}, {1162, 672}, {1279, 672}, {1052, 743},
-        {1162, 743}, {1279, 743}, {1430, 606}, {1430, 672}, {1430, 743}, {1430, 820}, {1052, 820}, {1279, 820},
-        {440, 350},  {480, 440},  {620, 480},  {490, 350}};
     *f1 = *f2 = 0.0f;
     if (id == 5) {
         *f1 = *f2 = 156.25f;
@@ -946,8 +999,8 @@ __device__ __forceinline__ bool tone_freqs(int id, float* f1, float* f2) {
         return true;
     }
     if (id >= 128 && id <= 163) {
-        *f1 = (float)dual[id - 128][0];
-        *f2 = (float)dual[id - 128][1];
+        *f1 = (float)k_dual_tones[id - 128][0];
+        *f2 = (float)k_dual_tones[id - 128][1];
         return true;
     }
     return false;
