@@ -189,17 +189,24 @@ struct __align__(16) WarpWS {
     } u;                                  // 16-byte aligned: rows are read with LDS.128
     float out[NS];                        // the frame's 160 float samples (lane i owns i, 32+i, ...)
     float gain[112];                      // per-component 2*Ml
-    Parms cur;                            // cur_mp, complete
-    ParmsSmall prev, enh;                 // prev_mp / prev_mp_enhanced without their bulk arrays
+    Parms cur;                            // cur_mp, complete (16-byte aligned for 128-bit struct copies)
+    uint32_t pad_cur;
+    ParmsSmall prev;                      // prev_mp / prev_mp_enhanced without their bulk arrays
+    uint32_t pad_prev;
+    ParmsSmall enh;
+    uint32_t pad_enh;
     float nz[57];                         // white-noise samples 1..56 of the frame (phase randomisation)
     unsigned rowbits[8];
     int ncomp;                            // oscillator components of this frame (0: no voiced synthesis)
     int off[WARPS_PER_BLOCK + 3];         // this warp's copy of the block's slot offsets (prefix of padded counts)
     unsigned k2mask;                      // list positions (< 32) of phase-interpolated harmonics
+    unsigned short interp_item[8];        // interpolated harmonics of the block this warp renders: owner << 8 | position
     unsigned char comp[112];              // component descriptor: harmonic << 2 | kind
     unsigned char rel[8 * 24];            // soft-bit reliabilities of the frame
 };
-static_assert(offsetof(WarpWS, u) % 16 == 0 && sizeof(WarpWS) % 16 == 0 && sizeof(BlockTables) % 16 == 0, "LDS.128 alignment");
+static_assert(offsetof(WarpWS, u) % 16 == 0 && sizeof(WarpWS) % 16 == 0 && sizeof(BlockTables) % 16 == 0 &&
+                  offsetof(WarpWS, cur) % 16 == 0 && offsetof(WarpWS, prev) % 16 == 0 && offsetof(WarpWS, enh) % 16 == 0,
+              "LDS.128 alignment");
 
 struct BlockShared {
     int cnt[WARPS_PER_BLOCK + 3];         // per stream: component count of the current frame

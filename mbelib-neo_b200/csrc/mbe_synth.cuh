@@ -43,13 +43,18 @@ __device__ __forceinline__ bool bands_ok(int L) { return L >= 1 && L <= MAXL; }
 // only ever reads back global words it wrote itself.
 template <class D, class S>
 __device__ __forceinline__ void copy_small(D& dst, const S& src, int lane) {
-    uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(&src);
-#pragma unroll 5
-    for (int i = lane; i < HEAD_WORDS; i += 32) {
-        d[i] = s[i];
+    // 298 head words = 74 x 16 bytes + 2 words; the structs are 16-byte aligned inside WarpWS
+    float4* d4 = reinterpret_cast<float4*>(&dst);
+    const float4* s4 = reinterpret_cast<const float4*>(&src);
+    d4[lane] = s4[lane];
+    d4[32 + lane] = s4[32 + lane];
+    if (lane < 10) {
+        d4[64 + lane] = s4[64 + lane];
     }
-    if (lane == 0) {
+    if (lane < 2) {
+        reinterpret_cast<uint32_t*>(&dst)[296 + lane] = reinterpret_cast<const uint32_t*>(&src)[296 + lane];
+    }
+    if (lane == 2) {
         dst.noiseSeed = src.noiseSeed;
     }
     __syncwarp();
@@ -803,11 +808,34 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
         STAGE_T(8);  // offsets + oscillator start states
         // this stream's slots inside the round
         const int lo = max(my_lo, base), hi = min(my_hi, base + 32 * W);
-        // interpolated harmonics of the round: every warp walks the same enumeration and takes every W-th
-        int n_interp = 0;
+        // interpolated harmonics of the round: every warp walks the same enumeration once and keeps every
+        // W-th item (owner stream, list position) for itself
+        int n_mine = 0;
+        {
+            unsigned any = 0;
 #pragma unroll
-        for (int i = 0; i < W; ++i) {
-            n_interp += __popc(round_k2mask(wsa[i].k2mask, off[i], bs->cnt[i], base, 32 * W));
+            for (int i = 0; i < W; ++i) {
+                any |= wsa[i].k2mask;
+            }
+            if (any) {
+                int t = 0;
+#pragma unroll 1
+                for (int i = 0; i < W; ++i) {
+                    unsigned m = round_k2mask(wsa[i].k2mask, off[i], bs->cnt[i], base, 32 * W);
+                    const int first = max(off[i], base) - off[i];
+                    while (m) {
+                        const int jj = __ffs(m) - 1;
+                        m &= m - 1;
+                        if ((t++ % W) == warp) {
+                            if (lane == 0) {
+                                me.interp_item[n_mine] = (unsigned short)((i << 8) | (first + jj));
+                            }
+                            ++n_mine;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
         }
         const bool has_pass = (base + 32 * warp) < total;  // warps beyond the last slot skip phase A
 #pragma unroll 1
@@ -830,32 +858,24 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
                 }
             }
             STAGE_T(9);  // phase A
-            if (n_interp) {
+            if (n_mine) {
                 const int n = 32 * ch + lane;
-                int t = 0;
 #pragma unroll 1
-                for (int i = 0; i < W; ++i) {
-                    unsigned m = round_k2mask(wsa[i].k2mask, off[i], bs->cnt[i], base, 32 * W);
-                    const int ilo = max(off[i], base);
-                    while (m) {
-                        const int jj = __ffs(m) - 1;
-                        m &= m - 1;
-                        if ((t++ % W) != warp) {
-                            continue;
-                        }
-                        const WarpWS& o = wsa[i];
-                        const int slot = ilo + jj - base;  // slot index inside the round
-                        const int l = o.comp[ilo - off[i] + jj] >> 2;
-                        const float cw0 = o.cur.w0, pw0 = o.enh.w0;
-                        const float pw0l = pw0 * (float)l;
-                        const float dphi = o.cur.PHIl[l] - o.enh.PHIl[l] - (((pw0 + cw0) * (float)(l * NS)) / 2.0f);
-                        const float dw = (1.0f / (float)NS)
-                                         * (dphi - (2.0f * MBE_PI_F * floorf((dphi + MBE_PI_F) / (2.0f * MBE_PI_F))));
-                        const float th = o.enh.PHIl[l] + ((pw0l + dw) * (float)n)
-                                         + (((cw0 - pw0) * (float)(l * n * n)) / (float)(2 * NS));
-                        const float am = o.enh.Ml[l] + (((float)n / (float)NS) * (o.cur.Ml[l] - o.enh.Ml[l]));
-                        wsa[slot >> 5].u.tile[lane * TILE_STRIDE + (slot & 31)] = 2.0f * am * dev_cosf(th);
-                    }
+                for (int q = 0; q < n_mine; ++q) {
+                    const int item = me.interp_item[q];
+                    const int i = item >> 8, pos = item & 255;
+                    const WarpWS& o = wsa[i];
+                    const int slot = off[i] + pos - base;  // slot index inside the round
+                    const int l = o.comp[pos] >> 2;
+                    const float cw0 = o.cur.w0, pw0 = o.enh.w0;
+                    const float pw0l = pw0 * (float)l;
+                    const float dphi = o.cur.PHIl[l] - o.enh.PHIl[l] - (((pw0 + cw0) * (float)(l * NS)) / 2.0f);
+                    const float dw = (1.0f / (float)NS)
+                                     * (dphi - (2.0f * MBE_PI_F * floorf((dphi + MBE_PI_F) / (2.0f * MBE_PI_F))));
+                    const float th = o.enh.PHIl[l] + ((pw0l + dw) * (float)n)
+                                     + (((cw0 - pw0) * (float)(l * n * n)) / (float)(2 * NS));
+                    const float am = o.enh.Ml[l] + (((float)n / (float)NS) * (o.cur.Ml[l] - o.enh.Ml[l]));
+                    wsa[slot >> 5].u.tile[lane * TILE_STRIDE + (slot & 31)] = 2.0f * am * dev_cosf(th);
                 }
             }
             STAGE_T(10);  // interpolated harmonics
@@ -864,13 +884,30 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
             if (hi > lo) {
                 const int n = 32 * ch + lane;
                 float a = me.out[n];
-#pragma unroll 2
-                for (int k4 = lo - base; k4 < hi - base; k4 += 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(wsa[k4 >> 5].u.tile + lane * TILE_STRIDE + (k4 & 31));
-                    a += v.x;
-                    a += v.y;
-                    a += v.z;
-                    a += v.w;
+                int k4 = lo - base;
+                const int end = hi - base;
+#pragma unroll 1
+                while (k4 < end) {
+                    // the part of this stream's slot range that lies in one tile: loads first, then the adds in order
+                    const int tix = k4 >> 5;
+                    const int e = min(end, (tix + 1) << 5);
+                    const float4* row = reinterpret_cast<const float4*>(wsa[tix].u.tile + lane * TILE_STRIDE + (k4 & 31));
+                    const int nq = (e - k4) >> 2;
+                    int q = 0;
+#pragma unroll 1
+                    for (; q + 4 <= nq; q += 4) {
+                        const float4 v0 = row[q], v1 = row[q + 1], v2 = row[q + 2], v3 = row[q + 3];
+                        a += v0.x; a += v0.y; a += v0.z; a += v0.w;
+                        a += v1.x; a += v1.y; a += v1.z; a += v1.w;
+                        a += v2.x; a += v2.y; a += v2.z; a += v2.w;
+                        a += v3.x; a += v3.y; a += v3.z; a += v3.w;
+                    }
+#pragma unroll 1
+                    for (; q < nq; ++q) {
+                        const float4 v = row[q];
+                        a += v.x; a += v.y; a += v.z; a += v.w;
+                    }
+                    k4 = e;
                 }
                 me.out[n] = a;
             }
