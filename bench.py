@@ -203,9 +203,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
+    from importlib import import_module
+    sharding = import_module("mbelib_neo_b200.sharding")
+    first_global, _ = sharding.weak_shard(S, rank)      # this rank's block of global stream ids
     dec = pkg.Decoder(max_streams=S, device=local_rank)
-    seeds = (np.arange(S, dtype=np.uint64) + 0xC0FFEE + rank * S).astype(np.uint32)
-    dec.init_streams(0, S, seeds)
+    dec.init_streams(0, S, sharding.stream_seeds(first_global, S))
 
     fb = FRAME_BITS[codec]
     gen = torch.Generator(device=dev)
@@ -225,11 +227,7 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(x, device=dev)
 
     # ---- device-resident arm ----
     with torch.cuda.stream(stream):
