@@ -85,7 +85,7 @@ __device__ __forceinline__ int resolve_total_errors(int c0, int prot, int c4, in
 // ---- IMBE 4400 frame state machine (imbe7200x4400.c:780-888) --------------------------------------
 __device__ __forceinline__ Action process_imbe(FrameCtx& fc, const unsigned dw[3], WarpWS& ws, const StreamHome& home,
                                                const DevTables* T, int lane) {
-    Parms& cur = ws.cur;
+    ParmsSmall& cur = ws.cur;
     ParmsSmall& prev = ws.prev;
     const float rate = (0.95f * prev.errorRate) + (0.000365f * (float)fc.total);
     __syncwarp();
@@ -149,12 +149,12 @@ __device__ __forceinline__ Action process_imbe(FrameCtx& fc, const unsigned dw[3
 
 // ---- AMBE helpers (ambe_common.c:191-271) ----------------------------------------------------------
 __device__ __forceinline__ void init_ambe(WarpWS& ws, const StreamHome& home, const DevTables* T, int lane) {
-    init_all(ws, home.prev, home.enh, T->ambe_default_w0, 15, 0, 0.096f, lane);
+    init_all(ws, home.cur, home.prev, home.enh, T->ambe_default_w0, 15, 0, 0.096f, lane);
 }
 
 // erasure model built in cur_mp from prev_mp: phases, noise generator and WOLA tail carried over
 __device__ __forceinline__ void set_erasure_model(WarpWS& ws, const StreamHome& home, int lane) {
-    Parms& mp = ws.cur;
+    ParmsSmall& mp = ws.cur;
     const ParmsSmall& src = ws.prev;
     for (int l = lane; l <= 56; l += 32) {
         mp.Ml[l] = 1.0f;
@@ -163,7 +163,7 @@ __device__ __forceinline__ void set_erasure_model(WarpWS& ws, const StreamHome& 
         mp.PHIl[l] = src.PHIl[l];
         mp.PSIl[l] = src.PSIl[l];
     }
-    bulk_load(mp, home.prev, lane);
+    bulk_copy(home.cur, home.prev, lane);
     if (lane == 0) {
         mp.swn = 0;
         mp.tonePhase = 0;
@@ -323,15 +323,19 @@ __device__ __forceinline__ int render_begin(const Action& act, WarpWS& ws, const
             rm0 = spectral_enhance(ws.cur, lane);
             has_rm0 = 1;
         } else {
-            // replay the last voice model (ambe3600x2450.c:808-816): cur_mp is parked in its HBM home
+            // replay the last voice model (ambe3600x2450.c:808-816): cur_mp is parked in the stream's scratch image
             const uint32_t* cw = reinterpret_cast<const uint32_t*>(&ws.cur);
-            for (int i = lane; i < PARMS_WORDS; i += 32) {
-                home.cur[i] = cw[i];
+            for (int i = lane; i < HEAD_WORDS; i += 32) {
+                home.spill[i] = cw[i];
             }
+            if (lane == 0) {
+                home.spill[SEED_WORD] = cw[HEAD_WORDS];
+            }
+            bulk_copy(home.spill, home.cur, lane);
             __syncwarp();
             cur_from_enh(ws, home, lane);
         }
-        return synth_begin(ws, T, has_rm0, rm0, lane);
+        return synth_begin(ws, reinterpret_cast<const float*>(home.cur + OVERLAP_WORD), T, has_rm0, rm0, lane);
     }
     if (AMBE) {
         if (kind == ACT_TONE) {
@@ -360,14 +364,18 @@ __device__ __forceinline__ void render_end(const Action& act, int go, WarpWS& ws
         return;
     }
     if (go) {
-        synth_finish(ws, reinterpret_cast<const float*>(home.enh + UW_WORD), T, bt, lane);
+        synth_finish(ws, home.cur, home.enh, T, bt, lane);
     }
     enh_from_cur(ws, home, lane);
     if (AMBE && kind == ACT_REPLAY) {
         uint32_t* cw = reinterpret_cast<uint32_t*>(&ws.cur);
-        for (int i = lane; i < PARMS_WORDS; i += 32) {
-            cw[i] = home.cur[i];
+        for (int i = lane; i < HEAD_WORDS; i += 32) {
+            cw[i] = home.spill[i];
         }
+        if (lane == 0) {
+            cw[HEAD_WORDS] = home.spill[SEED_WORD];  // written by lane 0 above
+        }
+        bulk_copy(home.cur, home.spill, lane);
         __syncwarp();
     }
 }
@@ -378,12 +386,6 @@ __device__ __forceinline__ void load_block_tables(BlockTables* bt, const DevTabl
     }
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         bt->tw[i] = T->tw[i];
-        bt->uvwin[i] = T->uvwin[i];
-    }
-    for (int i = threadIdx.x; i < 160; i += blockDim.x) {
-        bt->wola_wp[i] = T->wola_wp[i];
-        bt->wola_wc[i] = T->wola_wc[i];
-        bt->wola_den[i] = T->wola_den[i];
     }
     __syncthreads();
 }
@@ -402,19 +404,18 @@ __device__ __forceinline__ void store_pcm(const LaunchArgs& A, const WarpWS& ws,
     }
 }
 
-// stream state: HBM slot <-> shared memory (cur complete, prev / enh without their bulk arrays)
+// stream state: HBM slot <-> shared memory (the three structs without their bulk arrays, which stay in HBM)
 __device__ __forceinline__ void load_stream(WarpWS& ws, const uint32_t* gs, int lane) {
     uint32_t* c = reinterpret_cast<uint32_t*>(&ws.cur);
     uint32_t* p = reinterpret_cast<uint32_t*>(&ws.prev);
     uint32_t* e = reinterpret_cast<uint32_t*>(&ws.enh);
-    for (int i = lane; i < PARMS_WORDS; i += 32) {
-        c[i] = gs[i];
-    }
     for (int i = lane; i < HEAD_WORDS; i += 32) {
+        c[i] = gs[i];
         p[i] = gs[PARMS_WORDS + i];
         e[i] = gs[2 * PARMS_WORDS + i];
     }
     if (lane == 0) {
+        c[HEAD_WORDS] = gs[SEED_WORD];
         p[HEAD_WORDS] = gs[PARMS_WORDS + SEED_WORD];
         e[HEAD_WORDS] = gs[2 * PARMS_WORDS + SEED_WORD];
         ws.rng.comfort = (unsigned long long)gs[3 * PARMS_WORDS] | ((unsigned long long)gs[3 * PARMS_WORDS + 1] << 32);
@@ -429,14 +430,13 @@ __device__ __forceinline__ void store_stream(const WarpWS& ws, uint32_t* gs, int
     const uint32_t* p = reinterpret_cast<const uint32_t*>(&ws.prev);
     const uint32_t* e = reinterpret_cast<const uint32_t*>(&ws.enh);
     __syncwarp();
-    for (int i = lane; i < PARMS_WORDS; i += 32) {
-        gs[i] = c[i];
-    }
     for (int i = lane; i < HEAD_WORDS; i += 32) {
+        gs[i] = c[i];
         gs[PARMS_WORDS + i] = p[i];
         gs[2 * PARMS_WORDS + i] = e[i];
     }
     if (lane == 0) {
+        gs[SEED_WORD] = c[HEAD_WORDS];
         gs[PARMS_WORDS + SEED_WORD] = p[HEAD_WORDS];
         gs[2 * PARMS_WORDS + SEED_WORD] = e[HEAD_WORDS];
         gs[3 * PARMS_WORDS] = (uint32_t)(ws.rng.comfort & 0xffffffffULL);
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
     constexpr size_t fstride = (MODE == MODE_DATA) ? (size_t)pbits : (size_t)fbits * (SOFT ? 2u : 1u);
 
     uint32_t* gs = A.state + (size_t)(A.first_stream + (live ? s : 0)) * STATE_WORDS;
-    const StreamHome home = {gs, gs + PARMS_WORDS, gs + 2 * PARMS_WORDS};
+    const StreamHome home = {gs, gs + PARMS_WORDS, gs + 2 * PARMS_WORDS, gs + SPILL_WORD};
     if (live) {
         load_stream(ws, gs, lane);
     }
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
         if (live) {
             const uint8_t* fr = A.frames + idx * fstride;
             if (MODE == MODE_FRAMES) {
-                FrontResult R = front_end(CODEC, SOFT, fr, dw, ws.rel, ws.u.dec.cost, ws.rowbits, T, lane);
+                FrontResult R = front_end(CODEC, SOFT, fr, dw, ws.u.dec.rel, ws.u.dec.cost, ws.u.dec.rowbits, T, lane);
                 status = R.status;
                 fc.total = R.c0 + R.prot;
                 fc.c0 = R.c0;
@@ -629,14 +629,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
     uint32_t* e = reinterpret_cast<uint32_t*>(&ws.enh);
     int go = 0;
     if (live) {
-        for (int i = lane; i < PARMS_WORDS; i += 32) {
-            c[i] = gc[i];
-        }
         for (int i = lane; i < HEAD_WORDS; i += 32) {
+            c[i] = gc[i];
             e[i] = gp[i];
         }
         // RNG as after mbe_setThreadRngSeed(seed) (mbelib.c:173-181); no seeds: fresh-thread defaults
         if (lane == 0) {
+            c[HEAD_WORDS] = gc[SEED_WORD];
             e[HEAD_WORDS] = gp[SEED_WORD];
             if (A.synth_seeds) {
                 unsigned seed = A.synth_seeds[s];
@@ -653,7 +652,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
             }
         }
         __syncwarp();
-        go = synth_begin(ws, T, 0, 0.0f, lane);
+        go = synth_begin(ws, reinterpret_cast<const float*>(gc + OVERLAP_WORD), T, 0, 0.0f, lane);
     }
     if (lane == 0) {
         bs->cnt[warp] = go ? ws.ncomp : 0;
@@ -663,17 +662,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
     voiced_bank_block(wsa, bs, bt, tm, warp, lane);
     if (live) {
         if (go) {
-            synth_finish(ws, reinterpret_cast<const float*>(gp + UW_WORD), T, bt, lane);
+            synth_finish(ws, gc, gp, T, bt, lane);
         }
         __syncwarp();
         store_pcm(A, ws, (size_t)s, lane);
-        for (int i = lane; i < PARMS_WORDS; i += 32) {
-            gc[i] = c[i];
-        }
         for (int i = lane; i < HEAD_WORDS; i += 32) {
+            gc[i] = c[i];
             gp[i] = e[i];
         }
         if (lane == 0) {
+            gc[SEED_WORD] = c[HEAD_WORDS];
             gp[SEED_WORD] = e[HEAD_WORDS];
         }
     }

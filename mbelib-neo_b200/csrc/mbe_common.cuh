@@ -75,7 +75,8 @@ static_assert(offsetof(Parms, previousUw) == UW_WORD * 4 && offsetof(Parms, nois
               "mbe_parms offsets");
 constexpr int PARMS_WORDS = sizeof(Parms) / 4;            // 651
 constexpr int RNG_WORDS = 4;                              // comfort lo, comfort hi, uv seed, uv override
-constexpr int STATE_WORDS = 3 * PARMS_WORDS + RNG_WORDS;  // per stream in HBM: cur, prev, enh, rng (7828 B)
+constexpr int SPILL_WORD = 3 * PARMS_WORDS + RNG_WORDS;   // a fourth mbe_parms image: scratch of the AMBE+2 replay path
+constexpr int STATE_WORDS = 4 * PARMS_WORDS + RNG_WORDS;  // per stream in HBM: cur, prev, enh, rng, scratch (10432 B)
 
 // Tables computed on the host when a context is created (host libm = the reference's libm) and kept
 // in HBM; hot ones are staged into shared memory per block.
@@ -147,18 +148,16 @@ constexpr int TILE_STRIDE = 36;   // floats per sample row of the oscillator til
 struct __align__(16) BlockTables {
     float voiced_win[324];   // 321-pt voiced window Ws (mbelib_const.h), 16-byte aligned rows for LDS.128
     float tw[256];           // FFTPACK twiddles
-    float uvwin[256];        // unvoiced analysis window, centred at 128
-    float wola_wp[160], wola_wc[160], wola_den[160];
 };
 
 // Streams (= warps) per block.  The block walks its streams' frames in lockstep: per frame every warp
 // decodes its own stream, then the block pools the oscillator components of all its streams and
 // spreads them evenly over all lanes (voiced_bank_block), then every warp finishes its own stream.
 #ifndef MBE_WPB
-#define MBE_WPB 9
+#define MBE_WPB 8
 #endif
 #ifndef MBE_MINB
-#define MBE_MINB 2
+#define MBE_MINB 3
 #endif
 constexpr int WARPS_PER_BLOCK = MBE_WPB;
 constexpr int MIN_BLOCKS_PER_SM = MBE_MINB;
@@ -180,29 +179,30 @@ struct __align__(16) WarpWS {
             float b[NFFT];                // FFT pong buffer
             float scale[132];             // per-bin unvoiced band scale
         } fft;
-        struct {                          // parameter decode scratch (dead before synthesis starts)
+        struct {                          // front-end / parameter decode scratch (dead before synthesis starts)
             float tmp[128];               // per-harmonic terms [1..56], DCT coefficients [64+l]
             float Tl[60];
             int field[58];                // IMBE quantiser words b1..bL+1
             unsigned short cost[640];     // soft-decision partial cost tables
+            unsigned rowbits[8];
+            unsigned char rel[8 * 24];    // soft-bit reliabilities of the frame
         } dec;
+        float nz[57];                     // white-noise samples 1..56 of the frame (phase randomisation; dead before the bank)
     } u;                                  // 16-byte aligned: rows are read with LDS.128
     float out[NS];                        // the frame's 160 float samples (lane i owns i, 32+i, ...)
-    float gain[112];                      // per-component 2*Ml
-    Parms cur;                            // cur_mp, complete (16-byte aligned for 128-bit struct copies)
+    // The three mbe_parms of the stream WITHOUT their bulk arrays (previousUw / noiseOverlap stay in the
+    // stream's HBM slot); 16-byte aligned for 128-bit struct copies.
+    ParmsSmall cur;
     uint32_t pad_cur;
-    ParmsSmall prev;                      // prev_mp / prev_mp_enhanced without their bulk arrays
+    ParmsSmall prev;
     uint32_t pad_prev;
     ParmsSmall enh;
     uint32_t pad_enh;
-    float nz[57];                         // white-noise samples 1..56 of the frame (phase randomisation)
-    unsigned rowbits[8];
     int ncomp;                            // oscillator components of this frame (0: no voiced synthesis)
-    int off[WARPS_PER_BLOCK + 3];         // this warp's copy of the block's slot offsets (prefix of padded counts)
     unsigned k2mask;                      // list positions (< 32) of phase-interpolated harmonics
+    unsigned short off[WARPS_PER_BLOCK + 3];  // this warp's copy of the block's slot offsets (prefix of padded counts)
     unsigned short interp_item[8];        // interpolated harmonics of the block this warp renders: owner << 8 | position
     unsigned char comp[112];              // component descriptor: harmonic << 2 | kind
-    unsigned char rel[8 * 24];            // soft-bit reliabilities of the frame
 };
 static_assert(offsetof(WarpWS, u) % 16 == 0 && sizeof(WarpWS) % 16 == 0 && sizeof(BlockTables) % 16 == 0 &&
                   offsetof(WarpWS, cur) % 16 == 0 && offsetof(WarpWS, prev) % 16 == 0 && offsetof(WarpWS, enh) % 16 == 0,

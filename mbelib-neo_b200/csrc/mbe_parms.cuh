@@ -27,7 +27,7 @@ __device__ __forceinline__ unsigned pick(const unsigned dw[3]) {
 //   ambe = 1: rho = 0.65, add BigGamma, unvoiced magnitudes scaled by unvc
 __device__ __forceinline__ void predict_magnitudes(WarpWS& ws, const DevTables* T, int ambe, float rho, float unvc,
                                                    int lane) {
-    Parms& cur = ws.cur;
+    ParmsSmall& cur = ws.cur;
     ParmsSmall& prev = ws.prev;
     const int cur_L = cur.L;  // already within 9..56
     int prev_L = prev.L;
@@ -139,7 +139,7 @@ __device__ __forceinline__ void block_idct(WarpWS& ws, const DevTables* T, const
 
 // ---- IMBE 4400 ----  returns 0 (voice) or 1 (invalid fundamental -> repeat)
 __device__ __forceinline__ int decode_imbe(const unsigned dw[3], WarpWS& ws, const DevTables* T, int lane) {
-    Parms& cur = ws.cur;
+    ParmsSmall& cur = ws.cur;
     unsigned b0 = 0;
     {
         const int idx[8] = {0, 1, 2, 3, 4, 5, 85, 86};
@@ -270,7 +270,7 @@ struct AmbeBooks {
 
 __device__ __forceinline__ void ambe_tail(WarpWS& ws, const DevTables* T, const AmbeBooks& bk, int b3, int b4,
                                           const int hocidx[4], float unvc, int lane) {
-    Parms& cur = ws.cur;
+    ParmsSmall& cur = ws.cur;
     const int L = cur.L;
     if (lane < 8) {
         float g;
@@ -338,7 +338,7 @@ __device__ __forceinline__ void ambe_tail(WarpWS& ws, const DevTables* T, const 
 // ---- AMBE+2 3600x2450 ---- returns 0 voice | 2 erasure | 7 tone
 __device__ __forceinline__ int decode_ambe2450(const unsigned dw[3], WarpWS& ws, const DevTables* T, int total_errors,
                                                int lane) {
-    Parms& cur = ws.cur;
+    ParmsSmall& cur = ws.cur;
     unsigned u0 = 0, u1 = 0, u3 = 0;
     for (int i = 0; i < 12; ++i) {
         u0 = (u0 << 1) | getbit(dw, i);
@@ -400,7 +400,7 @@ __device__ __forceinline__ int decode_ambe2450(const unsigned dw[3], WarpWS& ws,
 
 // ---- AMBE 3600x2400 ---- returns 0 voice | 3 tone/silence marker | 5..122 D-STAR tone index
 __device__ __forceinline__ int decode_ambe2400(const unsigned dw[3], WarpWS& ws, const DevTables* T, int lane) {
-    Parms& cur = ws.cur;
+    ParmsSmall& cur = ws.cur;
     const int b0 = (int)pick<0, 1, 2, 3, 4, 5, 48>(dw);
     if ((b0 & 0x7E) == 0x7E) {
         // three remapped high bits (t7,t6,t5 tables of the reference folded into one) + five literal bits

@@ -60,31 +60,27 @@ __device__ __forceinline__ void copy_small(D& dst, const S& src, int lane) {
     __syncwarp();
 }
 
-__device__ __forceinline__ void bulk_store(const Parms& c, uint32_t* g, int lane) {
-    const uint32_t* uw = reinterpret_cast<const uint32_t*>(c.previousUw);
-    const uint32_t* ov = reinterpret_cast<const uint32_t*>(c.noiseOverlap);
+// previousUw[256] + noiseOverlap[96] of one struct image to another, both in HBM (11 independent loads per
+// lane in flight, then 11 stores)
+// (plain pointers: these words are written by this kernel too, so they must not go through the read-only path)
+__device__ __forceinline__ void bulk_copy(uint32_t* dst, const uint32_t* src, int lane) {
+    uint32_t v[11];
 #pragma unroll
-    for (int i = lane; i < 256; i += 32) {
-        g[UW_WORD + i] = uw[i];
+    for (int k = 0; k < 8; ++k) {
+        v[k] = src[UW_WORD + 32 * k + lane];
     }
 #pragma unroll
-    for (int i = lane; i < 96; i += 32) {
-        g[OVERLAP_WORD + i] = ov[i];
-    }
-}
-
-__device__ __forceinline__ void bulk_load(Parms& c, const uint32_t* g, int lane) {
-    uint32_t* uw = reinterpret_cast<uint32_t*>(c.previousUw);
-    uint32_t* ov = reinterpret_cast<uint32_t*>(c.noiseOverlap);
-#pragma unroll
-    for (int i = lane; i < 256; i += 32) {
-        uw[i] = g[UW_WORD + i];
+    for (int k = 0; k < 3; ++k) {
+        v[8 + k] = src[OVERLAP_WORD + 32 * k + lane];
     }
 #pragma unroll
-    for (int i = lane; i < 96; i += 32) {
-        ov[i] = g[OVERLAP_WORD + i];
+    for (int k = 0; k < 8; ++k) {
+        dst[UW_WORD + 32 * k + lane] = v[k];
     }
-    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        dst[OVERLAP_WORD + 32 * k + lane] = v[8 + k];
+    }
 }
 
 __device__ __forceinline__ void bulk_zero(uint32_t* g, int lane) {
@@ -98,28 +94,29 @@ __device__ __forceinline__ void bulk_zero(uint32_t* g, int lane) {
     }
 }
 
-// HBM homes of the stream's three structs
+// HBM homes of the stream's three structs (651-word mbe_parms images) + a scratch image
 struct StreamHome {
     uint32_t* cur;
     uint32_t* prev;
     uint32_t* enh;
+    uint32_t* spill;
 };
 
 __device__ __forceinline__ void prev_from_cur(WarpWS& ws, const StreamHome& h, int lane) {
     copy_small(ws.prev, ws.cur, lane);
-    bulk_store(ws.cur, h.prev, lane);
+    bulk_copy(h.prev, h.cur, lane);
 }
 __device__ __forceinline__ void enh_from_cur(WarpWS& ws, const StreamHome& h, int lane) {
     copy_small(ws.enh, ws.cur, lane);
-    bulk_store(ws.cur, h.enh, lane);
+    bulk_copy(h.enh, h.cur, lane);
 }
 __device__ __forceinline__ void cur_from_prev(WarpWS& ws, const StreamHome& h, int lane) {
     copy_small(ws.cur, ws.prev, lane);
-    bulk_load(ws.cur, h.prev, lane);
+    bulk_copy(h.cur, h.prev, lane);
 }
 __device__ __forceinline__ void cur_from_enh(WarpWS& ws, const StreamHome& h, int lane) {
     copy_small(ws.cur, ws.enh, lane);
-    bulk_load(ws.cur, h.enh, lane);
+    bulk_copy(h.cur, h.enh, lane);
 }
 
 // default model of mbe_initMbeParms / mbe_initAmbeParms_common (head fields + noiseSeed)
@@ -162,11 +159,12 @@ __device__ __forceinline__ void fill_default(Parms* p, float w0, int L, int K, f
     __syncwarp();
 }
 
-__device__ __noinline__ void init_all(WarpWS& ws, uint32_t* gprev, uint32_t* genh, float w0, int L, int K, float mute_thr,
-                                      int lane) {
-    fill_default(&ws.cur, w0, L, K, mute_thr, lane);
+__device__ __noinline__ void init_all(WarpWS& ws, uint32_t* gcur, uint32_t* gprev, uint32_t* genh, float w0, int L, int K,
+                                      float mute_thr, int lane) {
+    fill_default_small(&ws.cur, w0, L, K, mute_thr, lane);
     copy_small(ws.prev, ws.cur, lane);
     copy_small(ws.enh, ws.cur, lane);
+    bulk_zero(gcur, lane);
     bulk_zero(gprev, lane);
     bulk_zero(genh, lane);
 }
@@ -179,7 +177,7 @@ __device__ __forceinline__ void zero_out(WarpWS& ws, int lane) {
 }
 
 // ---- spectral amplitude enhancement (mbelib.c:412-661); returns pre-enhancement Rm0 -------------
-__device__ __forceinline__ float spectral_enhance(Parms& cur, int lane) {
+__device__ __forceinline__ float spectral_enhance(ParmsSmall& cur, int lane) {
     const int L = cur.L;
     if (!bands_ok(L)) {
         return 0.0f;
@@ -251,7 +249,7 @@ __device__ __forceinline__ float spectral_enhance(Parms& cur, int lane) {
 }
 
 // ---- adaptive smoothing, JMBE algorithms #111-116 (mbe_adaptive.c:151-276) -----------------------
-__device__ __forceinline__ void adaptive_smoothing(Parms& cur, const ParmsSmall& prev, int has_rm0, float rm0,
+__device__ __forceinline__ void adaptive_smoothing(ParmsSmall& cur, const ParmsSmall& prev, int has_rm0, float rm0,
                                                    int lane) {
     if (!bands_ok(cur.L) || !bands_ok(prev.L)) {
         return;
@@ -344,19 +342,18 @@ __device__ __noinline__ void comfort_noise(WarpWS& ws, const DevTables* T, int l
 // ---- white noise with overlap (mbe_unvoiced_fft.c:304-341) --------------------------------------
 // noise_peek: the raw samples 1..56 of the frame's buffer (what the phase update reads) come from the
 // overlap of the previous buffer, or are zero on a cold start; nothing is advanced yet.
-__device__ __forceinline__ void noise_peek(WarpWS& ws, int lane) {
-    const Parms& cur = ws.cur;
-    const bool cold = cur.noiseSeed < 0.0f;
+__device__ __forceinline__ void noise_peek(WarpWS& ws, const float* cur_overlap, int lane) {
+    const bool cold = ws.cur.noiseSeed < 0.0f;
     for (int i = lane; i < 57; i += 32) {
-        ws.nz[i] = cold ? 0.0f : cur.noiseOverlap[i];
+        ws.u.nz[i] = cold ? 0.0f : cur_overlap[i];
     }
     __syncwarp();
 }
 
 // make_noise: builds the frame's 256-sample buffer, advances the LCG / overlap state and writes the
-// WINDOWED buffer (noise * W256) straight into the FFT input.
-__device__ __forceinline__ void make_noise(WarpWS& ws, const DevTables* T, const BlockTables* bt, int lane) {
-    Parms& cur = ws.cur;
+// WINDOWED buffer (noise * W256) straight into the FFT input.  cur_overlap = cur_mp->noiseOverlap in HBM.
+__device__ __forceinline__ void make_noise(WarpWS& ws, float* cur_overlap, const DevTables* T, int lane) {
+    ParmsSmall& cur = ws.cur;
     float* A = ws.u.fft.a;
     const float seed = cur.noiseSeed;
     if (seed < 0.0f) {
@@ -364,7 +361,7 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, const DevTables* T, const
             A[i] = 0.0f;  // 0 * window
         }
         for (int i = lane; i < 96; i += 32) {
-            cur.noiseOverlap[i] = 0.0f;
+            cur_overlap[i] = 0.0f;
         }
         const float ns = ws.rng.uv_override ? (float)ws.rng.uv_seed : 3147.0f;
         __syncwarp();
@@ -376,21 +373,25 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, const DevTables* T, const
         return;
     }
     const unsigned st0 = ((unsigned)seed) % 53125u;
+    float ov[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        const int i = 32 * r + lane;
-        A[i] = cur.noiseOverlap[i] * bt->uvwin[i];
+        ov[r] = cur_overlap[32 * r + lane];
     }
-    __syncwarp();
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
         const int i = 32 * c + lane;
         const unsigned st = (T->uvA[i] * st0 + T->uvC[i]) % 53125u;
         const float v = (float)st;
-        A[96 + i] = v * bt->uvwin[96 + i];
+        A[96 + i] = v * T->uvwin[96 + i];
         if (i >= 64) {
-            cur.noiseOverlap[i - 64] = v;  // overlap <- buffer[160..255]
+            cur_overlap[i - 64] = v;  // overlap <- buffer[160..255] (same lane that read element i - 64 above)
         }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int i = 32 * r + lane;
+        A[i] = ov[r] * T->uvwin[i];
     }
     const unsigned stn = (T->uvA[160] * st0 + T->uvC[160]) % 53125u;
     __syncwarp();
@@ -573,9 +574,9 @@ __device__ __noinline__ void rfft256_backward(float* __restrict__ A, float* __re
 // ws.u.fft.a holds the windowed noise on entry; enh_uw = prev_mp_enhanced->previousUw in HBM.  Spectrum is kept in FFTPACK's native layout F[0]=DC,
 // F[2b-1]=Re(b), F[2b]=Im(b), F[255]=Nyquist; the reference's "ordered" layout is only a permutation of
 // it, so no reorder pass is needed.
-__device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, const float* __restrict__ enh_uw,
-                                                   const BlockTables* bt, int lane) {
-    Parms& cur = ws.cur;
+__device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, float* cur_uw, const float* enh_uw,
+                                                   const DevTables* T, const BlockTables* bt, int lane) {
+    ParmsSmall& cur = ws.cur;
     float* A = ws.u.fft.a;
     float* B = ws.u.fft.b;
     float* scale = ws.u.fft.scale;
@@ -634,16 +635,16 @@ __device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, const float* __re
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
         const int n = 32 * c + lane;
-        const float den = bt->wola_den[n];
+        const float den = T->wola_den[n];
         const float ps = (n + 128 < NFFT) ? enh_uw[n + 128] : 0.0f;
         const float cs = (n - 32 >= 0) ? A[n - 32] : 0.0f;
         if (den > 1e-10f) {
-            ws.out[n] += ((bt->wola_wp[n] * ps) + (bt->wola_wc[n] * cs)) / den;
+            ws.out[n] += ((T->wola_wp[n] * ps) + (T->wola_wc[n] * cs)) / den;
         }
     }
     __syncwarp();
     for (int i = lane; i < NFFT; i += 32) {
-        cur.previousUw[i] = A[i];
+        cur_uw[i] = A[i];
     }
     __syncwarp();
 }
@@ -656,7 +657,7 @@ __device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, const float* __re
 // Windowed components whose gain is exactly zero (the faded bands of mbelib.c:912-929) are dropped:
 // their contribution is +-0 and x + (+-0) == x for every accumulator value that can occur.
 __device__ __forceinline__ void build_components(WarpWS& ws, int maxl, int lane) {
-    const Parms& cur = ws.cur;
+    const ParmsSmall& cur = ws.cur;
     const ParmsSmall& prev = ws.enh;
     const float cw0 = cur.w0, pw0 = prev.w0;
     const bool stable = fabsf(cw0 - pw0) < (0.1f * cw0);
@@ -693,12 +694,10 @@ __device__ __forceinline__ void build_components(WarpWS& ws, int maxl, int lane)
         }
         if (first) {
             ws.comp[idx] = (unsigned char)((l << 2) | (interp ? 2 : 0));
-            ws.gain[idx] = 2.0f * prev.Ml[l];
             idx++;
         }
         if (second) {
             ws.comp[idx] = (unsigned char)((l << 2) | 1);
-            ws.gain[idx] = 2.0f * cur.Ml[l];
         }
         ncomp += __popc(mf) + __popc(ms);
     }
@@ -752,11 +751,11 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
             }
         }
         if (lane <= W) {
-            me.off[lane] = incl - padded;  // lane W: total
+            me.off[lane] = (unsigned short)(incl - padded);  // lane W: total
         }
         __syncwarp();
     }
-    const int* off = me.off;
+    const unsigned short* off = me.off;
     const int total = off[W];
     if (total == 0) {
         return;
@@ -791,12 +790,13 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
                 if ((id & 3) == 0) {
                     step = o.enh.w0 * (float)l;
                     ph = o.enh.PHIl[l];
+                    g = 2.0f * o.enh.Ml[l];
                     Wb = bt->voiced_win + NS;
                 } else {
                     step = o.cur.w0 * (float)l;
                     ph = o.cur.PHIl[l] - (step * (float)NS);
+                    g = 2.0f * o.cur.Ml[l];
                 }
-                g = o.gain[j];
                 const float2 d = dev_sincosf(step);
                 const float2 p = dev_sincosf(ph);
                 sd = d.x;
@@ -922,8 +922,9 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
 // cur = ws.cur, prev = ws.enh; the 160 float samples end up in ws.out.
 // synth_begin: everything up to the component list.  Returns 1 when the frame continues through
 // voiced_bank_block + synth_finish, 0 when it is already complete (silence or comfort noise).
-__device__ __noinline__ int synth_begin(WarpWS& ws, const DevTables* T, int has_rm0, float rm0, int lane) {
-    Parms& cur = ws.cur;
+__device__ __noinline__ int synth_begin(WarpWS& ws, const float* cur_overlap, const DevTables* T, int has_rm0,
+                                        float rm0, int lane) {
+    ParmsSmall& cur = ws.cur;
     ParmsSmall& prev = ws.enh;
     zero_out(ws, lane);
     if (!bands_ok(cur.L) || !bands_ok(prev.L)) {
@@ -938,7 +939,7 @@ __device__ __noinline__ int synth_begin(WarpWS& ws, const DevTables* T, int has_
         __syncwarp();
         return 0;
     }
-    noise_peek(ws, lane);
+    noise_peek(ws, cur_overlap, lane);
 
     // bands present in only one frame fade as zero-amplitude voiced bands (mbelib.c:912-929)
     int maxl;
@@ -984,7 +985,7 @@ __device__ __noinline__ int synth_begin(WarpWS& ws, const DevTables* T, int has_
             if (l <= (cL / 4)) {
                 cur.PHIl[l] = psi;
             } else {
-                const float pl = ((2.0f * MBE_PI_F / 53125.0f) * ws.nz[l]) - MBE_PI_F;
+                const float pl = ((2.0f * MBE_PI_F / 53125.0f) * ws.u.nz[l]) - MBE_PI_F;
                 cur.PHIl[l] = psi + (((float)numUv * pl) / (float)cL);
             }
         }
@@ -995,10 +996,11 @@ __device__ __noinline__ int synth_begin(WarpWS& ws, const DevTables* T, int has_
 }
 
 // synth_finish: unvoiced FFT/WOLA synthesis on top of the voiced samples, then the soft clip.
-__device__ __noinline__ void synth_finish(WarpWS& ws, const float* __restrict__ enh_uw, const DevTables* T,
+__device__ __noinline__ void synth_finish(WarpWS& ws, uint32_t* cur_home, const uint32_t* enh_home, const DevTables* T,
                                           const BlockTables* bt, int lane) {
-    make_noise(ws, T, bt, lane);
-    unvoiced_synthesis(ws, enh_uw, bt, lane);
+    make_noise(ws, reinterpret_cast<float*>(cur_home + OVERLAP_WORD), T, lane);
+    unvoiced_synthesis(ws, reinterpret_cast<float*>(cur_home + UW_WORD), reinterpret_cast<const float*>(enh_home + UW_WORD), T,
+                       bt, lane);
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
         float v = ws.out[32 * c + lane];
@@ -1055,7 +1057,7 @@ __device__ __forceinline__ float tone_sample(unsigned phase) {
 }
 
 __device__ __noinline__ void render_tone(WarpWS& ws, float f1, float f2, int amp, int lane) {
-    Parms& cur = ws.cur;
+    ParmsSmall& cur = ws.cur;
     if (f1 <= 0.0f) {
         zero_out(ws, lane);
         __syncwarp();
