@@ -386,6 +386,12 @@ __device__ __forceinline__ void load_block_tables(BlockTables* bt, const DevTabl
     }
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         bt->tw[i] = T->tw[i];
+        bt->uvwin[i] = T->uvwin[i];
+    }
+    for (int i = threadIdx.x; i < 160; i += blockDim.x) {
+        bt->wola_wp[i] = T->wola_wp[i];
+        bt->wola_wc[i] = T->wola_wc[i];
+        bt->wola_den[i] = T->wola_den[i];
     }
     __syncthreads();
 }

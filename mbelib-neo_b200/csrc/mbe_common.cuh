@@ -148,16 +148,18 @@ constexpr int TILE_STRIDE = 36;   // floats per sample row of the oscillator til
 struct __align__(16) BlockTables {
     float voiced_win[324];   // 321-pt voiced window Ws (mbelib_const.h), 16-byte aligned rows for LDS.128
     float tw[256];           // FFTPACK twiddles
+    float uvwin[256];        // unvoiced analysis window, centred at 128
+    float wola_wp[160], wola_wc[160], wola_den[160];
 };
 
 // Streams (= warps) per block.  The block walks its streams' frames in lockstep: per frame every warp
 // decodes its own stream, then the block pools the oscillator components of all its streams and
 // spreads them evenly over all lanes (voiced_bank_block), then every warp finishes its own stream.
 #ifndef MBE_WPB
-#define MBE_WPB 8
+#define MBE_WPB 12
 #endif
 #ifndef MBE_MINB
-#define MBE_MINB 3
+#define MBE_MINB 2
 #endif
 constexpr int WARPS_PER_BLOCK = MBE_WPB;
 constexpr int MIN_BLOCKS_PER_SM = MBE_MINB;

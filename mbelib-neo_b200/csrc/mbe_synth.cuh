@@ -352,7 +352,8 @@ __device__ __forceinline__ void noise_peek(WarpWS& ws, const float* cur_overlap,
 
 // make_noise: builds the frame's 256-sample buffer, advances the LCG / overlap state and writes the
 // WINDOWED buffer (noise * W256) straight into the FFT input.  cur_overlap = cur_mp->noiseOverlap in HBM.
-__device__ __forceinline__ void make_noise(WarpWS& ws, float* cur_overlap, const DevTables* T, int lane) {
+__device__ __forceinline__ void make_noise(WarpWS& ws, float* cur_overlap, const DevTables* T, const BlockTables* bt,
+                                           int lane) {
     ParmsSmall& cur = ws.cur;
     float* A = ws.u.fft.a;
     const float seed = cur.noiseSeed;
@@ -383,7 +384,7 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, float* cur_overlap, const
         const int i = 32 * c + lane;
         const unsigned st = (T->uvA[i] * st0 + T->uvC[i]) % 53125u;
         const float v = (float)st;
-        A[96 + i] = v * T->uvwin[96 + i];
+        A[96 + i] = v * bt->uvwin[96 + i];
         if (i >= 64) {
             cur_overlap[i - 64] = v;  // overlap <- buffer[160..255] (same lane that read element i - 64 above)
         }
@@ -391,7 +392,7 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, float* cur_overlap, const
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const int i = 32 * r + lane;
-        A[i] = ov[r] * T->uvwin[i];
+        A[i] = ov[r] * bt->uvwin[i];
     }
     const unsigned stn = (T->uvA[160] * st0 + T->uvC[160]) % 53125u;
     __syncwarp();
@@ -635,11 +636,11 @@ __device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, float* cur_uw, co
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
         const int n = 32 * c + lane;
-        const float den = T->wola_den[n];
+        const float den = bt->wola_den[n];
         const float ps = (n + 128 < NFFT) ? enh_uw[n + 128] : 0.0f;
         const float cs = (n - 32 >= 0) ? A[n - 32] : 0.0f;
         if (den > 1e-10f) {
-            ws.out[n] += ((T->wola_wp[n] * ps) + (T->wola_wc[n] * cs)) / den;
+            ws.out[n] += ((bt->wola_wp[n] * ps) + (bt->wola_wc[n] * cs)) / den;
         }
     }
     __syncwarp();
@@ -744,7 +745,7 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
         const int padded = (lane < W) ? ((bs->cnt[lane] + 3) & ~3) : 0;
         int incl = padded;
 #pragma unroll
-        for (int d = 1; d < 16; d <<= 1) {
+        for (int d = 1; d < 32; d <<= 1) {
             const int up = __shfl_up_sync(FULL, incl, d);
             if (lane >= d) {
                 incl += up;
@@ -998,7 +999,7 @@ __device__ __noinline__ int synth_begin(WarpWS& ws, const float* cur_overlap, co
 // synth_finish: unvoiced FFT/WOLA synthesis on top of the voiced samples, then the soft clip.
 __device__ __noinline__ void synth_finish(WarpWS& ws, uint32_t* cur_home, const uint32_t* enh_home, const DevTables* T,
                                           const BlockTables* bt, int lane) {
-    make_noise(ws, reinterpret_cast<float*>(cur_home + OVERLAP_WORD), T, lane);
+    make_noise(ws, reinterpret_cast<float*>(cur_home + OVERLAP_WORD), T, bt, lane);
     unvoiced_synthesis(ws, reinterpret_cast<float*>(cur_home + UW_WORD), reinterpret_cast<const float*>(enh_home + UW_WORD), T,
                        bt, lane);
 #pragma unroll
