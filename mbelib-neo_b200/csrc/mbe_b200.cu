@@ -397,6 +397,9 @@ __device__ __forceinline__ void load_block_tables(BlockTables* bt, const DevTabl
 }
 
 __device__ __forceinline__ void store_pcm(const LaunchArgs& A, const WarpWS& ws, size_t frame_idx, int lane) {
+    if (MBE_ABL & 256) {
+        return;
+    }
 #pragma unroll
     for (int ch = 0; ch < 5; ++ch) {
         const size_t o = frame_idx * NS + 32 * ch + lane;

@@ -177,8 +177,8 @@ struct __align__(16) WarpWS {
     union __align__(16) {
         float tile[32 * TILE_STRIDE];     // voiced bank: [sample][component], pre-weighted contributions
         struct {
-            float a[NFFT];                // FFT ping buffer (windowed noise on entry)
-            float b[NFFT];                // FFT pong buffer
+            float a[324];                 // FFT ping buffer (windowed noise on entry); 324: padded pass layouts
+            float b[324];                 // FFT pong buffer
             float scale[132];             // per-bin unvoiced band scale
         } fft;
         struct {                          // front-end / parameter decode scratch (dead before synthesis starts)

@@ -22,6 +22,10 @@ namespace mbe {
 #endif
 constexpr int kOscUnroll = MBE_OSC_UNROLL;  // oscillator steps per loop body = 4 * kOscUnroll
 #define MBE_PI_F 3.14159274101257324f /* (float)M_PI */
+// MBE_ABL: timing-only ablation mask for experimental builds (results are wrong when non-zero)
+#ifndef MBE_ABL
+#define MBE_ABL 0
+#endif
 #define MBE_CLIP_F ((32767.0f * 0.95f) / 7.0f)
 
 // The glibc-exact transcendental ports are large (double-precision kernels + Payne-Hanek style
@@ -64,6 +68,9 @@ __device__ __forceinline__ void copy_small(D& dst, const S& src, int lane) {
 // lane in flight, then 11 stores)
 // (plain pointers: these words are written by this kernel too, so they must not go through the read-only path)
 __device__ __forceinline__ void bulk_copy(uint32_t* dst, const uint32_t* src, int lane) {
+    if (MBE_ABL & 64) {
+        return;
+    }
     uint32_t v[11];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -183,6 +190,9 @@ __device__ __forceinline__ float spectral_enhance(ParmsSmall& cur, int lane) {
         return 0.0f;
     }
     const float w0 = cur.w0;
+    if (MBE_ABL & 32) {
+        return 1000.0f;
+    }
     const float2 sc = dev_sincosf(w0);
     const float ss = sc.x, cs = sc.y;
     // serial: cos(l*w0) by rotation, Rm0 = sum M^2, Rm1 = sum M^2 cos, all in harmonic order
@@ -402,179 +412,320 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, float* cur_overlap, const
     __syncwarp();
 }
 
-// ---- 256-point real FFT: FFTPACK radix-4 passes, lanes over butterflies -------------------------
-// One pass template each way, instantiated for the four (ido, l1) shapes of N = 256 so that all index
-// arithmetic folds into immediates.  `w` points at the pass's first twiddle row; rows two and three
-// follow at +ido and +2*ido.
-template <int ido, int l1>
-__device__ __forceinline__ void rfft_fwd_pass(const float* __restrict__ in, float* __restrict__ out,
-                                              const float* __restrict__ w, int lane) {
-#define FIN(i, k, j)  in[(i) + ido * ((k) + l1 * (j))]
-#define FOUT(i, j, k) out[(i) + ido * ((j) + 4 * (k))]
+// ---- 256-point real FFT: FFTPACK radix-4 passes (pffft.c:749-926), lanes over butterflies ---------
+// Arithmetic (operation order inside every butterfly) is FFTPACK's radf4 / radb4; only the placement of the
+// intermediate arrays in shared memory is ours.  The (re, im) pairs (i-1, i) that the ido > 1 butterflies
+// read and write are kept 8-byte aligned by shifting those arrays one word, so they move as LDS.64 / STS.64
+// and every pass touches shared memory (nearly) conflict-free:
+//   X0  time samples, natural order                         phys = p
+//   X1  after the ido=1 pass:  [4k + j]                      phys = p                (STS.128 / LDS.128 per k)
+//   X2  after the ido=4 pass:  [i + 4j + 16k]  row k, col c  phys = 20*k + c + 1     (rows padded to 20 words)
+//   X3  after the ido=16 pass: [i + 16j + 64k] row k, col c  phys = 80*k + c + 1     (rows padded to 80 words)
+//   X4  spectrum, FFTPACK order [DC, Re1, Im1, ..., Nyq]     phys = p + 1            (Re_b, Im_b at 2b, 2b+1)
+// The backward passes walk the same layouts in reverse.  A and B are the two 324-word ping-pong buffers.
+constexpr int X2S = 20, X3S = 80;
+
+struct Cpx { float re, im; };
+__device__ __forceinline__ Cpx ld2(const float* p) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    Cpx c = {v.x, v.y};
+    return c;
+}
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+
+// radf4 inner butterfly for one (i-1, i) pair (pffft.c radf4_ps, the i-loop): x0..x3 = inputs j = 0..3,
+// w1..w3 = (wa[i-2], wa[i-1]).  Outputs: o0 = (i-1, i) of output row 0, o2 = (i-1, i) of row 2,
+// m3 = (ic-1, ic) of row 3, m1 = (ic-1, ic) of row 1.
+__device__ __forceinline__ void radf4_pair(Cpx x0, Cpx x1, Cpx x2, Cpx x3, Cpx w1, Cpx w2, Cpx w3, Cpx& o0, Cpx& m1, Cpx& o2,
+                                           Cpx& m3) {
+    float cr2 = x1.re, ci2 = x1.im, cr3 = x2.re, ci3 = x2.im, cr4 = x3.re, ci4 = x3.im;
+    float t;
+    t = cr2 * w1.im;
+    cr2 = (cr2 * w1.re) + (ci2 * w1.im);
+    ci2 = (ci2 * w1.re) - t;
+    t = cr3 * w2.im;
+    cr3 = (cr3 * w2.re) + (ci3 * w2.im);
+    ci3 = (ci3 * w2.re) - t;
+    t = cr4 * w3.im;
+    cr4 = (cr4 * w3.re) + (ci4 * w3.im);
+    ci4 = (ci4 * w3.re) - t;
+    const float tr1 = cr2 + cr4, tr4 = cr4 - cr2;
+    const float tr2 = x0.re + cr3, tr3 = x0.re - cr3;
+    const float ti1 = ci2 + ci4, ti4 = ci2 - ci4;
+    const float ti2 = x0.im + ci3, ti3 = x0.im - ci3;
+    o0.re = tr1 + tr2;
+    m3.re = tr2 - tr1;
+    o2.re = ti4 + tr3;
+    m1.re = tr3 - ti4;
+    o0.im = ti1 + ti2;
+    m3.im = ti1 - ti2;
+    o2.im = tr4 + ti3;
+    m1.im = tr4 - ti3;
+}
+// radf4, i = 0 column: a0..a3 = inputs j = 0..3 -> (0,0) (ido-1,1) (0,2) (ido-1,3)
+__device__ __forceinline__ void radf4_first(float a0, float a1, float a2, float a3, float& o00, float& oL1, float& o02,
+                                            float& oL3) {
+    const float tr1 = a1 + a3;
+    const float tr2 = a0 + a2;
+    oL1 = a0 - a2;
+    o02 = a3 - a1;
+    o00 = tr1 + tr2;
+    oL3 = tr2 - tr1;
+}
+// radf4, i = ido-1 column: inputs j = 0..3 -> (ido-1,0) (0,1) (ido-1,2) (0,3)
+__device__ __forceinline__ void radf4_last(float c, float a, float d, float b, float& oL0, float& o01, float& oL2,
+                                           float& o03) {
     const float nhs2 = -0.70710678118654752440f;
-    const float* w1 = w;
-    const float* w2 = w + ido;
-    const float* w3 = w + 2 * ido;
-    for (int k = lane; k < l1; k += 32) {
-        float a0 = FIN(0, k, 0), a1 = FIN(0, k, 1), a2 = FIN(0, k, 2), a3 = FIN(0, k, 3);
-        float tr1 = a1 + a3;
-        float tr2 = a0 + a2;
-        FOUT(ido - 1, 1, k) = a0 - a2;
-        FOUT(0, 2, k) = a3 - a1;
-        FOUT(0, 0, k) = tr1 + tr2;
-        FOUT(ido - 1, 3, k) = tr2 - tr1;
-    }
-    if (ido >= 2) {
-        constexpr int ni = (ido / 2 - 1) > 0 ? (ido / 2 - 1) : 1;
-        const int it = lane;  // l1 * ni <= 31 for every pass of N = 256
-        if (it < l1 * (ido / 2 - 1)) {
-            const int k = it / ni;  // compile-time divisor
-            const int i = 2 + 2 * (it - k * ni);
-            const int ic = ido - i;
-            float cr2 = FIN(i - 1, k, 1), ci2 = FIN(i, k, 1);
-            float cr3 = FIN(i - 1, k, 2), ci3 = FIN(i, k, 2);
-            float cr4 = FIN(i - 1, k, 3), ci4 = FIN(i, k, 3);
-            float t;
-            t = cr2 * w1[i - 1];
-            cr2 = (cr2 * w1[i - 2]) + (ci2 * w1[i - 1]);
-            ci2 = (ci2 * w1[i - 2]) - t;
-            t = cr3 * w2[i - 1];
-            cr3 = (cr3 * w2[i - 2]) + (ci3 * w2[i - 1]);
-            ci3 = (ci3 * w2[i - 2]) - t;
-            t = cr4 * w3[i - 1];
-            cr4 = (cr4 * w3[i - 2]) + (ci4 * w3[i - 1]);
-            ci4 = (ci4 * w3[i - 2]) - t;
-            const float x0r = FIN(i - 1, k, 0), x0i = FIN(i, k, 0);
-            const float tr1 = cr2 + cr4, tr4 = cr4 - cr2;
-            const float tr2 = x0r + cr3, tr3 = x0r - cr3;
-            FOUT(i - 1, 0, k) = tr1 + tr2;
-            FOUT(ic - 1, 3, k) = tr2 - tr1;
-            const float ti1 = ci2 + ci4, ti4 = ci2 - ci4;
-            FOUT(i - 1, 2, k) = ti4 + tr3;
-            FOUT(ic - 1, 1, k) = tr3 - ti4;
-            const float ti2 = x0i + ci3, ti3 = x0i - ci3;
-            FOUT(i, 0, k) = ti1 + ti2;
-            FOUT(ic, 3, k) = ti1 - ti2;
-            FOUT(i, 2, k) = tr4 + ti3;
-            FOUT(ic, 1, k) = tr4 - ti3;
-        }
-        if (lane < l1) {
-            const int k = lane;
-            float a = FIN(ido - 1, k, 1), b = FIN(ido - 1, k, 3);
-            float c = FIN(ido - 1, k, 0), d = FIN(ido - 1, k, 2);
-            float ti1 = nhs2 * (a + b);
-            float tr1 = nhs2 * (b - a);
-            FOUT(ido - 1, 0, k) = tr1 + c;
-            FOUT(ido - 1, 2, k) = c - tr1;
-            FOUT(0, 1, k) = ti1 - d;
-            FOUT(0, 3, k) = ti1 + d;
-        }
-    }
-    __syncwarp();
-#undef FIN
-#undef FOUT
+    const float ti1 = nhs2 * (a + b);
+    const float tr1 = nhs2 * (b - a);
+    oL0 = tr1 + c;
+    oL2 = c - tr1;
+    o01 = ti1 - d;
+    o03 = ti1 + d;
 }
 
-template <int ido, int l1>
-__device__ __forceinline__ void rfft_bwd_pass(const float* __restrict__ in, float* __restrict__ out,
-                                              const float* __restrict__ w, int lane) {
-#define BIN(i, j, k)  in[(i) + ido * ((j) + 4 * (k))]
-#define BOUT(i, k, j) out[(i) + ido * ((k) + l1 * (j))]
+// radb4 inner butterfly: p0 = (i-1, i) of input row 0, p2 = of row 2, q3 = (ic-1, ic) of row 3, q1 = of row 1;
+// outputs y0..y3 = (i-1, i) of output j = 0..3
+__device__ __forceinline__ void radb4_pair(Cpx p0, Cpx q1, Cpx p2, Cpx q3, Cpx w1, Cpx w2, Cpx w3, Cpx& y0, Cpx& y1, Cpx& y2,
+                                           Cpx& y3) {
+    const float tr1 = p0.re - q3.re;
+    const float tr2 = p0.re + q3.re;
+    const float ti4 = p2.re - q1.re;
+    const float tr3 = p2.re + q1.re;
+    y0.re = tr2 + tr3;
+    float cr3 = tr2 - tr3;
+    const float ti3 = p2.im - q1.im;
+    const float tr4 = p2.im + q1.im;
+    float cr2 = tr1 - tr4;
+    float cr4 = tr1 + tr4;
+    const float ti1 = p0.im + q3.im;
+    const float ti2 = p0.im - q3.im;
+    y0.im = ti2 + ti3;
+    float ci3 = ti2 - ti3;
+    float ci2 = ti1 + ti4;
+    float ci4 = ti1 - ti4;
+    float t;
+    t = cr2 * w1.im;
+    y1.re = (cr2 * w1.re) - (ci2 * w1.im);
+    y1.im = (ci2 * w1.re) + t;
+    t = cr3 * w2.im;
+    y2.re = (cr3 * w2.re) - (ci3 * w2.im);
+    y2.im = (ci3 * w2.re) + t;
+    t = cr4 * w3.im;
+    y3.re = (cr4 * w3.re) - (ci4 * w3.im);
+    y3.im = (ci4 * w3.re) + t;
+}
+// radb4, i = 0 column: a = (0,0) d = (ido-1,1) c = (0,2) b = (ido-1,3) -> outputs j = 0..3
+__device__ __forceinline__ void radb4_first(float a, float d, float c, float b, float& y0, float& y1, float& y2, float& y3) {
+    const float tr3 = 2.f * d;
+    const float tr2 = a + b;
+    const float tr1 = a - b;
+    const float tr4 = 2.f * c;
+    y0 = tr2 + tr3;
+    y2 = tr2 - tr3;
+    y1 = tr1 - tr4;
+    y3 = tr1 + tr4;
+}
+// radb4, i = ido-1 column: c = (ido-1,0) a = (0,1) d = (ido-1,2) b = (0,3) -> outputs j = 0..3
+__device__ __forceinline__ void radb4_last(float c, float a, float d, float b, float& y0, float& y1, float& y2, float& y3) {
     const float nsq2 = -1.41421356237309504880f;
-    const float* w1 = w;
-    const float* w2 = w + ido;
-    const float* w3 = w + 2 * ido;
-    for (int k = lane; k < l1; k += 32) {
-        float a = BIN(0, 0, k), b = BIN(ido - 1, 3, k), c = BIN(0, 2, k), d = BIN(ido - 1, 1, k);
-        float tr3 = 2.f * d;
-        float tr2 = a + b;
-        float tr1 = a - b;
-        float tr4 = 2.f * c;
-        BOUT(0, k, 0) = tr2 + tr3;
-        BOUT(0, k, 2) = tr2 - tr3;
-        BOUT(0, k, 1) = tr1 - tr4;
-        BOUT(0, k, 3) = tr1 + tr4;
-    }
-    if (ido >= 2) {
-        constexpr int ni = (ido / 2 - 1) > 0 ? (ido / 2 - 1) : 1;
-        const int it = lane;
-        if (it < l1 * (ido / 2 - 1)) {
-            const int k = it / ni;  // compile-time divisor
-            const int i = 2 + 2 * (it - k * ni);
-            const int ic = ido - i;
-            float tr1 = BIN(i - 1, 0, k) - BIN(ic - 1, 3, k);
-            float tr2 = BIN(i - 1, 0, k) + BIN(ic - 1, 3, k);
-            float ti4 = BIN(i - 1, 2, k) - BIN(ic - 1, 1, k);
-            float tr3 = BIN(i - 1, 2, k) + BIN(ic - 1, 1, k);
-            BOUT(i - 1, k, 0) = tr2 + tr3;
-            float cr3 = tr2 - tr3;
-            float ti3 = BIN(i, 2, k) - BIN(ic, 1, k);
-            float tr4 = BIN(i, 2, k) + BIN(ic, 1, k);
-            float cr2 = tr1 - tr4;
-            float cr4 = tr1 + tr4;
-            float ti1 = BIN(i, 0, k) + BIN(ic, 3, k);
-            float ti2 = BIN(i, 0, k) - BIN(ic, 3, k);
-            BOUT(i, k, 0) = ti2 + ti3;
-            float ci3 = ti2 - ti3;
-            float ci2 = ti1 + ti4;
-            float ci4 = ti1 - ti4;
-            float t;
-            t = cr2 * w1[i - 1];
-            cr2 = (cr2 * w1[i - 2]) - (ci2 * w1[i - 1]);
-            ci2 = (ci2 * w1[i - 2]) + t;
-            BOUT(i - 1, k, 1) = cr2;
-            BOUT(i, k, 1) = ci2;
-            t = cr3 * w2[i - 1];
-            cr3 = (cr3 * w2[i - 2]) - (ci3 * w2[i - 1]);
-            ci3 = (ci3 * w2[i - 2]) + t;
-            BOUT(i - 1, k, 2) = cr3;
-            BOUT(i, k, 2) = ci3;
-            t = cr4 * w3[i - 1];
-            cr4 = (cr4 * w3[i - 2]) - (ci4 * w3[i - 1]);
-            ci4 = (ci4 * w3[i - 2]) + t;
-            BOUT(i - 1, k, 3) = cr4;
-            BOUT(i, k, 3) = ci4;
-        }
-        if (lane < l1) {
-            const int k = lane;
-            float c = BIN(ido - 1, 0, k), d = BIN(ido - 1, 2, k);
-            float a = BIN(0, 1, k), b = BIN(0, 3, k);
-            float tr1 = c - d;
-            float tr2 = c + d;
-            float ti1 = b + a;
-            float ti2 = b - a;
-            BOUT(ido - 1, k, 0) = tr2 + tr2;
-            BOUT(ido - 1, k, 1) = nsq2 * (ti1 - tr1);
-            BOUT(ido - 1, k, 2) = ti2 + ti2;
-            BOUT(ido - 1, k, 3) = nsq2 * (ti1 + tr1);
-        }
-    }
-    __syncwarp();
-#undef BIN
-#undef BOUT
+    const float tr1 = c - d;
+    const float tr2 = c + d;
+    const float ti1 = b + a;
+    const float ti2 = b - a;
+    y0 = tr2 + tr2;
+    y1 = nsq2 * (ti1 - tr1);
+    y2 = ti2 + ti2;
+    y3 = nsq2 * (ti1 + tr1);
 }
 
-// the two 256-point transforms: four radix-4 passes each, ping-ponging between A and B; result in A
+// forward transform: A = X0 on entry, A = X4 on exit (B scratch).  tw = FFTPACK twiddle table:
+// ido=64 rows at 0/64/128, ido=16 rows at 192/208/224, ido=4 rows at 240/244/248.
 __device__ __noinline__ void rfft256_forward(float* __restrict__ A, float* __restrict__ B, const float* __restrict__ tw,
                                              int lane) {
-    rfft_fwd_pass<1, 64>(A, B, tw + 252, lane);
-    rfft_fwd_pass<4, 16>(B, A, tw + 240, lane);
-    rfft_fwd_pass<16, 4>(A, B, tw + 192, lane);
-    rfft_fwd_pass<64, 1>(B, A, tw + 0, lane);
+    // ---- ido = 1, l1 = 64: X0 -> X1
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        float4 o;
+        radf4_first(A[k], A[k + 64], A[k + 128], A[k + 192], o.x, o.y, o.z, o.w);
+        *reinterpret_cast<float4*>(B + 4 * k) = o;
+    }
+    __syncwarp();
+    // ---- ido = 4, l1 = 16: X1 -> X2, lane = k owns row k
+    if (lane < 16) {
+        const float4 v0 = *reinterpret_cast<const float4*>(B + 4 * lane);
+        const float4 v1 = *reinterpret_cast<const float4*>(B + 4 * lane + 64);
+        const float4 v2 = *reinterpret_cast<const float4*>(B + 4 * lane + 128);
+        const float4 v3 = *reinterpret_cast<const float4*>(B + 4 * lane + 192);
+        float c0, c7, c8, c15, c3, c4, c11, c12;
+        radf4_first(v0.x, v1.x, v2.x, v3.x, c0, c7, c8, c15);
+        radf4_last(v0.w, v1.w, v2.w, v3.w, c3, c4, c11, c12);
+        Cpx o0, m1, o2, m3;
+        const Cpx x0 = {v0.y, v0.z}, x1 = {v1.y, v1.z}, x2 = {v2.y, v2.z}, x3 = {v3.y, v3.z};
+        radf4_pair(x0, x1, x2, x3, ld2(tw + 240), ld2(tw + 244), ld2(tw + 248), o0, m1, o2, m3);
+        float* row = A + X2S * lane;
+        row[1] = c0;
+        st2(row + 2, o0.re, o0.im);
+        *reinterpret_cast<float4*>(row + 4) = make_float4(c3, c4, m1.re, m1.im);
+        *reinterpret_cast<float4*>(row + 8) = make_float4(c7, c8, o2.re, o2.im);
+        *reinterpret_cast<float4*>(row + 12) = make_float4(c11, c12, m3.re, m3.im);
+        row[16] = c15;
+    }
+    __syncwarp();
+    // ---- ido = 16, l1 = 4: X2 -> X3, lane = 8k + q: q >= 1 pair (2q-1, 2q), q == 0 the two edge columns
+    {
+        const int k = lane >> 3, q = lane & 7;
+        const float* in = A + X2S * k;     // rows k + 4j
+        float* out = B + X3S * k;
+        if (q) {
+            Cpx o0, m1, o2, m3;
+            radf4_pair(ld2(in + 2 * q), ld2(in + 4 * X2S + 2 * q), ld2(in + 8 * X2S + 2 * q), ld2(in + 12 * X2S + 2 * q),
+                       ld2(tw + 190 + 2 * q), ld2(tw + 206 + 2 * q), ld2(tw + 222 + 2 * q), o0, m1, o2, m3);
+            st2(out + 2 * q, o0.re, o0.im);
+            st2(out + 32 - 2 * q, m1.re, m1.im);
+            st2(out + 32 + 2 * q, o2.re, o2.im);
+            st2(out + 64 - 2 * q, m3.re, m3.im);
+        } else {
+            float o00, oL1, o02, oL3, oL0, o01, oL2, o03;
+            radf4_first(in[1], in[4 * X2S + 1], in[8 * X2S + 1], in[12 * X2S + 1], o00, oL1, o02, oL3);
+            radf4_last(in[16], in[4 * X2S + 16], in[8 * X2S + 16], in[12 * X2S + 16], oL0, o01, oL2, o03);
+            out[1] = o00;
+            st2(out + 16, oL0, o01);
+            st2(out + 32, oL1, o02);
+            st2(out + 48, oL2, o03);
+            out[64] = oL3;
+        }
+    }
+    __syncwarp();
+    // ---- ido = 64, l1 = 1: X3 -> X4, lane p >= 1 pair (2p-1, 2p), lane 0 the two edge columns
+    if (lane) {
+        const int p2 = 2 * lane;
+        Cpx o0, m1, o2, m3;
+        radf4_pair(ld2(B + p2), ld2(B + X3S + p2), ld2(B + 2 * X3S + p2), ld2(B + 3 * X3S + p2), ld2(tw + p2 - 2),
+                   ld2(tw + 62 + p2), ld2(tw + 126 + p2), o0, m1, o2, m3);
+        st2(A + p2, o0.re, o0.im);
+        st2(A + 128 - p2, m1.re, m1.im);
+        st2(A + 128 + p2, o2.re, o2.im);
+        st2(A + 256 - p2, m3.re, m3.im);
+    } else {
+        float o00, oL1, o02, oL3, oL0, o01, oL2, o03;
+        radf4_first(B[1], B[X3S + 1], B[2 * X3S + 1], B[3 * X3S + 1], o00, oL1, o02, oL3);
+        radf4_last(B[64], B[X3S + 64], B[2 * X3S + 64], B[3 * X3S + 64], oL0, o01, oL2, o03);
+        A[1] = o00;
+        st2(A + 64, oL0, o01);
+        st2(A + 128, oL1, o02);
+        st2(A + 192, oL2, o03);
+        A[256] = oL3;
+    }
+    __syncwarp();
 }
 
+// backward transform: A = X4 on entry (unscaled spectrum; every bin is multiplied by scale[bin] as it is
+// loaded, mbe_unvoiced_fft.c:688-712), A = X0 on exit (B scratch)
 __device__ __noinline__ void rfft256_backward(float* __restrict__ A, float* __restrict__ B, const float* __restrict__ tw,
-                                              int lane) {
-    rfft_bwd_pass<64, 1>(A, B, tw + 0, lane);
-    rfft_bwd_pass<16, 4>(B, A, tw + 192, lane);
-    rfft_bwd_pass<4, 16>(A, B, tw + 240, lane);
-    rfft_bwd_pass<1, 64>(B, A, tw + 252, lane);
+                                              const float* __restrict__ scale, int lane) {
+    // ---- ido = 64: X4 -> X3
+    if (lane) {
+        const int p2 = 2 * lane;
+        Cpx p0 = ld2(A + p2), q1 = ld2(A + 128 - p2), pp2 = ld2(A + 128 + p2), q3 = ld2(A + 256 - p2);
+        const float s0 = scale[lane], s1 = scale[64 - lane], s2 = scale[64 + lane], s3 = scale[128 - lane];
+        p0.re *= s0;
+        p0.im *= s0;
+        q1.re *= s1;
+        q1.im *= s1;
+        pp2.re *= s2;
+        pp2.im *= s2;
+        q3.re *= s3;
+        q3.im *= s3;
+        Cpx y0, y1, y2, y3;
+        radb4_pair(p0, q1, pp2, q3, ld2(tw + p2 - 2), ld2(tw + 62 + p2), ld2(tw + 126 + p2), y0, y1, y2, y3);
+        st2(B + p2, y0.re, y0.im);
+        st2(B + X3S + p2, y1.re, y1.im);
+        st2(B + 2 * X3S + p2, y2.re, y2.im);
+        st2(B + 3 * X3S + p2, y3.re, y3.im);
+    } else {
+        const float s0 = scale[0], s32 = scale[32], s64 = scale[64], s96 = scale[96], s128 = scale[128];
+        float y0, y1, y2, y3;
+        radb4_first(A[1] * s0, A[128] * s64, A[129] * s64, A[256] * s128, y0, y1, y2, y3);
+        B[1] = y0;
+        B[X3S + 1] = y1;
+        B[2 * X3S + 1] = y2;
+        B[3 * X3S + 1] = y3;
+        radb4_last(A[64] * s32, A[65] * s32, A[192] * s96, A[193] * s96, y0, y1, y2, y3);
+        B[64] = y0;
+        B[X3S + 64] = y1;
+        B[2 * X3S + 64] = y2;
+        B[3 * X3S + 64] = y3;
+    }
+    __syncwarp();
+    // ---- ido = 16: X3 -> X2
+    {
+        const int k = lane >> 3, q = lane & 7;
+        const float* in = B + X3S * k;
+        float* out = A + X2S * k;
+        if (q) {
+            Cpx y0, y1, y2, y3;
+            radb4_pair(ld2(in + 2 * q), ld2(in + 32 - 2 * q), ld2(in + 32 + 2 * q), ld2(in + 64 - 2 * q), ld2(tw + 190 + 2 * q),
+                       ld2(tw + 206 + 2 * q), ld2(tw + 222 + 2 * q), y0, y1, y2, y3);
+            st2(out + 2 * q, y0.re, y0.im);
+            st2(out + 4 * X2S + 2 * q, y1.re, y1.im);
+            st2(out + 8 * X2S + 2 * q, y2.re, y2.im);
+            st2(out + 12 * X2S + 2 * q, y3.re, y3.im);
+        } else {
+            float y0, y1, y2, y3;
+            radb4_first(in[1], in[32], in[33], in[64], y0, y1, y2, y3);
+            out[1] = y0;
+            out[4 * X2S + 1] = y1;
+            out[8 * X2S + 1] = y2;
+            out[12 * X2S + 1] = y3;
+            radb4_last(in[16], in[17], in[48], in[49], y0, y1, y2, y3);
+            out[16] = y0;
+            out[4 * X2S + 16] = y1;
+            out[8 * X2S + 16] = y2;
+            out[12 * X2S + 16] = y3;
+        }
+    }
+    __syncwarp();
+    // ---- ido = 4: X2 -> X1, lane = k owns row k
+    if (lane < 16) {
+        const float* row = A + X2S * lane;
+        const float c0 = row[1];
+        const Cpx p0 = ld2(row + 2);
+        const float4 r1 = *reinterpret_cast<const float4*>(row + 4);    // cols 3..6
+        const float4 r2 = *reinterpret_cast<const float4*>(row + 8);    // cols 7..10
+        const float4 r3 = *reinterpret_cast<const float4*>(row + 12);   // cols 11..14
+        const float c15 = row[16];
+        float f0, f1, f2, f3, l0, l1, l2, l3;
+        radb4_first(c0, r2.x, r2.y, c15, f0, f1, f2, f3);
+        radb4_last(r1.x, r1.y, r3.x, r3.y, l0, l1, l2, l3);
+        const Cpx q1 = {r1.z, r1.w}, pp2 = {r2.z, r2.w}, q3 = {r3.z, r3.w};
+        Cpx y0, y1, y2, y3;
+        radb4_pair(p0, q1, pp2, q3, ld2(tw + 240), ld2(tw + 244), ld2(tw + 248), y0, y1, y2, y3);
+        *reinterpret_cast<float4*>(B + 4 * lane) = make_float4(f0, y0.re, y0.im, l0);
+        *reinterpret_cast<float4*>(B + 4 * lane + 64) = make_float4(f1, y1.re, y1.im, l1);
+        *reinterpret_cast<float4*>(B + 4 * lane + 128) = make_float4(f2, y2.re, y2.im, l2);
+        *reinterpret_cast<float4*>(B + 4 * lane + 192) = make_float4(f3, y3.re, y3.im, l3);
+    }
+    __syncwarp();
+    // ---- ido = 1: X1 -> X0
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        const float4 v = *reinterpret_cast<const float4*>(B + 4 * k);
+        float y0, y1, y2, y3;
+        radb4_first(v.x, v.y, v.z, v.w, y0, y1, y2, y3);
+        A[k] = y0;
+        A[k + 64] = y1;
+        A[k + 128] = y2;
+        A[k + 192] = y3;
+    }
+    __syncwarp();
 }
 
 // ---- unvoiced synthesis (mbe_unvoiced_fft.c:714-761); adds into ws.out and writes cur.previousUw --
-// ws.u.fft.a holds the windowed noise on entry; enh_uw = prev_mp_enhanced->previousUw in HBM.  Spectrum is kept in FFTPACK's native layout F[0]=DC,
-// F[2b-1]=Re(b), F[2b]=Im(b), F[255]=Nyquist; the reference's "ordered" layout is only a permutation of
-// it, so no reorder pass is needed.
+// ws.u.fft.a holds the windowed noise on entry; enh_uw = prev_mp_enhanced->previousUw in HBM.  The spectrum
+// stays in FFTPACK's native order (the reference's "ordered" layout is only a permutation of it).
 __device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, float* cur_uw, const float* enh_uw,
                                                    const DevTables* T, const BlockTables* bt, int lane) {
     ParmsSmall& cur = ws.cur;
@@ -585,8 +736,9 @@ __device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, float* cur_uw, co
     for (int i = lane; i < 129; i += 32) {
         scale[i] = 0.0f;
     }
-    __syncwarp();
-    rfft256_forward(A, B, tw, lane);
+    if (!(MBE_ABL & 128)) {
+        rfft256_forward(A, B, tw, lane);   // ends with __syncwarp: scale[] zeros are visible too
+    }
 
     const int L = cur.L;
     const float mult = (256.0f / (2.0f * 3.14159265358979323846f)) * cur.w0;
@@ -603,12 +755,12 @@ __device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, float* cur_uw, co
             float num = 0.0f;
             int s = a;
             if (s == 0) {
-                num += A[0] * A[0];
+                num += A[1] * A[1];
                 s = 1;
             }
             for (int bin = s; bin < b; ++bin) {
-                const float re = A[2 * bin - 1], im = A[2 * bin];
-                num += (re * re) + (im * im);
+                const Cpx v = ld2(A + 2 * bin);
+                num += (v.re * v.re) + (v.im * v.im);
             }
             if (num > 1e-10f) {
                 const float sc = 146.17696f * cur.Ml[l] / sqrtf(num / (float)(b - a));
@@ -619,33 +771,26 @@ __device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, float* cur_uw, co
         }
     }
     __syncwarp();
-    // per-bin scaling; bin 128 (Nyquist) is never covered by a band, so its scale stays 0
-    for (int i = lane; i < NFFT; i += 32) {
-        const int bin = (i == 0) ? 0 : ((i == NFFT - 1) ? NFFT / 2 : (i + 1) >> 1);
-        A[i] *= scale[bin];
+    // per-bin scaling happens inside the backward transform; bin 128 (Nyquist) is never covered by a band
+    if (!(MBE_ABL & 128)) {
+        rfft256_backward(A, B, tw, scale, lane);
     }
-    __syncwarp();
-    rfft256_backward(A, B, tw, lane);
     const float inv = 1.0f / (float)NFFT;
-    // scale by 1/N and hand the block to the state; the WOLA below reads this frame's samples back
-    for (int i = lane; i < NFFT; i += 32) {
-        A[i] *= inv;
-    }
-    __syncwarp();
-    // weighted overlap-add with the previous frame's inverse transform
+    // weighted overlap-add of this frame's block (scaled by 1/N as it is read) with the previous frame's
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
         const int n = 32 * c + lane;
         const float den = bt->wola_den[n];
         const float ps = (n + 128 < NFFT) ? enh_uw[n + 128] : 0.0f;
-        const float cs = (n - 32 >= 0) ? A[n - 32] : 0.0f;
+        const float cs = (n - 32 >= 0) ? (A[n - 32] * inv) : 0.0f;
         if (den > 1e-10f) {
             ws.out[n] += ((bt->wola_wp[n] * ps) + (bt->wola_wc[n] * cs)) / den;
         }
     }
-    __syncwarp();
-    for (int i = lane; i < NFFT; i += 32) {
-        cur_uw[i] = A[i];
+    // hand the block to the state
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        cur_uw[32 * c + lane] = A[32 * c + lane] * inv;
     }
     __syncwarp();
 }
@@ -798,8 +943,8 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
                     ph = o.cur.PHIl[l] - (step * (float)NS);
                     g = 2.0f * o.cur.Ml[l];
                 }
-                const float2 d = dev_sincosf(step);
-                const float2 p = dev_sincosf(ph);
+                const float2 d = (MBE_ABL & 4) ? make_float2(step, ph) : dev_sincosf(step);
+                const float2 p = (MBE_ABL & 4) ? make_float2(ph, step) : dev_sincosf(ph);
                 sd = d.x;
                 cd = d.y;
                 s = p.x;
@@ -844,7 +989,7 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
             const float* Wc = Wb + 32 * ch;
             float* tcol = tile + lane;
 #pragma unroll(kOscUnroll)
-            for (int n4 = 0; has_pass && n4 < 8; ++n4) {
+            for (int n4 = 0; has_pass && !(MBE_ABL & 2) && n4 < 8; ++n4) {
                 const float4 w4 = *reinterpret_cast<const float4*>(Wc + 4 * n4);
                 const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
@@ -859,7 +1004,7 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
                 }
             }
             STAGE_T(9);  // phase A
-            if (n_mine) {
+            if (n_mine && !(MBE_ABL & 8)) {
                 const int n = 32 * ch + lane;
 #pragma unroll 1
                 for (int q = 0; q < n_mine; ++q) {
@@ -882,7 +1027,7 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
             STAGE_T(10);  // interpolated harmonics
             __syncthreads();
             STAGE_T(11);  // wait for phase A of the block
-            if (hi > lo) {
+            if (hi > lo && !(MBE_ABL & 1)) {
                 const int n = 32 * ch + lane;
                 float a = me.out[n];
                 int k4 = lo - base;
@@ -999,6 +1144,9 @@ __device__ __noinline__ int synth_begin(WarpWS& ws, const float* cur_overlap, co
 // synth_finish: unvoiced FFT/WOLA synthesis on top of the voiced samples, then the soft clip.
 __device__ __noinline__ void synth_finish(WarpWS& ws, uint32_t* cur_home, const uint32_t* enh_home, const DevTables* T,
                                           const BlockTables* bt, int lane) {
+    if (MBE_ABL & 16) {
+        return;
+    }
     make_noise(ws, reinterpret_cast<float*>(cur_home + OVERLAP_WORD), T, bt, lane);
     unvoiced_synthesis(ws, reinterpret_cast<float*>(cur_home + UW_WORD), reinterpret_cast<const float*>(enh_home + UW_WORD), T,
                        bt, lane);
