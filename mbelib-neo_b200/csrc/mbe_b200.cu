@@ -35,6 +35,15 @@ namespace hosttab {
 #include "mbe_parms.cuh"
 #include "mbe_synth.cuh"
 
+#ifndef MBE_TOP_BARRIER
+#define MBE_TOP_BARRIER 1
+#endif
+// block barriers between the per-warp stages of a frame (bit mask; see MBE_STAGE_BARRIER in the stream kernel)
+#ifndef MBE_BARRIERS
+#define MBE_BARRIERS 3
+#endif
+#define MBE_STAGE_BARRIER(bit) do { if (MBE_BARRIERS & (bit)) __syncthreads(); } while (0)
+
 namespace mbe {
 
 constexpr unsigned FLAG_SOFT = 0x0001u, FLAG_C0 = 0x0002u, FLAG_C4 = 0x0004u, FLAG_TONE = 0x0010u,
@@ -86,7 +95,7 @@ __device__ __forceinline__ int resolve_total_errors(int c0, int prot, int c4, in
 __device__ __forceinline__ Action process_imbe(FrameCtx& fc, const unsigned dw[3], WarpWS& ws, const StreamHome& home,
                                                const DevTables* T, int lane) {
     ParmsSmall& cur = ws.cur;
-    ParmsSmall& prev = ws.prev;
+    PrevSmall& prev = ws.prev;
     const float rate = (0.95f * prev.errorRate) + (0.000365f * (float)fc.total);
     __syncwarp();
     if (lane == 0) {
@@ -155,13 +164,15 @@ __device__ __forceinline__ void init_ambe(WarpWS& ws, const StreamHome& home, co
 // erasure model built in cur_mp from prev_mp: phases, noise generator and WOLA tail carried over
 __device__ __forceinline__ void set_erasure_model(WarpWS& ws, const StreamHome& home, int lane) {
     ParmsSmall& mp = ws.cur;
-    const ParmsSmall& src = ws.prev;
+    const PrevSmall& src = ws.prev;
+    __syncwarp();
     for (int l = lane; l <= 56; l += 32) {
         mp.Ml[l] = 1.0f;
         mp.Vl[l] = 0;
         mp.log2Ml[l] = 0.0f;
-        mp.PHIl[l] = src.PHIl[l];
-        mp.PSIl[l] = src.PSIl[l];
+        // prev_mp's phases live in its HBM image (PHIl at words 174.., PSIl at 231..), PHIl[0] in shared memory
+        mp.PHIl[l] = (l == 0) ? src.PHIl0 : __uint_as_float(home.prev[174 + l]);
+        mp.PSIl[l] = __uint_as_float(home.prev[231 + l]);
     }
     bulk_copy(home.cur, home.prev, lane);
     if (lane == 0) {
@@ -308,20 +319,29 @@ __device__ __forceinline__ Action process_ambe2400(FrameCtx& fc, const unsigned 
 //                  ambe3600x2450.c:785-799).  Returns 1 if the frame goes through the bank.
 //   voiced_bank_block  all warps of the block together.
 //   render_end     per warp: unvoiced synthesis, clip, state hand-over.
+// render_begin is split in two (enhancement | synthesis set-up) and render_end in three (forward transform |
+// shaping + backward transform | overlap-add + hand-over) so that the kernel can put block barriers between the
+// stages: warps of a block that walk the same code share their instruction fetches.
+struct RenderState {
+    int voice;      // frame runs the speech synthesiser (ACT_VOICE or ACT_REPLAY)
+    int has_rm0;
+    float rm0;
+};
+
 template <bool AMBE>
-__device__ __forceinline__ int render_begin(const Action& act, WarpWS& ws, const StreamHome& home, const DevTables* T,
-                                            int lane) {
+__device__ __forceinline__ RenderState render_begin1(const Action& act, WarpWS& ws, const StreamHome& home,
+                                                     const DevTables* T, int lane) {
+    RenderState rs = {0, 0, 0.0f};
     int kind = act.kind;
     if (!AMBE) {
         kind = ACT_VOICE;
     }
     if (kind == ACT_VOICE || kind == ACT_REPLAY) {
-        float rm0 = 0.0f;
-        int has_rm0 = 0;
+        rs.voice = 1;
         if (kind == ACT_VOICE) {
             prev_from_cur(ws, home, lane);
-            rm0 = spectral_enhance(ws.cur, lane);
-            has_rm0 = 1;
+            rs.rm0 = spectral_enhance(ws.cur, lane);
+            rs.has_rm0 = 1;
         } else {
             // replay the last voice model (ambe3600x2450.c:808-816): cur_mp is parked in the stream's scratch image
             const uint32_t* cw = reinterpret_cast<const uint32_t*>(&ws.cur);
@@ -335,7 +355,7 @@ __device__ __forceinline__ int render_begin(const Action& act, WarpWS& ws, const
             __syncwarp();
             cur_from_enh(ws, home, lane);
         }
-        return synth_begin(ws, reinterpret_cast<const float*>(home.cur + OVERLAP_WORD), T, has_rm0, rm0, lane);
+        return rs;
     }
     if (AMBE) {
         if (kind == ACT_TONE) {
@@ -343,7 +363,7 @@ __device__ __forceinline__ int render_begin(const Action& act, WarpWS& ws, const
             if (act.keep_prev) {
                 prev_from_cur(ws, home, lane);
             }
-            return 0;
+            return rs;
         }
         comfort_noise(ws, T, lane);
         if (kind == ACT_COMFORT_ERASURE) {
@@ -353,21 +373,26 @@ __device__ __forceinline__ int render_begin(const Action& act, WarpWS& ws, const
             init_ambe(ws, home, T, lane);
         }
     }
-    return 0;
+    return rs;
 }
 
+__device__ __forceinline__ int render_begin2(const RenderState& rs, WarpWS& ws, const StreamHome& home, const DevTables* T,
+                                             int lane) {
+    if (!rs.voice) {
+        return 0;
+    }
+    return synth_begin(ws, reinterpret_cast<const float*>(home.cur + OVERLAP_WORD), T, rs.has_rm0, rs.rm0, lane);
+}
+
+// after the overlap-add: prev_mp_enhanced <- cur_mp, and the replay path puts the parked cur_mp back
 template <bool AMBE>
-__device__ __forceinline__ void render_end(const Action& act, int go, WarpWS& ws, const StreamHome& home,
-                                           const DevTables* T, const BlockTables* bt, int lane) {
-    const int kind = AMBE ? act.kind : (int)ACT_VOICE;
-    if (kind != ACT_VOICE && kind != ACT_REPLAY) {
+__device__ __forceinline__ void render_end(const Action& act, const RenderState& rs, WarpWS& ws, const StreamHome& home,
+                                           int lane) {
+    if (!rs.voice) {
         return;
     }
-    if (go) {
-        synth_finish(ws, home.cur, home.enh, T, bt, lane);
-    }
     enh_from_cur(ws, home, lane);
-    if (AMBE && kind == ACT_REPLAY) {
+    if (AMBE && act.kind == ACT_REPLAY) {
         uint32_t* cw = reinterpret_cast<uint32_t*>(&ws.cur);
         for (int i = lane; i < HEAD_WORDS; i += 32) {
             cw[i] = home.spill[i];
@@ -392,6 +417,9 @@ __device__ __forceinline__ void load_block_tables(BlockTables* bt, const DevTabl
         bt->wola_wp[i] = T->wola_wp[i];
         bt->wola_wc[i] = T->wola_wc[i];
         bt->wola_den[i] = T->wola_den[i];
+    }
+    if (threadIdx.x < 32) {
+        bt->uv_jump[threadIdx.x] = make_uint2(T->uvA[threadIdx.x], T->uvC[threadIdx.x]);
     }
     __syncthreads();
 }
@@ -420,13 +448,15 @@ __device__ __forceinline__ void load_stream(WarpWS& ws, const uint32_t* gs, int 
     uint32_t* e = reinterpret_cast<uint32_t*>(&ws.enh);
     for (int i = lane; i < HEAD_WORDS; i += 32) {
         c[i] = gs[i];
-        p[i] = gs[PARMS_WORDS + i];
-        e[i] = gs[2 * PARMS_WORDS + i];
+    }
+    for (int j = lane; j < PREV_WORDS; j += 32) {
+        p[j] = gs[PARMS_WORDS + prev_word(j)];
+    }
+    for (int j = lane; j < ENH_WORDS; j += 32) {
+        e[j] = gs[2 * PARMS_WORDS + enh_word(j)];
     }
     if (lane == 0) {
         c[HEAD_WORDS] = gs[SEED_WORD];
-        p[HEAD_WORDS] = gs[PARMS_WORDS + SEED_WORD];
-        e[HEAD_WORDS] = gs[2 * PARMS_WORDS + SEED_WORD];
         ws.rng.comfort = (unsigned long long)gs[3 * PARMS_WORDS] | ((unsigned long long)gs[3 * PARMS_WORDS + 1] << 32);
         ws.rng.uv_seed = gs[3 * PARMS_WORDS + 2];
         ws.rng.uv_override = gs[3 * PARMS_WORDS + 3];
@@ -441,13 +471,15 @@ __device__ __forceinline__ void store_stream(const WarpWS& ws, uint32_t* gs, int
     __syncwarp();
     for (int i = lane; i < HEAD_WORDS; i += 32) {
         gs[i] = c[i];
-        gs[PARMS_WORDS + i] = p[i];
-        gs[2 * PARMS_WORDS + i] = e[i];
+    }
+    for (int j = lane; j < PREV_WORDS; j += 32) {
+        gs[PARMS_WORDS + prev_word(j)] = p[j];
+    }
+    for (int j = lane; j < ENH_WORDS; j += 32) {
+        gs[2 * PARMS_WORDS + enh_word(j)] = e[j];
     }
     if (lane == 0) {
         gs[SEED_WORD] = c[HEAD_WORDS];
-        gs[PARMS_WORDS + SEED_WORD] = p[HEAD_WORDS];
-        gs[2 * PARMS_WORDS + SEED_WORD] = e[HEAD_WORDS];
         gs[3 * PARMS_WORDS] = (uint32_t)(ws.rng.comfort & 0xffffffffULL);
         gs[3 * PARMS_WORDS + 1] = (uint32_t)(ws.rng.comfort >> 32);
         gs[3 * PARMS_WORDS + 2] = ws.rng.uv_seed;
@@ -493,8 +525,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
 #endif
 #pragma unroll 1
     for (int f = 0; f < A.n_frames; ++f) {
-        __syncthreads();  // frame boundary: tiles / counters of the previous frame are dead
+        // no barrier at the frame boundary: the bank's last barrier has retired every cross-warp read of the
+        // previous frame's tiles and component lists, and the counters are double-buffered by frame parity
+#if MBE_TOP_BARRIER
+        __syncthreads();  // keeps the block's warps on the same code (instruction-cache locality)
+#endif
         STAGE_T(0);
+        int* cnt = bs->cnt[f & 1];
         const size_t idx = (size_t)s * A.n_frames + f;
         unsigned dw[3] = {0u, 0u, 0u};
         FrameCtx fc;
@@ -552,7 +589,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
                 fc.c4 = fc.c4v ? c4 : 0;
                 fc.total = total;
             }
-
+        }
+        MBE_STAGE_BARRIER(16);  // ECC front-end | parameter decode
+        if (live) {
             if (status >= 0) {
                 if (!AMBE) {
                     act = process_imbe(fc, dw, ws, home, T, lane);
@@ -562,23 +601,43 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
                     act = process_ambe2450(fc, dw, ws, home, T, lane);
                 }
                 STAGE_T(1);
-                go = render_begin<AMBE>(act, ws, home, T, lane);
-                STAGE_T(2);
-            } else {
-                zero_out(ws, lane);
             }
         }
+        RenderState rs = {0, 0, 0.0f};
+        MBE_STAGE_BARRIER(1);   // decode | enhancement
+        const bool ok = live && status >= 0;
+        if (ok) {
+            rs = render_begin1<AMBE>(act, ws, home, T, lane);
+        } else if (live) {
+            zero_out(ws, lane);
+        }
+        MBE_STAGE_BARRIER(2);   // enhancement | synthesis set-up
+        if (ok) {
+            go = render_begin2(rs, ws, home, T, lane);
+            STAGE_T(2);
+        }
         if (lane == 0) {
-            bs->cnt[warp] = go ? ws.ncomp : 0;
+            cnt[warp] = go ? ws.ncomp : 0;
         }
         __syncthreads();
         STAGE_T(3);
-        voiced_bank_block(wsa, bs, bt, tm, warp, lane);
+        voiced_bank_block(wsa, cnt, bt, tm, warp, lane);
         STAGE_T(4);
 
+        if (go && !(MBE_ABL & 16)) {
+            synth_finish_a(ws, home.cur, T, bt, lane);
+        }
+        MBE_STAGE_BARRIER(4);   // forward transform | shaping + backward transform
+        if (go && !(MBE_ABL & 16)) {
+            synth_finish_b(ws, bt, lane);
+        }
+        MBE_STAGE_BARRIER(8);   // backward transform | overlap-add, hand-over, stores
         if (live) {
             if (status >= 0) {
-                render_end<AMBE>(act, go, ws, home, T, bt, lane);
+                if (go && !(MBE_ABL & 16)) {
+                    synth_finish_c(ws, home.cur, home.enh, bt, lane);
+                }
+                render_end<AMBE>(act, rs, ws, home, lane);
                 STAGE_T(5);
                 status = fc.total;
                 rout.c0_errors = fc.c0;
@@ -640,12 +699,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
     if (live) {
         for (int i = lane; i < HEAD_WORDS; i += 32) {
             c[i] = gc[i];
-            e[i] = gp[i];
+        }
+        for (int j = lane; j < ENH_WORDS; j += 32) {
+            e[j] = gp[enh_word(j)];
         }
         // RNG as after mbe_setThreadRngSeed(seed) (mbelib.c:173-181); no seeds: fresh-thread defaults
         if (lane == 0) {
             c[HEAD_WORDS] = gc[SEED_WORD];
-            e[HEAD_WORDS] = gp[SEED_WORD];
             if (A.synth_seeds) {
                 unsigned seed = A.synth_seeds[s];
                 if (seed == 0u) {
@@ -664,24 +724,27 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
         go = synth_begin(ws, reinterpret_cast<const float*>(gc + OVERLAP_WORD), T, 0, 0.0f, lane);
     }
     if (lane == 0) {
-        bs->cnt[warp] = go ? ws.ncomp : 0;
+        bs->cnt[0][warp] = go ? ws.ncomp : 0;
     }
     __syncthreads();
     StageTimer tm;
-    voiced_bank_block(wsa, bs, bt, tm, warp, lane);
+    voiced_bank_block(wsa, bs->cnt[0], bt, tm, warp, lane);
     if (live) {
         if (go) {
-            synth_finish(ws, gc, gp, T, bt, lane);
+            synth_finish_a(ws, gc, T, bt, lane);
+            synth_finish_b(ws, bt, lane);
+            synth_finish_c(ws, gc, gp, bt, lane);
         }
         __syncwarp();
         store_pcm(A, ws, (size_t)s, lane);
         for (int i = lane; i < HEAD_WORDS; i += 32) {
             gc[i] = c[i];
-            gp[i] = e[i];
+        }
+        for (int j = lane; j < ENH_WORDS; j += 32) {
+            gp[enh_word(j)] = e[j];
         }
         if (lane == 0) {
             gc[SEED_WORD] = c[HEAD_WORDS];
-            gp[SEED_WORD] = e[HEAD_WORDS];
         }
     }
 }

@@ -65,6 +65,62 @@ struct ParmsSmall {
     float mutingThreshold;
     float noiseSeed;
 };
+// prev_mp in shared memory: only what the decoders read every frame (prediction source, error-rate filter,
+// repeat counters).  Its Vl / PHIl[1..56] / PSIl words stay in the stream's HBM image like the bulk arrays; they
+// are only moved by whole-struct copies (repeat, erasure model).
+struct PrevSmall {
+    float w0;
+    int L;
+    int K;
+    float Ml[57];
+    float log2Ml[57];
+    float PHIl0;                      // PHIl[0]: the reference's prediction reads log2Ml[57] == PHIl[0]
+    float gamma;
+    uint32_t tonePhase;
+    int swn;
+    float localEnergy;
+    int amplitudeThreshold;
+    float errorRate;
+    int errorCountTotal;
+    int errorCount4;
+    int repeatCount;
+    float mutingThreshold;
+    float noiseSeed;
+};
+// prev_mp_enhanced in shared memory: the synthesis continuity state; its log2Ml stays in HBM.
+struct EnhSmall {
+    float w0;
+    int L;
+    int K;
+    int Vl[57];
+    float Ml[57];
+    float PHIl[57];
+    float PSIl[57];
+    float gamma;
+    uint32_t tonePhase;
+    int swn;
+    float localEnergy;
+    int amplitudeThreshold;
+    float errorRate;
+    int errorCountTotal;
+    int errorCount4;
+    int repeatCount;
+    float mutingThreshold;
+    float noiseSeed;
+};
+constexpr int PREV_WORDS = 129, ENH_WORDS = 242;
+static_assert(sizeof(PrevSmall) == PREV_WORDS * 4 && sizeof(EnhSmall) == ENH_WORDS * 4, "compact layouts");
+// word j of the compact struct <-> word of the 651-word mbe_parms image
+__host__ __device__ constexpr int prev_word(int j) { return j < 3 ? j : (j < 118 ? j + 57 : (j < 128 ? j + 170 : 554)); }
+__host__ __device__ constexpr int enh_word(int j) { return j < 117 ? j : (j < 241 ? j + 57 : 554); }
+static_assert(prev_word(3) == 60 && prev_word(117) == 174 && prev_word(118) == 288 && prev_word(127) == 297, "prev map");
+static_assert(enh_word(116) == 116 && enh_word(117) == 174 && enh_word(231) == 288 && enh_word(240) == 297, "enh map");
+// mbe_parms words of prev_mp that are NOT in PrevSmall: Vl[0..56] = 3..59, PHIl[1..56] + PSIl[0..56] = 175..287 (170 words);
+// of prev_mp_enhanced: log2Ml[0..56] = 117..173 (57 words)
+__host__ __device__ constexpr int prev_home_word(int j) { return j < 57 ? 3 + j : 118 + j; }
+constexpr int PREV_HOME_WORDS = 170, ENH_HOME_WORD0 = 117, ENH_HOME_WORDS = 57;
+static_assert(prev_home_word(56) == 59 && prev_home_word(57) == 175 && prev_home_word(169) == 287, "prev home map");
+
 constexpr int HEAD_WORDS = 298;       // w0 .. mutingThreshold
 constexpr int UW_WORD = 298;          // previousUw[256]
 constexpr int SEED_WORD = 554;        // noiseSeed
@@ -141,7 +197,6 @@ struct LaunchArgs {
     unsigned long long* dbg;    // MBE_STAGE_TIMING builds: 16 accumulated per-stage cycle counters
 };
 
-constexpr int TILE_STRIDE = 36;   // floats per sample row of the oscillator tile (32 components + pad)
 
 // Tables every warp of a block reads with lane-varying indices on the synthesis path, staged into
 // shared memory once per block (5.3 KB).
@@ -150,13 +205,14 @@ struct __align__(16) BlockTables {
     float tw[256];           // FFTPACK twiddles
     float uvwin[256];        // unvoiced analysis window, centred at 128
     float wola_wp[160], wola_wc[160], wola_den[160];
+    uint2 uv_jump[32];       // unvoiced-noise LCG jump-ahead by `lane` steps: x -> (x * .x + .y) mod 53125
 };
 
 // Streams (= warps) per block.  The block walks its streams' frames in lockstep: per frame every warp
 // decodes its own stream, then the block pools the oscillator components of all its streams and
 // spreads them evenly over all lanes (voiced_bank_block), then every warp finishes its own stream.
 #ifndef MBE_WPB
-#define MBE_WPB 12
+#define MBE_WPB 14
 #endif
 #ifndef MBE_MINB
 #define MBE_MINB 2
@@ -175,7 +231,7 @@ struct StreamRng {
 struct __align__(16) WarpWS {
     StreamRng rng;
     union __align__(16) {
-        float tile[32 * TILE_STRIDE];     // voiced bank: [sample][component], pre-weighted contributions
+        float tile[32 * 32];              // voiced bank: [sample][slot] pre-weighted contributions, XOR-swizzled (tile_at)
         struct {
             float a[324];                 // FFT ping buffer (windowed noise on entry); 324: padded pass layouts
             float b[324];                 // FFT pong buffer
@@ -196,9 +252,8 @@ struct __align__(16) WarpWS {
     // stream's HBM slot); 16-byte aligned for 128-bit struct copies.
     ParmsSmall cur;
     uint32_t pad_cur;
-    ParmsSmall prev;
-    uint32_t pad_prev;
-    ParmsSmall enh;
+    PrevSmall prev;
+    EnhSmall enh;
     uint32_t pad_enh;
     int ncomp;                            // oscillator components of this frame (0: no voiced synthesis)
     unsigned k2mask;                      // list positions (< 32) of phase-interpolated harmonics
@@ -207,11 +262,11 @@ struct __align__(16) WarpWS {
     unsigned char comp[112];              // component descriptor: harmonic << 2 | kind
 };
 static_assert(offsetof(WarpWS, u) % 16 == 0 && sizeof(WarpWS) % 16 == 0 && sizeof(BlockTables) % 16 == 0 &&
-                  offsetof(WarpWS, cur) % 16 == 0 && offsetof(WarpWS, prev) % 16 == 0 && offsetof(WarpWS, enh) % 16 == 0,
+                  offsetof(WarpWS, cur) % 16 == 0,
               "LDS.128 alignment");
 
 struct BlockShared {
-    int cnt[WARPS_PER_BLOCK + 3];         // per stream: component count of the current frame
+    int cnt[2][WARPS_PER_BLOCK + 2];      // per stream: component count of the current frame (double-buffered by frame parity)
 };
 
 // MBE_STAGE_TIMING=1 builds accumulate per-stage clock64() deltas per warp into LaunchArgs.dbg (profiling aid)

@@ -28,7 +28,7 @@ __device__ __forceinline__ unsigned pick(const unsigned dw[3]) {
 __device__ __forceinline__ void predict_magnitudes(WarpWS& ws, const DevTables* T, int ambe, float rho, float unvc,
                                                    int lane) {
     ParmsSmall& cur = ws.cur;
-    ParmsSmall& prev = ws.prev;
+    PrevSmall& prev = ws.prev;
     const int cur_L = cur.L;  // already within 9..56
     int prev_L = prev.L;
     prev_L = prev_L < 1 ? 1 : (prev_L > 56 ? 56 : prev_L);

@@ -41,29 +41,10 @@ __device__ __noinline__ float dev_sinf(float y) { return mbelibm::sinf_glibc(y);
 __device__ __forceinline__ bool bands_ok(int L) { return L >= 1 && L <= MAXL; }
 
 // ---- whole-struct copies ---------------------------------------------------------------------------
-// cur_mp lives completely in shared memory; prev_mp / prev_mp_enhanced keep only their first 298 words
-// + noiseSeed there, their previousUw / noiseOverlap arrays stay in the stream's HBM slot (`g` below
-// points at that struct's 651-word image).  Array element i is always moved by lane i % 32, so a lane
-// only ever reads back global words it wrote itself.
-template <class D, class S>
-__device__ __forceinline__ void copy_small(D& dst, const S& src, int lane) {
-    // 298 head words = 74 x 16 bytes + 2 words; the structs are 16-byte aligned inside WarpWS
-    float4* d4 = reinterpret_cast<float4*>(&dst);
-    const float4* s4 = reinterpret_cast<const float4*>(&src);
-    d4[lane] = s4[lane];
-    d4[32 + lane] = s4[32 + lane];
-    if (lane < 10) {
-        d4[64 + lane] = s4[64 + lane];
-    }
-    if (lane < 2) {
-        reinterpret_cast<uint32_t*>(&dst)[296 + lane] = reinterpret_cast<const uint32_t*>(&src)[296 + lane];
-    }
-    if (lane == 2) {
-        dst.noiseSeed = src.noiseSeed;
-    }
-    __syncwarp();
-}
-
+// cur_mp's head (298 words + noiseSeed) lives in shared memory; prev_mp / prev_mp_enhanced keep compact
+// subsets there (PrevSmall / EnhSmall); everything else (their remaining head words, and previousUw /
+// noiseOverlap of all three) stays in the stream's HBM slot.  Global words are made visible between lanes
+// by the __syncwarp() that follows every copy.
 // previousUw[256] + noiseOverlap[96] of one struct image to another, both in HBM (11 independent loads per
 // lane in flight, then 11 stores)
 // (plain pointers: these words are written by this kernel too, so they must not go through the read-only path)
@@ -109,21 +90,66 @@ struct StreamHome {
     uint32_t* spill;
 };
 
+__device__ __forceinline__ uint32_t* cur_words(WarpWS& ws) { return reinterpret_cast<uint32_t*>(&ws.cur); }
+__device__ __forceinline__ int cur_slot(int w) { return w < HEAD_WORDS ? w : HEAD_WORDS; }  // noiseSeed (554) -> 298
+
 __device__ __forceinline__ void prev_from_cur(WarpWS& ws, const StreamHome& h, int lane) {
-    copy_small(ws.prev, ws.cur, lane);
+    const uint32_t* c = cur_words(ws);
+    uint32_t* p = reinterpret_cast<uint32_t*>(&ws.prev);
+#pragma unroll
+    for (int j = lane; j < PREV_WORDS; j += 32) {
+        p[j] = c[cur_slot(prev_word(j))];
+    }
+#pragma unroll
+    for (int j = lane; j < PREV_HOME_WORDS; j += 32) {
+        const int w = prev_home_word(j);
+        h.prev[w] = c[w];
+    }
     bulk_copy(h.prev, h.cur, lane);
+    __syncwarp();
 }
 __device__ __forceinline__ void enh_from_cur(WarpWS& ws, const StreamHome& h, int lane) {
-    copy_small(ws.enh, ws.cur, lane);
+    const uint32_t* c = cur_words(ws);
+    uint32_t* e = reinterpret_cast<uint32_t*>(&ws.enh);
+#pragma unroll
+    for (int j = lane; j < ENH_WORDS; j += 32) {
+        e[j] = c[cur_slot(enh_word(j))];
+    }
+#pragma unroll
+    for (int j = lane; j < ENH_HOME_WORDS; j += 32) {
+        h.enh[ENH_HOME_WORD0 + j] = c[ENH_HOME_WORD0 + j];
+    }
     bulk_copy(h.enh, h.cur, lane);
+    __syncwarp();
 }
 __device__ __forceinline__ void cur_from_prev(WarpWS& ws, const StreamHome& h, int lane) {
-    copy_small(ws.cur, ws.prev, lane);
+    uint32_t* c = cur_words(ws);
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(&ws.prev);
+#pragma unroll
+    for (int j = lane; j < PREV_WORDS; j += 32) {
+        c[cur_slot(prev_word(j))] = p[j];
+    }
+#pragma unroll
+    for (int j = lane; j < PREV_HOME_WORDS; j += 32) {
+        const int w = prev_home_word(j);
+        c[w] = h.prev[w];
+    }
     bulk_copy(h.cur, h.prev, lane);
+    __syncwarp();
 }
 __device__ __forceinline__ void cur_from_enh(WarpWS& ws, const StreamHome& h, int lane) {
-    copy_small(ws.cur, ws.enh, lane);
+    uint32_t* c = cur_words(ws);
+    const uint32_t* e = reinterpret_cast<const uint32_t*>(&ws.enh);
+#pragma unroll
+    for (int j = lane; j < ENH_WORDS; j += 32) {
+        c[cur_slot(enh_word(j))] = e[j];
+    }
+#pragma unroll
+    for (int j = lane; j < ENH_HOME_WORDS; j += 32) {
+        c[ENH_HOME_WORD0 + j] = h.enh[ENH_HOME_WORD0 + j];
+    }
     bulk_copy(h.cur, h.enh, lane);
+    __syncwarp();
 }
 
 // default model of mbe_initMbeParms / mbe_initAmbeParms_common (head fields + noiseSeed)
@@ -169,11 +195,11 @@ __device__ __forceinline__ void fill_default(Parms* p, float w0, int L, int K, f
 __device__ __noinline__ void init_all(WarpWS& ws, uint32_t* gcur, uint32_t* gprev, uint32_t* genh, float w0, int L, int K,
                                       float mute_thr, int lane) {
     fill_default_small(&ws.cur, w0, L, K, mute_thr, lane);
-    copy_small(ws.prev, ws.cur, lane);
-    copy_small(ws.enh, ws.cur, lane);
     bulk_zero(gcur, lane);
-    bulk_zero(gprev, lane);
-    bulk_zero(genh, lane);
+    __syncwarp();
+    const StreamHome h = {gcur, gprev, genh, nullptr};
+    prev_from_cur(ws, h, lane);
+    enh_from_cur(ws, h, lane);
 }
 
 __device__ __forceinline__ void zero_out(WarpWS& ws, int lane) {
@@ -259,7 +285,7 @@ __device__ __forceinline__ float spectral_enhance(ParmsSmall& cur, int lane) {
 }
 
 // ---- adaptive smoothing, JMBE algorithms #111-116 (mbe_adaptive.c:151-276) -----------------------
-__device__ __forceinline__ void adaptive_smoothing(ParmsSmall& cur, const ParmsSmall& prev, int has_rm0, float rm0,
+__device__ __forceinline__ void adaptive_smoothing(ParmsSmall& cur, const EnhSmall& prev, int has_rm0, float rm0,
                                                    int lane) {
     if (!bands_ok(cur.L) || !bands_ok(prev.L)) {
         return;
@@ -360,6 +386,22 @@ __device__ __forceinline__ void noise_peek(WarpWS& ws, const float* cur_overlap,
     __syncwarp();
 }
 
+// unvoiced-noise LCG x -> (171 x + 11213) mod 53125 (mbe_unvoiced_fft.c:277-302): coefficients of k steps at once
+__host__ __device__ constexpr unsigned lcg_pow_a(int k) {
+    unsigned long long a = 1;
+    for (int i = 0; i < k; ++i) {
+        a = (171ull * a) % 53125ull;
+    }
+    return (unsigned)a;
+}
+__host__ __device__ constexpr unsigned lcg_pow_c(int k) {
+    unsigned long long c = 0;
+    for (int i = 0; i < k; ++i) {
+        c = (171ull * c + 11213ull) % 53125ull;
+    }
+    return (unsigned)c;
+}
+
 // make_noise: builds the frame's 256-sample buffer, advances the LCG / overlap state and writes the
 // WINDOWED buffer (noise * W256) straight into the FFT input.  cur_overlap = cur_mp->noiseOverlap in HBM.
 __device__ __forceinline__ void make_noise(WarpWS& ws, float* cur_overlap, const DevTables* T, const BlockTables* bt,
@@ -383,7 +425,10 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, float* cur_overlap, const
         __syncwarp();
         return;
     }
-    const unsigned st0 = ((unsigned)seed) % 53125u;
+    // x_{32c + lane} = jump_lane(x_{32c}); x_{32(c+1)} = jump_32(x_{32c}); the frame leaves the generator at x_160
+    constexpr unsigned A32 = lcg_pow_a(32), C32 = lcg_pow_c(32);
+    unsigned sc = ((unsigned)seed) % 53125u;
+    const uint2 jl = bt->uv_jump[lane];
     float ov[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -392,7 +437,8 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, float* cur_overlap, const
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
         const int i = 32 * c + lane;
-        const unsigned st = (T->uvA[i] * st0 + T->uvC[i]) % 53125u;
+        const unsigned st = (jl.x * sc + jl.y) % 53125u;
+        sc = (A32 * sc + C32) % 53125u;
         const float v = (float)st;
         A[96 + i] = v * bt->uvwin[96 + i];
         if (i >= 64) {
@@ -404,7 +450,7 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, float* cur_overlap, const
         const int i = 32 * r + lane;
         A[i] = ov[r] * bt->uvwin[i];
     }
-    const unsigned stn = (T->uvA[160] * st0 + T->uvC[160]) % 53125u;
+    const unsigned stn = sc;
     __syncwarp();
     if (lane == 0) {
         cur.noiseSeed = (float)stn;
@@ -726,20 +772,23 @@ __device__ __noinline__ void rfft256_backward(float* __restrict__ A, float* __re
 // ---- unvoiced synthesis (mbe_unvoiced_fft.c:714-761); adds into ws.out and writes cur.previousUw --
 // ws.u.fft.a holds the windowed noise on entry; enh_uw = prev_mp_enhanced->previousUw in HBM.  The spectrum
 // stays in FFTPACK's native order (the reference's "ordered" layout is only a permutation of it).
-__device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, float* cur_uw, const float* enh_uw,
-                                                   const DevTables* T, const BlockTables* bt, int lane) {
-    ParmsSmall& cur = ws.cur;
-    float* A = ws.u.fft.a;
-    float* B = ws.u.fft.b;
+// Three stages (the stream kernel may put a block barrier between them to keep its warps on the same code):
+//   unvoiced_analyse   forward transform;   unvoiced_shape   band scales + backward transform;
+//   unvoiced_overlap   weighted overlap-add into ws.out, hand-over of the block to cur_mp->previousUw
+__device__ __forceinline__ void unvoiced_analyse(WarpWS& ws, const BlockTables* bt, int lane) {
     float* scale = ws.u.fft.scale;
-    const float* tw = bt->tw;
     for (int i = lane; i < 129; i += 32) {
         scale[i] = 0.0f;
     }
     if (!(MBE_ABL & 128)) {
-        rfft256_forward(A, B, tw, lane);   // ends with __syncwarp: scale[] zeros are visible too
+        rfft256_forward(ws.u.fft.a, ws.u.fft.b, bt->tw, lane);   // ends with __syncwarp: scale[] zeros are visible too
     }
+}
 
+__device__ __forceinline__ void unvoiced_shape(WarpWS& ws, const BlockTables* bt, int lane) {
+    ParmsSmall& cur = ws.cur;
+    float* A = ws.u.fft.a;
+    float* scale = ws.u.fft.scale;
     const int L = cur.L;
     const float mult = (256.0f / (2.0f * 3.14159265358979323846f)) * cur.w0;
     for (int l = 1 + lane; l <= L; l += 32) {
@@ -773,19 +822,32 @@ __device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, float* cur_uw, co
     __syncwarp();
     // per-bin scaling happens inside the backward transform; bin 128 (Nyquist) is never covered by a band
     if (!(MBE_ABL & 128)) {
-        rfft256_backward(A, B, tw, scale, lane);
+        rfft256_backward(A, ws.u.fft.b, bt->tw, scale, lane);
     }
+}
+
+__device__ __forceinline__ void unvoiced_overlap(WarpWS& ws, float* cur_uw, const float* enh_uw, const BlockTables* bt,
+                                                 int lane) {
+    const float* A = ws.u.fft.a;
     const float inv = 1.0f / (float)NFFT;
-    // weighted overlap-add of this frame's block (scaled by 1/N as it is read) with the previous frame's
+    // weighted overlap-add of this frame's block (scaled by 1/N as it is read) with the previous frame's,
+    // then the soft clip (mbelib.c:669-689)
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
         const int n = 32 * c + lane;
         const float den = bt->wola_den[n];
         const float ps = (n + 128 < NFFT) ? enh_uw[n + 128] : 0.0f;
         const float cs = (n - 32 >= 0) ? (A[n - 32] * inv) : 0.0f;
+        float v = ws.out[n];
         if (den > 1e-10f) {
-            ws.out[n] += ((bt->wola_wp[n] * ps) + (bt->wola_wc[n] * cs)) / den;
+            v += ((bt->wola_wp[n] * ps) + (bt->wola_wc[n] * cs)) / den;
         }
+        if (v > MBE_CLIP_F) {
+            v = MBE_CLIP_F;
+        } else if (v < -MBE_CLIP_F) {
+            v = -MBE_CLIP_F;
+        }
+        ws.out[n] = v;
     }
     // hand the block to the state
 #pragma unroll
@@ -804,7 +866,7 @@ __device__ __forceinline__ void unvoiced_synthesis(WarpWS& ws, float* cur_uw, co
 // their contribution is +-0 and x + (+-0) == x for every accumulator value that can occur.
 __device__ __forceinline__ void build_components(WarpWS& ws, int maxl, int lane) {
     const ParmsSmall& cur = ws.cur;
-    const ParmsSmall& prev = ws.enh;
+    const EnhSmall& prev = ws.enh;
     const float cw0 = cur.w0, pw0 = prev.w0;
     const bool stable = fabsf(cw0 - pw0) < (0.1f * cw0);
     int ncomp = 0;
@@ -869,6 +931,11 @@ __device__ __forceinline__ unsigned round_k2mask(unsigned k2mask, int off, int c
     return m;
 }
 
+// Oscillator tile: 32 samples x 32 slots, no padding.  Slot column c of sample row n lives at
+// n*32 + (c ^ ((n & 7) << 2)): phase A (lane = slot, one row per store) and phase B (lane = sample, LDS.128 over
+// four consecutive slots) are both bank-conflict free.
+__device__ __forceinline__ int tile_at(int n, int c) { return n * 32 + (c ^ ((n & 7) << 2)); }
+
 // voiced_bank_block: ALL warps of the block call this once per frame (block barriers inside).
 // The component lists of the block's streams are laid end to end (each stream's start rounded up to a
 // multiple of four slots) and cut into passes of 32 slots; pass p of a round is run by warp p:
@@ -880,14 +947,14 @@ __device__ __forceinline__ unsigned round_k2mask(unsigned k2mask, int off, int c
 //            each) from whichever tiles they landed in.
 // So oscillator work is spread evenly over the block no matter how the components are distributed
 // over streams, and a stream's additions keep the reference's order.
-__device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared* bs, const BlockTables* bt,
+__device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const int* cnt, const BlockTables* bt,
                                                   StageTimer& tm, int warp, int lane) {
     constexpr int W = WARPS_PER_BLOCK;
     WarpWS& me = wsa[warp];
     // slot offsets: exclusive prefix of the counts, each rounded up to a multiple of four (every warp
     // keeps its own copy in shared memory; lanes 0..W-1 scan)
     {
-        const int padded = (lane < W) ? ((bs->cnt[lane] + 3) & ~3) : 0;
+        const int padded = (lane < W) ? ((cnt[lane] + 3) & ~3) : 0;
         int incl = padded;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -906,7 +973,7 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
     if (total == 0) {
         return;
     }
-    const int my_lo = off[warp], my_cnt = bs->cnt[warp];
+    const int my_lo = off[warp], my_cnt = cnt[warp];
     const int my_hi = my_lo + ((my_cnt + 3) & ~3);
     float* tile = me.u.tile;
 
@@ -917,7 +984,7 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
         int owner = -1, j = 0;
 #pragma unroll
         for (int i = 0; i < W; ++i) {
-            if (k >= off[i] && k < off[i] + bs->cnt[i]) {
+            if (k >= off[i] && k < off[i] + cnt[i]) {
                 owner = i;
                 j = k - off[i];
             }
@@ -967,7 +1034,7 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
                 int t = 0;
 #pragma unroll 1
                 for (int i = 0; i < W; ++i) {
-                    unsigned m = round_k2mask(wsa[i].k2mask, off[i], bs->cnt[i], base, 32 * W);
+                    unsigned m = round_k2mask(wsa[i].k2mask, off[i], cnt[i], base, 32 * W);
                     const int first = max(off[i], base) - off[i];
                     while (m) {
                         const int jj = __ffs(m) - 1;
@@ -987,7 +1054,6 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
 #pragma unroll 1
         for (int ch = 0; ch < 5; ++ch) {
             const float* Wc = Wb + 32 * ch;
-            float* tcol = tile + lane;
 #pragma unroll(kOscUnroll)
             for (int n4 = 0; has_pass && !(MBE_ABL & 2) && n4 < 8; ++n4) {
                 const float4 w4 = *reinterpret_cast<const float4*>(Wc + 4 * n4);
@@ -995,7 +1061,7 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (!k2lane) {
-                        tcol[(4 * n4 + q) * TILE_STRIDE] = (g * wv[q]) * c;
+                        tile[tile_at(4 * n4 + q, lane)] = (g * wv[q]) * c;
                     }
                     const float cn = (c * cd) - (s * sd);
                     const float sn = (s * cd) + (c * sd);
@@ -1021,7 +1087,7 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
                     const float th = o.enh.PHIl[l] + ((pw0l + dw) * (float)n)
                                      + (((cw0 - pw0) * (float)(l * n * n)) / (float)(2 * NS));
                     const float am = o.enh.Ml[l] + (((float)n / (float)NS) * (o.cur.Ml[l] - o.enh.Ml[l]));
-                    wsa[slot >> 5].u.tile[lane * TILE_STRIDE + (slot & 31)] = 2.0f * am * dev_cosf(th);
+                    wsa[slot >> 5].u.tile[tile_at(lane, slot & 31)] = 2.0f * am * dev_cosf(th);
                 }
             }
             STAGE_T(10);  // interpolated harmonics
@@ -1037,20 +1103,22 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
                     // the part of this stream's slot range that lies in one tile: loads first, then the adds in order
                     const int tix = k4 >> 5;
                     const int e = min(end, (tix + 1) << 5);
-                    const float4* row = reinterpret_cast<const float4*>(wsa[tix].u.tile + lane * TILE_STRIDE + (k4 & 31));
-                    const int nq = (e - k4) >> 2;
-                    int q = 0;
+                    // row `lane` of that tile; its four-slot groups sit at group ^ (lane & 7)
+                    const float4* row = reinterpret_cast<const float4*>(wsa[tix].u.tile + lane * 32);
+                    const int sw = lane & 7;
+                    int gq = (k4 & 31) >> 2;
+                    const int ge = gq + ((e - k4) >> 2);
 #pragma unroll 1
-                    for (; q + 4 <= nq; q += 4) {
-                        const float4 v0 = row[q], v1 = row[q + 1], v2 = row[q + 2], v3 = row[q + 3];
+                    for (; gq + 4 <= ge; gq += 4) {
+                        const float4 v0 = row[gq ^ sw], v1 = row[(gq + 1) ^ sw], v2 = row[(gq + 2) ^ sw], v3 = row[(gq + 3) ^ sw];
                         a += v0.x; a += v0.y; a += v0.z; a += v0.w;
                         a += v1.x; a += v1.y; a += v1.z; a += v1.w;
                         a += v2.x; a += v2.y; a += v2.z; a += v2.w;
                         a += v3.x; a += v3.y; a += v3.z; a += v3.w;
                     }
 #pragma unroll 1
-                    for (; q < nq; ++q) {
-                        const float4 v = row[q];
+                    for (; gq < ge; ++gq) {
+                        const float4 v = row[gq ^ sw];
                         a += v.x; a += v.y; a += v.z; a += v.w;
                     }
                     k4 = e;
@@ -1071,7 +1139,7 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const BlockShared
 __device__ __noinline__ int synth_begin(WarpWS& ws, const float* cur_overlap, const DevTables* T, int has_rm0,
                                         float rm0, int lane) {
     ParmsSmall& cur = ws.cur;
-    ParmsSmall& prev = ws.enh;
+    EnhSmall& prev = ws.enh;
     zero_out(ws, lane);
     if (!bands_ok(cur.L) || !bands_ok(prev.L)) {
         __syncwarp();
@@ -1141,26 +1209,17 @@ __device__ __noinline__ int synth_begin(WarpWS& ws, const float* cur_overlap, co
     return 1;
 }
 
-// synth_finish: unvoiced FFT/WOLA synthesis on top of the voiced samples, then the soft clip.
-__device__ __noinline__ void synth_finish(WarpWS& ws, uint32_t* cur_home, const uint32_t* enh_home, const DevTables* T,
-                                          const BlockTables* bt, int lane) {
-    if (MBE_ABL & 16) {
-        return;
-    }
+// synth_finish_*: unvoiced FFT/WOLA synthesis on top of the voiced samples and the soft clip, in three stages
+__device__ __noinline__ void synth_finish_a(WarpWS& ws, uint32_t* cur_home, const DevTables* T, const BlockTables* bt,
+                                            int lane) {
     make_noise(ws, reinterpret_cast<float*>(cur_home + OVERLAP_WORD), T, bt, lane);
-    unvoiced_synthesis(ws, reinterpret_cast<float*>(cur_home + UW_WORD), reinterpret_cast<const float*>(enh_home + UW_WORD), T,
-                       bt, lane);
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        float v = ws.out[32 * c + lane];
-        if (v > MBE_CLIP_F) {
-            v = MBE_CLIP_F;
-        } else if (v < -MBE_CLIP_F) {
-            v = -MBE_CLIP_F;
-        }
-        ws.out[32 * c + lane] = v;
-    }
-    __syncwarp();
+    unvoiced_analyse(ws, bt, lane);
+}
+__device__ __noinline__ void synth_finish_b(WarpWS& ws, const BlockTables* bt, int lane) { unvoiced_shape(ws, bt, lane); }
+__device__ __noinline__ void synth_finish_c(WarpWS& ws, uint32_t* cur_home, const uint32_t* enh_home, const BlockTables* bt,
+                                            int lane) {
+    unvoiced_overlap(ws, reinterpret_cast<float*>(cur_home + UW_WORD), reinterpret_cast<const float*>(enh_home + UW_WORD), bt,
+                     lane);
 }
 
 // ---- tone synthesis (mbelib.c:692-856, src/internal/mbe_tone.h) -----------------------------------
