@@ -498,7 +498,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
     WarpWS* wsa = reinterpret_cast<WarpWS*>(smem_raw + sizeof(BlockTables));
     BlockShared* bs = reinterpret_cast<BlockShared*>(smem_raw + sizeof(BlockTables) + WARPS_PER_BLOCK * sizeof(WarpWS));
     const DevTables* T = A.tab;
-    load_block_tables(bt, T);
+    if (threadIdx.x == 0) {
+        bs->n_interp[0] = bs->n_interp[1] = 0;
+    }
+    load_block_tables(bt, T);   // ends with a block barrier
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -531,7 +534,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
         __syncthreads();  // keeps the block's warps on the same code (instruction-cache locality)
 #endif
         STAGE_T(0);
-        int* cnt = bs->cnt[f & 1];
+
         const size_t idx = (size_t)s * A.n_frames + f;
         unsigned dw[3] = {0u, 0u, 0u};
         FrameCtx fc;
@@ -616,12 +619,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
             go = render_begin2(rs, ws, home, T, lane);
             STAGE_T(2);
         }
-        if (lane == 0) {
-            cnt[warp] = go ? ws.ncomp : 0;
-        }
+        publish_components(bs, f & 1, ws, go, warp, lane);
         __syncthreads();
         STAGE_T(3);
-        voiced_bank_block(wsa, cnt, bt, tm, warp, lane);
+        voiced_bank_block(wsa, bs, f & 1, bt, tm, warp, lane);
         STAGE_T(4);
 
         if (go && !(MBE_ABL & 16)) {
@@ -723,12 +724,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
         __syncwarp();
         go = synth_begin(ws, reinterpret_cast<const float*>(gc + OVERLAP_WORD), T, 0, 0.0f, lane);
     }
-    if (lane == 0) {
-        bs->cnt[0][warp] = go ? ws.ncomp : 0;
+    if (threadIdx.x == 0) {
+        bs->n_interp[0] = 0;
     }
     __syncthreads();
+    publish_components(bs, 0, ws, go, warp, lane);
+    __syncthreads();
     StageTimer tm;
-    voiced_bank_block(wsa, bs->cnt[0], bt, tm, warp, lane);
+    voiced_bank_block(wsa, bs, 0, bt, tm, warp, lane);
     if (live) {
         if (go) {
             synth_finish_a(ws, gc, T, bt, lane);

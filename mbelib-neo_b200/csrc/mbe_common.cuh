@@ -258,7 +258,7 @@ struct __align__(16) WarpWS {
     int ncomp;                            // oscillator components of this frame (0: no voiced synthesis)
     unsigned k2mask;                      // list positions (< 32) of phase-interpolated harmonics
     unsigned short off[WARPS_PER_BLOCK + 3];  // this warp's copy of the block's slot offsets (prefix of padded counts)
-    unsigned short interp_item[8];        // interpolated harmonics of the block this warp renders: owner << 8 | position
+    unsigned short interp_item[8];        // interpolated harmonics of the block this warp renders in this round: owner << 8 | position
     unsigned char comp[112];              // component descriptor: harmonic << 2 | kind
 };
 static_assert(offsetof(WarpWS, u) % 16 == 0 && sizeof(WarpWS) % 16 == 0 && sizeof(BlockTables) % 16 == 0 &&
@@ -267,6 +267,8 @@ static_assert(offsetof(WarpWS, u) % 16 == 0 && sizeof(WarpWS) % 16 == 0 && sizeo
 
 struct BlockShared {
     int cnt[2][WARPS_PER_BLOCK + 2];      // per stream: component count of the current frame (double-buffered by frame parity)
+    int n_interp[2];                      // phase-interpolated harmonics of the block's streams in this frame
+    unsigned short interp[2][WARPS_PER_BLOCK * 7 + 2];  // owner stream << 8 | list position (at most 7 per stream: l < 8)
 };
 
 // MBE_STAGE_TIMING=1 builds accumulate per-stage clock64() deltas per warp into LaunchArgs.dbg (profiling aid)

@@ -916,19 +916,24 @@ __device__ __forceinline__ void build_components(WarpWS& ws, int maxl, int lane)
     __syncwarp();
 }
 
-// list positions (as a bit mask shifted to the round's first slot of that stream) of the interpolated
-// harmonics of stream `off .. off+cnt` that fall inside the round [base, base + round)
-__device__ __forceinline__ unsigned round_k2mask(unsigned k2mask, int off, int cnt, int base, int round) {
-    const int ilo = max(off, base), ihi = min(off + cnt, base + round);
-    const int sh = ilo - off;
-    if (ihi <= ilo || sh >= 32 || k2mask == 0u) {
-        return 0u;
+// publish_components: a stream tells the block how many oscillator slots it needs this frame and appends its
+// phase-interpolated harmonics to the block's work list (any order: every item writes its own tile column).
+__device__ __forceinline__ void publish_components(BlockShared* bs, int parity, const WarpWS& ws, int go, int warp, int lane) {
+    if (lane == 0) {
+        bs->cnt[parity][warp] = go ? ws.ncomp : 0;
     }
-    unsigned m = k2mask >> sh;
-    if (ihi - ilo < 32) {
-        m &= (1u << (ihi - ilo)) - 1u;
+    const unsigned m = go ? ws.k2mask : 0u;
+    if (m) {
+        const int n = __popc(m);
+        int at = 0;
+        if (lane == 0) {
+            at = atomicAdd(&bs->n_interp[parity], n);
+        }
+        at = __shfl_sync(FULL, at, 0);
+        if (lane < n) {
+            bs->interp[parity][at + lane] = (unsigned short)((warp << 8) | __fns(m, 0, lane + 1));
+        }
     }
-    return m;
 }
 
 // Oscillator tile: 32 samples x 32 slots, no padding.  Slot column c of sample row n lives at
@@ -947,10 +952,17 @@ __device__ __forceinline__ int tile_at(int n, int c) { return n * 32 + (c ^ ((n 
 //            each) from whichever tiles they landed in.
 // So oscillator work is spread evenly over the block no matter how the components are distributed
 // over streams, and a stream's additions keep the reference's order.
-__device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const int* cnt, const BlockTables* bt,
+__device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, BlockShared* bs, int parity, const BlockTables* bt,
                                                   StageTimer& tm, int warp, int lane) {
     constexpr int W = WARPS_PER_BLOCK;
+    static_assert(W <= 16, "owner search and slot offsets are sized for at most 16 streams per block");
     WarpWS& me = wsa[warp];
+    const int* cnt = bs->cnt[parity];
+    const int n_interp = bs->n_interp[parity];
+    const unsigned short* interp = bs->interp[parity];
+    if (warp == 0 && lane == 0) {
+        bs->n_interp[parity ^ 1] = 0;  // next frame's list (its appends come after at least one more block barrier)
+    }
     // slot offsets: exclusive prefix of the counts, each rounded up to a multiple of four (every warp
     // keeps its own copy in shared memory; lanes 0..W-1 scan)
     {
@@ -965,6 +977,8 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const int* cnt, c
         }
         if (lane <= W) {
             me.off[lane] = (unsigned short)(incl - padded);  // lane W: total
+        } else if (lane < W + 3) {
+            me.off[lane] = 0xffffu;                          // sentinels for the owner search
         }
         __syncwarp();
     }
@@ -976,18 +990,27 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const int* cnt, c
     const int my_lo = off[warp], my_cnt = cnt[warp];
     const int my_hi = my_lo + ((my_cnt + 3) & ~3);
     float* tile = me.u.tile;
+    float* tcol[8];  // this lane's (= slot's) column in tile rows n = m (mod 8): tile_at(n, lane) = 32 n + (lane ^ 4m)
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        tcol[m] = tile + (lane ^ (m << 2));
+    }
 
 #pragma unroll 1
     for (int base = 0; base < total; base += 32 * W) {
         // ---- oscillator owned by this lane in this round (idle slots and interpolated ones write zeros)
         const int k = base + 32 * warp + lane;
-        int owner = -1, j = 0;
-#pragma unroll
-        for (int i = 0; i < W; ++i) {
-            if (k >= off[i] && k < off[i] + cnt[i]) {
-                owner = i;
-                j = k - off[i];
-            }
+        // owner = the last stream whose first slot is <= k (offsets are non-decreasing; empty streams share theirs
+        // with the next one), found by a branch-free binary search over the 16 offset entries
+        int owner = 0;
+        owner += (off[owner + 8] <= k) ? 8 : 0;
+        owner += (off[owner + 4] <= k) ? 4 : 0;
+        owner += (off[owner + 2] <= k) ? 2 : 0;
+        owner += (off[owner + 1] <= k) ? 1 : 0;
+        int j = k - off[owner];
+        if (owner >= W || j >= cnt[owner]) {
+            owner = -1;
+            j = 0;
         }
         float g = 0.f, c = 0.f, s = 0.f, cd = 0.f, sd = 0.f;
         const float* Wb = bt->voiced_win;
@@ -1021,52 +1044,40 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, const int* cnt, c
         STAGE_T(8);  // offsets + oscillator start states
         // this stream's slots inside the round
         const int lo = max(my_lo, base), hi = min(my_hi, base + 32 * W);
-        // interpolated harmonics of the round: every warp walks the same enumeration once and keeps every
-        // W-th item (owner stream, list position) for itself
+        // interpolated harmonics of the round: the block's work list is dealt round-robin to the warps
         int n_mine = 0;
-        {
-            unsigned any = 0;
-#pragma unroll
-            for (int i = 0; i < W; ++i) {
-                any |= wsa[i].k2mask;
-            }
-            if (any) {
-                int t = 0;
-#pragma unroll 1
-                for (int i = 0; i < W; ++i) {
-                    unsigned m = round_k2mask(wsa[i].k2mask, off[i], cnt[i], base, 32 * W);
-                    const int first = max(off[i], base) - off[i];
-                    while (m) {
-                        const int jj = __ffs(m) - 1;
-                        m &= m - 1;
-                        if ((t++ % W) == warp) {
-                            if (lane == 0) {
-                                me.interp_item[n_mine] = (unsigned short)((i << 8) | (first + jj));
-                            }
-                            ++n_mine;
-                        }
-                    }
+        for (int t = warp; t < n_interp; t += W) {
+            const int item = interp[t];
+            const int slot = off[item >> 8] + (item & 255);
+            if (slot >= base && slot < base + 32 * W) {
+                if (lane == 0) {
+                    me.interp_item[n_mine] = (unsigned short)item;
                 }
-                __syncwarp();
+                ++n_mine;
             }
         }
+        __syncwarp();
         const bool has_pass = (base + 32 * warp) < total;  // warps beyond the last slot skip phase A
 #pragma unroll 1
         for (int ch = 0; ch < 5; ++ch) {
             const float* Wc = Wb + 32 * ch;
-#pragma unroll(kOscUnroll)
-            for (int n4 = 0; has_pass && !(MBE_ABL & 2) && n4 < 8; ++n4) {
-                const float4 w4 = *reinterpret_cast<const float4*>(Wc + 4 * n4);
-                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+            if (has_pass && !(MBE_ABL & 2)) {
+                // 32 oscillator steps, fully unrolled: row n of the tile is written at tcol[n & 7] + 32 n
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (!k2lane) {
-                        tile[tile_at(4 * n4 + q, lane)] = (g * wv[q]) * c;
+                for (int n4 = 0; n4 < 8; ++n4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(Wc + 4 * n4);
+                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int n = 4 * n4 + q;
+                        if (!k2lane) {
+                            tcol[n & 7][32 * n] = (g * wv[q]) * c;
+                        }
+                        const float cn = (c * cd) - (s * sd);
+                        const float sn = (s * cd) + (c * sd);
+                        c = cn;
+                        s = sn;
                     }
-                    const float cn = (c * cd) - (s * sd);
-                    const float sn = (s * cd) + (c * sd);
-                    c = cn;
-                    s = sn;
                 }
             }
             STAGE_T(9);  // phase A
