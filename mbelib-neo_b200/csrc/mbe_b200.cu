@@ -340,7 +340,7 @@ __device__ __forceinline__ RenderState render_begin1(const Action& act, WarpWS& 
         rs.voice = 1;
         if (kind == ACT_VOICE) {
             prev_from_cur(ws, home, lane);
-            rs.rm0 = spectral_enhance(ws.cur, lane);
+            rs.rm0 = spectral_enhance(ws.cur, ws.u.dec.tmp, lane);
             rs.has_rm0 = 1;
         } else {
             // replay the last voice model (ambe3600x2450.c:808-816): cur_mp is parked in the stream's scratch image

@@ -71,17 +71,23 @@ __device__ __forceinline__ void predict_magnitudes(WarpWS& ws, const DevTables* 
         }
     }
     __syncwarp();
-    float acc = 0.f;
-    for (int l = 1; l <= cur_L; ++l) {
-        acc = acc + ws.u.dec.tmp[l];
+    // the two ordered sums over the harmonics share one loop
+    float acc = 0.f, s42 = 0.f;
+    if (ambe) {
+#pragma unroll 4
+        for (int l = 1; l <= cur_L; ++l) {
+            acc = acc + ws.u.dec.tmp[l];
+            s42 += ws.u.dec.Tl[l];
+        }
+    } else {
+#pragma unroll 4
+        for (int l = 1; l <= cur_L; ++l) {
+            acc = acc + ws.u.dec.tmp[l];
+        }
     }
     acc = ((rho / (float)cur_L) * acc);
     float big_gamma = 0.f;
     if (ambe) {
-        float s42 = 0.f;
-        for (int l = 1; l <= cur_L; ++l) {
-            s42 += ws.u.dec.Tl[l];
-        }
         s42 = s42 / (float)cur_L;
         big_gamma = cur.gamma - (0.5f * T->log2_int[cur_L]) - s42;
     }
@@ -339,17 +345,11 @@ __device__ __forceinline__ void ambe_tail(WarpWS& ws, const DevTables* T, const 
 __device__ __forceinline__ int decode_ambe2450(const unsigned dw[3], WarpWS& ws, const DevTables* T, int total_errors,
                                                int lane) {
     ParmsSmall& cur = ws.cur;
-    unsigned u0 = 0, u1 = 0, u3 = 0;
-    for (int i = 0; i < 12; ++i) {
-        u0 = (u0 << 1) | getbit(dw, i);
-    }
-    for (int i = 12; i < 24; ++i) {
-        u1 = (u1 << 1) | getbit(dw, i);
-    }
-    for (int i = 35; i < 49; ++i) {
-        u3 = (u3 << 1) | getbit(dw, i);
-    }
-    const bool tone_ok = (((u0 >> 6) & 0x3fu) == 63u) && (((u3 & 0xfu) == 0u) || (((u1 >> 8) & 0xfu) == (u1 & 0xfu)));
+    // tone frame signature (ambe3600x2450.c:474-519) straight from the packed parameter words (bit i of the
+    // frame = bit i & 31 of dw[i >> 5]): u0[11:6] = bits 0..5 all ones, u3[3:0] = bits 45..48 all zero, or the
+    // two nibbles u1[11:8] = bits 12..15 and u1[3:0] = bits 20..23 equal
+    const bool tone_ok = ((dw[0] & 0x3fu) == 0x3fu) &&
+                         ((((dw[1] >> 13) & 0xfu) == 0u) || (((dw[0] >> 12) & 0xfu) == ((dw[0] >> 20) & 0xfu)));
     if (tone_ok && total_errors < 6) {
         return 7;
     }

@@ -210,7 +210,7 @@ __device__ __forceinline__ void zero_out(WarpWS& ws, int lane) {
 }
 
 // ---- spectral amplitude enhancement (mbelib.c:412-661); returns pre-enhancement Rm0 -------------
-__device__ __forceinline__ float spectral_enhance(ParmsSmall& cur, int lane) {
+__device__ __forceinline__ float spectral_enhance(ParmsSmall& cur, float* ws_scratch, int lane) {
     const int L = cur.L;
     if (!bands_ok(L)) {
         return 0.0f;
@@ -221,20 +221,17 @@ __device__ __forceinline__ float spectral_enhance(ParmsSmall& cur, int lane) {
     }
     const float2 sc = dev_sincosf(w0);
     const float ss = sc.x, cs = sc.y;
-    // serial: cos(l*w0) by rotation, Rm0 = sum M^2, Rm1 = sum M^2 cos, all in harmonic order
-    float c = 1.0f, s = 0.0f, Rm0 = 0.0f, Rm1 = 0.0f, cw0 = 0.0f, cw1 = 0.0f;
-#pragma unroll 2
+    // serial: cos(l*w0) by rotation, Rm0 = sum M^2, Rm1 = sum M^2 cos, all in harmonic order; the cosines are
+    // parked in the (dead) decode scratch for the per-harmonic weights below
+    float* cosl = ws_scratch;
+    float c = 1.0f, s = 0.0f, Rm0 = 0.0f, Rm1 = 0.0f;
+#pragma unroll 4
     for (int l = 1; l <= L; ++l) {
         float cn = (c * cs) - (s * ss);
         float sn = (s * cs) + (c * ss);
         c = cn;
         s = sn;
-        if (l == lane + 1) {
-            cw0 = c;
-        }
-        if (l == lane + 33) {
-            cw1 = c;
-        }
+        cosl[l] = c;
         const float m = cur.Ml[l];
         const float m2 = m * m;
         Rm0 += m2;
@@ -249,7 +246,7 @@ __device__ __forceinline__ float spectral_enhance(ParmsSmall& cur, int lane) {
         if (l <= L) {
             float M = cur.Ml[l];
             if (M != 0.0f) {
-                const float cosw = r ? cw1 : cw0;
+                const float cosw = cosl[l];
                 float W = sqrtf(M)
                           * sqrtf(sqrtf(((0.96f * MBE_PI_F) * ((R2m0 + R2m1) - ((2.0f * Rm0) * Rm1 * cosw)))
                                         / ((w0 * Rm0) * (R2m0 - R2m1))));
@@ -269,11 +266,8 @@ __device__ __forceinline__ float spectral_enhance(ParmsSmall& cur, int lane) {
     float sum = 0.0f;
 #pragma unroll 4
     for (int l = 1; l <= L; ++l) {
-        float M = cur.Ml[l];
-        if (M < 0.0f) {
-            M = -M;
-        }
-        sum += M * M;
+        const float M = cur.Ml[l];
+        sum += M * M;  // (the reference squares |M|: same product)
     }
     const float g = (sum == 0.0f) ? 1.0f : sqrtf(Rm0 / sum);
     __syncwarp();
@@ -1044,16 +1038,30 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, BlockShared* bs, 
         STAGE_T(8);  // offsets + oscillator start states
         // this stream's slots inside the round
         const int lo = max(my_lo, base), hi = min(my_hi, base + 32 * W);
-        // interpolated harmonics of the round: the block's work list is dealt round-robin to the warps
+        // interpolated harmonics of the round (one cosf per sample, about a fifth of an oscillator pass each): warps
+        // without a pass in the first round take up to three each, the rest is dealt round-robin to everybody
         int n_mine = 0;
-        for (int t = warp; t < n_interp; t += W) {
-            const int item = interp[t];
-            const int slot = off[item >> 8] + (item & 255);
-            if (slot >= base && slot < base + 32 * W) {
-                if (lane == 0) {
-                    me.interp_item[n_mine] = (unsigned short)item;
+        {
+            auto take = [&](int t) {
+                const int item = interp[t];
+                const int slot = off[item >> 8] + (item & 255);
+                if (slot >= base && slot < base + 32 * W) {
+                    if (lane == 0) {
+                        me.interp_item[n_mine] = (unsigned short)item;
+                    }
+                    ++n_mine;
                 }
-                ++n_mine;
+            };
+            const int npass0 = min(W, (total + 31) >> 5);
+            const int n_idle = W - npass0;
+            const int first_end = min(n_interp, 3 * n_idle);
+            if (warp >= npass0) {
+                for (int t = warp - npass0; t < first_end; t += n_idle) {
+                    take(t);
+                }
+            }
+            for (int t = first_end + warp; t < n_interp; t += W) {
+                take(t);
             }
         }
         __syncwarp();
