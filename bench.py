@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--codec", default="ambe3600x2450", choices=list(CODEC_NAMES.values()))
     ap.add_argument("--streams", type=int, default=65536, help="streams per GPU")
     ap.add_argument("--frames", type=int, default=50, help="frames per stream per step")
+    ap.add_argument("--soft", action="store_true", help="soft-decision input (bit + reliability per channel bit), random reliabilities")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -172,8 +173,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     S, F = args.streams, args.frames
-    workload = "%s hard-decision decode+synthesis, %d streams x %d synthetic random-bit frames per GPU" % (
-        CODEC_NAMES[codec], S, F)
+    soft = 1 if args.soft else 0
+    workload = "%s %s-decision decode+synthesis, %d streams x %d synthetic random-bit frames per GPU" % (
+        CODEC_NAMES[codec], "soft" if soft else "hard", S, F)
     config = {"workload": workload, "codec": CODEC_NAMES[codec], "streams_per_gpu": S, "frames_per_stream": F,
               "sharding": "streams/%d, no collective" % world,
               "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (S * F * (FRAME_BITS[codec] + 344) / 1e6)}
@@ -213,12 +215,15 @@ def main():
     gen = torch.Generator(device=dev)
     gen.manual_seed(0x2450 + rank)
     d_frames = torch.randint(0, 2, (S, F, fb), dtype=torch.uint8, device=dev, generator=gen)
+    if soft:  # mbe_soft_bit {bit, reliability} pairs
+        rel = torch.randint(0, 256, (S, F, fb), dtype=torch.uint8, device=dev, generator=gen)
+        d_frames = torch.stack((d_frames, rel), dim=-1).contiguous()
     d_pcm = torch.empty((S, F, 160), dtype=torch.int16, device=dev)
     d_res = torch.empty((S, F, 6), dtype=torch.int32, device=dev)
     stream = torch.cuda.Stream(device=dev)
 
     def step_dev():
-        dec.process_frames_dev(codec, 0, 0, S, F, d_frames.data_ptr(), d_pcm.data_ptr(), 0, d_res.data_ptr(), 0,
+        dec.process_frames_dev(codec, soft, 0, S, F, d_frames.data_ptr(), d_pcm.data_ptr(), 0, d_res.data_ptr(), 0,
                                stream.cuda_stream)
 
     def barrier():
@@ -261,7 +266,7 @@ def main():
     # ---- end-to-end arm: host frames in, host PCM + results out, through the host-pointer C-ABI call ----
     e2e = None
     if not args.no_e2e:
-        h_frames = torch.empty((S, F, fb), dtype=torch.uint8, pin_memory=True)
+        h_frames = torch.empty(tuple(d_frames.shape), dtype=torch.uint8, pin_memory=True)
         h_frames.copy_(d_frames)
         h_pcm = torch.empty((S, F, 160), dtype=torch.int16, pin_memory=True)
         h_res = torch.empty((S, F, 6), dtype=torch.int32, pin_memory=True)
@@ -271,7 +276,7 @@ def main():
         import ctypes
 
         def step_host():
-            rc = lib.mbe_b200_process_frames(h, codec, 0, 0, S, F, np_frames.ctypes.data_as(ctypes.c_void_p),
+            rc = lib.mbe_b200_process_frames(h, codec, soft, 0, S, F, np_frames.ctypes.data_as(ctypes.c_void_p),
                                              np_pcm.ctypes.data_as(ctypes.c_void_p), None,
                                              np_res.ctypes.data_as(ctypes.c_void_p), None)
             if rc != 0:
@@ -288,7 +293,7 @@ def main():
         e2e_s = max_over_ranks(t1 - t0)
         barrier()
         e2e = {"value": world * S * F * args.steps / e2e_s, "unit": "frames/s",
-               "h2d_bytes_per_step": int(S * F * fb), "d2h_bytes_per_step": int(S * F * (320 + RESULT_BYTES)),
+               "h2d_bytes_per_step": int(S * F * fb * (2 if soft else 1)), "d2h_bytes_per_step": int(S * F * (320 + RESULT_BYTES)),
                "ms_per_step": e2e_s * 1e3 / args.steps,
                "note": "mbe_b200_process_frames: pinned host bits in, int16 PCM + results to pinned host memory, "
                        "wall clock around the blocking calls, max over ranks"}
@@ -297,7 +302,7 @@ def main():
 
     # ---- roofline of the stream kernel ----
     hbm_peak, peak_src = measured_peaks()
-    alg_bytes = S * F * (fb + 320 + RESULT_BYTES) + 2 * S * STATE_BYTES
+    alg_bytes = S * F * (fb * (2 if soft else 1) + 320 + RESULT_BYTES) + 2 * S * STATE_BYTES
     hbm_ach = alg_bytes / (kern_ms * 1e-3) / 1e9
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     fp32_issue_peak = 148 * 128 * sm_mhz * 1e6 / 1e12  # TFLOP/s, one non-fused op per lane per clock
