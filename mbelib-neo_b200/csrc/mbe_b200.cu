@@ -386,12 +386,12 @@ __device__ __forceinline__ int render_begin2(const RenderState& rs, WarpWS& ws, 
 
 // after the overlap-add: prev_mp_enhanced <- cur_mp, and the replay path puts the parked cur_mp back
 template <bool AMBE>
-__device__ __forceinline__ void render_end(const Action& act, const RenderState& rs, WarpWS& ws, const StreamHome& home,
-                                           int lane) {
+__device__ __forceinline__ void render_end(const Action& act, const RenderState& rs, int go, WarpWS& ws,
+                                           const StreamHome& home, int lane) {
     if (!rs.voice) {
         return;
     }
-    enh_from_cur(ws, home, lane);
+    enh_from_cur(ws, home, lane, /*bulk=*/!go);
     if (AMBE && act.kind == ACT_REPLAY) {
         uint32_t* cw = reinterpret_cast<uint32_t*>(&ws.cur);
         for (int i = lane; i < HEAD_WORDS; i += 32) {
@@ -625,20 +625,21 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
         voiced_bank_block(wsa, bs, f & 1, bt, tm, warp, lane);
         STAGE_T(4);
 
-        if (go && !(MBE_ABL & 16)) {
-            synth_finish_a(ws, home.cur, T, bt, lane);
+        WolaTail tail;
+        if (go) {
+            synth_finish_a(ws, home.cur, home.enh, T, bt, lane);
         }
         MBE_STAGE_BARRIER(4);   // forward transform | shaping + backward transform
-        if (go && !(MBE_ABL & 16)) {
-            synth_finish_b(ws, bt, lane);
+        if (go) {
+            tail = synth_finish_b(ws, home.enh, bt, lane);
         }
         MBE_STAGE_BARRIER(8);   // backward transform | overlap-add, hand-over, stores
         if (live) {
             if (status >= 0) {
-                if (go && !(MBE_ABL & 16)) {
-                    synth_finish_c(ws, home.cur, home.enh, bt, lane);
+                if (go) {
+                    synth_finish_c(ws, home.cur, home.enh, tail, bt, lane);
                 }
-                render_end<AMBE>(act, rs, ws, home, lane);
+                render_end<AMBE>(act, rs, go, ws, home, lane);
                 STAGE_T(5);
                 status = fc.total;
                 rout.c0_errors = fc.c0;
@@ -734,9 +735,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
     voiced_bank_block(wsa, bs, 0, bt, tm, warp, lane);
     if (live) {
         if (go) {
-            synth_finish_a(ws, gc, T, bt, lane);
-            synth_finish_b(ws, bt, lane);
-            synth_finish_c(ws, gc, gp, bt, lane);
+            synth_finish_a(ws, gc, nullptr, T, bt, lane);
+            const WolaTail tail = synth_finish_b(ws, gp, bt, lane);
+            synth_finish_c(ws, gc, nullptr, tail, bt, lane);
         }
         __syncwarp();
         store_pcm(A, ws, (size_t)s, lane);

@@ -108,7 +108,7 @@ __device__ __forceinline__ void prev_from_cur(WarpWS& ws, const StreamHome& h, i
     bulk_copy(h.prev, h.cur, lane);
     __syncwarp();
 }
-__device__ __forceinline__ void enh_from_cur(WarpWS& ws, const StreamHome& h, int lane) {
+__device__ __forceinline__ void enh_from_cur(WarpWS& ws, const StreamHome& h, int lane, bool bulk = true) {
     const uint32_t* c = cur_words(ws);
     uint32_t* e = reinterpret_cast<uint32_t*>(&ws.enh);
 #pragma unroll
@@ -119,7 +119,9 @@ __device__ __forceinline__ void enh_from_cur(WarpWS& ws, const StreamHome& h, in
     for (int j = lane; j < ENH_HOME_WORDS; j += 32) {
         h.enh[ENH_HOME_WORD0 + j] = c[ENH_HOME_WORD0 + j];
     }
-    bulk_copy(h.enh, h.cur, lane);
+    if (bulk) {  // (the synthesis stages write prev_mp_enhanced's previousUw / noiseOverlap themselves)
+        bulk_copy(h.enh, h.cur, lane);
+    }
     __syncwarp();
 }
 __device__ __forceinline__ void cur_from_prev(WarpWS& ws, const StreamHome& h, int lane) {
@@ -372,10 +374,19 @@ __device__ __noinline__ void comfort_noise(WarpWS& ws, const DevTables* T, int l
 // ---- white noise with overlap (mbe_unvoiced_fft.c:304-341) --------------------------------------
 // noise_peek: the raw samples 1..56 of the frame's buffer (what the phase update reads) come from the
 // overlap of the previous buffer, or are zero on a cold start; nothing is advanced yet.
-__device__ __forceinline__ void noise_peek(WarpWS& ws, const float* cur_overlap, int lane) {
+// The two loads are issued early (noise_fetch) and parked in shared memory later (noise_peek) so that their HBM/L2
+// latency hides behind the adaptive smoothing.
+__device__ __forceinline__ float2 noise_fetch(const WarpWS& ws, const float* cur_overlap, int lane) {
     const bool cold = ws.cur.noiseSeed < 0.0f;
-    for (int i = lane; i < 57; i += 32) {
-        ws.u.nz[i] = cold ? 0.0f : cur_overlap[i];
+    float2 v;
+    v.x = cold ? 0.0f : cur_overlap[lane];
+    v.y = (cold || lane + 32 >= 57) ? 0.0f : cur_overlap[lane + 32];
+    return v;
+}
+__device__ __forceinline__ void noise_peek(WarpWS& ws, float2 v, int lane) {
+    ws.u.nz[lane] = v.x;
+    if (lane + 32 < 57) {
+        ws.u.nz[lane + 32] = v.y;
     }
     __syncwarp();
 }
@@ -398,8 +409,10 @@ __host__ __device__ constexpr unsigned lcg_pow_c(int k) {
 
 // make_noise: builds the frame's 256-sample buffer, advances the LCG / overlap state and writes the
 // WINDOWED buffer (noise * W256) straight into the FFT input.  cur_overlap = cur_mp->noiseOverlap in HBM.
-__device__ __forceinline__ void make_noise(WarpWS& ws, float* cur_overlap, const DevTables* T, const BlockTables* bt,
-                                           int lane) {
+// enh_overlap (may be null): prev_mp_enhanced->noiseOverlap gets the same new tail right away, which saves the
+// HBM -> HBM copy of the struct hand-over after synthesis.
+__device__ __forceinline__ void make_noise(WarpWS& ws, float* cur_overlap, float* enh_overlap, const DevTables* T,
+                                           const BlockTables* bt, int lane) {
     ParmsSmall& cur = ws.cur;
     float* A = ws.u.fft.a;
     const float seed = cur.noiseSeed;
@@ -409,6 +422,9 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, float* cur_overlap, const
         }
         for (int i = lane; i < 96; i += 32) {
             cur_overlap[i] = 0.0f;
+            if (enh_overlap) {
+                enh_overlap[i] = 0.0f;
+            }
         }
         const float ns = ws.rng.uv_override ? (float)ws.rng.uv_seed : 3147.0f;
         __syncwarp();
@@ -437,6 +453,9 @@ __device__ __forceinline__ void make_noise(WarpWS& ws, float* cur_overlap, const
         A[96 + i] = v * bt->uvwin[96 + i];
         if (i >= 64) {
             cur_overlap[i - 64] = v;  // overlap <- buffer[160..255] (same lane that read element i - 64 above)
+            if (enh_overlap) {
+                enh_overlap[i - 64] = v;
+            }
         }
     }
 #pragma unroll
@@ -820,8 +839,21 @@ __device__ __forceinline__ void unvoiced_shape(WarpWS& ws, const BlockTables* bt
     }
 }
 
-__device__ __forceinline__ void unvoiced_overlap(WarpWS& ws, float* cur_uw, const float* enh_uw, const BlockTables* bt,
-                                                 int lane) {
+// wola_fetch: the previous frame's tail prev_mp_enhanced->previousUw[128..255], fetched before the backward
+// transform so that the loads are back when the overlap-add needs them
+struct WolaTail { float ps[4]; };
+__device__ __forceinline__ WolaTail wola_fetch(const float* enh_uw, int lane) {
+    WolaTail t;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        t.ps[c] = enh_uw[128 + 32 * c + lane];
+    }
+    return t;
+}
+
+// enh_uw_out (may be null): prev_mp_enhanced->previousUw receives the new block together with cur_mp->previousUw
+__device__ __forceinline__ void unvoiced_overlap(WarpWS& ws, float* cur_uw, float* enh_uw_out, const WolaTail& tail,
+                                                 const BlockTables* bt, int lane) {
     const float* A = ws.u.fft.a;
     const float inv = 1.0f / (float)NFFT;
     // weighted overlap-add of this frame's block (scaled by 1/N as it is read) with the previous frame's,
@@ -830,7 +862,7 @@ __device__ __forceinline__ void unvoiced_overlap(WarpWS& ws, float* cur_uw, cons
     for (int c = 0; c < 5; ++c) {
         const int n = 32 * c + lane;
         const float den = bt->wola_den[n];
-        const float ps = (n + 128 < NFFT) ? enh_uw[n + 128] : 0.0f;
+        const float ps = (c < 4) ? tail.ps[c < 4 ? c : 0] : 0.0f;
         const float cs = (n - 32 >= 0) ? (A[n - 32] * inv) : 0.0f;
         float v = ws.out[n];
         if (den > 1e-10f) {
@@ -846,7 +878,11 @@ __device__ __forceinline__ void unvoiced_overlap(WarpWS& ws, float* cur_uw, cons
     // hand the block to the state
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        cur_uw[32 * c + lane] = A[32 * c + lane] * inv;
+        const float v = A[32 * c + lane] * inv;
+        cur_uw[32 * c + lane] = v;
+        if (enh_uw_out) {
+            enh_uw_out[32 * c + lane] = v;
+        }
     }
     __syncwarp();
 }
@@ -1164,6 +1200,7 @@ __device__ __noinline__ int synth_begin(WarpWS& ws, const float* cur_overlap, co
         __syncwarp();
         return 0;  // silence
     }
+    const float2 nz01 = noise_fetch(ws, cur_overlap, lane);
     adaptive_smoothing(cur, prev, has_rm0, rm0, lane);
 
     const bool mute_on_rate = fabsf(cur.mutingThreshold - 0.096f) > 1e-6f;
@@ -1172,7 +1209,7 @@ __device__ __noinline__ int synth_begin(WarpWS& ws, const float* cur_overlap, co
         __syncwarp();
         return 0;
     }
-    noise_peek(ws, cur_overlap, lane);
+    noise_peek(ws, nz01, lane);
 
     // bands present in only one frame fade as zero-amplitude voiced bands (mbelib.c:912-929)
     int maxl;
@@ -1228,17 +1265,24 @@ __device__ __noinline__ int synth_begin(WarpWS& ws, const float* cur_overlap, co
     return 1;
 }
 
-// synth_finish_*: unvoiced FFT/WOLA synthesis on top of the voiced samples and the soft clip, in three stages
-__device__ __noinline__ void synth_finish_a(WarpWS& ws, uint32_t* cur_home, const DevTables* T, const BlockTables* bt,
-                                            int lane) {
-    make_noise(ws, reinterpret_cast<float*>(cur_home + OVERLAP_WORD), T, bt, lane);
+// synth_finish_*: unvoiced FFT/WOLA synthesis on top of the voiced samples and the soft clip, in three stages.
+// enh_home_out: the stream's prev_mp_enhanced image when it is about to become a copy of cur_mp (stream kernel), null
+// when the caller keeps its previous-frame blob (batched mbe_synthesizeSpeech).
+__device__ __noinline__ void synth_finish_a(WarpWS& ws, uint32_t* cur_home, uint32_t* enh_home_out, const DevTables* T,
+                                            const BlockTables* bt, int lane) {
+    make_noise(ws, reinterpret_cast<float*>(cur_home + OVERLAP_WORD),
+               enh_home_out ? reinterpret_cast<float*>(enh_home_out + OVERLAP_WORD) : nullptr, T, bt, lane);
     unvoiced_analyse(ws, bt, lane);
 }
-__device__ __noinline__ void synth_finish_b(WarpWS& ws, const BlockTables* bt, int lane) { unvoiced_shape(ws, bt, lane); }
-__device__ __noinline__ void synth_finish_c(WarpWS& ws, uint32_t* cur_home, const uint32_t* enh_home, const BlockTables* bt,
-                                            int lane) {
-    unvoiced_overlap(ws, reinterpret_cast<float*>(cur_home + UW_WORD), reinterpret_cast<const float*>(enh_home + UW_WORD), bt,
-                     lane);
+__device__ __forceinline__ WolaTail synth_finish_b(WarpWS& ws, const uint32_t* enh_home, const BlockTables* bt, int lane) {
+    const WolaTail tail = wola_fetch(reinterpret_cast<const float*>(enh_home + UW_WORD), lane);
+    unvoiced_shape(ws, bt, lane);
+    return tail;
+}
+__device__ __forceinline__ void synth_finish_c(WarpWS& ws, uint32_t* cur_home, uint32_t* enh_home_out, const WolaTail& tail,
+                                               const BlockTables* bt, int lane) {
+    unvoiced_overlap(ws, reinterpret_cast<float*>(cur_home + UW_WORD),
+                     enh_home_out ? reinterpret_cast<float*>(enh_home_out + UW_WORD) : nullptr, tail, bt, lane);
 }
 
 // ---- tone synthesis (mbelib.c:692-856, src/internal/mbe_tone.h) -----------------------------------
