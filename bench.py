@@ -39,6 +39,10 @@ FRAME_BITS = {0: 184, 1: 168, 2: 96, 3: 96}
 # algorithmic FLOP per frame on iid random-bit frames (non-fused, mul = add = 1)
 FLOP_PER_FRAME = {0: 84e3, 1: 84e3, 2: 66e3, 3: 61e3}
 STATE_BYTES = 7828  # 3 x mbe_parms + 16 B RNG words per stream
+# DRAM traffic of the stream kernel per frame, measured: dram__bytes_read.sum + dram__bytes_write.sum of one
+# `ncu --set full` capture (profiles/r01h_stream_kernel_ncu_details.txt: 172.4 MB + 369.9 MB for 16576 streams x 50
+# frames of AMBE+2 hard-decision input) divided by the frames of that launch.  Only quoted for that workload.
+NCU_DRAM_BYTES_PER_FRAME = {("ambe3600x2450", 0): (172.365568e6 + 369.898496e6) / (16576 * 50)}
 RESULT_BYTES = 24
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -308,8 +312,12 @@ def main():
     fp32_issue_peak = 148 * 128 * sm_mhz * 1e6 / 1e12  # TFLOP/s, one non-fused op per lane per clock
     flops = S * F * FLOP_PER_FRAME[codec]
     fp32_ach = flops / (kern_ms * 1e-3) / 1e12
+    per_frame_dram = NCU_DRAM_BYTES_PER_FRAME.get((CODEC_NAMES[codec], soft))
     roofline = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "mbe_stream_kernel",
+                "traffic": (per_frame_dram * S * F) if per_frame_dram else None,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per frame (profiles/r01h_*) x frames per launch"
+                if per_frame_dram else None,
+                "peak_source": peak_src, "kernel": "mbe_stream_kernel",
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms,
                 "note": "the kernel is FP32-issue bound, not HBM bound (no dense contraction, ~1 KB/frame); see roofline_fp32"}
     roofline_fp32 = {"bound": "fp32-issue", "achieved": fp32_ach, "peak": fp32_issue_peak, "unit": "TFLOP/s",

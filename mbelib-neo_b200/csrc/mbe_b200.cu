@@ -1491,14 +1491,24 @@ static int ensure(mbe_b200_ctx* ctx, void** p, size_t* cap, size_t need) {
 }
 
 // Streams per pipeline chunk: whole waves of the stream kernel (2 blocks per SM x 148 SMs x WARPS_PER_BLOCK
-// streams), about eight chunks per batch, so the first copy-in and the last copy-out are the only exposed
+// streams), about sixteen chunks per batch, so the first copy-in and the last copy-out are the only exposed
 // transfers.
+constexpr int PIPELINE_CHUNKS = 16;
 static int pipeline_chunk_streams(int n_streams) {
     const int wave = 2 * 148 * WARPS_PER_BLOCK;
     if (n_streams <= 2 * wave) {
         return n_streams;
     }
-    int chunk = (n_streams + 7) / 8;
+    // MBE_B200_CHUNKS (environment): target number of pipeline chunks per call (tuning knob)
+    static int target = 0;
+    if (target == 0) {
+        const char* e = getenv("MBE_B200_CHUNKS");
+        target = e ? atoi(e) : 0;
+        if (target < 1 || target > MAX_CHUNKS) {
+            target = PIPELINE_CHUNKS;
+        }
+    }
+    int chunk = (n_streams + target - 1) / target;
     chunk = ((chunk + wave - 1) / wave) * wave;
     while ((n_streams + chunk - 1) / chunk > MAX_CHUNKS) {
         chunk += wave;
