@@ -102,6 +102,25 @@ MBE_B200_API int mbe_b200_process_frames(mbe_b200_ctx* ctx, int codec, int soft,
                                          int n_frames, const uint8_t* frames, int16_t* pcm, float* pcmf,
                                          mbe_b200_result* results, uint8_t* bits);
 
+/* Float PCM scale.  By default every `pcmf` output is in the reference's historical float scale
+ * (roughly int16/7, what mbe_process<Codec>Framef returns).  With enable != 0 the samples are multiplied by
+ * (7.0f / 32768.0f) on store, the normalisation include/mbelib-neo/mbelib.h:16-20 documents (about [-0.95, +0.95]
+ * after the soft clip).  int16 outputs are not affected. */
+MBE_B200_API int mbe_b200_set_normalized_float(mbe_b200_ctx* ctx, int enable);
+
+/* Bit-packed channel frames: the same hard-decision frames with eight channel bits per byte instead of
+ * the reference's one `char` per bit (README.md:171-178 of the reference).  Bit k = r*cols + c of `fr[r][c]` is bit
+ * 7 - (k & 7) of byte k >> 3 (MSB first); a frame takes mbe_b200_packed_frame_bytes(codec) = 23 / 21 / 12 / 12 bytes.
+ * Semantics per frame are those of mbe_process<Codec>Frame[f]; a packed bit can only be 0 or 1, so
+ * MBE_STATUS_INVALID_BITS cannot occur. */
+MBE_B200_API int mbe_b200_packed_frame_bytes(int codec);
+MBE_B200_API int mbe_b200_process_frames_packed_dev(mbe_b200_ctx* ctx, int codec, int first_stream, int n_streams,
+                                                    int n_frames, const uint8_t* d_packed, int16_t* d_pcm, float* d_pcmf,
+                                                    mbe_b200_result* d_results, uint8_t* d_bits, void* cuda_stream);
+MBE_B200_API int mbe_b200_process_frames_packed(mbe_b200_ctx* ctx, int codec, int first_stream, int n_streams,
+                                                int n_frames, const uint8_t* packed, int16_t* pcm, float* pcmf,
+                                                mbe_b200_result* results, uint8_t* bits);
+
 /* ---- stage-split entry points ----------------------------------------------------------------
  * decode_frames: batched mbe_decode<Codec>[Soft]Frame (mbelib.h:315,323,395,403,471,479,545,553):
  *   ECC + PN de-scrambling only; stateless; n = number of frames; bits [n][param_bits] one byte per bit.

@@ -33,7 +33,8 @@ _EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b
             "mbe_b200_export_rng", "mbe_b200_import_rng", "mbe_b200_process_frames_dev", "mbe_b200_process_frames",
             "mbe_b200_decode_frames_dev", "mbe_b200_decode_frames", "mbe_b200_process_data_dev",
             "mbe_b200_process_data", "mbe_b200_synthesize_speech", "mbe_b200_floattoshort",
-            "mbe_b200_floattoshort_dev", "mbe_b200_synchronize", "mbe_b200_debug_stage_cycles"]
+            "mbe_b200_floattoshort_dev", "mbe_b200_synchronize", "mbe_b200_debug_stage_cycles",
+            "mbe_b200_set_normalized_float", "mbe_b200_packed_frame_bytes", "mbe_b200_process_frames_packed_dev", "mbe_b200_process_frames_packed"]
 
 _lib = None
 
@@ -69,6 +70,10 @@ def load_library():
             getattr(lib, "mbe_b200_" + n).argtypes = [vp, ci, ci, vp]
         lib.mbe_b200_process_frames_dev.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
         lib.mbe_b200_process_frames.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp]
+        lib.mbe_b200_set_normalized_float.argtypes = [vp, ci]
+        lib.mbe_b200_packed_frame_bytes.argtypes = [ci]
+        lib.mbe_b200_process_frames_packed_dev.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
+        lib.mbe_b200_process_frames_packed.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]
         lib.mbe_b200_decode_frames_dev.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp]
         lib.mbe_b200_decode_frames.argtypes = [vp, ci, ci, ci, vp, vp, vp]
         lib.mbe_b200_process_data_dev.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]
@@ -80,6 +85,18 @@ def load_library():
         lib.mbe_b200_debug_stage_cycles.argtypes = [vp, vp, ci]
         _lib = lib
     return _lib
+
+
+def packed_frame_bytes(codec):
+    return (FRAME_BITS[codec] + 7) // 8
+
+
+def pack_frames(codec, frames):
+    """uint8 [..., frame_bits] of 0/1 (the reference's char fr[rows][cols], row-major) -> uint8 [..., packed bytes],
+    MSB first (host-side data preparation only; the decoding happens in the library)."""
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    assert frames.shape[-1] == FRAME_BITS[codec]
+    return np.packbits(frames, axis=-1, bitorder="big")
 
 
 def _p(a):
@@ -162,6 +179,28 @@ class Decoder:
         self._check(self.lib.mbe_b200_process_frames(self.h, codec, int(bool(soft)), first_stream, S, F, _p(frames),
                                                      _p(pcm), _p(pcmf), _p(res), _p(bits)), "process_frames")
         return dict(pcm=pcm, pcmf=pcmf, results=res, bits=bits)
+
+    def set_normalized_float(self, enable):
+        self._check(self.lib.mbe_b200_set_normalized_float(self.h, int(bool(enable))), "set_normalized_float")
+
+    def process_frames_packed(self, codec, packed, first_stream=0, want_float=False, want_bits=True, want_results=True):
+        """packed: uint8 [S][F][packed_frame_bytes(codec)] hard bits, eight per byte, MSB first (see pack_frames)."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        S, F = packed.shape[0], packed.shape[1]
+        pcm = np.zeros((S, F, SAMPLES), np.int16)
+        pcmf = np.zeros((S, F, SAMPLES), np.float32) if want_float else None
+        res = np.zeros((S, F), RESULT_DTYPE) if want_results else None
+        bits = np.zeros((S, F, PARAM_BITS[codec]), np.uint8) if want_bits else None
+        self._check(self.lib.mbe_b200_process_frames_packed(self.h, codec, first_stream, S, F, _p(packed), _p(pcm),
+                                                            _p(pcmf), _p(res), _p(bits)), "process_frames_packed")
+        return dict(pcm=pcm, pcmf=pcmf, results=res, bits=bits)
+
+    def process_frames_packed_dev(self, codec, first_stream, n_streams, n_frames, d_packed, d_pcm, d_pcmf=0,
+                                  d_results=0, d_bits=0, cuda_stream=0):
+        self._check(self.lib.mbe_b200_process_frames_packed_dev(self.h, codec, first_stream, n_streams, n_frames,
+                                                                _p(d_packed), _p(d_pcm or None), _p(d_pcmf or None),
+                                                                _p(d_results or None), _p(d_bits or None),
+                                                                _p(cuda_stream or None)), "process_frames_packed_dev")
 
     def process_frames_dev(self, codec, soft, first_stream, n_streams, n_frames, d_frames, d_pcm, d_pcmf=0,
                            d_results=0, d_bits=0, cuda_stream=0):

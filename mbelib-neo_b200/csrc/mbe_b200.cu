@@ -433,7 +433,7 @@ __device__ __forceinline__ void store_pcm(const LaunchArgs& A, const WarpWS& ws,
         const size_t o = frame_idx * NS + 32 * ch + lane;
         const float v = ws.out[32 * ch + lane];
         if (A.pcmf) {
-            A.pcmf[o] = v;
+            A.pcmf[o] = v * A.pcmf_scale;  // x 1.0f is exact: the default is the reference's float scale
         }
         if (A.pcm) {
             A.pcm[o] = float_to_short(v);
@@ -488,7 +488,8 @@ __device__ __forceinline__ void store_stream(const WarpWS& ws, uint32_t* gs, int
 }
 
 // =====================================================================================================
-// The stream kernel: CODEC in {0..3}, SOFT in {0,1}, MODE in {MODE_FRAMES, MODE_DATA}
+// The stream kernel: CODEC in {0..3}, SOFT in {0 hard bytes, 1 soft bits, 2 hard bits packed 8 per byte},
+// MODE in {MODE_FRAMES, MODE_DATA}
 // One block = WARPS_PER_BLOCK streams walking their frames in lockstep (see WARPS_PER_BLOCK).
 // =====================================================================================================
 template <int CODEC, int SOFT, int MODE>
@@ -511,7 +512,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
     constexpr bool AMBE = (CODEC >= MBE_B200_AMBE3600X2400);
     constexpr int fbits = (CODEC == MBE_B200_IMBE7200X4400) ? 184 : (CODEC == MBE_B200_IMBE7100X4400 ? 168 : 96);
     constexpr int pbits = AMBE ? 49 : 88;
-    constexpr size_t fstride = (MODE == MODE_DATA) ? (size_t)pbits : (size_t)fbits * (SOFT ? 2u : 1u);
+    constexpr bool PACKED = (SOFT == 2);
+    constexpr size_t fstride = (MODE == MODE_DATA) ? (size_t)pbits
+                                                   : (PACKED ? (size_t)((fbits + 7) / 8) : (size_t)fbits * (SOFT == 1 ? 2u : 1u));
 
     uint32_t* gs = A.state + (size_t)(A.first_stream + (live ? s : 0)) * STATE_WORDS;
     const StreamHome home = {gs, gs + PARMS_WORDS, gs + 2 * PARMS_WORDS, gs + SPILL_WORD};
@@ -547,7 +550,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
         if (live) {
             const uint8_t* fr = A.frames + idx * fstride;
             if (MODE == MODE_FRAMES) {
-                FrontResult R = front_end(CODEC, SOFT, fr, dw, ws.u.dec.rel, ws.u.dec.cost, ws.u.dec.rowbits, T, lane);
+                FrontResult R = front_end(CODEC, SOFT == 1, PACKED, fr, dw, ws.u.dec.rel, ws.u.dec.cost, ws.u.dec.rowbits, T, lane);
                 status = R.status;
                 fc.total = R.c0 + R.prot;
                 fc.c0 = R.c0;
@@ -769,7 +772,7 @@ __global__ void __launch_bounds__(256) mbe_decode_kernel(int n, const uint8_t* _
     constexpr int fbits = (CODEC == MBE_B200_IMBE7200X4400) ? 184 : (CODEC == MBE_B200_IMBE7100X4400 ? 168 : 96);
     constexpr int pbits = (CODEC <= MBE_B200_IMBE7100X4400) ? 88 : 49;
     unsigned dw[3];
-    FrontResult R = front_end(CODEC, SOFT, frames + (size_t)i * fbits * (SOFT ? 2 : 1), dw, rel[warp],
+    FrontResult R = front_end(CODEC, SOFT, 0, frames + (size_t)i * fbits * (SOFT ? 2 : 1), dw, rel[warp],
                               cost[SOFT ? warp : 0], rows[warp], T, lane);
     if (bits && R.status >= 0) {
 #pragma unroll
@@ -863,6 +866,7 @@ constexpr int MAX_CHUNKS = 32;
 struct mbe_b200_ctx {
     int device;
     int max_streams;
+    int normalized_float;  // float PCM outputs scaled by 7/32768 (mbelib.h:16-20) instead of the historical scale
     uint32_t* d_state;
     DevTables* d_tab;
     cudaStream_t stream;
@@ -1110,6 +1114,14 @@ static StreamKernelFn pick_stream_kernel(int codec, int soft, int mode) {
             default: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 0, MODE_DATA>;
         }
     }
+    if (soft == 2) {  // packed hard bits
+        switch (codec) {
+            case MBE_B200_IMBE7200X4400: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 2, MODE_FRAMES>;
+            case MBE_B200_IMBE7100X4400: return mbe_stream_kernel<MBE_B200_IMBE7100X4400, 2, MODE_FRAMES>;
+            case MBE_B200_AMBE3600X2400: return mbe_stream_kernel<MBE_B200_AMBE3600X2400, 2, MODE_FRAMES>;
+            default: return mbe_stream_kernel<MBE_B200_AMBE3600X2450, 2, MODE_FRAMES>;
+        }
+    }
     switch (codec * 2 + (soft ? 1 : 0)) {
         case 0: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 0, MODE_FRAMES>;
         case 1: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 1, MODE_FRAMES>;
@@ -1208,8 +1220,8 @@ int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams) {
     CUC(cudaMalloc(&ctx->d_dbg, 16 * sizeof(unsigned long long)));
     CUC(cudaMemset(ctx->d_dbg, 0, 16 * sizeof(unsigned long long)));
     for (int codec = 0; codec < 4; ++codec) {
-        for (int soft = 0; soft < 2; ++soft) {
-            for (int mode = 0; mode < 2; ++mode) {
+        for (int soft = 0; soft < 3; ++soft) {
+            for (int mode = 0; mode < (soft == 2 ? 1 : 2); ++mode) {
                 CUC(cudaFuncSetAttribute(pick_stream_kernel(codec, soft, mode), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)stream_kernel_smem()));
             }
@@ -1361,7 +1373,9 @@ int mbe_b200_import_rng(mbe_b200_ctx* ctx, int first, int count, const uint32_t*
     return state_xfer(ctx, first, count, const_cast<uint32_t*>(rng_words4), RNG_WORDS, 3 * PARMS_WORDS, 0);
 }
 
-static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a, cudaStream_t st) {
+static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaStream_t st) {
+    LaunchArgs a = a_in;
+    a.pcmf_scale = ctx->normalized_float ? (7.0f / 32768.0f) : 1.0f;
     const int blocks = (a.n_streams + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     if (a.mode == MODE_SYNTH) {
         mbe_synth_kernel<<<blocks, WARPS_PER_BLOCK * 32, stream_kernel_smem(), st>>>(a);
@@ -1373,9 +1387,45 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a, cudaStre
     return 0;
 }
 
+// input kinds of the frame entry points: 0 = one byte per hard bit, 1 = mbe_soft_bit pairs, 2 = hard bits packed
+static int frames_dev_impl(mbe_b200_ctx* ctx, int codec, int kind, int first_stream, int n_streams, int n_frames,
+                           const uint8_t* d_frames, int16_t* d_pcm, float* d_pcmf, mbe_b200_result* d_results,
+                           uint8_t* d_bits, void* cuda_stream);
+
 int mbe_b200_process_frames_dev(mbe_b200_ctx* ctx, int codec, int soft, int first_stream, int n_streams, int n_frames,
                                 const uint8_t* d_frames, int16_t* d_pcm, float* d_pcmf, mbe_b200_result* d_results,
                                 uint8_t* d_bits, void* cuda_stream) {
+    return frames_dev_impl(ctx, codec, soft ? 1 : 0, first_stream, n_streams, n_frames, d_frames, d_pcm, d_pcmf, d_results,
+                           d_bits, cuda_stream);
+}
+
+int mbe_b200_process_frames_packed_dev(mbe_b200_ctx* ctx, int codec, int first_stream, int n_streams, int n_frames,
+                                       const uint8_t* d_packed, int16_t* d_pcm, float* d_pcmf, mbe_b200_result* d_results,
+                                       uint8_t* d_bits, void* cuda_stream) {
+    return frames_dev_impl(ctx, codec, 2, first_stream, n_streams, n_frames, d_packed, d_pcm, d_pcmf, d_results, d_bits,
+                           cuda_stream);
+}
+
+int mbe_b200_set_normalized_float(mbe_b200_ctx* ctx, int enable) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    ctx->normalized_float = enable ? 1 : 0;
+    return 0;
+}
+
+int mbe_b200_packed_frame_bytes(int codec) {
+    int fb, pb;
+    if (mbe_b200_geometry(codec, &fb, &pb) != 0) {
+        return MBE_B200_E_ARG;
+    }
+    return (fb + 7) / 8;
+}
+
+static int frames_dev_impl(mbe_b200_ctx* ctx, int codec, int kind, int first_stream, int n_streams, int n_frames,
+                           const uint8_t* d_frames, int16_t* d_pcm, float* d_pcmf, mbe_b200_result* d_results,
+                           uint8_t* d_bits, void* cuda_stream) {
+    const int soft = kind;
     int rc = check_range(ctx, first_stream, n_streams);
     if (rc < 0) {
         return rc;
@@ -1390,7 +1440,7 @@ int mbe_b200_process_frames_dev(mbe_b200_ctx* ctx, int codec, int soft, int firs
     LaunchArgs a;
     memset(&a, 0, sizeof(a));
     a.codec = codec;
-    a.soft = soft ? 1 : 0;
+    a.soft = soft;
     a.mode = MODE_FRAMES;
     a.first_stream = first_stream;
     a.n_streams = n_streams;
@@ -1516,7 +1566,21 @@ static int pipeline_chunk_streams(int n_streams) {
     return chunk;
 }
 
+static int frames_host_impl(mbe_b200_ctx* ctx, int codec, int kind, int first_stream, int n_streams, int n_frames,
+                            const uint8_t* frames, int16_t* pcm, float* pcmf, mbe_b200_result* results, uint8_t* bits);
+
 int mbe_b200_process_frames(mbe_b200_ctx* ctx, int codec, int soft, int first_stream, int n_streams, int n_frames,
+                            const uint8_t* frames, int16_t* pcm, float* pcmf, mbe_b200_result* results, uint8_t* bits) {
+    return frames_host_impl(ctx, codec, soft ? 1 : 0, first_stream, n_streams, n_frames, frames, pcm, pcmf, results, bits);
+}
+
+int mbe_b200_process_frames_packed(mbe_b200_ctx* ctx, int codec, int first_stream, int n_streams, int n_frames,
+                                   const uint8_t* packed, int16_t* pcm, float* pcmf, mbe_b200_result* results,
+                                   uint8_t* bits) {
+    return frames_host_impl(ctx, codec, 2, first_stream, n_streams, n_frames, packed, pcm, pcmf, results, bits);
+}
+
+static int frames_host_impl(mbe_b200_ctx* ctx, int codec, int kind, int first_stream, int n_streams, int n_frames,
                             const uint8_t* frames, int16_t* pcm, float* pcmf, mbe_b200_result* results, uint8_t* bits) {
     int rc = check_range(ctx, first_stream, n_streams);
     if (rc < 0) {
@@ -1532,7 +1596,7 @@ int mbe_b200_process_frames(mbe_b200_ctx* ctx, int codec, int soft, int first_st
     CU(cudaSetDevice(ctx->device));
     int fb, pb;
     mbe_b200_geometry(codec, &fb, &pb);
-    const size_t in_per_frame = (size_t)fb * (soft ? 2 : 1);
+    const size_t in_per_frame = (kind == 2) ? (size_t)((fb + 7) / 8) : (size_t)fb * (kind == 1 ? 2 : 1);
     const size_t per_frame[4] = {pcm ? NS * sizeof(int16_t) : 0, pcmf ? NS * sizeof(float) : 0,
                                  results ? sizeof(mbe_b200_result) : 0, bits ? (size_t)pb : 0};
     if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, nf * in_per_frame)) < 0) {
@@ -1561,8 +1625,8 @@ int mbe_b200_process_frames(mbe_b200_ctx* ctx, int codec, int soft, int first_st
                            cudaMemcpyHostToDevice, ctx->s_in));
         CU(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
         CU(cudaStreamWaitEvent(sk, ctx->ev_in[c], 0));
-        rc = mbe_b200_process_frames_dev(
-            ctx, codec, soft, first_stream + s0, ns, n_frames, (const uint8_t*)ctx->d_in + f0 * in_per_frame,
+        rc = frames_dev_impl(
+            ctx, codec, kind, first_stream + s0, ns, n_frames, (const uint8_t*)ctx->d_in + f0 * in_per_frame,
             pcm ? (int16_t*)ctx->d_out[0] + f0 * NS : nullptr, pcmf ? (float*)ctx->d_out[1] + f0 * NS : nullptr,
             results ? (mbe_b200_result*)ctx->d_out[2] + f0 : nullptr, bits ? (uint8_t*)ctx->d_out[3] + f0 * pb : nullptr, sk);
         if (rc < 0) {

@@ -195,6 +195,7 @@ struct LaunchArgs {
     uint32_t* synth_prev;
     const uint32_t* synth_seeds;
     unsigned long long* dbg;    // MBE_STAGE_TIMING builds: 16 accumulated per-stage cycle counters
+    float pcmf_scale;           // float PCM is multiplied by this on store: 1 (reference scale) or 7/32768 (normalised)
 };
 
 

@@ -132,7 +132,8 @@ __device__ __forceinline__ unsigned getbit(const unsigned dw[3], int i) {
 //   ws_rel  : per-warp scratch for reliabilities (8*24 bytes)
 //   rb      : per-warp scratch, 8 words (corrected rows, so that lanes can index them dynamically)
 //   cost_tab: per-warp scratch, 640 uint16 (soft only)
-__device__ __forceinline__ FrontResult front_end(int codec, int soft, const uint8_t* __restrict__ fr, unsigned dw[3],
+//   packed  : hard bits packed eight per byte, MSB first, in the row-major order of the reference's fr[rows][cols]
+__device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed, const uint8_t* __restrict__ fr, unsigned dw[3],
                                                  unsigned char* ws_rel, unsigned short* cost_tab, unsigned* rb,
                                                  const DevTables* T, int lane) {
     FrontResult R;
@@ -149,6 +150,8 @@ __device__ __forceinline__ FrontResult front_end(int codec, int soft, const uint
             if (soft) {
                 v = fr[2 * idx];
                 ws_rel[r * 24 + lane] = fr[2 * idx + 1];
+            } else if (packed) {
+                v = ((unsigned)fr[idx >> 3] >> (7 - (idx & 7))) & 1u;
             } else {
                 v = fr[idx];
             }

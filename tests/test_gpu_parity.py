@@ -257,3 +257,45 @@ def test_process_data_without_context_uses_fallback_repeat_rules(dec):
             o.mbo_process_data(codec, T._ptr(out), None, T._ptr(d), T._ptr(cur), T._ptr(prev), T._ptr(enh), T._ptr(rng))
             o.mbo_float_to_short(T._ptr(out), T._ptr(sh))
             assert np.abs(sh.astype(np.int32) - got["pcm"][s, f].astype(np.int32)).max() <= PCM_MAX_LSB
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("codec", [0, 1, 2, 3])
+def test_packed_frames_equal_unpacked(dec, pkg, codec):
+    """bit-packed channel frames give exactly what the one-byte-per-bit frames give (and the oracle)."""
+    S, F = 96, 12
+    frames = T.random_hard_frames(codec, S, F, 0x9ACC + codec)
+    seeds = T.stream_seeds(S, 77)
+    dec.init_streams(0, S, seeds)
+    a = dec.process_frames(codec, frames, want_float=True)
+    sa = dec.export_state(0, S)
+    dec.init_streams(0, S, seeds)
+    packed = pkg.pack_frames(codec, frames)
+    assert packed.shape[-1] == pkg.packed_frame_bytes(codec) == dec.lib.mbe_b200_packed_frame_bytes(codec)
+    b = dec.process_frames_packed(codec, packed, want_float=True)
+    sb = dec.export_state(0, S)
+    assert np.array_equal(a["pcm"], b["pcm"]) and np.array_equal(a["pcmf"].view(np.uint32), b["pcmf"].view(np.uint32))
+    assert np.array_equal(a["bits"], b["bits"]) and np.array_equal(a["results"], b["results"])
+    assert np.array_equal(sa, sb)
+    want = T.run_cpu(T.load_oracle().mbo_run, codec, 0, frames, seeds, n_threads=8)
+    assert np.array_equal(b["pcm"], want["pcm"]) and np.array_equal(b["bits"], want["bits"])
+
+
+@pytest.mark.gpu
+def test_normalized_float_output(dec):
+    """normalised float PCM = reference-scale float PCM x (7/32768), int16 PCM unchanged."""
+    codec, S, F = 3, 64, 8
+    frames = T.random_hard_frames(codec, S, F, 0x7F10)
+    seeds = T.stream_seeds(S, 5)
+    dec.init_streams(0, S, seeds)
+    a = dec.process_frames(codec, frames, want_float=True)
+    dec.init_streams(0, S, seeds)
+    dec.set_normalized_float(True)
+    try:
+        b = dec.process_frames(codec, frames, want_float=True)
+    finally:
+        dec.set_normalized_float(False)
+    assert np.array_equal(a["pcm"], b["pcm"])
+    want = a["pcmf"] * np.float32(7.0 / 32768.0)
+    assert np.array_equal(want.view(np.uint32), b["pcmf"].view(np.uint32))
+    assert np.abs(b["pcmf"]).max() <= 0.951
