@@ -92,7 +92,10 @@ MBE_B200_API int mbe_b200_import_rng(mbe_b200_ctx* ctx, int first_stream, int co
  * Batched mbe_process<Codec>Frame / Framef / SoftFrame / SoftFramef
  * (mbelib.h:352-373, 429-447, 505-523, 564-582).  Streams first_stream .. first_stream+n_streams-1 each
  * consume n_frames consecutive frames.  Any of pcm / pcmf / results / bits may be NULL.
- *   _dev : all pointers are device pointers; the launch is asynchronous on `cuda_stream`.
+ *   _dev : all pointers are device pointers; the launch is asynchronous on `cuda_stream` (a cudaStream_t).  NULL selects
+ *          the context's own stream, which is created cudaStreamNonBlocking: it does NOT synchronise with the legacy
+ *          default stream, so order the producer of the inputs before the call (event / synchronize) or pass the
+ *          producer's stream.
  *   host : pointers are host memory (pinned or pageable); H2D copy, kernel and D2H copy run on the
  *          context's stream and the call returns when the results are in host memory. */
 MBE_B200_API int mbe_b200_process_frames_dev(mbe_b200_ctx* ctx, int codec, int soft, int first_stream, int n_streams,
