@@ -299,3 +299,36 @@ def test_normalized_float_output(dec):
     want = a["pcmf"] * np.float32(7.0 / 32768.0)
     assert np.array_equal(want.view(np.uint32), b["pcmf"].view(np.uint32))
     assert np.abs(b["pcmf"]).max() <= 0.951
+
+
+@pytest.mark.gpu
+def test_stream_window_and_degenerate_batches(dec):
+    """first_stream / n_streams address a window of the state pool; empty batches are no-ops; one stream and one frame
+    work (ragged blocks: 14 streams per block, so every size below exercises a partly filled block)."""
+    codec = 0
+    S, F = 37, 7
+    frames = T.random_hard_frames(codec, S, F, 0xABCD)
+    seeds = T.stream_seeds(S, 21)
+    dec.init_streams(0, S, seeds)
+    full = dec.process_frames(codec, frames)
+    # the same streams living at an offset of the pool, processed in two windows and frame by frame
+    off = 101
+    dec.init_streams(off, S, seeds)
+    a = dec.process_frames(codec, frames[:20], first_stream=off)
+    b0 = dec.process_frames(codec, frames[20:, :3], first_stream=off + 20)
+    b1 = dec.process_frames(codec, frames[20:, 3:4], first_stream=off + 20)
+    b2 = dec.process_frames(codec, frames[20:, 4:], first_stream=off + 20)
+    pcm = np.concatenate([a["pcm"], np.concatenate([b0["pcm"], b1["pcm"], b2["pcm"]], axis=1)], axis=0)
+    assert np.array_equal(pcm, full["pcm"])
+    assert np.array_equal(dec.export_state(0, S), dec.export_state(off, S))
+    # degenerate sizes
+    empty = dec.process_frames(codec, frames[:0])
+    assert empty["pcm"].shape == (0, F, 160)
+    none = dec.process_frames(codec, frames[:, :0])
+    assert none["pcm"].shape == (S, 0, 160)
+    dec.init_streams(0, 1, seeds[:1])
+    one = dec.process_frames(codec, frames[:1, :1])
+    assert np.array_equal(one["pcm"], full["pcm"][:1, :1])
+    # out-of-range windows are refused, not clipped
+    with pytest.raises(Exception):
+        dec.process_frames(codec, frames, first_stream=dec.max_streams - 3)
