@@ -169,6 +169,10 @@ def main():
     ap.add_argument("--streams", type=int, default=65536, help="streams per GPU")
     ap.add_argument("--frames", type=int, default=50, help="frames per stream per step")
     ap.add_argument("--soft", action="store_true", help="soft-decision input (bit + reliability per channel bit), random reliabilities")
+    ap.add_argument("--soft-channel", action="store_true",
+                    help="soft-decision input shaped like BASELINE.json configs[4]: valid encoded frames, every channel bit "
+                         "flipped with p = 0.10, reliability 255 for unflipped and U[0,64) for flipped bits (128 distinct "
+                         "streams tiled over the batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -177,9 +181,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     S, F = args.streams, args.frames
-    soft = 1 if args.soft else 0
-    workload = "%s %s-decision decode+synthesis, %d streams x %d synthetic random-bit frames per GPU" % (
-        CODEC_NAMES[codec], "soft" if soft else "hard", S, F)
+    soft = 1 if (args.soft or args.soft_channel) else 0
+    workload = "%s %s-decision decode+synthesis, %d streams x %d synthetic %s frames per GPU" % (
+        CODEC_NAMES[codec], "soft" if soft else "hard", S, F,
+        "valid encoded, 10% flipped-bit" if args.soft_channel else "random-bit")
     config = {"workload": workload, "codec": CODEC_NAMES[codec], "streams_per_gpu": S, "frames_per_stream": F,
               "sharding": "streams/%d, no collective" % world,
               "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (S * F * (FRAME_BITS[codec] + 344) / 1e6)}
@@ -219,7 +224,23 @@ def main():
     gen = torch.Generator(device=dev)
     gen.manual_seed(0x2450 + rank)
     d_frames = torch.randint(0, 2, (S, F, fb), dtype=torch.uint8, device=dev, generator=gen)
-    if soft:  # mbe_soft_bit {bit, reliability} pairs
+    if args.soft_channel:
+        import mbe_testlib as T
+        rng = np.random.default_rng(0x50F7 + rank)
+        B = 128
+        if codec == 1:
+            hard = T.random_hard_frames(codec, B, F, 0x7100)
+        else:
+            enc = T.encode_imbe7200_frame if codec == 0 else T.encode_ambe_frame
+            hard = np.zeros((B, F, fb), np.uint8)
+            for b in range(B):
+                for f in range(F):
+                    pb = rng.integers(0, 2, size=T.PARAM_BITS[codec], dtype=np.uint8)
+                    pb[0] = 0
+                    hard[b, f] = enc(pb).reshape(-1)
+        base = torch.from_numpy(T.soften(hard, rng, flip_p=0.10)).to(dev)
+        d_frames = base.repeat((S + B - 1) // B, 1, 1, 1)[:S].contiguous()
+    elif soft:  # mbe_soft_bit {bit, reliability} pairs
         rel = torch.randint(0, 256, (S, F, fb), dtype=torch.uint8, device=dev, generator=gen)
         d_frames = torch.stack((d_frames, rel), dim=-1).contiguous()
     d_pcm = torch.empty((S, F, 160), dtype=torch.int16, device=dev)

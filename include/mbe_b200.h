@@ -148,6 +148,11 @@ MBE_B200_API int mbe_b200_process_data(mbe_b200_ctx* ctx, int codec, int first_s
  * floattoshort: batched mbe_floattoshort (mbelib.h:675), n_frames x 160 samples. */
 MBE_B200_API int mbe_b200_synthesize_speech(mbe_b200_ctx* ctx, int n, void* cur_parms, void* prev_parms,
                                             const uint32_t* seeds, float* pcmf, int16_t* pcm);
+/* the same with the RNG state carried by the caller: rng_words4 = [n][4] {comfort_seed48 lo, hi, unvoiced seed,
+ * override flag} in and out, the words mbe_b200_export_rng moves (what the reference keeps in thread-local storage
+ * between calls, src/core/mbe_adaptive.c:29-30, src/core/mbe_unvoiced_fft.c:29-30) */
+MBE_B200_API int mbe_b200_synthesize_speech_rng(mbe_b200_ctx* ctx, int n, void* cur_parms, void* prev_parms,
+                                                uint32_t* rng_words4, float* pcmf, int16_t* pcm);
 MBE_B200_API int mbe_b200_floattoshort(mbe_b200_ctx* ctx, int n_frames, const float* in, int16_t* out);
 MBE_B200_API int mbe_b200_floattoshort_dev(mbe_b200_ctx* ctx, int n_frames, const float* d_in, int16_t* d_out,
                                            void* cuda_stream);

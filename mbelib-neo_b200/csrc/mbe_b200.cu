@@ -550,7 +550,20 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
         if (live) {
             const uint8_t* fr = A.frames + idx * fstride;
             if (MODE == MODE_FRAMES) {
-                FrontResult R = front_end(CODEC, SOFT == 1, PACKED, fr, dw, ws.u.dec.rel, ws.u.dec.cost, ws.u.dec.rowbits, T, lane);
+                // soft decision: the parity cost table takes the whole union and the small tables, reliabilities and
+                // corrected rows live in the sample row, which is dead until the synthesis writes it
+                SoftScratch S = {nullptr, nullptr, nullptr};
+                unsigned char* relp = ws.u.dec.rel;
+                unsigned* rowp = ws.u.dec.rowbits;
+                if (SOFT == 1) {
+                    unsigned char* o = reinterpret_cast<unsigned char*>(ws.out);
+                    S.cp = reinterpret_cast<unsigned short*>(&ws.u);
+                    S.ka = reinterpret_cast<unsigned*>(o);
+                    S.qa = reinterpret_cast<unsigned short*>(o + 256);
+                    relp = o + 384;
+                    rowp = reinterpret_cast<unsigned*>(o + 576);
+                }
+                FrontResult R = front_end(CODEC, SOFT == 1, PACKED, fr, dw, relp, S, rowp, T, lane);
                 status = R.status;
                 fc.total = R.c0 + R.prot;
                 fc.c0 = R.c0;
@@ -711,7 +724,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
         // RNG as after mbe_setThreadRngSeed(seed) (mbelib.c:173-181); no seeds: fresh-thread defaults
         if (lane == 0) {
             c[HEAD_WORDS] = gc[SEED_WORD];
-            if (A.synth_seeds) {
+            if (A.synth_rng) {  // the caller's RNG words, carried from call to call (single-stream shim)
+                const uint32_t* r = A.synth_rng + 4 * (size_t)s;
+                ws.rng.comfort = (unsigned long long)r[0] | ((unsigned long long)r[1] << 32);
+                ws.rng.uv_seed = r[2];
+                ws.rng.uv_override = r[3];
+            } else if (A.synth_seeds) {
                 unsigned seed = A.synth_seeds[s];
                 if (seed == 0u) {
                     seed = 0x6d25357bu;
@@ -752,6 +770,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
         }
         if (lane == 0) {
             gc[SEED_WORD] = c[HEAD_WORDS];
+            if (A.synth_rng) {
+                uint32_t* r = A.synth_rng + 4 * (size_t)s;
+                r[0] = (uint32_t)(ws.rng.comfort & 0xffffffffULL);
+                r[1] = (uint32_t)(ws.rng.comfort >> 32);
+                r[2] = ws.rng.uv_seed;
+                r[3] = ws.rng.uv_override;
+            }
         }
     }
 }
@@ -762,7 +787,9 @@ __global__ void __launch_bounds__(256) mbe_decode_kernel(int n, const uint8_t* _
                                                          uint8_t* __restrict__ bits, mbe_b200_result* __restrict__ results,
                                                          const DevTables* T) {
     __shared__ unsigned char rel[8][8 * 24];
-    __shared__ unsigned short cost[SOFT ? 8 : 1][640];
+    __shared__ __align__(16) unsigned short cp[SOFT ? 8 : 1][SOFT ? 2048 : 2];
+    __shared__ unsigned ka[SOFT ? 8 : 1][64];
+    __shared__ unsigned short qa[SOFT ? 8 : 1][64];
     __shared__ unsigned rows[8][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + warp;
@@ -772,8 +799,9 @@ __global__ void __launch_bounds__(256) mbe_decode_kernel(int n, const uint8_t* _
     constexpr int fbits = (CODEC == MBE_B200_IMBE7200X4400) ? 184 : (CODEC == MBE_B200_IMBE7100X4400 ? 168 : 96);
     constexpr int pbits = (CODEC <= MBE_B200_IMBE7100X4400) ? 88 : 49;
     unsigned dw[3];
-    FrontResult R = front_end(CODEC, SOFT, 0, frames + (size_t)i * fbits * (SOFT ? 2 : 1), dw, rel[warp],
-                              cost[SOFT ? warp : 0], rows[warp], T, lane);
+    const SoftScratch S = {cp[SOFT ? warp : 0], ka[SOFT ? warp : 0], qa[SOFT ? warp : 0]};
+    FrontResult R = front_end(CODEC, SOFT, 0, frames + (size_t)i * fbits * (SOFT ? 2 : 1), dw, rel[warp], S, rows[warp], T,
+                              lane);
     if (bits && R.status >= 0) {
 #pragma unroll
         for (int w = 0; w < 3; ++w) {
@@ -1070,6 +1098,20 @@ static void build_tables(DevTables* t) {
                     }
                 }
                 t->ham_cw[v][d] = (unsigned short)cw;
+            }
+            // parity bits of a codeword, compacted, as a linear function of the two halves of its data index
+            for (unsigned d = 0; d < 64; ++d) {
+                unsigned lo = 0, hi = 0;
+                for (int i = 0; i < 4; ++i) {
+                    lo |= ((unsigned)(t->ham_cw[v][d] >> ppos[v][i]) & 1u) << i;
+                    if (d < 32) {
+                        hi |= ((unsigned)(t->ham_cw[v][d << 6] >> ppos[v][i]) & 1u) << i;
+                    }
+                }
+                t->ham_par_lo[v][d] = (unsigned char)lo;
+                if (d < 32) {
+                    t->ham_par_hi[v][d] = (unsigned char)hi;
+                }
             }
         }
     }
@@ -1739,8 +1781,8 @@ int mbe_b200_decode_frames(mbe_b200_ctx* ctx, int codec, int soft, int n, const 
     return 0;
 }
 
-int mbe_b200_synthesize_speech(mbe_b200_ctx* ctx, int n, void* cur_parms, void* prev_parms, const uint32_t* seeds,
-                               float* pcmf, int16_t* pcm) {
+static int synthesize_speech_impl(mbe_b200_ctx* ctx, int n, void* cur_parms, void* prev_parms, const uint32_t* seeds,
+                                  uint32_t* rng_inout, float* pcmf, int16_t* pcm) {
     if (!ctx) {
         return MBE_B200_E_ARG;
     }
@@ -1752,16 +1794,19 @@ int mbe_b200_synthesize_speech(mbe_b200_ctx* ctx, int n, void* cur_parms, void* 
     }
     CU(cudaSetDevice(ctx->device));
     const size_t pbytes = (size_t)n * sizeof(Parms);
+    const size_t rbytes = rng_inout ? (size_t)n * 16 : (size_t)n * 4;
     int rc;
-    // d_in: [cur | prev | seeds]
-    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, 2 * pbytes + (size_t)n * 4)) < 0) {
+    // d_in: [cur | prev | seeds or RNG words]
+    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, 2 * pbytes + rbytes)) < 0) {
         return rc;
     }
     uint8_t* base = (uint8_t*)ctx->d_in;
     CU(cudaMemcpyAsync(base, cur_parms, pbytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(base + pbytes, prev_parms, pbytes, cudaMemcpyHostToDevice, ctx->stream));
-    if (seeds) {
-        CU(cudaMemcpyAsync(base + 2 * pbytes, seeds, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (rng_inout) {
+        CU(cudaMemcpyAsync(base + 2 * pbytes, rng_inout, rbytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else if (seeds) {
+        CU(cudaMemcpyAsync(base + 2 * pbytes, seeds, rbytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     const size_t ob[2] = {pcm ? (size_t)n * NS * sizeof(int16_t) : 0, pcmf ? (size_t)n * NS * sizeof(float) : 0};
     for (int i = 0; i < 2; ++i) {
@@ -1779,12 +1824,16 @@ int mbe_b200_synthesize_speech(mbe_b200_ctx* ctx, int n, void* cur_parms, void* 
     a.tab = ctx->d_tab;
     a.synth_cur = (uint32_t*)base;
     a.synth_prev = (uint32_t*)(base + pbytes);
-    a.synth_seeds = seeds ? (const uint32_t*)(base + 2 * pbytes) : nullptr;
+    a.synth_seeds = (!rng_inout && seeds) ? (const uint32_t*)(base + 2 * pbytes) : nullptr;
+    a.synth_rng = rng_inout ? (uint32_t*)(base + 2 * pbytes) : nullptr;
     if ((rc = launch_stream_kernel(ctx, a, ctx->stream)) < 0) {
         return rc;
     }
     CU(cudaMemcpyAsync(cur_parms, base, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(prev_parms, base + pbytes, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rng_inout) {
+        CU(cudaMemcpyAsync(rng_inout, base + 2 * pbytes, rbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (pcm) {
         CU(cudaMemcpyAsync(pcm, ctx->d_out[0], ob[0], cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -1793,6 +1842,19 @@ int mbe_b200_synthesize_speech(mbe_b200_ctx* ctx, int n, void* cur_parms, void* 
     }
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+int mbe_b200_synthesize_speech(mbe_b200_ctx* ctx, int n, void* cur_parms, void* prev_parms, const uint32_t* seeds,
+                               float* pcmf, int16_t* pcm) {
+    return synthesize_speech_impl(ctx, n, cur_parms, prev_parms, seeds, nullptr, pcmf, pcm);
+}
+
+int mbe_b200_synthesize_speech_rng(mbe_b200_ctx* ctx, int n, void* cur_parms, void* prev_parms, uint32_t* rng_words4,
+                                   float* pcmf, int16_t* pcm) {
+    if (ctx && !rng_words4) {
+        return fail(ctx, MBE_B200_E_ARG, "synthesize_speech_rng: bad argument", cudaSuccess);
+    }
+    return synthesize_speech_impl(ctx, n, cur_parms, prev_parms, nullptr, rng_words4, pcmf, pcm);
 }
 
 int mbe_b200_floattoshort(mbe_b200_ctx* ctx, int n_frames, const float* in, int16_t* out) {

@@ -170,6 +170,7 @@ struct DevTables {
     unsigned short ham_cw[2][2048];     // all Hamming(15,11) codewords in the reference's enumeration order
     unsigned short ham_rows[2][4];
     unsigned short ham_flip[2][16];
+    unsigned char ham_par_hi[2][32], ham_par_lo[2][64];  // compacted parity of codeword (d << 6) / d
     // windows
     float uvwin[256];                   // 211-pt trapezoid centred at 128
     float wola_wp[160], wola_wc[160], wola_den[160];
@@ -194,6 +195,7 @@ struct LaunchArgs {
     uint32_t* synth_cur;
     uint32_t* synth_prev;
     const uint32_t* synth_seeds;
+    uint32_t* synth_rng;        // MODE_SYNTH: [n][4] RNG words in/out (overrides synth_seeds)
     unsigned long long* dbg;    // MBE_STAGE_TIMING builds: 16 accumulated per-stage cycle counters
     float pcmf_scale;           // float PCM is multiplied by this on store: 1 (reference scale) or 7/32768 (normalised)
 };
@@ -242,7 +244,6 @@ struct __align__(16) WarpWS {
             float tmp[128];               // per-harmonic terms [1..56], DCT coefficients [64+l]
             float Tl[60];
             int field[58];                // IMBE quantiser words b1..bL+1
-            unsigned short cost[640];     // soft-decision partial cost tables
             unsigned rowbits[8];
             unsigned char rel[8 * 24];    // soft-bit reliabilities of the frame
         } dec;
@@ -262,6 +263,7 @@ struct __align__(16) WarpWS {
     unsigned short interp_item[8];        // interpolated harmonics of the block this warp renders in this round: owner << 8 | position
     unsigned char comp[112];              // component descriptor: harmonic << 2 | kind
 };
+static_assert(sizeof(((WarpWS*)0)->u) >= 4096 && sizeof(((WarpWS*)0)->out) >= 608, "soft-decision scratch (SoftScratch)");
 static_assert(offsetof(WarpWS, u) % 16 == 0 && sizeof(WarpWS) % 16 == 0 && sizeof(BlockTables) % 16 == 0 &&
                   offsetof(WarpWS, cur) % 16 == 0,
               "LDS.128 alignment");

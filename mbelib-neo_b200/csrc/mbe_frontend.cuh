@@ -41,82 +41,194 @@ __device__ __forceinline__ unsigned hamming_hard(unsigned w15, int variant, cons
     return w15 ^ (unsigned)T->ham_flip[variant][syn];
 }
 
-// Soft-decision decode of one row: exhaustive maximum-likelihood search over all codewords with the
-// reference's tie-break order (src/ecc/ecc.c:54-67): lowest cost, then the candidate equal to the
-// hard decode, then fewest differing bits, then lowest data index.  Cost = sum of reliabilities of
-// the positions where the candidate differs from the received hard bits, evaluated through three
-// byte-indexed partial-sum tables built per row in shared memory.
-//   cost_tab: 640 uint16 of per-warp scratch.
-__device__ __forceinline__ void soft_build_cost(unsigned short* cost_tab, const unsigned char* rel, int nbits, int lane) {
-    // tab[g][v] = sum over set bits b of v of rel[8g + b]
-    for (int e = lane; e < 640; e += 32) {
-        int g = e >> 8, v = e & 255;
-        if (e >= 512) {
-            g = 2;
-            v = e - 512;
+// Soft-decision decode of one row: exact maximum-likelihood search over all codewords with the reference's
+// tie-break order (src/ecc/ecc.c:54-67,157-215): lowest cost, then the candidate equal to the hard decode, then
+// fewest differing bits, then lowest data index.  Cost = sum of reliabilities of the positions where the candidate
+// differs from the received hard bits.
+//
+// The search is exhaustive like the reference's, but it walks the coset instead of re-encoding every candidate:
+// with d' = data ^ received data, the difference pattern of a candidate is (d', parity(d') ^ syndrome), so
+//   key(d') = cost << 16 | differing bits << 12 | data  =  KA[d' >> 6] + KB[d' & 63] + CP[par(d' >> 6) ^ par(d' & 63) ^ syn] << 16
+// is a sum of three table terms (every field is additive and cannot carry).  A lane keeps KB / par of its two low
+// halves in registers and walks the 64 high halves: one 16-bit shared-memory load and three integer instructions
+// per candidate.  The hard decode is the only candidate that wins ties on "equal to the hard decode", so it is
+// the answer unless some candidate costs strictly less than it does; and when the (dmin - t) least reliable
+// positions outside its t corrected positions already weigh at least as much as those t, nothing can cost less
+// and the search is skipped altogether.
+struct SoftScratch {
+    unsigned short* cp;  // 2048 x uint16 (4-byte aligned): cost of every 11-bit parity difference pattern
+    unsigned* ka;        // 64 x uint32: partial key of each high data half
+    unsigned short* qa;  // 64 x uint16: (parity of the high data half ^ syndrome) as a byte offset into cp
+};
+
+// sum of the k least reliable positions outside `inside` (bit p = position p), nbits positions in all
+__device__ __forceinline__ unsigned soft_least_outside(const unsigned char* rel, unsigned inside, int nbits, int k, int lane) {
+    unsigned mine = (lane < nbits && !((inside >> lane) & 1u)) ? (((unsigned)rel[lane] << 5) | (unsigned)lane) : 0xffffffffu;
+    unsigned sum = 0;
+    for (int i = 0; i < k; ++i) {
+        const unsigned m = __reduce_min_sync(FULL, mine);
+        sum += m >> 5;
+        if (mine == m) {
+            mine = 0xffffffffu;
         }
-        int s = 0;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            int pos = 8 * g + b;
-            if (((v >> b) & 1) && pos < nbits) {
-                s += (int)rel[pos];
-            }
-        }
-        cost_tab[e] = (unsigned short)s;
     }
-    __syncwarp();
+    return sum;
 }
 
-__device__ __forceinline__ unsigned golay_soft(unsigned hard23, const unsigned char* rel, unsigned short* cost_tab,
+__device__ __forceinline__ unsigned soft_cost_of(const unsigned char* rel, unsigned pattern, int nbits, int lane) {
+    return __reduce_add_sync(FULL, (lane < nbits && ((pattern >> lane) & 1u)) ? (unsigned)rel[lane] : 0u);
+}
+
+__device__ __forceinline__ unsigned golay_soft(unsigned hard23, const unsigned char* rel, const SoftScratch& S,
                                                const DevTables* T, int lane, int* errs) {
-    int dummy;
-    const unsigned hard_fixed = golay_hard(hard23, T, &dummy);
-    soft_build_cost(cost_tab, rel, 23, lane);
+    int e_hard;
+    const unsigned hf = golay_hard(hard23, T, &e_hard);
+    const unsigned hd = (hard23 >> 11) & 0xfffu;
+    const unsigned syn = golay_parity(hd, T) ^ (hard23 & 0x7ffu);
+    // the hard decode's difference pattern (weight <= 3) and its cost
+    const unsigned dhf = hf ^ hd;
+    const unsigned xhf = (dhf << 11) | (golay_parity(dhf, T) ^ syn);
+    const unsigned U = soft_cost_of(rel, xhf, 23, lane);
+    if (U == 0u || soft_least_outside(rel, xhf, 23, 7 - __popc(xhf), lane) >= U) {
+        *errs = e_hard;
+        return hf;
+    }
+    // five-bit subset sums selected by the lane number: positions 17..21 (high data half), 11..15 (low data half),
+    // 1..5 and 6..10 (parity)
+    unsigned sA = 0, sB = 0, sL = 0, sH = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const unsigned bit = ((unsigned)lane >> i) & 1u;
+        sA += bit * (unsigned)rel[17 + i];
+        sB += bit * (unsigned)rel[11 + i];
+        sL += bit * (unsigned)rel[1 + i];
+        sH += bit * (unsigned)rel[6 + i];
+    }
+    const unsigned pl = (unsigned)__popc(lane);
+    const unsigned hdh = hd >> 6, hdl = hd & 63u;
+    __syncwarp();
+    S.ka[lane] = (sA << 16) | (pl << 12) | ((((unsigned)lane) ^ hdh) << 6);
+    S.ka[lane + 32] = ((sA + (unsigned)rel[22]) << 16) | ((pl + 1u) << 12) | ((((unsigned)lane + 32u) ^ hdh) << 6);
+    S.qa[lane] = (unsigned short)(((unsigned)T->golay_par_hi[lane] ^ syn) << 1);
+    S.qa[lane + 32] = (unsigned short)(((unsigned)T->golay_par_hi[lane + 32] ^ syn) << 1);
+    const unsigned kb0 = (sB << 16) | (pl << 12) | (((unsigned)lane) ^ hdl);
+    const unsigned kb1 = ((sB + (unsigned)rel[16]) << 16) | ((pl + 1u) << 12) | (((unsigned)lane + 32u) ^ hdl);
+    const unsigned pb0 = (unsigned)T->golay_par_lo[lane] << 1;
+    const unsigned pb1 = (unsigned)T->golay_par_lo[lane + 32] << 1;
+    {
+        // cp[64 h + 2 lane + j], j = 0, 1, written as one word per lane and h
+        const unsigned pair = sL | ((sL + (unsigned)rel[0]) << 16);
+        const unsigned hdup = sH * 0x10001u;
+        unsigned* cp32 = reinterpret_cast<unsigned*>(S.cp);
+#pragma unroll 8
+        for (int h = 0; h < 32; ++h) {
+            cp32[32 * h + lane] = pair + __shfl_sync(FULL, hdup, h);
+        }
+    }
+    __syncwarp();
+    const unsigned char* cpb = reinterpret_cast<const unsigned char*>(S.cp);
     unsigned best = 0xffffffffu;
-    for (unsigned data = (unsigned)lane; data < 4096u; data += 32u) {
-        unsigned x = T->golay_cw[data] ^ hard23;
-        unsigned cost = (unsigned)cost_tab[x & 255u] + (unsigned)cost_tab[256 + ((x >> 8) & 255u)]
-                        + (unsigned)cost_tab[512 + (x >> 16)];
-        unsigned key = (cost << 17) | ((data != hard_fixed) ? (1u << 16) : 0u) | ((unsigned)__popc(x >> 11) << 12) | data;
-        best = min(best, key);
+#pragma unroll 8
+    for (int a = 0; a < 64; ++a) {
+        const unsigned q = S.qa[a];
+        const unsigned k = S.ka[a];
+        const unsigned c0 = *reinterpret_cast<const unsigned short*>(cpb + (q ^ pb0));
+        const unsigned c1 = *reinterpret_cast<const unsigned short*>(cpb + (q ^ pb1));
+        best = min(best, ((c0 << 16) + kb0) + k);
+        best = min(best, ((c1 << 16) + kb1) + k);
     }
     best = __reduce_min_sync(FULL, best);
     __syncwarp();
-    *errs = (int)((best >> 12) & 15u);
-    return best & 0xfffu;
+    if ((best >> 16) < U) {
+        *errs = (int)((best >> 12) & 15u);
+        return best & 0xfffu;
+    }
+    *errs = e_hard;
+    return hf;
 }
 
-__device__ __forceinline__ unsigned hamming_soft(unsigned hard15, int variant, const unsigned char* rel,
-                                                 unsigned short* cost_tab, const DevTables* T, int lane, int* errs) {
-    int dummy;
-    const unsigned hard_fixed = hamming_hard(hard15, variant, T, &dummy);
-    soft_build_cost(cost_tab, rel, 15, lane);
+// Hamming(15,11), both bit layouts (V = 0: ecc.c:366-408, V = 1: the IMBE 7100 variant, ecc.c:422-464).  Same coset
+// walk: 11 data bits = 5 high x 6 low, 4 parity bits through a 16-entry key table.  Returns the codeword.
+template <int V>
+__device__ __forceinline__ unsigned hamming_soft(unsigned hard15, const unsigned char* rel, const SoftScratch& S,
+                                                 const DevTables* T, int lane, int* errs) {
+    constexpr int dpos[2][11] = {{2, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14}, {4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14}};
+    constexpr int ppos[2][4] = {{0, 1, 3, 7}, {0, 1, 2, 3}};
+    int e_hard;
+    const unsigned hf = hamming_hard(hard15, V, T, &e_hard);
+    const unsigned xhf = hf ^ hard15;  // at most one position
+    const unsigned U = soft_cost_of(rel, xhf, 15, lane);
+    if (U == 0u || soft_least_outside(rel, xhf, 15, 3 - __popc(xhf), lane) >= U) {
+        *errs = e_hard;
+        return hf;
+    }
+    unsigned dh = 0, hp = 0;
+#pragma unroll
+    for (int i = 0; i < 11; ++i) {
+        dh |= ((hard15 >> dpos[V][i]) & 1u) << i;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        hp |= ((hard15 >> ppos[V][j]) & 1u) << j;
+    }
+    const unsigned syn = ((unsigned)T->ham_par_hi[V][dh >> 6] ^ (unsigned)T->ham_par_lo[V][dh & 63u]) ^ hp;
+    unsigned sA = 0, sB = 0, sP = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const unsigned bit = ((unsigned)lane >> i) & 1u;
+        sA += bit * (unsigned)rel[dpos[V][6 + i]];
+        sB += bit * (unsigned)rel[dpos[V][i]];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sP += (((unsigned)lane >> j) & 1u) * (unsigned)rel[ppos[V][j]];
+    }
+    const unsigned pl = (unsigned)__popc(lane);
+    unsigned* cp16 = reinterpret_cast<unsigned*>(S.cp);
+    __syncwarp();
+    if (lane < 16) {
+        cp16[lane] = (sP << 16) | (pl << 11);
+    }
+    S.ka[lane] = (sA << 16) | (pl << 11) | ((((unsigned)lane) << 6) ^ (dh & 0x7c0u));
+    S.qa[lane] = (unsigned short)(((unsigned)T->ham_par_hi[V][lane] ^ syn) << 2);
+    const unsigned kb0 = (sB << 16) | (pl << 11) | (((unsigned)lane) ^ (dh & 63u));
+    const unsigned kb1 = ((sB + (unsigned)rel[dpos[V][5]]) << 16) | ((pl + 1u) << 11) | (((unsigned)lane + 32u) ^ (dh & 63u));
+    const unsigned pb0 = (unsigned)T->ham_par_lo[V][lane] << 2;
+    const unsigned pb1 = (unsigned)T->ham_par_lo[V][lane + 32] << 2;
+    __syncwarp();
+    const unsigned char* cpb = reinterpret_cast<const unsigned char*>(S.cp);
     unsigned best = 0xffffffffu;
-    for (unsigned data = (unsigned)lane; data < 2048u; data += 32u) {
-        unsigned cw = (unsigned)T->ham_cw[variant][data];
-        unsigned x = cw ^ hard15;
-        unsigned cost = (unsigned)cost_tab[x & 255u] + (unsigned)cost_tab[256 + (x >> 8)];
-        unsigned key = (cost << 16) | ((cw != hard_fixed) ? (1u << 15) : 0u) | ((unsigned)__popc(x) << 11) | data;
-        best = min(best, key);
+#pragma unroll 8
+    for (int a = 0; a < 32; ++a) {
+        const unsigned q = S.qa[a];
+        const unsigned k = S.ka[a];
+        const unsigned c0 = *reinterpret_cast<const unsigned*>(cpb + (q ^ pb0));
+        const unsigned c1 = *reinterpret_cast<const unsigned*>(cpb + (q ^ pb1));
+        best = min(best, (c0 + kb0) + k);
+        best = min(best, (c1 + kb1) + k);
     }
     best = __reduce_min_sync(FULL, best);
     __syncwarp();
-    *errs = (int)((best >> 11) & 15u);
-    return (unsigned)T->ham_cw[variant][best & 0x7ffu];
+    if ((best >> 16) < U) {
+        *errs = (int)((best >> 11) & 15u);
+        return (unsigned)T->ham_cw[V][best & 0x7ffu];
+    }
+    *errs = e_hard;
+    return hf;
 }
 
 // Golay row, hard or soft; `w` holds the 23 received bits, returns the row with corrected data bits and
 // the received parity bits (both decoders echo the input parity, ecc.c:290-292,352-355).
-__device__ __forceinline__ unsigned golay_row(unsigned w, const unsigned char* rel, int soft, unsigned short* cost_tab,
+__device__ __forceinline__ unsigned golay_row(unsigned w, const unsigned char* rel, int soft, const SoftScratch& S,
                                               const DevTables* T, int lane, int* errs) {
-    unsigned data = soft ? golay_soft(w, rel, cost_tab, T, lane, errs) : golay_hard(w, T, errs);
+    unsigned data = soft ? golay_soft(w, rel, S, T, lane, errs) : golay_hard(w, T, errs);
     return (data << 11) | (w & 0x7ffu);
 }
 
-__device__ __forceinline__ unsigned hamming_row(unsigned w, int variant, const unsigned char* rel, int soft,
-                                                unsigned short* cost_tab, const DevTables* T, int lane, int* errs) {
-    return soft ? hamming_soft(w, variant, rel, cost_tab, T, lane, errs) : hamming_hard(w, variant, T, errs);
+template <int V>
+__device__ __forceinline__ unsigned hamming_row(unsigned w, const unsigned char* rel, int soft, const SoftScratch& S,
+                                                const DevTables* T, int lane, int* errs) {
+    return soft ? hamming_soft<V>(w, rel, S, T, lane, errs) : hamming_hard(w, V, T, errs);
 }
 
 __device__ __forceinline__ unsigned pn_bit(unsigned p0, int k, const DevTables* T) {
@@ -131,16 +243,17 @@ __device__ __forceinline__ unsigned getbit(const unsigned dw[3], int i) {
 // (bit i of the reference's imbe_d/ambe_d = bit (i & 31) of dw[i >> 5]).
 //   ws_rel  : per-warp scratch for reliabilities (8*24 bytes)
 //   rb      : per-warp scratch, 8 words (corrected rows, so that lanes can index them dynamically)
-//   cost_tab: per-warp scratch, 640 uint16 (soft only)
+//   S       : per-warp soft-decision scratch (soft only)
 //   packed  : hard bits packed eight per byte, MSB first, in the row-major order of the reference's fr[rows][cols]
 __device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed, const uint8_t* __restrict__ fr, unsigned dw[3],
-                                                 unsigned char* ws_rel, unsigned short* cost_tab, unsigned* rb,
+                                                 unsigned char* ws_rel, const SoftScratch& S, unsigned* rb,
                                                  const DevTables* T, int lane) {
     FrontResult R;
     const int rows = (codec == MBE_B200_IMBE7200X4400) ? 8 : (codec == MBE_B200_IMBE7100X4400 ? 7 : 4);
     const int cols = (codec == MBE_B200_IMBE7200X4400) ? 23 : 24;
     unsigned row[8];
     bool bad = false;
+    __syncwarp();  // the scratch may alias rows the previous frame's stores have just read
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         unsigned b = 0;
@@ -171,7 +284,7 @@ __device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed
     int c0 = 0, prot = 0, c4 = 0, e;
 
     if (codec == MBE_B200_IMBE7200X4400) {
-        row[0] = golay_row(row[0], ws_rel, soft, cost_tab, T, lane, &c0);
+        row[0] = golay_row(row[0], ws_rel, soft, S, T, lane, &c0);
         const unsigned p0 = (16u * ((row[0] >> 11) & 0xfffu)) & 0xffffu;
         // PN masks: rows 1..3 use k = 1 + 23 (r-1) + (22 - j); rows 4..6 use k = 70 + 15 (r-4) + (14 - j)
 #pragma unroll
@@ -186,12 +299,12 @@ __device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed
         }
 #pragma unroll
         for (int r = 1; r < 4; ++r) {
-            row[r] = golay_row(row[r] & 0x7fffffu, ws_rel + 24 * r, soft, cost_tab, T, lane, &e);
+            row[r] = golay_row(row[r] & 0x7fffffu, ws_rel + 24 * r, soft, S, T, lane, &e);
             prot += e;
         }
 #pragma unroll
         for (int r = 4; r < 7; ++r) {
-            row[r] = hamming_row(row[r] & 0x7fffu, 0, ws_rel + 24 * r, soft, cost_tab, T, lane, &e);
+            row[r] = hamming_row<0>(row[r] & 0x7fffu, ws_rel + 24 * r, soft, S, T, lane, &e);
             prot += e;
             if (r == 4) {
                 c4 = e;
@@ -230,7 +343,7 @@ __device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed
             __syncwarp();
         }
         unsigned w0 = (row[0] >> 1) & 0x3ffffu;
-        unsigned d0 = golay_row(w0, ws_rel + 7 * 24, soft, cost_tab, T, lane, &c0);
+        unsigned d0 = golay_row(w0, ws_rel + 7 * 24, soft, S, T, lane, &c0);
         row[0] = (row[0] & ~(0x3ffffu << 1)) | ((d0 & 0x3ffffu) << 1);
         const unsigned seed = (row[0] >> 12) & 0x7fu;
         const unsigned p0 = (16u * seed) & 0xffffu;
@@ -250,18 +363,18 @@ __device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed
         }
         // row 1 carries its Golay word in columns 1..23
         {
-            unsigned g = golay_row((row[1] >> 1) & 0x7fffffu, ws_rel + 24 * 1 + 1, soft, cost_tab, T, lane, &e);
+            unsigned g = golay_row((row[1] >> 1) & 0x7fffffu, ws_rel + 24 * 1 + 1, soft, S, T, lane, &e);
             row[1] = (row[1] & 1u) | (g << 1);
             prot = e;
         }
 #pragma unroll
         for (int r = 2; r < 4; ++r) {
-            row[r] = golay_row(row[r] & 0x7fffffu, ws_rel + 24 * r, soft, cost_tab, T, lane, &e);
+            row[r] = golay_row(row[r] & 0x7fffffu, ws_rel + 24 * r, soft, S, T, lane, &e);
             prot += e;
         }
 #pragma unroll
         for (int r = 4; r < 6; ++r) {
-            row[r] = hamming_row(row[r] & 0x7fffu, 1, ws_rel + 24 * r, soft, cost_tab, T, lane, &e);
+            row[r] = hamming_row<1>(row[r] & 0x7fffu, ws_rel + 24 * r, soft, S, T, lane, &e);
             prot += e;
             if (r == 4) {
                 c4 = e;
@@ -333,7 +446,7 @@ __device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed
         R.flags = 0x0002u | 0x0004u;
     } else {
         // AMBE 3600: C0 = Golay on columns 1..23 + overall parity in column 0
-        unsigned g = golay_row((row[0] >> 1) & 0x7fffffu, ws_rel + 1, soft, cost_tab, T, lane, &c0);
+        unsigned g = golay_row((row[0] >> 1) & 0x7fffffu, ws_rel + 1, soft, S, T, lane, &c0);
         row[0] = (row[0] & 1u) | (g << 1);
         if (c0 == 0 && (__popc(row[0] & 0xffffffu) & 1)) {
             row[0] ^= 1u;
@@ -344,7 +457,7 @@ __device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed
             unsigned b = (lane < 23) ? pn_bit(p0, 1 + (22 - lane), T) : 0u;
             row[1] ^= __ballot_sync(FULL, b);
         }
-        row[1] = (row[1] & 0x800000u) | golay_row(row[1] & 0x7fffffu, ws_rel + 24, soft, cost_tab, T, lane, &prot);
+        row[1] = (row[1] & 0x800000u) | golay_row(row[1] & 0x7fffffu, ws_rel + 24, soft, S, T, lane, &prot);
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
             int o = 32 * w + lane;
