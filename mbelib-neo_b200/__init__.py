@@ -32,7 +32,7 @@ _EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b
             "mbe_b200_launch_count", "mbe_b200_init_streams", "mbe_b200_export_state", "mbe_b200_import_state",
             "mbe_b200_export_rng", "mbe_b200_import_rng", "mbe_b200_process_frames_dev", "mbe_b200_process_frames",
             "mbe_b200_decode_frames_dev", "mbe_b200_decode_frames", "mbe_b200_process_data_dev",
-            "mbe_b200_process_data", "mbe_b200_synthesize_speech", "mbe_b200_floattoshort",
+            "mbe_b200_process_data", "mbe_b200_synthesize_speech", "mbe_b200_synthesize_speech_rng", "mbe_b200_floattoshort",
             "mbe_b200_floattoshort_dev", "mbe_b200_synchronize", "mbe_b200_debug_stage_cycles",
             "mbe_b200_set_normalized_float", "mbe_b200_packed_frame_bytes", "mbe_b200_process_frames_packed_dev", "mbe_b200_process_frames_packed"]
 
@@ -79,6 +79,7 @@ def load_library():
         lib.mbe_b200_process_data_dev.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]
         lib.mbe_b200_process_data.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, vp]
         lib.mbe_b200_synthesize_speech.argtypes = [vp, ci, vp, vp, vp, vp, vp]
+        lib.mbe_b200_synthesize_speech_rng.argtypes = [vp, ci, vp, vp, vp, vp, vp]
         lib.mbe_b200_floattoshort.argtypes = [vp, ci, vp, vp]
         lib.mbe_b200_floattoshort_dev.argtypes = [vp, ci, vp, vp, vp]
         lib.mbe_b200_synchronize.argtypes = [vp]

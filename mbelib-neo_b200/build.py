@@ -25,6 +25,23 @@ NVCC_FLAGS = [
 ]
 
 
+SHIM_OUT = os.path.join(HERE, "libmbe-neo-b200shim.so")
+SHIM_DEPS = ["mbe_single_shim.c", os.path.join("..", "..", "include", "mbe_b200.h"),
+             os.path.join("..", "..", "include", "mbe_b200_compat.h")]
+
+
+def build_shim(force=False):
+    """The single-stream drop-in shim: plain C on top of the C-ABI, linked against libmbe_b200.so."""
+    if not force and os.path.exists(SHIM_OUT) and os.path.exists(OUT):
+        t = os.path.getmtime(SHIM_OUT)
+        if t >= os.path.getmtime(OUT) and all(os.path.getmtime(os.path.join(CSRC, d)) <= t for d in SHIM_DEPS):
+            return SHIM_OUT
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=gnu99", "-Wall", "-fPIC", "-fvisibility=hidden", "-shared", "-o", SHIM_OUT,
+           os.path.join(CSRC, "mbe_single_shim.c"), "-L" + HERE, "-lmbe_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"]
+    subprocess.check_call(cmd)
+    return SHIM_OUT
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True
@@ -34,12 +51,15 @@ def needs_build():
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
+        build_shim()
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("MBE_NVCC_EXTRA", "").split()
     out = os.environ.get("MBE_LIB_OUT", OUT)
     cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
+    if out == OUT:
+        build_shim(force=True)
     return out
 
 

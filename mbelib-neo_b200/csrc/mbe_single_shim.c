@@ -1,0 +1,397 @@
+/*
+ * mbe_single_shim.c - single-stream drop-in shim (include/mbe_b200_compat.h): the reference's per-frame
+ * entry points on top of a batch of ONE through libmbe_b200.so.  Plain C host code; all decode and synthesis work
+ * happens in the CUDA kernels behind the C-ABI, this file only moves the caller-owned state in and out and mirrors
+ * the reference's argument checks (NULL pointers -> MBE_STATUS_INVALID_ARGUMENT before anything is touched).
+ *
+ * State mapping per call: {cur_mp, prev_mp, prev_mp_enhanced} -> stream slot 0 (mbe_b200_import_state), the calling
+ * thread's RNG words (the reference's thread-locals, src/core/mbe_adaptive.c:29-30, src/core/mbe_unvoiced_fft.c:29-30)
+ * -> mbe_b200_import_rng; one frame; both exported back.  One process-wide context guarded by a mutex.
+ */
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/mbe_b200.h"
+#include "../../include/mbe_b200_compat.h"
+
+#define NSAMP 160
+
+static mbe_b200_ctx* g_ctx;
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static __thread uint32_t t_rng[4];
+static __thread int t_rng_ready;
+
+/* the shared context, created on first use; no GPU = no product path: say so and stop */
+static mbe_b200_ctx* ctx_locked(void) {
+    if (!g_ctx) {
+        const char* dev = getenv("MBE_B200_DEVICE");
+        const int rc = mbe_b200_create(&g_ctx, dev ? atoi(dev) : 0, 1);
+        if (rc != 0) {
+            fprintf(stderr, "libmbe-neo-b200shim: mbe_b200_create failed (%d): %s - there is no CPU fallback\n", rc,
+                    mbe_b200_last_error(NULL));
+            abort();
+        }
+    }
+    return g_ctx;
+}
+
+static void die(mbe_b200_ctx* c, const char* what, int rc) {
+    fprintf(stderr, "libmbe-neo-b200shim: %s failed (%d): %s\n", what, rc, mbe_b200_last_error(c));
+    abort();
+}
+#define CK(call)                                                                                                      \
+    do {                                                                                                              \
+        const int rc_ = (call);                                                                                       \
+        if (rc_ != 0) {                                                                                               \
+            die(c, #call, rc_);                                                                                       \
+        }                                                                                                             \
+    } while (0)
+
+/* this thread's RNG words; a thread that never called mbe_setThreadRngSeed starts from the fresh-thread defaults */
+static void rng_ready_locked(mbe_b200_ctx* c) {
+    if (!t_rng_ready) {
+        CK(mbe_b200_init_streams(c, 0, 1, NULL));
+        CK(mbe_b200_export_rng(c, 0, 1, t_rng));
+        t_rng_ready = 1;
+    }
+}
+
+/* ---- host-only helpers ----------------------------------------------------------------------------------- */
+void mbe_initProcessResult(mbe_process_result* result) { /* mbelib.c:61-67 */
+    if (result) {
+        memset(result, 0, sizeof(*result));
+    }
+}
+
+void mbe_formatProcessResult(char* str, size_t size, const mbe_process_result* result) { /* mbelib.c:69-105 */
+    static const unsigned flag[4] = {MBE_PROCESS_FLAG_ERASURE, MBE_PROCESS_FLAG_TONE, MBE_PROCESS_FLAG_REPEAT,
+                                     MBE_PROCESS_FLAG_MUTE};
+    static const char mark[4] = {'E', 'T', 'R', 'M'};
+    if (!str || size == 0u) {
+        return;
+    }
+    size_t n = 0;
+    const int errs = (result && result->total_errors > 0) ? result->total_errors : 0;
+    while (n < (size_t)errs && n + 1u < size) {
+        str[n++] = '=';
+    }
+    for (int i = 0; result && i < 4 && n + 1u < size; ++i) {
+        if (result->flags & flag[i]) {
+            str[n++] = mark[i];
+        }
+    }
+    str[n] = '\0';
+}
+
+mbe_soft_bit mbe_softBitFromHard(int bit, uint8_t reliability) { /* mbelib.c:117-123 */
+    mbe_soft_bit s = {(uint8_t)(bit ? 1 : 0), reliability};
+    return s;
+}
+
+mbe_soft_bit mbe_softBitFromLlr(int16_t llr) { /* mbelib.c:125-132: sign = bit, |llr| saturated to 255 = reliability */
+    const int mag = llr < 0 ? -(int)llr : (int)llr;
+    mbe_soft_bit s = {(uint8_t)(llr > 0 ? 1 : 0), (uint8_t)(mag > 255 ? 255 : mag)};
+    return s;
+}
+
+static int bits_status(const char* bits, size_t count) { /* src/internal/mbe_result.h:18-30 */
+    if (!bits) {
+        return MBE_STATUS_INVALID_ARGUMENT;
+    }
+    for (size_t i = 0; i < count; ++i) {
+        if (bits[i] != 0 && bits[i] != 1) {
+            return MBE_STATUS_INVALID_BITS;
+        }
+    }
+    return 0;
+}
+
+int mbe_softBitsFromHard(const char* bits, mbe_soft_bit* soft, size_t count, uint8_t reliability) { /* mbelib.c:134-147 */
+    if (!soft) {
+        return MBE_STATUS_INVALID_ARGUMENT;
+    }
+    const int st = bits_status(bits, count);
+    if (st < 0) {
+        return st;
+    }
+    for (size_t i = 0; i < count; ++i) {
+        soft[i] = mbe_softBitFromHard(bits[i], reliability);
+    }
+    return 0;
+}
+
+int mbe_softBitsFromLlr(const int16_t* llr, mbe_soft_bit* soft, size_t count) { /* mbelib.c:149-158 */
+    if (!llr || !soft) {
+        return MBE_STATUS_INVALID_ARGUMENT;
+    }
+    for (size_t i = 0; i < count; ++i) {
+        soft[i] = mbe_softBitFromLlr(llr[i]);
+    }
+    return 0;
+}
+
+const char* mbe_versionString(void) { return "2.0.0"; } /* the reference version this shim mirrors (mbelib.c:323-326) */
+
+void mbe_moveMbeParms(const mbe_parms* source_mp, mbe_parms* destination_mp) { /* mbelib.c:338-344 */
+    if (source_mp && destination_mp) {
+        memmove(destination_mp, source_mp, sizeof(*destination_mp));
+    }
+}
+
+void mbe_useLastMbeParms(mbe_parms* cur_mp, const mbe_parms* prev_mp) { /* mbelib.c:353-359 */
+    if (cur_mp && prev_mp) {
+        memmove(cur_mp, prev_mp, sizeof(*cur_mp));
+    }
+}
+
+void mbe_synthesizeSilencef(float* aout_buf) { /* mbelib.c:862-868 */
+    if (aout_buf) {
+        memset(aout_buf, 0, NSAMP * sizeof(float));
+    }
+}
+
+void mbe_synthesizeSilence(short* aout_buf) { /* mbelib.c:874-880 */
+    if (aout_buf) {
+        memset(aout_buf, 0, NSAMP * sizeof(short));
+    }
+}
+
+/* ---- state ------------------------------------------------------------------------------------------------- */
+void mbe_setThreadRngSeed(uint32_t seed) { /* mbelib.c:173-181: the device derives both generators from the seed */
+    pthread_mutex_lock(&g_mu);
+    mbe_b200_ctx* c = ctx_locked();
+    CK(mbe_b200_init_streams(c, 0, 1, &seed));
+    CK(mbe_b200_export_rng(c, 0, 1, t_rng));
+    t_rng_ready = 1;
+    pthread_mutex_unlock(&g_mu);
+}
+
+void mbe_initMbeParms(mbe_parms* cur_mp, mbe_parms* prev_mp, mbe_parms* prev_mp_enhanced) { /* mbelib.c:367-410 */
+    if (!cur_mp || !prev_mp || !prev_mp_enhanced) {
+        return;
+    }
+    mbe_parms t[3];
+    pthread_mutex_lock(&g_mu);
+    mbe_b200_ctx* c = ctx_locked();
+    rng_ready_locked(c);  /* (before the slot is reset, so a fresh thread's defaults are captured once) */
+    CK(mbe_b200_init_streams(c, 0, 1, NULL));
+    CK(mbe_b200_export_state(c, 0, 1, t));
+    pthread_mutex_unlock(&g_mu);
+    *cur_mp = t[0];
+    *prev_mp = t[1];
+    *prev_mp_enhanced = t[2];
+}
+
+/* ---- the hot path, one frame at a time --------------------------------------------------------------------- */
+static void result_out(mbe_process_result* result, const mbe_b200_result* r) {
+    if (result) {
+        result->c0_errors = r->c0_errors;
+        result->protected_errors = r->protected_errors;
+        result->c4_errors = r->c4_errors;
+        result->total_errors = r->total_errors;
+        result->flags = r->flags;
+    }
+}
+
+static void slot_in(mbe_b200_ctx* c, const mbe_parms* cur, const mbe_parms* prev, const mbe_parms* enh) {
+    mbe_parms t[3];
+    t[0] = *cur;
+    t[1] = *prev;
+    t[2] = *enh;
+    rng_ready_locked(c);
+    CK(mbe_b200_import_state(c, 0, 1, t));
+    CK(mbe_b200_import_rng(c, 0, 1, t_rng));
+}
+
+static void slot_out(mbe_b200_ctx* c, mbe_parms* cur, mbe_parms* prev, mbe_parms* enh) {
+    mbe_parms t[3];
+    CK(mbe_b200_export_state(c, 0, 1, t));
+    CK(mbe_b200_export_rng(c, 0, 1, t_rng));
+    *cur = t[0];
+    *prev = t[1];
+    *enh = t[2];
+}
+
+/* mbe_decode<Codec>[Soft]Frame: the result is reset first, then the arguments are checked (imbe7200x4400.c:709-744) */
+static int shim_decode(int codec, int soft, const void* fr, char* d, mbe_process_result* result) {
+    int fbits = 0, pbits = 0;
+    mbe_b200_geometry(codec, &fbits, &pbits);
+    mbe_initProcessResult(result);
+    if (!d || !fr) {
+        return MBE_STATUS_INVALID_ARGUMENT;
+    }
+    uint8_t bits[88];
+    mbe_b200_result r;
+    pthread_mutex_lock(&g_mu);
+    mbe_b200_ctx* c = ctx_locked();
+    CK(mbe_b200_decode_frames(c, codec, soft, 1, (const uint8_t*)fr, bits, &r));
+    pthread_mutex_unlock(&g_mu);
+    if (r.status < 0) {
+        return r.status;
+    }
+    memcpy(d, bits, (size_t)pbits);
+    result_out(result, &r);
+    return r.status;
+}
+
+/* mbe_process<Codec>[Soft]Frame[f] = decode stage, then the Dataf stage on its output (imbe7200x4400.c:933-1007): the
+ * decode stage has already written `d` and `result` when the Dataf stage rejects a NULL state pointer */
+static int shim_frame(int codec, int soft, float* outf, short* outs, int want_short, mbe_process_result* result,
+                      const void* fr, char* d, mbe_parms* cur, mbe_parms* prev, mbe_parms* enh) {
+    int fbits = 0, pbits = 0;
+    mbe_b200_geometry(codec, &fbits, &pbits);
+    if (want_short && !outs) {
+        return MBE_STATUS_INVALID_ARGUMENT;
+    }
+    if ((!want_short && !outf) || !cur || !prev || !enh) {
+        const int st = shim_decode(codec, soft, fr, d, result);
+        return st < 0 ? st : MBE_STATUS_INVALID_ARGUMENT;
+    }
+    mbe_initProcessResult(result);
+    if (!d || !fr) {
+        return MBE_STATUS_INVALID_ARGUMENT;
+    }
+    uint8_t bits[88];
+    float pf[NSAMP];
+    int16_t ps[NSAMP];
+    mbe_b200_result r;
+    pthread_mutex_lock(&g_mu);
+    mbe_b200_ctx* c = ctx_locked();
+    slot_in(c, cur, prev, enh);
+    CK(mbe_b200_process_frames(c, codec, soft, 0, 1, 1, (const uint8_t*)fr, want_short ? ps : NULL, want_short ? NULL : pf,
+                               &r, bits));
+    if (r.status >= 0) {
+        slot_out(c, cur, prev, enh);
+    }
+    pthread_mutex_unlock(&g_mu);
+    if (r.status < 0) {
+        return r.status;  /* nothing but the (reset) result has been touched, like the reference's early return */
+    }
+    memcpy(d, bits, (size_t)pbits);
+    if (want_short) {
+        memcpy(outs, ps, sizeof(ps));
+    } else {
+        memcpy(outf, pf, sizeof(pf));
+    }
+    result_out(result, &r);
+    return r.status;
+}
+
+/* mbe_process<Codec>Data[f] (imbe7200x4400.c:863-924): result is an optional in/out decode context */
+static int shim_data(int codec, float* outf, short* outs, int want_short, mbe_process_result* result, const char* d,
+                     mbe_parms* cur, mbe_parms* prev, mbe_parms* enh) {
+    int fbits = 0, pbits = 0;
+    mbe_b200_geometry(codec, &fbits, &pbits);
+    if ((want_short ? (void*)outs : (void*)outf) == NULL || !cur || !prev || !enh) {
+        return MBE_STATUS_INVALID_ARGUMENT;
+    }
+    mbe_b200_result r;
+    memset(&r, 0, sizeof(r));
+    if (result) {
+        r.c0_errors = result->c0_errors;
+        r.protected_errors = result->protected_errors;
+        r.c4_errors = result->c4_errors;
+        r.total_errors = result->total_errors;
+        r.flags = result->flags;
+    }
+    if (!d) {
+        return MBE_STATUS_INVALID_ARGUMENT;  /* (an inconsistent result context gives the same code, mbe_result.h:44-97) */
+    }
+    float pf[NSAMP];
+    int16_t ps[NSAMP];
+    pthread_mutex_lock(&g_mu);
+    mbe_b200_ctx* c = ctx_locked();
+    slot_in(c, cur, prev, enh);
+    CK(mbe_b200_process_data(c, codec, 0, 1, 1, (const uint8_t*)d, &r, want_short ? ps : NULL, want_short ? NULL : pf));
+    if (r.status >= 0) {
+        slot_out(c, cur, prev, enh);
+    }
+    pthread_mutex_unlock(&g_mu);
+    if (r.status < 0) {
+        return r.status;
+    }
+    if (want_short) {
+        memcpy(outs, ps, sizeof(ps));
+    } else {
+        memcpy(outf, pf, sizeof(pf));
+    }
+    result_out(result, &r);
+    return r.status;
+}
+
+#define DECODE_FN(name, codec, R, C, N)                                                                               \
+    int name##Frame(const char fr[R][C], char d[N], mbe_process_result* result) {                                     \
+        return shim_decode(codec, 0, fr, d, result);                                                                  \
+    }                                                                                                                 \
+    int name##SoftFrame(const mbe_soft_bit fr[R][C], char d[N], mbe_process_result* result) {                         \
+        return shim_decode(codec, 1, fr, d, result);                                                                  \
+    }
+DECODE_FN(mbe_decodeImbe7200x4400, MBE_B200_IMBE7200X4400, 8, 23, 88)
+DECODE_FN(mbe_decodeImbe7100x4400, MBE_B200_IMBE7100X4400, 7, 24, 88)
+DECODE_FN(mbe_decodeAmbe3600x2400, MBE_B200_AMBE3600X2400, 4, 24, 49)
+DECODE_FN(mbe_decodeAmbe3600x2450, MBE_B200_AMBE3600X2450, 4, 24, 49)
+
+#define FRAME_FN(name, codec, R, C, N)                                                                                \
+    int name##Framef(float* o, mbe_process_result* res, const char fr[R][C], char d[N], mbe_parms* c, mbe_parms* p,   \
+                     mbe_parms* e) {                                                                                  \
+        return shim_frame(codec, 0, o, NULL, 0, res, fr, d, c, p, e);                                                 \
+    }                                                                                                                 \
+    int name##Frame(short* o, mbe_process_result* res, const char fr[R][C], char d[N], mbe_parms* c, mbe_parms* p,    \
+                    mbe_parms* e) {                                                                                   \
+        return shim_frame(codec, 0, NULL, o, 1, res, fr, d, c, p, e);                                                 \
+    }                                                                                                                 \
+    int name##SoftFramef(float* o, mbe_process_result* res, const mbe_soft_bit fr[R][C], char d[N], mbe_parms* c,     \
+                         mbe_parms* p, mbe_parms* e) {                                                                \
+        return shim_frame(codec, 1, o, NULL, 0, res, fr, d, c, p, e);                                                 \
+    }                                                                                                                 \
+    int name##SoftFrame(short* o, mbe_process_result* res, const mbe_soft_bit fr[R][C], char d[N], mbe_parms* c,      \
+                        mbe_parms* p, mbe_parms* e) {                                                                 \
+        return shim_frame(codec, 1, NULL, o, 1, res, fr, d, c, p, e);                                                 \
+    }
+FRAME_FN(mbe_processImbe7200x4400, MBE_B200_IMBE7200X4400, 8, 23, 88)
+FRAME_FN(mbe_processImbe7100x4400, MBE_B200_IMBE7100X4400, 7, 24, 88)
+FRAME_FN(mbe_processAmbe3600x2400, MBE_B200_AMBE3600X2400, 4, 24, 49)
+FRAME_FN(mbe_processAmbe3600x2450, MBE_B200_AMBE3600X2450, 4, 24, 49)
+
+#define DATA_FN(name, codec, N)                                                                                       \
+    int name##f(float* o, mbe_process_result* res, const char d[N], mbe_parms* c, mbe_parms* p, mbe_parms* e) {       \
+        return shim_data(codec, o, NULL, 0, res, d, c, p, e);                                                         \
+    }                                                                                                                 \
+    int name(short* o, mbe_process_result* res, const char d[N], mbe_parms* c, mbe_parms* p, mbe_parms* e) {          \
+        return shim_data(codec, NULL, o, 1, res, d, c, p, e);                                                         \
+    }
+DATA_FN(mbe_processImbe4400Data, MBE_B200_IMBE7200X4400, 88)
+DATA_FN(mbe_processAmbe2400Data, MBE_B200_AMBE3600X2400, 49)
+DATA_FN(mbe_processAmbe2450Data, MBE_B200_AMBE3600X2450, 49)
+
+/* ---- synthesis only ---------------------------------------------------------------------------------------- */
+static void shim_synth(float* outf, short* outs, mbe_parms* cur, mbe_parms* prev) { /* mbelib.c:1042-1146 */
+    if ((!outf && !outs) || !cur || !prev) {
+        return;
+    }
+    pthread_mutex_lock(&g_mu);
+    mbe_b200_ctx* c = ctx_locked();
+    rng_ready_locked(c);
+    CK(mbe_b200_synthesize_speech_rng(c, 1, cur, prev, t_rng, outf, (int16_t*)outs));
+    pthread_mutex_unlock(&g_mu);
+}
+
+void mbe_synthesizeSpeechf(float* aout_buf, mbe_parms* cur_mp, mbe_parms* prev_mp) {
+    shim_synth(aout_buf, NULL, cur_mp, prev_mp);
+}
+
+void mbe_synthesizeSpeech(short* aout_buf, mbe_parms* cur_mp, mbe_parms* prev_mp) {
+    shim_synth(NULL, aout_buf, cur_mp, prev_mp);
+}
+
+void mbe_floattoshort(const float* float_buf, short* aout_buf) { /* mbelib.c:1148-1177,1312-1320 */
+    if (!float_buf || !aout_buf) {
+        return;
+    }
+    pthread_mutex_lock(&g_mu);
+    mbe_b200_ctx* c = ctx_locked();
+    CK(mbe_b200_floattoshort(c, 1, float_buf, (int16_t*)aout_buf));
+    pthread_mutex_unlock(&g_mu);
+}

@@ -1,0 +1,80 @@
+"""Single-stream drop-in shim on the GPU.
+
+1. The reference's OWN test programs that stay inside the hot path's boundary (tests/test_golden_pcm.c,
+   test_noise_determinism.c, test_floattoshort_parity.c, test_frame_paths.c, test_api.c of arancormonk/mbelib-neo),
+   compiled unmodified by oracle/Makefile (`make shimtests`, binaries in oracle/_ref/, shipped with the repo snapshot) and
+   linked against libmbe-neo-b200shim.so instead of libmbe-neo: they must pass frame by frame on the CUDA path.
+2. A frame-by-frame run through the shim's mbe_process<Codec>Frame with a caller-owned mbe_parms triplet against the
+   oracle's batch run of the same stream: PCM, parameter bits, error counts and the final triplet."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import mbe_testlib as T
+from __graft_entry__ import ROOT
+
+pytestmark = pytest.mark.gpu
+
+SHIM = os.path.join(ROOT, "mbelib-neo_b200", "libmbe-neo-b200shim.so")
+REFTESTS = ["test_golden_pcm", "test_noise_determinism", "test_floattoshort_parity", "test_frame_paths", "test_api"]
+
+
+@pytest.mark.parametrize("name", REFTESTS)
+def test_reference_test_program_passes_on_the_gpu_path(name):
+    exe = os.path.join(ROOT, "oracle", "_ref", "shim_" + name)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/shim_%s not built (needs /root/reference at build time: make -C oracle shimtests)" % name)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, "%s failed on the shim:\n%s\n%s" % (name, r.stdout[-2000:], r.stderr[-2000:])
+
+
+class Result(ctypes.Structure):
+    _fields_ = [("c0_errors", ctypes.c_int), ("protected_errors", ctypes.c_int), ("c4_errors", ctypes.c_int),
+                ("total_errors", ctypes.c_int), ("flags", ctypes.c_uint)]
+
+
+FRAME_FN = {0: "mbe_processImbe7200x4400", 1: "mbe_processImbe7100x4400", 2: "mbe_processAmbe3600x2400",
+            3: "mbe_processAmbe3600x2450"}
+
+
+@pytest.mark.parametrize("codec,soft", [(0, 0), (1, 0), (2, 0), (3, 0), (0, 1), (3, 1)])
+def test_frame_by_frame_through_the_shim_equals_the_oracle(codec, soft):
+    shim = ctypes.CDLL(SHIM)
+    F = 24
+    seed = 0xC0FFEE + 7
+    hard = T.random_hard_frames(codec, 1, F, 0x51A + codec)
+    frames = T.soften(hard, np.random.default_rng(5), flip_p=0.0, rel_ok=0) if soft else hard
+    if soft:  # random reliabilities
+        frames[..., 1] = np.random.default_rng(6).integers(0, 256, size=frames[..., 1].shape)
+    want = T.run_cpu(T.load_oracle().mbo_run, codec, soft, frames, np.array([seed], np.uint32))
+    vp = ctypes.c_void_p
+    shim.mbe_setThreadRngSeed.argtypes = [ctypes.c_uint32]
+    shim.mbe_initMbeParms.argtypes = [vp, vp, vp]
+    fn = getattr(shim, FRAME_FN[codec] + ("SoftFrame" if soft else "Frame"))
+    fnf = getattr(shim, FRAME_FN[codec] + ("SoftFramef" if soft else "Framef"))
+    fn.argtypes = fnf.argtypes = [vp] * 7
+    trip = np.zeros((2, 3, T.PARMS_BYTES), np.uint8)   # one triplet per output flavour
+    pcm = np.zeros((F, 160), np.int16)
+    pcmf = np.zeros((F, 160), np.float32)
+    bits = np.zeros((F, T.PARAM_BITS[codec]), np.uint8)
+    total = np.zeros(F, np.int32)
+    for k, (f_, out) in enumerate(((fn, pcm), (fnf, pcmf))):
+        shim.mbe_setThreadRngSeed(seed)
+        shim.mbe_initMbeParms(trip[k, 0].ctypes.data, trip[k, 1].ctypes.data, trip[k, 2].ctypes.data)
+        for f in range(F):
+            r = Result()
+            fr = np.ascontiguousarray(frames[0, f])
+            rc = f_(out[f].ctypes.data, ctypes.addressof(r), fr.ctypes.data, bits[f].ctypes.data, trip[k, 0].ctypes.data,
+                    trip[k, 1].ctypes.data, trip[k, 2].ctypes.data)
+            assert rc == r.total_errors >= 0
+            total[f] = rc
+    assert np.array_equal(bits, want["bits"][0])
+    assert np.array_equal(total, want["results"][0, :, 4])
+    d = np.abs(pcm.astype(np.int32) - want["pcm"][0].astype(np.int32))
+    assert d.max() <= 2 and (d == 0).mean() >= 0.9999   # the north star's PCM tolerance (measured: exact)
+    assert np.array_equal(pcmf.view(np.uint32), want["pcmf"][0].view(np.uint32))
+    final = want["state"][0].reshape(3, T.PARMS_BYTES)
+    assert np.array_equal(trip[0], final) and np.array_equal(trip[1], final)
