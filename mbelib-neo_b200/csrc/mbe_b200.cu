@@ -132,6 +132,7 @@ __device__ __forceinline__ Action process_imbe(FrameCtx& fc, const unsigned dw[3
                 cur.swn = 0;
                 cur.tonePhase = 0;
                 cur.w0 = T->imbe_default_w0;
+                ws.w0row = COSW_IMBE_DEFAULT;
                 cur.L = T->imbe_default_L;
                 cur.K = 12;
                 cur.gamma = 0.0f;
@@ -340,7 +341,7 @@ __device__ __forceinline__ RenderState render_begin1(const Action& act, WarpWS& 
         rs.voice = 1;
         if (kind == ACT_VOICE) {
             prev_from_cur(ws, home, lane);
-            rs.rm0 = spectral_enhance(ws.cur, ws.u.dec.tmp, lane);
+            rs.rm0 = spectral_enhance(ws, T, reinterpret_cast<float*>(&ws.u), lane);
             rs.has_rm0 = 1;
         } else {
             // replay the last voice model (ambe3600x2450.c:808-816): cur_mp is parked in the stream's scratch image
@@ -520,6 +521,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
     const StreamHome home = {gs, gs + PARMS_WORDS, gs + 2 * PARMS_WORDS, gs + SPILL_WORD};
     if (live) {
         load_stream(ws, gs, lane);
+    }
+    if (lane == 0) {
+        ws.w0row = ws.w0row_prev = -1;
     }
 
     StageTimer tm;
@@ -1258,6 +1262,9 @@ int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams) {
     }
     CUC(cudaMalloc(&ctx->d_tab, sizeof(DevTables)));
     CUC(cudaMemcpy(ctx->d_tab, ht, sizeof(DevTables), cudaMemcpyHostToDevice));
+    mbe_costab_kernel<<<(COSW_ROWS + 63) / 64, 64, 0, ctx->stream>>>(ctx->d_tab);
+    CUC(cudaGetLastError());
+    CUC(cudaStreamSynchronize(ctx->stream));
     CUC(cudaMalloc(&ctx->d_state, (size_t)max_streams * STATE_WORDS * sizeof(uint32_t)));
     CUC(cudaMalloc(&ctx->d_dbg, 16 * sizeof(unsigned long long)));
     CUC(cudaMemset(ctx->d_dbg, 0, 16 * sizeof(unsigned long long)));

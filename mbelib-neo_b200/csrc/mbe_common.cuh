@@ -136,6 +136,16 @@ constexpr int STATE_WORDS = 4 * PARMS_WORDS + RNG_WORDS;  // per stream in HBM: 
 
 // Tables computed on the host when a context is created (host libm = the reference's libm) and kept
 // in HBM; hot ones are staged into shared memory per block.
+// rows of DevTables::cosw
+constexpr int COSW_IMBE = 0;                 // + b0 (0..207)
+constexpr int COSW_A2450 = 208;              // + b0 (0..119)
+constexpr int COSW_A2450_SILENCE = 328;
+constexpr int COSW_A2400 = 329;              // + b0 (0..125)
+constexpr int COSW_A2400_SILENCE = 455;
+constexpr int COSW_IMBE_DEFAULT = 456;
+constexpr int COSW_AMBE_DEFAULT = 457;
+constexpr int COSW_ROWS = 458;
+
 struct DevTables {
     // DCT cosines (src/imbe/imbe7200x4400.c:97-111, src/ambe/ambe3600x2450.c:60-74)
     float ri6[36];      // [m-1][i-1]
@@ -176,6 +186,12 @@ struct DevTables {
     float wola_wp[160], wola_wc[160], wola_den[160];
     float voiced_win[324];
     unsigned short golay_fix[2048];
+    // cos(l * w0), l = 1..56, for every fundamental the decoders can produce, generated ON THE DEVICE at context
+    // creation by the reference's own rotation recurrence (mbelib.c:412-424) so the values are the ones the
+    // enhancement would compute frame by frame.  Row r belongs to the fundamental cosw_w0[r]; a frame whose w0 is not
+    // bitwise equal to its row's runs the recurrence itself.
+    float cosw_w0[COSW_ROWS];
+    float cosw[COSW_ROWS][57];
 };
 
 // mode of the stream kernel
@@ -253,7 +269,8 @@ struct __align__(16) WarpWS {
     // The three mbe_parms of the stream WITHOUT their bulk arrays (previousUw / noiseOverlap stay in the
     // stream's HBM slot); 16-byte aligned for 128-bit struct copies.
     ParmsSmall cur;
-    uint32_t pad_cur;
+    short w0row;                          // DevTables::cosw row of the fundamental this frame's decoder chose (unverified)
+    short w0row_prev;                     // row that matched the previous enhanced frame
     PrevSmall prev;
     EnhSmall enh;
     uint32_t pad_enh;

@@ -161,6 +161,7 @@ __device__ __forceinline__ int decode_imbe(const unsigned dw[3], WarpWS& ws, con
     const int K = (int)T->imbe_Kv[b0];
     if (lane == 0) {
         cur.w0 = T->imbe_w0[b0];
+        ws.w0row = (short)(COSW_IMBE + (int)b0);
         cur.L = L;
         cur.K = K;
     }
@@ -385,6 +386,7 @@ __device__ __forceinline__ int decode_ambe2450(const unsigned dw[3], WarpWS& ws,
     }
     if (lane == 0) {
         cur.w0 = w0;
+        ws.w0row = (short)(silence ? COSW_A2450_SILENCE : COSW_A2450 + b0);
         cur.L = L;
         cur.gamma = dg + (0.5f * ws.prev.gamma);
     }
@@ -434,6 +436,7 @@ __device__ __forceinline__ int decode_ambe2400(const unsigned dw[3], WarpWS& ws,
     }
     if (lane == 0) {
         cur.w0 = w0;
+        ws.w0row = (short)(COSW_A2400 + b0);
         cur.L = L;
         cur.gamma = dg + (0.5f * ws.prev.gamma);
     }

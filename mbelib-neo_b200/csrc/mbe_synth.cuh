@@ -212,7 +212,51 @@ __device__ __forceinline__ void zero_out(WarpWS& ws, int lane) {
 }
 
 // ---- spectral amplitude enhancement (mbelib.c:412-661); returns pre-enhancement Rm0 -------------
-__device__ __forceinline__ float spectral_enhance(ParmsSmall& cur, float* ws_scratch, int lane) {
+// cos(l w0) by the reference's rotation recurrence from one sincosf(w0): one lane's worth of serial work
+__device__ __forceinline__ void cos_recurrence(float w0, int L, float* cosl) {
+    const float2 sc = dev_sincosf(w0);
+    const float ss = sc.x, cs = sc.y;
+    float c = 1.0f, s = 0.0f;
+#pragma unroll 4
+    for (int l = 1; l <= L; ++l) {
+        const float cn = (c * cs) - (s * ss);
+        const float sn = (s * cs) + (c * ss);
+        c = cn;
+        s = sn;
+        cosl[l] = c;
+    }
+}
+
+// fills DevTables::cosw at context creation: one thread per row, the same code the frames would run
+__global__ void mbe_costab_kernel(DevTables* T) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= COSW_ROWS) {
+        return;
+    }
+    float w0;
+    if (r < COSW_A2450) {
+        w0 = T->imbe_w0[r - COSW_IMBE];
+    } else if (r < COSW_A2450_SILENCE) {
+        w0 = T->a2450_w0[r - COSW_A2450];
+    } else if (r == COSW_A2450_SILENCE) {
+        w0 = T->a2450_w0_silence;
+    } else if (r < COSW_A2400_SILENCE) {
+        w0 = T->a2400_w0[r - COSW_A2400];
+    } else if (r == COSW_A2400_SILENCE) {
+        w0 = T->a2400_w0_silence;
+    } else if (r == COSW_IMBE_DEFAULT) {
+        w0 = T->imbe_default_w0;
+    } else {
+        w0 = T->ambe_default_w0;
+    }
+    T->cosw_w0[r] = w0;
+    T->cosw[r][0] = 1.0f;
+    cos_recurrence(w0, 56, T->cosw[r]);
+}
+
+// scratch: 3 x 58 floats, 8-byte aligned (the workspace union: the decode scratch is dead, the synthesis has not begun)
+__device__ __forceinline__ float spectral_enhance(WarpWS& ws, const DevTables* T, float* scratch, int lane) {
+    ParmsSmall& cur = ws.cur;
     const int L = cur.L;
     if (!bands_ok(L)) {
         return 0.0f;
@@ -221,23 +265,58 @@ __device__ __forceinline__ float spectral_enhance(ParmsSmall& cur, float* ws_scr
     if (MBE_ABL & 32) {
         return 1000.0f;
     }
-    const float2 sc = dev_sincosf(w0);
-    const float ss = sc.x, cs = sc.y;
-    // serial: cos(l*w0) by rotation, Rm0 = sum M^2, Rm1 = sum M^2 cos, all in harmonic order; the cosines are
-    // parked in the (dead) decode scratch for the per-harmonic weights below
-    float* cosl = ws_scratch;
-    float c = 1.0f, s = 0.0f, Rm0 = 0.0f, Rm1 = 0.0f;
+    // the cosines come from the table when this frame's (or, after a repeat, the previous frame's) row matches w0
+    // bit for bit; otherwise (erasure model, imported state, first frame of a launch after a repeat) from the recurrence
+    int row = ws.w0row;
+    bool hit = row >= 0 && row < COSW_ROWS && __float_as_uint(T->cosw_w0[row]) == __float_as_uint(w0);
+    if (!hit) {
+        row = ws.w0row_prev;
+        hit = row >= 0 && row < COSW_ROWS && __float_as_uint(T->cosw_w0[row]) == __float_as_uint(w0);
+    }
+    float2* pair = reinterpret_cast<float2*>(scratch);  // (M^2, M^2 cos) per harmonic
+    float cosv[2] = {0.0f, 0.0f};
+    __syncwarp();
+    if (hit) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int l = 1 + lane + 32 * r;
+            if (l <= L) {
+                cosv[r] = T->cosw[row][l];
+            }
+        }
+    } else {
+        float* cosl = scratch + 2 * 58;
+        cos_recurrence(w0, L, cosl);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int l = 1 + lane + 32 * r;
+            if (l <= L) {
+                cosv[r] = cosl[l];
+            }
+        }
+        row = -1;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int l = 1 + lane + 32 * r;
+        if (l <= L) {
+            const float m = cur.Ml[l];
+            const float m2 = m * m;
+            pair[l] = make_float2(m2, m2 * cosv[r]);
+        }
+    }
+    if (lane == 0) {
+        ws.w0row_prev = (short)row;
+    }
+    __syncwarp();
+    // serial: Rm0 = sum M^2, Rm1 = sum M^2 cos, in harmonic order
+    float Rm0 = 0.0f, Rm1 = 0.0f;
 #pragma unroll 4
     for (int l = 1; l <= L; ++l) {
-        float cn = (c * cs) - (s * ss);
-        float sn = (s * cs) + (c * ss);
-        c = cn;
-        s = sn;
-        cosl[l] = c;
-        const float m = cur.Ml[l];
-        const float m2 = m * m;
-        Rm0 += m2;
-        Rm1 += m2 * c;
+        const float2 v = pair[l];
+        Rm0 += v.x;
+        Rm1 += v.y;
     }
     const float R2m0 = Rm0 * Rm0;
     const float R2m1 = Rm1 * Rm1;
@@ -248,7 +327,7 @@ __device__ __forceinline__ float spectral_enhance(ParmsSmall& cur, float* ws_scr
         if (l <= L) {
             float M = cur.Ml[l];
             if (M != 0.0f) {
-                const float cosw = cosl[l];
+                const float cosw = cosv[r];
                 float W = sqrtf(M)
                           * sqrtf(sqrtf(((0.96f * MBE_PI_F) * ((R2m0 + R2m1) - ((2.0f * Rm0) * Rm1 * cosw)))
                                         / ((w0 * Rm0) * (R2m0 - R2m1))));
@@ -262,14 +341,14 @@ __device__ __forceinline__ float spectral_enhance(ParmsSmall& cur, float* ws_scr
                 }
                 cur.Ml[l] = M;
             }
+            scratch[l] = M * M;  // (the reference squares |M|: same product)
         }
     }
     __syncwarp();
     float sum = 0.0f;
 #pragma unroll 4
     for (int l = 1; l <= L; ++l) {
-        const float M = cur.Ml[l];
-        sum += M * M;  // (the reference squares |M|: same product)
+        sum += scratch[l];
     }
     const float g = (sum == 0.0f) ? 1.0f : sqrtf(Rm0 / sum);
     __syncwarp();
