@@ -40,9 +40,9 @@ FRAME_BITS = {0: 184, 1: 168, 2: 96, 3: 96}
 FLOP_PER_FRAME = {0: 84e3, 1: 84e3, 2: 66e3, 3: 61e3}
 STATE_BYTES = 7828  # 3 x mbe_parms + 16 B RNG words per stream
 # DRAM traffic of the stream kernel per frame, measured: dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` capture (profiles/r01h_stream_kernel_ncu_details.txt: 172.4 MB + 369.9 MB for 16576 streams x 50
+# `ncu --set full` capture (profiles/r01j_stream_kernel_ncu_details.txt: 172.5 MB + 365.4 MB for 16576 streams x 50
 # frames of AMBE+2 hard-decision input) divided by the frames of that launch.  Only quoted for that workload.
-NCU_DRAM_BYTES_PER_FRAME = {("ambe3600x2450", 0): (172.365568e6 + 369.898496e6) / (16576 * 50)}
+NCU_DRAM_BYTES_PER_FRAME = {("ambe3600x2450", 0): (172.532224e6 + 365.409024e6) / (16576 * 50)}
 RESULT_BYTES = 24
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -61,27 +61,65 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    """SM clock / throttle-reason samples during the timed region: NVML (nvidia_ml_py, one sample every few ms) when it
+    loads, else `nvidia-smi` polling."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []      # (sm MHz, max MHz, watts, [active reason names])
         self.stop = threading.Event()
         self.th = None
+        self.nvml = None
+        self.handle = None
+        self.source = "nvidia-smi"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it is a plain list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+        mx = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+        pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        try:
+            bits = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        masks = [getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8), getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)]
+        self.rows.append((sm, mx, pw, [nm for nm, m in zip(self.NAMES, masks) if bits & m]))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [x.strip() for x in out.strip().split(",")]
+        if len(parts) >= 7:
+            self.rows.append((float(parts[0]), float(parts[1]), float(parts[2]),
+                              [nm for k, nm in enumerate(self.NAMES) if parts[3 + k].lower().startswith("active")]))
 
     def _run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                if self.nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.004 if self.nvml else 0.1)
 
     def __enter__(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -94,14 +132,11 @@ class ClockSampler:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
-        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "power_w": round(max(pw), 1) if pw else None, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [nm for nm in self.NAMES if any(nm in r[3] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[1] for r in self.rows), "reasons": reasons,
+                "power_w": round(max(r[2] for r in self.rows), 1), "samples": len(self.rows), "source": self.source}
 
 
 def host_cores():
@@ -360,7 +395,7 @@ def main():
     per_frame_dram = NCU_DRAM_BYTES_PER_FRAME.get((CODEC_NAMES[codec], soft))
     roofline = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                 "traffic": (per_frame_dram * S * F) if per_frame_dram else None,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per frame (profiles/r01h_*) x frames per launch"
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per frame (profiles/r01j_*) x frames per launch"
                 if per_frame_dram else None,
                 "peak_source": peak_src, "kernel": "mbe_stream_kernel",
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms,

@@ -14,12 +14,21 @@ __device__ __forceinline__ float pow2i(int e) {  // exact 2^e for -126 <= e <= 1
     return __int_as_float((127 + e) << 23);
 }
 
-// gather parameter bits (MSB first) at compile-time positions: the index lists fold into immediates
-template <int... IDX>
-__device__ __forceinline__ unsigned pick(const unsigned dw[3]) {
-    unsigned v = 0;
-    ((v = (v << 1) | ((dw[IDX >> 5] >> (IDX & 31)) & 1u)), ...);
-    return v;
+// Runs of consecutive parameter bits, MSB first, from the bit-reversed parameter words: frame bit i sits at bit
+// 63 - i of (hi:lo) = (brev(dw[0]) : brev(dw[1])), so bits a .. a+n-1 are one funnel shift and a mask.
+struct RevBits {
+    unsigned hi, lo;
+};
+__device__ __forceinline__ RevBits rev_bits(const unsigned dw[3]) {
+    RevBits r = {__brev(dw[0]), __brev(dw[1])};
+    return r;
+}
+template <int A, int N>
+__device__ __forceinline__ unsigned field(const RevBits& r) {
+    static_assert(A >= 0 && N >= 1 && N <= 16 && A + N <= 64, "field range");
+    constexpr int sh = 64 - A - N;
+    const unsigned v = (sh >= 32) ? (r.hi >> (sh - 32)) : __funnelshift_r(r.lo, r.hi, sh);
+    return v & ((1u << N) - 1u);
 }
 
 // log-magnitude prediction + exp2 (imbe7200x4400.c:294-354 / ambe3600x2450.c:389-459).
@@ -47,6 +56,7 @@ __device__ __forceinline__ void predict_magnitudes(WarpWS& ws, const DevTables* 
     __syncwarp();
     const float* P = prev.log2Ml;  // P[57] aliases PHIl[0], exactly as in the reference's struct
     const float ratio = (float)prev_L / (float)cur_L;
+    float2* pair = reinterpret_cast<float2*>(ws.u.dec.tmp);  // AMBE: (interpolated term, Tl) per harmonic; the DCT input is dead
     float dl[2], pa[2], pb[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -67,17 +77,23 @@ __device__ __forceinline__ void predict_magnitudes(WarpWS& ws, const DevTables* 
             dl[r] = fk - (float)ik;
             pa[r] = P[ik];
             pb[r] = P[up];
-            ws.u.dec.tmp[l] = (((float)1 - dl[r]) * pa[r]) + (dl[r] * pb[r]);
+            const float term = (((float)1 - dl[r]) * pa[r]) + (dl[r] * pb[r]);
+            if (ambe) {
+                pair[l] = make_float2(term, ws.u.dec.Tl[l]);
+            } else {
+                ws.u.dec.tmp[l] = term;
+            }
         }
     }
     __syncwarp();
-    // the two ordered sums over the harmonics share one loop
+    // the two ordered sums over the harmonics share one loop (and one 64-bit load per harmonic)
     float acc = 0.f, s42 = 0.f;
     if (ambe) {
 #pragma unroll 4
         for (int l = 1; l <= cur_L; ++l) {
-            acc = acc + ws.u.dec.tmp[l];
-            s42 += ws.u.dec.Tl[l];
+            const float2 v = pair[l];
+            acc = acc + v.x;
+            s42 += v.y;
         }
     } else {
 #pragma unroll 4
@@ -354,7 +370,8 @@ __device__ __forceinline__ int decode_ambe2450(const unsigned dw[3], WarpWS& ws,
     if (tone_ok && total_errors < 6) {
         return 7;
     }
-    const int b0 = (int)pick<0, 1, 2, 3, 37, 38, 39>(dw);
+    const RevBits rb = rev_bits(dw);
+    const int b0 = (int)((field<0, 4>(rb) << 3) | field<37, 3>(rb));  // bits 0-3, 37-39
     if (b0 >= 120 && b0 <= 123) {
         return 2;
     }
@@ -374,8 +391,8 @@ __device__ __forceinline__ int decode_ambe2450(const unsigned dw[3], WarpWS& ws,
         L = t_a2450_L[b0];
     }
     const float unvc = 0.2046f / sqrtf(w0);
-    const unsigned vmask = t_a2450_vuv[pick<4, 5, 6, 7, 35>(dw)];
-    const float dg = t_a2450_dgain[pick<8, 9, 10, 11, 36>(dw)];
+    const unsigned vmask = t_a2450_vuv[(field<4, 4>(rb) << 1) | field<35, 1>(rb)];   // bits 4-7, 35
+    const float dg = t_a2450_dgain[(field<8, 4>(rb) << 1) | field<36, 1>(rb)];       // bits 8-11, 36
     for (int l = 1 + lane; l <= L; l += 32) {
         if (silence) {
             cur.Vl[l] = 0;
@@ -393,17 +410,19 @@ __device__ __forceinline__ int decode_ambe2450(const unsigned dw[3], WarpWS& ws,
     __syncwarp();
     AmbeBooks bk = {t_a2450_prba24, t_a2450_prba58, {t_a2450_hoc5, t_a2450_hoc6, t_a2450_hoc7, t_a2450_hoc8},
                     t_a2450_blocklen};
-    const int hocidx[4] = {(int)pick<24, 25, 26, 27, 44>(dw), (int)pick<28, 29, 30, 45>(dw), (int)pick<31, 32, 33, 46>(dw),
-                           (int)pick<34, 47, 48>(dw)};
-    ambe_tail(ws, T, bk, (int)pick<12, 13, 14, 15, 16, 17, 18, 19, 40>(dw), (int)pick<20, 21, 22, 23, 41, 42, 43>(dw), hocidx,
-              unvc, lane);
+    // b5 = bits 24-27, 44; b6 = 28-30, 45; b7 = 31-33, 46; b8 = 34, 47, 48; b3 = 12-19, 40; b4 = 20-23, 41-43
+    const int hocidx[4] = {(int)((field<24, 4>(rb) << 1) | field<44, 1>(rb)), (int)((field<28, 3>(rb) << 1) | field<45, 1>(rb)),
+                           (int)((field<31, 3>(rb) << 1) | field<46, 1>(rb)), (int)((field<34, 1>(rb) << 2) | field<47, 2>(rb))};
+    ambe_tail(ws, T, bk, (int)((field<12, 8>(rb) << 1) | field<40, 1>(rb)), (int)((field<20, 4>(rb) << 3) | field<41, 3>(rb)),
+              hocidx, unvc, lane);
     return 0;
 }
 
 // ---- AMBE 3600x2400 ---- returns 0 voice | 3 tone/silence marker | 5..122 D-STAR tone index
 __device__ __forceinline__ int decode_ambe2400(const unsigned dw[3], WarpWS& ws, const DevTables* T, int lane) {
     ParmsSmall& cur = ws.cur;
-    const int b0 = (int)pick<0, 1, 2, 3, 4, 5, 48>(dw);
+    const RevBits rb = rev_bits(dw);
+    const int b0 = (int)((field<0, 6>(rb) << 1) | field<48, 1>(rb));  // bits 0-5, 48
     if ((b0 & 0x7E) == 0x7E) {
         // three remapped high bits (t7,t6,t5 tables of the reference folded into one) + five literal bits
         const unsigned hi3 = (0x56732104u >> (4 * ((getbit(dw, 6) << 2) | (getbit(dw, 7) << 1) | getbit(dw, 8)))) & 7u;
@@ -428,8 +447,8 @@ __device__ __forceinline__ int decode_ambe2400(const unsigned dw[3], WarpWS& ws,
     const float w0 = T->a2400_w0[b0];
     const int L = t_a2400_L[b0];
     const float unvc = 0.2046f / sqrtf(w0);
-    const unsigned vmask = t_a2400_vuv[pick<38, 39, 40, 41>(dw)];
-    const float dg = t_a2400_dgain[pick<6, 7, 8, 9, 42, 43>(dw)];
+    const unsigned vmask = t_a2400_vuv[field<38, 4>(rb)];                              // bits 38-41
+    const float dg = t_a2400_dgain[(field<6, 4>(rb) << 2) | field<42, 2>(rb)];         // bits 6-9, 42, 43
     for (int l = 1 + lane; l <= L; l += 32) {
         int jl = (int)((float)l * 16.0f * f0);
         cur.Vl[l] = (int)((vmask >> jl) & 1u);
@@ -443,10 +462,11 @@ __device__ __forceinline__ int decode_ambe2400(const unsigned dw[3], WarpWS& ws,
     __syncwarp();
     AmbeBooks bk = {t_a2400_prba24, t_a2400_prba58, {t_a2400_hoc5, t_a2400_hoc6, t_a2400_hoc7, t_a2400_hoc8},
                     t_a2400_blocklen};
-    const int hocidx[4] = {(int)pick<22, 23, 25, 26>(dw), (int)pick<27, 28, 29, 30>(dw), (int)pick<31, 32, 33, 34>(dw),
-                           (int)(pick<35, 36, 37>(dw) << 1)};
-    ambe_tail(ws, T, bk, (int)pick<10, 11, 12, 13, 14, 15, 16, 44, 45>(dw), (int)pick<17, 18, 19, 20, 21, 46, 47>(dw), hocidx,
-              unvc, lane);
+    // b5 = bits 22, 23, 25, 26; b6 = 27-30; b7 = 31-34; b8 = 35-37 (LSB forced 0); b3 = 10-16, 44, 45; b4 = 17-21, 46, 47
+    const int hocidx[4] = {(int)((field<22, 2>(rb) << 2) | field<25, 2>(rb)), (int)field<27, 4>(rb), (int)field<31, 4>(rb),
+                           (int)(field<35, 3>(rb) << 1)};
+    ambe_tail(ws, T, bk, (int)((field<10, 7>(rb) << 2) | field<44, 2>(rb)), (int)((field<17, 5>(rb) << 2) | field<46, 2>(rb)),
+              hocidx, unvc, lane);
     return 0;
 }
 
