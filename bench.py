@@ -157,7 +157,26 @@ def cpu_model():
     return "unknown"
 
 
-def run_cpu_reference(codec, n_frames, steps, warmup, streams_per_thread):
+def channel_like_frames(codec, n_streams, n_frames, seed):
+    """BASELINE.json configs[4]-shaped soft input: valid encoded frames (random bits for IMBE 7100, whose encoder the
+    tests do not have), every channel bit flipped with p = 0.10, reliability 255 for unflipped and U[0,64) for flipped
+    bits.  Returns uint8 [streams][frames][bits][2]."""
+    import mbe_testlib as T
+    rng = np.random.default_rng(seed)
+    if codec == 1:
+        hard = T.random_hard_frames(codec, n_streams, n_frames, 0x7100)
+    else:
+        enc = T.encode_imbe7200_frame if codec == 0 else T.encode_ambe_frame
+        hard = np.zeros((n_streams, n_frames, FRAME_BITS[codec]), np.uint8)
+        for b in range(n_streams):
+            for f in range(n_frames):
+                pb = rng.integers(0, 2, size=T.PARAM_BITS[codec], dtype=np.uint8)
+                pb[0] = 0
+                hard[b, f] = enc(pb).reshape(-1)
+    return T.soften(hard, rng, flip_p=0.10)
+
+
+def run_cpu_reference(codec, n_frames, steps, warmup, streams_per_thread, soft=0, soft_channel=False):
     """Times the reference's CPU implementation (oracle/_ref dev-release build; the oracle port if the compiled
     reference is missing) on all host cores.  Returns (frames/s, info dict, seconds per step)."""
     import mbe_testlib as T
@@ -175,21 +194,33 @@ def run_cpu_reference(codec, n_frames, steps, warmup, streams_per_thread):
         fn = T.load_oracle().mbo_run
         kind = "port"
         flavour = "oracle/libmbe_oracle.so (C restatement)"
+    if soft:
+        streams_per_thread = max(1, streams_per_thread // 50)  # the reference's soft ECC is ~1 ms per IMBE frame
     S = min(cores * streams_per_thread, 65536)
-    frames = T.random_hard_frames(codec, S, n_frames, 0x2450)
+    if soft_channel:
+        base = channel_like_frames(codec, min(S, 128), n_frames, 0x50F7)
+        frames = np.ascontiguousarray(np.tile(base, ((S + len(base) - 1) // len(base), 1, 1, 1))[:S])
+    elif soft:
+        rng = np.random.default_rng(0x2450)
+        frames = np.stack([T.random_hard_frames(codec, S, n_frames, 0x2450),
+                           rng.integers(0, 256, size=(S, n_frames, FRAME_BITS[codec]), dtype=np.uint8)], axis=-1)
+    else:
+        frames = T.random_hard_frames(codec, S, n_frames, 0x2450)
     seeds = T.stream_seeds(S)
     pcm = np.zeros((S, n_frames, 160), np.int16)
     res = np.zeros((S, n_frames, 6), np.int32)
     times = []
     for it in range(warmup + steps):
-        sec = fn(codec, 0, S, n_frames, T._ptr(frames), T._ptr(seeds), T._ptr(pcm), None, T._ptr(res), None, None, cores)
+        sec = fn(codec, int(bool(soft)), S, n_frames, T._ptr(frames), T._ptr(seeds), T._ptr(pcm), None, T._ptr(res), None, None, cores)
         if it >= warmup:
             times.append(sec)
     sec = float(np.mean(times))
     fps = S * n_frames / sec
     info = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
-            "sample": "%d streams x %d frames per step (%d per thread), %s, one stream per task over %d pthreads, %s" % (
-                S, n_frames, streams_per_thread, CODEC_NAMES[codec], cores, flavour),
+            "sample": "%d streams x %d frames per step (%d per thread), %s %s, one stream per task over %d pthreads, %s" % (
+                S, n_frames, streams_per_thread, CODEC_NAMES[codec],
+                "soft-decision (10% flipped bits)" if soft_channel else ("soft-decision" if soft else "hard-decision"), cores,
+                flavour),
             "cpu_model": cpu_model(), "frames_per_s_per_core": fps / cores}
     return fps, info, sec
 
@@ -228,7 +259,8 @@ def main():
         if rank != 0:
             return 0
         warm = max(1, min(args.warmup, 3))
-        fps, info, sec = run_cpu_reference(codec, F, args.steps, warm, streams_per_thread=1000)
+        fps, info, sec = run_cpu_reference(codec, F, args.steps, warm, streams_per_thread=1000, soft=soft,
+                                           soft_channel=args.soft_channel)
         line = {"impl": "reference", "metric": "decoded frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -260,20 +292,8 @@ def main():
     gen.manual_seed(0x2450 + rank)
     d_frames = torch.randint(0, 2, (S, F, fb), dtype=torch.uint8, device=dev, generator=gen)
     if args.soft_channel:
-        import mbe_testlib as T
-        rng = np.random.default_rng(0x50F7 + rank)
         B = 128
-        if codec == 1:
-            hard = T.random_hard_frames(codec, B, F, 0x7100)
-        else:
-            enc = T.encode_imbe7200_frame if codec == 0 else T.encode_ambe_frame
-            hard = np.zeros((B, F, fb), np.uint8)
-            for b in range(B):
-                for f in range(F):
-                    pb = rng.integers(0, 2, size=T.PARAM_BITS[codec], dtype=np.uint8)
-                    pb[0] = 0
-                    hard[b, f] = enc(pb).reshape(-1)
-        base = torch.from_numpy(T.soften(hard, rng, flip_p=0.10)).to(dev)
+        base = torch.from_numpy(channel_like_frames(codec, B, F, 0x50F7 + rank)).to(dev)
         d_frames = base.repeat((S + B - 1) // B, 1, 1, 1)[:S].contiguous()
     elif soft:  # mbe_soft_bit {bit, reliability} pairs
         rel = torch.randint(0, 256, (S, F, fb), dtype=torch.uint8, device=dev, generator=gen)
@@ -412,7 +432,7 @@ def main():
             "roofline": roofline, "roofline_fp32": roofline_fp32}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        _, info, _ = run_cpu_reference(codec, F, 2, 1, streams_per_thread=1000)
+        _, info, _ = run_cpu_reference(codec, F, 2, 1, streams_per_thread=1000, soft=soft, soft_channel=args.soft_channel)
         line["cpu_baseline"] = info
     dec.close()
     if world > 1:

@@ -73,6 +73,7 @@ MBE_B200_API void mbe_b200_destroy(mbe_b200_ctx* ctx);
 MBE_B200_API const char* mbe_b200_last_error(const mbe_b200_ctx* ctx); /* ctx may be NULL: last create() error */
 MBE_B200_API const char* mbe_b200_version(void);
 MBE_B200_API int mbe_b200_geometry(int codec, int* frame_bits, int* param_bits); /* 184/168/96/96, 88/88/49/49 */
+MBE_B200_API int mbe_b200_device_count(void); /* usable CUDA devices (0 when there is none or the driver is missing) */
 /* kernel launches issued by this context so far (bench.py reports it as gpu_launches) */
 MBE_B200_API long long mbe_b200_launch_count(const mbe_b200_ctx* ctx);
 
@@ -157,6 +158,31 @@ MBE_B200_API int mbe_b200_floattoshort(mbe_b200_ctx* ctx, int n_frames, const fl
 MBE_B200_API int mbe_b200_floattoshort_dev(mbe_b200_ctx* ctx, int n_frames, const float* d_in, int16_t* d_out,
                                            void* cuda_stream);
 
+/* ---- many GPUs from one process ------------------------------------------------------
+ * A pool owns one context per device and shards the global stream range [0, max_streams) into contiguous blocks of
+ * ceil(max_streams / n_devices) streams, block i on device_ordinals[i] (NULL: devices 0..n-1; n_devices == 0: every
+ * visible device).  The same ordinal may be listed more than once (several contexts on one GPU).  A pool call runs the
+ * corresponding per-context call on every shard that owns part of the stream range, concurrently from one host thread
+ * per shard; all pointers are HOST pointers, laid out for the whole range exactly as in the per-context calls.  Nothing
+ * is exchanged between GPUs (streams are independent): the host only scatters frame bits and gathers PCM.  End to end
+ * the PCM gather is host-bandwidth bound on a many-GPU box; keep PCM device-resident through
+ * mbe_b200_pool_shard() + the _dev entry points when that matters. */
+typedef struct mbe_b200_pool mbe_b200_pool;
+MBE_B200_API int mbe_b200_pool_create(mbe_b200_pool** out, int n_devices, const int* device_ordinals, int max_streams);
+MBE_B200_API void mbe_b200_pool_destroy(mbe_b200_pool* pool);
+MBE_B200_API const char* mbe_b200_pool_last_error(const mbe_b200_pool* pool); /* pool may be NULL: last create() error */
+MBE_B200_API int mbe_b200_pool_shards(const mbe_b200_pool* pool);
+MBE_B200_API int mbe_b200_pool_shard(const mbe_b200_pool* pool, int shard, int* first_stream, int* n_streams,
+                                     mbe_b200_ctx** ctx);
+MBE_B200_API int mbe_b200_pool_init_streams(mbe_b200_pool* pool, int first_stream, int count, const uint32_t* seeds);
+MBE_B200_API int mbe_b200_pool_export_state(mbe_b200_pool* pool, int first_stream, int count, void* parms_triplets);
+MBE_B200_API int mbe_b200_pool_import_state(mbe_b200_pool* pool, int first_stream, int count, const void* parms_triplets);
+MBE_B200_API int mbe_b200_pool_process_frames(mbe_b200_pool* pool, int codec, int soft, int first_stream, int n_streams,
+                                              int n_frames, const uint8_t* frames, int16_t* pcm, float* pcmf,
+                                              mbe_b200_result* results, uint8_t* bits);
+MBE_B200_API int mbe_b200_pool_process_frames_packed(mbe_b200_pool* pool, int codec, int first_stream, int n_streams,
+                                                     int n_frames, const uint8_t* packed, int16_t* pcm, float* pcmf,
+                                                     mbe_b200_result* results, uint8_t* bits);
 /* profiling aid: per-stage clock64() sums of the stream kernel; all zero unless the library was built with
  * -DMBE_STAGE_TIMING=1.  out16[0..7] = {frame barrier, front-end + decode, enhance + synthesis
  * setup, count barrier, voiced bank, unvoiced + hand-over, output stores, state store}, out16[8..13] = inside the bank

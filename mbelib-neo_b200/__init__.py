@@ -34,7 +34,10 @@ _EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b
             "mbe_b200_decode_frames_dev", "mbe_b200_decode_frames", "mbe_b200_process_data_dev",
             "mbe_b200_process_data", "mbe_b200_synthesize_speech", "mbe_b200_synthesize_speech_rng", "mbe_b200_floattoshort",
             "mbe_b200_floattoshort_dev", "mbe_b200_synchronize", "mbe_b200_debug_stage_cycles",
-            "mbe_b200_set_normalized_float", "mbe_b200_packed_frame_bytes", "mbe_b200_process_frames_packed_dev", "mbe_b200_process_frames_packed"]
+            "mbe_b200_set_normalized_float", "mbe_b200_packed_frame_bytes", "mbe_b200_process_frames_packed_dev", "mbe_b200_process_frames_packed",
+            "mbe_b200_device_count", "mbe_b200_pool_create", "mbe_b200_pool_destroy", "mbe_b200_pool_last_error",
+            "mbe_b200_pool_shards", "mbe_b200_pool_shard", "mbe_b200_pool_init_streams", "mbe_b200_pool_export_state",
+            "mbe_b200_pool_import_state", "mbe_b200_pool_process_frames", "mbe_b200_pool_process_frames_packed"]
 
 _lib = None
 
@@ -84,6 +87,18 @@ def load_library():
         lib.mbe_b200_floattoshort_dev.argtypes = [vp, ci, vp, vp, vp]
         lib.mbe_b200_synchronize.argtypes = [vp]
         lib.mbe_b200_debug_stage_cycles.argtypes = [vp, vp, ci]
+        lib.mbe_b200_pool_create.argtypes = [ctypes.POINTER(vp), ci, vp, ci]
+        lib.mbe_b200_pool_destroy.argtypes = [vp]
+        lib.mbe_b200_pool_destroy.restype = None
+        lib.mbe_b200_pool_last_error.argtypes = [vp]
+        lib.mbe_b200_pool_last_error.restype = ctypes.c_char_p
+        lib.mbe_b200_pool_shards.argtypes = [vp]
+        lib.mbe_b200_pool_shard.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(vp)]
+        lib.mbe_b200_pool_init_streams.argtypes = [vp, ci, ci, vp]
+        lib.mbe_b200_pool_export_state.argtypes = [vp, ci, ci, vp]
+        lib.mbe_b200_pool_import_state.argtypes = [vp, ci, ci, vp]
+        lib.mbe_b200_pool_process_frames.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp]
+        lib.mbe_b200_pool_process_frames_packed.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]
         _lib = lib
     return _lib
 
@@ -106,6 +121,76 @@ def _p(a):
     if isinstance(a, int):
         return ctypes.c_void_p(a)
     return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Pool:
+    """Many GPUs from one process: one context per device, the stream range sharded in contiguous blocks
+    (mbe_b200_pool_*).  `devices`: list of CUDA ordinals (an ordinal may repeat), or None for every visible device."""
+
+    def __init__(self, max_streams, devices=None):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p()
+        n = 0 if devices is None else len(devices)
+        arr = (ctypes.c_int * n)(*devices) if n else None
+        rc = self.lib.mbe_b200_pool_create(ctypes.byref(self.h), n, arr, int(max_streams))
+        if rc != 0:
+            raise MbeB200Error("mbe_b200_pool_create failed (%d): %s" % (rc, self.lib.mbe_b200_pool_last_error(None).decode()))
+        self.max_streams = int(max_streams)
+
+    def close(self):
+        if self.h:
+            self.lib.mbe_b200_pool_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise MbeB200Error("%s failed (%d): %s" % (what, rc, self.lib.mbe_b200_pool_last_error(self.h).decode()))
+
+    def shards(self):
+        """[(first_stream, n_streams)] per shard."""
+        out = []
+        for i in range(self.lib.mbe_b200_pool_shards(self.h)):
+            a, b = ctypes.c_int(), ctypes.c_int()
+            self._check(self.lib.mbe_b200_pool_shard(self.h, i, ctypes.byref(a), ctypes.byref(b), None), "pool_shard")
+            out.append((a.value, b.value))
+        return out
+
+    def init_streams(self, first, count, seeds=None):
+        if seeds is not None:
+            seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        self._check(self.lib.mbe_b200_pool_init_streams(self.h, first, count, _p(seeds)), "pool_init_streams")
+
+    def export_state(self, first=0, count=None):
+        count = self.max_streams - first if count is None else count
+        out = np.zeros((count, 3, PARMS_BYTES), np.uint8)
+        self._check(self.lib.mbe_b200_pool_export_state(self.h, first, count, _p(out)), "pool_export_state")
+        return out
+
+    def import_state(self, blobs, first=0):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(-1, 3, PARMS_BYTES)
+        self._check(self.lib.mbe_b200_pool_import_state(self.h, first, blobs.shape[0], _p(blobs)), "pool_import_state")
+
+    def process_frames(self, codec, frames, soft=False, first_stream=0, want_float=False, packed=False):
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        S, F = frames.shape[0], frames.shape[1]
+        pcm = np.zeros((S, F, SAMPLES), np.int16)
+        pcmf = np.zeros((S, F, SAMPLES), np.float32) if want_float else None
+        res = np.zeros((S, F), RESULT_DTYPE)
+        bits = np.zeros((S, F, PARAM_BITS[codec]), np.uint8)
+        if packed:
+            rc = self.lib.mbe_b200_pool_process_frames_packed(self.h, codec, first_stream, S, F, _p(frames), _p(pcm), _p(pcmf),
+                                                              _p(res), _p(bits))
+        else:
+            rc = self.lib.mbe_b200_pool_process_frames(self.h, codec, int(bool(soft)), first_stream, S, F, _p(frames), _p(pcm),
+                                                       _p(pcmf), _p(res), _p(bits))
+        self._check(rc, "pool_process_frames")
+        return dict(pcm=pcm, pcmf=pcmf, results=res, bits=bits)
 
 
 class Decoder:

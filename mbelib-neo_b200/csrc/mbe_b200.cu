@@ -1202,6 +1202,15 @@ const char* mbe_b200_last_error(const mbe_b200_ctx* ctx) { return ctx ? ctx->err
 
 long long mbe_b200_launch_count(const mbe_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int mbe_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 int mbe_b200_geometry(int codec, int* frame_bits, int* param_bits) {
     if (codec < 0 || codec > 3) {
         return MBE_B200_E_ARG;

@@ -75,3 +75,14 @@ def test_product_does_not_link_the_oracle(pkg):
     assert "oracle" not in out and "mberef" not in out
     src = open(os.path.join(ROOT, "mbelib-neo_b200", "__init__.py")).read()
     assert "oracle" not in src.replace("no CPU fallback", "")
+
+
+def test_pool_has_no_cpu_fallback(pkg):
+    """mbe_b200_pool_create over "every visible device" fails with MBE_B200_E_NOGPU when there is none."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    assert pkg.load_library().mbe_b200_device_count() == 0
+    with pytest.raises(pkg.MbeB200Error) as e:
+        pkg.Pool(max_streams=8)
+    assert "-3" in str(e.value)

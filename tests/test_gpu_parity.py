@@ -332,3 +332,50 @@ def test_stream_window_and_degenerate_batches(dec):
     # out-of-range windows are refused, not clipped
     with pytest.raises(Exception):
         dec.process_frames(codec, frames, first_stream=dec.max_streams - 3)
+
+
+@pytest.mark.parametrize("codec", [0, 1, 2, 3])
+def test_soft_decode_degenerate_reliabilities(dec, codec):
+    """Soft-decision ECC on reliability patterns that force ties and defeat the hard decode (the tie-break order of
+    src/ecc/ecc.c:54-67,196-197 decides): all-equal reliabilities, erasures, two- and three-level reliabilities, flipped
+    bits that claim to be reliable.  ECC stage only (mbe_b200_decode_frames) against the oracle, frame by frame."""
+    import ctypes
+    oracle = T.load_oracle()
+    oracle.mbo_decode_frame.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.default_rng(900 + codec)
+    n = 40 if codec < 2 else 96
+    fb, pb = T.FRAME_BITS[codec], T.PARAM_BITS[codec]
+    enc = {0: T.encode_imbe7200_frame, 2: T.encode_ambe_frame, 3: T.encode_ambe_frame}.get(codec)
+    patterns = {
+        "all 0": lambda s: np.zeros(s, np.uint8),
+        "all 255": lambda s: np.full(s, 255, np.uint8),
+        "all 7": lambda s: np.full(s, 7, np.uint8),
+        "0 or 255": lambda s: (rng.integers(0, 2, size=s) * 255).astype(np.uint8),
+        "0..2": lambda s: rng.integers(0, 3, size=s).astype(np.uint8),
+        "mostly 0, some 1": lambda s: (rng.random(s) < 0.2).astype(np.uint8),
+    }
+    for name, make in patterns.items():
+        if enc is not None:
+            hard = np.zeros((n, fb), np.uint8)
+            for i in range(n):
+                p = rng.integers(0, 2, size=pb, dtype=np.uint8)
+                hard[i] = enc(p).reshape(-1)
+            flips = rng.random(hard.shape) < 0.12
+            bits_in = hard ^ flips.astype(np.uint8)
+        else:
+            bits_in = rng.integers(0, 2, size=(n, fb), dtype=np.uint8)
+            flips = np.zeros(bits_in.shape, bool)
+        rel = make(bits_in.shape)
+        if name == "0 or 255":
+            rel = np.where(flips, 255, rel).astype(np.uint8)  # the flipped bits claim to be reliable
+        frames = np.ascontiguousarray(np.stack([bits_in, rel], axis=-1))
+        got_bits, got_res = dec.decode_frames(codec, frames, soft=True)
+        for i in range(n):
+            wb = np.zeros(pb, np.uint8)
+            wr = np.zeros(5, np.int32)
+            rc = oracle.mbo_decode_frame(codec, 1, frames[i].ctypes.data, wb.ctypes.data, wr.ctypes.data)
+            assert got_res["status"][i] == rc, (name, i)
+            assert np.array_equal(got_bits[i], wb), (name, i)
+            assert (got_res["c0_errors"][i], got_res["protected_errors"][i], got_res["c4_errors"][i],
+                    got_res["total_errors"][i]) == tuple(int(x) for x in wr[:4]), (name, i)
+            assert int(got_res["flags"][i]) == int(np.uint32(wr[4])), (name, i)

@@ -1,0 +1,67 @@
+"""Many GPUs from one process (mbe_b200_pool_*): the stream range is sharded in contiguous blocks over
+per-device contexts, nothing is exchanged between them.  On a one-GPU box the pool lists ordinal 0 several times (several
+contexts on one GPU), which exercises the same sharding, offset and threading logic; with more GPUs visible it uses them
+all.  Results must equal the single-context path bit for bit wherever a stream lands."""
+import numpy as np
+import pytest
+
+import mbe_testlib as T
+from __graft_entry__ import load_package
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return load_package()
+
+
+def _devices(n):
+    import torch
+    have = torch.cuda.device_count()
+    return [i % have for i in range(n)]
+
+
+@pytest.mark.parametrize("n_shards,codec", [(3, 3), (2, 0), (5, 2)])
+def test_pool_equals_single_context(pkg, n_shards, codec):
+    S, F = 100, 12                       # ragged: 100 streams do not divide evenly into 3 or 5 shards
+    frames = T.random_hard_frames(codec, S, 2 * F, 0xA00 + codec)
+    seeds = T.stream_seeds(S, 0xBEEF)
+    one = pkg.Decoder(max_streams=S, device=0)
+    one.init_streams(0, S, seeds)
+    want_a = one.process_frames(codec, frames[:, :F], want_float=True)
+    want_b = one.process_frames(codec, frames[:, F:], want_float=True)
+    want_state = one.export_state(0, S)
+    one.close()
+
+    pool = pkg.Pool(S, devices=_devices(n_shards))
+    sh = pool.shards()
+    assert len(sh) == n_shards and sh[0][0] == 0 and sum(n for _, n in sh) == S
+    assert all(sh[i][0] + sh[i][1] == sh[i + 1][0] for i in range(n_shards - 1))
+    pool.init_streams(0, S, seeds)
+    got_a = pool.process_frames(codec, frames[:, :F], want_float=True)
+    # second half through two windows that straddle shard boundaries, the second one bit-packed
+    cut = sh[0][1] + 3
+    got_b1 = pool.process_frames(codec, frames[:cut, F:], first_stream=0, want_float=True)
+    got_b2 = pool.process_frames(codec, pkg.pack_frames(codec, frames[cut:, F:]), first_stream=cut, want_float=True, packed=True)
+    for k in ("pcm", "bits"):
+        assert np.array_equal(got_a[k], want_a[k]), k
+        assert np.array_equal(np.concatenate([got_b1[k], got_b2[k]]), want_b[k]), k
+    assert np.array_equal(got_a["pcmf"].view(np.uint32), want_a["pcmf"].view(np.uint32))
+    assert np.array_equal(np.concatenate([got_b1["results"], got_b2["results"]]), want_b["results"])
+    assert np.array_equal(pool.export_state(0, S), want_state)
+    # state moves between pools of different shapes (a stream changes device)
+    other = pkg.Pool(S, devices=_devices(2 if n_shards != 2 else 3))
+    other.import_state(want_state[10:90], first=10)
+    assert np.array_equal(other.export_state(10, 80), want_state[10:90])
+    other.close()
+    pool.close()
+
+
+def test_pool_range_errors(pkg):
+    pool = pkg.Pool(16, devices=_devices(2))
+    with pytest.raises(pkg.MbeB200Error):
+        pool.init_streams(10, 7)
+    with pytest.raises(pkg.MbeB200Error):
+        pool.process_frames(3, np.zeros((17, 1, 96), np.uint8))
+    pool.close()

@@ -18,6 +18,12 @@ for codec in (3, 0, 2, 1):
     soft = T.soften(frames, rng, flip_p=0.05)
     dec.init_streams(0, S, T.stream_seeds(S))
     r2 = dec.process_frames(codec, soft, soft=True)
+    # random reliabilities: every row runs the full soft-decision search
+    soft[..., 1] = rng.integers(0, 256, size=soft[..., 1].shape)
+    dec.init_streams(0, S, T.stream_seeds(S))
+    r2b = dec.process_frames(codec, soft, soft=True)
+    bits, res = dec.decode_frames(codec, soft.reshape(S * F, -1), soft=True)
+    assert np.array_equal(bits.reshape(S, F, -1), r2b["bits"])
     dec.init_streams(0, S, T.stream_seeds(S))
     r3 = dec.process_frames_packed(codec, pkg.pack_frames(codec, frames))
     assert np.array_equal(r["pcm"], r3["pcm"])
