@@ -139,6 +139,31 @@ class ClockSampler:
                 "power_w": round(max(r[2] for r in self.rows), 1), "samples": len(self.rows), "source": self.source}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank (and first-touch its pinned host buffers) on the CPUs next to its GPU: with eight ranks gathering
+    PCM at once the host side is the limit, and remote-node staging makes it worse.  Returns a short
+    description; does nothing when the box exposes no NUMA topology."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read().strip())
+        if node < 0:
+            return "numa: none exposed (%s)" % bdf
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "numa: node %d has no allowed cpu" % node
+        os.sched_setaffinity(0, cpus)
+        return "numa: node %d, %d cpus (%s)" % (node, len(cpus), bdf)
+    except Exception as e:
+        return "numa: not bound (%s)" % type(e).__name__
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -277,6 +302,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)")
     pkg = load_package()
     torch.cuda.set_device(local_rank)
+    numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 else "numa: single rank, not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -374,7 +400,7 @@ def main():
         barrier()
         e2e = {"value": world * S * F * args.steps / e2e_s, "unit": "frames/s",
                "h2d_bytes_per_step": int(S * F * fb * (2 if soft else 1)), "d2h_bytes_per_step": int(S * F * (320 + RESULT_BYTES)),
-               "ms_per_step": e2e_s * 1e3 / args.steps,
+               "ms_per_step": e2e_s * 1e3 / args.steps, "host_binding": numa_note,
                "note": "mbe_b200_process_frames: pinned host bits in, int16 PCM + results to pinned host memory, "
                        "wall clock around the blocking calls, max over ranks"}
         if float(np.abs(np_pcm[:64]).max()) == 0:

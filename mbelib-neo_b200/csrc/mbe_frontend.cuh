@@ -50,8 +50,9 @@ __device__ __forceinline__ unsigned hamming_hard(unsigned w15, int variant, cons
 // with d' = data ^ received data, the difference pattern of a candidate is (d', parity(d') ^ syndrome), so
 //   key(d') = cost << 16 | differing bits << 12 | data  =  KA[d' >> 6] + KB[d' & 63] + CP[par(d' >> 6) ^ par(d' & 63) ^ syn] << 16
 // is a sum of three table terms (every field is additive and cannot carry).  A lane keeps KB / par of its two low
-// halves in registers and walks the 64 high halves: one 16-bit shared-memory load and three integer instructions
-// per candidate.  The hard decode is the only candidate that wins ties on "equal to the hard decode", so it is
+// halves in registers and walks the high halves: one 16-bit shared-memory load and a few integer instructions per
+// candidate; the complement of a candidate is a candidate as well (all-ones is a codeword) and its key is a constant
+// minus the key, so only half of the high halves are walked, tracking minimum and maximum.  The hard decode is the only candidate that wins ties on "equal to the hard decode", so it is
 // the answer unless some candidate costs strictly less than it does; and when the (dmin - t) least reliable
 // positions outside its t corrected positions already weigh at least as much as those t, nothing can cost less
 // and the search is skipped altogether.
@@ -59,6 +60,7 @@ struct SoftScratch {
     unsigned short* cp;  // 2048 x uint16 (4-byte aligned): cost of every 11-bit parity difference pattern
     unsigned* ka;        // 64 x uint32: partial key of each high data half
     unsigned short* qa;  // 64 x uint16: (parity of the high data half ^ syndrome) as a byte offset into cp
+                         // (the first 32 / 16 entries of ka and qa are used: see the complement rule below)
 };
 
 // sum of the k least reliable positions outside `inside` (bit p = position p), nbits positions in all
@@ -108,9 +110,7 @@ __device__ __forceinline__ unsigned golay_soft(unsigned hard23, const unsigned c
     const unsigned hdh = hd >> 6, hdl = hd & 63u;
     __syncwarp();
     S.ka[lane] = (sA << 16) | (pl << 12) | ((((unsigned)lane) ^ hdh) << 6);
-    S.ka[lane + 32] = ((sA + (unsigned)rel[22]) << 16) | ((pl + 1u) << 12) | ((((unsigned)lane + 32u) ^ hdh) << 6);
     S.qa[lane] = (unsigned short)(((unsigned)T->golay_par_hi[lane] ^ syn) << 1);
-    S.qa[lane + 32] = (unsigned short)(((unsigned)T->golay_par_hi[lane + 32] ^ syn) << 1);
     const unsigned kb0 = (sB << 16) | (pl << 12) | (((unsigned)lane) ^ hdl);
     const unsigned kb1 = ((sB + (unsigned)rel[16]) << 16) | ((pl + 1u) << 12) | (((unsigned)lane + 32u) ^ hdl);
     const unsigned pb0 = (unsigned)T->golay_par_lo[lane] << 1;
@@ -127,17 +127,23 @@ __device__ __forceinline__ unsigned golay_soft(unsigned hard23, const unsigned c
     }
     __syncwarp();
     const unsigned char* cpb = reinterpret_cast<const unsigned char*>(S.cp);
-    unsigned best = 0xffffffffu;
+    // The all-ones word is a codeword, so the complement of every candidate is a candidate too, and its key is
+    // KMAX - key with no borrow between the fields (cost -> total - cost, differing bits -> 12 - n, data -> 0xfff - data):
+    // walk the 32 high halves with a clear top bit, keep the smallest AND the largest key
+    const unsigned total = soft_cost_of(rel, 0x7fffffu, 23, lane);
+    const unsigned kmax = (total << 16) | (12u << 12) | 0xfffu;
+    unsigned best = 0xffffffffu, worst = 0u;
 #pragma unroll 8
-    for (int a = 0; a < 64; ++a) {
+    for (int a = 0; a < 32; ++a) {
         const unsigned q = S.qa[a];
         const unsigned k = S.ka[a];
         const unsigned c0 = *reinterpret_cast<const unsigned short*>(cpb + (q ^ pb0));
         const unsigned c1 = *reinterpret_cast<const unsigned short*>(cpb + (q ^ pb1));
-        best = min(best, ((c0 << 16) + kb0) + k);
-        best = min(best, ((c1 << 16) + kb1) + k);
+        const unsigned k0 = ((c0 << 16) + kb0) + k, k1 = ((c1 << 16) + kb1) + k;
+        best = min(best, min(k0, k1));
+        worst = max(worst, max(k0, k1));
     }
-    best = __reduce_min_sync(FULL, best);
+    best = __reduce_min_sync(FULL, min(best, kmax - worst));
     __syncwarp();
     if ((best >> 16) < U) {
         *errs = (int)((best >> 12) & 15u);
@@ -197,17 +203,21 @@ __device__ __forceinline__ unsigned hamming_soft(unsigned hard15, const unsigned
     const unsigned pb1 = (unsigned)T->ham_par_lo[V][lane + 32] << 2;
     __syncwarp();
     const unsigned char* cpb = reinterpret_cast<const unsigned char*>(S.cp);
-    unsigned best = 0xffffffffu;
+    // all-ones is a codeword of both layouts (every check row has even weight): complements as in golay_soft
+    const unsigned total = soft_cost_of(rel, 0x7fffu, 15, lane);
+    const unsigned kmax = (total << 16) | (15u << 11) | 0x7ffu;
+    unsigned best = 0xffffffffu, worst = 0u;
 #pragma unroll 8
-    for (int a = 0; a < 32; ++a) {
+    for (int a = 0; a < 16; ++a) {
         const unsigned q = S.qa[a];
         const unsigned k = S.ka[a];
         const unsigned c0 = *reinterpret_cast<const unsigned*>(cpb + (q ^ pb0));
         const unsigned c1 = *reinterpret_cast<const unsigned*>(cpb + (q ^ pb1));
-        best = min(best, (c0 + kb0) + k);
-        best = min(best, (c1 + kb1) + k);
+        const unsigned k0 = (c0 + kb0) + k, k1 = (c1 + kb1) + k;
+        best = min(best, min(k0, k1));
+        worst = max(worst, max(k0, k1));
     }
-    best = __reduce_min_sync(FULL, best);
+    best = __reduce_min_sync(FULL, min(best, kmax - worst));
     __syncwarp();
     if ((best >> 16) < U) {
         *errs = (int)((best >> 11) & 15u);
