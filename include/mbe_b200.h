@@ -118,6 +118,15 @@ MBE_B200_API int mbe_b200_set_normalized_float(mbe_b200_ctx* ctx, int enable);
  * Semantics per frame are those of mbe_process<Codec>Frame[f]; a packed bit can only be 0 or 1, so
  * MBE_STATUS_INVALID_BITS cannot occur. */
 MBE_B200_API int mbe_b200_packed_frame_bytes(int codec);
+/* Channel map (on-device de-interleave): by default packed bit k is frame position k.  With a map,
+ * the packed frame holds the n_bits transmitted bits of the air interface in transmission order (MSB first, n_bits <=
+ * rows*cols, mbe_b200_channel_frame_bytes() bytes per frame) and transmitted bit k lands at frame position
+ * map[k] = r*cols + c of the reference's `fr[r][c]`; positions no transmitted bit maps to read 0 (the unused corners of
+ * the reference's bit planes).  The de-interleave schedule itself is the air interface's (P25 LDU, DMR burst, D-STAR,
+ * ...) and is supplied by the caller; the reference leaves it to the caller too.  map == NULL restores the identity.
+ * A configuration call: it synchronises the device.  Applies to mbe_b200_process_frames_packed[_dev] of that codec. */
+MBE_B200_API int mbe_b200_set_channel_map(mbe_b200_ctx* ctx, int codec, const uint16_t* map, int n_bits);
+MBE_B200_API int mbe_b200_channel_frame_bytes(const mbe_b200_ctx* ctx, int codec);
 MBE_B200_API int mbe_b200_process_frames_packed_dev(mbe_b200_ctx* ctx, int codec, int first_stream, int n_streams,
                                                     int n_frames, const uint8_t* d_packed, int16_t* d_pcm, float* d_pcmf,
                                                     mbe_b200_result* d_results, uint8_t* d_bits, void* cuda_stream);
@@ -180,6 +189,7 @@ MBE_B200_API int mbe_b200_pool_import_state(mbe_b200_pool* pool, int first_strea
 MBE_B200_API int mbe_b200_pool_process_frames(mbe_b200_pool* pool, int codec, int soft, int first_stream, int n_streams,
                                               int n_frames, const uint8_t* frames, int16_t* pcm, float* pcmf,
                                               mbe_b200_result* results, uint8_t* bits);
+MBE_B200_API int mbe_b200_pool_set_channel_map(mbe_b200_pool* pool, int codec, const uint16_t* map, int n_bits);
 MBE_B200_API int mbe_b200_pool_process_frames_packed(mbe_b200_pool* pool, int codec, int first_stream, int n_streams,
                                                      int n_frames, const uint8_t* packed, int16_t* pcm, float* pcmf,
                                                      mbe_b200_result* results, uint8_t* bits);

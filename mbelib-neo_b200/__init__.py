@@ -35,6 +35,7 @@ _EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b
             "mbe_b200_process_data", "mbe_b200_synthesize_speech", "mbe_b200_synthesize_speech_rng", "mbe_b200_floattoshort",
             "mbe_b200_floattoshort_dev", "mbe_b200_synchronize", "mbe_b200_debug_stage_cycles",
             "mbe_b200_set_normalized_float", "mbe_b200_packed_frame_bytes", "mbe_b200_process_frames_packed_dev", "mbe_b200_process_frames_packed",
+            "mbe_b200_set_channel_map", "mbe_b200_channel_frame_bytes", "mbe_b200_pool_set_channel_map",
             "mbe_b200_device_count", "mbe_b200_pool_create", "mbe_b200_pool_destroy", "mbe_b200_pool_last_error",
             "mbe_b200_pool_shards", "mbe_b200_pool_shard", "mbe_b200_pool_init_streams", "mbe_b200_pool_export_state",
             "mbe_b200_pool_import_state", "mbe_b200_pool_process_frames", "mbe_b200_pool_process_frames_packed"]
@@ -87,6 +88,9 @@ def load_library():
         lib.mbe_b200_floattoshort_dev.argtypes = [vp, ci, vp, vp, vp]
         lib.mbe_b200_synchronize.argtypes = [vp]
         lib.mbe_b200_debug_stage_cycles.argtypes = [vp, vp, ci]
+        lib.mbe_b200_set_channel_map.argtypes = [vp, ci, vp, ci]
+        lib.mbe_b200_channel_frame_bytes.argtypes = [vp, ci]
+        lib.mbe_b200_pool_set_channel_map.argtypes = [vp, ci, vp, ci]
         lib.mbe_b200_pool_create.argtypes = [ctypes.POINTER(vp), ci, vp, ci]
         lib.mbe_b200_pool_destroy.argtypes = [vp]
         lib.mbe_b200_pool_destroy.restype = None
@@ -265,6 +269,17 @@ class Decoder:
         self._check(self.lib.mbe_b200_process_frames(self.h, codec, int(bool(soft)), first_stream, S, F, _p(frames),
                                                      _p(pcm), _p(pcmf), _p(res), _p(bits)), "process_frames")
         return dict(pcm=pcm, pcmf=pcmf, results=res, bits=bits)
+
+    def set_channel_map(self, codec, channel_map=None):
+        """channel_map[k] = frame position (r*cols + c) of transmitted bit k of the bit-packed input; None = identity."""
+        if channel_map is None:
+            self._check(self.lib.mbe_b200_set_channel_map(self.h, codec, None, 0), "set_channel_map")
+        else:
+            m = np.ascontiguousarray(channel_map, dtype=np.uint16)
+            self._check(self.lib.mbe_b200_set_channel_map(self.h, codec, _p(m), int(m.size)), "set_channel_map")
+
+    def channel_frame_bytes(self, codec):
+        return int(self.lib.mbe_b200_channel_frame_bytes(self.h, codec))
 
     def set_normalized_float(self, enable):
         self._check(self.lib.mbe_b200_set_normalized_float(self.h, int(bool(enable))), "set_normalized_float")

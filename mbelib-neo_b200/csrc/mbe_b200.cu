@@ -514,8 +514,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
     constexpr int fbits = (CODEC == MBE_B200_IMBE7200X4400) ? 184 : (CODEC == MBE_B200_IMBE7100X4400 ? 168 : 96);
     constexpr int pbits = AMBE ? 49 : 88;
     constexpr bool PACKED = (SOFT == 2);
-    constexpr size_t fstride = (MODE == MODE_DATA) ? (size_t)pbits
-                                                   : (PACKED ? (size_t)((fbits + 7) / 8) : (size_t)fbits * (SOFT == 1 ? 2u : 1u));
+    const size_t fstride = (MODE == MODE_DATA) ? (size_t)pbits
+                                               : (PACKED ? (size_t)A.packed_bytes : (size_t)fbits * (SOFT == 1 ? 2u : 1u));
 
     uint32_t* gs = A.state + (size_t)(A.first_stream + (live ? s : 0)) * STATE_WORDS;
     const StreamHome home = {gs, gs + PARMS_WORDS, gs + 2 * PARMS_WORDS, gs + SPILL_WORD};
@@ -898,6 +898,7 @@ constexpr int MAX_CHUNKS = 32;
 struct mbe_b200_ctx {
     int device;
     int max_streams;
+    int chan_bits[4];      // transmitted bits per bit-packed frame (channel map; default = rows * cols)
     int normalized_float;  // float PCM outputs scaled by 7/32768 (mbelib.h:16-20) instead of the historical scale
     uint32_t* d_state;
     DevTables* d_tab;
@@ -1059,6 +1060,11 @@ static void build_tables(DevTables* t) {
         t->golay_cw[d] = (d << 11) | (unsigned)(t->golay_par_hi[d >> 6] ^ t->golay_par_lo[d & 63]);
     }
     memcpy(t->golay_fix, hosttab::t_golay_fix, sizeof(t->golay_fix));
+    for (int c = 0; c < 4; ++c) {
+        for (int i = 0; i < 184; ++i) {
+            t->chan_src[c][i] = (unsigned short)i;
+        }
+    }
     // Hamming(15,11), standard and IMBE-7100 layouts (ecc_const.c:17-19, ecc.c:133-136)
     {
         const unsigned short rows[2][4] = {{0x7f08, 0x78e4, 0x66d2, 0x55b1}, {0x7ac8, 0x3d64, 0x1eb2, 0x7591}};
@@ -1246,6 +1252,11 @@ int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams) {
     ctx->max_streams = max_streams;
     DevTables* ht = (DevTables*)malloc(sizeof(DevTables));
     build_tables(ht);
+    for (int c = 0; c < 4; ++c) {
+        int fb0 = 0, pb0 = 0;
+        mbe_b200_geometry(c, &fb0, &pb0);
+        ctx->chan_bits[c] = fb0;
+    }
     ctx->imbe_default_w0 = ht->imbe_default_w0;
     ctx->imbe_default_L = ht->imbe_default_L;
 #define CUC(call)                                                                  \
@@ -1434,6 +1445,7 @@ int mbe_b200_import_rng(mbe_b200_ctx* ctx, int first, int count, const uint32_t*
 static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaStream_t st) {
     LaunchArgs a = a_in;
     a.pcmf_scale = ctx->normalized_float ? (7.0f / 32768.0f) : 1.0f;
+    a.packed_bytes = (a.mode == MODE_FRAMES && a.soft == 2) ? (ctx->chan_bits[a.codec] + 7) / 8 : 0;
     const int blocks = (a.n_streams + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     if (a.mode == MODE_SYNTH) {
         mbe_synth_kernel<<<blocks, WARPS_PER_BLOCK * 32, stream_kernel_smem(), st>>>(a);
@@ -1469,6 +1481,42 @@ int mbe_b200_set_normalized_float(mbe_b200_ctx* ctx, int enable) {
         return MBE_B200_E_ARG;
     }
     ctx->normalized_float = enable ? 1 : 0;
+    return 0;
+}
+
+int mbe_b200_channel_frame_bytes(const mbe_b200_ctx* ctx, int codec) {
+    if (!ctx || codec < 0 || codec > 3) {
+        return MBE_B200_E_ARG;
+    }
+    return (ctx->chan_bits[codec] + 7) / 8;
+}
+
+int mbe_b200_set_channel_map(mbe_b200_ctx* ctx, int codec, const uint16_t* map, int n_bits) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    int fb, pb;
+    if (mbe_b200_geometry(codec, &fb, &pb) != 0 || (map && (n_bits < 1 || n_bits > fb))) {
+        return fail(ctx, MBE_B200_E_ARG, "set_channel_map: bad argument", cudaSuccess);
+    }
+    unsigned short src[184];
+    for (int i = 0; i < 184; ++i) {
+        src[i] = map ? 0xffffu : (unsigned short)i;
+    }
+    if (map) {
+        for (int k = 0; k < n_bits; ++k) {
+            if (map[k] >= fb || src[map[k]] != 0xffffu) {
+                return fail(ctx, MBE_B200_E_ARG, "set_channel_map: position out of range or used twice", cudaSuccess);
+            }
+            src[map[k]] = (unsigned short)k;
+        }
+    } else {
+        n_bits = fb;
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());  // configuration call: no launch of this device may still be reading the old map
+    CU(cudaMemcpy(&ctx->d_tab->chan_src[codec][0], src, sizeof(src), cudaMemcpyHostToDevice));
+    ctx->chan_bits[codec] = n_bits;
     return 0;
 }
 
@@ -1654,7 +1702,7 @@ static int frames_host_impl(mbe_b200_ctx* ctx, int codec, int kind, int first_st
     CU(cudaSetDevice(ctx->device));
     int fb, pb;
     mbe_b200_geometry(codec, &fb, &pb);
-    const size_t in_per_frame = (kind == 2) ? (size_t)((fb + 7) / 8) : (size_t)fb * (kind == 1 ? 2 : 1);
+    const size_t in_per_frame = (kind == 2) ? (size_t)((ctx->chan_bits[codec] + 7) / 8) : (size_t)fb * (kind == 1 ? 2 : 1);
     const size_t per_frame[4] = {pcm ? NS * sizeof(int16_t) : 0, pcmf ? NS * sizeof(float) : 0,
                                  results ? sizeof(mbe_b200_result) : 0, bits ? (size_t)pb : 0};
     if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, nf * in_per_frame)) < 0) {

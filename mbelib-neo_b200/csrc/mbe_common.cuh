@@ -190,6 +190,9 @@ struct DevTables {
     // creation by the reference's own rotation recurrence (mbelib.c:412-424) so the values are the ones the
     // enhancement would compute frame by frame.  Row r belongs to the fundamental cosw_w0[r]; a frame whose w0 is not
     // bitwise equal to its row's runs the recurrence itself.
+    // channel map of the bit-packed input (mbe_b200_set_channel_map): frame position r*cols + c takes transmitted bit
+    // chan_src[codec][pos] of the packed frame (0xffff: the position is not transmitted and reads 0); identity by default
+    unsigned short chan_src[4][184];
     float cosw_w0[COSW_ROWS];
     float cosw[COSW_ROWS][57];
 };
@@ -213,6 +216,7 @@ struct LaunchArgs {
     const uint32_t* synth_seeds;
     uint32_t* synth_rng;        // MODE_SYNTH: [n][4] RNG words in/out (overrides synth_seeds)
     unsigned long long* dbg;    // MBE_STAGE_TIMING builds: 16 accumulated per-stage cycle counters
+    int packed_bytes;           // bit-packed input: bytes per frame (transmitted bits of the channel map, rounded up)
     float pcmf_scale;           // float PCM is multiplied by this on store: 1 (reference scale) or 7/32768 (normalised)
 };
 

@@ -254,7 +254,8 @@ __device__ __forceinline__ unsigned getbit(const unsigned dw[3], int i) {
 //   ws_rel  : per-warp scratch for reliabilities (8*24 bytes)
 //   rb      : per-warp scratch, 8 words (corrected rows, so that lanes can index them dynamically)
 //   S       : per-warp soft-decision scratch (soft only)
-//   packed  : hard bits packed eight per byte, MSB first, in the row-major order of the reference's fr[rows][cols]
+//   packed  : hard bits packed eight per byte, MSB first, in the row-major order of the reference's fr[rows][cols] or in
+//             the transmission order given by the context's channel map
 __device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed, const uint8_t* __restrict__ fr, unsigned dw[3],
                                                  unsigned char* ws_rel, const SoftScratch& S, unsigned* rb,
                                                  const DevTables* T, int lane) {
@@ -274,7 +275,8 @@ __device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed
                 v = fr[2 * idx];
                 ws_rel[r * 24 + lane] = fr[2 * idx + 1];
             } else if (packed) {
-                v = ((unsigned)fr[idx >> 3] >> (7 - (idx & 7))) & 1u;
+                const unsigned src = T->chan_src[codec][idx];  // transmitted bit that lands here (identity by default)
+                v = (src == 0xffffu) ? 0u : (((unsigned)fr[src >> 3] >> (7 - (src & 7))) & 1u);
             } else {
                 v = fr[idx];
             }

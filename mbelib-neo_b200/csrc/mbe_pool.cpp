@@ -160,7 +160,8 @@ static int pool_process(mbe_b200_pool* p, const char* what, int codec, int soft,
         snprintf(p->err, sizeof(p->err), "%s: bad argument", what);
         return MBE_B200_E_ARG;
     }
-    const size_t fbytes = packed ? (size_t)mbe_b200_packed_frame_bytes(codec) : (size_t)fbits * (soft ? 2u : 1u);
+    const size_t fbytes = packed ? (size_t)mbe_b200_channel_frame_bytes(p ? p->ctx[0] : nullptr, codec)
+                                 : (size_t)fbits * (soft ? 2u : 1u);
     const size_t F = (size_t)n_frames;
     return for_each_shard(p, what, first_stream, n_streams, [=](int, mbe_b200_ctx* c, int lo, int n, size_t off) {
         const uint8_t* fr = frames + off * F * fbytes;
@@ -171,6 +172,20 @@ static int pool_process(mbe_b200_pool* p, const char* what, int codec, int soft,
         return packed ? mbe_b200_process_frames_packed(c, codec, lo, n, n_frames, fr, o16, of, r, b)
                       : mbe_b200_process_frames(c, codec, soft, lo, n, n_frames, fr, o16, of, r, b);
     });
+}
+
+int mbe_b200_pool_set_channel_map(mbe_b200_pool* p, int codec, const uint16_t* map, int n_bits) {
+    if (!p) {
+        return MBE_B200_E_ARG;
+    }
+    for (size_t i = 0; i < p->ctx.size(); ++i) {
+        const int rc = mbe_b200_set_channel_map(p->ctx[i], codec, map, n_bits);
+        if (rc != 0) {
+            snprintf(p->err, sizeof(p->err), "pool_set_channel_map: shard %d: %s", (int)i, mbe_b200_last_error(p->ctx[i]));
+            return rc;
+        }
+    }
+    return 0;
 }
 
 int mbe_b200_pool_process_frames(mbe_b200_pool* p, int codec, int soft, int first_stream, int n_streams, int n_frames,

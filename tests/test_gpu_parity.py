@@ -379,3 +379,49 @@ def test_soft_decode_degenerate_reliabilities(dec, codec):
             assert (got_res["c0_errors"][i], got_res["protected_errors"][i], got_res["c4_errors"][i],
                     got_res["total_errors"][i]) == tuple(int(x) for x in wr[:4]), (name, i)
             assert int(got_res["flags"][i]) == int(np.uint32(wr[4])), (name, i)
+
+
+def _transmitted_positions(codec):
+    """Frame positions (r*cols + c) that carry channel bits: everything for the random-bit tests except the unused
+    corners of the reference's bit planes for the two 72/144-bit air interfaces."""
+    if codec == 0:    # IMBE 7200x4400: 4 x 23 + 3 x 15 + 7 = 144 bits of char[8][23]
+        pos = [r * 23 + c for r in range(4) for c in range(23)] + [r * 23 + c for r in range(4, 7) for c in range(15)]
+        return pos + [7 * 23 + c for c in range(7)]
+    if codec in (2, 3):  # AMBE 3600: 24 + 23 + 11 + 14 = 72 bits of char[4][24]
+        return list(range(24)) + [24 + c for c in range(23)] + [48 + c for c in range(11)] + [72 + c for c in range(14)]
+    return list(range(T.FRAME_BITS[codec]))
+
+
+@pytest.mark.parametrize("codec", [0, 1, 2, 3])
+def test_channel_map_deinterleaves_on_device(dec, pkg, codec):
+    """bit-packed frames in TRANSMISSION order + a caller-supplied interleave schedule
+    (mbe_b200_set_channel_map) decode exactly like the same frames laid out as the reference's fr[rows][cols]."""
+    rng = np.random.default_rng(0xC4A + codec)
+    S, F = 64, 10
+    pos = np.array(_transmitted_positions(codec), np.uint16)
+    cmap = rng.permutation(pos)                       # transmitted bit k lands at frame position cmap[k]
+    frames = T.random_hard_frames(codec, S, F, 0x77 + codec)
+    mask = np.zeros(T.FRAME_BITS[codec], np.uint8)
+    mask[pos] = 1
+    frames &= mask                                    # positions the air interface does not carry are zero
+    air = np.packbits(frames[..., cmap], axis=-1, bitorder="big")   # the caller's buffer: interleaved, eight bits per byte
+    seeds = T.stream_seeds(S, 5)
+    dec.init_streams(0, S, seeds)
+    want = dec.process_frames(codec, frames, want_float=True)
+    try:
+        dec.set_channel_map(codec, cmap)
+        assert dec.channel_frame_bytes(codec) == (len(cmap) + 7) // 8 == air.shape[-1]
+        dec.init_streams(0, S, seeds)
+        got = dec.process_frames_packed(codec, air, want_float=True)
+        with pytest.raises(pkg.MbeB200Error):
+            dec.set_channel_map(codec, np.array([0, 0], np.uint16))      # a position used twice
+    finally:
+        dec.set_channel_map(codec, None)
+    assert dec.channel_frame_bytes(codec) == pkg.packed_frame_bytes(codec)
+    for k in ("pcm", "bits", "results"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.array_equal(got["pcmf"].view(np.uint32), want["pcmf"].view(np.uint32))
+    # the identity map is back: plain packed frames decode as before
+    dec.init_streams(0, S, seeds)
+    again = dec.process_frames_packed(codec, pkg.pack_frames(codec, frames))
+    assert np.array_equal(again["pcm"], want["pcm"])
