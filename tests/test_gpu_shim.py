@@ -78,3 +78,43 @@ def test_frame_by_frame_through_the_shim_equals_the_oracle(codec, soft):
     assert np.array_equal(pcmf.view(np.uint32), want["pcmf"][0].view(np.uint32))
     final = want["state"][0].reshape(3, T.PARMS_BYTES)
     assert np.array_equal(trip[0], final) and np.array_equal(trip[1], final)
+
+
+def test_two_threads_keep_their_own_rng_state():
+    """The reference keeps its RNG in thread-local storage (mbelib.h:28-30); the shim does too.  Two host threads decode
+    different streams through the shim at the same time (seeded differently, unvoiced-heavy random frames, so the noise
+    generator matters) and each must equal the oracle's run of its own stream."""
+    import threading
+    shim = ctypes.CDLL(SHIM)
+    vp = ctypes.c_void_p
+    shim.mbe_setThreadRngSeed.argtypes = [ctypes.c_uint32]
+    shim.mbe_initMbeParms.argtypes = [vp, vp, vp]
+    F = 30
+    jobs = [(3, 0xAAA1), (0, 0xBBB2)]
+    out = {}
+
+    def work(codec, seed):
+        fn = getattr(shim, FRAME_FN[codec] + "Frame")
+        fn.argtypes = [vp] * 7
+        frames = T.random_hard_frames(codec, 1, F, seed)
+        trip = np.zeros((3, T.PARMS_BYTES), np.uint8)
+        pcm = np.zeros((F, 160), np.int16)
+        bits = np.zeros(T.PARAM_BITS[codec], np.uint8)
+        shim.mbe_setThreadRngSeed(seed)
+        shim.mbe_initMbeParms(trip[0].ctypes.data, trip[1].ctypes.data, trip[2].ctypes.data)
+        for f in range(F):
+            fr = np.ascontiguousarray(frames[0, f])
+            rc = fn(pcm[f].ctypes.data, None, fr.ctypes.data, bits.ctypes.data, trip[0].ctypes.data, trip[1].ctypes.data,
+                    trip[2].ctypes.data)
+            assert rc >= 0
+        out[codec] = (frames, pcm)
+
+    th = [threading.Thread(target=work, args=j) for j in jobs]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for codec, seed in jobs:
+        frames, pcm = out[codec]
+        want = T.run_cpu(T.load_oracle().mbo_run, codec, 0, frames, np.array([seed], np.uint32))
+        assert np.array_equal(pcm, want["pcm"][0]), T.CODEC_NAMES[codec]
