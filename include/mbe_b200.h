@@ -145,6 +145,18 @@ MBE_B200_API int mbe_b200_decode_frames_dev(mbe_b200_ctx* ctx, int codec, int so
                                             uint8_t* d_bits, mbe_b200_result* d_results, void* cuda_stream);
 MBE_B200_API int mbe_b200_decode_frames(mbe_b200_ctx* ctx, int codec, int soft, int n, const uint8_t* frames,
                                         uint8_t* bits, mbe_b200_result* results);
+/* ecc_blocks: batched mbe_golay2312 / mbe_golay2312Soft (code 0), mbe_hamming1511[Soft] (code 1) and
+ *   mbe_7100x4400hamming1511[Soft] (code 2) (mbelib.h:238-274): n independent code words of 23 / 15 bits, one byte per
+ *   bit with bit i of the word at index i (soft: mbe_soft_bit pairs); out = corrected word (Golay: corrected data bits,
+ *   parity bits echoed from the input like the reference), status[i] = the reference's return value (changed data bits /
+ *   corrected bits, or MBE_STATUS_INVALID_BITS with out[i] untouched). */
+#define MBE_B200_ECC_GOLAY2312        0
+#define MBE_B200_ECC_HAMMING1511      1
+#define MBE_B200_ECC_HAMMING1511_7100 2
+MBE_B200_API int mbe_b200_ecc_blocks_dev(mbe_b200_ctx* ctx, int code, int soft, int n, const uint8_t* d_in, uint8_t* d_out,
+                                         int32_t* d_status, void* cuda_stream);
+MBE_B200_API int mbe_b200_ecc_blocks(mbe_b200_ctx* ctx, int code, int soft, int n, const uint8_t* in, uint8_t* out,
+                                     int32_t* status);
 MBE_B200_API int mbe_b200_process_data_dev(mbe_b200_ctx* ctx, int codec, int first_stream, int n_streams, int n_frames,
                                            const uint8_t* d_bits, mbe_b200_result* d_results_inout, int16_t* d_pcm,
                                            float* d_pcmf, void* cuda_stream);

@@ -5,16 +5,16 @@
  * libmbe-neo-b200shim.so exports, under the reference's own names and signatures, the entry points of the decode-and-
  * synthesis hot path plus the host-only helpers their callers need.  A program built against the reference's header can
  * be linked against the shim instead of libmbe-neo (the structs below are layout-compatible with mbelib.h:88-191); the
- * reference's own test binaries test_golden_pcm, test_noise_determinism, test_floattoshort_parity, test_frame_paths and
- * test_api run unmodified on top of it (tests/test_gpu_shim.py).
+ * reference's own test binaries test_golden_pcm, test_noise_determinism, test_floattoshort_parity, test_frame_paths, test_ecc
+ * and test_api run unmodified on top of it (tests/test_gpu_shim.py).
  *
  * Every call moves the caller-owned mbe_parms triplet and the calling thread's RNG words to the device, runs ONE frame
  * through the same kernels as the batched API and moves the state back: it is latency-bound (tens of microseconds of
  * copies and launch per 20 ms frame) and exists for API completeness and for testing - use mbe_b200.h for throughput.
  * There is no CPU fallback: without a CUDA device the first call prints the error and aborts.
  *
- * Reference symbols that are NOT provided (outside the hot path's boundary): the per-block ECC helpers
- * (mbe_golay2312*, mbe_hamming1511*, mbe_checkGolayBlock), the staged per-codec steps (mbe_ecc*C0/Data,
+ * Reference symbols that are NOT provided (inside the path rather than on its boundary): the staged
+ * per-codec steps (mbe_ecc*C0/Data,
  * mbe_demodulate*Data, mbe_convertImbe7100to7200, mbe_decode*Parms), mbe_spectralAmpEnhance,
  * mbe_applyAdaptiveSmoothing and its predicates, mbe_synthesizeTonef[dstar], mbe_synthesizeComfortNoise[f], mbe_dump*.
  */
@@ -95,6 +95,15 @@ MBE_COMPAT_API void mbe_synthesizeSilence(short* aout_buf);
 /* state (mbelib.h:596,615) */
 MBE_COMPAT_API void mbe_setThreadRngSeed(uint32_t seed);
 MBE_COMPAT_API void mbe_initMbeParms(mbe_parms* cur_mp, mbe_parms* prev_mp, mbe_parms* prev_mp_enhanced);
+
+/* block decoders (mbelib.h:231-274) */
+MBE_COMPAT_API int mbe_checkGolayBlock(long int* block);
+MBE_COMPAT_API int mbe_golay2312(const char* in, char* out);
+MBE_COMPAT_API int mbe_golay2312Soft(const mbe_soft_bit* in, char* out);
+MBE_COMPAT_API int mbe_hamming1511(const char* in, char* out);
+MBE_COMPAT_API int mbe_hamming1511Soft(const mbe_soft_bit* in, char* out);
+MBE_COMPAT_API int mbe_7100x4400hamming1511(const char* in, char* out);
+MBE_COMPAT_API int mbe_7100x4400hamming1511Soft(const mbe_soft_bit* in, char* out);
 
 /* ECC stage (mbelib.h:315,323,395,403,471,479,545,553) */
 MBE_COMPAT_API int mbe_decodeImbe7200x4400Frame(const char imbe_fr[8][23], char imbe_d[88], mbe_process_result* result);

@@ -35,7 +35,7 @@ _EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b
             "mbe_b200_process_data", "mbe_b200_synthesize_speech", "mbe_b200_synthesize_speech_rng", "mbe_b200_floattoshort",
             "mbe_b200_floattoshort_dev", "mbe_b200_synchronize", "mbe_b200_debug_stage_cycles",
             "mbe_b200_set_normalized_float", "mbe_b200_packed_frame_bytes", "mbe_b200_process_frames_packed_dev", "mbe_b200_process_frames_packed",
-            "mbe_b200_set_channel_map", "mbe_b200_channel_frame_bytes", "mbe_b200_pool_set_channel_map",
+            "mbe_b200_ecc_blocks", "mbe_b200_ecc_blocks_dev", "mbe_b200_set_channel_map", "mbe_b200_channel_frame_bytes", "mbe_b200_pool_set_channel_map",
             "mbe_b200_device_count", "mbe_b200_pool_create", "mbe_b200_pool_destroy", "mbe_b200_pool_last_error",
             "mbe_b200_pool_shards", "mbe_b200_pool_shard", "mbe_b200_pool_init_streams", "mbe_b200_pool_export_state",
             "mbe_b200_pool_import_state", "mbe_b200_pool_process_frames", "mbe_b200_pool_process_frames_packed"]
@@ -88,6 +88,8 @@ def load_library():
         lib.mbe_b200_floattoshort_dev.argtypes = [vp, ci, vp, vp, vp]
         lib.mbe_b200_synchronize.argtypes = [vp]
         lib.mbe_b200_debug_stage_cycles.argtypes = [vp, vp, ci]
+        lib.mbe_b200_ecc_blocks.argtypes = [vp, ci, ci, ci, vp, vp, vp]
+        lib.mbe_b200_ecc_blocks_dev.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp]
         lib.mbe_b200_set_channel_map.argtypes = [vp, ci, vp, ci]
         lib.mbe_b200_channel_frame_bytes.argtypes = [vp, ci]
         lib.mbe_b200_pool_set_channel_map.argtypes = [vp, ci, vp, ci]
@@ -319,6 +321,16 @@ class Decoder:
         self._check(self.lib.mbe_b200_decode_frames(self.h, codec, int(bool(soft)), n, _p(frames), _p(bits), _p(res)),
                     "decode_frames")
         return bits, res
+
+    def ecc_blocks(self, code, words, soft=False):
+        """words: uint8 [n][len] bits (or [n][len][2] soft bits), len = 23 (code 0) or 15.  Returns (out [n][len], status [n])."""
+        words = np.ascontiguousarray(words, dtype=np.uint8)
+        n = words.shape[0]
+        ln = 23 if code == 0 else 15
+        out = np.zeros((n, ln), np.uint8)
+        status = np.zeros(n, np.int32)
+        self._check(self.lib.mbe_b200_ecc_blocks(self.h, code, int(bool(soft)), n, _p(words), _p(out), _p(status)), "ecc_blocks")
+        return out, status
 
     def process_data(self, codec, bits, results=None, first_stream=0, want_float=False):
         bits = np.ascontiguousarray(bits, dtype=np.uint8)

@@ -827,6 +827,68 @@ __global__ void __launch_bounds__(256) mbe_decode_kernel(int n, const uint8_t* _
     }
 }
 
+// batched block decoders: one warp per code word (mbe_golay2312[Soft], mbe_hamming1511[Soft],
+// mbe_7100x4400hamming1511[Soft]; src/ecc/ecc.c:259-357,366-469).  CODE: 0 Golay(23,12), 1 Hamming(15,11), 2 Hamming(15,11)
+// in the IMBE 7100 layout.  in: [n][len] bits or [n][len] mbe_soft_bit pairs, bit i of the word at index i; out: [n][len].
+template <int CODE, int SOFT>
+__global__ void __launch_bounds__(256) mbe_ecc_block_kernel(int n, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                            int32_t* __restrict__ status, const DevTables* T) {
+    __shared__ unsigned char rel[8][24];
+    __shared__ __align__(16) unsigned short cp[SOFT ? 8 : 1][SOFT ? 2048 : 2];
+    __shared__ unsigned ka[SOFT ? 8 : 1][64];
+    __shared__ unsigned short qa[SOFT ? 8 : 1][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= n) {
+        return;
+    }
+    constexpr int len = (CODE == 0) ? 23 : 15;
+    unsigned v = 0;
+    if (lane < len) {
+        if (SOFT) {
+            v = in[((size_t)i * len + lane) * 2];
+            rel[warp][lane] = in[((size_t)i * len + lane) * 2 + 1];
+        } else {
+            v = in[(size_t)i * len + lane];
+        }
+    }
+    const bool bad = __any_sync(FULL, v > 1u);
+    const unsigned w = __ballot_sync(FULL, (v & 1u) != 0u);
+    __syncwarp();
+    if (bad) {
+        if (lane == 0) {
+            status[i] = -2;  // MBE_STATUS_INVALID_BITS: output untouched, like the reference
+        }
+        return;
+    }
+    const SoftScratch S = {cp[SOFT ? warp : 0], ka[SOFT ? warp : 0], qa[SOFT ? warp : 0]};
+    int errs = 0;
+    unsigned r;
+    if (CODE == 0) {
+        r = golay_row(w, rel[warp], SOFT, S, T, lane, &errs);
+    } else {
+        r = hamming_row<CODE == 2 ? 1 : 0>(w, rel[warp], SOFT, S, T, lane, &errs);
+    }
+    if (lane < len) {
+        out[(size_t)i * len + lane] = (uint8_t)((r >> lane) & 1u);
+    }
+    if (lane == 0) {
+        status[i] = errs;
+    }
+}
+
+typedef void (*ecc_block_kernel_fn)(int, const uint8_t*, uint8_t*, int32_t*, const DevTables*);
+static ecc_block_kernel_fn pick_ecc_block_kernel(int code, int soft) {
+    switch (code * 2 + (soft ? 1 : 0)) {
+        case 0: return mbe_ecc_block_kernel<0, 0>;
+        case 1: return mbe_ecc_block_kernel<0, 1>;
+        case 2: return mbe_ecc_block_kernel<1, 0>;
+        case 3: return mbe_ecc_block_kernel<1, 1>;
+        case 4: return mbe_ecc_block_kernel<2, 0>;
+        default: return mbe_ecc_block_kernel<2, 1>;
+    }
+}
+
 __global__ void mbe_floattoshort_kernel(size_t n, const float* __restrict__ in, int16_t* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -1841,6 +1903,55 @@ int mbe_b200_decode_frames(mbe_b200_ctx* ctx, int codec, int soft, int n, const 
     if (rb) {
         CU(cudaMemcpyAsync(results, ctx->d_out[2], rb, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mbe_b200_ecc_blocks_dev(mbe_b200_ctx* ctx, int code, int soft, int n, const uint8_t* d_in, uint8_t* d_out,
+                            int32_t* d_status, void* cuda_stream) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    if (code < 0 || code > 2 || n < 0 || !d_in || !d_out || !d_status) {
+        return fail(ctx, MBE_B200_E_ARG, "ecc_blocks: bad argument", cudaSuccess);
+    }
+    if (n == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    pick_ecc_block_kernel(code, soft)<<<(n + 7) / 8, 256, 0, st>>>(n, d_in, d_out, d_status, ctx->d_tab);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mbe_b200_ecc_blocks(mbe_b200_ctx* ctx, int code, int soft, int n, const uint8_t* in, uint8_t* out, int32_t* status) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    if (code < 0 || code > 2 || n < 0 || !in || !out || !status) {
+        return fail(ctx, MBE_B200_E_ARG, "ecc_blocks: bad argument", cudaSuccess);
+    }
+    if (n == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    const size_t len = code == 0 ? 23 : 15;
+    const size_t ib = (size_t)n * len * (soft ? 2 : 1), ob = (size_t)n * len, sb = (size_t)n * sizeof(int32_t);
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, ib)) < 0 || (rc = ensure(ctx, &ctx->d_out[3], &ctx->d_out_cap[3], ob)) < 0 ||
+        (rc = ensure(ctx, &ctx->d_out[2], &ctx->d_out_cap[2], sb)) < 0) {
+        return rc;
+    }
+    CU(cudaMemcpyAsync(ctx->d_in, in, ib, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_out[3], out, ob, cudaMemcpyHostToDevice, ctx->stream));  // words with invalid bits keep `out`
+    if ((rc = mbe_b200_ecc_blocks_dev(ctx, code, soft, n, (const uint8_t*)ctx->d_in, (uint8_t*)ctx->d_out[3],
+                                      (int32_t*)ctx->d_out[2], ctx->stream)) < 0) {
+        return rc;
+    }
+    CU(cudaMemcpyAsync(out, ctx->d_out[3], ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(status, ctx->d_out[2], sb, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

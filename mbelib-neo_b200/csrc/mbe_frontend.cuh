@@ -63,11 +63,13 @@ struct SoftScratch {
                          // (the first 32 / 16 entries of ka and qa are used: see the complement rule below)
 };
 
-// sum of the k least reliable positions outside `inside` (bit p = position p), nbits positions in all
-__device__ __forceinline__ unsigned soft_least_outside(const unsigned char* rel, unsigned inside, int nbits, int k, int lane) {
+// sum of the k least reliable positions outside `inside` (bit p = position p), nbits positions in all; stops early
+// once the partial sum has reached `enough` (all the caller asks is whether the sum gets that far)
+__device__ __forceinline__ unsigned soft_least_outside(const unsigned char* rel, unsigned inside, int nbits, int k,
+                                                       unsigned enough, int lane) {
     unsigned mine = (lane < nbits && !((inside >> lane) & 1u)) ? (((unsigned)rel[lane] << 5) | (unsigned)lane) : 0xffffffffu;
     unsigned sum = 0;
-    for (int i = 0; i < k; ++i) {
+    for (int i = 0; i < k && sum < enough; ++i) {
         const unsigned m = __reduce_min_sync(FULL, mine);
         sum += m >> 5;
         if (mine == m) {
@@ -91,7 +93,7 @@ __device__ __forceinline__ unsigned golay_soft(unsigned hard23, const unsigned c
     const unsigned dhf = hf ^ hd;
     const unsigned xhf = (dhf << 11) | (golay_parity(dhf, T) ^ syn);
     const unsigned U = soft_cost_of(rel, xhf, 23, lane);
-    if (U == 0u || soft_least_outside(rel, xhf, 23, 7 - __popc(xhf), lane) >= U) {
+    if (U == 0u || soft_least_outside(rel, xhf, 23, 7 - __popc(xhf), U, lane) >= U) {
         *errs = e_hard;
         return hf;
     }
@@ -164,7 +166,7 @@ __device__ __forceinline__ unsigned hamming_soft(unsigned hard15, const unsigned
     const unsigned hf = hamming_hard(hard15, V, T, &e_hard);
     const unsigned xhf = hf ^ hard15;  // at most one position
     const unsigned U = soft_cost_of(rel, xhf, 15, lane);
-    if (U == 0u || soft_least_outside(rel, xhf, 15, 3 - __popc(xhf), lane) >= U) {
+    if (U == 0u || soft_least_outside(rel, xhf, 15, 3 - __popc(xhf), U, lane) >= U) {
         *errs = e_hard;
         return hf;
     }

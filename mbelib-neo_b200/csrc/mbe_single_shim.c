@@ -366,6 +366,57 @@ DATA_FN(mbe_processImbe4400Data, MBE_B200_IMBE7200X4400, 88)
 DATA_FN(mbe_processAmbe2400Data, MBE_B200_AMBE3600X2400, 49)
 DATA_FN(mbe_processAmbe2450Data, MBE_B200_AMBE3600X2450, 49)
 
+/* ---- block decoders (mbelib.h:231-274; src/ecc/ecc.c:221-469) -------------------------------------------- */
+static int shim_ecc(int code, int soft, const void* in, char* out, int len) {
+    if (!out || !in) {
+        return MBE_STATUS_INVALID_ARGUMENT;
+    }
+    uint8_t o[23];
+    int32_t st = 0;
+    memcpy(o, out, (size_t)len);
+    pthread_mutex_lock(&g_mu);
+    mbe_b200_ctx* c = ctx_locked();
+    CK(mbe_b200_ecc_blocks(c, code, soft, 1, (const uint8_t*)in, o, &st));
+    pthread_mutex_unlock(&g_mu);
+    if (st >= 0) {
+        memcpy(out, o, (size_t)len);
+    }
+    return st;
+}
+
+int mbe_golay2312(const char* in, char* out) { return shim_ecc(MBE_B200_ECC_GOLAY2312, 0, in, out, 23); }
+int mbe_golay2312Soft(const mbe_soft_bit* in, char* out) { return shim_ecc(MBE_B200_ECC_GOLAY2312, 1, in, out, 23); }
+int mbe_hamming1511(const char* in, char* out) { return shim_ecc(MBE_B200_ECC_HAMMING1511, 0, in, out, 15); }
+int mbe_hamming1511Soft(const mbe_soft_bit* in, char* out) { return shim_ecc(MBE_B200_ECC_HAMMING1511, 1, in, out, 15); }
+int mbe_7100x4400hamming1511(const char* in, char* out) { return shim_ecc(MBE_B200_ECC_HAMMING1511_7100, 0, in, out, 15); }
+int mbe_7100x4400hamming1511Soft(const mbe_soft_bit* in, char* out) {
+    return shim_ecc(MBE_B200_ECC_HAMMING1511_7100, 1, in, out, 15);
+}
+
+/* packed 23-bit code word in, corrected 12 data bits out; bits above the code word pass through the shift like in the
+ * reference (ecc.c:221-251: databits = block >> 11) */
+int mbe_checkGolayBlock(long int* block) {
+    if (!block) {
+        return MBE_STATUS_INVALID_ARGUMENT;
+    }
+    const uint32_t b = (uint32_t)(*block);
+    char in[23], out[23];
+    for (int i = 0; i < 23; ++i) {
+        in[i] = (char)((b >> i) & 1u);
+    }
+    memset(out, 0, sizeof(out));
+    const int st = shim_ecc(MBE_B200_ECC_GOLAY2312, 0, in, out, 23);
+    if (st < 0) {
+        return st;
+    }
+    uint32_t data = 0;
+    for (int i = 22; i >= 11; --i) {
+        data = (data << 1) | (uint32_t)(out[i] & 1);
+    }
+    *block = (long)(int)(((b >> 23) << 12) | data);
+    return 0;
+}
+
 /* ---- synthesis only ---------------------------------------------------------------------------------------- */
 static void shim_synth(float* outf, short* outs, mbe_parms* cur, mbe_parms* prev) { /* mbelib.c:1042-1146 */
     if ((!outf && !outs) || !cur || !prev) {

@@ -1,7 +1,7 @@
 """Single-stream drop-in shim on the GPU.
 
 1. The reference's OWN test programs that stay inside the hot path's boundary (tests/test_golden_pcm.c,
-   test_noise_determinism.c, test_floattoshort_parity.c, test_frame_paths.c, test_api.c of arancormonk/mbelib-neo),
+   test_noise_determinism.c, test_floattoshort_parity.c, test_frame_paths.c, test_api.c, test_ecc.c of arancormonk/mbelib-neo),
    compiled unmodified by oracle/Makefile (`make shimtests`, binaries in oracle/_ref/, shipped with the repo snapshot) and
    linked against libmbe-neo-b200shim.so instead of libmbe-neo: they must pass frame by frame on the CUDA path.
 2. A frame-by-frame run through the shim's mbe_process<Codec>Frame with a caller-owned mbe_parms triplet against the
@@ -19,7 +19,7 @@ from __graft_entry__ import ROOT
 pytestmark = pytest.mark.gpu
 
 SHIM = os.path.join(ROOT, "mbelib-neo_b200", "libmbe-neo-b200shim.so")
-REFTESTS = ["test_golden_pcm", "test_noise_determinism", "test_floattoshort_parity", "test_frame_paths", "test_api"]
+REFTESTS = ["test_golden_pcm", "test_noise_determinism", "test_floattoshort_parity", "test_frame_paths", "test_api", "test_ecc"]
 
 
 @pytest.mark.parametrize("name", REFTESTS)
