@@ -43,6 +43,9 @@ STATE_BYTES = 7828  # 3 x mbe_parms + 16 B RNG words per stream
 # `ncu --set full` capture (profiles/r01j_stream_kernel_ncu_details.txt: 172.5 MB + 365.4 MB for 16576 streams x 50
 # frames of AMBE+2 hard-decision input) divided by the frames of that launch.  Only quoted for that workload.
 NCU_DRAM_BYTES_PER_FRAME = {("ambe3600x2450", 0): (172.532224e6 + 365.409024e6) / (16576 * 50)}
+# executed warp-instructions per frame of the same capture (smsp__inst_executed.sum / frames): the kernel is bound by
+# instruction issue, so this x frames/s against 148 SM x 4 schedulers x SM clock is the utilisation that matters
+NCU_WARP_INSTR_PER_FRAME = {("ambe3600x2450", 0): 4644997378.0 / (16576 * 50)}
 RESULT_BYTES = 24
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -451,6 +454,14 @@ def main():
                      "peak_source": "148 SM x 128 FP32 lanes x %.0f MHz sampled SM clock, non-fused (mul and add issue "
                                     "separately because parity forbids FMA contraction); FMA-counted peak is 2x" % sm_mhz}
 
+    wipf = NCU_WARP_INSTR_PER_FRAME.get((CODEC_NAMES[codec], soft))
+    if wipf:
+        issue_peak = 148 * 4 * sm_mhz * 1e6   # warp-instructions per second, one per scheduler per clock
+        issue_ach = wipf * S * F / (kern_ms * 1e-3)
+        roofline_fp32["issue_slots"] = {
+            "achieved": issue_ach / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instr/s", "frac": issue_ach / issue_peak,
+            "warp_instr_per_frame": wipf,
+            "source": "ncu smsp__inst_executed.sum per frame (profiles/r01j_*) x frames per launch / event-timed launch"}
     line = {"metric": "decoded frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,

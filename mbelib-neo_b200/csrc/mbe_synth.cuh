@@ -1225,7 +1225,9 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, BlockShared* bs, 
                 }
             }
             STAGE_T(10);  // interpolated harmonics
-            __syncthreads();
+            if (!(MBE_ABL & 512)) {  // (512: timing-only bound on what the bank's barriers cost; results are wrong)
+                __syncthreads();
+            }
             STAGE_T(11);  // wait for phase A of the block
             if (hi > lo && !(MBE_ABL & 1)) {
                 const int n = 32 * ch + lane;
@@ -1260,7 +1262,9 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, BlockShared* bs, 
                 me.out[n] = a;
             }
             STAGE_T(12);  // phase B
-            __syncthreads();
+            if (!(MBE_ABL & 512)) {
+                __syncthreads();
+            }
             STAGE_T(13);  // wait for phase B of the block
         }
     }
