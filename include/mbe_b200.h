@@ -163,6 +163,19 @@ MBE_B200_API int mbe_b200_process_data_dev(mbe_b200_ctx* ctx, int codec, int fir
 MBE_B200_API int mbe_b200_process_data(mbe_b200_ctx* ctx, int codec, int first_stream, int n_streams, int n_frames,
                                        const uint8_t* bits, mbe_b200_result* results_inout, int16_t* pcm, float* pcmf);
 
+/* ---- single stages on caller-held parameter sets -------------------------------------------------------
+ * Batched forms of the reference's per-stage helpers, one element = one call, host `mbe_parms` blobs updated in place:
+ *   decode_parms         mbe_decodeImbe4400Parms / mbe_decodeAmbe2400Parms / mbe_decodeAmbe2450Parms (mbelib.h:301,385,461):
+ *                        bits [n][88 or 49] -> cur[i] (w0, L, K, Vl, Ml, log2Ml, gamma) from prev[i]; prev[i] is updated
+ *                        too (the decoders extend its magnitudes); status[i] = the reference's return value (0 voice,
+ *                        codec-specific non-zero for invalid / erasure / tone frames, MBE_STATUS_INVALID_BITS).
+ *   spectral_amp_enhance mbe_spectralAmpEnhance (mbelib.h:623); rm0 (optional) receives the pre-enhancement energy.
+ *   adaptive_smoothing   mbe_applyAdaptiveSmoothing (mbelib.h:725).
+ * They run the same device functions the frame kernels fuse and exist for stage-level consumers and stage-level parity. */
+MBE_B200_API int mbe_b200_decode_parms(mbe_b200_ctx* ctx, int codec, int n, const uint8_t* bits, void* cur_parms,
+                                       void* prev_parms, int32_t* status);
+MBE_B200_API int mbe_b200_spectral_amp_enhance(mbe_b200_ctx* ctx, int n, void* cur_parms, float* rm0);
+MBE_B200_API int mbe_b200_adaptive_smoothing(mbe_b200_ctx* ctx, int n, void* cur_parms, const void* prev_parms);
 /* ---- synthesis-only entry points --------------------------------------------------------------
  * synthesize_speech: batched mbe_synthesizeSpeechf / mbe_synthesizeSpeech (mbelib.h:652,662): element i
  *   synthesises one frame from host parameter sets cur[i], prev[i] (mbe_parms blobs, updated in place

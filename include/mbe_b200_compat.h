@@ -14,9 +14,8 @@
  * There is no CPU fallback: without a CUDA device the first call prints the error and aborts.
  *
  * Reference symbols that are NOT provided (inside the path rather than on its boundary): the staged
- * per-codec steps (mbe_ecc*C0/Data,
- * mbe_demodulate*Data, mbe_convertImbe7100to7200, mbe_decode*Parms), mbe_spectralAmpEnhance,
- * mbe_applyAdaptiveSmoothing and its predicates, mbe_synthesizeTonef[dstar], mbe_synthesizeComfortNoise[f], mbe_dump*.
+ * per-codec channel steps (mbe_ecc*C0/Data, mbe_demodulate*Data, mbe_convertImbe7100to7200), the tone and comfort-noise
+ * generators (mbe_synthesizeTonef[dstar], mbe_synthesizeComfortNoise[f]) and the mbe_dump* printers.
  */
 #ifndef MBE_B200_COMPAT_H
 #define MBE_B200_COMPAT_H
@@ -95,6 +94,16 @@ MBE_COMPAT_API void mbe_synthesizeSilence(short* aout_buf);
 /* state (mbelib.h:596,615) */
 MBE_COMPAT_API void mbe_setThreadRngSeed(uint32_t seed);
 MBE_COMPAT_API void mbe_initMbeParms(mbe_parms* cur_mp, mbe_parms* prev_mp, mbe_parms* prev_mp_enhanced);
+
+/* single stages on the caller's parameter sets (mbelib.h:301,385,461,623,693,700,725,732) */
+MBE_COMPAT_API int mbe_decodeImbe4400Parms(const char* imbe_d, mbe_parms* cur_mp, mbe_parms* prev_mp);
+MBE_COMPAT_API int mbe_decodeAmbe2400Parms(const char* ambe_d, mbe_parms* cur_mp, mbe_parms* prev_mp);
+MBE_COMPAT_API int mbe_decodeAmbe2450Parms(const char* ambe_d, mbe_parms* cur_mp, mbe_parms* prev_mp);
+MBE_COMPAT_API void mbe_spectralAmpEnhance(mbe_parms* cur_mp);
+MBE_COMPAT_API void mbe_applyAdaptiveSmoothing(mbe_parms* cur_mp, const mbe_parms* prev_mp);
+MBE_COMPAT_API int mbe_requiresAdaptiveSmoothing(const mbe_parms* mp);
+MBE_COMPAT_API int mbe_requiresMuting(const mbe_parms* mp);
+MBE_COMPAT_API int mbe_isMaxFrameRepeat(const mbe_parms* mp);
 
 /* block decoders (mbelib.h:231-274) */
 MBE_COMPAT_API int mbe_checkGolayBlock(long int* block);

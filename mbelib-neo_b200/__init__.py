@@ -35,7 +35,8 @@ _EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b
             "mbe_b200_process_data", "mbe_b200_synthesize_speech", "mbe_b200_synthesize_speech_rng", "mbe_b200_floattoshort",
             "mbe_b200_floattoshort_dev", "mbe_b200_synchronize", "mbe_b200_debug_stage_cycles",
             "mbe_b200_set_normalized_float", "mbe_b200_packed_frame_bytes", "mbe_b200_process_frames_packed_dev", "mbe_b200_process_frames_packed",
-            "mbe_b200_ecc_blocks", "mbe_b200_ecc_blocks_dev", "mbe_b200_set_channel_map", "mbe_b200_channel_frame_bytes", "mbe_b200_pool_set_channel_map",
+            "mbe_b200_ecc_blocks", "mbe_b200_ecc_blocks_dev", "mbe_b200_decode_parms", "mbe_b200_spectral_amp_enhance",
+            "mbe_b200_adaptive_smoothing", "mbe_b200_set_channel_map", "mbe_b200_channel_frame_bytes", "mbe_b200_pool_set_channel_map",
             "mbe_b200_device_count", "mbe_b200_pool_create", "mbe_b200_pool_destroy", "mbe_b200_pool_last_error",
             "mbe_b200_pool_shards", "mbe_b200_pool_shard", "mbe_b200_pool_init_streams", "mbe_b200_pool_export_state",
             "mbe_b200_pool_import_state", "mbe_b200_pool_process_frames", "mbe_b200_pool_process_frames_packed"]
@@ -88,6 +89,9 @@ def load_library():
         lib.mbe_b200_floattoshort_dev.argtypes = [vp, ci, vp, vp, vp]
         lib.mbe_b200_synchronize.argtypes = [vp]
         lib.mbe_b200_debug_stage_cycles.argtypes = [vp, vp, ci]
+        lib.mbe_b200_decode_parms.argtypes = [vp, ci, ci, vp, vp, vp, vp]
+        lib.mbe_b200_spectral_amp_enhance.argtypes = [vp, ci, vp, vp]
+        lib.mbe_b200_adaptive_smoothing.argtypes = [vp, ci, vp, vp]
         lib.mbe_b200_ecc_blocks.argtypes = [vp, ci, ci, ci, vp, vp, vp]
         lib.mbe_b200_ecc_blocks_dev.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp]
         lib.mbe_b200_set_channel_map.argtypes = [vp, ci, vp, ci]
@@ -321,6 +325,22 @@ class Decoder:
         self._check(self.lib.mbe_b200_decode_frames(self.h, codec, int(bool(soft)), n, _p(frames), _p(bits), _p(res)),
                     "decode_frames")
         return bits, res
+
+    def decode_parms(self, codec, bits, cur, prev):
+        """bits uint8 [n][88|49]; cur/prev uint8 [n][2604] blobs, updated in place.  Returns status int32 [n]."""
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        n = bits.shape[0]
+        status = np.zeros(n, np.int32)
+        self._check(self.lib.mbe_b200_decode_parms(self.h, codec, n, _p(bits), _p(cur), _p(prev), _p(status)), "decode_parms")
+        return status
+
+    def spectral_amp_enhance(self, cur):
+        rm0 = np.zeros(cur.shape[0], np.float32)
+        self._check(self.lib.mbe_b200_spectral_amp_enhance(self.h, cur.shape[0], _p(cur), _p(rm0)), "spectral_amp_enhance")
+        return rm0
+
+    def adaptive_smoothing(self, cur, prev):
+        self._check(self.lib.mbe_b200_adaptive_smoothing(self.h, cur.shape[0], _p(cur), _p(prev)), "adaptive_smoothing")
 
     def ecc_blocks(self, code, words, soft=False):
         """words: uint8 [n][len] bits (or [n][len][2] soft bits), len = 23 (code 0) or 15.  Returns (out [n][len], status [n])."""

@@ -785,6 +785,91 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
     }
 }
 
+// Single stages of the path on caller-held parameter sets (batched mbe_decode<Codec>Parms, mbe_spectralAmpEnhance,
+// mbe_applyAdaptiveSmoothing; mbelib.h:301,385,461,623,725): the same device functions the stream kernel fuses, one warp
+// per element, so that rows P1-P5 of SURVEY 8(a) can be checked on their own.  No block barriers.
+enum { STAGE_PARMS_IMBE = 0, STAGE_PARMS_A2400 = 1, STAGE_PARMS_A2450 = 2, STAGE_ENHANCE = 3, STAGE_SMOOTH = 4 };
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM)
+mbe_stage_kernel(int op, int n, const uint8_t* __restrict__ bits, uint32_t* cur, uint32_t* prev, int32_t* status, float* rm0,
+                 const DevTables* T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpWS* wsa = reinterpret_cast<WarpWS*>(smem_raw + sizeof(BlockTables));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (s >= n) {
+        return;
+    }
+    WarpWS& ws = wsa[warp];
+    uint32_t* gc = cur + (size_t)s * PARMS_WORDS;
+    uint32_t* gp = prev ? prev + (size_t)s * PARMS_WORDS : nullptr;
+    uint32_t* c = reinterpret_cast<uint32_t*>(&ws.cur);
+    uint32_t* p = reinterpret_cast<uint32_t*>(&ws.prev);
+    uint32_t* e = reinterpret_cast<uint32_t*>(&ws.enh);
+    for (int i = lane; i < HEAD_WORDS; i += 32) {
+        c[i] = gc[i];
+    }
+    if (lane == 0) {
+        c[HEAD_WORDS] = gc[SEED_WORD];
+        ws.w0row = ws.w0row_prev = -1;
+    }
+    if (op <= STAGE_PARMS_A2450) {
+        for (int j = lane; j < PREV_WORDS; j += 32) {
+            p[j] = gp[prev_word(j)];
+        }
+    } else if (op == STAGE_SMOOTH) {
+        for (int j = lane; j < ENH_WORDS; j += 32) {
+            e[j] = gp[enh_word(j)];
+        }
+    }
+    __syncwarp();
+    int rc = 0;
+    if (op <= STAGE_PARMS_A2450) {
+        const int pbits = (op == STAGE_PARMS_IMBE) ? 88 : 49;
+        const uint8_t* d = bits + (size_t)s * pbits;
+        unsigned dw[3];
+        bool bad = false;
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            const int i = 32 * w + lane;
+            unsigned b = 0;
+            if (i < pbits) {
+                const unsigned v = d[i];
+                bad |= (v > 1u);
+                b = v & 1u;
+            }
+            dw[w] = __ballot_sync(FULL, b);
+        }
+        if (__any_sync(FULL, bad)) {
+            rc = -2;  // MBE_STATUS_INVALID_BITS, nothing touched
+        } else if (op == STAGE_PARMS_IMBE) {
+            rc = decode_imbe(dw, ws, T, lane);
+        } else if (op == STAGE_PARMS_A2400) {
+            rc = decode_ambe2400(dw, ws, T, lane);
+        } else {
+            rc = decode_ambe2450(dw, ws, T, -1, lane);  // the public wrapper passes "no error count" (ambe3600x2450.c:630-633)
+        }
+    } else if (op == STAGE_ENHANCE) {
+        const float r = spectral_enhance(ws, T, reinterpret_cast<float*>(&ws.u), lane);
+        if (rm0 && lane == 0) {
+            rm0[s] = r;
+        }
+    } else {
+        adaptive_smoothing(ws.cur, ws.enh, 0, 0.0f, lane);
+    }
+    __syncwarp();
+    for (int i = lane; i < HEAD_WORDS; i += 32) {
+        gc[i] = c[i];
+    }
+    if (op <= STAGE_PARMS_A2450) {  // the decoders extend / touch prev_mp's magnitudes (SURVEY 8(a) trap T3)
+        for (int j = lane; j < PREV_WORDS - 1; j += 32) {
+            gp[prev_word(j)] = p[j];
+        }
+    }
+    if (status && lane == 0) {
+        status[s] = rc;
+    }
+}
+
 // stateless ECC-only kernel: one warp per frame (batched mbe_decode<Codec>[Soft]Frame)
 template <int CODEC, int SOFT>
 __global__ void __launch_bounds__(256) mbe_decode_kernel(int n, const uint8_t* __restrict__ frames,
@@ -1359,6 +1444,7 @@ int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams) {
         }
     }
     CUC(cudaFuncSetAttribute(mbe_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_kernel_smem()));
+    CUC(cudaFuncSetAttribute(mbe_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_kernel_smem()));
 #undef CUC
     free(ht);
     *out = ctx;
@@ -1954,6 +2040,75 @@ int mbe_b200_ecc_blocks(mbe_b200_ctx* ctx, int code, int soft, int n, const uint
     CU(cudaMemcpyAsync(status, ctx->d_out[2], sb, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+// op: STAGE_*; bits / prev / status / rm0 as the stage needs them (host pointers)
+static int stage_impl(mbe_b200_ctx* ctx, const char* what, int op, int n, const uint8_t* bits, void* cur_parms, void* prev_parms,
+                      bool prev_out, int32_t* status, float* rm0) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    const bool need_prev = (op != STAGE_ENHANCE), need_bits = (op <= STAGE_PARMS_A2450);
+    if (n < 0 || !cur_parms || (need_prev && !prev_parms) || (need_bits && !bits)) {
+        return fail(ctx, MBE_B200_E_ARG, what, cudaSuccess);
+    }
+    if (n == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    const size_t pbytes = (size_t)n * sizeof(Parms);
+    const size_t bbytes = need_bits ? (size_t)n * (op == STAGE_PARMS_IMBE ? 88 : 49) : 0;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, 2 * pbytes + bbytes)) < 0 ||
+        (rc = ensure(ctx, &ctx->d_out[2], &ctx->d_out_cap[2], (size_t)n * 8)) < 0) {
+        return rc;
+    }
+    uint8_t* base = (uint8_t*)ctx->d_in;
+    CU(cudaMemcpyAsync(base, cur_parms, pbytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (need_prev) {
+        CU(cudaMemcpyAsync(base + pbytes, prev_parms, pbytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (need_bits) {
+        CU(cudaMemcpyAsync(base + 2 * pbytes, bits, bbytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int32_t* d_status = (int32_t*)ctx->d_out[2];
+    float* d_rm0 = (float*)ctx->d_out[2] + n;
+    const int blocks = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    mbe_stage_kernel<<<blocks, WARPS_PER_BLOCK * 32, stream_kernel_smem(), ctx->stream>>>(
+        op, n, base + 2 * pbytes, (uint32_t*)base, need_prev ? (uint32_t*)(base + pbytes) : nullptr, d_status, d_rm0, ctx->d_tab);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(cur_parms, base, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (prev_out) {
+        CU(cudaMemcpyAsync(prev_parms, base + pbytes, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (status) {
+        CU(cudaMemcpyAsync(status, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (rm0) {
+        CU(cudaMemcpyAsync(rm0, d_rm0, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mbe_b200_decode_parms(mbe_b200_ctx* ctx, int codec, int n, const uint8_t* bits, void* cur_parms, void* prev_parms,
+                          int32_t* status) {
+    if (ctx && (codec < 0 || codec > 3)) {
+        return fail(ctx, MBE_B200_E_ARG, "decode_parms: bad codec", cudaSuccess);
+    }
+    const int op = codec <= MBE_B200_IMBE7100X4400 ? STAGE_PARMS_IMBE
+                                                   : (codec == MBE_B200_AMBE3600X2400 ? STAGE_PARMS_A2400 : STAGE_PARMS_A2450);
+    return stage_impl(ctx, "decode_parms: bad argument", op, n, bits, cur_parms, prev_parms, true, status, nullptr);
+}
+
+int mbe_b200_spectral_amp_enhance(mbe_b200_ctx* ctx, int n, void* cur_parms, float* rm0) {
+    return stage_impl(ctx, "spectral_amp_enhance: bad argument", STAGE_ENHANCE, n, nullptr, cur_parms, nullptr, false, nullptr, rm0);
+}
+
+int mbe_b200_adaptive_smoothing(mbe_b200_ctx* ctx, int n, void* cur_parms, const void* prev_parms) {
+    return stage_impl(ctx, "adaptive_smoothing: bad argument", STAGE_SMOOTH, n, nullptr, cur_parms,
+                      const_cast<void*>(prev_parms), false, nullptr, nullptr);
 }
 
 static int synthesize_speech_impl(mbe_b200_ctx* ctx, int n, void* cur_parms, void* prev_parms, const uint32_t* seeds,

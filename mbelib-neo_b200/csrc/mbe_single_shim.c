@@ -366,6 +366,53 @@ DATA_FN(mbe_processImbe4400Data, MBE_B200_IMBE7200X4400, 88)
 DATA_FN(mbe_processAmbe2400Data, MBE_B200_AMBE3600X2400, 49)
 DATA_FN(mbe_processAmbe2450Data, MBE_B200_AMBE3600X2450, 49)
 
+/* ---- single stages on the caller's parameter sets (mbelib.h:301,385,461,623,725) ---------------------------- */
+static int shim_decode_parms(int codec, const char* d, mbe_parms* cur, mbe_parms* prev) {
+    if (!cur || !prev || !d) {
+        return MBE_STATUS_INVALID_ARGUMENT;  /* imbe7200x4400.c:596-602: state pointers, then the bit array */
+    }
+    int32_t st = 0;
+    pthread_mutex_lock(&g_mu);
+    mbe_b200_ctx* c = ctx_locked();
+    CK(mbe_b200_decode_parms(c, codec, 1, (const uint8_t*)d, cur, prev, &st));
+    pthread_mutex_unlock(&g_mu);
+    return st;
+}
+int mbe_decodeImbe4400Parms(const char* imbe_d, mbe_parms* cur_mp, mbe_parms* prev_mp) {
+    return shim_decode_parms(MBE_B200_IMBE7200X4400, imbe_d, cur_mp, prev_mp);
+}
+int mbe_decodeAmbe2400Parms(const char* ambe_d, mbe_parms* cur_mp, mbe_parms* prev_mp) {
+    return shim_decode_parms(MBE_B200_AMBE3600X2400, ambe_d, cur_mp, prev_mp);
+}
+int mbe_decodeAmbe2450Parms(const char* ambe_d, mbe_parms* cur_mp, mbe_parms* prev_mp) {
+    return shim_decode_parms(MBE_B200_AMBE3600X2450, ambe_d, cur_mp, prev_mp);
+}
+
+void mbe_spectralAmpEnhance(mbe_parms* cur_mp) { /* mbelib.c:663-666 */
+    if (!cur_mp) {
+        return;
+    }
+    pthread_mutex_lock(&g_mu);
+    mbe_b200_ctx* c = ctx_locked();
+    CK(mbe_b200_spectral_amp_enhance(c, 1, cur_mp, NULL));
+    pthread_mutex_unlock(&g_mu);
+}
+
+void mbe_applyAdaptiveSmoothing(mbe_parms* cur_mp, const mbe_parms* prev_mp) { /* mbe_adaptive.c:266-276 */
+    if (!cur_mp || !prev_mp) {
+        return;
+    }
+    pthread_mutex_lock(&g_mu);
+    mbe_b200_ctx* c = ctx_locked();
+    CK(mbe_b200_adaptive_smoothing(c, 1, cur_mp, prev_mp));
+    pthread_mutex_unlock(&g_mu);
+}
+
+/* host-only predicates on a parameter set (mbe_adaptive.c:70-107) */
+int mbe_requiresAdaptiveSmoothing(const mbe_parms* mp) { return mp ? (mp->errorRate > 0.0125f || mp->errorCountTotal > 4) : 0; }
+int mbe_requiresMuting(const mbe_parms* mp) { return mp ? (mp->errorRate > mp->mutingThreshold) : 0; }
+int mbe_isMaxFrameRepeat(const mbe_parms* mp) { return mp ? (mp->repeatCount >= 4) : 0; }
+
 /* ---- block decoders (mbelib.h:231-274; src/ecc/ecc.c:221-469) -------------------------------------------- */
 static int shim_ecc(int code, int soft, const void* in, char* out, int len) {
     if (!out || !in) {

@@ -44,7 +44,7 @@ def declared():
 
 def test_header_covers_the_frame_level_api():
     names = declared()
-    assert len(names) == 53
+    assert len(names) == 61
     for codec in ("Imbe7200x4400", "Imbe7100x4400", "Ambe3600x2400", "Ambe3600x2450"):
         for suffix in ("Frame", "Framef", "SoftFrame", "SoftFramef"):
             assert "mbe_process%s%s" % (codec, suffix) in names
