@@ -176,6 +176,19 @@ MBE_B200_API int mbe_b200_decode_parms(mbe_b200_ctx* ctx, int codec, int n, cons
                                        void* prev_parms, int32_t* status);
 MBE_B200_API int mbe_b200_spectral_amp_enhance(mbe_b200_ctx* ctx, int n, void* cur_parms, float* rm0);
 MBE_B200_API int mbe_b200_adaptive_smoothing(mbe_b200_ctx* ctx, int n, void* cur_parms, const void* prev_parms);
+/*   synthesize_tone      mbe_synthesizeTonef (dstar_id == NULL: amplitude and tone index parsed from bits49) and
+ *                        mbe_synthesizeTonefdstar (dstar_id[i] = ID1; bits49 may be NULL) (mbelib.h:630,638): 160 float
+ *                        samples per element, cur[i]'s tone phases advanced; unknown tones and invalid bits give silence.
+ *   comfort_noise        mbe_synthesizeComfortNoisef (mbelib.h:706) with the caller's RNG words (in/out, as export_rng).
+ *   channel_step         the front-end one step at a time on caller-held frames, hard decision, one byte per bit:
+ *                        step 0 mbe_ecc<Codec>C0 (frame in/out), 1 mbe_demodulate<Codec>Data (frame in/out),
+ *                        2 mbe_ecc<Codec>Data (frame in, bits out), 3 mbe_convertImbe7100to7200 (bits in/out, codec 1 only);
+ *                        status[i] = the reference's return value. */
+MBE_B200_API int mbe_b200_synthesize_tone(mbe_b200_ctx* ctx, int n, const uint8_t* bits49, const int32_t* dstar_id,
+                                          void* cur_parms, float* pcmf);
+MBE_B200_API int mbe_b200_comfort_noise(mbe_b200_ctx* ctx, int n, uint32_t* rng_words4, float* pcmf);
+MBE_B200_API int mbe_b200_channel_step(mbe_b200_ctx* ctx, int codec, int step, int n, uint8_t* frames, uint8_t* bits,
+                                       int32_t* status);
 /* ---- synthesis-only entry points --------------------------------------------------------------
  * synthesize_speech: batched mbe_synthesizeSpeechf / mbe_synthesizeSpeech (mbelib.h:652,662): element i
  *   synthesises one frame from host parameter sets cur[i], prev[i] (mbe_parms blobs, updated in place

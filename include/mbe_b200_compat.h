@@ -5,17 +5,17 @@
  * libmbe-neo-b200shim.so exports, under the reference's own names and signatures, the entry points of the decode-and-
  * synthesis hot path plus the host-only helpers their callers need.  A program built against the reference's header can
  * be linked against the shim instead of libmbe-neo (the structs below are layout-compatible with mbelib.h:88-191); the
- * reference's own test binaries test_golden_pcm, test_noise_determinism, test_floattoshort_parity, test_frame_paths, test_ecc
- * and test_api run unmodified on top of it (tests/test_gpu_shim.py).
+ * reference's own test binaries test_api, test_ecc, test_floattoshort_parity, test_frame_paths,
+ * test_golden_pcm, test_input_validation, test_noise_determinism and test_params run unmodified on top of it (tests/test_gpu_shim.py).
  *
  * Every call moves the caller-owned mbe_parms triplet and the calling thread's RNG words to the device, runs ONE frame
  * through the same kernels as the batched API and moves the state back: it is latency-bound (tens of microseconds of
  * copies and launch per 20 ms frame) and exists for API completeness and for testing - use mbe_b200.h for throughput.
  * There is no CPU fallback: without a CUDA device the first call prints the error and aborts.
  *
- * Reference symbols that are NOT provided (inside the path rather than on its boundary): the staged
- * per-codec channel steps (mbe_ecc*C0/Data, mbe_demodulate*Data, mbe_convertImbe7100to7200), the tone and comfort-noise
- * generators (mbe_synthesizeTonef[dstar], mbe_synthesizeComfortNoise[f]) and the mbe_dump* printers.
+ * All 87 functions of the reference's header are provided.  The steps inside the path (block decoders, C0 / de-scramble /
+ * data ECC, parameter decoders, enhancement, smoothing, tone and comfort-noise generators) run the same device functions
+ * the fused frame kernels use, one call = one small launch.
  */
 #ifndef MBE_B200_COMPAT_H
 #define MBE_B200_COMPAT_H
@@ -104,6 +104,34 @@ MBE_COMPAT_API void mbe_applyAdaptiveSmoothing(mbe_parms* cur_mp, const mbe_parm
 MBE_COMPAT_API int mbe_requiresAdaptiveSmoothing(const mbe_parms* mp);
 MBE_COMPAT_API int mbe_requiresMuting(const mbe_parms* mp);
 MBE_COMPAT_API int mbe_isMaxFrameRepeat(const mbe_parms* mp);
+
+/* the channel front-end one step at a time (mbelib.h:286-307,381-387,457-463,531-537) */
+#define MBE_COMPAT_STEPS(name, R, C)                                                                                  \
+    MBE_COMPAT_API int mbe_ecc##name##C0(char fr[R][C]);                                                              \
+    MBE_COMPAT_API int mbe_demodulate##name##Data(char fr[R][C]);                                                     \
+    MBE_COMPAT_API int mbe_ecc##name##Data(char fr[R][C], char* d);
+MBE_COMPAT_STEPS(Imbe7200x4400, 8, 23)
+MBE_COMPAT_STEPS(Imbe7100x4400, 7, 24)
+MBE_COMPAT_STEPS(Ambe3600x2400, 4, 24)
+MBE_COMPAT_STEPS(Ambe3600x2450, 4, 24)
+MBE_COMPAT_API int mbe_convertImbe7100to7200(char* imbe_d);
+
+/* tone and comfort-noise generators (mbelib.h:630,638,706,712) */
+MBE_COMPAT_API void mbe_synthesizeTonef(float* aout_buf, const char* ambe_d, mbe_parms* cur_mp);
+MBE_COMPAT_API void mbe_synthesizeTonefdstar(float* aout_buf, const char* ambe_d, mbe_parms* cur_mp, int ID1);
+MBE_COMPAT_API void mbe_synthesizeComfortNoisef(float* aout_buf);
+MBE_COMPAT_API void mbe_synthesizeComfortNoise(short* aout_buf);
+
+/* debug printers (stderr; mbelib.h:278-280,377-379,451-455,527-529) */
+MBE_COMPAT_API void mbe_dumpAmbe2400Data(const char* ambe_d);
+MBE_COMPAT_API void mbe_dumpAmbe3600x2400Frame(const char ambe_fr[4][24]);
+MBE_COMPAT_API void mbe_dumpAmbe2450Data(const char* ambe_d);
+MBE_COMPAT_API void mbe_dumpAmbe3600x2450Frame(const char ambe_fr[4][24]);
+MBE_COMPAT_API void mbe_dumpImbe4400Data(const char* imbe_d);
+MBE_COMPAT_API void mbe_dumpImbe7200x4400Data(const char* imbe_d);
+MBE_COMPAT_API void mbe_dumpImbe7200x4400Frame(const char imbe_fr[8][23]);
+MBE_COMPAT_API void mbe_dumpImbe7100x4400Data(const char* imbe_d);
+MBE_COMPAT_API void mbe_dumpImbe7100x4400Frame(const char imbe_fr[7][24]);
 
 /* block decoders (mbelib.h:231-274) */
 MBE_COMPAT_API int mbe_checkGolayBlock(long int* block);

@@ -36,7 +36,7 @@ _EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b
             "mbe_b200_floattoshort_dev", "mbe_b200_synchronize", "mbe_b200_debug_stage_cycles",
             "mbe_b200_set_normalized_float", "mbe_b200_packed_frame_bytes", "mbe_b200_process_frames_packed_dev", "mbe_b200_process_frames_packed",
             "mbe_b200_ecc_blocks", "mbe_b200_ecc_blocks_dev", "mbe_b200_decode_parms", "mbe_b200_spectral_amp_enhance",
-            "mbe_b200_adaptive_smoothing", "mbe_b200_set_channel_map", "mbe_b200_channel_frame_bytes", "mbe_b200_pool_set_channel_map",
+            "mbe_b200_adaptive_smoothing", "mbe_b200_synthesize_tone", "mbe_b200_comfort_noise", "mbe_b200_channel_step", "mbe_b200_set_channel_map", "mbe_b200_channel_frame_bytes", "mbe_b200_pool_set_channel_map",
             "mbe_b200_device_count", "mbe_b200_pool_create", "mbe_b200_pool_destroy", "mbe_b200_pool_last_error",
             "mbe_b200_pool_shards", "mbe_b200_pool_shard", "mbe_b200_pool_init_streams", "mbe_b200_pool_export_state",
             "mbe_b200_pool_import_state", "mbe_b200_pool_process_frames", "mbe_b200_pool_process_frames_packed"]
@@ -92,6 +92,9 @@ def load_library():
         lib.mbe_b200_decode_parms.argtypes = [vp, ci, ci, vp, vp, vp, vp]
         lib.mbe_b200_spectral_amp_enhance.argtypes = [vp, ci, vp, vp]
         lib.mbe_b200_adaptive_smoothing.argtypes = [vp, ci, vp, vp]
+        lib.mbe_b200_synthesize_tone.argtypes = [vp, ci, vp, vp, vp, vp]
+        lib.mbe_b200_comfort_noise.argtypes = [vp, ci, vp, vp]
+        lib.mbe_b200_channel_step.argtypes = [vp, ci, ci, ci, vp, vp, vp]
         lib.mbe_b200_ecc_blocks.argtypes = [vp, ci, ci, ci, vp, vp, vp]
         lib.mbe_b200_ecc_blocks_dev.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp]
         lib.mbe_b200_set_channel_map.argtypes = [vp, ci, vp, ci]
@@ -341,6 +344,30 @@ class Decoder:
 
     def adaptive_smoothing(self, cur, prev):
         self._check(self.lib.mbe_b200_adaptive_smoothing(self.h, cur.shape[0], _p(cur), _p(prev)), "adaptive_smoothing")
+
+    def synthesize_tone(self, cur, bits49=None, dstar_id=None):
+        n = cur.shape[0]
+        pcmf = np.zeros((n, SAMPLES), np.float32)
+        if bits49 is not None:
+            bits49 = np.ascontiguousarray(bits49, dtype=np.uint8)
+        if dstar_id is not None:
+            dstar_id = np.ascontiguousarray(dstar_id, dtype=np.int32)
+        self._check(self.lib.mbe_b200_synthesize_tone(self.h, n, _p(bits49), _p(dstar_id), _p(cur), _p(pcmf)), "synthesize_tone")
+        return pcmf
+
+    def comfort_noise(self, rng_words):
+        """rng_words uint32 [n][4] (as export_rng), updated in place."""
+        n = rng_words.shape[0]
+        pcmf = np.zeros((n, SAMPLES), np.float32)
+        self._check(self.lib.mbe_b200_comfort_noise(self.h, n, _p(rng_words), _p(pcmf)), "comfort_noise")
+        return pcmf
+
+    def channel_step(self, codec, step, frames=None, bits=None):
+        """step 0/1: frames uint8 [n][frame_bits] updated in place; 2: frames -> bits; 3: bits [n][88] in place."""
+        n = (frames if frames is not None else bits).shape[0]
+        status = np.zeros(n, np.int32)
+        self._check(self.lib.mbe_b200_channel_step(self.h, codec, step, n, _p(frames), _p(bits), _p(status)), "channel_step")
+        return status
 
     def ecc_blocks(self, code, words, soft=False):
         """words: uint8 [n][len] bits (or [n][len][2] soft bits), len = 23 (code 0) or 15.  Returns (out [n][len], status [n])."""

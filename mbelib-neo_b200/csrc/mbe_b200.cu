@@ -788,10 +788,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
 // Single stages of the path on caller-held parameter sets (batched mbe_decode<Codec>Parms, mbe_spectralAmpEnhance,
 // mbe_applyAdaptiveSmoothing; mbelib.h:301,385,461,623,725): the same device functions the stream kernel fuses, one warp
 // per element, so that rows P1-P5 of SURVEY 8(a) can be checked on their own.  No block barriers.
-enum { STAGE_PARMS_IMBE = 0, STAGE_PARMS_A2400 = 1, STAGE_PARMS_A2450 = 2, STAGE_ENHANCE = 3, STAGE_SMOOTH = 4 };
+// STAGE_TONE: mbe_synthesizeTonef (tone_id == nullptr: indices parsed from the 49 parameter bits) / mbe_synthesizeTonefdstar
+// (tone_id[i] = ID1) into pcmf, tone phases of cur updated; STAGE_COMFORT: mbe_synthesizeComfortNoisef with the caller's RNG
+// words in `rng` (in/out) instead of cur.
+enum { STAGE_PARMS_IMBE = 0, STAGE_PARMS_A2400 = 1, STAGE_PARMS_A2450 = 2, STAGE_ENHANCE = 3, STAGE_SMOOTH = 4, STAGE_TONE = 5,
+       STAGE_COMFORT = 6 };
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM)
 mbe_stage_kernel(int op, int n, const uint8_t* __restrict__ bits, uint32_t* cur, uint32_t* prev, int32_t* status, float* rm0,
-                 const DevTables* T) {
+                 float* pcmf, const int32_t* tone_id, uint32_t* rng, const DevTables* T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpWS* wsa = reinterpret_cast<WarpWS*>(smem_raw + sizeof(BlockTables));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -800,6 +804,22 @@ mbe_stage_kernel(int op, int n, const uint8_t* __restrict__ bits, uint32_t* cur,
         return;
     }
     WarpWS& ws = wsa[warp];
+    if (op == STAGE_COMFORT) {
+        uint32_t* r = rng + 4 * (size_t)s;
+        if (lane == 0) {
+            ws.rng.comfort = (unsigned long long)r[0] | ((unsigned long long)r[1] << 32);
+        }
+        __syncwarp();
+        comfort_noise(ws, T, lane);
+        for (int i = lane; i < NS; i += 32) {
+            pcmf[(size_t)s * NS + i] = ws.out[i];
+        }
+        if (lane == 0) {
+            r[0] = (uint32_t)(ws.rng.comfort & 0xffffffffULL);
+            r[1] = (uint32_t)(ws.rng.comfort >> 32);
+        }
+        return;
+    }
     uint32_t* gc = cur + (size_t)s * PARMS_WORDS;
     uint32_t* gp = prev ? prev + (size_t)s * PARMS_WORDS : nullptr;
     uint32_t* c = reinterpret_cast<uint32_t*>(&ws.cur);
@@ -853,6 +873,46 @@ mbe_stage_kernel(int op, int n, const uint8_t* __restrict__ bits, uint32_t* cur,
         if (rm0 && lane == 0) {
             rm0[s] = r;
         }
+    } else if (op == STAGE_TONE) {
+        // mbelib.c:762-856: invalid bits, unknown tone ids and (D-STAR) anything but the single tones give silence
+        const uint8_t* d = bits + (size_t)s * 49;
+        unsigned dw[3] = {0u, 0u, 0u};
+        bool bad = false;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const int i = 32 * w + lane;
+            unsigned b = 0;
+            if (i < 49) {
+                const unsigned v = d[i];
+                bad |= (v > 1u);
+                b = v & 1u;
+            }
+            dw[w] = __ballot_sync(FULL, b);
+        }
+        float f1 = 0.0f, f2 = 0.0f;
+        int amp = 103;
+        bool ok;
+        if (tone_id) {
+            const int id = tone_id[s];
+            ok = (id >= 5 && id <= 122) && tone_freqs(id, &f1, &f2);
+        } else {
+            unsigned u0 = 0, u1 = 0, u3 = 0;
+            for (int i = 0; i < 12; ++i) {
+                u0 = (u0 << 1) | getbit(dw, i);
+            }
+            for (int i = 12; i < 24; ++i) {
+                u1 = (u1 << 1) | getbit(dw, i);
+            }
+            for (int i = 35; i < 49; ++i) {
+                u3 = (u3 << 1) | getbit(dw, i);
+            }
+            amp = (int)(((u0 & 0x3fu) << 1) + ((u3 >> 4) & 1u));
+            ok = !__any_sync(FULL, bad) && tone_freqs((int)((u1 & 0xfffu) >> 4), &f1, &f2);
+        }
+        render_tone(ws, ok ? f1 : 0.0f, f2, amp, lane);
+        for (int i = lane; i < NS; i += 32) {
+            pcmf[(size_t)s * NS + i] = ws.out[i];
+        }
     } else {
         adaptive_smoothing(ws.cur, ws.enh, 0, 0.0f, lane);
     }
@@ -867,6 +927,86 @@ mbe_stage_kernel(int op, int n, const uint8_t* __restrict__ bits, uint32_t* cur,
     }
     if (status && lane == 0) {
         status[s] = rc;
+    }
+}
+
+// The channel front-end one step at a time on caller-held frames (batched mbe_ecc<Codec>C0, mbe_demodulate<Codec>Data,
+// mbe_ecc<Codec>Data, mbe_convertImbe7100to7200): step 0 = C0 ECC in place, 1 = de-scramble in place, 2 = data ECC ->
+// parameter bits, 3 = IMBE 7100 -> 7200 bit layout in place.  status = the reference's return value.  One warp per frame.
+template <int CODEC>
+__global__ void __launch_bounds__(256) mbe_front_step_kernel(int step, int n, uint8_t* fr, uint8_t* d, int32_t* status,
+                                                             const DevTables* T) {
+    __shared__ unsigned rows_s[8][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= n) {
+        return;
+    }
+    constexpr int fbits = (CODEC == MBE_B200_IMBE7200X4400) ? 184 : (CODEC == MBE_B200_IMBE7100X4400 ? 168 : 96);
+    constexpr int pbits = (CODEC <= MBE_B200_IMBE7100X4400) ? 88 : 49;
+    const SoftScratch S = {nullptr, nullptr, nullptr};
+    unsigned dw[3] = {0u, 0u, 0u};
+    int rc = 0;
+    if (step == 3) {
+        uint8_t* dd = d + (size_t)i * 88;
+        unsigned pre[3];
+        bool bad = false;
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            const int k = 32 * w + lane;
+            unsigned b = 0;
+            if (k < 88) {
+                const unsigned v = dd[k];
+                bad |= (v > 1u);
+                b = v & 1u;
+            }
+            pre[w] = __ballot_sync(FULL, b);
+        }
+        if (__any_sync(FULL, bad)) {
+            rc = -2;
+        } else {
+            fe_convert7100(pre, dw, T, lane);
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                const int k = 32 * w + lane;
+                if (k < 88) {
+                    dd[k] = (uint8_t)((dw[w] >> lane) & 1u);
+                }
+            }
+        }
+    } else {
+        uint8_t* f = fr + (size_t)i * fbits;
+        unsigned row[8];
+        if (fe_read(CODEC, 0, 0, f, row, nullptr, T, lane)) {
+            rc = -2;  // MBE_STATUS_INVALID_BITS: nothing touched
+        } else if (step == 2) {
+            int c4;
+            rc = fe_data(CODEC, 0, false, row, nullptr, S, rows_s[warp], T, lane, dw, &c4);
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                const int k = 32 * w + lane;
+                if (k < pbits) {
+                    d[(size_t)i * pbits + k] = (uint8_t)((dw[w] >> lane) & 1u);
+                }
+            }
+        } else {
+            if (step == 0) {
+                rc = fe_c0(CODEC, 0, row, nullptr, S, T, lane);
+            } else {
+                fe_demod(CODEC, row, T, lane);
+            }
+            constexpr int rows = (CODEC == MBE_B200_IMBE7200X4400) ? 8 : (CODEC == MBE_B200_IMBE7100X4400 ? 7 : 4);
+            constexpr int cols = (CODEC == MBE_B200_IMBE7200X4400) ? 23 : 24;
+#pragma unroll
+            for (int r = 0; r < rows; ++r) {
+                if (lane < cols) {
+                    f[r * cols + lane] = (uint8_t)((row[r] >> lane) & 1u);
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        status[i] = rc;
     }
 }
 
@@ -2075,7 +2215,8 @@ static int stage_impl(mbe_b200_ctx* ctx, const char* what, int op, int n, const 
     float* d_rm0 = (float*)ctx->d_out[2] + n;
     const int blocks = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     mbe_stage_kernel<<<blocks, WARPS_PER_BLOCK * 32, stream_kernel_smem(), ctx->stream>>>(
-        op, n, base + 2 * pbytes, (uint32_t*)base, need_prev ? (uint32_t*)(base + pbytes) : nullptr, d_status, d_rm0, ctx->d_tab);
+        op, n, base + 2 * pbytes, (uint32_t*)base, need_prev ? (uint32_t*)(base + pbytes) : nullptr, d_status, d_rm0, nullptr,
+        nullptr, nullptr, ctx->d_tab);
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(cur_parms, base, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2109,6 +2250,115 @@ int mbe_b200_spectral_amp_enhance(mbe_b200_ctx* ctx, int n, void* cur_parms, flo
 int mbe_b200_adaptive_smoothing(mbe_b200_ctx* ctx, int n, void* cur_parms, const void* prev_parms) {
     return stage_impl(ctx, "adaptive_smoothing: bad argument", STAGE_SMOOTH, n, nullptr, cur_parms,
                       const_cast<void*>(prev_parms), false, nullptr, nullptr);
+}
+
+int mbe_b200_synthesize_tone(mbe_b200_ctx* ctx, int n, const uint8_t* bits49, const int32_t* dstar_id, void* cur_parms,
+                             float* pcmf) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    if (n < 0 || !cur_parms || !pcmf || (!bits49 && !dstar_id)) {
+        return fail(ctx, MBE_B200_E_ARG, "synthesize_tone: bad argument", cudaSuccess);
+    }
+    if (n == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    const size_t pbytes = (size_t)n * sizeof(Parms), bbytes = (size_t)n * 49, ibytes = (size_t)n * 4, ob = (size_t)n * NS * 4;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, pbytes + ibytes + bbytes)) < 0 ||
+        (rc = ensure(ctx, &ctx->d_out[1], &ctx->d_out_cap[1], ob)) < 0) {
+        return rc;
+    }
+    uint8_t* base = (uint8_t*)ctx->d_in;
+    CU(cudaMemcpyAsync(base, cur_parms, pbytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (dstar_id) {
+        CU(cudaMemcpyAsync(base + pbytes, dstar_id, ibytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (bits49) {
+        CU(cudaMemcpyAsync(base + pbytes + ibytes, bits49, bbytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        CU(cudaMemsetAsync(base + pbytes + ibytes, 0, bbytes, ctx->stream));
+    }
+    mbe_stage_kernel<<<(n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, stream_kernel_smem(), ctx->stream>>>(
+        STAGE_TONE, n, base + pbytes + ibytes, (uint32_t*)base, nullptr, nullptr, nullptr, (float*)ctx->d_out[1],
+        dstar_id ? (const int32_t*)(base + pbytes) : nullptr, nullptr, ctx->d_tab);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(cur_parms, base, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(pcmf, ctx->d_out[1], ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mbe_b200_comfort_noise(mbe_b200_ctx* ctx, int n, uint32_t* rng_words4, float* pcmf) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    if (n < 0 || !rng_words4 || !pcmf) {
+        return fail(ctx, MBE_B200_E_ARG, "comfort_noise: bad argument", cudaSuccess);
+    }
+    if (n == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    const size_t rb = (size_t)n * 16, ob = (size_t)n * NS * 4;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, rb)) < 0 || (rc = ensure(ctx, &ctx->d_out[1], &ctx->d_out_cap[1], ob)) < 0) {
+        return rc;
+    }
+    CU(cudaMemcpyAsync(ctx->d_in, rng_words4, rb, cudaMemcpyHostToDevice, ctx->stream));
+    mbe_stage_kernel<<<(n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, stream_kernel_smem(), ctx->stream>>>(
+        STAGE_COMFORT, n, nullptr, nullptr, nullptr, nullptr, nullptr, (float*)ctx->d_out[1], nullptr, (uint32_t*)ctx->d_in,
+        ctx->d_tab);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(rng_words4, ctx->d_in, rb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(pcmf, ctx->d_out[1], ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mbe_b200_channel_step(mbe_b200_ctx* ctx, int codec, int step, int n, uint8_t* frames, uint8_t* bits, int32_t* status) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    int fb, pb;
+    const bool need_fr = step >= 0 && step <= 2, need_d = step == 2 || step == 3;
+    if (mbe_b200_geometry(codec, &fb, &pb) != 0 || step < 0 || step > 3 || (step == 3 && codec != MBE_B200_IMBE7100X4400) || n < 0 ||
+        !status || (need_fr && !frames) || (need_d && !bits)) {
+        return fail(ctx, MBE_B200_E_ARG, "channel_step: bad argument", cudaSuccess);
+    }
+    if (n == 0) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    const size_t fbytes = need_fr ? (size_t)n * fb : 0, dbytes = need_d ? (size_t)n * pb : 0;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, fbytes + 16)) < 0 || (rc = ensure(ctx, &ctx->d_out[3], &ctx->d_out_cap[3], dbytes + 16)) < 0 ||
+        (rc = ensure(ctx, &ctx->d_out[2], &ctx->d_out_cap[2], (size_t)n * 4)) < 0) {
+        return rc;
+    }
+    if (need_fr) {
+        CU(cudaMemcpyAsync(ctx->d_in, frames, fbytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (need_d) {
+        CU(cudaMemcpyAsync(ctx->d_out[3], bits, dbytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    void (*k)(int, int, uint8_t*, uint8_t*, int32_t*, const DevTables*) =
+        codec == 0 ? mbe_front_step_kernel<0> : (codec == 1 ? mbe_front_step_kernel<1> : (codec == 2 ? mbe_front_step_kernel<2> : mbe_front_step_kernel<3>));
+    k<<<(n + 7) / 8, 256, 0, ctx->stream>>>(step, n, (uint8_t*)ctx->d_in, (uint8_t*)ctx->d_out[3], (int32_t*)ctx->d_out[2], ctx->d_tab);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (step <= 1) {
+        CU(cudaMemcpyAsync(frames, ctx->d_in, fbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (need_d) {
+        CU(cudaMemcpyAsync(bits, ctx->d_out[3], dbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(status, ctx->d_out[2], (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 static int synthesize_speech_impl(mbe_b200_ctx* ctx, int n, void* cur_parms, void* prev_parms, const uint32_t* seeds,

@@ -251,20 +251,21 @@ __device__ __forceinline__ unsigned getbit(const unsigned dw[3], int i) {
     return (dw[i >> 5] >> (i & 31)) & 1u;
 }
 
-// Decode one frame held in global memory.  Outputs the parameter bits as three ballot words
-// (bit i of the reference's imbe_d/ambe_d = bit (i & 31) of dw[i >> 5]).
+// ---- the channel front-end in its four steps: read | C0 | de-scramble | data ----------------------------------------
+// (the reference exposes them one by one: mbe_ecc<Codec>C0, mbe_demodulate<Codec>Data, mbe_ecc<Codec>Data,
+//  mbe_convertImbe7100to7200; the frame kernels run them back to back on rows that stay in registers.)
 //   ws_rel  : per-warp scratch for reliabilities (8*24 bytes)
 //   rb      : per-warp scratch, 8 words (corrected rows, so that lanes can index them dynamically)
 //   S       : per-warp soft-decision scratch (soft only)
 //   packed  : hard bits packed eight per byte, MSB first, in the row-major order of the reference's fr[rows][cols] or in
 //             the transmission order given by the context's channel map
-__device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed, const uint8_t* __restrict__ fr, unsigned dw[3],
-                                                 unsigned char* ws_rel, const SoftScratch& S, unsigned* rb,
-                                                 const DevTables* T, int lane) {
-    FrontResult R;
-    const int rows = (codec == MBE_B200_IMBE7200X4400) ? 8 : (codec == MBE_B200_IMBE7100X4400 ? 7 : 4);
-    const int cols = (codec == MBE_B200_IMBE7200X4400) ? 23 : 24;
-    unsigned row[8];
+__device__ __forceinline__ int fe_rows(int codec) { return (codec == MBE_B200_IMBE7200X4400) ? 8 : (codec == MBE_B200_IMBE7100X4400 ? 7 : 4); }
+__device__ __forceinline__ int fe_cols(int codec) { return (codec == MBE_B200_IMBE7200X4400) ? 23 : 24; }
+
+// rows of the frame as ballot words (lane j = column j); returns true when a bit is neither 0 nor 1
+__device__ __forceinline__ bool fe_read(int codec, int soft, int packed, const uint8_t* __restrict__ fr, unsigned row[8],
+                                        unsigned char* ws_rel, const DevTables* T, int lane) {
+    const int rows = fe_rows(codec), cols = fe_cols(codec);
     bool bad = false;
     __syncwarp();  // the scratch may alias rows the previous frame's stores have just read
 #pragma unroll
@@ -288,17 +289,42 @@ __device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed
         row[r] = __ballot_sync(FULL, b);
     }
     __syncwarp();
-    if (__any_sync(FULL, bad)) {
-        R.status = -2;  // MBE_STATUS_INVALID_BITS
-        R.c0 = R.prot = R.c4 = 0;
-        R.flags = 0;
-        dw[0] = dw[1] = dw[2] = 0;
-        return R;
-    }
-    int c0 = 0, prot = 0, c4 = 0, e;
+    return __any_sync(FULL, bad);
+}
 
+// C0 in place; returns its error count
+__device__ __forceinline__ int fe_c0(int codec, int soft, unsigned row[8], unsigned char* ws_rel, const SoftScratch& S,
+                                     const DevTables* T, int lane) {
+    int c0 = 0;
     if (codec == MBE_B200_IMBE7200X4400) {
         row[0] = golay_row(row[0], ws_rel, soft, S, T, lane, &c0);
+    } else if (codec == MBE_B200_IMBE7100X4400) {
+        // C0: columns 1..18 zero-extended to a 23-bit Golay word; pad bits are fully reliable zeros
+        if (soft) {
+            // build a dedicated reliability vector for the padded word in the row-7 scratch slot
+            if (lane < 23) {
+                ws_rel[7 * 24 + lane] = (lane < 18) ? ws_rel[lane + 1] : (unsigned char)255;
+            }
+            __syncwarp();
+        }
+        unsigned w0 = (row[0] >> 1) & 0x3ffffu;
+        unsigned d0 = golay_row(w0, ws_rel + 7 * 24, soft, S, T, lane, &c0);
+        row[0] = (row[0] & ~(0x3ffffu << 1)) | ((d0 & 0x3ffffu) << 1);
+    } else {
+        // AMBE 3600: C0 = Golay on columns 1..23 + overall parity in column 0
+        unsigned g = golay_row((row[0] >> 1) & 0x7fffffu, ws_rel + 1, soft, S, T, lane, &c0);
+        row[0] = (row[0] & 1u) | (g << 1);
+        if (c0 == 0 && (__popc(row[0] & 0xffffffu) & 1)) {
+            row[0] ^= 1u;
+            c0 = 1;
+        }
+    }
+    return c0;
+}
+
+// PN de-scrambling of the protected rows with the sequence seeded by C0's data bits
+__device__ __forceinline__ void fe_demod(int codec, unsigned row[8], const DevTables* T, int lane) {
+    if (codec == MBE_B200_IMBE7200X4400) {
         const unsigned p0 = (16u * ((row[0] >> 11) & 0xfffu)) & 0xffffu;
         // PN masks: rows 1..3 use k = 1 + 23 (r-1) + (22 - j); rows 4..6 use k = 70 + 15 (r-4) + (14 - j)
 #pragma unroll
@@ -311,6 +337,75 @@ __device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed
             unsigned b = (lane < 15) ? pn_bit(p0, 70 + 15 * (r - 4) + (14 - lane), T) : 0u;
             row[r] ^= __ballot_sync(FULL, b);
         }
+    } else if (codec == MBE_B200_IMBE7100X4400) {
+        const unsigned seed = (row[0] >> 12) & 0x7fu;
+        const unsigned p0 = (16u * seed) & 0xffffu;
+        {
+            unsigned b = (lane < 24) ? pn_bit(p0, 1 + (23 - lane), T) : 0u;
+            row[1] ^= __ballot_sync(FULL, b);
+        }
+#pragma unroll
+        for (int r = 2; r < 4; ++r) {
+            unsigned b = (lane < 23) ? pn_bit(p0, 25 + 23 * (r - 2) + (22 - lane), T) : 0u;
+            row[r] ^= __ballot_sync(FULL, b);
+        }
+#pragma unroll
+        for (int r = 4; r < 6; ++r) {
+            unsigned b = (lane < 15) ? pn_bit(p0, 71 + 15 * (r - 4) + (14 - lane), T) : 0u;
+            row[r] ^= __ballot_sync(FULL, b);
+        }
+    } else {
+        const unsigned p0 = (16u * ((row[0] >> 12) & 0xfffu)) & 0xffffu;
+        unsigned b = (lane < 23) ? pn_bit(p0, 1 + (22 - lane), T) : 0u;
+        row[1] ^= __ballot_sync(FULL, b);
+    }
+}
+
+// K-dependent permutation of the 88 IMBE 7100 parameter bits to the 7200 layout (imbe7100x4400.c:380-437)
+__device__ __forceinline__ void fe_convert7100(const unsigned pre[3], unsigned dw[3], const DevTables* T, int lane) {
+    unsigned b0 = 0;
+    {
+        const int idx[8] = {1, 2, 3, 4, 5, 6, 86, 87};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            b0 = (b0 << 1) | getbit(pre, idx[i]);
+        }
+    }
+    const int K = (int)T->imbe_K[b0];
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+        int j = 32 * w + lane;
+        unsigned b = 0;
+        if (j < 88) {
+            int src;
+            if (j == 87) {
+                src = 0;
+            } else if (j < 48) {
+                src = (j + 1 <= 41) ? j + 1 : j + K + 3;
+            } else if (j < 48 + K) {
+                src = 44 + (j - 48);
+            } else if (j == 48 + K) {
+                src = 42;
+            } else if (j == 49 + K) {
+                src = 43;
+            } else {
+                int n = j - K - 2;
+                src = (n + 1 <= 41) ? n + 1 : n + K + 3;
+            }
+            b = getbit(pre, src);
+        }
+        dw[w] = __ballot_sync(FULL, b);
+    }
+}
+
+// ECC of the remaining rows and packing of the parameter bits as three ballot words (bit i of the reference's
+// imbe_d/ambe_d = bit (i & 31) of dw[i >> 5]); returns the protected-field error count.  convert: IMBE 7100 only, also
+// apply fe_convert7100 (the frame paths do; mbe_eccImbe7100x4400Data alone does not).
+__device__ __forceinline__ int fe_data(int codec, int soft, bool convert, unsigned row[8], unsigned char* ws_rel,
+                                       const SoftScratch& S, unsigned* rb, const DevTables* T, int lane, unsigned dw[3],
+                                       int* c4_out) {
+    int prot = 0, c4 = 0, e;
+    if (codec == MBE_B200_IMBE7200X4400) {
 #pragma unroll
         for (int r = 1; r < 4; ++r) {
             row[r] = golay_row(row[r] & 0x7fffffu, ws_rel + 24 * r, soft, S, T, lane, &e);
@@ -346,35 +441,7 @@ __device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed
             }
             dw[w] = __ballot_sync(FULL, b);
         }
-        R.flags = 0x0002u | 0x0004u;
     } else if (codec == MBE_B200_IMBE7100X4400) {
-        // C0: columns 1..18 zero-extended to a 23-bit Golay word; pad bits are fully reliable zeros
-        if (soft) {
-            // build a dedicated reliability vector for the padded word in the row-7 scratch slot
-            if (lane < 23) {
-                ws_rel[7 * 24 + lane] = (lane < 18) ? ws_rel[lane + 1] : (unsigned char)255;
-            }
-            __syncwarp();
-        }
-        unsigned w0 = (row[0] >> 1) & 0x3ffffu;
-        unsigned d0 = golay_row(w0, ws_rel + 7 * 24, soft, S, T, lane, &c0);
-        row[0] = (row[0] & ~(0x3ffffu << 1)) | ((d0 & 0x3ffffu) << 1);
-        const unsigned seed = (row[0] >> 12) & 0x7fu;
-        const unsigned p0 = (16u * seed) & 0xffffu;
-        {
-            unsigned b = (lane < 24) ? pn_bit(p0, 1 + (23 - lane), T) : 0u;
-            row[1] ^= __ballot_sync(FULL, b);
-        }
-#pragma unroll
-        for (int r = 2; r < 4; ++r) {
-            unsigned b = (lane < 23) ? pn_bit(p0, 25 + 23 * (r - 2) + (22 - lane), T) : 0u;
-            row[r] ^= __ballot_sync(FULL, b);
-        }
-#pragma unroll
-        for (int r = 4; r < 6; ++r) {
-            unsigned b = (lane < 15) ? pn_bit(p0, 71 + 15 * (r - 4) + (14 - lane), T) : 0u;
-            row[r] ^= __ballot_sync(FULL, b);
-        }
         // row 1 carries its Golay word in columns 1..23
         {
             unsigned g = golay_row((row[1] >> 1) & 0x7fffffu, ws_rel + 24 * 1 + 1, soft, S, T, lane, &e);
@@ -423,54 +490,14 @@ __device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed
             }
             pre[w] = __ballot_sync(FULL, b);
         }
-        // permutation to the 7200 layout (imbe7100x4400.c:380-437)
-        unsigned b0 = 0;
-        {
-            const int idx[8] = {1, 2, 3, 4, 5, 6, 86, 87};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                b0 = (b0 << 1) | getbit(pre, idx[i]);
-            }
+        if (convert) {
+            fe_convert7100(pre, dw, T, lane);
+        } else {
+            dw[0] = pre[0];
+            dw[1] = pre[1];
+            dw[2] = pre[2];
         }
-        const int K = (int)T->imbe_K[b0];
-#pragma unroll
-        for (int w = 0; w < 3; ++w) {
-            int j = 32 * w + lane;
-            unsigned b = 0;
-            if (j < 88) {
-                int src;
-                if (j == 87) {
-                    src = 0;
-                } else if (j < 48) {
-                    src = (j + 1 <= 41) ? j + 1 : j + K + 3;
-                } else if (j < 48 + K) {
-                    src = 44 + (j - 48);
-                } else if (j == 48 + K) {
-                    src = 42;
-                } else if (j == 49 + K) {
-                    src = 43;
-                } else {
-                    int n = j - K - 2;
-                    src = (n + 1 <= 41) ? n + 1 : n + K + 3;
-                }
-                b = getbit(pre, src);
-            }
-            dw[w] = __ballot_sync(FULL, b);
-        }
-        R.flags = 0x0002u | 0x0004u;
     } else {
-        // AMBE 3600: C0 = Golay on columns 1..23 + overall parity in column 0
-        unsigned g = golay_row((row[0] >> 1) & 0x7fffffu, ws_rel + 1, soft, S, T, lane, &c0);
-        row[0] = (row[0] & 1u) | (g << 1);
-        if (c0 == 0 && (__popc(row[0] & 0xffffffu) & 1)) {
-            row[0] ^= 1u;
-            c0 = 1;
-        }
-        const unsigned p0 = (16u * ((row[0] >> 12) & 0xfffu)) & 0xffffu;
-        {
-            unsigned b = (lane < 23) ? pn_bit(p0, 1 + (22 - lane), T) : 0u;
-            row[1] ^= __ballot_sync(FULL, b);
-        }
         row[1] = (row[1] & 0x800000u) | golay_row(row[1] & 0x7fffffu, ws_rel + 24, soft, S, T, lane, &prot);
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
@@ -488,8 +515,29 @@ __device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed
             dw[w] = __ballot_sync(FULL, b);
         }
         dw[2] = 0;
-        R.flags = 0x0002u;
     }
+    *c4_out = c4;
+    return prot;
+}
+
+// Decode one frame held in global memory: the four steps back to back.
+__device__ __forceinline__ FrontResult front_end(int codec, int soft, int packed, const uint8_t* __restrict__ fr, unsigned dw[3],
+                                                 unsigned char* ws_rel, const SoftScratch& S, unsigned* rb,
+                                                 const DevTables* T, int lane) {
+    FrontResult R;
+    unsigned row[8];
+    if (fe_read(codec, soft, packed, fr, row, ws_rel, T, lane)) {
+        R.status = -2;  // MBE_STATUS_INVALID_BITS
+        R.c0 = R.prot = R.c4 = 0;
+        R.flags = 0;
+        dw[0] = dw[1] = dw[2] = 0;
+        return R;
+    }
+    int c4 = 0;
+    const int c0 = fe_c0(codec, soft, row, ws_rel, S, T, lane);
+    fe_demod(codec, row, T, lane);
+    const int prot = fe_data(codec, soft, true, row, ws_rel, S, rb, T, lane, dw, &c4);
+    R.flags = (codec <= MBE_B200_IMBE7100X4400) ? (0x0002u | 0x0004u) : 0x0002u;
     if (soft) {
         R.flags |= 0x0001u;
     }

@@ -413,6 +413,129 @@ int mbe_requiresAdaptiveSmoothing(const mbe_parms* mp) { return mp ? (mp->errorR
 int mbe_requiresMuting(const mbe_parms* mp) { return mp ? (mp->errorRate > mp->mutingThreshold) : 0; }
 int mbe_isMaxFrameRepeat(const mbe_parms* mp) { return mp ? (mp->repeatCount >= 4) : 0; }
 
+/* ---- the channel front-end one step at a time (mbelib.h:286-307,381-387,457-463,531-537) --------------------- */
+static int shim_step(int codec, int step, char* fr, char* d) {
+    if ((step <= 2 && !fr) || (step >= 2 && !d)) {
+        return MBE_STATUS_INVALID_ARGUMENT;
+    }
+    int32_t st = 0;
+    pthread_mutex_lock(&g_mu);
+    mbe_b200_ctx* c = ctx_locked();
+    CK(mbe_b200_channel_step(c, codec, step, 1, (uint8_t*)fr, (uint8_t*)d, &st));
+    pthread_mutex_unlock(&g_mu);
+    return st;
+}
+#define STEP_FN(name, codec, R, C)                                                                                    \
+    int mbe_ecc##name##C0(char fr[R][C]) { return shim_step(codec, 0, (char*)fr, NULL); }                             \
+    int mbe_demodulate##name##Data(char fr[R][C]) { return shim_step(codec, 1, (char*)fr, NULL); }                    \
+    int mbe_ecc##name##Data(char fr[R][C], char* d) {                                                                 \
+        return d ? shim_step(codec, 2, (char*)fr, d) : MBE_STATUS_INVALID_ARGUMENT;                                   \
+    }
+STEP_FN(Imbe7200x4400, MBE_B200_IMBE7200X4400, 8, 23)
+STEP_FN(Imbe7100x4400, MBE_B200_IMBE7100X4400, 7, 24)
+STEP_FN(Ambe3600x2400, MBE_B200_AMBE3600X2400, 4, 24)
+STEP_FN(Ambe3600x2450, MBE_B200_AMBE3600X2450, 4, 24)
+int mbe_convertImbe7100to7200(char* imbe_d) { return shim_step(MBE_B200_IMBE7100X4400, 3, NULL, imbe_d); }
+
+/* ---- tone and comfort-noise generators (mbelib.h:630,638,706,712) -------------------------------------------- */
+static void shim_tone(float* aout_buf, const char* ambe_d, mbe_parms* cur_mp, const int32_t* dstar_id) {
+    if (!aout_buf) {
+        return;
+    }
+    if (!cur_mp || (!dstar_id && !ambe_d)) {
+        mbe_synthesizeSilencef(aout_buf);  /* mbelib.c:771-774,826-829 */
+        return;
+    }
+    pthread_mutex_lock(&g_mu);
+    mbe_b200_ctx* c = ctx_locked();
+    CK(mbe_b200_synthesize_tone(c, 1, dstar_id ? NULL : (const uint8_t*)ambe_d, dstar_id, cur_mp, aout_buf));
+    pthread_mutex_unlock(&g_mu);
+}
+void mbe_synthesizeTonef(float* aout_buf, const char* ambe_d, mbe_parms* cur_mp) { shim_tone(aout_buf, ambe_d, cur_mp, NULL); }
+void mbe_synthesizeTonefdstar(float* aout_buf, const char* ambe_d, mbe_parms* cur_mp, int ID1) {
+    const int32_t id = ID1;
+    (void)ambe_d;
+    shim_tone(aout_buf, NULL, cur_mp, &id);
+}
+
+void mbe_synthesizeComfortNoisef(float* aout_buf) { /* mbe_adaptive.c:116-131: advances the calling thread's generator */
+    if (!aout_buf) {
+        return;
+    }
+    pthread_mutex_lock(&g_mu);
+    mbe_b200_ctx* c = ctx_locked();
+    rng_ready_locked(c);
+    CK(mbe_b200_comfort_noise(c, 1, t_rng, aout_buf));
+    pthread_mutex_unlock(&g_mu);
+}
+void mbe_synthesizeComfortNoise(short* aout_buf) { /* mbe_adaptive.c:133-149 */
+    float f[NSAMP];
+    if (!aout_buf) {
+        return;
+    }
+    mbe_synthesizeComfortNoisef(f);
+    mbe_floattoshort(f, aout_buf);
+}
+
+/* ---- debug printers: host-only text output on stderr in the reference's formats -------------------------------- */
+static void dump_run(const char* row, int hi, int lo, int gap_before) { /* bits hi..lo, a blank before bit gap_before */
+    for (int j = hi; j >= lo; --j) {
+        if (j == gap_before) {
+            fputc(' ', stderr);
+        }
+        fprintf(stderr, "%i", row[j]);
+    }
+}
+static void dump_flat(const char* d, int n, const int* gaps, int n_gaps) {
+    for (int i = 0; i < n; ++i) {
+        for (int g = 0; g < n_gaps; ++g) {
+            if (gaps[g] == i) {
+                fputc(' ', stderr);
+            }
+        }
+        fprintf(stderr, "%i", d[i]);
+    }
+}
+static void dump_ambe_frame(const char fr[4][24]) { /* ambe3600x2450.c:113-142, ambe3600x2400.c:101-130 */
+    static const int hi[4] = {23, 22, 10, 13};
+    for (int r = 0; r < 4; ++r) {
+        fprintf(stderr, "ambe_fr c%d: ", r);
+        dump_run(fr[r], hi[r], 0, -1);
+        fputc(' ', stderr);
+    }
+}
+void mbe_dumpAmbe2400Data(const char* ambe_d) { dump_flat(ambe_d, 49, NULL, 0); fputc(' ', stderr); }
+void mbe_dumpAmbe2450Data(const char* ambe_d) { dump_flat(ambe_d, 49, NULL, 0); fputc(' ', stderr); }
+void mbe_dumpAmbe3600x2400Frame(const char ambe_fr[4][24]) { dump_ambe_frame(ambe_fr); }
+void mbe_dumpAmbe3600x2450Frame(const char ambe_fr[4][24]) { dump_ambe_frame(ambe_fr); }
+void mbe_dumpImbe4400Data(const char* imbe_d) { dump_flat(imbe_d, 88, NULL, 0); }
+void mbe_dumpImbe7200x4400Data(const char* imbe_d) { /* imbe7200x4400.c:377-391 */
+    static const int gaps[7] = {12, 24, 36, 48, 59, 70, 81};
+    dump_flat(imbe_d, 88, gaps, 7);
+}
+void mbe_dumpImbe7100x4400Data(const char* imbe_d) { /* imbe7100x4400.c:30-44 */
+    static const int gaps[6] = {7, 19, 31, 43, 54, 65};
+    dump_flat(imbe_d, 88, gaps, 6);
+}
+void mbe_dumpImbe7200x4400Frame(const char imbe_fr[8][23]) { /* imbe7200x4400.c:397-417 */
+    for (int r = 0; r < 7; ++r) {
+        dump_run(imbe_fr[r], r < 4 ? 22 : 14, 0, -1);
+        fputc(' ', stderr);
+    }
+    dump_run(imbe_fr[7], 6, 0, -1);
+}
+void mbe_dumpImbe7100x4400Frame(const char imbe_fr[7][24]) { /* imbe7100x4400.c:50-92 */
+    dump_run(imbe_fr[0], 18, 0, 11);
+    fputc(' ', stderr);
+    dump_run(imbe_fr[1], 23, 0, 11);
+    fputc(' ', stderr);
+    for (int r = 2; r < 6; ++r) {
+        dump_run(imbe_fr[r], r < 4 ? 22 : 14, 0, r < 4 ? 10 : 3);
+        fputc(' ', stderr);
+    }
+    dump_run(imbe_fr[6], 22, 0, -1);
+}
+
 /* ---- block decoders (mbelib.h:231-274; src/ecc/ecc.c:221-469) -------------------------------------------- */
 static int shim_ecc(int code, int soft, const void* in, char* out, int len) {
     if (!out || !in) {

@@ -19,7 +19,8 @@ from __graft_entry__ import ROOT
 pytestmark = pytest.mark.gpu
 
 SHIM = os.path.join(ROOT, "mbelib-neo_b200", "libmbe-neo-b200shim.so")
-REFTESTS = ["test_golden_pcm", "test_noise_determinism", "test_floattoshort_parity", "test_frame_paths", "test_api", "test_ecc"]
+REFTESTS = ["test_golden_pcm", "test_noise_determinism", "test_floattoshort_parity", "test_frame_paths", "test_api", "test_ecc",
+            "test_params", "test_input_validation"]
 
 
 @pytest.mark.parametrize("name", REFTESTS)

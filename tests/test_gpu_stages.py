@@ -103,3 +103,104 @@ def test_enhance_and_smoothing(dec, codec):
     for i in range(m):
         o.mbo_adaptive_smoothing(vp(want[i].ctypes.data), vp(enh[i].ctypes.data), 0, 0.0)
     assert np.array_equal(cur, want), "mbe_applyAdaptiveSmoothing"
+
+
+STEP_FN = {0: ("mbe_eccImbe7200x4400C0", "mbe_demodulateImbe7200x4400Data", "mbe_eccImbe7200x4400Data"),
+           1: ("mbe_eccImbe7100x4400C0", "mbe_demodulateImbe7100x4400Data", "mbe_eccImbe7100x4400Data"),
+           2: ("mbe_eccAmbe3600x2400C0", "mbe_demodulateAmbe3600x2400Data", "mbe_eccAmbe3600x2400Data"),
+           3: ("mbe_eccAmbe3600x2450C0", "mbe_demodulateAmbe3600x2450Data", "mbe_eccAmbe3600x2450Data")}
+
+
+@pytest.mark.parametrize("codec", [0, 1, 2, 3])
+def test_channel_steps(dec, codec):
+    """SURVEY 8(a) rows E6-E9 step by step: C0 ECC, de-scrambling, data ECC (and the 7100 -> 7200 bit permutation) run
+    one at a time on caller-held frames.  The chain must equal the fused front-end (mbe_b200_decode_frames), and - when
+    the compiled reference travels with the repo (oracle/_ref) - every intermediate frame must equal what the reference's
+    own mbe_ecc<Codec>C0 / mbe_demodulate<Codec>Data / mbe_ecc<Codec>Data / mbe_convertImbe7100to7200 leave behind."""
+    n = 200
+    fb, pb = T.FRAME_BITS[codec], T.PARAM_BITS[codec]
+    frames = T.random_hard_frames(codec, n, 1, 0x5E0 + codec).reshape(n, fb)
+    want_bits, want_res = dec.decode_frames(codec, frames)
+    ref = T.load_ref_api()
+    g = frames.copy()
+    r = frames.copy()
+    c0 = dec.channel_step(codec, 0, frames=g)
+    if ref is not None:
+        rc0 = np.array([getattr(ref, STEP_FN[codec][0])(vp(r[i].ctypes.data)) for i in range(n)])
+        assert np.array_equal(c0, rc0) and np.array_equal(g, r), "C0 step"
+    st = dec.channel_step(codec, 1, frames=g)
+    assert not st.any()
+    if ref is not None:
+        for i in range(n):
+            assert getattr(ref, STEP_FN[codec][1])(vp(r[i].ctypes.data)) == 0
+        assert np.array_equal(g, r), "de-scramble step"
+    bits = np.zeros((n, pb), np.uint8)
+    before = g.copy()
+    prot = dec.channel_step(codec, 2, frames=g, bits=bits)
+    assert np.array_equal(g, before)                      # the data step does not modify the frame
+    if ref is not None:
+        rbits = np.zeros((n, pb), np.uint8)
+        rprot = np.array([getattr(ref, STEP_FN[codec][2])(vp(r[i].ctypes.data), vp(rbits[i].ctypes.data)) for i in range(n)])
+        assert np.array_equal(prot, rprot) and np.array_equal(bits, rbits), "data step"
+    if codec == 1:
+        st = dec.channel_step(codec, 3, bits=bits)
+        assert not st.any()
+        if ref is not None:
+            for i in range(n):
+                assert ref.mbe_convertImbe7100to7200(vp(rbits[i].ctypes.data)) == 0
+            assert np.array_equal(bits, rbits), "7100 -> 7200 permutation"
+    assert np.array_equal(bits, want_bits)
+    assert np.array_equal(c0, want_res["c0_errors"]) and np.array_equal(prot, want_res["protected_errors"])
+    bad = frames[:3].copy()
+    bad[1, 9] = 7
+    keep = bad.copy()
+    st = dec.channel_step(codec, 0, frames=bad)
+    assert st[1] == -2 and np.array_equal(bad[1], keep[1])
+
+
+def test_tone_and_comfort_noise(dec):
+    """Rows S5 / S6 on their own: mbe_synthesizeTonef, mbe_synthesizeTonefdstar and mbe_synthesizeComfortNoisef against
+    the oracle, float samples bitwise, tone phases and RNG state carried from call to call."""
+    o = T.load_oracle()
+    o.mbo_synthesize_tone.argtypes = [vp, vp, vp]
+    o.mbo_synthesize_tone_dstar.argtypes = [vp, vp, ctypes.c_int]
+    o.mbo_comfort_noise.argtypes = [vp, vp]
+    rng = np.random.default_rng(0x70E)
+    ids = [5, 6, 7, 40, 122, 128, 141, 163, 4, 123, 200, 0]
+    n = len(ids)
+    bits = rng.integers(0, 2, size=(n, 49), dtype=np.uint8)
+    for i, tid in enumerate(ids):             # ID1 = u1[11:4] = bits 12..19, AD from u0[5:0] (bits 6..11) and u3 bit 4
+        for k in range(8):
+            bits[i, 12 + k] = (tid >> (7 - k)) & 1
+    st = _fresh(n)
+    cur_g, cur_w = st[:, 0].copy(), st[:, 0].copy()
+    out_w = np.zeros((n, 160), np.float32)
+    for rep in range(3):                      # phases continue across frames
+        out_g = dec.synthesize_tone(cur_g, bits49=bits)
+        for i in range(n):
+            o.mbo_synthesize_tone(vp(out_w[i].ctypes.data), vp(bits[i].ctypes.data), vp(cur_w[i].ctypes.data))
+        assert np.array_equal(out_g.view(np.uint32), out_w.view(np.uint32)), "mbe_synthesizeTonef rep %d" % rep
+        assert np.array_equal(cur_g, cur_w)
+    assert out_g[:8].any() and not out_g[8:].any()        # valid ids sound, invalid ids are silent
+    dst = np.array([5, 6, 64, 122, 128, 4, 123, -1], np.int32)
+    m = len(dst)
+    cur_g, cur_w = st[:m, 0].copy(), st[:m, 0].copy()
+    for rep in range(2):
+        out_g = dec.synthesize_tone(cur_g, dstar_id=dst)
+        for i in range(m):
+            o.mbo_synthesize_tone_dstar(vp(out_w[i].ctypes.data), vp(cur_w[i].ctypes.data), int(dst[i]))
+        assert np.array_equal(out_g.view(np.uint32), out_w[:m].view(np.uint32)), "mbe_synthesizeTonefdstar"
+        assert np.array_equal(cur_g, cur_w)
+    # comfort noise: per-element RNG words (seeded like mbe_setThreadRngSeed), three frames in a row
+    d2 = load_package().Decoder(max_streams=16, device=0)
+    d2.init_streams(0, 16, np.arange(16, dtype=np.uint32) + 77)
+    words_g = d2.export_rng(0, 16)
+    d2.close()
+    words_w = words_g.copy()
+    noise_w = np.zeros((16, 160), np.float32)
+    for rep in range(3):
+        out_g = dec.comfort_noise(words_g)
+        for i in range(16):
+            o.mbo_comfort_noise(vp(noise_w[i].ctypes.data), vp(words_w[i].ctypes.data))
+        assert np.array_equal(out_g.view(np.uint32), noise_w.view(np.uint32)), "mbe_synthesizeComfortNoisef"
+        assert np.array_equal(words_g, words_w)

@@ -39,12 +39,14 @@ def declared():
         names |= {base, base + "f"}
     for base in re.findall(r"^MBE_COMPAT_FRAME\((mbe_\w+),", text, re.M):
         names |= {base + s for s in ("Frame", "Framef", "SoftFrame", "SoftFramef")}
+    for codec in re.findall(r"^MBE_COMPAT_STEPS\((\w+),", text, re.M):
+        names |= {"mbe_ecc%sC0" % codec, "mbe_demodulate%sData" % codec, "mbe_ecc%sData" % codec}
     return sorted(n for n in names if "##" not in n and n != "name")
 
 
 def test_header_covers_the_frame_level_api():
     names = declared()
-    assert len(names) == 61
+    assert len(names) == 87
     for codec in ("Imbe7200x4400", "Imbe7100x4400", "Ambe3600x2400", "Ambe3600x2450"):
         for suffix in ("Frame", "Framef", "SoftFrame", "SoftFramef"):
             assert "mbe_process%s%s" % (codec, suffix) in names

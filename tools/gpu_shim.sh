@@ -2,7 +2,7 @@
 # shim check: the reference's test programs on the GPU path + the shim parity test.  usage: bash tools/gpu_shim.sh <tag>
 TAG=${1:-shim}
 OUT=gpurun_out; mkdir -p $OUT
-for t in test_api test_floattoshort_parity test_golden_pcm test_noise_determinism test_frame_paths test_ecc; do
+for t in test_api test_floattoshort_parity test_golden_pcm test_noise_determinism test_frame_paths test_ecc test_params test_input_validation; do
   echo "== $t" >> $OUT/${TAG}_reftests.log
   timeout 120 oracle/_ref/shim_$t >> $OUT/${TAG}_reftests.log 2>&1
   echo "exit $?" >> $OUT/${TAG}_reftests.log
