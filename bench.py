@@ -204,7 +204,25 @@ def channel_like_frames(codec, n_streams, n_frames, seed):
     return T.soften(hard, rng, flip_p=0.10)
 
 
-def run_cpu_reference(codec, n_frames, steps, warmup, streams_per_thread, soft=0, soft_channel=False):
+def tone_unvoiced_frames(n_streams, n_frames, seed):
+    """BASELINE.json configs[3]-shaped input (AMBE 3600x2400 only): frames built from parameter bits - a third tone / silence
+    frames, a third unvoiced-only voice frames (FFT / WOLA / noise-generator path), a third ordinary voice frames - Golay
+    encoded and PN scrambled into valid channel frames.  Returns uint8 [streams][frames][96]."""
+    import mbe_testlib as T
+    rng = np.random.default_rng(seed)
+    frames = np.zeros((n_streams, n_frames, 96), np.uint8)
+    for s in range(n_streams):
+        for f in range(n_frames):
+            p = rng.integers(0, 2, size=49, dtype=np.uint8)
+            if (s + f // 5) % 3 == 0:
+                p[0:6] = 1
+            elif s % 2:
+                p[38:42] = 0
+            frames[s, f] = T.encode_ambe_frame(p).reshape(-1)
+    return frames
+
+
+def run_cpu_reference(codec, n_frames, steps, warmup, streams_per_thread, soft=0, soft_channel=False, tones=False):
     """Times the reference's CPU implementation (oracle/_ref dev-release build; the oracle port if the compiled
     reference is missing) on all host cores.  Returns (frames/s, info dict, seconds per step)."""
     import mbe_testlib as T
@@ -225,7 +243,10 @@ def run_cpu_reference(codec, n_frames, steps, warmup, streams_per_thread, soft=0
     if soft:
         streams_per_thread = max(1, streams_per_thread // 50)  # the reference's soft ECC is ~1 ms per IMBE frame
     S = min(cores * streams_per_thread, 65536)
-    if soft_channel:
+    if tones:
+        base = tone_unvoiced_frames(min(S, 128), n_frames, 0x2400)
+        frames = np.ascontiguousarray(np.tile(base, ((S + len(base) - 1) // len(base), 1, 1))[:S])
+    elif soft_channel:
         base = channel_like_frames(codec, min(S, 128), n_frames, 0x50F7)
         frames = np.ascontiguousarray(np.tile(base, ((S + len(base) - 1) // len(base), 1, 1, 1))[:S])
     elif soft:
@@ -267,9 +288,14 @@ def main():
                     help="soft-decision input shaped like BASELINE.json configs[4]: valid encoded frames, every channel bit "
                          "flipped with p = 0.10, reliability 255 for unflipped and U[0,64) for flipped bits (128 distinct "
                          "streams tiled over the batch)")
+    ap.add_argument("--tones-unvoiced", action="store_true",
+                    help="BASELINE.json configs[3]-shaped input (forces --codec ambe3600x2400): tone, unvoiced-only and voice "
+                         "frames from parameter bits, valid channel frames (128 distinct streams tiled over the batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    if args.tones_unvoiced:
+        args.codec = "ambe3600x2400"
     codec = {v: k for k, v in CODEC_NAMES.items()}[args.codec]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -278,7 +304,8 @@ def main():
     soft = 1 if (args.soft or args.soft_channel) else 0
     workload = "%s %s-decision decode+synthesis, %d streams x %d synthetic %s frames per GPU" % (
         CODEC_NAMES[codec], "soft" if soft else "hard", S, F,
-        "valid encoded, 10% flipped-bit" if args.soft_channel else "random-bit")
+        "valid encoded, 10% flipped-bit" if args.soft_channel else ("tone / unvoiced-only / voice" if args.tones_unvoiced
+                                                                      else "random-bit"))
     config = {"workload": workload, "codec": CODEC_NAMES[codec], "streams_per_gpu": S, "frames_per_stream": F,
               "sharding": "streams/%d, no collective" % world,
               "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (S * F * (FRAME_BITS[codec] + 344) / 1e6)}
@@ -288,7 +315,7 @@ def main():
             return 0
         warm = max(1, min(args.warmup, 3))
         fps, info, sec = run_cpu_reference(codec, F, args.steps, warm, streams_per_thread=1000, soft=soft,
-                                           soft_channel=args.soft_channel)
+                                           soft_channel=args.soft_channel, tones=args.tones_unvoiced)
         line = {"impl": "reference", "metric": "decoded frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -320,7 +347,11 @@ def main():
     gen = torch.Generator(device=dev)
     gen.manual_seed(0x2450 + rank)
     d_frames = torch.randint(0, 2, (S, F, fb), dtype=torch.uint8, device=dev, generator=gen)
-    if args.soft_channel:
+    if args.tones_unvoiced:
+        B = 128
+        base = torch.from_numpy(tone_unvoiced_frames(B, F, 0x2400 + rank)).to(dev)
+        d_frames = base.repeat((S + B - 1) // B, 1, 1)[:S].contiguous()
+    elif args.soft_channel:
         B = 128
         base = torch.from_numpy(channel_like_frames(codec, B, F, 0x50F7 + rank)).to(dev)
         d_frames = base.repeat((S + B - 1) // B, 1, 1, 1)[:S].contiguous()
@@ -469,7 +500,8 @@ def main():
             "roofline": roofline, "roofline_fp32": roofline_fp32}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        _, info, _ = run_cpu_reference(codec, F, 2, 1, streams_per_thread=1000, soft=soft, soft_channel=args.soft_channel)
+        _, info, _ = run_cpu_reference(codec, F, 2, 1, streams_per_thread=1000, soft=soft, soft_channel=args.soft_channel,
+                                       tones=args.tones_unvoiced)
         line["cpu_baseline"] = info
     dec.close()
     if world > 1:

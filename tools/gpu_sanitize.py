@@ -27,5 +27,29 @@ for codec in (3, 0, 2, 1):
     dec.init_streams(0, S, T.stream_seeds(S))
     r3 = dec.process_frames_packed(codec, pkg.pack_frames(codec, frames))
     assert np.array_equal(r["pcm"], r3["pcm"])
+    # stage-level entry points on the same data
+    fr1 = frames.reshape(S * F, -1).copy()
+    dec.channel_step(codec, 0, frames=fr1)
+    dec.channel_step(codec, 1, frames=fr1)
+    d1 = np.zeros((S * F, pkg.PARAM_BITS[codec]), np.uint8)
+    dec.channel_step(codec, 2, frames=fr1, bits=d1)
+    if codec == 1:
+        dec.channel_step(codec, 3, bits=d1)
+    assert np.array_equal(d1.reshape(S, F, -1), r["bits"])
+    st = dec.export_state(0, S)
+    cur, prev, enh = st[:, 0].copy(), st[:, 1].copy(), st[:, 2].copy()
+    dec.decode_parms(codec, d1[:S], cur, prev)
+    dec.spectral_amp_enhance(cur)
+    dec.adaptive_smoothing(cur, enh)
     print("codec", codec, "ok", int(np.abs(r["pcm"]).max()), int(np.abs(r2["pcm"]).max()))
+words = rng.integers(0, 2, size=(64, 23), dtype=np.uint8)
+rel = rng.integers(0, 256, size=(64, 23), dtype=np.uint8)
+for code, ln in ((0, 23), (1, 15), (2, 15)):
+    dec.ecc_blocks(code, words[:, :ln])
+    dec.ecc_blocks(code, np.ascontiguousarray(np.stack([words[:, :ln], rel[:, :ln]], axis=-1)), soft=True)
+cur = dec.export_state(0, 8)[:, 0].copy()
+dec.synthesize_tone(cur, bits49=rng.integers(0, 2, size=(8, 49), dtype=np.uint8))
+dec.synthesize_tone(cur, dstar_id=np.arange(8, dtype=np.int32) + 3)
+dec.comfort_noise(dec.export_rng(0, 8))
+print("stage entry points ok")
 dec.close()
