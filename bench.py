@@ -362,8 +362,23 @@ def main():
     d_res = torch.empty((S, F, 6), dtype=torch.int32, device=dev)
     stream = torch.cuda.Stream(device=dev)
 
+    # Short launches (a real-time server decodes ONE 20 ms frame per stream per launch) must not see the same frames
+    # launch after launch: a stream fed the same frame twice has a perfectly stable pitch, which sends every low harmonic
+    # through the phase-interpolated (one cosf per sample) path and times a workload nobody has.  Rotate through enough
+    # different frame sets to cover 50 frames per stream.
+    rot_sets = [d_frames]
+    if F < 50 and not (args.soft_channel or args.tones_unvoiced):
+        for k in range(1, min(50 // F, 25)):
+            x = torch.randint(0, 2, (S, F, fb), dtype=torch.uint8, device=dev, generator=gen)
+            if soft:
+                x = torch.stack((x, torch.randint(0, 256, (S, F, fb), dtype=torch.uint8, device=dev, generator=gen)), dim=-1).contiguous()
+            rot_sets.append(x)
+    step_no = [0]
+
     def step_dev():
-        dec.process_frames_dev(codec, soft, 0, S, F, d_frames.data_ptr(), d_pcm.data_ptr(), 0, d_res.data_ptr(), 0,
+        fr = rot_sets[step_no[0] % len(rot_sets)]
+        step_no[0] += 1
+        dec.process_frames_dev(codec, soft, 0, S, F, fr.data_ptr(), d_pcm.data_ptr(), 0, d_res.data_ptr(), 0,
                                stream.cuda_stream)
 
     def barrier():

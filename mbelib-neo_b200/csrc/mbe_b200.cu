@@ -443,24 +443,63 @@ __device__ __forceinline__ void store_pcm(const LaunchArgs& A, const WarpWS& ws,
 }
 
 // stream state: HBM slot <-> shared memory (the three structs without their bulk arrays, which stay in HBM)
+// All 23 loads of a lane are issued before the first one is consumed: with one frame per launch (a real-time server)
+// the state round trip is a large part of a stream's lifetime, and one load at a time costs ~20 HBM latencies.
 __device__ __forceinline__ void load_stream(WarpWS& ws, const uint32_t* gs, int lane) {
     uint32_t* c = reinterpret_cast<uint32_t*>(&ws.cur);
     uint32_t* p = reinterpret_cast<uint32_t*>(&ws.prev);
     uint32_t* e = reinterpret_cast<uint32_t*>(&ws.enh);
-    for (int i = lane; i < HEAD_WORDS; i += 32) {
-        c[i] = gs[i];
+    constexpr int NC = (HEAD_WORDS + 31) / 32, NP = (PREV_WORDS + 31) / 32, NE = (ENH_WORDS + 31) / 32;
+    uint32_t vc[NC], vp[NP], ve[NE];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const int i = lane + 32 * k;
+        vc[k] = (i < HEAD_WORDS) ? gs[i] : 0u;
     }
-    for (int j = lane; j < PREV_WORDS; j += 32) {
-        p[j] = gs[PARMS_WORDS + prev_word(j)];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const int j = lane + 32 * k;
+        vp[k] = (j < PREV_WORDS) ? gs[PARMS_WORDS + prev_word(j)] : 0u;
     }
-    for (int j = lane; j < ENH_WORDS; j += 32) {
-        e[j] = gs[2 * PARMS_WORDS + enh_word(j)];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const int j = lane + 32 * k;
+        ve[k] = (j < ENH_WORDS) ? gs[2 * PARMS_WORDS + enh_word(j)] : 0u;
+    }
+    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, seed = 0;
+    if (lane == 0) {
+        seed = gs[SEED_WORD];
+        r0 = gs[3 * PARMS_WORDS];
+        r1 = gs[3 * PARMS_WORDS + 1];
+        r2 = gs[3 * PARMS_WORDS + 2];
+        r3 = gs[3 * PARMS_WORDS + 3];
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        const int i = lane + 32 * k;
+        if (i < HEAD_WORDS) {
+            c[i] = vc[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const int j = lane + 32 * k;
+        if (j < PREV_WORDS) {
+            p[j] = vp[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+        const int j = lane + 32 * k;
+        if (j < ENH_WORDS) {
+            e[j] = ve[k];
+        }
     }
     if (lane == 0) {
-        c[HEAD_WORDS] = gs[SEED_WORD];
-        ws.rng.comfort = (unsigned long long)gs[3 * PARMS_WORDS] | ((unsigned long long)gs[3 * PARMS_WORDS + 1] << 32);
-        ws.rng.uv_seed = gs[3 * PARMS_WORDS + 2];
-        ws.rng.uv_override = gs[3 * PARMS_WORDS + 3];
+        c[HEAD_WORDS] = seed;
+        ws.rng.comfort = (unsigned long long)r0 | ((unsigned long long)r1 << 32);
+        ws.rng.uv_seed = r2;
+        ws.rng.uv_override = r3;
     }
     __syncwarp();
 }
