@@ -421,17 +421,25 @@ def main():
     # ---- end-to-end arm: host frames in, host PCM + results out, through the host-pointer C-ABI call ----
     e2e = None
     if not args.no_e2e:
-        h_frames = torch.empty(tuple(d_frames.shape), dtype=torch.uint8, pin_memory=True)
-        h_frames.copy_(d_frames)
+        h_sets = []
+        for x in rot_sets:       # (short launches rotate through different frame sets here too)
+            hx = torch.empty(tuple(x.shape), dtype=torch.uint8, pin_memory=True)
+            hx.copy_(x)
+            h_sets.append(hx)
+        h_frames = h_sets[0]
         h_pcm = torch.empty((S, F, 160), dtype=torch.int16, pin_memory=True)
         h_res = torch.empty((S, F, 6), dtype=torch.int32, pin_memory=True)
         np_frames, np_pcm = h_frames.numpy(), h_pcm.numpy()
+        np_sets = [x.numpy() for x in h_sets]
         np_res = h_res.numpy().view(pkg.RESULT_DTYPE).reshape(S, F)
         lib, h = dec.lib, dec.h
         import ctypes
+        host_step = [0]
 
         def step_host():
-            rc = lib.mbe_b200_process_frames(h, codec, soft, 0, S, F, np_frames.ctypes.data_as(ctypes.c_void_p),
+            cur_frames = np_sets[host_step[0] % len(np_sets)]
+            host_step[0] += 1
+            rc = lib.mbe_b200_process_frames(h, codec, soft, 0, S, F, cur_frames.ctypes.data_as(ctypes.c_void_p),
                                              np_pcm.ctypes.data_as(ctypes.c_void_p), None,
                                              np_res.ctypes.data_as(ctypes.c_void_p), None)
             if rc != 0:
@@ -454,7 +462,7 @@ def main():
                        "wall clock around the blocking calls, max over ranks"}
         if float(np.abs(np_pcm[:64]).max()) == 0:
             raise SystemExit("bench.py: e2e path produced silence")
-        if not soft:
+        if not soft and len(rot_sets) == 1:
             # the same call with bit-packed channel frames: 8x less host->device traffic
             h_packed = torch.from_numpy(pkg.pack_frames(codec, np_frames)).pin_memory()
             np_packed = h_packed.numpy()
