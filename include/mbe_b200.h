@@ -106,6 +106,15 @@ MBE_B200_API int mbe_b200_process_frames(mbe_b200_ctx* ctx, int codec, int soft,
                                          int n_frames, const uint8_t* frames, int16_t* pcm, float* pcmf,
                                          mbe_b200_result* results, uint8_t* bits);
 
+/* The host-pointer call in two halves, for a server thread that has other work while a batch is in flight (filling the
+ * next frame's buffer, driving the contexts of several GPUs from one thread): submit_frames queues copy-in, kernels and
+ * copy-out and returns; the host buffers must stay valid and untouched until mbe_b200_wait() returns (use pinned memory,
+ * pageable memory makes the copies synchronous).  One submission may be pending per context; every other call on the
+ * context must wait for it first. */
+MBE_B200_API int mbe_b200_submit_frames(mbe_b200_ctx* ctx, int codec, int soft, int first_stream, int n_streams,
+                                        int n_frames, const uint8_t* frames, int16_t* pcm, float* pcmf,
+                                        mbe_b200_result* results, uint8_t* bits);
+MBE_B200_API int mbe_b200_wait(mbe_b200_ctx* ctx);
 /* Float PCM scale.  By default every `pcmf` output is in the reference's historical float scale
  * (roughly int16/7, what mbe_process<Codec>Framef returns).  With enable != 0 the samples are multiplied by
  * (7.0f / 32768.0f) on store, the normalisation include/mbelib-neo/mbelib.h:16-20 documents (about [-0.95, +0.95]

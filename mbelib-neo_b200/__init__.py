@@ -35,7 +35,7 @@ _EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b
             "mbe_b200_process_data", "mbe_b200_synthesize_speech", "mbe_b200_synthesize_speech_rng", "mbe_b200_floattoshort",
             "mbe_b200_floattoshort_dev", "mbe_b200_synchronize", "mbe_b200_debug_stage_cycles",
             "mbe_b200_set_normalized_float", "mbe_b200_packed_frame_bytes", "mbe_b200_process_frames_packed_dev", "mbe_b200_process_frames_packed",
-            "mbe_b200_ecc_blocks", "mbe_b200_ecc_blocks_dev", "mbe_b200_decode_parms", "mbe_b200_spectral_amp_enhance",
+            "mbe_b200_submit_frames", "mbe_b200_wait", "mbe_b200_ecc_blocks", "mbe_b200_ecc_blocks_dev", "mbe_b200_decode_parms", "mbe_b200_spectral_amp_enhance",
             "mbe_b200_adaptive_smoothing", "mbe_b200_synthesize_tone", "mbe_b200_comfort_noise", "mbe_b200_channel_step", "mbe_b200_set_channel_map", "mbe_b200_channel_frame_bytes", "mbe_b200_pool_set_channel_map",
             "mbe_b200_device_count", "mbe_b200_pool_create", "mbe_b200_pool_destroy", "mbe_b200_pool_last_error",
             "mbe_b200_pool_shards", "mbe_b200_pool_shard", "mbe_b200_pool_init_streams", "mbe_b200_pool_export_state",
@@ -75,6 +75,8 @@ def load_library():
             getattr(lib, "mbe_b200_" + n).argtypes = [vp, ci, ci, vp]
         lib.mbe_b200_process_frames_dev.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
         lib.mbe_b200_process_frames.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp]
+        lib.mbe_b200_submit_frames.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp]
+        lib.mbe_b200_wait.argtypes = [vp]
         lib.mbe_b200_set_normalized_float.argtypes = [vp, ci]
         lib.mbe_b200_packed_frame_bytes.argtypes = [ci]
         lib.mbe_b200_process_frames_packed_dev.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
@@ -289,6 +291,17 @@ class Decoder:
 
     def channel_frame_bytes(self, codec):
         return int(self.lib.mbe_b200_channel_frame_bytes(self.h, codec))
+
+    def submit_frames(self, codec, frames, out, soft=False, first_stream=0):
+        """Asynchronous process_frames: `frames` and the arrays of `out` (dict with pcm / results / bits, any may be missing)
+        must stay alive and untouched until wait()."""
+        S, F = frames.shape[0], frames.shape[1]
+        self._check(self.lib.mbe_b200_submit_frames(self.h, codec, int(bool(soft)), first_stream, S, F, _p(frames),
+                                                    _p(out.get("pcm")), _p(out.get("pcmf")), _p(out.get("results")),
+                                                    _p(out.get("bits"))), "submit_frames")
+
+    def wait(self):
+        self._check(self.lib.mbe_b200_wait(self.h), "wait")
 
     def set_normalized_float(self, enable):
         self._check(self.lib.mbe_b200_set_normalized_float(self.h, int(bool(enable))), "set_normalized_float")

@@ -1224,6 +1224,7 @@ constexpr int MAX_CHUNKS = 32;
 struct mbe_b200_ctx {
     int device;
     int max_streams;
+    int pending;           // an mbe_b200_submit_frames batch has not been waited for yet
     int chan_bits[4];      // transmitted bits per bit-packed frame (channel map; default = rows * cols)
     int normalized_float;  // float PCM outputs scaled by 7/32768 (mbelib.h:16-20) instead of the historical scale
     uint32_t* d_state;
@@ -2000,7 +2001,33 @@ static int pipeline_chunk_streams(int n_streams) {
 }
 
 static int frames_host_impl(mbe_b200_ctx* ctx, int codec, int kind, int first_stream, int n_streams, int n_frames,
-                            const uint8_t* frames, int16_t* pcm, float* pcmf, mbe_b200_result* results, uint8_t* bits);
+                            const uint8_t* frames, int16_t* pcm, float* pcmf, mbe_b200_result* results, uint8_t* bits,
+                            bool wait = true);
+
+int mbe_b200_wait(mbe_b200_ctx* ctx) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->s_out));
+    CU(cudaStreamSynchronize(ctx->s_k[0]));
+    CU(cudaStreamSynchronize(ctx->s_k[1]));
+    ctx->pending = 0;
+    return 0;
+}
+
+int mbe_b200_submit_frames(mbe_b200_ctx* ctx, int codec, int soft, int first_stream, int n_streams, int n_frames,
+                           const uint8_t* frames, int16_t* pcm, float* pcmf, mbe_b200_result* results, uint8_t* bits) {
+    if (ctx && ctx->pending) {
+        return fail(ctx, MBE_B200_E_ARG, "submit_frames: a submission is still pending (call mbe_b200_wait first)", cudaSuccess);
+    }
+    const int rc = frames_host_impl(ctx, codec, soft ? 1 : 0, first_stream, n_streams, n_frames, frames, pcm, pcmf, results, bits,
+                                    false);
+    if (rc == 0) {
+        ctx->pending = 1;
+    }
+    return rc;
+}
 
 int mbe_b200_process_frames(mbe_b200_ctx* ctx, int codec, int soft, int first_stream, int n_streams, int n_frames,
                             const uint8_t* frames, int16_t* pcm, float* pcmf, mbe_b200_result* results, uint8_t* bits) {
@@ -2014,8 +2041,12 @@ int mbe_b200_process_frames_packed(mbe_b200_ctx* ctx, int codec, int first_strea
 }
 
 static int frames_host_impl(mbe_b200_ctx* ctx, int codec, int kind, int first_stream, int n_streams, int n_frames,
-                            const uint8_t* frames, int16_t* pcm, float* pcmf, mbe_b200_result* results, uint8_t* bits) {
+                            const uint8_t* frames, int16_t* pcm, float* pcmf, mbe_b200_result* results, uint8_t* bits,
+                            bool wait) {
     int rc = check_range(ctx, first_stream, n_streams);
+    if (rc == 0 && ctx->pending) {
+        return fail(ctx, MBE_B200_E_ARG, "process_frames: a submission is still pending (call mbe_b200_wait first)", cudaSuccess);
+    }
     if (rc < 0) {
         return rc;
     }
@@ -2074,9 +2105,11 @@ static int frames_host_impl(mbe_b200_ctx* ctx, int codec, int kind, int first_st
             }
         }
     }
-    CU(cudaStreamSynchronize(ctx->s_out));
-    CU(cudaStreamSynchronize(ctx->s_k[0]));
-    CU(cudaStreamSynchronize(ctx->s_k[1]));
+    if (wait) {
+        CU(cudaStreamSynchronize(ctx->s_out));
+        CU(cudaStreamSynchronize(ctx->s_k[0]));
+        CU(cudaStreamSynchronize(ctx->s_k[1]));
+    }
     return 0;
 }
 

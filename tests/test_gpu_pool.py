@@ -65,3 +65,43 @@ def test_pool_range_errors(pkg):
     with pytest.raises(pkg.MbeB200Error):
         pool.process_frames(3, np.zeros((17, 1, 96), np.uint8))
     pool.close()
+
+
+def test_submit_and_wait_from_one_thread(pkg):
+    """mbe_b200_submit_frames / mbe_b200_wait: one host thread queues a batch on several contexts, then collects them; a
+    second submission on a busy context is refused; results equal the blocking call."""
+    import torch
+    codec, S, F = 3, 300, 8
+    n_ctx = 3
+    frames = [T.random_hard_frames(codec, S, F, 0xD00 + k) for k in range(n_ctx)]
+    seeds = T.stream_seeds(S, 0x51)
+    ref = pkg.Decoder(max_streams=S, device=0)
+    want = []
+    for k in range(n_ctx):
+        ref.init_streams(0, S, seeds)
+        want.append(ref.process_frames(codec, frames[k]))
+    ref.close()
+    decs = [pkg.Decoder(max_streams=S, device=k % torch.cuda.device_count()) for k in range(n_ctx)]
+    pinned = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+    ins, outs = [], []
+    for k, d in enumerate(decs):
+        d.init_streams(0, S, seeds)
+        fr = pinned(frames[k].shape, torch.uint8)
+        fr[...] = frames[k]
+        out = dict(pcm=pinned((S, F, 160), torch.int16), bits=pinned((S, F, pkg.PARAM_BITS[codec]), torch.uint8),
+                   results=pinned((S, F, 6), torch.int32).view(pkg.RESULT_DTYPE).reshape(S, F))
+        d.submit_frames(codec, fr, out)
+        ins.append(fr)
+        outs.append(out)
+    with pytest.raises(pkg.MbeB200Error):
+        decs[0].submit_frames(codec, ins[0], outs[0])          # still pending
+    for d in decs:
+        d.wait()
+    for k in range(n_ctx):
+        for key in ("pcm", "bits", "results"):
+            assert np.array_equal(outs[k][key], want[k][key]), (k, key)
+    decs[0].wait()                                              # waiting twice is harmless
+    again = decs[0].process_frames(codec, frames[0])            # and the context is usable again
+    assert again["pcm"].shape == (S, F, 160)
+    for d in decs:
+        d.close()
