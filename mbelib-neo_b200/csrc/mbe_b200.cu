@@ -1979,8 +1979,9 @@ static int ensure(mbe_b200_ctx* ctx, void** p, size_t* cap, size_t need) {
 // transfers.
 constexpr int PIPELINE_CHUNKS = 16;
 static int pipeline_chunk_streams(int n_streams) {
-    const int wave = 2 * 148 * WARPS_PER_BLOCK;
-    if (n_streams <= 2 * wave) {
+    // granularity: one block per SM (half a wave): with two alternating compute streams consecutive chunks share the SMs
+    const int wave = 148 * WARPS_PER_BLOCK;
+    if (n_streams <= 4 * wave) {
         return n_streams;
     }
     // MBE_B200_CHUNKS (environment): target number of pipeline chunks per call (tuning knob)

@@ -425,3 +425,33 @@ def test_channel_map_deinterleaves_on_device(dec, pkg, codec):
     dec.init_streams(0, S, seeds)
     again = dec.process_frames_packed(codec, pkg.pack_frames(codec, frames))
     assert np.array_equal(again["pcm"], want["pcm"])
+
+
+def test_host_pipeline_chunks_equal_single_launch(pkg):
+    """The host-pointer call cuts a large batch into stream chunks and pipelines copy-in / kernels / copy-out over several
+    CUDA streams; every chunk must land where a single device-resident launch puts it (PCM, results, bits, final state)."""
+    import torch
+    codec, F = 3, 3
+    S = 20000                                  # > 4 x 148 x 14 streams: several chunks, the last one ragged
+    frames = np.ascontiguousarray(np.tile(T.random_hard_frames(codec, 250, F, 0xC0C), (S // 250, 1, 1)))
+    seeds = T.stream_seeds(S, 0x99)
+    d = pkg.Decoder(max_streams=S, device=0)
+    d.init_streams(0, S, seeds)
+    got = d.process_frames(codec, frames, want_float=True)
+    st_host = d.export_state(0, S)
+    d.init_streams(0, S, seeds)
+    dev = torch.device("cuda", 0)
+    d_fr = torch.from_numpy(frames).to(dev)
+    d_pcm = torch.empty((S, F, 160), dtype=torch.int16, device=dev)
+    d_pcmf = torch.empty((S, F, 160), dtype=torch.float32, device=dev)
+    d_res = torch.empty((S, F, 6), dtype=torch.int32, device=dev)
+    d_bits = torch.empty((S, F, pkg.PARAM_BITS[codec]), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    d.process_frames_dev(codec, 0, 0, S, F, d_fr.data_ptr(), d_pcm.data_ptr(), d_pcmf.data_ptr(), d_res.data_ptr(), d_bits.data_ptr())
+    d.synchronize()
+    assert np.array_equal(got["pcm"], d_pcm.cpu().numpy())
+    assert np.array_equal(got["pcmf"].view(np.uint32), d_pcmf.cpu().numpy().view(np.uint32))
+    assert np.array_equal(got["bits"], d_bits.cpu().numpy())
+    assert np.array_equal(got["results"].view(np.int32).reshape(S, F, 6), d_res.cpu().numpy())
+    assert np.array_equal(st_host, d.export_state(0, S))
+    d.close()
