@@ -293,6 +293,7 @@ struct BlockShared {
     int cnt[2][WARPS_PER_BLOCK + 2];      // per stream: component count of the current frame (double-buffered by frame parity)
     int n_interp[2];                      // phase-interpolated harmonics of the block's streams in this frame
     unsigned short interp[2][WARPS_PER_BLOCK * 7 + 2];  // owner stream << 8 | list position (at most 7 per stream: l < 8)
+    float interp_a1[2][WARPS_PER_BLOCK * 7 + 2];        // per item: the phase increment per sample, pw0*l + delta-omega
 };
 
 // MBE_STAGE_TIMING=1 builds accumulate per-stage clock64() deltas per warp into LaunchArgs.dbg (profiling aid)

@@ -1040,7 +1040,17 @@ __device__ __forceinline__ void publish_components(BlockShared* bs, int parity, 
         }
         at = __shfl_sync(FULL, at, 0);
         if (lane < n) {
-            bs->interp[parity][at + lane] = (unsigned short)((warp << 8) | __fns(m, 0, lane + 1));
+            // the item's per-sample phase increment (mbelib.c:959-961) is the same for all 160 samples: computed once here,
+            // one lane per item, instead of once per 32-sample chunk by whoever renders it
+            const int pos = (int)__fns(m, 0, lane + 1);
+            const int l = ws.comp[pos] >> 2;
+            const float cw0 = ws.cur.w0, pw0 = ws.enh.w0;
+            const float pw0l = pw0 * (float)l;
+            const float dphi = ws.cur.PHIl[l] - ws.enh.PHIl[l] - (((pw0 + cw0) * (float)(l * NS)) / 2.0f);
+            const float dw = (1.0f / (float)NS)
+                             * (dphi - (2.0f * MBE_PI_F * floorf((dphi + MBE_PI_F) / (2.0f * MBE_PI_F))));
+            bs->interp[parity][at + lane] = (unsigned short)((warp << 8) | pos);
+            bs->interp_a1[parity][at + lane] = pw0l + dw;
         }
     }
 }
@@ -1069,6 +1079,7 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, BlockShared* bs, 
     const int* cnt = bs->cnt[parity];
     const int n_interp = bs->n_interp[parity];
     const unsigned short* interp = bs->interp[parity];
+    const float* interp_a1 = bs->interp_a1[parity];
     if (warp == 0 && lane == 0) {
         bs->n_interp[parity ^ 1] = 0;  // next frame's list (its appends come after at least one more block barrier)
     }
@@ -1162,7 +1173,7 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, BlockShared* bs, 
                 const int slot = off[item >> 8] + (item & 255);
                 if (slot >= base && slot < base + 32 * W) {
                     if (lane == 0) {
-                        me.interp_item[n_mine] = (unsigned short)item;
+                        me.interp_item[n_mine] = (unsigned short)t;  // index into the block's work list
                     }
                     ++n_mine;
                 }
@@ -1208,17 +1219,14 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, BlockShared* bs, 
                 const int n = 32 * ch + lane;
 #pragma unroll 1
                 for (int q = 0; q < n_mine; ++q) {
-                    const int item = me.interp_item[q];
+                    const int t = me.interp_item[q];
+                    const int item = interp[t];
                     const int i = item >> 8, pos = item & 255;
                     const WarpWS& o = wsa[i];
                     const int slot = off[i] + pos - base;  // slot index inside the round
                     const int l = o.comp[pos] >> 2;
                     const float cw0 = o.cur.w0, pw0 = o.enh.w0;
-                    const float pw0l = pw0 * (float)l;
-                    const float dphi = o.cur.PHIl[l] - o.enh.PHIl[l] - (((pw0 + cw0) * (float)(l * NS)) / 2.0f);
-                    const float dw = (1.0f / (float)NS)
-                                     * (dphi - (2.0f * MBE_PI_F * floorf((dphi + MBE_PI_F) / (2.0f * MBE_PI_F))));
-                    const float th = o.enh.PHIl[l] + ((pw0l + dw) * (float)n)
+                    const float th = o.enh.PHIl[l] + (interp_a1[t] * (float)n)
                                      + (((cw0 - pw0) * (float)(l * n * n)) / (float)(2 * NS));
                     const float am = o.enh.Ml[l] + (((float)n / (float)NS) * (o.cur.Ml[l] - o.enh.Ml[l]));
                     wsa[slot >> 5].u.tile[tile_at(lane, slot & 31)] = 2.0f * am * dev_cosf(th);
