@@ -40,12 +40,12 @@ FRAME_BITS = {0: 184, 1: 168, 2: 96, 3: 96}
 FLOP_PER_FRAME = {0: 84e3, 1: 84e3, 2: 66e3, 3: 61e3}
 STATE_BYTES = 7828  # 3 x mbe_parms + 16 B RNG words per stream
 # DRAM traffic of the stream kernel per frame, measured: dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` capture (profiles/r01o_stream_kernel_ncu_details.txt: 173.2 MB + 366.6 MB for 16576 streams x 50
+# `ncu --set full` capture (profiles/r01s_stream_kernel_ncu_details.txt: 172.4 MB + 367.4 MB for 16576 streams x 50
 # frames of AMBE+2 hard-decision input) divided by the frames of that launch.  Only quoted for that workload.
-NCU_DRAM_BYTES_PER_FRAME = {("ambe3600x2450", 0): (173.174272e6 + 366.612992e6) / (16576 * 50)}
+NCU_DRAM_BYTES_PER_FRAME = {("ambe3600x2450", 0): (172.412928e6 + 367.429632e6) / (16576 * 50)}
 # executed warp-instructions per frame of the same capture (smsp__inst_executed.sum / frames): the kernel is bound by
 # instruction issue, so this x frames/s against 148 SM x 4 schedulers x SM clock is the utilisation that matters
-NCU_WARP_INSTR_PER_FRAME = {("ambe3600x2450", 0): 4582643573.0 / (16576 * 50)}
+NCU_WARP_INSTR_PER_FRAME = {("ambe3600x2450", 0): 4565407027.0 / (16576 * 50)}
 RESULT_BYTES = 24
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -498,7 +498,7 @@ def main():
     per_frame_dram = NCU_DRAM_BYTES_PER_FRAME.get((CODEC_NAMES[codec], soft))
     roofline = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                 "traffic": (per_frame_dram * S * F) if per_frame_dram else None,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per frame (profiles/r01o_*) x frames per launch"
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per frame (profiles/r01s_*) x frames per launch"
                 if per_frame_dram else None,
                 "peak_source": peak_src, "kernel": "mbe_stream_kernel",
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms,
@@ -515,7 +515,7 @@ def main():
         roofline_fp32["issue_slots"] = {
             "achieved": issue_ach / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instr/s", "frac": issue_ach / issue_peak,
             "warp_instr_per_frame": wipf,
-            "source": "ncu smsp__inst_executed.sum per frame (profiles/r01o_*) x frames per launch / event-timed launch"}
+            "source": "ncu smsp__inst_executed.sum per frame (profiles/r01s_*) x frames per launch / event-timed launch"}
     line = {"metric": "decoded frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
