@@ -105,3 +105,25 @@ def test_submit_and_wait_from_one_thread(pkg):
     assert again["pcm"].shape == (S, F, 160)
     for d in decs:
         d.close()
+
+
+def test_contexts_release_their_device_memory(pkg):
+    """create / use / destroy in a loop: tables, state pool, staging buffers, streams and events all go back."""
+    import torch
+    codec, S, F = 3, 2048, 4
+    frames = T.random_hard_frames(codec, S, F, 1)
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(0)
+    for k in range(12):
+        d = pkg.Decoder(max_streams=S, device=0)
+        d.init_streams(0, S, None)
+        d.process_frames(codec, frames, want_float=True)
+        d.decode_frames(codec, frames.reshape(S * F, -1))
+        d.close()
+        p = pkg.Pool(S, devices=[0, 0])
+        p.init_streams(0, S, None)
+        p.process_frames(codec, frames)
+        p.close()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info(0)
+    assert free0 - free1 < 64 << 20, "device memory not released: %d MB" % ((free0 - free1) >> 20)
