@@ -455,3 +455,36 @@ def test_host_pipeline_chunks_equal_single_launch(pkg):
     assert np.array_equal(got["results"].view(np.int32).reshape(S, F, 6), d_res.cpu().numpy())
     assert np.array_equal(st_host, d.export_state(0, S))
     d.close()
+
+
+def test_short_launches_over_many_streams(pkg):
+    """One or two frames per launch over many streams (what a real-time server does): 66 000 streams = 4715 blocks with a
+    ragged last one, launches of 1, 2, 1, 2 frames; replicas of 300 distinct streams must equal the oracle wherever they
+    sit in the grid, frame after frame, and so must the final state."""
+    import torch
+    codec, S, B, F = 3, 66000, 300, 6
+    base = T.random_hard_frames(codec, B, F, 0x4E5)
+    frames = np.ascontiguousarray(np.tile(base, ((S + B - 1) // B, 1, 1))[:S])
+    seeds = np.tile(T.stream_seeds(B, 0x77), (S + B - 1) // B)[:S].astype(np.uint32)
+    want = T.run_cpu(T.load_oracle().mbo_run, codec, 0, base, T.stream_seeds(B, 0x77), n_threads=8)
+    dev = torch.device("cuda", 0)
+    d_fr = torch.from_numpy(frames).to(dev)
+    d = pkg.Decoder(max_streams=S, device=0)
+    d.init_streams(0, S, seeds)
+    d_pcm = torch.empty((S, F, 160), dtype=torch.int16, device=dev)
+    d_res = torch.empty((S, F, 6), dtype=torch.int32, device=dev)
+    for f0, nf in ((0, 1), (1, 2), (3, 1), (4, 2)):
+        fr = d_fr[:, f0:f0 + nf].contiguous()
+        pcm = torch.empty((S, nf, 160), dtype=torch.int16, device=dev)
+        res = torch.empty((S, nf, 6), dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        d.process_frames_dev(codec, 0, 0, S, nf, fr.data_ptr(), pcm.data_ptr(), 0, res.data_ptr(), 0)
+        d.synchronize()
+        d_pcm[:, f0:f0 + nf] = pcm
+        d_res[:, f0:f0 + nf] = res
+    pcm, res, st = d_pcm.cpu().numpy(), d_res.cpu().numpy(), d.export_state(0, S)
+    d.close()
+    for k in (0, (S // B // 2) * B, (S // B - 1) * B):           # replicas at the start, the middle and the end of the grid
+        assert np.array_equal(pcm[k:k + B], want["pcm"]), k
+        assert np.array_equal(res[k:k + B, :, 4], want["results"][..., 4]), k
+        assert np.array_equal(st[k:k + B], want["state"]), k
