@@ -127,6 +127,13 @@ MBE_B200_API int mbe_b200_set_normalized_float(mbe_b200_ctx* ctx, int enable);
  * Semantics per frame are those of mbe_process<Codec>Frame[f]; a packed bit can only be 0 or 1, so
  * MBE_STATUS_INVALID_BITS cannot occur. */
 MBE_B200_API int mbe_b200_packed_frame_bytes(int codec);
+/* How a host-pointer call of n_streams streams is cut into pipeline chunks (host logic only, no device needed): writes
+ * up to `cap` chunk sizes in stream order and returns the number of chunks (0 for an empty call).  Small batches are one
+ * chunk; large ones are about 32 chunks of whole blocks-per-SM multiples, with pieces that double from / halve towards
+ * the two ends so that the copy-in ahead of the first kernel and the copy-out behind the last one stay small.
+ * MBE_B200_CHUNKS / MBE_B200_TAPER / MBE_B200_KSTREAMS (environment) override chunk count, smallest piece in blocks
+ * (0 = no taper) and the number of compute streams; they are tuning knobs, results do not depend on them. */
+MBE_B200_API int mbe_b200_pipeline_plan(int n_streams, int* sizes, int cap);
 /* Channel map (on-device de-interleave): by default packed bit k is frame position k.  With a map,
  * the packed frame holds the n_bits transmitted bits of the air interface in transmission order (MSB first, n_bits <=
  * rows*cols, mbe_b200_channel_frame_bytes() bytes per frame) and transmitted bit k lands at frame position

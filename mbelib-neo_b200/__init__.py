@@ -34,7 +34,7 @@ _EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b
             "mbe_b200_decode_frames_dev", "mbe_b200_decode_frames", "mbe_b200_process_data_dev",
             "mbe_b200_process_data", "mbe_b200_synthesize_speech", "mbe_b200_synthesize_speech_rng", "mbe_b200_floattoshort",
             "mbe_b200_floattoshort_dev", "mbe_b200_synchronize", "mbe_b200_debug_stage_cycles",
-            "mbe_b200_set_normalized_float", "mbe_b200_packed_frame_bytes", "mbe_b200_process_frames_packed_dev", "mbe_b200_process_frames_packed",
+            "mbe_b200_set_normalized_float", "mbe_b200_packed_frame_bytes", "mbe_b200_pipeline_plan", "mbe_b200_process_frames_packed_dev", "mbe_b200_process_frames_packed",
             "mbe_b200_submit_frames", "mbe_b200_wait", "mbe_b200_ecc_blocks", "mbe_b200_ecc_blocks_dev", "mbe_b200_decode_parms", "mbe_b200_spectral_amp_enhance",
             "mbe_b200_adaptive_smoothing", "mbe_b200_synthesize_tone", "mbe_b200_comfort_noise", "mbe_b200_channel_step", "mbe_b200_set_channel_map", "mbe_b200_channel_frame_bytes", "mbe_b200_pool_set_channel_map",
             "mbe_b200_device_count", "mbe_b200_pool_create", "mbe_b200_pool_destroy", "mbe_b200_pool_last_error",
@@ -79,6 +79,7 @@ def load_library():
         lib.mbe_b200_wait.argtypes = [vp]
         lib.mbe_b200_set_normalized_float.argtypes = [vp, ci]
         lib.mbe_b200_packed_frame_bytes.argtypes = [ci]
+        lib.mbe_b200_pipeline_plan.argtypes = [ci, ctypes.POINTER(ci), ci]
         lib.mbe_b200_process_frames_packed_dev.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
         lib.mbe_b200_process_frames_packed.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp]
         lib.mbe_b200_decode_frames_dev.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp]

@@ -1219,7 +1219,8 @@ __global__ void mbe_state_xfer_kernel(uint32_t* state, int first, int count, uin
 using namespace mbe;
 
 // the host-pointer entry points cut a batch into up to MAX_CHUNKS stream ranges and pipeline them
-constexpr int MAX_CHUNKS = 32;
+constexpr int MAX_CHUNKS = 64;
+constexpr int MAX_KSTREAMS = 4;
 
 struct mbe_b200_ctx {
     int device;
@@ -1230,8 +1231,8 @@ struct mbe_b200_ctx {
     uint32_t* d_state;
     DevTables* d_tab;
     cudaStream_t stream;
-    // host-pointer pipeline: copy-in stream, two alternating compute streams, copy-out stream, chunk events
-    cudaStream_t s_in, s_k[2], s_out;
+    // host-pointer pipeline: copy-in stream, compute streams taken in rotation, copy-out stream, chunk events
+    cudaStream_t s_in, s_k[MAX_KSTREAMS], s_out;
     cudaEvent_t ev_in[MAX_CHUNKS], ev_k[MAX_CHUNKS], ev_start;
     // staging for the host-pointer entry points (grown on demand)
     void* d_in;
@@ -1599,8 +1600,9 @@ int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams) {
     CUC(cudaSetDevice(device_ordinal));
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
-    CUC(cudaStreamCreateWithFlags(&ctx->s_k[0], cudaStreamNonBlocking));
-    CUC(cudaStreamCreateWithFlags(&ctx->s_k[1], cudaStreamNonBlocking));
+    for (int i = 0; i < MAX_KSTREAMS; ++i) {
+        CUC(cudaStreamCreateWithFlags(&ctx->s_k[i], cudaStreamNonBlocking));
+    }
     CUC(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
     CUC(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
     for (int i = 0; i < MAX_CHUNKS; ++i) {
@@ -1647,8 +1649,11 @@ void mbe_b200_destroy(mbe_b200_ctx* ctx) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
     }
-    cudaStream_t extra[4] = {ctx->s_in, ctx->s_k[0], ctx->s_k[1], ctx->s_out};
-    for (int i = 0; i < 4; ++i) {
+    cudaStream_t extra[2 + MAX_KSTREAMS] = {ctx->s_in, ctx->s_out};
+    for (int i = 0; i < MAX_KSTREAMS; ++i) {
+        extra[2 + i] = ctx->s_k[i];
+    }
+    for (int i = 0; i < 2 + MAX_KSTREAMS; ++i) {
         if (extra[i]) {
             cudaStreamSynchronize(extra[i]);
             cudaStreamDestroy(extra[i]);
@@ -1974,12 +1979,14 @@ static int ensure(mbe_b200_ctx* ctx, void** p, size_t* cap, size_t need) {
     return 0;
 }
 
-// Streams per pipeline chunk: whole waves of the stream kernel (2 blocks per SM x 148 SMs x WARPS_PER_BLOCK
-// streams), about sixteen chunks per batch, so the first copy-in and the last copy-out are the only exposed
-// transfers.
-constexpr int PIPELINE_CHUNKS = 16;
+// Streams per pipeline chunk: half waves of the stream kernel (1 block per SM x 148 SMs x WARPS_PER_BLOCK streams),
+// about thirty-two chunks per batch on four compute streams, tapered at both ends (pipeline_schedule), so the first
+// copy-in and the last copy-out are the only exposed transfers and both are small
+// (profiles/experiments/r01x_pipeline_taper.txt).
+constexpr int PIPELINE_CHUNKS = 32;
+constexpr int PIPELINE_TAPER_BLOCKS = 18;
 static int pipeline_chunk_streams(int n_streams) {
-    // granularity: one block per SM (half a wave): with two alternating compute streams consecutive chunks share the SMs
+    // granularity: one block per SM (half a wave): consecutive chunks run on different compute streams and share the SMs
     const int wave = 148 * WARPS_PER_BLOCK;
     if (n_streams <= 4 * wave) {
         return n_streams;
@@ -2001,6 +2008,82 @@ static int pipeline_chunk_streams(int n_streams) {
     return chunk;
 }
 
+// The chunk sizes of one call.  Body chunks of `chunk` streams; with a taper (MBE_B200_TAPER = smallest piece in
+// blocks, 0 = none) the first and the last chunk's worth of streams are cut into pieces that double towards the body /
+// halve towards the end, so the copy-in in front of the first kernel and the copy-out behind the last one are small.
+static int pipeline_taper_blocks() {
+    static int t = -1;
+    if (t < 0) {
+        const char* e = getenv("MBE_B200_TAPER");
+        t = e ? atoi(e) : PIPELINE_TAPER_BLOCKS;
+        if (t < 0 || t > 148) {
+            t = PIPELINE_TAPER_BLOCKS;
+        }
+    }
+    return t;
+}
+
+static int pipeline_kstreams() {
+    static int k = 0;
+    if (k == 0) {
+        const char* e = getenv("MBE_B200_KSTREAMS");
+        k = e ? atoi(e) : MAX_KSTREAMS;
+        if (k < 1 || k > MAX_KSTREAMS) {
+            k = MAX_KSTREAMS;
+        }
+    }
+    return k;
+}
+
+static int pipeline_schedule(int n_streams, int chunk, int* sizes) {
+    const int min_piece = pipeline_taper_blocks() * WARPS_PER_BLOCK;
+    int n = 0;
+    if (min_piece == 0 || n_streams < 4 * chunk) {
+        for (int s0 = 0; s0 < n_streams; s0 += chunk) {
+            sizes[n++] = (n_streams - s0 < chunk) ? (n_streams - s0) : chunk;
+        }
+        return n;
+    }
+    int head[8], tail[8], nh = 0, nt = 0, used = 0;
+    for (int p = min_piece; p < chunk && nh < 8; p *= 2) {  // min, 2 min, 4 min ... (< chunk) at both ends
+        head[nh++] = p;
+        tail[nt++] = p;
+        used += 2 * p;
+    }
+    int body = n_streams - used;
+    for (int i = 0; i < nh; ++i) {
+        sizes[n++] = head[i];
+    }
+    while (body > 0 && n < MAX_CHUNKS - nt) {
+        const int left = MAX_CHUNKS - nt - n;  // chunks still available for the body
+        int take = (body < chunk) ? body : chunk;
+        if (left == 1) {
+            take = body;
+        }
+        sizes[n++] = take;
+        body -= take;
+    }
+    for (int i = nt - 1; i >= 0; --i) {
+        sizes[n++] = tail[i];
+    }
+    return n;
+}
+
+int mbe_b200_pipeline_plan(int n_streams, int* sizes, int cap) {
+    if (n_streams < 0 || (cap > 0 && !sizes)) {
+        return MBE_B200_E_ARG;
+    }
+    if (n_streams == 0) {
+        return 0;
+    }
+    int tmp[MAX_CHUNKS];
+    const int n = pipeline_schedule(n_streams, pipeline_chunk_streams(n_streams), tmp);
+    for (int i = 0; i < n && i < cap; ++i) {
+        sizes[i] = tmp[i];
+    }
+    return n;
+}
+
 static int frames_host_impl(mbe_b200_ctx* ctx, int codec, int kind, int first_stream, int n_streams, int n_frames,
                             const uint8_t* frames, int16_t* pcm, float* pcmf, mbe_b200_result* results, uint8_t* bits,
                             bool wait = true);
@@ -2011,8 +2094,9 @@ int mbe_b200_wait(mbe_b200_ctx* ctx) {
     }
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->s_out));
-    CU(cudaStreamSynchronize(ctx->s_k[0]));
-    CU(cudaStreamSynchronize(ctx->s_k[1]));
+    for (int i = 0; i < MAX_KSTREAMS; ++i) {
+        CU(cudaStreamSynchronize(ctx->s_k[i]));
+    }
     ctx->pending = 0;
     return 0;
 }
@@ -2079,21 +2163,27 @@ static int frames_host_impl(mbe_b200_ctx* ctx, int codec, int kind, int first_st
     const int chunk = pipeline_chunk_streams(n_streams);
     CU(cudaEventRecord(ctx->ev_start, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
-    CU(cudaStreamWaitEvent(ctx->s_k[0], ctx->ev_start, 0));
-    CU(cudaStreamWaitEvent(ctx->s_k[1], ctx->ev_start, 0));
-    int c = 0;
-    for (int s0 = 0; s0 < n_streams; s0 += chunk, ++c) {
-        const int ns = (n_streams - s0 < chunk) ? (n_streams - s0) : chunk;
+    for (int i = 0; i < MAX_KSTREAMS; ++i) {
+        CU(cudaStreamWaitEvent(ctx->s_k[i], ctx->ev_start, 0));
+    }
+    int sizes[MAX_CHUNKS];
+    const int n_chunks = pipeline_schedule(n_streams, chunk, sizes);
+    const int n_k = pipeline_kstreams();
+    int s0 = 0;
+    for (int c = 0; c < n_chunks; s0 += sizes[c], ++c) {
+        const int ns = sizes[c];
         const size_t f0 = (size_t)s0 * n_frames, fn = (size_t)ns * n_frames;
-        cudaStream_t sk = ctx->s_k[c & 1];
+        cudaStream_t sk = ctx->s_k[c % n_k];
         CU(cudaMemcpyAsync((uint8_t*)ctx->d_in + f0 * in_per_frame, frames + f0 * in_per_frame, fn * in_per_frame,
                            cudaMemcpyHostToDevice, ctx->s_in));
         CU(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
         CU(cudaStreamWaitEvent(sk, ctx->ev_in[c], 0));
-        rc = frames_dev_impl(
-            ctx, codec, kind, first_stream + s0, ns, n_frames, (const uint8_t*)ctx->d_in + f0 * in_per_frame,
-            pcm ? (int16_t*)ctx->d_out[0] + f0 * NS : nullptr, pcmf ? (float*)ctx->d_out[1] + f0 * NS : nullptr,
-            results ? (mbe_b200_result*)ctx->d_out[2] + f0 : nullptr, bits ? (uint8_t*)ctx->d_out[3] + f0 * pb : nullptr, sk);
+        int16_t* const o_pcm = pcm ? (int16_t*)ctx->d_out[0] + f0 * NS : nullptr;
+        float* const o_pcmf = pcmf ? (float*)ctx->d_out[1] + f0 * NS : nullptr;
+        mbe_b200_result* const o_res = results ? (mbe_b200_result*)ctx->d_out[2] + f0 : nullptr;
+        uint8_t* const o_bits = bits ? (uint8_t*)ctx->d_out[3] + f0 * pb : nullptr;
+        const uint8_t* const i_fr = (const uint8_t*)ctx->d_in + f0 * in_per_frame;
+        rc = frames_dev_impl(ctx, codec, kind, first_stream + s0, ns, n_frames, i_fr, o_pcm, o_pcmf, o_res, o_bits, sk);
         if (rc < 0) {
             return rc;
         }
@@ -2108,8 +2198,9 @@ static int frames_host_impl(mbe_b200_ctx* ctx, int codec, int kind, int first_st
     }
     if (wait) {
         CU(cudaStreamSynchronize(ctx->s_out));
-        CU(cudaStreamSynchronize(ctx->s_k[0]));
-        CU(cudaStreamSynchronize(ctx->s_k[1]));
+        for (int i = 0; i < MAX_KSTREAMS; ++i) {
+            CU(cudaStreamSynchronize(ctx->s_k[i]));
+        }
     }
     return 0;
 }

@@ -86,3 +86,30 @@ def test_pool_has_no_cpu_fallback(pkg):
     with pytest.raises(pkg.MbeB200Error) as e:
         pkg.Pool(max_streams=8)
     assert "-3" in str(e.value)
+
+
+def test_pipeline_plan_covers_every_stream_once(pkg):
+    """Host logic of the host-pointer call: the chunk plan of a batch covers [0, n_streams) exactly once in
+    order, small batches stay one chunk, large ones are tapered at both ends, and the plan never exceeds the event pool."""
+    lib = pkg.load_library()
+    ci = ctypes.c_int
+    buf = (ci * 64)()
+    assert lib.mbe_b200_pipeline_plan(0, buf, 64) == 0
+    assert lib.mbe_b200_pipeline_plan(-1, buf, 64) < 0
+    assert lib.mbe_b200_pipeline_plan(10, None, 64) < 0
+    half_wave = 148 * 14
+    for n in (1, 13, 14, 15, 2072, 4 * half_wave, 4 * half_wave + 1, 20000, 65536, 66000, 131072, 262144, 1048576, 1048577,
+              4000000):
+        k = lib.mbe_b200_pipeline_plan(n, buf, 64)
+        assert 1 <= k <= 64, (n, k)
+        sizes = list(buf[:k])
+        assert all(s > 0 for s in sizes) and sum(sizes) == n, (n, sizes)
+        if n <= 4 * half_wave:
+            assert k == 1
+        assert lib.mbe_b200_pipeline_plan(n, buf, 0) == k      # count only
+    # the bench workload: small pieces at both ends, half-wave multiples in between
+    k = lib.mbe_b200_pipeline_plan(65536, buf, 64)
+    sizes = list(buf[:k])
+    assert sizes[0] == sizes[-1] == 18 * 14 and sizes[1] == sizes[-2] == 36 * 14
+    assert max(sizes) == half_wave and sizes[:4] == sorted(sizes[:4]) and sizes[-4:] == sorted(sizes[-4:], reverse=True)
+    assert all(s % 14 == 0 for s in sizes[:-5])

@@ -427,11 +427,13 @@ def test_channel_map_deinterleaves_on_device(dec, pkg, codec):
     assert np.array_equal(again["pcm"], want["pcm"])
 
 
-def test_host_pipeline_chunks_equal_single_launch(pkg):
-    """The host-pointer call cuts a large batch into stream chunks and pipelines copy-in / kernels / copy-out over several
-    CUDA streams; every chunk must land where a single device-resident launch puts it (PCM, results, bits, final state)."""
+@pytest.mark.parametrize("F", [3, 33])
+def test_host_pipeline_chunks_equal_single_launch(pkg, F):
+    """The host-pointer call cuts a large batch into stream chunks (tapered at both ends, a ragged one in the middle) and
+    pipelines copy-in / kernels / copy-out over several CUDA streams; every chunk must land where a single
+    device-resident launch puts it (PCM, float PCM, results, bits, final state), for short and long launches."""
     import torch
-    codec, F = 3, 3
+    codec = 3
     S = 20000                                  # > 4 x 148 x 14 streams: several chunks, the last one ragged
     frames = np.ascontiguousarray(np.tile(T.random_hard_frames(codec, 250, F, 0xC0C), (S // 250, 1, 1)))
     seeds = T.stream_seeds(S, 0x99)
