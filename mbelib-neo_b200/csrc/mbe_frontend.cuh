@@ -83,20 +83,14 @@ __device__ __forceinline__ unsigned soft_cost_of(const unsigned char* rel, unsig
     return __reduce_add_sync(FULL, (lane < nbits && ((pattern >> lane) & 1u)) ? (unsigned)rel[lane] : 0u);
 }
 
-__device__ __forceinline__ unsigned golay_soft(unsigned hard23, const unsigned char* rel, const SoftScratch& S,
-                                               const DevTables* T, int lane, int* errs) {
-    int e_hard;
-    const unsigned hf = golay_hard(hard23, T, &e_hard);
+// The search proper: the smallest key over the whole coset (see above).  The soft decoders are one copy per kernel
+// (golay_soft_packed / hamming_soft_packed are __noinline__): the callers sit in unrolled row loops, and four inlined copies
+// of the Golay decoder plus three of the Hamming decoder push the soft-decision kernels past the instruction cache (profiles/r01z_imbe_soft_kernel_sass_summary.txt: 33 % of the stall samples were
+// instruction fetch).
+__device__ __forceinline__ unsigned golay_soft_search(unsigned hard23, const unsigned char* rel, unsigned short* s_cp, unsigned* s_ka,
+                                                   unsigned short* s_qa, const DevTables* T, int lane) {
     const unsigned hd = (hard23 >> 11) & 0xfffu;
     const unsigned syn = golay_parity(hd, T) ^ (hard23 & 0x7ffu);
-    // the hard decode's difference pattern (weight <= 3) and its cost
-    const unsigned dhf = hf ^ hd;
-    const unsigned xhf = (dhf << 11) | (golay_parity(dhf, T) ^ syn);
-    const unsigned U = soft_cost_of(rel, xhf, 23, lane);
-    if (U == 0u || soft_least_outside(rel, xhf, 23, 7 - __popc(xhf), U, lane) >= U) {
-        *errs = e_hard;
-        return hf;
-    }
     // five-bit subset sums selected by the lane number: positions 17..21 (high data half), 11..15 (low data half),
     // 1..5 and 6..10 (parity)
     unsigned sA = 0, sB = 0, sL = 0, sH = 0;
@@ -111,8 +105,8 @@ __device__ __forceinline__ unsigned golay_soft(unsigned hard23, const unsigned c
     const unsigned pl = (unsigned)__popc(lane);
     const unsigned hdh = hd >> 6, hdl = hd & 63u;
     __syncwarp();
-    S.ka[lane] = (sA << 16) | (pl << 12) | ((((unsigned)lane) ^ hdh) << 6);
-    S.qa[lane] = (unsigned short)(((unsigned)T->golay_par_hi[lane] ^ syn) << 1);
+    s_ka[lane] = (sA << 16) | (pl << 12) | ((((unsigned)lane) ^ hdh) << 6);
+    s_qa[lane] = (unsigned short)(((unsigned)T->golay_par_hi[lane] ^ syn) << 1);
     const unsigned kb0 = (sB << 16) | (pl << 12) | (((unsigned)lane) ^ hdl);
     const unsigned kb1 = ((sB + (unsigned)rel[16]) << 16) | ((pl + 1u) << 12) | (((unsigned)lane + 32u) ^ hdl);
     const unsigned pb0 = (unsigned)T->golay_par_lo[lane] << 1;
@@ -121,14 +115,14 @@ __device__ __forceinline__ unsigned golay_soft(unsigned hard23, const unsigned c
         // cp[64 h + 2 lane + j], j = 0, 1, written as one word per lane and h
         const unsigned pair = sL | ((sL + (unsigned)rel[0]) << 16);
         const unsigned hdup = sH * 0x10001u;
-        unsigned* cp32 = reinterpret_cast<unsigned*>(S.cp);
+        unsigned* cp32 = reinterpret_cast<unsigned*>(s_cp);
 #pragma unroll 8
         for (int h = 0; h < 32; ++h) {
             cp32[32 * h + lane] = pair + __shfl_sync(FULL, hdup, h);
         }
     }
     __syncwarp();
-    const unsigned char* cpb = reinterpret_cast<const unsigned char*>(S.cp);
+    const unsigned char* cpb = reinterpret_cast<const unsigned char*>(s_cp);
     // The all-ones word is a codeword, so the complement of every candidate is a candidate too, and its key is
     // KMAX - key with no borrow between the fields (cost -> total - cost, differing bits -> 12 - n, data -> 0xfff - data):
     // walk the 32 high halves with a clear top bit, keep the smallest AND the largest key
@@ -137,8 +131,8 @@ __device__ __forceinline__ unsigned golay_soft(unsigned hard23, const unsigned c
     unsigned best = 0xffffffffu, worst = 0u;
 #pragma unroll 8
     for (int a = 0; a < 32; ++a) {
-        const unsigned q = S.qa[a];
-        const unsigned k = S.ka[a];
+        const unsigned q = s_qa[a];
+        const unsigned k = s_ka[a];
         const unsigned c0 = *reinterpret_cast<const unsigned short*>(cpb + (q ^ pb0));
         const unsigned c1 = *reinterpret_cast<const unsigned short*>(cpb + (q ^ pb1));
         const unsigned k0 = ((c0 << 16) + kb0) + k, k1 = ((c1 << 16) + kb1) + k;
@@ -147,29 +141,52 @@ __device__ __forceinline__ unsigned golay_soft(unsigned hard23, const unsigned c
     }
     best = __reduce_min_sync(FULL, min(best, kmax - worst));
     __syncwarp();
-    if ((best >> 16) < U) {
-        *errs = (int)((best >> 12) & 15u);
-        return best & 0xfffu;
+    return best;
+}
+
+// returns corrected data | changed data bits << 24
+__device__ __forceinline__ unsigned golay_soft_body(unsigned hard23, const unsigned char* rel, unsigned short* s_cp, unsigned* s_ka,
+                                                   unsigned short* s_qa, const DevTables* T, int lane) {
+    int e_hard;
+    const unsigned hf = golay_hard(hard23, T, &e_hard);
+    const unsigned hd = (hard23 >> 11) & 0xfffu;
+    const unsigned syn = golay_parity(hd, T) ^ (hard23 & 0x7ffu);
+    // the hard decode's difference pattern (weight <= 3) and its cost
+    const unsigned dhf = hf ^ hd;
+    const unsigned xhf = (dhf << 11) | (golay_parity(dhf, T) ^ syn);
+    const unsigned U = soft_cost_of(rel, xhf, 23, lane);
+    if (U == 0u || soft_least_outside(rel, xhf, 23, 7 - __popc(xhf), U, lane) >= U) {
+        return hf | ((unsigned)e_hard << 24);
     }
-    *errs = e_hard;
-    return hf;
+    const unsigned best = golay_soft_search(hard23, rel, s_cp, s_ka, s_qa, T, lane);
+    if ((best >> 16) < U) {
+        return (best & 0xfffu) | (((best >> 12) & 15u) << 24);
+    }
+    return hf | ((unsigned)e_hard << 24);
+}
+
+__device__ __noinline__ unsigned golay_soft_packed(unsigned hard23, const unsigned char* rel, unsigned short* s_cp, unsigned* s_ka,
+                                                   unsigned short* s_qa, const DevTables* T, int lane) {
+    return golay_soft_body(hard23, rel, s_cp, s_ka, s_qa, T, lane);
+}
+
+// outlined: one shared copy of the decoder (the IMBE front-ends call it four times per frame from unrolled loops);
+// the AMBE front-ends, with two calls and smaller kernels, keep it inline (1-2 % faster there)
+__device__ __forceinline__ unsigned golay_soft(unsigned hard23, const unsigned char* rel, const SoftScratch& S,
+                                               const DevTables* T, int lane, int* errs, bool outlined) {
+    const unsigned r = outlined ? golay_soft_packed(hard23, rel, S.cp, S.ka, S.qa, T, lane)
+                                : golay_soft_body(hard23, rel, S.cp, S.ka, S.qa, T, lane);
+    *errs = (int)(r >> 24);
+    return r & 0xffffffu;
 }
 
 // Hamming(15,11), both bit layouts (V = 0: ecc.c:366-408, V = 1: the IMBE 7100 variant, ecc.c:422-464).  Same coset
 // walk: 11 data bits = 5 high x 6 low, 4 parity bits through a 16-entry key table.  Returns the codeword.
 template <int V>
-__device__ __forceinline__ unsigned hamming_soft(unsigned hard15, const unsigned char* rel, const SoftScratch& S,
-                                                 const DevTables* T, int lane, int* errs) {
+__device__ __forceinline__ unsigned hamming_soft_search(unsigned hard15, const unsigned char* rel, unsigned short* s_cp, unsigned* s_ka,
+                                                     unsigned short* s_qa, const DevTables* T, int lane) {
     constexpr int dpos[2][11] = {{2, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14}, {4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14}};
     constexpr int ppos[2][4] = {{0, 1, 3, 7}, {0, 1, 2, 3}};
-    int e_hard;
-    const unsigned hf = hamming_hard(hard15, V, T, &e_hard);
-    const unsigned xhf = hf ^ hard15;  // at most one position
-    const unsigned U = soft_cost_of(rel, xhf, 15, lane);
-    if (U == 0u || soft_least_outside(rel, xhf, 15, 3 - __popc(xhf), U, lane) >= U) {
-        *errs = e_hard;
-        return hf;
-    }
     unsigned dh = 0, hp = 0;
 #pragma unroll
     for (int i = 0; i < 11; ++i) {
@@ -192,27 +209,27 @@ __device__ __forceinline__ unsigned hamming_soft(unsigned hard15, const unsigned
         sP += (((unsigned)lane >> j) & 1u) * (unsigned)rel[ppos[V][j]];
     }
     const unsigned pl = (unsigned)__popc(lane);
-    unsigned* cp16 = reinterpret_cast<unsigned*>(S.cp);
+    unsigned* cp16 = reinterpret_cast<unsigned*>(s_cp);
     __syncwarp();
     if (lane < 16) {
         cp16[lane] = (sP << 16) | (pl << 11);
     }
-    S.ka[lane] = (sA << 16) | (pl << 11) | ((((unsigned)lane) << 6) ^ (dh & 0x7c0u));
-    S.qa[lane] = (unsigned short)(((unsigned)T->ham_par_hi[V][lane] ^ syn) << 2);
+    s_ka[lane] = (sA << 16) | (pl << 11) | ((((unsigned)lane) << 6) ^ (dh & 0x7c0u));
+    s_qa[lane] = (unsigned short)(((unsigned)T->ham_par_hi[V][lane] ^ syn) << 2);
     const unsigned kb0 = (sB << 16) | (pl << 11) | (((unsigned)lane) ^ (dh & 63u));
     const unsigned kb1 = ((sB + (unsigned)rel[dpos[V][5]]) << 16) | ((pl + 1u) << 11) | (((unsigned)lane + 32u) ^ (dh & 63u));
     const unsigned pb0 = (unsigned)T->ham_par_lo[V][lane] << 2;
     const unsigned pb1 = (unsigned)T->ham_par_lo[V][lane + 32] << 2;
     __syncwarp();
-    const unsigned char* cpb = reinterpret_cast<const unsigned char*>(S.cp);
+    const unsigned char* cpb = reinterpret_cast<const unsigned char*>(s_cp);
     // all-ones is a codeword of both layouts (every check row has even weight): complements as in golay_soft
     const unsigned total = soft_cost_of(rel, 0x7fffu, 15, lane);
     const unsigned kmax = (total << 16) | (15u << 11) | 0x7ffu;
     unsigned best = 0xffffffffu, worst = 0u;
 #pragma unroll 8
     for (int a = 0; a < 16; ++a) {
-        const unsigned q = S.qa[a];
-        const unsigned k = S.ka[a];
+        const unsigned q = s_qa[a];
+        const unsigned k = s_ka[a];
         const unsigned c0 = *reinterpret_cast<const unsigned*>(cpb + (q ^ pb0));
         const unsigned c1 = *reinterpret_cast<const unsigned*>(cpb + (q ^ pb1));
         const unsigned k0 = (c0 + kb0) + k, k1 = (c1 + kb1) + k;
@@ -221,19 +238,40 @@ __device__ __forceinline__ unsigned hamming_soft(unsigned hard15, const unsigned
     }
     best = __reduce_min_sync(FULL, min(best, kmax - worst));
     __syncwarp();
-    if ((best >> 16) < U) {
-        *errs = (int)((best >> 11) & 15u);
-        return (unsigned)T->ham_cw[V][best & 0x7ffu];
+    return best;
+}
+
+// returns the codeword | differing bits << 24
+template <int V>
+__device__ __noinline__ unsigned hamming_soft_packed(unsigned hard15, const unsigned char* rel, unsigned short* s_cp, unsigned* s_ka,
+                                                     unsigned short* s_qa, const DevTables* T, int lane) {
+    int e_hard;
+    const unsigned hf = hamming_hard(hard15, V, T, &e_hard);
+    const unsigned xhf = hf ^ hard15;  // at most one position
+    const unsigned U = soft_cost_of(rel, xhf, 15, lane);
+    if (U == 0u || soft_least_outside(rel, xhf, 15, 3 - __popc(xhf), U, lane) >= U) {
+        return hf | ((unsigned)e_hard << 24);
     }
-    *errs = e_hard;
-    return hf;
+    const unsigned best = hamming_soft_search<V>(hard15, rel, s_cp, s_ka, s_qa, T, lane);
+    if ((best >> 16) < U) {
+        return (unsigned)T->ham_cw[V][best & 0x7ffu] | (((best >> 11) & 15u) << 24);
+    }
+    return hf | ((unsigned)e_hard << 24);
+}
+
+template <int V>
+__device__ __forceinline__ unsigned hamming_soft(unsigned hard15, const unsigned char* rel, const SoftScratch& S,
+                                                 const DevTables* T, int lane, int* errs) {
+    const unsigned r = hamming_soft_packed<V>(hard15, rel, S.cp, S.ka, S.qa, T, lane);
+    *errs = (int)(r >> 24);
+    return r & 0xffffffu;
 }
 
 // Golay row, hard or soft; `w` holds the 23 received bits, returns the row with corrected data bits and
 // the received parity bits (both decoders echo the input parity, ecc.c:290-292,352-355).
 __device__ __forceinline__ unsigned golay_row(unsigned w, const unsigned char* rel, int soft, const SoftScratch& S,
-                                              const DevTables* T, int lane, int* errs) {
-    unsigned data = soft ? golay_soft(w, rel, S, T, lane, errs) : golay_hard(w, T, errs);
+                                              const DevTables* T, int lane, int* errs, bool outlined = true) {
+    unsigned data = soft ? golay_soft(w, rel, S, T, lane, errs, outlined) : golay_hard(w, T, errs);
     return (data << 11) | (w & 0x7ffu);
 }
 
@@ -312,7 +350,7 @@ __device__ __forceinline__ int fe_c0(int codec, int soft, unsigned row[8], unsig
         row[0] = (row[0] & ~(0x3ffffu << 1)) | ((d0 & 0x3ffffu) << 1);
     } else {
         // AMBE 3600: C0 = Golay on columns 1..23 + overall parity in column 0
-        unsigned g = golay_row((row[0] >> 1) & 0x7fffffu, ws_rel + 1, soft, S, T, lane, &c0);
+        unsigned g = golay_row((row[0] >> 1) & 0x7fffffu, ws_rel + 1, soft, S, T, lane, &c0, false);
         row[0] = (row[0] & 1u) | (g << 1);
         if (c0 == 0 && (__popc(row[0] & 0xffffffu) & 1)) {
             row[0] ^= 1u;
@@ -498,7 +536,7 @@ __device__ __forceinline__ int fe_data(int codec, int soft, bool convert, unsign
             dw[2] = pre[2];
         }
     } else {
-        row[1] = (row[1] & 0x800000u) | golay_row(row[1] & 0x7fffffu, ws_rel + 24, soft, S, T, lane, &prot);
+        row[1] = (row[1] & 0x800000u) | golay_row(row[1] & 0x7fffffu, ws_rel + 24, soft, S, T, lane, &prot, false);
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
             int o = 32 * w + lane;
