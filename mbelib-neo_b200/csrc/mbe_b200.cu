@@ -652,7 +652,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
                 fc.total = total;
             }
         }
-        MBE_STAGE_BARRIER(16);  // ECC front-end | parameter decode
+        // ECC front-end | parameter decode: soft-decision kernels re-join here, because their front-end runs a data-dependent
+        // number of coset walks per stream and the block would otherwise walk the parameter decode out of step (instruction
+        // fetch stalls; +6 to +13 % on soft input, profiles/experiments/r01z_soft_front_end_barrier.txt)
+        if (SOFT == 1 && MODE == MODE_FRAMES) {
+            __syncthreads();
+        } else {
+            MBE_STAGE_BARRIER(16);
+        }
         if (live) {
             if (status >= 0) {
                 if (!AMBE) {
