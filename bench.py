@@ -1,24 +1,30 @@
 #!/usr/bin/env python
 """bench.py - decoded 20 ms frames/s of the batched IMBE/AMBE decode+synthesis path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|4]
 
-One "step" = one pass of the hot path (frame bits -> ECC -> parameter decode -> synthesis -> int16 PCM) over
-one batch: BASELINE.json configs[1], AMBE+2 3600x2450, 65,536 streams x 50 synthetic random-bit frames per
-GPU.  Streams are independent, so N GPUs run N disjoint stream shards with no collective on the data path
-("scaling": "weak"); torch.distributed is used only for the barrier and the max-over-ranks of the timings.
+One "step" = one pass of the hot path (frame bits -> ECC -> parameter decode -> synthesis -> int16 PCM) over one batch.
+Default workload = BASELINE.json configs[2], the configuration the metric is quoted on: IMBE 7200x4400 hard-decision ECC +
+synthesis, 1,048,576 streams x 50 synthetic random-bit frames, the streams SHARDED over the N GPUs (1M / N per rank, "scaling":
+"strong"; /root/reference/src/imbe/imbe7200x4400.c:986-1001 is the per-frame call it replaces).  --config 1 / 3 / 4 select the
+other BASELINE configs (AMBE+2 65,536 streams per GPU; AMBE 3600x2400 tone / unvoiced-heavy frames, 262,144 streams; the
+mixed-codec soft-decision workload, 1M streams, a third per codec); --codec / --streams / --soft ... build a custom single-codec
+workload with --streams per GPU (used by the A/B tools).  Streams are independent, so N GPUs run N disjoint stream shards with no
+collective on the data path; torch.distributed is used only for the barrier and the max-over-ranks of the timings.
 
 Numbers in the JSON line:
   value        frames/s, whole job, inputs resident in HBM, timed with CUDA events on the launching stream.
-  e2e          frames/s through the host-pointer C-ABI call (mbe_b200_process_frames): pinned HOST frame
-               bits in, int16 PCM + results in HOST memory out, copies inside the timed region.
-  roofline     HBM view of the stream kernel: algorithmic bytes per launch / mean launch time.
-  roofline_fp32  the bound that actually applies (FP32 issue): algorithmic FLOP per launch / launch time
-               against the non-fused FP32 issue peak (148 SM x 128 lanes x SM clock).
-  cpu_baseline the reference's own CPU build (oracle/_ref, dev-release flags) on the box's host cores,
-               bounded sample of the same workload.
-`--impl reference` times only that CPU arm.  The CUDA library is mandatory for the default arm: there is no
-CPU fallback in the product, and nothing under oracle/ is on the measured GPU path.
+  e2e          frames/s through the host-pointer C-ABI call (mbe_b200_process_frames[_packed]): pinned HOST frame bits in,
+               int16 PCM + results in HOST memory out, copies inside the timed region; link_ceiling = the same bytes moved
+               by plain cudaMemcpyAsync on all ranks at once (what the box's host links allow), frac_of_link = e2e / that.
+  roofline     the bound that applies (FP32 issue; parity forbids FMA contraction): algorithmic FLOP per launch / launch time
+               against 148 SM x 128 lanes x sampled SM clock; traffic = ncu DRAM bytes per launch; issue_slots = ncu warp
+               instructions per frame x frames/s against 148 x 4 schedulers x SM clock (profiles/ncu_constants.json).
+  roofline_hbm the HBM view of the same launch (algorithmic bytes / launch time against the measured copy peak).
+  cpu_baseline the reference's own CPU build (oracle/_ref, dev-release flags) on the box's host cores, bounded sample of the
+               same workload, the SAME counter-based input bits.
+`--impl reference` times only that CPU arm.  The CUDA library is mandatory for the default arm: there is no CPU fallback in
+the product, and nothing under oracle/ is on the measured GPU path.
 """
 import argparse
 import json
@@ -35,19 +41,92 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 CODEC_NAMES = {0: "imbe7200x4400", 1: "imbe7100x4400", 2: "ambe3600x2400", 3: "ambe3600x2450"}
+CODEC_IDS = {v: k for k, v in CODEC_NAMES.items()}
 FRAME_BITS = {0: 184, 1: 168, 2: 96, 3: 96}
 # algorithmic FLOP per frame on iid random-bit frames (non-fused, mul = add = 1)
 FLOP_PER_FRAME = {0: 84e3, 1: 84e3, 2: 66e3, 3: 61e3}
 STATE_BYTES = 7828  # 3 x mbe_parms + 16 B RNG words per stream
-# DRAM traffic of the stream kernel per frame, measured: dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` capture (profiles/r01s_stream_kernel_ncu_details.txt: 172.4 MB + 367.4 MB for 16576 streams x 50
-# frames of AMBE+2 hard-decision input) divided by the frames of that launch.  Only quoted for that workload.
-NCU_DRAM_BYTES_PER_FRAME = {("ambe3600x2450", 0): (172.412928e6 + 367.429632e6) / (16576 * 50)}
-# executed warp-instructions per frame of the same capture (smsp__inst_executed.sum / frames): the kernel is bound by
-# instruction issue, so this x frames/s against 148 SM x 4 schedulers x SM clock is the utilisation that matters
-NCU_WARP_INSTR_PER_FRAME = {("ambe3600x2450", 0): 4565407027.0 / (16576 * 50)}
 RESULT_BYTES = 24
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+INPUT_SEED = 0x4400
+
+# BASELINE.json configs; a part = (codec, input kind).  Input kinds: "hard" iid random bits (counter-based, identical on the
+# CPU and the GPU arm), "tones" configs[3]-shaped frames, "softch" configs[4]-shaped soft-decision frames.
+CONFIGS = {
+    1: {"parts": [("ambe3600x2450", "hard")], "streams": 65536, "scaling": "weak",
+        "what": "configs[1] AMBE+2 3600x2450 hard-decision, 65,536 streams per GPU"},
+    2: {"parts": [("imbe7200x4400", "hard")], "streams": 1048576, "scaling": "strong",
+        "what": "configs[2] IMBE 7200x4400 hard-decision ECC + synthesis, 1,048,576 streams sharded over the GPUs"},
+    3: {"parts": [("ambe3600x2400", "tones")], "streams": 262144, "scaling": "strong",
+        "what": "configs[3] AMBE 3600x2400 tone / unvoiced-only / voice frames, 262,144 streams sharded over the GPUs"},
+    4: {"parts": [("imbe7200x4400", "softch"), ("imbe7100x4400", "softch"), ("ambe3600x2450", "softch")], "streams": 1048576,
+        "scaling": "strong",
+        "what": "configs[4] mixed-codec soft-decision (a third of the streams per codec), valid frames with 10% flipped bits, "
+                "1,048,576 streams sharded over the GPUs"},
+}
+
+
+def ncu_constants():
+    """Per (codec, input kind) constants measured with ncu on this kernel build: executed warp-instructions, FP32 thread
+    instructions and DRAM bytes per frame.  Written by tools/ncu_constants.py from the captures of tools/gpu_prof.sh."""
+    p = os.path.join(ROOT, "profiles", "ncu_constants.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def _splitmix64_np(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def counter_bits_numpy(codec, first_stream, n_streams, n_frames, seed=INPUT_SEED):
+    """iid Bernoulli(1/2) channel bits as a pure function of (seed, codec, GLOBAL stream id, frame, bit): bit j of word k of
+    splitmix64(seed ^ codec << 56 ^ stream << 24 ^ frame << 8 ^ k) is frame bit 64 k + j.  uint8 [streams][frames][bits]."""
+    fb = FRAME_BITS[codec]
+    nw = (fb + 63) // 64
+    with np.errstate(over="ignore"):
+        s = (np.arange(n_streams, dtype=np.uint64) + np.uint64(first_stream))[:, None, None]
+        f = np.arange(n_frames, dtype=np.uint64)[None, :, None]
+        k = np.arange(nw, dtype=np.uint64)[None, None, :]
+        key = np.uint64(seed) ^ (np.uint64(codec) << np.uint64(56)) ^ (s << np.uint64(24)) ^ (f << np.uint64(8)) ^ k
+        w = _splitmix64_np(key)
+    bits = ((w[..., None] >> np.arange(64, dtype=np.uint64)) & np.uint64(1)).astype(np.uint8)
+    return np.ascontiguousarray(bits.reshape(n_streams, n_frames, nw * 64)[:, :, :fb])
+
+
+def counter_bits_torch(codec, first_stream, n_streams, n_frames, device, seed=INPUT_SEED, chunk=32768):
+    """The same bits generated on the device (int64 arithmetic wraps like uint64; right shifts are made logical)."""
+    import torch
+    fb = FRAME_BITS[codec]
+    nw = (fb + 63) // 64
+    out = torch.empty((n_streams, n_frames, fb), dtype=torch.uint8, device=device)
+
+    def i64(v):
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def lsr(x, n):
+        return (x >> n) & ((1 << (64 - n)) - 1)
+
+    f = torch.arange(n_frames, dtype=torch.int64, device=device)[None, :, None]
+    k = torch.arange(nw, dtype=torch.int64, device=device)[None, None, :]
+    sh = torch.arange(64, dtype=torch.int64, device=device)
+    for s0 in range(0, n_streams, chunk):
+        n = min(chunk, n_streams - s0)
+        s = (torch.arange(n, dtype=torch.int64, device=device) + (first_stream + s0))[:, None, None]
+        x = (s << 24) ^ (f << 8) ^ k ^ i64(seed ^ (codec << 56))
+        x = x + i64(0x9E3779B97F4A7C15)
+        x = (x ^ lsr(x, 30)) * i64(0xBF58476D1CE4E5B9)
+        x = (x ^ lsr(x, 27)) * i64(0x94D049BB133111EB)
+        x = x ^ lsr(x, 31)
+        b = ((x[..., None] >> sh) & 1).to(torch.uint8).reshape(n, n_frames, nw * 64)
+        out[s0:s0 + n] = b[:, :, :fb]
+    return out
 
 
 def measured_peaks():
@@ -186,15 +265,15 @@ def cpu_model():
 
 
 def channel_like_frames(codec, n_streams, n_frames, seed):
-    """BASELINE.json configs[4]-shaped soft input: valid encoded frames (random bits for IMBE 7100, whose encoder the
-    tests do not have), every channel bit flipped with p = 0.10, reliability 255 for unflipped and U[0,64) for flipped
+    """BASELINE.json configs[4]-shaped soft input: valid encoded frames, every channel bit flipped with p = 0.10, reliability 255 for unflipped and U[0,64) for flipped
     bits.  Returns uint8 [streams][frames][bits][2]."""
     import mbe_testlib as T
     rng = np.random.default_rng(seed)
-    if codec == 1:
+    enc7100 = getattr(T, "encode_imbe7100_frame", None)
+    if codec == 1 and enc7100 is None:
         hard = T.random_hard_frames(codec, n_streams, n_frames, 0x7100)
     else:
-        enc = T.encode_imbe7200_frame if codec == 0 else T.encode_ambe_frame
+        enc = T.encode_imbe7200_frame if codec == 0 else (enc7100 if codec == 1 else T.encode_ambe_frame)
         hard = np.zeros((n_streams, n_frames, FRAME_BITS[codec]), np.uint8)
         for b in range(n_streams):
             for f in range(n_frames):
@@ -222,56 +301,79 @@ def tone_unvoiced_frames(n_streams, n_frames, seed):
     return frames
 
 
-def run_cpu_reference(codec, n_frames, steps, warmup, streams_per_thread, soft=0, soft_channel=False, tones=False):
-    """Times the reference's CPU implementation (oracle/_ref dev-release build; the oracle port if the compiled
-    reference is missing) on all host cores.  Returns (frames/s, info dict, seconds per step)."""
+def part_frames_numpy(codec, kind, first_stream, n_streams, n_frames):
+    """Host copy of a part's input for global streams [first, first + n): the counter-based bits for "hard", 128 distinct
+    seeded streams tiled over the range otherwise (the same 128 on every rank and on both arms)."""
+    if kind == "hard":
+        return counter_bits_numpy(codec, first_stream, n_streams, n_frames)
+    B = 128
+    base = tone_unvoiced_frames(B, n_frames, 0x2400) if kind == "tones" else (
+        channel_like_frames(codec, B, n_frames, 0x50F7) if kind == "softch" else None)
+    if base is None:  # "soft": random bits with random reliabilities
+        rng = np.random.default_rng(0x2450)
+        bits = counter_bits_numpy(codec, first_stream, n_streams, n_frames)
+        return np.stack([bits, rng.integers(0, 256, size=bits.shape, dtype=np.uint8)], axis=-1)
+    idx = (np.arange(n_streams) + first_stream) % B
+    return np.ascontiguousarray(base[idx])
+
+
+def load_cpu_reference():
+    import mbe_testlib as T
+    if T.ref_available(fast=True):
+        return T.load_ref(fast=True).ref_bench_run, "reference", \
+            "oracle/_ref/libmberef_fast.so (unmodified reference, dev-release flags: SIMD + fast-math + LTO)"
+    if T.ref_available(fast=False):
+        return T.load_ref(fast=False).ref_bench_run, "reference", "oracle/_ref/libmberef.so (unmodified reference, Release flags)"
+    return T.load_oracle().mbo_run, "port", "oracle/libmbe_oracle.so (C restatement)"
+
+
+def run_cpu_reference(parts, n_frames, steps, warmup, streams_per_thread):
+    """Times the reference's CPU implementation (oracle/_ref dev-release build; the oracle port if the compiled reference is
+    missing) on all host cores, worker threads pinned 1:1 to cores, on a bounded sample of the workload: global streams
+    0 .. S-1 of every part with the same input bits the GPU arm decodes.  Returns (frames/s, info dict, seconds per step)."""
     import mbe_testlib as T
     cores = host_cores()
-    lib, kind, fn = None, "reference", None
-    if T.ref_available(fast=True):
-        lib = T.load_ref(fast=True)
-        fn = lib.ref_bench_run
-        flavour = "oracle/_ref/libmberef_fast.so (unmodified reference, dev-release flags: SIMD + fast-math + LTO)"
-    elif T.ref_available(fast=False):
-        lib = T.load_ref(fast=False)
-        fn = lib.ref_bench_run
-        flavour = "oracle/_ref/libmberef.so (unmodified reference, Release flags)"
-    else:
-        fn = T.load_oracle().mbo_run
-        kind = "port"
-        flavour = "oracle/libmbe_oracle.so (C restatement)"
-    if soft:
-        streams_per_thread = max(1, streams_per_thread // 50)  # the reference's soft ECC is ~1 ms per IMBE frame
-    S = min(cores * streams_per_thread, 65536)
-    if tones:
-        base = tone_unvoiced_frames(min(S, 128), n_frames, 0x2400)
-        frames = np.ascontiguousarray(np.tile(base, ((S + len(base) - 1) // len(base), 1, 1))[:S])
-    elif soft_channel:
-        base = channel_like_frames(codec, min(S, 128), n_frames, 0x50F7)
-        frames = np.ascontiguousarray(np.tile(base, ((S + len(base) - 1) // len(base), 1, 1, 1))[:S])
-    elif soft:
-        rng = np.random.default_rng(0x2450)
-        frames = np.stack([T.random_hard_frames(codec, S, n_frames, 0x2450),
-                           rng.integers(0, 256, size=(S, n_frames, FRAME_BITS[codec]), dtype=np.uint8)], axis=-1)
-    else:
-        frames = T.random_hard_frames(codec, S, n_frames, 0x2450)
-    seeds = T.stream_seeds(S)
-    pcm = np.zeros((S, n_frames, 160), np.int16)
-    res = np.zeros((S, n_frames, 6), np.int32)
-    times = []
-    for it in range(warmup + steps):
-        sec = fn(codec, int(bool(soft)), S, n_frames, T._ptr(frames), T._ptr(seeds), T._ptr(pcm), None, T._ptr(res), None, None, cores)
-        if it >= warmup:
-            times.append(sec)
-    sec = float(np.mean(times))
-    fps = S * n_frames / sec
+    fn, kind, flavour = load_cpu_reference()
+    total_frames, total_sec, notes = 0, 0.0, []
+    for codec, ikind in parts:
+        soft = ikind in ("soft", "softch")
+        spt = max(1, streams_per_thread // 50) if soft else streams_per_thread  # the reference's soft ECC is ~1 ms per IMBE frame
+        S = min(cores * spt, 65536)
+        frames = part_frames_numpy(codec, ikind, 0, S, n_frames)
+        seeds = T.stream_seeds(S)
+        pcm = np.zeros((S, n_frames, 160), np.int16)
+        res = np.zeros((S, n_frames, 6), np.int32)
+        times = []
+        for it in range(warmup + steps):
+            sec = fn(codec, int(soft), S, n_frames, T._ptr(frames), T._ptr(seeds), T._ptr(pcm), None, T._ptr(res), None, None, cores)
+            if it >= warmup:
+                times.append(sec)
+        total_sec += float(np.mean(times))
+        total_frames += S * n_frames
+        notes.append("%s %s: %d streams x %d frames (%d per thread)" % (CODEC_NAMES[codec], ikind, S, n_frames, spt))
+    fps = total_frames / total_sec
     info = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
-            "sample": "%d streams x %d frames per step (%d per thread), %s %s, one stream per task over %d pthreads, %s" % (
-                S, n_frames, streams_per_thread, CODEC_NAMES[codec],
-                "soft-decision (10% flipped bits)" if soft_channel else ("soft-decision" if soft else "hard-decision"), cores,
-                flavour),
+            "sample": "%s per step; one stream per task over %d pthreads pinned 1:1 to cores; %s; input = the GPU arm's bits "
+                      "for global streams 0.. of each part" % ("; ".join(notes), cores, flavour),
             "cpu_model": cpu_model(), "frames_per_s_per_core": fps / cores}
-    return fps, info, sec
+    return fps, info, total_sec
+
+
+def build_workload(args, world):
+    """-> dict(parts=[(codec id, input kind)], total streams (None: per-GPU count), per_gpu, scaling, what)."""
+    custom = args.codec is not None or args.soft or args.soft_channel or args.tones_unvoiced
+    if custom:
+        codec = "ambe3600x2400" if args.tones_unvoiced else (args.codec or "ambe3600x2450")
+        kind = "tones" if args.tones_unvoiced else ("softch" if args.soft_channel else ("soft" if args.soft else "hard"))
+        per_gpu = args.streams or 65536
+        return {"parts": [(CODEC_IDS[codec], kind)], "total": per_gpu * world, "scaling": "weak", "config": None,
+                "what": "custom: %s %s input, %d streams per GPU" % (codec, kind, per_gpu)}
+    c = CONFIGS[args.config]
+    parts = [(CODEC_IDS[n], k) for n, k in c["parts"]]
+    if c["scaling"] == "weak":
+        per_gpu = args.streams or c["streams"]
+        return {"parts": parts, "total": per_gpu * world, "scaling": "weak", "config": args.config, "what": c["what"]}
+    return {"parts": parts, "total": args.streams or c["streams"], "scaling": "strong", "config": args.config, "what": c["what"]}
 
 
 def main():
@@ -280,45 +382,57 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--codec", default="ambe3600x2450", choices=list(CODEC_NAMES.values()))
-    ap.add_argument("--streams", type=int, default=65536, help="streams per GPU")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4], help="BASELINE.json configs[N] (default 2: the headline)")
+    ap.add_argument("--codec", default=None, choices=list(CODEC_NAMES.values()), help="custom single-codec workload")
+    ap.add_argument("--streams", type=int, default=None,
+                    help="total streams (sharded configs 2-4) or streams per GPU (config 1 and custom workloads)")
     ap.add_argument("--frames", type=int, default=50, help="frames per stream per step")
-    ap.add_argument("--soft", action="store_true", help="soft-decision input (bit + reliability per channel bit), random reliabilities")
+    ap.add_argument("--soft", action="store_true", help="custom: soft-decision input (bit + reliability per channel bit), random reliabilities")
     ap.add_argument("--soft-channel", action="store_true",
-                    help="soft-decision input shaped like BASELINE.json configs[4]: valid encoded frames, every channel bit "
+                    help="custom: soft-decision input shaped like BASELINE.json configs[4]: valid encoded frames, every channel bit "
                          "flipped with p = 0.10, reliability 255 for unflipped and U[0,64) for flipped bits (128 distinct "
                          "streams tiled over the batch)")
     ap.add_argument("--tones-unvoiced", action="store_true",
-                    help="BASELINE.json configs[3]-shaped input (forces --codec ambe3600x2400): tone, unvoiced-only and voice "
+                    help="custom: BASELINE.json configs[3]-shaped input (forces --codec ambe3600x2400): tone, unvoiced-only and voice "
                          "frames from parameter bits, valid channel frames (128 distinct streams tiled over the batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
-    if args.tones_unvoiced:
-        args.codec = "ambe3600x2400"
-    codec = {v: k for k, v in CODEC_NAMES.items()}[args.codec]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    S, F = args.streams, args.frames
-    soft = 1 if (args.soft or args.soft_channel) else 0
-    workload = "%s %s-decision decode+synthesis, %d streams x %d synthetic %s frames per GPU" % (
-        CODEC_NAMES[codec], "soft" if soft else "hard", S, F,
-        "valid encoded, 10% flipped-bit" if args.soft_channel else ("tone / unvoiced-only / voice" if args.tones_unvoiced
-                                                                      else "random-bit"))
-    config = {"workload": workload, "codec": CODEC_NAMES[codec], "streams_per_gpu": S, "frames_per_stream": F,
-              "sharding": "streams/%d, no collective" % world,
-              "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (S * F * (FRAME_BITS[codec] + 344) / 1e6)}
+    F = args.frames
+    wl = build_workload(args, world)
+    parts = wl["parts"]
+    total_streams = wl["total"]
+
+    sys.path.insert(0, os.path.join(ROOT, "mbelib-neo_b200"))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mbe_b200_sharding", os.path.join(ROOT, "mbelib-neo_b200", "sharding.py"))
+    sharding = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sharding)
+    first_global, S = sharding.shard_range(total_streams, rank, world)     # this rank's block of global stream ids
+    # the rank's streams are cut into one contiguous range per part (configs[4]: a third per codec)
+    bounds = [S * i // len(parts) for i in range(len(parts) + 1)]
+    bytes_in_per_frame = [FRAME_BITS[c] * (2 if k in ("soft", "softch") else 1) for c, k in parts]
+    io_mb = sum((bounds[i + 1] - bounds[i]) * F * (bytes_in_per_frame[i] + 344) for i in range(len(parts))) / 1e6
+    config = {"workload": wl["what"] + ", %d synthetic frames per stream per step" % F,
+              "baseline_config": ("configs[%d]" % wl["config"]) if wl["config"] else None,
+              "parts": ["%s/%s" % (CODEC_NAMES[c], k) for c, k in parts],
+              "total_streams": total_streams, "streams_this_rank": S, "frames_per_stream": F,
+              "sharding": "contiguous global stream ids, %d per rank over %d rank(s), no collective" % (S, world),
+              "input": "counter-based splitmix64 bits keyed on (codec, global stream, frame): identical on every arm"
+                       if all(k == "hard" for _, k in parts) else "128 seeded distinct streams tiled over the batch",
+              "l2": "inputs+outputs per step on this rank (%.0f MB) exceed the 126 MB L2" % io_mb}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         warm = max(1, min(args.warmup, 3))
-        fps, info, sec = run_cpu_reference(codec, F, args.steps, warm, streams_per_thread=1000, soft=soft,
-                                           soft_channel=args.soft_channel, tones=args.tones_unvoiced)
+        fps, info, sec = run_cpu_reference(parts, F, args.steps, warm, streams_per_thread=1000)
         line = {"impl": "reference", "metric": "decoded frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "realtime_channels": fps / 50.0, "cpu_baseline": info,
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -337,49 +451,51 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    from importlib import import_module
-    sharding = import_module("mbelib_neo_b200.sharding")
-    first_global, _ = sharding.weak_shard(S, rank)      # this rank's block of global stream ids
-    dec = pkg.Decoder(max_streams=S, device=local_rank)
+    dec = pkg.Decoder(max_streams=max(S, 1), device=local_rank)
     dec.init_streams(0, S, sharding.stream_seeds(first_global, S))
 
-    fb = FRAME_BITS[codec]
+    # ---- inputs, one tensor per part: rot[p] is a list of frame sets the steps rotate through
     gen = torch.Generator(device=dev)
     gen.manual_seed(0x2450 + rank)
-    d_frames = torch.randint(0, 2, (S, F, fb), dtype=torch.uint8, device=dev, generator=gen)
-    if args.tones_unvoiced:
-        B = 128
-        base = torch.from_numpy(tone_unvoiced_frames(B, F, 0x2400 + rank)).to(dev)
-        d_frames = base.repeat((S + B - 1) // B, 1, 1)[:S].contiguous()
-    elif args.soft_channel:
-        B = 128
-        base = torch.from_numpy(channel_like_frames(codec, B, F, 0x50F7 + rank)).to(dev)
-        d_frames = base.repeat((S + B - 1) // B, 1, 1, 1)[:S].contiguous()
-    elif soft:  # mbe_soft_bit {bit, reliability} pairs
-        rel = torch.randint(0, 256, (S, F, fb), dtype=torch.uint8, device=dev, generator=gen)
-        d_frames = torch.stack((d_frames, rel), dim=-1).contiguous()
-    d_pcm = torch.empty((S, F, 160), dtype=torch.int16, device=dev)
-    d_res = torch.empty((S, F, 6), dtype=torch.int32, device=dev)
+    rot, outs = [], []
+    for p, (codec, kind) in enumerate(parts):
+        s0, n = bounds[p], bounds[p + 1] - bounds[p]
+        fb = FRAME_BITS[codec]
+        if kind == "hard":
+            x = counter_bits_torch(codec, first_global + s0, n, F, dev)
+        elif kind == "soft":
+            x = torch.stack((counter_bits_torch(codec, first_global + s0, n, F, dev),
+                             torch.randint(0, 256, (n, F, fb), dtype=torch.uint8, device=dev, generator=gen)), dim=-1).contiguous()
+        else:
+            B = 128
+            base = torch.from_numpy(part_frames_numpy(codec, kind, 0, B, F)).to(dev)
+            idx = (torch.arange(n, device=dev) + (first_global + s0)) % B
+            x = base[idx].contiguous()
+        sets = [x]
+        # Short launches (a real-time server decodes ONE 20 ms frame per stream per launch) must not see the same frames
+        # launch after launch: a stream fed the same frame twice has a perfectly stable pitch, which sends every low harmonic
+        # through the phase-interpolated (one cosf per sample) path and times a workload nobody has.  Rotate through enough
+        # different frame sets to cover 50 frames per stream.
+        if F < 50 and kind in ("hard", "soft"):
+            for k in range(1, min(50 // F, 25)):
+                y = torch.randint(0, 2, (n, F, fb), dtype=torch.uint8, device=dev, generator=gen)
+                if kind == "soft":
+                    y = torch.stack((y, torch.randint(0, 256, (n, F, fb), dtype=torch.uint8, device=dev, generator=gen)), dim=-1).contiguous()
+                sets.append(y)
+        rot.append(sets)
+        outs.append((torch.empty((n, F, 160), dtype=torch.int16, device=dev), torch.empty((n, F, 6), dtype=torch.int32, device=dev)))
     stream = torch.cuda.Stream(device=dev)
-
-    # Short launches (a real-time server decodes ONE 20 ms frame per stream per launch) must not see the same frames
-    # launch after launch: a stream fed the same frame twice has a perfectly stable pitch, which sends every low harmonic
-    # through the phase-interpolated (one cosf per sample) path and times a workload nobody has.  Rotate through enough
-    # different frame sets to cover 50 frames per stream.
-    rot_sets = [d_frames]
-    if F < 50 and not (args.soft_channel or args.tones_unvoiced):
-        for k in range(1, min(50 // F, 25)):
-            x = torch.randint(0, 2, (S, F, fb), dtype=torch.uint8, device=dev, generator=gen)
-            if soft:
-                x = torch.stack((x, torch.randint(0, 256, (S, F, fb), dtype=torch.uint8, device=dev, generator=gen)), dim=-1).contiguous()
-            rot_sets.append(x)
     step_no = [0]
 
     def step_dev():
-        fr = rot_sets[step_no[0] % len(rot_sets)]
+        for p, (codec, kind) in enumerate(parts):
+            n = bounds[p + 1] - bounds[p]
+            if n == 0:
+                continue
+            fr = rot[p][step_no[0] % len(rot[p])]
+            dec.process_frames_dev(codec, 1 if kind in ("soft", "softch") else 0, bounds[p], n, F, fr.data_ptr(),
+                                   outs[p][0].data_ptr(), 0, outs[p][1].data_ptr(), 0, stream.cuda_stream)
         step_no[0] += 1
-        dec.process_frames_dev(codec, soft, 0, S, F, fr.data_ptr(), d_pcm.data_ptr(), 0, d_res.data_ptr(), 0,
-                               stream.cuda_stream)
 
     def barrier():
         if world > 1:
@@ -407,124 +523,180 @@ def main():
         barrier()
     launches = dec.launches - l0
     total_ms = max_over_ranks(evs[0].elapsed_time(evs[-1]))
-    per_launch_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
-    kern_ms = float(np.mean(per_launch_ms))
-    value = world * S * F * args.steps / (total_ms * 1e-3)
+    per_step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    kern_ms = float(np.mean(per_step_ms))
+    value = total_streams * F * args.steps / (total_ms * 1e-3)
     clocks = clk.summary()
 
     # sanity: the PCM that came out is not silence and statuses are valid
-    chk = d_pcm[:64].abs().max().item()
-    st_min = int(d_res[:, :, 0].min().item())
-    if chk == 0 or st_min < 0:
-        raise SystemExit("bench.py: device path produced silence or error statuses (max |pcm| %d, min status %d)" % (chk, st_min))
+    for p in range(len(parts)):
+        if bounds[p + 1] - bounds[p] == 0:
+            continue
+        chk = outs[p][0][:64].abs().max().item()
+        st_min = int(outs[p][1][:, :, 0].min().item())
+        if chk == 0 or st_min < 0:
+            raise SystemExit("bench.py: device path produced silence or error statuses (part %d: max |pcm| %d, min status %d)" % (p, chk, st_min))
 
-    # ---- end-to-end arm: host frames in, host PCM + results out, through the host-pointer C-ABI call ----
+    # ---- end-to-end arm: host frames in, host PCM + results out, through the host-pointer C-ABI calls ----
     e2e = None
-    if not args.no_e2e:
-        h_sets = []
-        for x in rot_sets:       # (short launches rotate through different frame sets here too)
-            hx = torch.empty(tuple(x.shape), dtype=torch.uint8, pin_memory=True)
-            hx.copy_(x)
-            h_sets.append(hx)
-        h_frames = h_sets[0]
-        h_pcm = torch.empty((S, F, 160), dtype=torch.int16, pin_memory=True)
-        h_res = torch.empty((S, F, 6), dtype=torch.int32, pin_memory=True)
-        np_frames, np_pcm = h_frames.numpy(), h_pcm.numpy()
-        np_sets = [x.numpy() for x in h_sets]
-        np_res = h_res.numpy().view(pkg.RESULT_DTYPE).reshape(S, F)
-        lib, h = dec.lib, dec.h
+    if not args.no_e2e and S > 0:
         import ctypes
+        lib, h = dec.lib, dec.h
+        vp = ctypes.c_void_p
+        host = []   # per part: (list of pinned frame sets, packed frames or None, pcm, results)
+        h2d = d2h = h2d_packed = 0
+        all_hard = all(k == "hard" for _, k in parts) and all(len(r) == 1 for r in rot)
+        for p, (codec, kind) in enumerate(parts):
+            n = bounds[p + 1] - bounds[p]
+            sets = []
+            for x in rot[p]:
+                hx = torch.empty(tuple(x.shape), dtype=torch.uint8, pin_memory=True)
+                hx.copy_(x)
+                sets.append(hx.numpy())
+            packed = None
+            if all_hard:
+                packed = torch.from_numpy(pkg.pack_frames(codec, sets[0])).pin_memory().numpy()
+                h2d_packed += packed.size
+            h_pcm = torch.empty((n, F, 160), dtype=torch.int16, pin_memory=True).numpy()
+            h_res = torch.empty((n, F, 6), dtype=torch.int32, pin_memory=True).numpy()
+            host.append((sets, packed, h_pcm, h_res))
+            h2d += sets[0].size
+            d2h += n * F * (320 + RESULT_BYTES)
         host_step = [0]
 
-        def step_host():
-            cur_frames = np_sets[host_step[0] % len(np_sets)]
-            host_step[0] += 1
-            rc = lib.mbe_b200_process_frames(h, codec, soft, 0, S, F, cur_frames.ctypes.data_as(ctypes.c_void_p),
-                                             np_pcm.ctypes.data_as(ctypes.c_void_p), None,
-                                             np_res.ctypes.data_as(ctypes.c_void_p), None)
-            if rc != 0:
-                raise SystemExit("mbe_b200_process_frames failed: %s" % lib.mbe_b200_last_error(h).decode())
-
-        for _ in range(max(1, min(args.warmup, 3))):
-            step_host()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_host()          # returns when PCM + results are in host memory
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        e2e_s = max_over_ranks(t1 - t0)
-        barrier()
-        e2e = {"value": world * S * F * args.steps / e2e_s, "unit": "frames/s",
-               "h2d_bytes_per_step": int(S * F * fb * (2 if soft else 1)), "d2h_bytes_per_step": int(S * F * (320 + RESULT_BYTES)),
-               "ms_per_step": e2e_s * 1e3 / args.steps, "host_binding": numa_note,
-               "note": "mbe_b200_process_frames: pinned host bits in, int16 PCM + results to pinned host memory, "
-                       "wall clock around the blocking calls, max over ranks"}
-        if float(np.abs(np_pcm[:64]).max()) == 0:
-            raise SystemExit("bench.py: e2e path produced silence")
-        if not soft and len(rot_sets) == 1:
-            # the same call with bit-packed channel frames: 8x less host->device traffic
-            h_packed = torch.from_numpy(pkg.pack_frames(codec, np_frames)).pin_memory()
-            np_packed = h_packed.numpy()
-
-            def step_packed():
-                rc = lib.mbe_b200_process_frames_packed(h, codec, 0, S, F, np_packed.ctypes.data_as(ctypes.c_void_p),
-                                                        np_pcm.ctypes.data_as(ctypes.c_void_p), None,
-                                                        np_res.ctypes.data_as(ctypes.c_void_p), None)
+        def step_host(use_packed):
+            for p, (codec, kind) in enumerate(parts):
+                n = bounds[p + 1] - bounds[p]
+                if n == 0:
+                    continue
+                sets, packed, h_pcm, h_res = host[p]
+                if use_packed:
+                    rc = lib.mbe_b200_process_frames_packed(h, codec, bounds[p], n, F, packed.ctypes.data_as(vp), h_pcm.ctypes.data_as(vp),
+                                                            None, h_res.ctypes.data_as(vp), None)
+                else:
+                    cur = sets[host_step[0] % len(sets)]
+                    rc = lib.mbe_b200_process_frames(h, codec, 1 if kind in ("soft", "softch") else 0, bounds[p], n, F,
+                                                     cur.ctypes.data_as(vp), h_pcm.ctypes.data_as(vp), None, h_res.ctypes.data_as(vp), None)
                 if rc != 0:
-                    raise SystemExit("mbe_b200_process_frames_packed failed: %s" % lib.mbe_b200_last_error(h).decode())
+                    raise SystemExit("mbe_b200_process_frames failed: %s" % lib.mbe_b200_last_error(h).decode())
+            host_step[0] += 1
 
-            step_packed()
+        def time_host(use_packed):
+            for _ in range(max(1, min(args.warmup, 2))):
+                step_host(use_packed)
             barrier()
             t0 = time.perf_counter()
             for _ in range(args.steps):
-                step_packed()
+                step_host(use_packed)          # returns when PCM + results are in host memory
             torch.cuda.synchronize()
             t1 = time.perf_counter()
-            p_s = max_over_ranks(t1 - t0)
+            sec = max_over_ranks(t1 - t0)
             barrier()
-            e2e["packed_input"] = {"value": world * S * F * args.steps / p_s, "unit": "frames/s",
-                                   "h2d_bytes_per_step": int(np_packed.size),
-                                   "note": "mbe_b200_process_frames_packed: hard bits packed eight per byte"}
+            return sec
 
-    # ---- roofline of the stream kernel ----
+        sec_bytes = time_host(False)
+        if float(np.abs(host[0][2][:64]).max()) == 0:
+            raise SystemExit("bench.py: e2e path produced silence")
+        res_bytes = {"value": total_streams * F * args.steps / sec_bytes, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                     "ms_per_step": sec_bytes * 1e3 / args.steps,
+                     "note": "mbe_b200_process_frames: one byte per channel bit (the reference's char fr[][] layout)"}
+        res_packed = None
+        if all_hard:
+            sec_packed = time_host(True)
+            res_packed = {"value": total_streams * F * args.steps / sec_packed, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_packed),
+                          "ms_per_step": sec_packed * 1e3 / args.steps,
+                          "note": "mbe_b200_process_frames_packed: hard bits packed eight per byte (SURVEY 8(f)-1)"}
+        # what the host links allow: the step's bytes moved by plain copies on two streams, every rank at once
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def link_time(packed_in):
+            srcs = [torch.from_numpy(hp[1] if packed_in else hp[0][0]) for hp in host]
+            dsts = [torch.empty(x.shape, dtype=torch.uint8, device=dev) for x in srcs]
+            back = [(torch.from_numpy(hp[2]), torch.from_numpy(hp[3])) for hp in host]
+            best = None
+            for it in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                with torch.cuda.stream(s_in):
+                    for a, b in zip(srcs, dsts):
+                        b.copy_(a, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    for p in range(len(parts)):
+                        back[p][0].copy_(outs[p][0], non_blocking=True)
+                        back[p][1].copy_(outs[p][1], non_blocking=True)
+                torch.cuda.synchronize()
+                t = max_over_ranks(time.perf_counter() - t0)
+                best = t if best is None else min(best, t)
+            del dsts
+            return best
+
+        use_packed_headline = world > 1 and res_packed is not None
+        head = res_packed if use_packed_headline else res_bytes
+        t_link = link_time(use_packed_headline)
+        link_fps = total_streams * F / t_link
+        e2e = {"value": head["value"], "unit": "frames/s", "h2d_bytes_per_step": head["h2d_bytes_per_step"],
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": head["ms_per_step"],
+               "input": "bit-packed channel frames" if use_packed_headline else "one byte per channel bit",
+               "bytes_input": res_bytes, "packed_input": res_packed, "host_binding": numa_note,
+               "link_ceiling": {"value": link_fps, "unit": "frames/s", "ms_per_step": t_link * 1e3,
+                                "gbytes_per_s_this_rank": (head["h2d_bytes_per_step"] + d2h) / t_link / 1e9,
+                                "note": "the step's host<->device bytes as plain pinned copies (in and out on two streams), all ranks "
+                                        "at once, best of 3, max over ranks: no kernel, no pipeline"},
+               "frac_of_link": head["value"] / link_fps,
+               "frac_of_device": head["value"] / value,
+               "note": "pinned host frame bits in, int16 PCM + results to pinned host memory, wall clock around the blocking "
+                       "C-ABI calls, max over ranks; packed input is the headline at N > 1 (the host links are the limit there)"}
+
+    # ---- rooflines of the stream kernel ----
     hbm_peak, peak_src = measured_peaks()
-    alg_bytes = S * F * (fb * (2 if soft else 1) + 320 + RESULT_BYTES) + 2 * S * STATE_BYTES
-    hbm_ach = alg_bytes / (kern_ms * 1e-3) / 1e9
+    consts = ncu_constants()
+    alg_bytes = flops = dram = winstr = 0.0
+    have_all = True
+    per_part = []
+    for p, (codec, kind) in enumerate(parts):
+        n = bounds[p + 1] - bounds[p]
+        alg_bytes += n * F * (bytes_in_per_frame[p] + 320 + RESULT_BYTES) + 2 * n * STATE_BYTES
+        flops += n * F * FLOP_PER_FRAME[codec]
+        c = consts.get("%s/%s" % (CODEC_NAMES[codec], kind))
+        if c:
+            dram += n * F * c["dram_bytes_per_frame"]
+            winstr += n * F * c["warp_instr_per_frame"]
+            per_part.append({"part": "%s/%s" % (CODEC_NAMES[codec], kind), **c})
+        else:
+            have_all = False
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     fp32_issue_peak = 148 * 128 * sm_mhz * 1e6 / 1e12  # TFLOP/s, one non-fused op per lane per clock
-    flops = S * F * FLOP_PER_FRAME[codec]
     fp32_ach = flops / (kern_ms * 1e-3) / 1e12
-    per_frame_dram = NCU_DRAM_BYTES_PER_FRAME.get((CODEC_NAMES[codec], soft))
-    roofline = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                "traffic": (per_frame_dram * S * F) if per_frame_dram else None,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per frame (profiles/r01s_*) x frames per launch"
-                if per_frame_dram else None,
-                "peak_source": peak_src, "kernel": "mbe_stream_kernel",
-                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kern_ms,
-                "note": "the kernel is FP32-issue bound, not HBM bound (no dense contraction, ~1 KB/frame); see roofline_fp32"}
-    roofline_fp32 = {"bound": "fp32-issue", "achieved": fp32_ach, "peak": fp32_issue_peak, "unit": "TFLOP/s",
-                     "frac": fp32_ach / fp32_issue_peak, "flop_per_frame": FLOP_PER_FRAME[codec],
-                     "peak_source": "148 SM x 128 FP32 lanes x %.0f MHz sampled SM clock, non-fused (mul and add issue "
-                                    "separately because parity forbids FMA contraction); FMA-counted peak is 2x" % sm_mhz}
-
-    wipf = NCU_WARP_INSTR_PER_FRAME.get((CODEC_NAMES[codec], soft))
-    if wipf:
+    hbm_ach = alg_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "fp32-issue", "achieved": fp32_ach, "peak": fp32_issue_peak, "unit": "TFLOP/s",
+                "frac": fp32_ach / fp32_issue_peak, "traffic": dram if (have_all and dram) else None,
+                "kernel": "mbe_stream_kernel", "launch_ms": kern_ms, "algorithmic_flop_per_launch": flops,
+                "flop_per_frame": {CODEC_NAMES[c]: FLOP_PER_FRAME[c] for c, _ in parts},
+                "peak_source": "148 SM x 128 FP32 lanes x %.0f MHz sampled SM clock, non-fused (mul and add issue separately "
+                               "because parity forbids FMA contraction); the FMA-counted peak is 2x; the path has no dense "
+                               "contraction, so neither HBM nor the tensor cores bound it (see roofline_hbm)" % sm_mhz,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per frame x frames per launch "
+                                  "(profiles/ncu_constants.json)" if (have_all and dram) else None}
+    if have_all and winstr:
         issue_peak = 148 * 4 * sm_mhz * 1e6   # warp-instructions per second, one per scheduler per clock
-        issue_ach = wipf * S * F / (kern_ms * 1e-3)
-        roofline_fp32["issue_slots"] = {
-            "achieved": issue_ach / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instr/s", "frac": issue_ach / issue_peak,
-            "warp_instr_per_frame": wipf,
-            "source": "ncu smsp__inst_executed.sum per frame (profiles/r01s_*) x frames per launch / event-timed launch"}
+        issue_ach = winstr / (kern_ms * 1e-3)
+        roofline["issue_slots"] = {"achieved": issue_ach / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instr/s",
+                                   "frac": issue_ach / issue_peak, "warp_instr_per_frame": winstr / (S * F),
+                                   "source": "ncu smsp__inst_executed.sum per frame (profiles/ncu_constants.json) x frames per "
+                                             "launch / event-timed launch"}
+        roofline["ncu"] = per_part
+    roofline_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                    "traffic": dram if (have_all and dram) else None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "note": "bit-in / PCM-out / state traffic of the launch: ~1 KB per frame, HBM is ~99 % idle"}
     line = {"metric": "decoded frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "realtime_channels": value / 50.0, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "roofline_fp32": roofline_fp32}
+            "roofline": roofline, "roofline_hbm": roofline_hbm}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        _, info, _ = run_cpu_reference(codec, F, 2, 1, streams_per_thread=1000, soft=soft, soft_channel=args.soft_channel,
-                                       tones=args.tones_unvoiced)
+        _, info, _ = run_cpu_reference(parts, F, 2, 1, streams_per_thread=1000)
         line["cpu_baseline"] = info
     dec.close()
     if world > 1:

@@ -407,8 +407,8 @@ __device__ __forceinline__ void render_end(const Action& act, const RenderState&
 }
 
 __device__ __forceinline__ void load_block_tables(BlockTables* bt, const DevTables* T) {
-    for (int i = threadIdx.x; i < 324; i += blockDim.x) {
-        bt->voiced_win[i] = T->voiced_win[i];
+    for (int i = threadIdx.x; i < 2 * NS; i += blockDim.x) {
+        bt->voiced_win[i < NS ? i : i + (WIN_PREV - NS)] = T->voiced_win[i];
     }
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         bt->tw[i] = T->tw[i];
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
         load_stream(ws, gs, lane);
     }
     if (lane == 0) {
-        ws.w0row = ws.w0row_prev = -1;
+        ws.w0row = ws.w0row_prev = ws.w0row_enh = -1;
     }
 
     StageTimer tm;
@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
         publish_components(bs, f & 1, ws, go, warp, lane);
         __syncthreads();
         STAGE_T(3);
-        voiced_bank_block(wsa, bs, f & 1, bt, tm, warp, lane);
+        voiced_bank_block(wsa, bs, f & 1, bt, T, tm, warp, lane);
         STAGE_T(4);
 
         WolaTail tail;
@@ -773,6 +773,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
         }
         // RNG as after mbe_setThreadRngSeed(seed) (mbelib.c:173-181); no seeds: fresh-thread defaults
         if (lane == 0) {
+            ws.w0row = ws.w0row_prev = ws.w0row_enh = -1;
             c[HEAD_WORDS] = gc[SEED_WORD];
             if (A.synth_rng) {  // the caller's RNG words, carried from call to call (single-stream shim)
                 const uint32_t* r = A.synth_rng + 4 * (size_t)s;
@@ -803,7 +804,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
     publish_components(bs, 0, ws, go, warp, lane);
     __syncthreads();
     StageTimer tm;
-    voiced_bank_block(wsa, bs, 0, bt, tm, warp, lane);
+    voiced_bank_block(wsa, bs, 0, bt, T, tm, warp, lane);
     if (live) {
         if (go) {
             synth_finish_a(ws, gc, nullptr, T, bt, lane);
@@ -876,7 +877,7 @@ mbe_stage_kernel(int op, int n, const uint8_t* __restrict__ bits, uint32_t* cur,
     }
     if (lane == 0) {
         c[HEAD_WORDS] = gc[SEED_WORD];
-        ws.w0row = ws.w0row_prev = -1;
+        ws.w0row = ws.w0row_prev = ws.w0row_enh = -1;
     }
     if (op <= STAGE_PARMS_A2450) {
         for (int j = lane; j < PREV_WORDS; j += 32) {

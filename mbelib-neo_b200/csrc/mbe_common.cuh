@@ -12,6 +12,7 @@ namespace mbe {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NS = 160;     // samples per frame
 constexpr int NFFT = 256;   // unvoiced FFT length
+constexpr int WIN_PREV = 164;  // BlockTables::voiced_win: where the previous-frame half of the window starts
 constexpr int MAXL = 56;    // max harmonics
 
 // Device image of the reference's `struct mbe_parameters` (include/mbelib-neo/mbelib.h:88-137).
@@ -195,6 +196,9 @@ struct DevTables {
     unsigned short chan_src[4][184];
     float cosw_w0[COSW_ROWS];
     float cosw[COSW_ROWS][57];
+    // (sin, cos) of l * w0 as the kernel's sincosf port gives them (the oscillator step of harmonic l, mbelib.c:978-1011),
+    // generated on the device; same row key and same bitwise row check as cosw
+    float2 stepsc[COSW_ROWS][57];
 };
 
 // mode of the stream kernel
@@ -224,7 +228,11 @@ struct LaunchArgs {
 // Tables every warp of a block reads with lane-varying indices on the synthesis path, staged into
 // shared memory once per block (5.3 KB).
 struct __align__(16) BlockTables {
-    float voiced_win[324];   // 321-pt voiced window Ws (mbelib_const.h), 16-byte aligned rows for LDS.128
+    // 321-pt voiced window Ws (mbelib_const.h) as its two halves: a current-frame component is weighted by Ws[n], a
+    // previous-frame one by Ws[160 + n], n = 0..159.  The halves sit 164 floats apart: the lanes of a warp broadcast-load
+    // (LDS.128) from both at the same n, and 160 floats apart they would hit the same four banks (59 % of the kernel's
+    // excess shared-memory wavefronts in profiles/r01z_imbe_hard_kernel_ncu_details.txt)
+    float voiced_win[328];   // [0, 160): Ws[n];  [164, 324): Ws[160 + n]
     float tw[256];           // FFTPACK twiddles
     float uvwin[256];        // unvoiced analysis window, centred at 128
     float wola_wp[160], wola_wc[160], wola_den[160];
@@ -275,9 +283,10 @@ struct __align__(16) WarpWS {
     ParmsSmall cur;
     short w0row;                          // DevTables::cosw row of the fundamental this frame's decoder chose (unverified)
     short w0row_prev;                     // row that matched the previous enhanced frame
+    short w0row_enh;                      // candidate row of prev_mp_enhanced's fundamental (checked bitwise at use)
+    short pad0;
     PrevSmall prev;
     EnhSmall enh;
-    uint32_t pad_enh;
     int ncomp;                            // oscillator components of this frame (0: no voiced synthesis)
     unsigned k2mask;                      // list positions (< 32) of phase-interpolated harmonics
     unsigned short off[WARPS_PER_BLOCK + 3];  // this warp's copy of the block's slot offsets (prefix of padded counts)

@@ -286,7 +286,9 @@ __device__ __forceinline__ unsigned pn_bit(unsigned p0, int k, const DevTables* 
 }
 
 __device__ __forceinline__ unsigned getbit(const unsigned dw[3], int i) {
-    return (dw[i >> 5] >> (i & 31)) & 1u;
+    // (selects, not an indexed load: a run-time index would put the three words into local memory)
+    const unsigned w = (i < 32) ? dw[0] : (i < 64 ? dw[1] : dw[2]);
+    return (w >> (i & 31)) & 1u;
 }
 
 // ---- the channel front-end in its four steps: read | C0 | de-scramble | data ----------------------------------------

@@ -56,7 +56,10 @@ __device__ __forceinline__ void predict_magnitudes(WarpWS& ws, const DevTables* 
     __syncwarp();
     const float* P = prev.log2Ml;  // P[57] aliases PHIl[0], exactly as in the reference's struct
     const float ratio = (float)prev_L / (float)cur_L;
-    float2* pair = reinterpret_cast<float2*>(ws.u.dec.tmp);  // AMBE: (interpolated term, Tl) per harmonic; the DCT input is dead
+    // ordered sums over the harmonics: the terms of harmonic l sit at [l - 1], zero padded to a multiple of four harmonics
+    // (x + 0 = x), so the serial loops move four terms per LDS.128.  AMBE: (interpolated term, Tl) pairs; the DCT input is dead.
+    const int Lpad = (cur_L + 3) & ~3;
+    float2* pair = reinterpret_cast<float2*>(ws.u.dec.tmp);
     float dl[2], pa[2], pb[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -79,26 +82,44 @@ __device__ __forceinline__ void predict_magnitudes(WarpWS& ws, const DevTables* 
             pb[r] = P[up];
             const float term = (((float)1 - dl[r]) * pa[r]) + (dl[r] * pb[r]);
             if (ambe) {
-                pair[l] = make_float2(term, ws.u.dec.Tl[l]);
+                pair[l - 1] = make_float2(term, ws.u.dec.Tl[l]);
             } else {
-                ws.u.dec.tmp[l] = term;
+                ws.u.dec.tmp[l - 1] = term;
+            }
+        } else if (l <= Lpad) {
+            if (ambe) {
+                pair[l - 1] = make_float2(0.f, 0.f);
+            } else {
+                ws.u.dec.tmp[l - 1] = 0.f;
             }
         }
     }
     __syncwarp();
-    // the two ordered sums over the harmonics share one loop (and one 64-bit load per harmonic)
     float acc = 0.f, s42 = 0.f;
-    if (ambe) {
-#pragma unroll 4
-        for (int l = 1; l <= cur_L; ++l) {
-            const float2 v = pair[l];
-            acc = acc + v.x;
-            s42 += v.y;
-        }
-    } else {
-#pragma unroll 4
-        for (int l = 1; l <= cur_L; ++l) {
-            acc = acc + ws.u.dec.tmp[l];
+    {
+        const float4* p4 = reinterpret_cast<const float4*>(ws.u.dec.tmp);
+        if (ambe) {
+#pragma unroll 2
+            for (int i = 0; i < Lpad; i += 4) {
+                const float4 u = p4[i >> 1], v = p4[(i >> 1) + 1];
+                acc = acc + u.x;
+                s42 += u.y;
+                acc = acc + u.z;
+                s42 += u.w;
+                acc = acc + v.x;
+                s42 += v.y;
+                acc = acc + v.z;
+                s42 += v.w;
+            }
+        } else {
+#pragma unroll 2
+            for (int i = 0; i < Lpad; i += 4) {
+                const float4 u = p4[i >> 2];
+                acc = acc + u.x;
+                acc = acc + u.y;
+                acc = acc + u.z;
+                acc = acc + u.w;
+            }
         }
     }
     acc = ((rho / (float)cur_L) * acc);

@@ -122,6 +122,9 @@ __device__ __forceinline__ void enh_from_cur(WarpWS& ws, const StreamHome& h, in
     if (bulk) {  // (the synthesis stages write prev_mp_enhanced's previousUw / noiseOverlap themselves)
         bulk_copy(h.enh, h.cur, lane);
     }
+    if (lane == 0) {
+        ws.w0row_enh = ws.w0row_prev;  // candidate table row of the fundamental that just became prev_mp_enhanced's
+    }
     __syncwarp();
 }
 __device__ __forceinline__ void cur_from_prev(WarpWS& ws, const StreamHome& h, int lane) {
@@ -252,9 +255,15 @@ __global__ void mbe_costab_kernel(DevTables* T) {
     T->cosw_w0[r] = w0;
     T->cosw[r][0] = 1.0f;
     cos_recurrence(w0, 56, T->cosw[r]);
+    for (int l = 0; l <= 56; ++l) {
+        T->stepsc[r][l] = dev_sincosf(w0 * (float)l);  // the expression the bank evaluates for harmonic l's step
+    }
 }
 
-// scratch: 3 x 58 floats, 8-byte aligned (the workspace union: the decode scratch is dead, the synthesis has not begun)
+// scratch: 176 floats, 16-byte aligned (the workspace union: the decode scratch is dead, the synthesis has not begun).
+// The ordered sums (Rm0, Rm1, sum of M^2; mbelib.c:490-494) run over arrays padded with zeros to a multiple of four
+// harmonics (x + 0 = x), four terms per LDS.128.  On return scratch[0..] holds the enhanced magnitudes M_1..M_L, zero
+// padded the same way, for the amplitude sum of the adaptive smoothing.
 __device__ __forceinline__ float spectral_enhance(WarpWS& ws, const DevTables* T, float* scratch, int lane) {
     ParmsSmall& cur = ws.cur;
     const int L = cur.L;
@@ -265,6 +274,7 @@ __device__ __forceinline__ float spectral_enhance(WarpWS& ws, const DevTables* T
     if (MBE_ABL & 32) {
         return 1000.0f;
     }
+    const int Lpad = (L + 3) & ~3;
     // the cosines come from the table when this frame's (or, after a repeat, the previous frame's) row matches w0
     // bit for bit; otherwise (erasure model, imported state, first frame of a launch after a repeat) from the recurrence
     int row = ws.w0row;
@@ -273,7 +283,7 @@ __device__ __forceinline__ float spectral_enhance(WarpWS& ws, const DevTables* T
         row = ws.w0row_prev;
         hit = row >= 0 && row < COSW_ROWS && __float_as_uint(T->cosw_w0[row]) == __float_as_uint(w0);
     }
-    float2* pair = reinterpret_cast<float2*>(scratch);  // (M^2, M^2 cos) per harmonic
+    float2* pair = reinterpret_cast<float2*>(scratch);  // (M^2, M^2 cos) of harmonic l at [l - 1]
     float cosv[2] = {0.0f, 0.0f};
     __syncwarp();
     if (hit) {
@@ -303,7 +313,9 @@ __device__ __forceinline__ float spectral_enhance(WarpWS& ws, const DevTables* T
         if (l <= L) {
             const float m = cur.Ml[l];
             const float m2 = m * m;
-            pair[l] = make_float2(m2, m2 * cosv[r]);
+            pair[l - 1] = make_float2(m2, m2 * cosv[r]);
+        } else if (l <= Lpad) {
+            pair[l - 1] = make_float2(0.0f, 0.0f);
         }
     }
     if (lane == 0) {
@@ -312,15 +324,25 @@ __device__ __forceinline__ float spectral_enhance(WarpWS& ws, const DevTables* T
     __syncwarp();
     // serial: Rm0 = sum M^2, Rm1 = sum M^2 cos, in harmonic order
     float Rm0 = 0.0f, Rm1 = 0.0f;
-#pragma unroll 4
-    for (int l = 1; l <= L; ++l) {
-        const float2 v = pair[l];
-        Rm0 += v.x;
-        Rm1 += v.y;
+    {
+        const float4* p4 = reinterpret_cast<const float4*>(scratch);
+#pragma unroll 2
+        for (int i = 0; i < Lpad; i += 4) {
+            const float4 u = p4[i >> 1], v = p4[(i >> 1) + 1];
+            Rm0 += u.x;
+            Rm1 += u.y;
+            Rm0 += u.z;
+            Rm1 += u.w;
+            Rm0 += v.x;
+            Rm1 += v.y;
+            Rm0 += v.z;
+            Rm1 += v.w;
+        }
     }
     const float R2m0 = Rm0 * Rm0;
     const float R2m1 = Rm1 * Rm1;
     __syncwarp();
+    float Mv[2] = {0.0f, 0.0f};
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int l = 1 + lane + 32 * r;
@@ -339,29 +361,45 @@ __device__ __forceinline__ float spectral_enhance(WarpWS& ws, const DevTables* T
                 } else {
                     M = W * M;
                 }
-                cur.Ml[l] = M;
             }
-            scratch[l] = M * M;  // (the reference squares |M|: same product)
+            Mv[r] = M;
+            scratch[l - 1] = M * M;  // (the reference squares |M|: same product)
+        } else if (l <= Lpad) {
+            scratch[l - 1] = 0.0f;
         }
     }
     __syncwarp();
     float sum = 0.0f;
-#pragma unroll 4
-    for (int l = 1; l <= L; ++l) {
-        sum += scratch[l];
+    {
+        const float4* p4 = reinterpret_cast<const float4*>(scratch);
+#pragma unroll 2
+        for (int i = 0; i < Lpad; i += 4) {
+            const float4 u = p4[i >> 2];
+            sum += u.x;
+            sum += u.y;
+            sum += u.z;
+            sum += u.w;
+        }
     }
     const float g = (sum == 0.0f) ? 1.0f : sqrtf(Rm0 / sum);
     __syncwarp();
-    for (int l = 1 + lane; l <= L; l += 32) {
-        cur.Ml[l] = g * cur.Ml[l];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int l = 1 + lane + 32 * r;
+        if (l <= L) {
+            const float M = g * Mv[r];
+            cur.Ml[l] = M;
+            scratch[l - 1] = M;
+        }
     }
     __syncwarp();
     return Rm0;
 }
 
 // ---- adaptive smoothing, JMBE algorithms #111-116 (mbe_adaptive.c:151-276) -----------------------
+// ml_list (may be null): the magnitudes M_1..M_L as spectral_enhance left them, zero padded to a multiple of four
 __device__ __forceinline__ void adaptive_smoothing(ParmsSmall& cur, const EnhSmall& prev, int has_rm0, float rm0,
-                                                   int lane) {
+                                                   int lane, const float* ml_list = nullptr) {
     if (!bands_ok(cur.L) || !bands_ok(prev.L)) {
         return;
     }
@@ -412,9 +450,21 @@ __device__ __forceinline__ void adaptive_smoothing(ParmsSmall& cur, const EnhSma
         }
     }
     float Am = 0.0f;
+    if (ml_list) {
+        const float4* p4 = reinterpret_cast<const float4*>(ml_list);
+#pragma unroll 2
+        for (int i = 0; i < L; i += 4) {
+            const float4 u = p4[i >> 2];
+            Am += u.x;
+            Am += u.y;
+            Am += u.z;
+            Am += u.w;
+        }
+    } else {
 #pragma unroll 4
-    for (int l = 1; l <= L; ++l) {
-        Am += cur.Ml[l];
+        for (int l = 1; l <= L; ++l) {
+            Am += cur.Ml[l];
+        }
     }
     __syncwarp();
     if (lane == 0) {
@@ -1072,7 +1122,7 @@ __device__ __forceinline__ int tile_at(int n, int c) { return n * 32 + (c ^ ((n 
 // So oscillator work is spread evenly over the block no matter how the components are distributed
 // over streams, and a stream's additions keep the reference's order.
 __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, BlockShared* bs, int parity, const BlockTables* bt,
-                                                  StageTimer& tm, int warp, int lane) {
+                                                  const DevTables* T, StageTimer& tm, int warp, int lane) {
     constexpr int W = WARPS_PER_BLOCK;
     static_assert(W <= 16, "owner search and slot offsets are sized for at most 16 streams per block");
     WarpWS& me = wsa[warp];
@@ -1142,19 +1192,32 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, BlockShared* bs, 
                 k2lane = true;
             } else {
                 const int l = id >> 2;
-                float step, ph;
+                float step, ph, w0;
+                int row;
                 if ((id & 3) == 0) {
-                    step = o.enh.w0 * (float)l;
+                    w0 = o.enh.w0;
+                    row = o.w0row_enh;
+                    step = w0 * (float)l;
                     ph = o.enh.PHIl[l];
                     g = 2.0f * o.enh.Ml[l];
-                    Wb = bt->voiced_win + NS;
+                    Wb = bt->voiced_win + WIN_PREV;
                 } else {
-                    step = o.cur.w0 * (float)l;
+                    w0 = o.cur.w0;
+                    row = o.w0row_prev;   // (after the enhancement: the row that matched this frame's fundamental)
+                    step = w0 * (float)l;
                     ph = o.cur.PHIl[l] - (step * (float)NS);
                     g = 2.0f * o.cur.Ml[l];
                 }
-                const float2 d = (MBE_ABL & 4) ? make_float2(step, ph) : dev_sincosf(step);
+                // sincosf(l w0) from the device-generated table when the row's fundamental is this one bit for bit; the two
+                // loads do not depend on each other and are in flight while the phase's sincosf runs
+                const bool rowok = row >= 0 && row < COSW_ROWS;
+                const int rr = rowok ? row : 0;
+                const float tw0 = T->cosw_w0[rr];
+                float2 d = T->stepsc[rr][l];
                 const float2 p = (MBE_ABL & 4) ? make_float2(ph, step) : dev_sincosf(ph);
+                if (!(rowok && __float_as_uint(tw0) == __float_as_uint(w0))) {
+                    d = dev_sincosf(step);
+                }
                 sd = d.x;
                 cd = d.y;
                 s = p.x;
@@ -1292,7 +1355,7 @@ __device__ __noinline__ int synth_begin(WarpWS& ws, const float* cur_overlap, co
         return 0;  // silence
     }
     const float2 nz01 = noise_fetch(ws, cur_overlap, lane);
-    adaptive_smoothing(cur, prev, has_rm0, rm0, lane);
+    adaptive_smoothing(cur, prev, has_rm0, rm0, lane, has_rm0 ? reinterpret_cast<const float*>(&ws.u) : nullptr);
 
     const bool mute_on_rate = fabsf(cur.mutingThreshold - 0.096f) > 1e-6f;
     if (cur.repeatCount >= 4 || (mute_on_rate && cur.errorRate > cur.mutingThreshold)) {

@@ -13,6 +13,7 @@
  */
 #define _GNU_SOURCE
 #include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -189,9 +190,31 @@ ref_bench_run(int codec, int soft, int n_streams, int n_frames, const uint8_t* f
     if (n_threads == 1) {
         worker(&j);
     } else {
+        /* worker i is pinned to the i-th CPU of the caller's affinity mask, 1:1 while there are CPUs left
+           ("nproc worker threads pinned 1:1 to cores"); best effort, unpinned on failure */
+        cpu_set_t allowed;
+        int cpus[1024], n_cpus = 0;
+        if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+            for (int c = 0; c < CPU_SETSIZE && n_cpus < 1024; ++c) {
+                if (CPU_ISSET(c, &allowed)) {
+                    cpus[n_cpus++] = c;
+                }
+            }
+        }
         pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
         for (int i = 0; i < n_threads; ++i) {
-            pthread_create(&th[i], NULL, worker, &j);
+            pthread_attr_t at;
+            pthread_attr_init(&at);
+            if (n_cpus > 0 && n_threads <= n_cpus) {
+                cpu_set_t one;
+                CPU_ZERO(&one);
+                CPU_SET(cpus[i], &one);
+                pthread_attr_setaffinity_np(&at, sizeof(one), &one);
+            }
+            if (pthread_create(&th[i], &at, worker, &j) != 0) {
+                pthread_create(&th[i], NULL, worker, &j);
+            }
+            pthread_attr_destroy(&at);
         }
         for (int i = 0; i < n_threads; ++i) {
             pthread_join(th[i], NULL);

@@ -199,6 +199,67 @@ def encode_imbe7200_frame(bits88):
     return fr
 
 
+def imbe7100_to_7200_layout(d88):
+    """The K-dependent bit permutation between the IMBE 7100x4400 and 7200x4400 parameter layouts
+    (what mbe_convertImbe7100to7200 does, /root/reference/src/imbe/imbe7100x4400.c:380-437)."""
+    d = [int(x) for x in d88]
+    b0 = int("".join(str(d[i]) for i in (1, 2, 3, 4, 5, 6, 86, 87)), 2)
+    w0 = np.float32(np.float32(4 * np.pi) / np.float32(np.float32(b0) + 39.5))
+    L = int(0.9254 * int((np.pi / float(w0)) + 0.25))
+    K = int(np.float32(L + 2) / np.float32(3)) if L < 37 else 12
+    out = [0] * 88
+    out[87] = d[0]
+    out[48 + K] = d[42]
+    out[49 + K] = d[43]
+    for i in range(K):
+        out[48 + i] = d[44 + i]
+    j, k = 0, 1
+    while j < 87:
+        out[j] = d[k]
+        j += 1
+        if j == 48:
+            j += K + 2
+        k += 1
+        if k == 42:
+            k += K + 2
+    return np.array(out, np.uint8)
+
+
+def encode_imbe7100_frame(d88):
+    """88 data bits in the 7100x4400 LAYOUT (what mbe_eccImbe7100x4400Data emits, before the 7100 -> 7200 permutation)
+    -> valid char[7][24] ProVoice frame: shortened Golay on C0 (7 data bits, five zero-extended), Golay on C1..C3, the
+    7100 variant of Hamming(15,11) on C4 / C5, 23 raw bits, PN scrambling keyed by the 7 C0 data bits (the inverse of
+    /root/reference/src/imbe/imbe7100x4400.c:99-122,152-212,291-334)."""
+    b = [int(x) for x in d88]
+    word = lambda lo, n: int("".join(map(str, b[lo:lo + n])), 2)
+    fr = np.zeros((7, 24), np.uint8)
+    u0 = word(0, 7)
+    c0 = golay_encode(u0)                      # data bits 7..11 are zero, so code word bits 18..22 are zero
+    for j in range(18):
+        fr[0][j + 1] = (c0 >> j) & 1
+    pn = pn_sequence(u0, 100)
+    k = 0
+    cw = golay_encode(word(7, 12))
+    for j in range(23):
+        fr[1][j + 1] = (cw >> j) & 1
+    for j in range(23, -1, -1):                # the de-scrambler walks all 24 columns of row 1
+        fr[1][j] ^= pn[k]
+        k += 1
+    for i in (2, 3):
+        cw = golay_encode(word(19 + 12 * (i - 2), 12))
+        for j in range(22, -1, -1):
+            fr[i][j] = ((cw >> j) & 1) ^ pn[k]
+            k += 1
+    for i in (4, 5):
+        cw = hamming_encode_hi11(word(43 + 11 * (i - 4), 11), 1)
+        for j in range(14, -1, -1):
+            fr[i][j] = ((cw >> j) & 1) ^ pn[k]
+            k += 1
+    for idx, j in enumerate(range(22, -1, -1)):
+        fr[6][j] = b[65 + idx]
+    return fr
+
+
 def soften(frames_hard, rng, flip_p=0.0, rel_ok=255, rel_bad_max=64):
     """Hard frames -> soft frames with seeded bit flips: unflipped bits get reliability `rel_ok`,
     flipped bits a reliability drawn from U[0, rel_bad_max)."""

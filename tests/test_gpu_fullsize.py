@@ -91,21 +91,18 @@ def test_config4_ambe2400_tones_and_unvoiced_262144_streams():
 
 def test_config5_mixed_codec_soft_decision_10pct_errors():
     """BASELINE.json configs[4] at its per-GPU size (1M streams / 8 GPUs = 131,072, a third per codec): valid encoded
-    frames (random soft bits for IMBE 7100) with every channel bit flipped with p = 0.10, reliability 255 for
-    unflipped and U[0,64) for flipped bits, soft-decision ECC, 50 frames."""
+    frames for all three codecs (IMBE 7100 through tests/mbe_testlib.encode_imbe7100_frame) with every channel bit flipped
+    with p = 0.10, reliability 255 for unflipped and U[0,64) for flipped bits, soft-decision ECC, 50 frames."""
     rng = np.random.default_rng(0x50F7)
     F, B = 50, 32
     per_codec = 43680  # 1365 x 32
     for codec in (0, 1, 3):
-        if codec == 1:
-            hard = T.random_hard_frames(codec, B, F, 0x7100)
-        else:
-            enc = T.encode_imbe7200_frame if codec == 0 else T.encode_ambe_frame
-            hard = np.zeros((B, F, T.FRAME_BITS[codec]), np.uint8)
-            for s in range(B):
-                for f in range(F):
-                    p = rng.integers(0, 2, size=T.PARAM_BITS[codec], dtype=np.uint8)
-                    p[0] = 0
-                    hard[s, f] = enc(p).reshape(-1)
+        enc = {0: T.encode_imbe7200_frame, 1: T.encode_imbe7100_frame, 3: T.encode_ambe_frame}[codec]
+        hard = np.zeros((B, F, T.FRAME_BITS[codec]), np.uint8)
+        for s in range(B):
+            for f in range(F):
+                p = rng.integers(0, 2, size=T.PARAM_BITS[codec], dtype=np.uint8)
+                p[1 if codec == 1 else 0] = 0   # most significant bit of b0: a valid fundamental
+                hard[s, f] = enc(p).reshape(-1)
         soft = T.soften(hard, rng, flip_p=0.10)
         _run_fullsize(codec, per_codec, F, 0, base_frames=soft, soft=1)

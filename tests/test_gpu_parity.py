@@ -55,7 +55,23 @@ def check_batch(dec, codec, soft, frames, seeds, strict_state=True):
                     assert a[name] == b[name], (name, s, k)
                 assert np.array_equal(a["Vl"], b["Vl"])
     fexact = float((got["pcmf"].view(np.uint32) == want["pcmf"].view(np.uint32)).mean())
-    return dict(exact=exact, maxd=int(d.max()), float_exact=fexact, state_equal=state_equal)
+    out = dict(exact=exact, maxd=int(d.max()), float_exact=fexact, state_equal=state_equal)
+    # Second checker, one hop closer: the UNMODIFIED reference compiled by oracle/Makefile (Release flags, the parity
+    # build of SURVEY 8(c)), when oracle/_ref travelled with the tree.  Same bars as against the port.
+    if T.ref_available(fast=False):
+        ref = T.run_cpu(T.load_ref(fast=False).ref_bench_run, codec, soft, frames, seeds, n_threads=8)
+        assert np.array_equal(res["status"], ref["results"][..., 0]), "status differs from the compiled reference"
+        assert np.array_equal(got["bits"], ref["bits"]), "parameter bits differ from the compiled reference"
+        for name, col in (("c0_errors", 1), ("protected_errors", 2), ("c4_errors", 3), ("total_errors", 4)):
+            assert np.array_equal(res[name], ref["results"][..., col]), name + " differs from the compiled reference"
+        assert np.array_equal(res["flags"].astype(np.int64), ref["results"][..., 5].astype(np.int64) & 0xffffffff)
+        dr = np.abs(got["pcm"].astype(np.int32) - ref["pcm"].astype(np.int32))
+        assert dr.max() <= PCM_MAX_LSB, "max |delta| vs the compiled reference = %d LSB" % dr.max()
+        assert float((dr == 0).mean()) >= PCM_EXACT_FRACTION
+        out["ref_exact"] = float((dr == 0).mean())
+        out["ref_float_exact"] = float((got["pcmf"].view(np.uint32) == ref["pcmf"].view(np.uint32)).mean())
+        out["ref_state_equal"] = bool(np.array_equal(st, ref["state"]))
+    return out
 
 
 @pytest.mark.parametrize("codec", [0, 1, 2, 3])
@@ -75,17 +91,17 @@ def test_random_soft_frames(dec, codec):
     print(T.CODEC_NAMES[codec], r)
 
 
-@pytest.mark.parametrize("codec,ber", [(3, 0.0), (3, 0.03), (2, 0.0), (2, 0.02), (0, 0.0), (0, 0.03)])
+@pytest.mark.parametrize("codec,ber", [(3, 0.0), (3, 0.03), (2, 0.0), (2, 0.02), (0, 0.0), (0, 0.03), (1, 0.0), (1, 0.03)])
 def test_encoded_voice_frames(dec, codec, ber):
     rng = np.random.default_rng(300 + codec + int(ber * 1000))
     S, F = 64, 50
-    enc = T.encode_imbe7200_frame if codec == 0 else T.encode_ambe_frame
+    enc = {0: T.encode_imbe7200_frame, 1: T.encode_imbe7100_frame}.get(codec, T.encode_ambe_frame)
     frames = np.zeros((S, F, T.FRAME_BITS[codec]), np.uint8)
     for s in range(S):
         for f in range(F):
             p = rng.integers(0, 2, size=T.PARAM_BITS[codec], dtype=np.uint8)
-            if codec == 0:
-                p[0] = 0
+            if codec <= 1:
+                p[codec] = 0
             frames[s, f] = enc(p).reshape(-1)
     frames ^= (rng.random(frames.shape) < ber).astype(np.uint8)
     r = check_batch(dec, codec, 0, frames, T.stream_seeds(S, 5))
@@ -502,16 +518,13 @@ def test_long_streams_stay_exact(dec, codec):
     rng = np.random.default_rng(0x10C0 + codec)
     S, F, P = 48, 1200, 160
     fb = T.FRAME_BITS[codec]
-    if codec == 1:      # no encoder for the 7100x4400 interleave in the test library: random frames, held and bursty
-        pool = T.random_hard_frames(codec, 1, P, 0x7100)[0]
-    else:
-        enc = T.encode_imbe7200_frame if codec == 0 else T.encode_ambe_frame
-        pool = np.zeros((P, fb), np.uint8)
-        for i in range(P):
-            p = rng.integers(0, 2, size=T.PARAM_BITS[codec], dtype=np.uint8)
-            if codec == 0:
-                p[0] = 0
-            pool[i] = enc(p).reshape(-1)
+    enc = {0: T.encode_imbe7200_frame, 1: T.encode_imbe7100_frame}.get(codec, T.encode_ambe_frame)
+    pool = np.zeros((P, fb), np.uint8)
+    for i in range(P):
+        p = rng.integers(0, 2, size=T.PARAM_BITS[codec], dtype=np.uint8)
+        if codec <= 1:
+            p[codec] = 0        # most significant bit of b0 (bit 0 in the 7200 layout, bit 1 in the 7100 layout)
+        pool[i] = enc(p).reshape(-1)
     frames = np.zeros((S, F, fb), np.uint8)
     for s in range(S):
         f = 0

@@ -28,7 +28,7 @@ print("launch %.3f ms for %d streams x %d frames = %.4g frames/s; a warp slot (1
 names = ["frame-top barrier", "front-end+decode+state machine", "enhance+synth_begin", "count barrier", "voiced bank (incl. barriers)",
          "unvoiced+handover", "output stores", "state store", "  bank: osc setup", "  bank: phase A", "  bank: interp",
          "  bank: wait A", "  bank: phase B", "  bank: wait B", "-", "-"]
-tot = c[:8].sum()
+tot = c[:14].sum()   # (the bank's inner timers take over the running clock: its time is the sum of the sub-stages)
 for n, v in zip(names, c):
     print("%-34s %6.1f%%  %8.0f cycles/frame/warp" % (n, 100 * v / tot, v / (S * F)))
 print("total %.0f cycles/frame/warp" % (tot / (S * F)))
