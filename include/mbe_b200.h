@@ -20,7 +20,9 @@
  *   - per-frame status: `mbe_b200_result` = the reference's mbe_process_result (mbelib.h:180-191) plus
  *     the call's return value (`status`: >= 0 total corrected errors, MBE_STATUS_INVALID_ARGUMENT (-1),
  *     MBE_STATUS_INVALID_BITS (-2)).  A frame with negative status leaves the stream state untouched
- *     and produces silence.
+ *     and produces silence; its parameter-bit output (`bits`) reads all zero and, on the process_data
+ *     path, its result element is the caller's input with only `.status` replaced (the reference
+ *     returns before touching either; a batched output array has no "untouched" - check `.status`).
  *   - per-stream state lives on the device: the reference's caller-owned triplet cur_mp / prev_mp /
  *     prev_mp_enhanced (3 x 2604 bytes, `struct mbe_parameters` layout, mbelib.h:88-137) plus the
  *     reference's thread-local RNG state (comfort-noise LCG48 and unvoiced cold-start seed,

@@ -192,6 +192,14 @@ class Pool:
         blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(-1, 3, PARMS_BYTES)
         self._check(self.lib.mbe_b200_pool_import_state(self.h, first, blobs.shape[0], _p(blobs)), "pool_import_state")
 
+    def set_channel_map(self, codec, channel_map=None):
+        """mbe_b200_pool_set_channel_map: the same interleave schedule on every shard (None: identity)."""
+        if channel_map is None:
+            self._check(self.lib.mbe_b200_pool_set_channel_map(self.h, codec, None, 0), "pool_set_channel_map")
+        else:
+            m = np.ascontiguousarray(channel_map, dtype=np.uint16)
+            self._check(self.lib.mbe_b200_pool_set_channel_map(self.h, codec, _p(m), int(m.size)), "pool_set_channel_map")
+
     def process_frames(self, codec, frames, soft=False, first_stream=0, want_float=False, packed=False):
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         S, F = frames.shape[0], frames.shape[1]

@@ -16,6 +16,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "mbe_common.cuh"
 
 // ---- codec tables: device copy + host copy (host copy is only used to derive DevTables) ----------
@@ -1480,14 +1483,34 @@ static void build_tables(DevTables* t) {
     }
 }
 
-static size_t stream_kernel_smem(void) {
-    // MBE_B200_PAD_SMEM (bytes) is a profiling knob: it lowers occupancy without touching the code
-    static long pad = -1;
-    if (pad < 0) {
+// Tuning knobs from the environment, read ONCE (the pool calls the host-pointer entry points from one thread per shard):
+//   MBE_B200_PAD_SMEM  bytes of extra dynamic shared memory per block (profiling: lowers occupancy without touching code)
+//   MBE_B200_CHUNKS    target number of pipeline chunks of a host-pointer call
+//   MBE_B200_TAPER     smallest piece of the tapered ends, in blocks (0 = no taper)
+//   MBE_B200_KSTREAMS  compute streams the chunks rotate over
+struct Knobs {
+    long pad_smem;
+    int chunks, taper_blocks, kstreams;
+};
+static Knobs g_knobs;
+static std::once_flag g_knobs_once;
+static std::atomic<int> g_sm_count{148};   // SMs of the device of the most recently created context (B200: 148)
+static const Knobs& knobs() {
+    std::call_once(g_knobs_once, []() {
         const char* e = getenv("MBE_B200_PAD_SMEM");
-        pad = e ? atol(e) : 0;
-    }
-    return sizeof(BlockTables) + (size_t)WARPS_PER_BLOCK * sizeof(WarpWS) + sizeof(BlockShared) + (size_t)pad;
+        g_knobs.pad_smem = e ? atol(e) : 0;
+        e = getenv("MBE_B200_CHUNKS");
+        g_knobs.chunks = e ? atoi(e) : 0;
+        e = getenv("MBE_B200_TAPER");
+        g_knobs.taper_blocks = e ? atoi(e) : -1;
+        e = getenv("MBE_B200_KSTREAMS");
+        g_knobs.kstreams = e ? atoi(e) : 0;
+    });
+    return g_knobs;
+}
+
+static size_t stream_kernel_smem(void) {
+    return sizeof(BlockTables) + (size_t)WARPS_PER_BLOCK * sizeof(WarpWS) + sizeof(BlockShared) + (size_t)knobs().pad_smem;
 }
 
 typedef void (*StreamKernelFn)(const LaunchArgs);
@@ -1606,6 +1629,12 @@ int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams) {
         }                                                                          \
     } while (0)
     CUC(cudaSetDevice(device_ordinal));
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_ordinal) == cudaSuccess && sms > 0) {
+            g_sm_count.store(sms);   // chunk sizes of the host pipeline are whole waves of this many SMs
+        }
+    }
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     for (int i = 0; i < MAX_KSTREAMS; ++i) {
@@ -1710,6 +1739,22 @@ int mbe_b200_synchronize(mbe_b200_ctx* ctx) {
     return 0;
 }
 
+// one mbe_b200_submit_frames batch may be in flight per context; until mbe_b200_wait() every other call is refused,
+// because it would reuse the staging buffers or the stream state the in-flight kernels and copies still work on
+static int check_idle(mbe_b200_ctx* ctx, const char* what) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    if (ctx->pending) {
+        char msg[160];
+        snprintf(msg, sizeof(msg), "%s: a submission is still pending (call mbe_b200_wait first)", what);
+        return fail(ctx, MBE_B200_E_ARG, msg, cudaSuccess);
+    }
+    return 0;
+}
+
+static int ensure(mbe_b200_ctx* ctx, void** p, size_t* cap, size_t need);
+
 static int check_range(mbe_b200_ctx* ctx, int first, int count) {
     if (!ctx) {
         return MBE_B200_E_ARG;
@@ -1725,10 +1770,17 @@ int mbe_b200_init_streams(mbe_b200_ctx* ctx, int first, int count, const uint32_
     if (rc < 0 || count == 0) {
         return rc;
     }
+    if (check_idle(ctx, "init_streams") < 0) {
+        return MBE_B200_E_ARG;
+    }
     CU(cudaSetDevice(ctx->device));
+    // seeds are staged through the context's input buffer (no cudaMalloc / cudaFree pair, nothing to leak on an error path)
     uint32_t* d_seeds = nullptr;
     if (seeds) {
-        CU(cudaMalloc(&d_seeds, (size_t)count * sizeof(uint32_t)));
+        if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, (size_t)count * sizeof(uint32_t))) < 0) {
+            return rc;
+        }
+        d_seeds = (uint32_t*)ctx->d_in;
         CU(cudaMemcpyAsync(d_seeds, seeds, (size_t)count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
     const int threads = 256, wpb = threads / 32;
@@ -1738,9 +1790,6 @@ int mbe_b200_init_streams(mbe_b200_ctx* ctx, int first, int count, const uint32_
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
-    if (d_seeds) {
-        cudaFree(d_seeds);
-    }
     return 0;
 }
 
@@ -1752,21 +1801,29 @@ static int state_xfer(mbe_b200_ctx* ctx, int first, int count, void* host, int w
     if (!host) {
         return fail(ctx, MBE_B200_E_ARG, "NULL host buffer", cudaSuccess);
     }
+    if (check_idle(ctx, "export/import") < 0) {
+        return MBE_B200_E_ARG;
+    }
     CU(cudaSetDevice(ctx->device));
     const size_t bytes = (size_t)count * words * sizeof(uint32_t);
-    uint32_t* dense = nullptr;
-    CU(cudaMalloc(&dense, bytes));
+    // dense staging copy in the context's input buffer; grid sized from the words that actually move (the single-stream
+    // shim moves one stream's state four times per 20 ms frame)
+    if ((rc = ensure(ctx, &ctx->d_in, &ctx->d_in_cap, bytes)) < 0) {
+        return rc;
+    }
+    uint32_t* dense = (uint32_t*)ctx->d_in;
     if (!to_host) {
         CU(cudaMemcpyAsync(dense, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
-    mbe_state_xfer_kernel<<<1024, 256, 0, ctx->stream>>>(ctx->d_state, first, count, dense, words, offset, to_host);
+    const size_t n_words = (size_t)count * words;
+    const int blocks = (int)((n_words + 255) / 256 < 1024 ? (n_words + 255) / 256 : 1024);
+    mbe_state_xfer_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_state, first, count, dense, words, offset, to_host);
     ctx->launches++;
     CU(cudaGetLastError());
     if (to_host) {
         CU(cudaMemcpyAsync(host, dense, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(dense);
     return 0;
 }
 
@@ -1853,6 +1910,9 @@ int mbe_b200_set_channel_map(mbe_b200_ctx* ctx, int codec, const uint16_t* map, 
         }
     } else {
         n_bits = fb;
+    }
+    if (check_idle(ctx, "set_channel_map") < 0) {
+        return MBE_B200_E_ARG;
     }
     CU(cudaSetDevice(ctx->device));
     CU(cudaDeviceSynchronize());  // configuration call: no launch of this device may still be reading the old map
@@ -1995,18 +2055,13 @@ constexpr int PIPELINE_CHUNKS = 32;
 constexpr int PIPELINE_TAPER_BLOCKS = 18;
 static int pipeline_chunk_streams(int n_streams) {
     // granularity: one block per SM (half a wave): consecutive chunks run on different compute streams and share the SMs
-    const int wave = 148 * WARPS_PER_BLOCK;
+    const int wave = g_sm_count.load() * WARPS_PER_BLOCK;
     if (n_streams <= 4 * wave) {
         return n_streams;
     }
-    // MBE_B200_CHUNKS (environment): target number of pipeline chunks per call (tuning knob)
-    static int target = 0;
-    if (target == 0) {
-        const char* e = getenv("MBE_B200_CHUNKS");
-        target = e ? atoi(e) : 0;
-        if (target < 1 || target > MAX_CHUNKS) {
-            target = PIPELINE_CHUNKS;
-        }
+    int target = knobs().chunks;
+    if (target < 1 || target > MAX_CHUNKS) {
+        target = PIPELINE_CHUNKS;
     }
     int chunk = (n_streams + target - 1) / target;
     chunk = ((chunk + wave - 1) / wave) * wave;
@@ -2020,27 +2075,13 @@ static int pipeline_chunk_streams(int n_streams) {
 // blocks, 0 = none) the first and the last chunk's worth of streams are cut into pieces that double towards the body /
 // halve towards the end, so the copy-in in front of the first kernel and the copy-out behind the last one are small.
 static int pipeline_taper_blocks() {
-    static int t = -1;
-    if (t < 0) {
-        const char* e = getenv("MBE_B200_TAPER");
-        t = e ? atoi(e) : PIPELINE_TAPER_BLOCKS;
-        if (t < 0 || t > 148) {
-            t = PIPELINE_TAPER_BLOCKS;
-        }
-    }
-    return t;
+    const int t = knobs().taper_blocks;
+    return (t < 0 || t > 148) ? PIPELINE_TAPER_BLOCKS : t;
 }
 
 static int pipeline_kstreams() {
-    static int k = 0;
-    if (k == 0) {
-        const char* e = getenv("MBE_B200_KSTREAMS");
-        k = e ? atoi(e) : MAX_KSTREAMS;
-        if (k < 1 || k > MAX_KSTREAMS) {
-            k = MAX_KSTREAMS;
-        }
-    }
-    return k;
+    const int k = knobs().kstreams;
+    return (k < 1 || k > MAX_KSTREAMS) ? MAX_KSTREAMS : k;
 }
 
 static int pipeline_schedule(int n_streams, int chunk, int* sizes) {
@@ -2169,40 +2210,56 @@ static int frames_host_impl(mbe_b200_ctx* ctx, int codec, int kind, int first_st
     // already queued on the context's own stream; the call returns when the results are in host memory.
     void* host[4] = {pcm, pcmf, results, bits};
     const int chunk = pipeline_chunk_streams(n_streams);
-    CU(cudaEventRecord(ctx->ev_start, ctx->stream));
-    CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
-    for (int i = 0; i < MAX_KSTREAMS; ++i) {
-        CU(cudaStreamWaitEvent(ctx->s_k[i], ctx->ev_start, 0));
-    }
     int sizes[MAX_CHUNKS];
     const int n_chunks = pipeline_schedule(n_streams, chunk, sizes);
     const int n_k = pipeline_kstreams();
-    int s0 = 0;
-    for (int c = 0; c < n_chunks; s0 += sizes[c], ++c) {
-        const int ns = sizes[c];
-        const size_t f0 = (size_t)s0 * n_frames, fn = (size_t)ns * n_frames;
-        cudaStream_t sk = ctx->s_k[c % n_k];
-        CU(cudaMemcpyAsync((uint8_t*)ctx->d_in + f0 * in_per_frame, frames + f0 * in_per_frame, fn * in_per_frame,
-                           cudaMemcpyHostToDevice, ctx->s_in));
-        CU(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
-        CU(cudaStreamWaitEvent(sk, ctx->ev_in[c], 0));
-        int16_t* const o_pcm = pcm ? (int16_t*)ctx->d_out[0] + f0 * NS : nullptr;
-        float* const o_pcmf = pcmf ? (float*)ctx->d_out[1] + f0 * NS : nullptr;
-        mbe_b200_result* const o_res = results ? (mbe_b200_result*)ctx->d_out[2] + f0 : nullptr;
-        uint8_t* const o_bits = bits ? (uint8_t*)ctx->d_out[3] + f0 * pb : nullptr;
-        const uint8_t* const i_fr = (const uint8_t*)ctx->d_in + f0 * in_per_frame;
-        rc = frames_dev_impl(ctx, codec, kind, first_stream + s0, ns, n_frames, i_fr, o_pcm, o_pcmf, o_res, o_bits, sk);
-        if (rc < 0) {
-            return rc;
+    // a failure in the middle leaves copies into the caller's buffers queued: the pipeline streams are drained before the
+    // error is returned, so the caller may free its buffers right away
+    auto drain = [&]() {
+        cudaStreamSynchronize(ctx->s_in);
+        for (int i = 0; i < MAX_KSTREAMS; ++i) {
+            cudaStreamSynchronize(ctx->s_k[i]);
         }
-        CU(cudaEventRecord(ctx->ev_k[c], sk));
-        CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[c], 0));
-        for (int i = 0; i < 4; ++i) {
-            if (per_frame[i]) {
-                CU(cudaMemcpyAsync((uint8_t*)host[i] + f0 * per_frame[i], (uint8_t*)ctx->d_out[i] + f0 * per_frame[i],
-                                   fn * per_frame[i], cudaMemcpyDeviceToHost, ctx->s_out));
+        cudaStreamSynchronize(ctx->s_out);
+    };
+    auto enqueue = [&]() -> int {
+        CU(cudaEventRecord(ctx->ev_start, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
+        for (int i = 0; i < MAX_KSTREAMS; ++i) {
+            CU(cudaStreamWaitEvent(ctx->s_k[i], ctx->ev_start, 0));
+        }
+        int s0 = 0;
+        for (int c = 0; c < n_chunks; s0 += sizes[c], ++c) {
+            const int ns = sizes[c];
+            const size_t f0 = (size_t)s0 * n_frames, fn = (size_t)ns * n_frames;
+            cudaStream_t sk = ctx->s_k[c % n_k];
+            CU(cudaMemcpyAsync((uint8_t*)ctx->d_in + f0 * in_per_frame, frames + f0 * in_per_frame, fn * in_per_frame,
+                               cudaMemcpyHostToDevice, ctx->s_in));
+            CU(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+            CU(cudaStreamWaitEvent(sk, ctx->ev_in[c], 0));
+            int16_t* const o_pcm = pcm ? (int16_t*)ctx->d_out[0] + f0 * NS : nullptr;
+            float* const o_pcmf = pcmf ? (float*)ctx->d_out[1] + f0 * NS : nullptr;
+            mbe_b200_result* const o_res = results ? (mbe_b200_result*)ctx->d_out[2] + f0 : nullptr;
+            uint8_t* const o_bits = bits ? (uint8_t*)ctx->d_out[3] + f0 * pb : nullptr;
+            const uint8_t* const i_fr = (const uint8_t*)ctx->d_in + f0 * in_per_frame;
+            const int rk = frames_dev_impl(ctx, codec, kind, first_stream + s0, ns, n_frames, i_fr, o_pcm, o_pcmf, o_res, o_bits, sk);
+            if (rk < 0) {
+                return rk;
+            }
+            CU(cudaEventRecord(ctx->ev_k[c], sk));
+            CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[c], 0));
+            for (int i = 0; i < 4; ++i) {
+                if (per_frame[i]) {
+                    CU(cudaMemcpyAsync((uint8_t*)host[i] + f0 * per_frame[i], (uint8_t*)ctx->d_out[i] + f0 * per_frame[i],
+                                       fn * per_frame[i], cudaMemcpyDeviceToHost, ctx->s_out));
+                }
             }
         }
+        return 0;
+    };
+    if ((rc = enqueue()) < 0) {
+        drain();
+        return rc;
     }
     if (wait) {
         CU(cudaStreamSynchronize(ctx->s_out));
@@ -2225,6 +2282,9 @@ int mbe_b200_process_data(mbe_b200_ctx* ctx, int codec, int first_stream, int n_
     const size_t nf = (size_t)n_streams * n_frames;
     if (nf == 0) {
         return 0;
+    }
+    if (check_idle(ctx, "process_data") < 0) {
+        return MBE_B200_E_ARG;
     }
     CU(cudaSetDevice(ctx->device));
     int fb, pb;
@@ -2271,6 +2331,9 @@ int mbe_b200_decode_frames(mbe_b200_ctx* ctx, int codec, int soft, int n, const 
     }
     if (n == 0) {
         return 0;
+    }
+    if (check_idle(ctx, "decode_frames") < 0) {
+        return MBE_B200_E_ARG;
     }
     CU(cudaSetDevice(ctx->device));
     int fb, pb, rc;
@@ -2334,6 +2397,9 @@ int mbe_b200_ecc_blocks(mbe_b200_ctx* ctx, int code, int soft, int n, const uint
     if (n == 0) {
         return 0;
     }
+    if (check_idle(ctx, "ecc_blocks") < 0) {
+        return MBE_B200_E_ARG;
+    }
     CU(cudaSetDevice(ctx->device));
     const size_t len = code == 0 ? 23 : 15;
     const size_t ib = (size_t)n * len * (soft ? 2 : 1), ob = (size_t)n * len, sb = (size_t)n * sizeof(int32_t);
@@ -2366,6 +2432,9 @@ static int stage_impl(mbe_b200_ctx* ctx, const char* what, int op, int n, const 
     }
     if (n == 0) {
         return 0;
+    }
+    if (check_idle(ctx, "stage call") < 0) {
+        return MBE_B200_E_ARG;
     }
     CU(cudaSetDevice(ctx->device));
     const size_t pbytes = (size_t)n * sizeof(Parms);
@@ -2435,6 +2504,9 @@ int mbe_b200_synthesize_tone(mbe_b200_ctx* ctx, int n, const uint8_t* bits49, co
     if (n == 0) {
         return 0;
     }
+    if (check_idle(ctx, "synthesize_tone") < 0) {
+        return MBE_B200_E_ARG;
+    }
     CU(cudaSetDevice(ctx->device));
     const size_t pbytes = (size_t)n * sizeof(Parms), bbytes = (size_t)n * 49, ibytes = (size_t)n * 4, ob = (size_t)n * NS * 4;
     int rc;
@@ -2473,6 +2545,9 @@ int mbe_b200_comfort_noise(mbe_b200_ctx* ctx, int n, uint32_t* rng_words4, float
     if (n == 0) {
         return 0;
     }
+    if (check_idle(ctx, "comfort_noise") < 0) {
+        return MBE_B200_E_ARG;
+    }
     CU(cudaSetDevice(ctx->device));
     const size_t rb = (size_t)n * 16, ob = (size_t)n * NS * 4;
     int rc;
@@ -2503,6 +2578,9 @@ int mbe_b200_channel_step(mbe_b200_ctx* ctx, int codec, int step, int n, uint8_t
     }
     if (n == 0) {
         return 0;
+    }
+    if (check_idle(ctx, "channel_step") < 0) {
+        return MBE_B200_E_ARG;
     }
     CU(cudaSetDevice(ctx->device));
     const size_t fbytes = need_fr ? (size_t)n * fb : 0, dbytes = need_d ? (size_t)n * pb : 0;
@@ -2543,6 +2621,9 @@ static int synthesize_speech_impl(mbe_b200_ctx* ctx, int n, void* cur_parms, voi
     }
     if (n == 0) {
         return 0;
+    }
+    if (check_idle(ctx, "synthesize_speech") < 0) {
+        return MBE_B200_E_ARG;
     }
     CU(cudaSetDevice(ctx->device));
     const size_t pbytes = (size_t)n * sizeof(Parms);
@@ -2618,6 +2699,9 @@ int mbe_b200_floattoshort(mbe_b200_ctx* ctx, int n_frames, const float* in, int1
     }
     if (n_frames == 0) {
         return 0;
+    }
+    if (check_idle(ctx, "floattoshort") < 0) {
+        return MBE_B200_E_ARG;
     }
     CU(cudaSetDevice(ctx->device));
     const size_t n = (size_t)n_frames * NS;

@@ -41,12 +41,14 @@ int mbe_b200_pool_create(mbe_b200_pool** out, int n_devices, const int* device_o
     mbe_b200_pool* p = new mbe_b200_pool();
     p->max_streams = max_streams;
     p->err[0] = 0;
-    const int per = (max_streams + n_devices - 1) / n_devices;
+    // base + remainder, like sharding.shard_range: n_devices <= max_streams, so no shard is empty and every entry of
+    // p->ctx is a live context (9 streams on 8 GPUs: 2 1 1 1 1 1 1 1, not 2 2 2 2 1 0 0 0)
+    const int base = max_streams / n_devices, rem = max_streams % n_devices;
     for (int i = 0; i < n_devices; ++i) {
-        const int lo = std::min(i * per, max_streams), hi = std::min(lo + per, max_streams);
+        const int lo = i * base + std::min(i, rem), hi = lo + base + (i < rem ? 1 : 0);
         p->first.push_back(lo);
         mbe_b200_ctx* c = nullptr;
-        const int rc = (hi > lo) ? mbe_b200_create(&c, device_ordinals ? device_ordinals[i] : i, hi - lo) : 0;
+        const int rc = mbe_b200_create(&c, device_ordinals ? device_ordinals[i] : i, hi - lo);
         if (rc != 0) {
             snprintf(g_pool_err, sizeof(g_pool_err), "mbe_b200_pool_create: shard %d: %s", i, mbe_b200_last_error(nullptr));
             for (mbe_b200_ctx* q : p->ctx) {
@@ -179,6 +181,9 @@ int mbe_b200_pool_set_channel_map(mbe_b200_pool* p, int codec, const uint16_t* m
         return MBE_B200_E_ARG;
     }
     for (size_t i = 0; i < p->ctx.size(); ++i) {
+        if (!p->ctx[i]) {
+            continue;
+        }
         const int rc = mbe_b200_set_channel_map(p->ctx[i], codec, map, n_bits);
         if (rc != 0) {
             snprintf(p->err, sizeof(p->err), "pool_set_channel_map: shard %d: %s", (int)i, mbe_b200_last_error(p->ctx[i]));

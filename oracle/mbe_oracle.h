@@ -98,6 +98,7 @@ int mbo_golay2312(const char* in, char* out);
 int mbo_golay2312_soft(const mbo_soft_bit* in, char* out);
 int mbo_hamming1511(const char* in, char* out, int variant7100);
 int mbo_hamming1511_soft(const mbo_soft_bit* in, char* out, int variant7100);
+void mbo_ecc_blocks(int code, int soft, int fast, int n, const uint8_t* in, uint8_t* out, int32_t* status, int n_threads);
 
 /* frame bits -> parameter bits (mbe_decode<Codec>[Soft]Frame) */
 int mbo_decode_frame(int codec, int soft, const void* frame, char* bits, mbo_result* result);

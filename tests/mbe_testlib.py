@@ -260,6 +260,44 @@ def encode_imbe7100_frame(d88):
     return fr
 
 
+def ecc_test_words(code, n, seed):
+    """n soft-decision words for the block decoders (code 0 Golay(23,12), 1 / 2 Hamming(15,11) standard / 7100 layout):
+    valid code words with 0..6 flipped bits (beyond what the hard decoders correct), reliabilities from five families that
+    make cost ties and the "equals the hard decode" tie-break fire constantly: uniform 0..255, {0, 1, 2}, {k, k + 1},
+    two-level {low, 255} with the flipped bits low, and two-level with the flipped bits claiming to be reliable.
+    uint8 [n][len][2]."""
+    rng = np.random.default_rng(seed)
+    ln = 23 if code == 0 else 15
+    if code == 0:
+        cws = np.array([golay_encode(d) for d in range(4096)], np.uint32)
+    else:
+        cws = np.array([hamming_encode_hi11(d, code - 1) for d in range(2048)], np.uint32)
+    cw = cws[rng.integers(0, len(cws), size=n)]
+    bits = ((cw[:, None] >> np.arange(ln, dtype=np.uint32)) & 1).astype(np.uint8)
+    nflip = rng.integers(0, 7, size=n)
+    flip = (rng.random((n, ln)).argsort(axis=1).argsort(axis=1) < nflip[:, None])
+    bits ^= flip.astype(np.uint8)
+    fam = rng.integers(0, 5, size=n)
+    k = rng.integers(0, 255, size=(n, 1))
+    rel = np.where(fam[:, None] == 0, rng.integers(0, 256, size=(n, ln)),
+          np.where(fam[:, None] == 1, rng.integers(0, 3, size=(n, ln)),
+          np.where(fam[:, None] == 2, k + rng.integers(0, 2, size=(n, ln)),
+          np.where(fam[:, None] == 3, np.where(flip, rng.integers(0, 64, size=(n, ln)), 255),
+                   np.where(flip, 255, rng.integers(0, 64, size=(n, ln)))))))
+    return np.ascontiguousarray(np.stack([bits, rel.astype(np.uint8)], axis=-1))
+
+
+def oracle_ecc_blocks(code, words, soft, fast=True, n_threads=8):
+    """oracle/mbe_oracle.c mbo_ecc_blocks: (decoded [n][len], status [n])."""
+    o = load_oracle()
+    n, ln = words.shape[0], words.shape[1]
+    out = np.zeros((n, ln), np.uint8)
+    st = np.zeros(n, np.int32)
+    o.mbo_ecc_blocks(int(code), int(bool(soft)), int(bool(fast)), int(n), _ptr(np.ascontiguousarray(words)), _ptr(out), _ptr(st),
+                     int(n_threads))
+    return out, st
+
+
 def soften(frames_hard, rng, flip_p=0.0, rel_ok=255, rel_bad_max=64):
     """Hard frames -> soft frames with seeded bit flips: unflipped bits get reliability `rel_ok`,
     flipped bits a reliability drawn from U[0, rel_bad_max)."""

@@ -122,6 +122,26 @@ def test_random_words_equal_the_oracle(dec, code):
             assert rc == st_s[i] and np.array_equal(out_s[i], want.view(np.uint8)), i
 
 
+@pytest.mark.parametrize("code", [0, 1, 2])
+def test_soft_decoders_million_words_per_code(dec, code):
+    """The soft decoders were restructured (coset walk, complement rule, lower-bound skip: mbe_frontend.cuh), which is where
+    the reference's three-level tie-break (/root/reference/src/ecc/ecc.c:54-67,196-197) could silently break: 1,048,576 words
+    per code - valid code words with 0..6 flips, five reliability families built to force ties (T.ecc_test_words) - through
+    mbe_b200_ecc_blocks(soft=1) against the oracle's exhaustive search, every word; a 20,000-word subsample also against the
+    line-by-line restatement."""
+    n = 1 << 20
+    words = T.ecc_test_words(code, n, 0x50F7ECC + code)
+    got, st = dec.ecc_blocks(code, words, soft=True)
+    want, wst = T.oracle_ecc_blocks(code, words, soft=True, fast=True, n_threads=16)
+    bad = np.nonzero((st != wst) | (got != want).any(axis=1))[0]
+    assert bad.size == 0, "first mismatch at word %d: %r" % (bad[0], words[bad[0]].tolist())
+    sub = np.random.default_rng(code).choice(n, 20000, replace=False)
+    want2, wst2 = T.oracle_ecc_blocks(code, words[sub], soft=True, fast=False, n_threads=16)
+    assert np.array_equal(got[sub], want2) and np.array_equal(st[sub], wst2)
+    hard, hst = dec.ecc_blocks(code, np.ascontiguousarray(words[..., 0]))
+    print("code %d: %.1f %% of the soft decodes differ from the hard decode" % (code, 100.0 * (got != hard).any(axis=1).mean()))
+
+
 def test_invalid_bits_leave_the_output_alone(dec):
     words = np.zeros((3, 23), np.uint8)
     words[1, 7] = 2

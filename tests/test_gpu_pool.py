@@ -58,6 +58,37 @@ def test_pool_equals_single_context(pkg, n_shards, codec):
     pool.close()
 
 
+def test_more_shards_than_divide_the_streams_and_a_channel_map(pkg):
+    """9 streams over 8 shards: every shard owns at least one stream (2 1 1 1 1 1 1 1, base + remainder like
+    sharding.shard_range), and a channel map set on the pool reaches every shard (it used to fail half-way on the empty
+    trailing shards of a ceil() partition)."""
+    codec, S, F = 3, 9, 6
+    pool = pkg.Pool(S, devices=_devices(8))
+    sh = pool.shards()
+    assert [n for _, n in sh] == [2, 1, 1, 1, 1, 1, 1, 1] and [a for a, _ in sh] == [0, 2, 3, 4, 5, 6, 7, 8]
+    rng = np.random.default_rng(99)
+    pos = np.array(list(range(24)) + [24 + c for c in range(23)] + [48 + c for c in range(11)] + [72 + c for c in range(14)],
+                   np.uint16)
+    cmap = rng.permutation(pos)
+    frames = T.random_hard_frames(codec, S, F, 0x909)
+    mask = np.zeros(T.FRAME_BITS[codec], np.uint8)
+    mask[pos] = 1
+    frames &= mask
+    air = np.packbits(frames[..., cmap], axis=-1, bitorder="big")
+    seeds = T.stream_seeds(S, 17)
+    pool.init_streams(0, S, seeds)
+    want = pool.process_frames(codec, frames, want_float=True)
+    pool.set_channel_map(codec, cmap)
+    pool.init_streams(0, S, seeds)
+    got = pool.process_frames(codec, air, want_float=True, packed=True)
+    pool.set_channel_map(codec, None)
+    for k in ("pcm", "bits", "results"):
+        assert np.array_equal(got[k], want[k]), k
+    cpu = T.run_cpu(T.load_oracle().mbo_run, codec, 0, frames, seeds)
+    assert np.array_equal(want["pcm"], cpu["pcm"])
+    pool.close()
+
+
 def test_pool_range_errors(pkg):
     pool = pkg.Pool(16, devices=_devices(2))
     with pytest.raises(pkg.MbeB200Error):

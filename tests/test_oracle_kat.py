@@ -9,6 +9,7 @@ hold for this path, independent of oracle/_ref being pres
 import ctypes
 
 import numpy as np
+import pytest
 
 import mbe_testlib as T
 
@@ -230,3 +231,16 @@ def test_fft256_roundtrip_and_dc():
     ref = np.fft.rfft(x.astype(np.float64))
     assert abs(X[0] - ref[0].real) < 1e-3 and abs(X[1] - ref[128].real) < 1e-3
     assert np.allclose(X[2::2], ref[1:128].real, atol=2e-3) and np.allclose(X[3::2], ref[1:128].imag, atol=2e-3)
+
+
+@pytest.mark.parametrize("code", [0, 1, 2])
+def test_fast_exhaustive_soft_decoders_equal_the_restatement(code):
+    """oracle/mbe_oracle.c has two exhaustive soft decoders: the line-by-line restatement of src/ecc/ecc.c:157-215,303-357
+    (pinned to the compiled reference by test_oracle_vs_ref.py and to tests/test_ecc.c by the vectors above) and a table
+    driven one (same enumeration order, same tie-break function) that the million-word GPU differential uses.  They must
+    agree word for word, including on reliabilities that force cost ties."""
+    words = T.ecc_test_words(code, 6000, 0xECC0 + code)
+    a = T.oracle_ecc_blocks(code, words, soft=True, fast=False)
+    b = T.oracle_ecc_blocks(code, words, soft=True, fast=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert (a[1] > 0).mean() > 0.3      # the sample does exercise corrections
