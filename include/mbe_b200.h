@@ -78,6 +78,12 @@ MBE_B200_API int mbe_b200_geometry(int codec, int* frame_bits, int* param_bits);
 MBE_B200_API int mbe_b200_device_count(void); /* usable CUDA devices (0 when there is none or the driver is missing) */
 /* kernel launches issued by this context so far (bench.py reports it as gpu_launches) */
 MBE_B200_API long long mbe_b200_launch_count(const mbe_b200_ctx* ctx);
+/* Kernel path of the frame entry points (process_frames*, process_data*): 0 = one fused kernel per batch, 1 = a parameter
+ * kernel (ECC, decode, state machine, enhancement) that leaves a descriptor per frame + a synthesis kernel (oscillator
+ * bank, FFT / overlap-add, PCM) - DESIGN 4.5.  Results are bit-identical; the default comes from the build
+ * (MBE_B200_SPLIT in the environment overrides it).  kernel_path() returns the current setting. */
+MBE_B200_API int mbe_b200_set_kernel_path(mbe_b200_ctx* ctx, int path);
+MBE_B200_API int mbe_b200_kernel_path(const mbe_b200_ctx* ctx);
 
 /* ---- stream state ---------------------------------------------------------------------------
  * init_streams == per stream: mbe_setThreadRngSeed(seed) (mbelib.h:596; seeds==NULL: fresh-thread

@@ -39,7 +39,8 @@ _EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b
             "mbe_b200_adaptive_smoothing", "mbe_b200_synthesize_tone", "mbe_b200_comfort_noise", "mbe_b200_channel_step", "mbe_b200_set_channel_map", "mbe_b200_channel_frame_bytes", "mbe_b200_pool_set_channel_map",
             "mbe_b200_device_count", "mbe_b200_pool_create", "mbe_b200_pool_destroy", "mbe_b200_pool_last_error",
             "mbe_b200_pool_shards", "mbe_b200_pool_shard", "mbe_b200_pool_init_streams", "mbe_b200_pool_export_state",
-            "mbe_b200_pool_import_state", "mbe_b200_pool_process_frames", "mbe_b200_pool_process_frames_packed"]
+            "mbe_b200_pool_import_state", "mbe_b200_pool_process_frames", "mbe_b200_pool_process_frames_packed",
+            "mbe_b200_set_kernel_path", "mbe_b200_kernel_path"]
 
 _lib = None
 
@@ -78,6 +79,8 @@ def load_library():
         lib.mbe_b200_submit_frames.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp]
         lib.mbe_b200_wait.argtypes = [vp]
         lib.mbe_b200_set_normalized_float.argtypes = [vp, ci]
+        lib.mbe_b200_set_kernel_path.argtypes = [vp, ci]
+        lib.mbe_b200_kernel_path.argtypes = [vp]
         lib.mbe_b200_packed_frame_bytes.argtypes = [ci]
         lib.mbe_b200_pipeline_plan.argtypes = [ci, ctypes.POINTER(ci), ci]
         lib.mbe_b200_process_frames_packed_dev.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
@@ -311,6 +314,13 @@ class Decoder:
 
     def wait(self):
         self._check(self.lib.mbe_b200_wait(self.h), "wait")
+
+    def set_kernel_path(self, path):
+        """0: one fused kernel per batch; 1: parameter kernel + synthesis kernel (bit-identical results)."""
+        self._check(self.lib.mbe_b200_set_kernel_path(self.h, int(path)), "set_kernel_path")
+
+    def kernel_path(self):
+        return int(self.lib.mbe_b200_kernel_path(self.h))
 
     def set_normalized_float(self, enable):
         self._check(self.lib.mbe_b200_set_normalized_float(self.h, int(bool(enable))), "set_normalized_float")

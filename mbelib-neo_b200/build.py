@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmbe_b200.so")
 SOURCES = ["mbe_b200.cu", "mbe_pool.cpp"]
-DEPS = ["mbe_b200.cu", "mbe_pool.cpp", "mbe_common.cuh", "mbe_frontend.cuh", "mbe_parms.cuh", "mbe_synth.cuh", "mbe_libm.cuh",
+DEPS = ["mbe_b200.cu", "mbe_pool.cpp", "mbe_common.cuh", "mbe_frontend.cuh", "mbe_parms.cuh", "mbe_synth.cuh", "mbe_split.cuh", "mbe_libm.cuh",
         "mbe_tables.inc", "mbe_exp2_tab.inc", os.path.join("..", "..", "include", "mbe_b200.h")]
 
 NVCC_FLAGS = [

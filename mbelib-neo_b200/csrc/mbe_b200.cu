@@ -37,7 +37,11 @@ namespace hosttab {
 #include "mbe_frontend.cuh"
 #include "mbe_parms.cuh"
 #include "mbe_synth.cuh"
+#include "mbe_split.cuh"
 
+#ifndef MBE_SPLIT_DEFAULT
+#define MBE_SPLIT_DEFAULT 0
+#endif
 #ifndef MBE_TOP_BARRIER
 #define MBE_TOP_BARRIER 1
 #endif
@@ -95,7 +99,8 @@ __device__ __forceinline__ int resolve_total_errors(int c0, int prot, int c4, in
 }
 
 // ---- IMBE 4400 frame state machine (imbe7200x4400.c:780-888) --------------------------------------
-__device__ __forceinline__ Action process_imbe(FrameCtx& fc, const unsigned dw[3], WarpWS& ws, const StreamHome& home,
+template <class H>
+__device__ __forceinline__ Action process_imbe(FrameCtx& fc, const unsigned dw[3], WarpWS& ws, const H& home,
                                                const DevTables* T, int lane) {
     ParmsSmall& cur = ws.cur;
     PrevSmall& prev = ws.prev;
@@ -161,12 +166,14 @@ __device__ __forceinline__ Action process_imbe(FrameCtx& fc, const unsigned dw[3
 }
 
 // ---- AMBE helpers (ambe_common.c:191-271) ----------------------------------------------------------
-__device__ __forceinline__ void init_ambe(WarpWS& ws, const StreamHome& home, const DevTables* T, int lane) {
-    init_all(ws, home.cur, home.prev, home.enh, T->ambe_default_w0, 15, 0, 0.096f, lane);
+template <class H>
+__device__ __forceinline__ void init_ambe(WarpWS& ws, const H& home, const DevTables* T, int lane) {
+    init_all(ws, home, T->ambe_default_w0, 15, 0, 0.096f, lane);
 }
 
 // erasure model built in cur_mp from prev_mp: phases, noise generator and WOLA tail carried over
-__device__ __forceinline__ void set_erasure_model(WarpWS& ws, const StreamHome& home, int lane) {
+template <class H>
+__device__ __forceinline__ void set_erasure_model(WarpWS& ws, const H& home, int lane) {
     ParmsSmall& mp = ws.cur;
     const PrevSmall& src = ws.prev;
     __syncwarp();
@@ -178,7 +185,7 @@ __device__ __forceinline__ void set_erasure_model(WarpWS& ws, const StreamHome& 
         mp.PHIl[l] = (l == 0) ? src.PHIl0 : __uint_as_float(home.prev[174 + l]);
         mp.PSIl[l] = __uint_as_float(home.prev[231 + l]);
     }
-    bulk_copy(home.cur, home.prev, lane);
+    bulk_copy(ws, home, home.cur, home.prev, OP_CUR_FROM_PREV, lane);
     if (lane == 0) {
         mp.swn = 0;
         mp.tonePhase = 0;
@@ -193,7 +200,8 @@ __device__ __forceinline__ void set_erasure_model(WarpWS& ws, const StreamHome& 
     __syncwarp();
 }
 
-__device__ __forceinline__ void prepare_ambe(const FrameCtx& fc, WarpWS& ws, const StreamHome& home, const DevTables* T,
+template <class H>
+__device__ __forceinline__ void prepare_ambe(const FrameCtx& fc, WarpWS& ws, const H& home, const DevTables* T,
                                              int lane) {
     if (fabsf(ws.prev.mutingThreshold - 0.096f) > 1e-6f) {
         __syncwarp();
@@ -218,7 +226,8 @@ __device__ __forceinline__ int ambe_voice_or_mute(FrameCtx& fc, const WarpWS& ws
     return ACT_COMFORT_INIT;
 }
 
-__device__ __forceinline__ void ambe_repeat(WarpWS& ws, const StreamHome& home, FrameCtx& fc, int lane) {
+template <class H>
+__device__ __forceinline__ void ambe_repeat(WarpWS& ws, const H& home, FrameCtx& fc, int lane) {
     cur_from_prev(ws, home, lane);
     if (lane == 0) {
         ws.cur.repeatCount = ws.cur.repeatCount + 1;
@@ -228,8 +237,9 @@ __device__ __forceinline__ void ambe_repeat(WarpWS& ws, const StreamHome& home, 
 }
 
 // ---- AMBE+2 3600x2450 (ambe3600x2450.c:716-877) -----------------------------------------------------
+template <class H>
 __device__ __forceinline__ Action process_ambe2450(FrameCtx& fc, const unsigned dw[3], WarpWS& ws,
-                                                   const StreamHome& home, const DevTables* T, int lane) {
+                                                   const H& home, const DevTables* T, int lane) {
     Action act = {ACT_COMFORT_INIT, 0.0f, 0.0f, 0, 0};
     prepare_ambe(fc, ws, home, T, lane);
     const int bad = decode_ambe2450(dw, ws, T, fc.total, lane);
@@ -284,8 +294,9 @@ __device__ __forceinline__ Action process_ambe2450(FrameCtx& fc, const unsigned 
 }
 
 // ---- AMBE 3600x2400 (ambe3600x2400.c:629-762) --------------------------------------------------------
+template <class H>
 __device__ __forceinline__ Action process_ambe2400(FrameCtx& fc, const unsigned dw[3], WarpWS& ws,
-                                                   const StreamHome& home, const DevTables* T, int lane) {
+                                                   const H& home, const DevTables* T, int lane) {
     Action act = {ACT_COMFORT_INIT, 0.0f, 0.0f, 0, 0};
     prepare_ambe(fc, ws, home, T, lane);
     const int bad = decode_ambe2400(dw, ws, T, lane);
@@ -332,8 +343,8 @@ struct RenderState {
     float rm0;
 };
 
-template <bool AMBE>
-__device__ __forceinline__ RenderState render_begin1(const Action& act, WarpWS& ws, const StreamHome& home,
+template <bool AMBE, class H>
+__device__ __forceinline__ RenderState render_begin1(const Action& act, WarpWS& ws, const H& home,
                                                      const DevTables* T, int lane) {
     RenderState rs = {0, 0, 0.0f};
     int kind = act.kind;
@@ -355,7 +366,7 @@ __device__ __forceinline__ RenderState render_begin1(const Action& act, WarpWS& 
             if (lane == 0) {
                 home.spill[SEED_WORD] = cw[HEAD_WORDS];
             }
-            bulk_copy(home.spill, home.cur, lane);
+            bulk_copy(ws, home, home.spill, home.cur, OP_SPILL_FROM_CUR, lane);
             __syncwarp();
             cur_from_enh(ws, home, lane);
         }
@@ -380,18 +391,19 @@ __device__ __forceinline__ RenderState render_begin1(const Action& act, WarpWS& 
     return rs;
 }
 
-__device__ __forceinline__ int render_begin2(const RenderState& rs, WarpWS& ws, const StreamHome& home, const DevTables* T,
+template <class H>
+__device__ __forceinline__ int render_begin2(const RenderState& rs, WarpWS& ws, const H& home, const DevTables* T,
                                              int lane) {
     if (!rs.voice) {
         return 0;
     }
-    return synth_begin(ws, reinterpret_cast<const float*>(home.cur + OVERLAP_WORD), T, rs.has_rm0, rs.rm0, lane);
+    return synth_begin<true>(ws, reinterpret_cast<const float*>(home.cur + OVERLAP_WORD), T, rs.has_rm0, rs.rm0, lane);
 }
 
 // after the overlap-add: prev_mp_enhanced <- cur_mp, and the replay path puts the parked cur_mp back
-template <bool AMBE>
+template <bool AMBE, class H>
 __device__ __forceinline__ void render_end(const Action& act, const RenderState& rs, int go, WarpWS& ws,
-                                           const StreamHome& home, int lane) {
+                                           const H& home, int lane) {
     if (!rs.voice) {
         return;
     }
@@ -404,7 +416,7 @@ __device__ __forceinline__ void render_end(const Action& act, const RenderState&
         if (lane == 0) {
             cw[HEAD_WORDS] = home.spill[SEED_WORD];  // written by lane 0 above
         }
-        bulk_copy(home.cur, home.spill, lane);
+        bulk_copy(ws, home, home.cur, home.spill, OP_CUR_FROM_SPILL, lane);
         __syncwarp();
     }
 }
@@ -535,7 +547,9 @@ __device__ __forceinline__ void store_stream(const WarpWS& ws, uint32_t* gs, int
 // MODE in {MODE_FRAMES, MODE_DATA}
 // One block = WARPS_PER_BLOCK streams walking their frames in lockstep (see WARPS_PER_BLOCK).
 // =====================================================================================================
-template <int CODEC, int SOFT, int MODE>
+// SPLIT: the parameter kernel of the two-kernel path (mbe_split.cuh): no oscillator bank, no transforms; every frame
+// leaves a descriptor for mbe_split_synth_kernel, frames without speech synthesis are finished here.
+template <int CODEC, int SOFT, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_stream_kernel(const LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BlockTables* bt = reinterpret_cast<BlockTables*>(smem_raw);
@@ -560,12 +574,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
                                                : (PACKED ? (size_t)A.packed_bytes : (size_t)fbits * (SOFT == 1 ? 2u : 1u));
 
     uint32_t* gs = A.state + (size_t)(A.first_stream + (live ? s : 0)) * STATE_WORDS;
-    const StreamHome home = {gs, gs + PARMS_WORDS, gs + 2 * PARMS_WORDS, gs + SPILL_WORD};
+    const StreamHomeT<SPLIT> home = {gs, gs + PARMS_WORDS, gs + 2 * PARMS_WORDS, gs + SPILL_WORD};
     if (live) {
         load_stream(ws, gs, lane);
     }
     if (lane == 0) {
         ws.w0row = ws.w0row_prev = ws.w0row_enh = -1;
+        ws.ops = ws.nops = 0;
     }
 
     StageTimer tm;
@@ -584,7 +599,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
 #endif
         STAGE_T(0);
 
-        const size_t idx = (size_t)s * A.n_frames + f;
+        const size_t idx = (size_t)(A.io_base + s) * A.n_frames + f;   // element of the caller's [stream][frame] arrays
         unsigned dw[3] = {0u, 0u, 0u};
         FrameCtx fc;
         int status = -1, go = 0;
@@ -688,6 +703,38 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
             go = render_begin2(rs, ws, home, T, lane);
             STAGE_T(2);
         }
+        if (SPLIT) {
+            if (live) {
+                uint32_t* dsc = A.desc + ((size_t)s * A.n_frames + f) * DESC_WORDS;
+                float seed_before = 0.0f;
+                if (go) {
+                    float ov[3];
+                    make_noise_state(ws, reinterpret_cast<float*>(home.cur + OVERLAP_WORD),
+                                     reinterpret_cast<float*>(home.enh + OVERLAP_WORD), bt, lane, ov, &seed_before);
+                    record_op(ws, OP_SYNTH, lane);
+                    emit_desc_arrays(dsc, ws, ov, T, lane);
+                }
+                emit_desc_info(dsc, ws, go, seed_before, lane);
+                if (status >= 0) {
+                    render_end<AMBE>(act, rs, go, ws, home, lane);
+                    STAGE_T(5);
+                    status = fc.total;
+                    rout.c0_errors = fc.c0;
+                    rout.c4_errors = fc.c4;
+                    rout.total_errors = fc.total;
+                    rout.protected_errors = fc.total - fc.c0;
+                    rout.flags = fc.flags;
+                }
+                __syncwarp();
+                emit_desc_ops(dsc, ws, lane);
+                if (lane == 0) {
+                    ws.ops = ws.nops = 0;
+                }
+                if (!go) {
+                    store_pcm(A, ws, idx, lane);   // silence, tone or comfort noise: complete without the synthesis kernel
+                }
+            }
+        } else {
         publish_components(bs, f & 1, ws, go, warp, lane);
         __syncthreads();
         STAGE_T(3);
@@ -719,6 +766,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
             }
             __syncwarp();
             store_pcm(A, ws, idx, lane);
+        }
+        }
+        if (live) {
             if (A.results && lane == 0) {
                 rout.status = status;
                 A.results[idx] = rout;
@@ -1254,6 +1304,12 @@ struct mbe_b200_ctx {
     unsigned long long* d_dbg;  // 16 stage counters (MBE_STAGE_TIMING builds)
     float imbe_default_w0;
     int imbe_default_L;
+    // two-kernel path (mbe_split.cuh): descriptor buffers, one per pipeline compute stream + one shared by every other
+    // stream; a buffer is reused only after the synthesis kernel that read it has finished (ev_desc)
+    int split;
+    void* d_desc[MAX_KSTREAMS + 1];
+    size_t d_desc_cap[MAX_KSTREAMS + 1];
+    cudaEvent_t ev_desc[MAX_KSTREAMS + 1];
     char err[256];
 };
 
@@ -1491,6 +1547,8 @@ static void build_tables(DevTables* t) {
 struct Knobs {
     long pad_smem;
     int chunks, taper_blocks, kstreams;
+    int split;        // MBE_B200_SPLIT: default kernel path of new contexts (0 fused, 1 parameter + synthesis kernels)
+    long desc_mb;     // MBE_B200_DESC_MB: descriptor buffer budget per launch, MiB
 };
 static Knobs g_knobs;
 static std::once_flag g_knobs_once;
@@ -1505,6 +1563,13 @@ static const Knobs& knobs() {
         g_knobs.taper_blocks = e ? atoi(e) : -1;
         e = getenv("MBE_B200_KSTREAMS");
         g_knobs.kstreams = e ? atoi(e) : 0;
+        e = getenv("MBE_B200_SPLIT");
+        g_knobs.split = e ? atoi(e) : MBE_SPLIT_DEFAULT;
+        e = getenv("MBE_B200_DESC_MB");
+        g_knobs.desc_mb = e ? atol(e) : 2048;
+        if (g_knobs.desc_mb < 1) {
+            g_knobs.desc_mb = 1;
+        }
     });
     return g_knobs;
 }
@@ -1517,33 +1582,41 @@ typedef void (*StreamKernelFn)(const LaunchArgs);
 
 // one kernel image per (codec, soft) for channel frames; parameter-bit input (mbe_process<Codec>Data) has no
 // soft variant and IMBE 7100 shares the IMBE 4400 parameter layout
-static StreamKernelFn pick_stream_kernel(int codec, int soft, int mode) {
+template <bool SPLIT>
+static StreamKernelFn pick_stream_kernel_t(int codec, int soft, int mode) {
     if (mode == MODE_DATA) {
         switch (codec) {
-            case MBE_B200_AMBE3600X2400: return mbe_stream_kernel<MBE_B200_AMBE3600X2400, 0, MODE_DATA>;
-            case MBE_B200_AMBE3600X2450: return mbe_stream_kernel<MBE_B200_AMBE3600X2450, 0, MODE_DATA>;
-            default: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 0, MODE_DATA>;
+            case MBE_B200_AMBE3600X2400: return mbe_stream_kernel<MBE_B200_AMBE3600X2400, 0, MODE_DATA, SPLIT>;
+            case MBE_B200_AMBE3600X2450: return mbe_stream_kernel<MBE_B200_AMBE3600X2450, 0, MODE_DATA, SPLIT>;
+            default: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 0, MODE_DATA, SPLIT>;
         }
     }
     if (soft == 2) {  // packed hard bits
         switch (codec) {
-            case MBE_B200_IMBE7200X4400: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 2, MODE_FRAMES>;
-            case MBE_B200_IMBE7100X4400: return mbe_stream_kernel<MBE_B200_IMBE7100X4400, 2, MODE_FRAMES>;
-            case MBE_B200_AMBE3600X2400: return mbe_stream_kernel<MBE_B200_AMBE3600X2400, 2, MODE_FRAMES>;
-            default: return mbe_stream_kernel<MBE_B200_AMBE3600X2450, 2, MODE_FRAMES>;
+            case MBE_B200_IMBE7200X4400: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 2, MODE_FRAMES, SPLIT>;
+            case MBE_B200_IMBE7100X4400: return mbe_stream_kernel<MBE_B200_IMBE7100X4400, 2, MODE_FRAMES, SPLIT>;
+            case MBE_B200_AMBE3600X2400: return mbe_stream_kernel<MBE_B200_AMBE3600X2400, 2, MODE_FRAMES, SPLIT>;
+            default: return mbe_stream_kernel<MBE_B200_AMBE3600X2450, 2, MODE_FRAMES, SPLIT>;
         }
     }
     switch (codec * 2 + (soft ? 1 : 0)) {
-        case 0: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 0, MODE_FRAMES>;
-        case 1: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 1, MODE_FRAMES>;
-        case 2: return mbe_stream_kernel<MBE_B200_IMBE7100X4400, 0, MODE_FRAMES>;
-        case 3: return mbe_stream_kernel<MBE_B200_IMBE7100X4400, 1, MODE_FRAMES>;
-        case 4: return mbe_stream_kernel<MBE_B200_AMBE3600X2400, 0, MODE_FRAMES>;
-        case 5: return mbe_stream_kernel<MBE_B200_AMBE3600X2400, 1, MODE_FRAMES>;
-        case 6: return mbe_stream_kernel<MBE_B200_AMBE3600X2450, 0, MODE_FRAMES>;
-        default: return mbe_stream_kernel<MBE_B200_AMBE3600X2450, 1, MODE_FRAMES>;
+        case 0: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 0, MODE_FRAMES, SPLIT>;
+        case 1: return mbe_stream_kernel<MBE_B200_IMBE7200X4400, 1, MODE_FRAMES, SPLIT>;
+        case 2: return mbe_stream_kernel<MBE_B200_IMBE7100X4400, 0, MODE_FRAMES, SPLIT>;
+        case 3: return mbe_stream_kernel<MBE_B200_IMBE7100X4400, 1, MODE_FRAMES, SPLIT>;
+        case 4: return mbe_stream_kernel<MBE_B200_AMBE3600X2400, 0, MODE_FRAMES, SPLIT>;
+        case 5: return mbe_stream_kernel<MBE_B200_AMBE3600X2400, 1, MODE_FRAMES, SPLIT>;
+        case 6: return mbe_stream_kernel<MBE_B200_AMBE3600X2450, 0, MODE_FRAMES, SPLIT>;
+        default: return mbe_stream_kernel<MBE_B200_AMBE3600X2450, 1, MODE_FRAMES, SPLIT>;
     }
 }
+
+static StreamKernelFn pick_stream_kernel(int codec, int soft, int mode, bool split = false) {
+    return split ? pick_stream_kernel_t<true>(codec, soft, mode) : pick_stream_kernel_t<false>(codec, soft, mode);
+}
+
+static size_t bank_kernel_smem(void) { return 336 * sizeof(float) + (size_t)B_WARPS * sizeof(BankWS); }
+static size_t unvoiced_kernel_smem(void) { return sizeof(BlockTables) + (size_t)U_WARPS * sizeof(UnvWS); }
 
 typedef void (*DecodeKernelFn)(int, const uint8_t*, uint8_t*, mbe_b200_result*, const DevTables*);
 static DecodeKernelFn pick_decode_kernel(int codec, int soft) {
@@ -1657,12 +1730,21 @@ int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams) {
     for (int codec = 0; codec < 4; ++codec) {
         for (int soft = 0; soft < 3; ++soft) {
             for (int mode = 0; mode < (soft == 2 ? 1 : 2); ++mode) {
-                CUC(cudaFuncSetAttribute(pick_stream_kernel(codec, soft, mode), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)stream_kernel_smem()));
+                for (int split = 0; split < 2; ++split) {
+                    CUC(cudaFuncSetAttribute(pick_stream_kernel(codec, soft, mode, split != 0),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_kernel_smem()));
+                }
             }
         }
     }
     CUC(cudaFuncSetAttribute(mbe_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_kernel_smem()));
+    CUC(cudaFuncSetAttribute(mbe_split_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bank_kernel_smem()));
+    CUC(cudaFuncSetAttribute(mbe_split_unvoiced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)unvoiced_kernel_smem()));
+    for (int i = 0; i <= MAX_KSTREAMS; ++i) {
+        CUC(cudaEventCreateWithFlags(&ctx->ev_desc[i], cudaEventDisableTiming));
+    }
+    ctx->split = knobs().split ? 1 : 0;
     CUC(cudaFuncSetAttribute(mbe_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_kernel_smem()));
 #undef CUC
     free(ht);
@@ -1706,6 +1788,12 @@ void mbe_b200_destroy(mbe_b200_ctx* ctx) {
         if (ctx->ev_k[i]) {
             cudaEventDestroy(ctx->ev_k[i]);
         }
+    }
+    for (int i = 0; i <= MAX_KSTREAMS; ++i) {
+        if (ctx->ev_desc[i]) {
+            cudaEventDestroy(ctx->ev_desc[i]);
+        }
+        cudaFree(ctx->d_desc[i]);
     }
     cudaFree(ctx->d_state);
     cudaFree(ctx->d_dbg);
@@ -1844,16 +1932,89 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaS
     LaunchArgs a = a_in;
     a.pcmf_scale = ctx->normalized_float ? (7.0f / 32768.0f) : 1.0f;
     a.packed_bytes = (a.mode == MODE_FRAMES && a.soft == 2) ? (ctx->chan_bits[a.codec] + 7) / 8 : 0;
-    const int blocks = (a.n_streams + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     if (a.mode == MODE_SYNTH) {
+        const int blocks = (a.n_streams + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
         mbe_synth_kernel<<<blocks, WARPS_PER_BLOCK * 32, stream_kernel_smem(), st>>>(a);
-    } else {
-        pick_stream_kernel(a.codec, a.soft, a.mode)<<<blocks, WARPS_PER_BLOCK * 32, stream_kernel_smem(), st>>>(a);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        return 0;
     }
-    ctx->launches++;
-    CU(cudaGetLastError());
+    if (!ctx->split) {
+        const int blocks = (a.n_streams + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+        pick_stream_kernel(a.codec, a.soft, a.mode)<<<blocks, WARPS_PER_BLOCK * 32, stream_kernel_smem(), st>>>(a);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
+    // two-kernel path: parameter kernel -> descriptors -> synthesis kernel, in ranges of streams whose descriptors fit the
+    // buffer of this CUDA stream's slot
+    int slot = MAX_KSTREAMS;
+    for (int i = 0; i < MAX_KSTREAMS; ++i) {
+        if (st == ctx->s_k[i]) {
+            slot = i;
+        }
+    }
+    const size_t per_stream = (size_t)a.n_frames * DESC_WORDS * sizeof(uint32_t);
+    size_t cap_streams = ((size_t)knobs().desc_mb << 20) / per_stream;
+    const size_t gran = (size_t)g_sm_count.load() * WARPS_PER_BLOCK * MIN_BLOCKS_PER_SM;   // one wave of the parameter kernel
+    if (cap_streams >= gran) {
+        cap_streams -= cap_streams % gran;
+    } else if (cap_streams < (size_t)WARPS_PER_BLOCK) {
+        cap_streams = WARPS_PER_BLOCK;
+    }
+    const int sub = (int)(cap_streams < (size_t)a.n_streams ? cap_streams : (size_t)a.n_streams);
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_desc[slot], &ctx->d_desc_cap[slot], (size_t)sub * per_stream)) < 0) {
+        return rc;
+    }
+    CU(cudaStreamWaitEvent(st, ctx->ev_desc[slot], 0));   // the slot's previous user (possibly on another stream) is done
+    StreamKernelFn pk = pick_stream_kernel(a.codec, a.soft, a.mode, true);
+    const int n_total = a.n_streams, first0 = a.first_stream;
+    for (int o = 0; o < n_total; o += sub) {
+        const int ns = (n_total - o < sub) ? (n_total - o) : sub;
+        a.first_stream = first0 + o;
+        a.io_base = a_in.io_base + o;
+        a.n_streams = ns;
+        a.desc = (uint32_t*)ctx->d_desc[slot];
+        pk<<<(ns + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, stream_kernel_smem(), st>>>(a);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        SynthArgs sa;
+        sa.first_stream = a.first_stream;
+        sa.io_base = a.io_base;
+        sa.n_streams = ns;
+        sa.n_frames = a.n_frames;
+        sa.desc = a.desc;
+        sa.pcm = a.pcm;
+        sa.pcmf = a.pcmf;
+        sa.pcmf_scale = a.pcmf_scale;
+        sa.state = a.state;
+        sa.tab = a.tab;
+        const long long groups = ((long long)ns * a.n_frames + BG - 1) / BG;
+        mbe_split_bank_kernel<<<(unsigned)((groups + B_WARPS - 1) / B_WARPS), B_WARPS * 32, bank_kernel_smem(), st>>>(sa);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        mbe_split_unvoiced_kernel<<<(ns + U_WARPS - 1) / U_WARPS, U_WARPS * 32, unvoiced_kernel_smem(), st>>>(sa);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(ctx->ev_desc[slot], st));
     return 0;
 }
+
+int mbe_b200_set_kernel_path(mbe_b200_ctx* ctx, int path) {
+    if (!ctx || path < 0 || path > 1) {
+        return ctx ? fail(ctx, MBE_B200_E_ARG, "set_kernel_path: 0 (fused) or 1 (parameter + synthesis kernels)", cudaSuccess)
+                   : MBE_B200_E_ARG;
+    }
+    if (check_idle(ctx, "set_kernel_path") < 0) {
+        return MBE_B200_E_ARG;
+    }
+    ctx->split = path;
+    return 0;
+}
+
+int mbe_b200_kernel_path(const mbe_b200_ctx* ctx) { return ctx ? ctx->split : MBE_B200_E_ARG; }
 
 // input kinds of the frame entry points: 0 = one byte per hard bit, 1 = mbe_soft_bit pairs, 2 = hard bits packed
 static int frames_dev_impl(mbe_b200_ctx* ctx, int codec, int kind, int first_stream, int n_streams, int n_frames,

@@ -222,6 +222,8 @@ struct LaunchArgs {
     unsigned long long* dbg;    // MBE_STAGE_TIMING builds: 16 accumulated per-stage cycle counters
     int packed_bytes;           // bit-packed input: bytes per frame (transmitted bits of the channel map, rounded up)
     float pcmf_scale;           // float PCM is multiplied by this on store: 1 (reference scale) or 7/32768 (normalised)
+    uint32_t* desc;             // split path: frame descriptors [n_streams][n_frames][DESC_WORDS] (mbe_split.cuh)
+    int io_base;                // stream s of the launch is element io_base + s of the caller's frame / PCM / result arrays
 };
 
 
@@ -285,6 +287,8 @@ struct __align__(16) WarpWS {
     short w0row_prev;                     // row that matched the previous enhanced frame
     short w0row_enh;                      // candidate row of prev_mp_enhanced's fundamental (checked bitwise at use)
     short pad0;
+    // split path (mbe_split.cuh): the previousUw copies this frame's state machine asked for, 4 bits each, in order
+    unsigned ops, nops, pad1, pad2;
     PrevSmall prev;
     EnhSmall enh;
     int ncomp;                            // oscillator components of this frame (0: no voiced synthesis)

@@ -48,7 +48,7 @@ __device__ __forceinline__ bool bands_ok(int L) { return L >= 1 && L <= MAXL; }
 // previousUw[256] + noiseOverlap[96] of one struct image to another, both in HBM (11 independent loads per
 // lane in flight, then 11 stores)
 // (plain pointers: these words are written by this kernel too, so they must not go through the read-only path)
-__device__ __forceinline__ void bulk_copy(uint32_t* dst, const uint32_t* src, int lane) {
+__device__ __forceinline__ void bulk_copy_all(uint32_t* dst, const uint32_t* src, int lane) {
     if (MBE_ABL & 64) {
         return;
     }
@@ -71,10 +71,58 @@ __device__ __forceinline__ void bulk_copy(uint32_t* dst, const uint32_t* src, in
     }
 }
 
-__device__ __forceinline__ void bulk_zero(uint32_t* g, int lane) {
+// HBM homes of the stream's three structs (651-word mbe_parms images) + a scratch image.
+// SPLIT: the frame program runs as two kernels (mbe_split.cuh).  The parameter kernel then owns everything but the
+// previousUw arrays: its struct copies move only noiseOverlap and RECORD the copy as a 4-bit op code in the frame's
+// descriptor; the synthesis kernel, which owns previousUw, replays the ops in order.
+template <bool SPLIT_>
+struct StreamHomeT {
+    static constexpr bool SPLIT = SPLIT_;
+    uint32_t* cur;
+    uint32_t* prev;
+    uint32_t* enh;
+    uint32_t* spill;
+};
+using StreamHome = StreamHomeT<false>;
+
+enum { OP_CUR_FROM_PREV = 1, OP_PREV_FROM_CUR = 2, OP_ENH_FROM_CUR = 3, OP_CUR_FROM_ENH = 4, OP_ZERO_CUR = 5,
+       OP_SPILL_FROM_CUR = 6, OP_CUR_FROM_SPILL = 7, OP_SYNTH = 8 };
+
+__device__ __forceinline__ void record_op(WarpWS& ws, int op, int lane) {
+    if (lane == 0) {
+        const unsigned n = ws.nops;
+        ws.ops |= (n < 8u) ? ((unsigned)op << (4u * n)) : 0u;   // (a frame records at most seven)
+        ws.nops = n + 1u;
+    }
+}
+
+template <class H>
+__device__ __forceinline__ void bulk_copy(WarpWS& ws, const H&, uint32_t* dst, const uint32_t* src, int op, int lane) {
+    if (H::SPLIT) {
+        uint32_t v[3];
 #pragma unroll
-    for (int i = lane; i < 256; i += 32) {
-        g[UW_WORD + i] = 0u;
+        for (int k = 0; k < 3; ++k) {
+            v[k] = src[OVERLAP_WORD + 32 * k + lane];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            dst[OVERLAP_WORD + 32 * k + lane] = v[k];
+        }
+        record_op(ws, op, lane);
+    } else {
+        bulk_copy_all(dst, src, lane);
+    }
+}
+
+template <class H>
+__device__ __forceinline__ void bulk_zero(WarpWS& ws, const H&, uint32_t* g, int lane) {
+    if (!H::SPLIT) {
+#pragma unroll
+        for (int i = lane; i < 256; i += 32) {
+            g[UW_WORD + i] = 0u;
+        }
+    } else {
+        record_op(ws, OP_ZERO_CUR, lane);
     }
 #pragma unroll
     for (int i = lane; i < 96; i += 32) {
@@ -82,18 +130,11 @@ __device__ __forceinline__ void bulk_zero(uint32_t* g, int lane) {
     }
 }
 
-// HBM homes of the stream's three structs (651-word mbe_parms images) + a scratch image
-struct StreamHome {
-    uint32_t* cur;
-    uint32_t* prev;
-    uint32_t* enh;
-    uint32_t* spill;
-};
-
 __device__ __forceinline__ uint32_t* cur_words(WarpWS& ws) { return reinterpret_cast<uint32_t*>(&ws.cur); }
 __device__ __forceinline__ int cur_slot(int w) { return w < HEAD_WORDS ? w : HEAD_WORDS; }  // noiseSeed (554) -> 298
 
-__device__ __forceinline__ void prev_from_cur(WarpWS& ws, const StreamHome& h, int lane) {
+template <class H>
+__device__ __forceinline__ void prev_from_cur(WarpWS& ws, const H& h, int lane) {
     const uint32_t* c = cur_words(ws);
     uint32_t* p = reinterpret_cast<uint32_t*>(&ws.prev);
 #pragma unroll
@@ -105,10 +146,11 @@ __device__ __forceinline__ void prev_from_cur(WarpWS& ws, const StreamHome& h, i
         const int w = prev_home_word(j);
         h.prev[w] = c[w];
     }
-    bulk_copy(h.prev, h.cur, lane);
+    bulk_copy(ws, h, h.prev, h.cur, OP_PREV_FROM_CUR, lane);
     __syncwarp();
 }
-__device__ __forceinline__ void enh_from_cur(WarpWS& ws, const StreamHome& h, int lane, bool bulk = true) {
+template <class H>
+__device__ __forceinline__ void enh_from_cur(WarpWS& ws, const H& h, int lane, bool bulk = true) {
     const uint32_t* c = cur_words(ws);
     uint32_t* e = reinterpret_cast<uint32_t*>(&ws.enh);
 #pragma unroll
@@ -120,14 +162,15 @@ __device__ __forceinline__ void enh_from_cur(WarpWS& ws, const StreamHome& h, in
         h.enh[ENH_HOME_WORD0 + j] = c[ENH_HOME_WORD0 + j];
     }
     if (bulk) {  // (the synthesis stages write prev_mp_enhanced's previousUw / noiseOverlap themselves)
-        bulk_copy(h.enh, h.cur, lane);
+        bulk_copy(ws, h, h.enh, h.cur, OP_ENH_FROM_CUR, lane);
     }
     if (lane == 0) {
         ws.w0row_enh = ws.w0row_prev;  // candidate table row of the fundamental that just became prev_mp_enhanced's
     }
     __syncwarp();
 }
-__device__ __forceinline__ void cur_from_prev(WarpWS& ws, const StreamHome& h, int lane) {
+template <class H>
+__device__ __forceinline__ void cur_from_prev(WarpWS& ws, const H& h, int lane) {
     uint32_t* c = cur_words(ws);
     const uint32_t* p = reinterpret_cast<const uint32_t*>(&ws.prev);
 #pragma unroll
@@ -139,10 +182,11 @@ __device__ __forceinline__ void cur_from_prev(WarpWS& ws, const StreamHome& h, i
         const int w = prev_home_word(j);
         c[w] = h.prev[w];
     }
-    bulk_copy(h.cur, h.prev, lane);
+    bulk_copy(ws, h, h.cur, h.prev, OP_CUR_FROM_PREV, lane);
     __syncwarp();
 }
-__device__ __forceinline__ void cur_from_enh(WarpWS& ws, const StreamHome& h, int lane) {
+template <class H>
+__device__ __forceinline__ void cur_from_enh(WarpWS& ws, const H& h, int lane) {
     uint32_t* c = cur_words(ws);
     const uint32_t* e = reinterpret_cast<const uint32_t*>(&ws.enh);
 #pragma unroll
@@ -153,7 +197,7 @@ __device__ __forceinline__ void cur_from_enh(WarpWS& ws, const StreamHome& h, in
     for (int j = lane; j < ENH_HOME_WORDS; j += 32) {
         c[ENH_HOME_WORD0 + j] = h.enh[ENH_HOME_WORD0 + j];
     }
-    bulk_copy(h.cur, h.enh, lane);
+    bulk_copy(ws, h, h.cur, h.enh, OP_CUR_FROM_ENH, lane);
     __syncwarp();
 }
 
@@ -197,12 +241,11 @@ __device__ __forceinline__ void fill_default(Parms* p, float w0, int L, int K, f
     __syncwarp();
 }
 
-__device__ __noinline__ void init_all(WarpWS& ws, uint32_t* gcur, uint32_t* gprev, uint32_t* genh, float w0, int L, int K,
-                                      float mute_thr, int lane) {
+template <class H>
+__device__ __noinline__ void init_all(WarpWS& ws, const H& h, float w0, int L, int K, float mute_thr, int lane) {
     fill_default_small(&ws.cur, w0, L, K, mute_thr, lane);
-    bulk_zero(gcur, lane);
+    bulk_zero(ws, h, h.cur, lane);
     __syncwarp();
-    const StreamHome h = {gcur, gprev, genh, nullptr};
     prev_from_cur(ws, h, lane);
     enh_from_cur(ws, h, lane);
 }
@@ -1345,6 +1388,8 @@ __device__ __forceinline__ void voiced_bank_block(WarpWS* wsa, BlockShared* bs, 
 // cur = ws.cur, prev = ws.enh; the 160 float samples end up in ws.out.
 // synth_begin: everything up to the component list.  Returns 1 when the frame continues through
 // voiced_bank_block + synth_finish, 0 when it is already complete (silence or comfort noise).
+// COMPONENTS = false (split path): the synthesis kernel builds its own component lists from the frame's descriptor
+template <bool COMPONENTS = true>
 __device__ __noinline__ int synth_begin(WarpWS& ws, const float* cur_overlap, const DevTables* T, int has_rm0,
                                         float rm0, int lane) {
     ParmsSmall& cur = ws.cur;
@@ -1415,7 +1460,11 @@ __device__ __noinline__ int synth_begin(WarpWS& ws, const float* cur_overlap, co
         }
     }
     __syncwarp();
-    build_components(ws, maxl, lane);
+    if (COMPONENTS) {
+        build_components(ws, maxl, lane);
+    } else if (lane == 0) {
+        ws.ncomp = maxl;   // split path: what the descriptor carries instead of a component count
+    }
     return 1;
 }
 

@@ -20,9 +20,13 @@ def pkg():
     return load_package()
 
 
-@pytest.fixture(scope="module")
-def dec(pkg):
+# every test that takes `dec` runs on both kernel paths of the frame entry points: the fused kernel and the parameter +
+# synthesis kernel pair (mbe_b200_set_kernel_path); both must meet the same bars against the oracle
+@pytest.fixture(scope="module", params=[0, 1], ids=["fused", "split"])
+def dec(pkg, request):
     d = pkg.Decoder(max_streams=4096, device=0)
+    d.set_kernel_path(request.param)
+    assert d.kernel_path() == request.param
     yield d
     d.close()
 

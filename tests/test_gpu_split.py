@@ -1,0 +1,91 @@
+"""The two kernel paths of the frame entry points against each other: the fused kernel and the parameter kernel
++ synthesis kernel pair must agree bit for bit - parameter bits, results, int16 and float PCM, and the final mbe_parms
+triplets including the previousUw / noiseOverlap arrays the two kernels of the split path own separately.  (Each path is
+also checked against the oracle: tests/test_gpu_parity.py runs every case on both.)"""
+import numpy as np
+import pytest
+
+import mbe_testlib as T
+from __graft_entry__ import load_package
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return load_package()
+
+
+def _mixed_frames(codec, S, F, seed):
+    """random bits (repeats, mutes, re-initialisation), valid voice held for several frames (stable pitch: interpolated
+    harmonics), valid frames with flipped bits, and for the AMBE codecs tone / erasure frames."""
+    rng = np.random.default_rng(seed)
+    fb = T.FRAME_BITS[codec]
+    enc = {0: T.encode_imbe7200_frame, 1: T.encode_imbe7100_frame}.get(codec, T.encode_ambe_frame)
+    frames = rng.integers(0, 2, size=(S, F, fb), dtype=np.uint8)
+    for s in range(0, S, 2):
+        f = 0
+        while f < F:
+            n = int(min(F - f, rng.integers(2, 9)))
+            p = rng.integers(0, 2, size=T.PARAM_BITS[codec], dtype=np.uint8)
+            if codec <= 1:
+                p[codec] = 0
+            elif rng.random() < 0.15:
+                p[0:6] = 1                       # AMBE tone / erasure signatures
+                if rng.random() < 0.5:
+                    p[45:49] = 0
+            fr = enc(p).reshape(-1)
+            frames[s, f:f + n] = fr
+            if rng.random() < 0.4:
+                frames[s, f:f + n] ^= (rng.random((n, fb)) < 0.04).astype(np.uint8)
+            f += n
+    return frames
+
+
+@pytest.mark.parametrize("codec", [0, 1, 2, 3])
+@pytest.mark.parametrize("soft", [0, 1])
+def test_split_equals_fused(pkg, codec, soft):
+    S, F = (300, 40) if not soft else (60, 12)
+    frames = _mixed_frames(codec, S, F, 0x5917 + 10 * codec + soft)
+    if soft:
+        rng = np.random.default_rng(codec)
+        frames = T.soften(frames, rng, flip_p=0.05)
+    seeds = T.stream_seeds(S, 0x51)
+    out = []
+    for path in (0, 1):
+        dec = pkg.Decoder(max_streams=S, device=0)
+        dec.set_kernel_path(path)
+        dec.init_streams(0, S, seeds)
+        # three launches of different lengths: the state round trip between launches is part of the comparison
+        cuts = [(0, 1), (1, F // 2), (F // 2, F)]
+        parts = [dec.process_frames(codec, np.ascontiguousarray(frames[:, a:b]), soft=bool(soft), want_float=True) for a, b in cuts]
+        out.append((parts, dec.export_state(0, S), dec.export_rng(0, S)))
+        dec.close()
+    (pa, sa, ra), (pb, sb, rb) = out
+    for x, y in zip(pa, pb):
+        assert np.array_equal(x["bits"], y["bits"])
+        assert np.array_equal(x["results"], y["results"])
+        assert np.array_equal(x["pcmf"].view(np.uint32), y["pcmf"].view(np.uint32))
+        assert np.array_equal(x["pcm"], y["pcm"])
+    assert np.array_equal(sa, sb), "final parameter sets differ (previousUw / noiseOverlap included)"
+    assert np.array_equal(ra, rb)
+
+
+def test_split_descriptor_buffer_ranges(pkg, monkeypatch):
+    """A batch whose descriptors exceed the buffer budget is cut into stream ranges inside the call (MBE_B200_DESC_MB is read
+    once per process, so this test only checks a batch much larger than one block through both paths: ragged last block,
+    stream window in the middle of the pool)."""
+    codec, S, F = 3, 1000, 9
+    frames = T.random_hard_frames(codec, S, F, 0xD5C)
+    seeds = T.stream_seeds(S + 50, 7)
+    res = []
+    for path in (0, 1):
+        dec = pkg.Decoder(max_streams=S + 50, device=0)
+        dec.set_kernel_path(path)
+        dec.init_streams(0, S + 50, seeds)
+        got = dec.process_frames(codec, frames, first_stream=37, want_float=True)
+        res.append((got, dec.export_state(0, S + 50)))
+        dec.close()
+    assert np.array_equal(res[0][0]["pcmf"].view(np.uint32), res[1][0]["pcmf"].view(np.uint32))
+    assert np.array_equal(res[0][0]["results"], res[1][0]["results"])
+    assert np.array_equal(res[0][1], res[1][1])
