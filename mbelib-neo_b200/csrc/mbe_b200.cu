@@ -1282,6 +1282,8 @@ using namespace mbe;
 // the host-pointer entry points cut a batch into up to MAX_CHUNKS stream ranges and pipeline them
 constexpr int MAX_CHUNKS = 64;
 constexpr int MAX_KSTREAMS = 4;
+constexpr int MAX_AUX = 4;                          // internal streams of a two-kernel-path launch on a caller's stream
+constexpr int DESC_SLOTS = MAX_KSTREAMS + MAX_AUX;  // descriptor buffers: one per pipeline compute stream, one per internal stream
 
 struct mbe_b200_ctx {
     int device;
@@ -1307,9 +1309,13 @@ struct mbe_b200_ctx {
     // two-kernel path (mbe_split.cuh): descriptor buffers, one per pipeline compute stream + one shared by every other
     // stream; a buffer is reused only after the synthesis kernel that read it has finished (ev_desc)
     int split;
-    void* d_desc[MAX_KSTREAMS + 1];
-    size_t d_desc_cap[MAX_KSTREAMS + 1];
-    cudaEvent_t ev_desc[MAX_KSTREAMS + 1];
+    void* d_desc[DESC_SLOTS];
+    size_t d_desc_cap[DESC_SLOTS];
+    cudaEvent_t ev_desc[DESC_SLOTS];
+    // launches on any other stream fork their stream ranges over these, so that the parameter kernel of one range runs
+    // while the bank / unvoiced kernels of the previous ones do (slots MAX_KSTREAMS.. of d_desc)
+    cudaStream_t s_aux[MAX_AUX];
+    cudaEvent_t ev_fork, ev_join[MAX_AUX];
     char err[256];
 };
 
@@ -1547,6 +1553,7 @@ static void build_tables(DevTables* t) {
 struct Knobs {
     long pad_smem;
     int chunks, taper_blocks, kstreams;
+    int aux_streams;  // MBE_B200_AUX: internal streams a multi-kernel launch forks its stream ranges over
     int split;        // MBE_B200_SPLIT: default kernel path of new contexts (0 fused, 1 parameter + synthesis kernels)
     long desc_mb;     // MBE_B200_DESC_MB: descriptor buffer budget per launch, MiB
 };
@@ -1563,6 +1570,8 @@ static const Knobs& knobs() {
         g_knobs.taper_blocks = e ? atoi(e) : -1;
         e = getenv("MBE_B200_KSTREAMS");
         g_knobs.kstreams = e ? atoi(e) : 0;
+        e = getenv("MBE_B200_AUX");
+        g_knobs.aux_streams = e ? atoi(e) : 0;
         e = getenv("MBE_B200_SPLIT");
         g_knobs.split = e ? atoi(e) : MBE_SPLIT_DEFAULT;
         e = getenv("MBE_B200_DESC_MB");
@@ -1615,7 +1624,7 @@ static StreamKernelFn pick_stream_kernel(int codec, int soft, int mode, bool spl
     return split ? pick_stream_kernel_t<true>(codec, soft, mode) : pick_stream_kernel_t<false>(codec, soft, mode);
 }
 
-static size_t bank_kernel_smem(void) { return 336 * sizeof(float) + (size_t)B_WARPS * sizeof(BankWS); }
+static size_t bank_kernel_smem(void) { return BANK_TAB_FLOATS * sizeof(float) + (size_t)B_WARPS * sizeof(BankWS); }
 static size_t unvoiced_kernel_smem(void) { return sizeof(BlockTables) + (size_t)U_WARPS * sizeof(UnvWS); }
 
 typedef void (*DecodeKernelFn)(int, const uint8_t*, uint8_t*, mbe_b200_result*, const DevTables*);
@@ -1741,9 +1750,14 @@ int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams) {
     CUC(cudaFuncSetAttribute(mbe_split_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bank_kernel_smem()));
     CUC(cudaFuncSetAttribute(mbe_split_unvoiced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)unvoiced_kernel_smem()));
-    for (int i = 0; i <= MAX_KSTREAMS; ++i) {
+    for (int i = 0; i < DESC_SLOTS; ++i) {
         CUC(cudaEventCreateWithFlags(&ctx->ev_desc[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < MAX_AUX; ++i) {
+        CUC(cudaStreamCreateWithFlags(&ctx->s_aux[i], cudaStreamNonBlocking));
+        CUC(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+    }
+    CUC(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     ctx->split = knobs().split ? 1 : 0;
     CUC(cudaFuncSetAttribute(mbe_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_kernel_smem()));
 #undef CUC
@@ -1789,7 +1803,19 @@ void mbe_b200_destroy(mbe_b200_ctx* ctx) {
             cudaEventDestroy(ctx->ev_k[i]);
         }
     }
-    for (int i = 0; i <= MAX_KSTREAMS; ++i) {
+    for (int i = 0; i < MAX_AUX; ++i) {
+        if (ctx->s_aux[i]) {
+            cudaStreamSynchronize(ctx->s_aux[i]);
+            cudaStreamDestroy(ctx->s_aux[i]);
+        }
+        if (ctx->ev_join[i]) {
+            cudaEventDestroy(ctx->ev_join[i]);
+        }
+    }
+    if (ctx->ev_fork) {
+        cudaEventDestroy(ctx->ev_fork);
+    }
+    for (int i = 0; i < DESC_SLOTS; ++i) {
         if (ctx->ev_desc[i]) {
             cudaEventDestroy(ctx->ev_desc[i]);
         }
@@ -1946,12 +1972,14 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaS
         CU(cudaGetLastError());
         return 0;
     }
-    // two-kernel path: parameter kernel -> descriptors -> synthesis kernel, in ranges of streams whose descriptors fit the
-    // buffer of this CUDA stream's slot
-    int slot = MAX_KSTREAMS;
+    // multi-kernel path: parameter kernel -> descriptors -> bank kernel -> unvoiced kernel, in ranges of streams whose
+    // descriptors fit a buffer.  On a pipeline compute stream the ranges run one after the other on that stream (the
+    // pipeline's other streams overlap them); on any other stream they are forked over internal streams, so that the
+    // kernels of consecutive ranges overlap, and joined back into the caller's stream.
+    int kslot = -1;
     for (int i = 0; i < MAX_KSTREAMS; ++i) {
         if (st == ctx->s_k[i]) {
-            slot = i;
+            kslot = i;
         }
     }
     const size_t per_stream = (size_t)a.n_frames * DESC_WORDS * sizeof(uint32_t);
@@ -1963,20 +1991,37 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaS
         cap_streams = WARPS_PER_BLOCK;
     }
     const int sub = (int)(cap_streams < (size_t)a.n_streams ? cap_streams : (size_t)a.n_streams);
-    int rc;
-    if ((rc = ensure(ctx, &ctx->d_desc[slot], &ctx->d_desc_cap[slot], (size_t)sub * per_stream)) < 0) {
-        return rc;
+    const int n_sub = (a.n_streams + sub - 1) / sub;
+    int n_aux = knobs().aux_streams;
+    if (n_aux < 1 || n_aux > MAX_AUX) {
+        n_aux = MAX_AUX;
     }
-    CU(cudaStreamWaitEvent(st, ctx->ev_desc[slot], 0));   // the slot's previous user (possibly on another stream) is done
+    if (n_aux > n_sub) {
+        n_aux = n_sub;
+    }
+    const bool fork = (kslot < 0);
+    int rc;
+    if (fork) {
+        CU(cudaEventRecord(ctx->ev_fork, st));
+        for (int i = 0; i < n_aux; ++i) {
+            CU(cudaStreamWaitEvent(ctx->s_aux[i], ctx->ev_fork, 0));
+        }
+    }
     StreamKernelFn pk = pick_stream_kernel(a.codec, a.soft, a.mode, true);
     const int n_total = a.n_streams, first0 = a.first_stream;
-    for (int o = 0; o < n_total; o += sub) {
+    for (int i = 0, o = 0; o < n_total; o += sub, ++i) {
+        const int slot = fork ? MAX_KSTREAMS + (i % n_aux) : kslot;
+        cudaStream_t ss = fork ? ctx->s_aux[i % n_aux] : st;
+        if ((rc = ensure(ctx, &ctx->d_desc[slot], &ctx->d_desc_cap[slot], (size_t)sub * per_stream)) < 0) {
+            return rc;
+        }
+        CU(cudaStreamWaitEvent(ss, ctx->ev_desc[slot], 0));   // the slot's previous user is done with the buffer
         const int ns = (n_total - o < sub) ? (n_total - o) : sub;
         a.first_stream = first0 + o;
         a.io_base = a_in.io_base + o;
         a.n_streams = ns;
         a.desc = (uint32_t*)ctx->d_desc[slot];
-        pk<<<(ns + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, stream_kernel_smem(), st>>>(a);
+        pk<<<(ns + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, stream_kernel_smem(), ss>>>(a);
         ctx->launches++;
         CU(cudaGetLastError());
         SynthArgs sa;
@@ -1991,14 +2036,25 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaS
         sa.state = a.state;
         sa.tab = a.tab;
         const long long groups = ((long long)ns * a.n_frames + BG - 1) / BG;
-        mbe_split_bank_kernel<<<(unsigned)((groups + B_WARPS - 1) / B_WARPS), B_WARPS * 32, bank_kernel_smem(), st>>>(sa);
+        long long bank_blocks = (groups + B_WARPS - 1) / B_WARPS;
+        const long long resident = (long long)g_sm_count.load() * B_MINB;   // grid-stride warps: one resident wave is enough
+        if (bank_blocks > resident) {
+            bank_blocks = resident;
+        }
+        mbe_split_bank_kernel<<<(unsigned)bank_blocks, B_WARPS * 32, bank_kernel_smem(), ss>>>(sa);
         ctx->launches++;
         CU(cudaGetLastError());
-        mbe_split_unvoiced_kernel<<<(ns + U_WARPS - 1) / U_WARPS, U_WARPS * 32, unvoiced_kernel_smem(), st>>>(sa);
+        mbe_split_unvoiced_kernel<<<(ns + U_WARPS - 1) / U_WARPS, U_WARPS * 32, unvoiced_kernel_smem(), ss>>>(sa);
         ctx->launches++;
         CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev_desc[slot], ss));
     }
-    CU(cudaEventRecord(ctx->ev_desc[slot], st));
+    if (fork) {
+        for (int i = 0; i < n_aux; ++i) {
+            CU(cudaEventRecord(ctx->ev_join[i], ctx->s_aux[i]));
+            CU(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
+        }
+    }
     return 0;
 }
 

@@ -62,7 +62,7 @@ static_assert(D_SD + 112 <= DESC_WORDS && D_VOICED + NS <= D_S, "descriptor layo
 #define MBE_UMINB 4
 #endif
 #ifndef MBE_U_LOCKSTEP
-#define MBE_U_LOCKSTEP 1
+#define MBE_U_LOCKSTEP 0
 #endif
 constexpr int BG = MBE_BG;            // frames pooled per warp of the bank kernel
 constexpr int B_WARPS = MBE_BWARPS;   // warps per block of the bank kernel
@@ -241,156 +241,185 @@ struct __align__(16) BankWS {
     float out[BG][NS];      // voiced samples of the group's frames (lane i owns i, 32 + i, ...)
 };
 
+// smem: voiced window halves (BlockTables::voiced_win layout, 336 floats) | n / 160 for n = 0..159 | per-warp workspaces
+constexpr int BANK_TAB_FLOATS = 336 + NS;
+
 __global__ void __launch_bounds__(B_WARPS * 32, B_MINB) mbe_split_bank_kernel(const SynthArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* vwin = reinterpret_cast<float*>(smem_raw);   // BlockTables::voiced_win layout (328 floats)
-    BankWS* wsa = reinterpret_cast<BankWS*>(smem_raw + 336 * sizeof(float));
+    float* vwin = reinterpret_cast<float*>(smem_raw);
+    float* nfrac = vwin + 336;   // (float)n / (float)N of the amplitude interpolation (mbelib.c:963), the same division
+    BankWS* wsa = reinterpret_cast<BankWS*>(smem_raw + BANK_TAB_FLOATS * sizeof(float));
     for (int i = threadIdx.x; i < 2 * NS; i += blockDim.x) {
         vwin[i < NS ? i : i + (WIN_PREV - NS)] = A.tab->voiced_win[i];
+    }
+    for (int i = threadIdx.x; i < NS; i += blockDim.x) {
+        nfrac[i] = (float)i / (float)NS;
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     BankWS& ws = wsa[warp];
-    const long long n_items = (long long)A.n_streams * A.n_frames;
-    const long long i0 = ((long long)blockIdx.x * B_WARPS + warp) * BG;   // first frame of this warp's group
-    if (i0 >= n_items) {
-        return;
-    }
-    const int n_live = (int)min((long long)BG, n_items - i0);
-    uint32_t* const d0 = A.desc + (size_t)i0 * DESC_WORDS;
     float* tile = ws.tile;
+    const long long n_items = (long long)A.n_streams * A.n_frames;
+    const long long n_groups = (n_items + BG - 1) / BG;
+    const long long warps_total = (long long)gridDim.x * B_WARPS;
+    // the grid is resident (a few blocks per SM); every warp walks groups of BG consecutive frames with a grid stride
+#pragma unroll 1
+    for (long long grp = (long long)blockIdx.x * B_WARPS + warp; grp < n_groups; grp += warps_total) {
+        const long long i0 = grp * BG;
+        const int n_live = (int)min((long long)BG, n_items - i0);
+        uint32_t* const d0 = A.desc + (size_t)i0 * DESC_WORDS;
 
-    int off[BG + 1], cnt[BG];
-    int total = 0;
-    unsigned go_mask = 0;   // frames of the group that run the synthesis (bit q)
+        int off[BG + 1], cnt[BG];
+        int total = 0;
+        unsigned go_mask = 0;   // frames of the group that run the synthesis (bit q)
 #pragma unroll
-    for (int q = 0; q < BG; ++q) {
-        off[q] = total;
-        cnt[q] = 0;
-        if (q < n_live) {
-            const unsigned info = d0[(size_t)q * DESC_WORDS + D_INFO];
-            if (info & 1u) {
-                go_mask |= 1u << q;
-                cnt[q] = (int)((info >> 16) & 255u);
-                total += (cnt[q] + 3) & ~3;
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            ws.out[q][32 * c + lane] = 0.0f;
-        }
-    }
-    off[BG] = total;
-    if (go_mask == 0u) {
-        return;   // (no frame of the group runs the synthesis: nothing to leave behind)
-    }
-
-#pragma unroll 1
-    for (int base = 0; base < total; base += 32) {
-        const int k = base + lane;
-        int q = 0;
-#pragma unroll
-        for (int t = 1; t < BG; ++t) {
-            q += (off[t] <= k) ? 1 : 0;
-        }
-        int ofs_q = off[0], cnt_q = cnt[0];
-#pragma unroll
-        for (int t = 1; t < BG; ++t) {
-            if (q == t) {
-                ofs_q = off[t];
-                cnt_q = cnt[t];
-            }
-        }
-        const int pos = k - ofs_q;
-        const bool used = pos < cnt_q;
-        float g = 0.f, c = 0.f, s = 0.f, cd = 0.f, sd = 0.f, dw0 = 0.f;
-        int kind = 0, l = 0;
-        const uint32_t* d = d0 + (size_t)q * DESC_WORDS;
-        if (used) {
-            const unsigned id = reinterpret_cast<const unsigned char*>(d + D_KIND)[pos];
-            kind = (int)(id & 3u);
-            l = (int)(id >> 2);
-            g = __uint_as_float(d[D_G + pos]);
-            c = __uint_as_float(d[D_C + pos]);
-            s = __uint_as_float(d[D_S + pos]);
-            cd = __uint_as_float(d[D_CD + pos]);
-            sd = __uint_as_float(d[D_SD + pos]);
-            dw0 = __uint_as_float(d[D_DW0]);
-        }
-        const bool k2lane = (kind == 2);
-        const unsigned k2mask = __ballot_sync(FULL, k2lane);
-        const float* Wb = vwin + ((kind == 0) ? WIN_PREV : 0);
-        const float gg = k2lane ? 0.0f : g;   // interpolated slots are written by whoever renders them
-        const float rec_c = c, rec_s = s;     // (the recurrence below rotates c and s on every lane)
-#pragma unroll 1
-        for (int ch = 0; ch < 5; ++ch) {
-            // phase A: 32 oscillator steps, eight per loop body (the body stays in the L0 instruction cache)
-            const float* Wc = Wb + 32 * ch;
-#pragma unroll 1
-            for (int n8 = 0; n8 < 4; ++n8) {
-                const float4 wa = *reinterpret_cast<const float4*>(Wc + 8 * n8);
-                const float4 wb = *reinterpret_cast<const float4*>(Wc + 8 * n8 + 4);
-                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    // row n = 8 n8 + i of the tile: tile_at(n, lane) = 32 n + (lane ^ 4 i)
-                    if (!k2lane) {
-                        tile[(256 * n8 + 32 * i) + (lane ^ (i << 2))] = (gg * wv[i]) * c;
-                    }
-                    const float cn = (c * cd) - (s * sd);
-                    const float sn = (s * cd) + (c * sd);
-                    c = cn;
-                    s = sn;
+        for (int q = 0; q < BG; ++q) {
+            off[q] = total;
+            cnt[q] = 0;
+            if (q < n_live) {
+                const unsigned info = d0[(size_t)q * DESC_WORDS + D_INFO];
+                if (info & 1u) {
+                    go_mask |= 1u << q;
+                    cnt[q] = (int)((info >> 16) & 255u);
+                    total += (cnt[q] + 3) & ~3;
                 }
             }
-            // phase-interpolated harmonics of this pass: lane = sample (mbelib.c:953-968); the slot's lane holds its record
-            for (unsigned m = k2mask; m; m &= m - 1u) {
-                const int sl = __ffs(m) - 1;
-                const float a1 = __shfl_sync(FULL, g, sl), phi = __shfl_sync(FULL, rec_c, sl), pM = __shfl_sync(FULL, rec_s, sl),
-                            cM = __shfl_sync(FULL, cd, sl), dw = __shfl_sync(FULL, dw0, sl);
-                const int ll = __shfl_sync(FULL, l, sl);
-                const int n = 32 * ch + lane;
-                const float th = phi + (a1 * (float)n) + ((dw * (float)(ll * n * n)) / (float)(2 * NS));
-                const float am = pM + (((float)n / (float)NS) * (cM - pM));
-                tile[tile_at(lane, sl)] = 2.0f * am * dev_cosf(th);
-            }
-            __syncwarp();
-            // phase B: every frame with slots in this pass adds them in list order, lane = sample
-            {
-                const float4* row = reinterpret_cast<const float4*>(tile + lane * 32);
-                const int sw = lane & 7;
-#pragma unroll
-                for (int t = 0; t < BG; ++t) {
-                    const int lo = max(off[t], base), hi = min(off[t] + ((cnt[t] + 3) & ~3), base + 32);
-                    if (hi > lo) {
-                        float a = ws.out[t][32 * ch + lane];
-                        int gq = (lo - base) >> 2;
-                        const int ge = (hi - base) >> 2;
-#pragma unroll 1
-                        for (; gq + 2 <= ge; gq += 2) {
-                            const float4 v0 = row[gq ^ sw], v1 = row[(gq + 1) ^ sw];
-                            a += v0.x; a += v0.y; a += v0.z; a += v0.w;
-                            a += v1.x; a += v1.y; a += v1.z; a += v1.w;
-                        }
-                        if (gq < ge) {
-                            const float4 v = row[gq ^ sw];
-                            a += v.x; a += v.y; a += v.z; a += v.w;
-                        }
-                        ws.out[t][32 * ch + lane] = a;
-                    }
-                }
-            }
-            __syncwarp();
         }
-    }
-    // the frames' voiced samples replace their (now dead) slot records
+        off[BG] = total;
+        if (go_mask == 0u) {
+            continue;   // (no frame of the group runs the synthesis: nothing to leave behind)
+        }
 #pragma unroll
-    for (int q = 0; q < BG; ++q) {
-        if ((go_mask >> q) & 1u) {
+        for (int q = 0; q < BG; ++q) {
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
-                d0[(size_t)q * DESC_WORDS + D_VOICED + 32 * c + lane] = __float_as_uint(ws.out[q][32 * c + lane]);
+                ws.out[q][32 * c + lane] = 0.0f;
+            }
+        }
+
+#pragma unroll 1
+        for (int base = 0; base < total; base += 32) {
+            const int k = base + lane;
+            int q = 0;
+#pragma unroll
+            for (int t = 1; t < BG; ++t) {
+                q += (off[t] <= k) ? 1 : 0;
+            }
+            int ofs_q = off[0], cnt_q = cnt[0];
+#pragma unroll
+            for (int t = 1; t < BG; ++t) {
+                if (q == t) {
+                    ofs_q = off[t];
+                    cnt_q = cnt[t];
+                }
+            }
+            const int pos = k - ofs_q;
+            const bool used = pos < cnt_q;
+            float g = 0.f, c = 0.f, s = 0.f, cd = 0.f, sd = 0.f, dw0 = 0.f;
+            int kind = 0, l = 0;
+            if (used) {
+                const uint32_t* d = d0 + (size_t)q * DESC_WORDS;
+                const unsigned id = reinterpret_cast<const unsigned char*>(d + D_KIND)[pos];
+                kind = (int)(id & 3u);
+                l = (int)(id >> 2);
+                g = __uint_as_float(d[D_G + pos]);
+                c = __uint_as_float(d[D_C + pos]);
+                s = __uint_as_float(d[D_S + pos]);
+                cd = __uint_as_float(d[D_CD + pos]);
+                sd = __uint_as_float(d[D_SD + pos]);
+                dw0 = __uint_as_float(d[D_DW0]);
+            }
+            const bool k2lane = (kind == 2);
+            const unsigned k2mask = __ballot_sync(FULL, k2lane);
+            const float* Wb = vwin + ((kind == 0) ? WIN_PREV : 0);
+            const float gg = k2lane ? 0.0f : g;   // interpolated slots are written by whoever renders them
+            const float rec_c = c, rec_s = s;     // (the recurrence below rotates c and s on every lane)
+            // this pass's part of every frame of the group, in four-slot groups of the tile: [glo, ghi)
+            int glo[BG], ghi[BG];
+#pragma unroll
+            for (int t = 0; t < BG; ++t) {
+                const int lo = max(off[t], base), hi = min(off[t] + ((cnt[t] + 3) & ~3), base + 32);
+                glo[t] = (lo - base) >> 2;
+                ghi[t] = (hi > lo) ? ((hi - base) >> 2) : glo[t];
+            }
+#pragma unroll 1
+            for (int ch = 0; ch < 5; ++ch) {
+                // phase A: 32 oscillator steps, eight per loop body (the body stays in the L0 instruction cache)
+                const float* Wc = Wb + 32 * ch;
+#pragma unroll 1
+                for (int n8 = 0; n8 < 4; ++n8) {
+                    const float4 wa = *reinterpret_cast<const float4*>(Wc + 8 * n8);
+                    const float4 wb = *reinterpret_cast<const float4*>(Wc + 8 * n8 + 4);
+                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        // row n = 8 n8 + i of the tile: tile_at(n, lane) = 32 n + (lane ^ 4 i)
+                        if (!k2lane) {
+                            tile[(256 * n8 + 32 * i) + (lane ^ (i << 2))] = (gg * wv[i]) * c;
+                        }
+                        const float cn = (c * cd) - (s * sd);
+                        const float sn = (s * cd) + (c * sd);
+                        c = cn;
+                        s = sn;
+                    }
+                }
+                // phase-interpolated harmonics of this pass: lane = sample (mbelib.c:953-968); the slot's lane holds its record
+                if (k2mask) {
+                    const int n = 32 * ch + lane;
+                    const float fn = (float)n, fr = nfrac[n];
+                    const int nn = n * n;
+                    for (unsigned m = k2mask; m; m &= m - 1u) {
+                        const int sl = __ffs(m) - 1;
+                        const float a1 = __shfl_sync(FULL, g, sl), phi = __shfl_sync(FULL, rec_c, sl),
+                                    pM = __shfl_sync(FULL, rec_s, sl), cM = __shfl_sync(FULL, cd, sl),
+                                    dw = __shfl_sync(FULL, dw0, sl);
+                        const int ll = __shfl_sync(FULL, l, sl);
+                        const float th = phi + (a1 * fn) + ((dw * (float)(ll * nn)) / (float)(2 * NS));
+                        const float am = pM + (fr * (cM - pM));
+                        tile[tile_at(lane, sl)] = 2.0f * am * dev_cosf(th);
+                    }
+                }
+                __syncwarp();
+                // phase B: every frame with slots in this pass adds them in list order, lane = sample
+                {
+                    const float4* row = reinterpret_cast<const float4*>(tile + lane * 32);
+                    const int sw = lane & 7;
+#pragma unroll
+                    for (int t = 0; t < BG; ++t) {
+                        if (ghi[t] > glo[t]) {
+                            float a = ws.out[t][32 * ch + lane];
+                            int gq = glo[t];
+                            const int ge = ghi[t];
+#pragma unroll 1
+                            for (; gq + 4 <= ge; gq += 4) {
+                                const float4 v0 = row[gq ^ sw], v1 = row[(gq + 1) ^ sw], v2 = row[(gq + 2) ^ sw],
+                                             v3 = row[(gq + 3) ^ sw];
+                                a += v0.x; a += v0.y; a += v0.z; a += v0.w;
+                                a += v1.x; a += v1.y; a += v1.z; a += v1.w;
+                                a += v2.x; a += v2.y; a += v2.z; a += v2.w;
+                                a += v3.x; a += v3.y; a += v3.z; a += v3.w;
+                            }
+#pragma unroll 1
+                            for (; gq < ge; ++gq) {
+                                const float4 v = row[gq ^ sw];
+                                a += v.x; a += v.y; a += v.z; a += v.w;
+                            }
+                            ws.out[t][32 * ch + lane] = a;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // the frames' voiced samples replace their (now dead) slot records
+#pragma unroll
+        for (int q = 0; q < BG; ++q) {
+            if ((go_mask >> q) & 1u) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    d0[(size_t)q * DESC_WORDS + D_VOICED + 32 * c + lane] = __float_as_uint(ws.out[q][32 * c + lane]);
+                }
             }
         }
     }
