@@ -236,8 +236,12 @@ struct SynthArgs {
     const DevTables* tab;
 };
 
+// Oscillator tile of the bank kernel: 32 samples x 32 slots, rows padded to 36 words: phase A (lane = slot, one row per
+// store) and phase B (lane = sample, LDS.128 over four consecutive slots) are both bank-conflict free, and every access is
+// a base register + immediate offset (no swizzle arithmetic in the loops)
+constexpr int BT_STRIDE = 36;
 struct __align__(16) BankWS {
-    float tile[32 * 32];    // oscillator tile of the current pass, XOR-swizzled (tile_at)
+    float tile[32 * BT_STRIDE];
     float out[BG][NS];      // voiced samples of the group's frames (lane i owns i, 32 + i, ...)
 };
 
@@ -345,24 +349,27 @@ __global__ void __launch_bounds__(B_WARPS * 32, B_MINB) mbe_split_bank_kernel(co
             }
 #pragma unroll 1
             for (int ch = 0; ch < 5; ++ch) {
-                // phase A: 32 oscillator steps, eight per loop body (the body stays in the L0 instruction cache)
-                const float* Wc = Wb + 32 * ch;
+                // phase A: 32 oscillator steps, sixteen per loop body (the body stays in the L0 instruction cache)
+                const float4* W4 = reinterpret_cast<const float4*>(Wb) + 8 * ch;
+                float* tp = tile + lane;
 #pragma unroll 1
-                for (int n8 = 0; n8 < 4; ++n8) {
-                    const float4 wa = *reinterpret_cast<const float4*>(Wc + 8 * n8);
-                    const float4 wb = *reinterpret_cast<const float4*>(Wc + 8 * n8 + 4);
-                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        // row n = 8 n8 + i of the tile: tile_at(n, lane) = 32 n + (lane ^ 4 i)
-                        if (!k2lane) {
-                            tile[(256 * n8 + 32 * i) + (lane ^ (i << 2))] = (gg * wv[i]) * c;
+                    for (int n4 = 0; n4 < 4; ++n4) {
+                        const float4 w4 = W4[4 * h + n4];
+                        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (!k2lane) {
+                                tp[(4 * n4 + i) * BT_STRIDE] = (gg * wv[i]) * c;   // row n = 16 h + 4 n4 + i
+                            }
+                            const float cn = (c * cd) - (s * sd);
+                            const float sn = (s * cd) + (c * sd);
+                            c = cn;
+                            s = sn;
                         }
-                        const float cn = (c * cd) - (s * sd);
-                        const float sn = (s * cd) + (c * sd);
-                        c = cn;
-                        s = sn;
                     }
+                    tp += 16 * BT_STRIDE;
                 }
                 // phase-interpolated harmonics of this pass: lane = sample (mbelib.c:953-968); the slot's lane holds its record
                 if (k2mask) {
@@ -377,32 +384,35 @@ __global__ void __launch_bounds__(B_WARPS * 32, B_MINB) mbe_split_bank_kernel(co
                         const int ll = __shfl_sync(FULL, l, sl);
                         const float th = phi + (a1 * fn) + ((dw * (float)(ll * nn)) / (float)(2 * NS));
                         const float am = pM + (fr * (cM - pM));
-                        tile[tile_at(lane, sl)] = 2.0f * am * dev_cosf(th);
+                        tile[lane * BT_STRIDE + sl] = 2.0f * am * dev_cosf(th);
                     }
                 }
                 __syncwarp();
                 // phase B: every frame with slots in this pass adds them in list order, lane = sample
                 {
-                    const float4* row = reinterpret_cast<const float4*>(tile + lane * 32);
-                    const int sw = lane & 7;
+                    const float4* row = reinterpret_cast<const float4*>(tile + lane * BT_STRIDE);
 #pragma unroll
                     for (int t = 0; t < BG; ++t) {
                         if (ghi[t] > glo[t]) {
                             float a = ws.out[t][32 * ch + lane];
-                            int gq = glo[t];
-                            const int ge = ghi[t];
+                            const float4* p = row + glo[t];
+                            const float4* const pe = row + ghi[t];
 #pragma unroll 1
-                            for (; gq + 4 <= ge; gq += 4) {
-                                const float4 v0 = row[gq ^ sw], v1 = row[(gq + 1) ^ sw], v2 = row[(gq + 2) ^ sw],
-                                             v3 = row[(gq + 3) ^ sw];
+                            for (; p + 4 <= pe; p += 4) {
+                                const float4 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
                                 a += v0.x; a += v0.y; a += v0.z; a += v0.w;
                                 a += v1.x; a += v1.y; a += v1.z; a += v1.w;
                                 a += v2.x; a += v2.y; a += v2.z; a += v2.w;
                                 a += v3.x; a += v3.y; a += v3.z; a += v3.w;
                             }
-#pragma unroll 1
-                            for (; gq < ge; ++gq) {
-                                const float4 v = row[gq ^ sw];
+                            if (p + 2 <= pe) {
+                                const float4 v0 = p[0], v1 = p[1];
+                                a += v0.x; a += v0.y; a += v0.z; a += v0.w;
+                                a += v1.x; a += v1.y; a += v1.z; a += v1.w;
+                                p += 2;
+                            }
+                            if (p < pe) {
+                                const float4 v = p[0];
                                 a += v.x; a += v.y; a += v.z; a += v.w;
                             }
                             ws.out[t][32 * ch + lane] = a;
