@@ -549,23 +549,33 @@ __device__ __forceinline__ void store_stream(const WarpWS& ws, uint32_t* gs, int
 // =====================================================================================================
 // SPLIT: the parameter kernel of the two-kernel path (mbe_split.cuh): no oscillator bank, no transforms; every frame
 // leaves a descriptor for mbe_split_synth_kernel, frames without speech synthesis are finished here.
+// block shape of the stream kernel: the multi-kernel path's parameter kernel on hard-decision input has no tile and fits 64
+// registers, so it runs P_WARPS warps per block on the short per-warp stride
+template <int SOFT, bool SPLIT>
+struct StreamShape {
+    static constexpr bool SMALL = SPLIT && SOFT != 1;
+    static constexpr int WARPS = SMALL ? P_WARPS : WARPS_PER_BLOCK;
+    static constexpr size_t STRIDE = SMALL ? WS_STRIDE_SMALL : sizeof(WarpWS);
+};
+
 template <int CODEC, int SOFT, int MODE, bool SPLIT>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_stream_kernel(const LaunchArgs A) {
+__global__ void __launch_bounds__(StreamShape<SOFT, SPLIT>::WARPS * 32, MIN_BLOCKS_PER_SM) mbe_stream_kernel(const LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Shape = StreamShape<SOFT, SPLIT>;
     BlockTables* bt = reinterpret_cast<BlockTables*>(smem_raw);
     WarpWS* wsa = reinterpret_cast<WarpWS*>(smem_raw + sizeof(BlockTables));
     BlockShared* bs = reinterpret_cast<BlockShared*>(smem_raw + sizeof(BlockTables) + WARPS_PER_BLOCK * sizeof(WarpWS));
     const DevTables* T = A.tab;
-    if (threadIdx.x == 0) {
+    if (!SPLIT && threadIdx.x == 0) {
         bs->n_interp[0] = bs->n_interp[1] = 0;
     }
     load_block_tables(bt, T);   // ends with a block barrier
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int s = blockIdx.x * Shape::WARPS + warp;
     const bool live = s < A.n_streams;  // idle warps of the last block still take part in the bank
-    WarpWS& ws = wsa[warp];
+    WarpWS& ws = *reinterpret_cast<WarpWS*>(smem_raw + sizeof(BlockTables) + (size_t)warp * Shape::STRIDE);
     constexpr bool AMBE = (CODEC >= MBE_B200_AMBE3600X2400);
     constexpr int fbits = (CODEC == MBE_B200_IMBE7200X4400) ? 184 : (CODEC == MBE_B200_IMBE7100X4400 ? 168 : 96);
     constexpr int pbits = AMBE ? 49 : 88;
@@ -1586,6 +1596,13 @@ static const Knobs& knobs() {
 static size_t stream_kernel_smem(void) {
     return sizeof(BlockTables) + (size_t)WARPS_PER_BLOCK * sizeof(WarpWS) + sizeof(BlockShared) + (size_t)knobs().pad_smem;
 }
+// the multi-kernel path's parameter kernel: block shape by input kind (StreamShape)
+static bool parm_kernel_small(int soft) { return soft != 1; }
+static int parm_kernel_warps(int soft) { return parm_kernel_small(soft) ? P_WARPS : WARPS_PER_BLOCK; }
+static size_t parm_kernel_smem(int soft) {
+    return parm_kernel_small(soft) ? sizeof(BlockTables) + (size_t)P_WARPS * WS_STRIDE_SMALL + (size_t)knobs().pad_smem
+                                   : stream_kernel_smem();
+}
 
 typedef void (*StreamKernelFn)(const LaunchArgs);
 
@@ -1739,10 +1756,10 @@ int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams) {
     for (int codec = 0; codec < 4; ++codec) {
         for (int soft = 0; soft < 3; ++soft) {
             for (int mode = 0; mode < (soft == 2 ? 1 : 2); ++mode) {
-                for (int split = 0; split < 2; ++split) {
-                    CUC(cudaFuncSetAttribute(pick_stream_kernel(codec, soft, mode, split != 0),
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_kernel_smem()));
-                }
+                CUC(cudaFuncSetAttribute(pick_stream_kernel(codec, soft, mode, false),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_kernel_smem()));
+                CUC(cudaFuncSetAttribute(pick_stream_kernel(codec, soft, mode, true),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)parm_kernel_smem(soft)));
             }
         }
     }
@@ -1984,7 +2001,8 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaS
     }
     const size_t per_stream = (size_t)a.n_frames * DESC_WORDS * sizeof(uint32_t);
     size_t cap_streams = ((size_t)knobs().desc_mb << 20) / per_stream;
-    const size_t gran = (size_t)g_sm_count.load() * WARPS_PER_BLOCK * MIN_BLOCKS_PER_SM;   // one wave of the parameter kernel
+    const int pw = parm_kernel_warps(a.soft);
+    const size_t gran = (size_t)g_sm_count.load() * pw * MIN_BLOCKS_PER_SM;   // one wave of the parameter kernel
     if (cap_streams >= gran) {
         cap_streams -= cap_streams % gran;
     } else if (cap_streams < (size_t)WARPS_PER_BLOCK) {
@@ -2021,7 +2039,7 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaS
         a.io_base = a_in.io_base + o;
         a.n_streams = ns;
         a.desc = (uint32_t*)ctx->d_desc[slot];
-        pk<<<(ns + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, stream_kernel_smem(), ss>>>(a);
+        pk<<<(ns + pw - 1) / pw, pw * 32, parm_kernel_smem(a.soft), ss>>>(a);
         ctx->launches++;
         CU(cudaGetLastError());
         SynthArgs sa;

@@ -263,22 +263,6 @@ struct StreamRng {
 // Per-warp shared-memory workspace: one warp owns one stream for the whole launch.
 struct __align__(16) WarpWS {
     StreamRng rng;
-    union __align__(16) {
-        float tile[32 * 32];              // voiced bank: [sample][slot] pre-weighted contributions, XOR-swizzled (tile_at)
-        struct {
-            float a[324];                 // FFT ping buffer (windowed noise on entry); 324: padded pass layouts
-            float b[324];                 // FFT pong buffer
-            float scale[132];             // per-bin unvoiced band scale
-        } fft;
-        struct {                          // front-end / parameter decode scratch (dead before synthesis starts)
-            float tmp[128];               // per-harmonic terms [1..56], DCT coefficients [64+l]
-            float Tl[60];
-            int field[58];                // IMBE quantiser words b1..bL+1
-            unsigned rowbits[8];
-            unsigned char rel[8 * 24];    // soft-bit reliabilities of the frame
-        } dec;
-        float nz[57];                     // white-noise samples 1..56 of the frame (phase randomisation; dead before the bank)
-    } u;                                  // 16-byte aligned: rows are read with LDS.128
     float out[NS];                        // the frame's 160 float samples (lane i owns i, 32+i, ...)
     // The three mbe_parms of the stream WITHOUT their bulk arrays (previousUw / noiseOverlap stay in the
     // stream's HBM slot); 16-byte aligned for 128-bit struct copies.
@@ -296,11 +280,38 @@ struct __align__(16) WarpWS {
     unsigned short off[WARPS_PER_BLOCK + 3];  // this warp's copy of the block's slot offsets (prefix of padded counts)
     unsigned short interp_item[8];        // interpolated harmonics of the block this warp renders in this round: owner << 8 | position
     unsigned char comp[112];              // component descriptor: harmonic << 2 | kind
+    // LAST member: the parameter kernel of the multi-kernel path with hard-decision input only needs the decode scratch
+    // (WS_STRIDE_SMALL), so its per-warp stride stops short of the tile
+    union __align__(16) {
+        float tile[32 * 32];              // voiced bank: [sample][slot] pre-weighted contributions, XOR-swizzled (tile_at)
+        struct {
+            float a[324];                 // FFT ping buffer (windowed noise on entry); 324: padded pass layouts
+            float b[324];                 // FFT pong buffer
+            float scale[132];             // per-bin unvoiced band scale
+        } fft;
+        struct {                          // front-end / parameter decode scratch (dead before synthesis starts)
+            float tmp[128];               // per-harmonic terms [1..56], DCT coefficients [64+l]
+            float Tl[60];
+            int field[58];                // IMBE quantiser words b1..bL+1
+            unsigned rowbits[8];
+            unsigned char rel[8 * 24];    // soft-bit reliabilities of the frame
+        } dec;
+        float nz[57];                     // white-noise samples 1..56 of the frame (phase randomisation; dead before the bank)
+    } u;                                  // 16-byte aligned: rows are read with LDS.128
 };
 static_assert(sizeof(((WarpWS*)0)->u) >= 4096 && sizeof(((WarpWS*)0)->out) >= 608, "soft-decision scratch (SoftScratch)");
 static_assert(offsetof(WarpWS, u) % 16 == 0 && sizeof(WarpWS) % 16 == 0 && sizeof(BlockTables) % 16 == 0 &&
                   offsetof(WarpWS, cur) % 16 == 0,
               "LDS.128 alignment");
+// per-warp stride of the multi-kernel path's parameter kernel on hard-decision input: everything up to the union + the
+// decode scratch / the 176-float scratch of the spectral enhancement (no tile, no transforms in that kernel)
+constexpr size_t WS_DEC_BYTES = (sizeof(((WarpWS*)0)->u.dec) + 15) & ~(size_t)15;
+static_assert(WS_DEC_BYTES >= 176 * 4 + 16, "spectral_enhance scratch");
+constexpr size_t WS_STRIDE_SMALL = offsetof(WarpWS, u) + WS_DEC_BYTES;
+#ifndef MBE_PWPB
+#define MBE_PWPB 18
+#endif
+constexpr int P_WARPS = MBE_PWPB;   // warps per block of that kernel (64 registers per thread at two blocks per SM)
 
 struct BlockShared {
     int cnt[2][WARPS_PER_BLOCK + 2];      // per stream: component count of the current frame (double-buffered by frame parity)
