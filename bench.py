@@ -511,6 +511,7 @@ def main():
             step_dev()
     barrier()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    dec.set_kernel_timing(True)     # an event pair around every kernel launch, on the stream it runs on (kernel_timing below)
     l0 = dec.launches
     with ClockSampler(local_rank) as clk:
         barrier()
@@ -522,6 +523,9 @@ def main():
         stream.synchronize()
         barrier()
     launches = dec.launches - l0
+    kernel_ms, bank_work = dec.kernel_timing()
+    dec.set_kernel_timing(False)
+    kernel_path = dec.kernel_path()
     total_ms = max_over_ranks(evs[0].elapsed_time(evs[-1]))
     per_step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     kern_ms = float(np.mean(per_step_ms))
@@ -647,7 +651,11 @@ def main():
                "note": "pinned host frame bits in, int16 PCM + results to pinned host memory, wall clock around the blocking "
                        "C-ABI calls, max over ranks; packed input is the headline at N > 1 (the host links are the limit there)"}
 
-    # ---- rooflines of the stream kernel ----
+    # ---- rooflines ----
+    # `roofline` is the dominant kernel's: on the multi-kernel path the bank kernel (mbe_split_bank_kernel), whose launches were
+    # bracketed by CUDA events on their own streams during the timed region and whose work (oscillator slots x 160 samples,
+    # interpolated harmonics) the kernel counted itself; on the fused path the stream kernel.  `roofline_step` is the whole
+    # step (every kernel) against the same FP32-issue peak, `roofline_hbm` the HBM view of the step.
     hbm_peak, peak_src = measured_peaks()
     consts = ncu_constants()
     alg_bytes = flops = dram = winstr = 0.0
@@ -666,34 +674,71 @@ def main():
             have_all = False
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     fp32_issue_peak = 148 * 128 * sm_mhz * 1e6 / 1e12  # TFLOP/s, one non-fused op per lane per clock
+    peak_note = ("148 SM x 128 FP32 lanes x %.0f MHz sampled SM clock, non-fused (mul and add issue separately because parity "
+                 "forbids FMA contraction); the FMA-counted peak is 2x; the path has no dense contraction, so neither HBM nor "
+                 "the tensor cores bound it (see roofline_hbm)" % sm_mhz)
     fp32_ach = flops / (kern_ms * 1e-3) / 1e12
     hbm_ach = alg_bytes / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "fp32-issue", "achieved": fp32_ach, "peak": fp32_issue_peak, "unit": "TFLOP/s",
-                "frac": fp32_ach / fp32_issue_peak, "traffic": dram if (have_all and dram) else None,
-                "kernel": "mbe_stream_kernel", "launch_ms": kern_ms, "algorithmic_flop_per_launch": flops,
-                "flop_per_frame": {CODEC_NAMES[c]: FLOP_PER_FRAME[c] for c, _ in parts},
-                "peak_source": "148 SM x 128 FP32 lanes x %.0f MHz sampled SM clock, non-fused (mul and add issue separately "
-                               "because parity forbids FMA contraction); the FMA-counted peak is 2x; the path has no dense "
-                               "contraction, so neither HBM nor the tensor cores bound it (see roofline_hbm)" % sm_mhz,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per frame x frames per launch "
-                                  "(profiles/ncu_constants.json)" if (have_all and dram) else None}
+    roofline_step = {"bound": "fp32-issue", "achieved": fp32_ach, "peak": fp32_issue_peak, "unit": "TFLOP/s",
+                     "frac": fp32_ach / fp32_issue_peak, "step_ms": kern_ms, "algorithmic_flop_per_step": flops,
+                     "flop_per_frame": {CODEC_NAMES[c]: FLOP_PER_FRAME[c] for c, _ in parts},
+                     "note": "every kernel of the step: SURVEY 8(d)'s analytic FLOP per frame x frames / event-timed step"}
+    kinds_ms = {k: v[0] for k, v in kernel_ms.items()}
+    kinds_n = {k: v[1] for k, v in kernel_ms.items()}
+    busy = sum(kinds_ms.values()) or 1.0
+    kernels = {k: {"launches": kinds_n[k], "ms_total": kinds_ms[k], "ms_per_launch": kinds_ms[k] / max(1, kinds_n[k]),
+                   "share_of_kernel_time": kinds_ms[k] / busy} for k in kinds_ms if kinds_n[k]}
+    if kernel_path == 1 and kinds_n.get("bank"):
+        # per slot: 160 x (6 rotation + 2 gain / window + 1 ordered add) = 1440 FLOP; per interpolated harmonic 160 x 46
+        win_slots = bank_work["slots"] - bank_work["interpolated"]
+        bank_flop = 1440.0 * win_slots + 160.0 * 46.0 * bank_work["interpolated"]
+        # The step's kernels run on several streams at once, so an event pair around one launch also counts the time its
+        # neighbours held the SMs: the sum of all bracketed durations is `concurrency` x the step.  The bank kernel's own
+        # share of the step is its share of that sum; achieved = its FLOP / (step time x share).
+        wall_ms = evs[0].elapsed_time(evs[-1])
+        concurrency = busy / wall_ms
+        share = kernels["bank"]["share_of_kernel_time"]
+        ach = bank_flop / (wall_ms * share * 1e-3) / 1e12
+        roofline = {"bound": "fp32-issue", "achieved": ach, "peak": fp32_issue_peak, "unit": "TFLOP/s", "frac": ach / fp32_issue_peak,
+                    "traffic": None, "kernel": "mbe_split_bank_kernel",
+                    "launch_ms": kernels["bank"]["ms_per_launch"] / concurrency, "launch_ms_bracketed": kernels["bank"]["ms_per_launch"],
+                    "concurrency": concurrency, "launches": kinds_n["bank"],
+                    "algorithmic_flop_per_launch": bank_flop / kinds_n["bank"],
+                    "work": {"oscillator_slots": bank_work["slots"], "interpolated_harmonics": bank_work["interpolated"],
+                             "frames_synthesised": bank_work["frames"],
+                             "slots_per_frame": bank_work["slots"] / max(1, bank_work["frames"])},
+                    "share_of_step": share,
+                    "peak_source": peak_note,
+                    "note": "launch durations are CUDA-event pairs on the launching streams inside the timed region; launch_ms = "
+                            "bracketed duration / concurrency (see bench.py); the solo, cold-cache durations and the pipe "
+                            "utilisation of the same launches are in profiles/ (ncu launch list, ncu_constants.json)"}
+    else:
+        roofline = dict(roofline_step)
+        roofline.update({"traffic": None, "kernel": "mbe_stream_kernel", "launch_ms": kern_ms,
+                         "algorithmic_flop_per_launch": flops, "peak_source": peak_note})
+    if have_all and dram:
+        roofline["traffic"] = dram
+        roofline["traffic_source"] = ("ncu dram__bytes_read.sum + dram__bytes_write.sum per frame, all kernels of the path, x frames per "
+                                      "step (profiles/ncu_constants.json)")
     if have_all and winstr:
         issue_peak = 148 * 4 * sm_mhz * 1e6   # warp-instructions per second, one per scheduler per clock
         issue_ach = winstr / (kern_ms * 1e-3)
         roofline["issue_slots"] = {"achieved": issue_ach / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instr/s",
                                    "frac": issue_ach / issue_peak, "warp_instr_per_frame": winstr / (S * F),
-                                   "source": "ncu smsp__inst_executed.sum per frame (profiles/ncu_constants.json) x frames per "
-                                             "launch / event-timed launch"}
+                                   "source": "ncu smsp__inst_executed.sum per frame, all kernels of the path "
+                                             "(profiles/ncu_constants.json) x frames per step / event-timed step"}
         roofline["ncu"] = per_part
     roofline_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                     "traffic": dram if (have_all and dram) else None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes,
-                    "note": "bit-in / PCM-out / state traffic of the launch: ~1 KB per frame, HBM is ~99 % idle"}
+                    "note": "bit-in / PCM-out / state traffic of the step: ~1 KB per frame (the multi-kernel path adds its "
+                            "descriptors, ~3 KB per frame written and read once: see traffic); HBM stays > 90 % idle"}
     line = {"metric": "decoded frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "realtime_channels": value / 50.0, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "roofline_hbm": roofline_hbm}
+            "roofline": roofline, "roofline_step": roofline_step, "roofline_hbm": roofline_hbm,
+            "kernel_path": "multi-kernel (parameter + bank + unvoiced)" if kernel_path == 1 else "fused", "kernels": kernels}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, info, _ = run_cpu_reference(parts, F, 2, 1, streams_per_thread=1000)

@@ -80,10 +80,17 @@ MBE_B200_API int mbe_b200_device_count(void); /* usable CUDA devices (0 when the
 MBE_B200_API long long mbe_b200_launch_count(const mbe_b200_ctx* ctx);
 /* Kernel path of the frame entry points (process_frames*, process_data*): 0 = one fused kernel per batch, 1 = a parameter
  * kernel (ECC, decode, state machine, enhancement) that leaves a descriptor per frame + a synthesis kernel (oscillator
- * bank, FFT / overlap-add, PCM) - DESIGN 4.5.  Results are bit-identical; the default comes from the build
- * (MBE_B200_SPLIT in the environment overrides it).  kernel_path() returns the current setting. */
+ * bank, FFT / overlap-add, PCM: a bank kernel and an unvoiced kernel) - DESIGN 4.5.  Results are bit-identical; the
+ * default is 1 (MBE_B200_SPLIT in the environment overrides it).  kernel_path() returns the current setting. */
 MBE_B200_API int mbe_b200_set_kernel_path(mbe_b200_ctx* ctx, int path);
 MBE_B200_API int mbe_b200_kernel_path(const mbe_b200_ctx* ctx);
+/* Measurement aid (bench.py): while enabled, every launch of the frame kernels is bracketed by a CUDA event pair on the
+ * stream it runs on.  kernel_timing() synchronises and returns, per kernel kind (0 parameter or fused kernel, 1 bank
+ * kernel, 2 unvoiced kernel), the summed device time in ms and the launch count since timing was enabled, plus the bank
+ * kernel's work counters: [0] oscillator slots run (160 samples each), [1] of them phase-interpolated harmonics,
+ * [2] frames synthesised. */
+MBE_B200_API int mbe_b200_set_kernel_timing(mbe_b200_ctx* ctx, int enable);
+MBE_B200_API int mbe_b200_kernel_timing(mbe_b200_ctx* ctx, double ms[3], long long launches[3], unsigned long long counters[4]);
 
 /* ---- stream state ---------------------------------------------------------------------------
  * init_streams == per stream: mbe_setThreadRngSeed(seed) (mbelib.h:596; seeds==NULL: fresh-thread

@@ -40,7 +40,7 @@ _EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b
             "mbe_b200_device_count", "mbe_b200_pool_create", "mbe_b200_pool_destroy", "mbe_b200_pool_last_error",
             "mbe_b200_pool_shards", "mbe_b200_pool_shard", "mbe_b200_pool_init_streams", "mbe_b200_pool_export_state",
             "mbe_b200_pool_import_state", "mbe_b200_pool_process_frames", "mbe_b200_pool_process_frames_packed",
-            "mbe_b200_set_kernel_path", "mbe_b200_kernel_path"]
+            "mbe_b200_set_kernel_path", "mbe_b200_kernel_path", "mbe_b200_set_kernel_timing", "mbe_b200_kernel_timing"]
 
 _lib = None
 
@@ -81,6 +81,8 @@ def load_library():
         lib.mbe_b200_set_normalized_float.argtypes = [vp, ci]
         lib.mbe_b200_set_kernel_path.argtypes = [vp, ci]
         lib.mbe_b200_kernel_path.argtypes = [vp]
+        lib.mbe_b200_set_kernel_timing.argtypes = [vp, ci]
+        lib.mbe_b200_kernel_timing.argtypes = [vp, vp, vp, vp]
         lib.mbe_b200_packed_frame_bytes.argtypes = [ci]
         lib.mbe_b200_pipeline_plan.argtypes = [ci, ctypes.POINTER(ci), ci]
         lib.mbe_b200_process_frames_packed_dev.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
@@ -321,6 +323,19 @@ class Decoder:
 
     def kernel_path(self):
         return int(self.lib.mbe_b200_kernel_path(self.h))
+
+    def set_kernel_timing(self, enable):
+        self._check(self.lib.mbe_b200_set_kernel_timing(self.h, int(bool(enable))), "set_kernel_timing")
+
+    def kernel_timing(self):
+        """{kind: (ms, launches)} for kinds parameter / bank / unvoiced, and the bank kernel's work counters."""
+        ms = np.zeros(3, np.float64)
+        n = np.zeros(3, np.int64)
+        cnt = np.zeros(4, np.uint64)
+        self._check(self.lib.mbe_b200_kernel_timing(self.h, _p(ms), _p(n), _p(cnt)), "kernel_timing")
+        names = ("parameter", "bank", "unvoiced")
+        return ({names[i]: (float(ms[i]), int(n[i])) for i in range(3)},
+                dict(slots=int(cnt[0]), interpolated=int(cnt[1]), frames=int(cnt[2])))
 
     def set_normalized_float(self, enable):
         self._check(self.lib.mbe_b200_set_normalized_float(self.h, int(bool(enable))), "set_normalized_float")

@@ -40,7 +40,7 @@ namespace hosttab {
 #include "mbe_split.cuh"
 
 #ifndef MBE_SPLIT_DEFAULT
-#define MBE_SPLIT_DEFAULT 0
+#define MBE_SPLIT_DEFAULT 1
 #endif
 #ifndef MBE_TOP_BARRIER
 #define MBE_TOP_BARRIER 1
@@ -1292,6 +1292,7 @@ using namespace mbe;
 // the host-pointer entry points cut a batch into up to MAX_CHUNKS stream ranges and pipeline them
 constexpr int MAX_CHUNKS = 64;
 constexpr int MAX_KSTREAMS = 4;
+constexpr int KT_MAX = 8192;                        // launches a timing session can hold
 constexpr int MAX_AUX = 4;                          // internal streams of a two-kernel-path launch on a caller's stream
 constexpr int DESC_SLOTS = MAX_KSTREAMS + MAX_AUX;  // descriptor buffers: one per pipeline compute stream, one per internal stream
 
@@ -1326,6 +1327,11 @@ struct mbe_b200_ctx {
     // while the bank / unvoiced kernels of the previous ones do (slots MAX_KSTREAMS.. of d_desc)
     cudaStream_t s_aux[MAX_AUX];
     cudaEvent_t ev_fork, ev_join[MAX_AUX];
+    // per-kernel device time (mbe_b200_set_kernel_timing): an event pair around every launch of the frame kernels
+    int kt_on, kt_n;
+    cudaEvent_t* kt_ev;               // [2 * KT_MAX]
+    unsigned char* kt_kind;           // [KT_MAX]: 0 parameter (or fused) kernel, 1 bank kernel, 2 unvoiced kernel
+    unsigned long long* d_cnt;        // [4] device counters of the bank kernel
     char err[256];
 };
 
@@ -1746,13 +1752,18 @@ int mbe_b200_create(mbe_b200_ctx** out, int device_ordinal, int max_streams) {
         CUC(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
     }
     CUC(cudaMalloc(&ctx->d_tab, sizeof(DevTables)));
-    CUC(cudaMemcpy(ctx->d_tab, ht, sizeof(DevTables), cudaMemcpyHostToDevice));
+    // stream-ordered: a plain cudaMemcpy from pageable memory may return before its DMA has landed, and the context's
+    // streams are non-blocking (no implicit ordering with the NULL stream) - the table kernel would race the upload and a
+    // late DMA chunk would wipe the rows it wrote (seen as rare PCM mismatches with many contexts on one GPU)
+    CUC(cudaMemcpyAsync(ctx->d_tab, ht, sizeof(DevTables), cudaMemcpyHostToDevice, ctx->stream));
+    CUC(cudaStreamSynchronize(ctx->stream));
     mbe_costab_kernel<<<(COSW_ROWS + 63) / 64, 64, 0, ctx->stream>>>(ctx->d_tab);
     CUC(cudaGetLastError());
     CUC(cudaStreamSynchronize(ctx->stream));
     CUC(cudaMalloc(&ctx->d_state, (size_t)max_streams * STATE_WORDS * sizeof(uint32_t)));
     CUC(cudaMalloc(&ctx->d_dbg, 16 * sizeof(unsigned long long)));
-    CUC(cudaMemset(ctx->d_dbg, 0, 16 * sizeof(unsigned long long)));
+    CUC(cudaMemsetAsync(ctx->d_dbg, 0, 16 * sizeof(unsigned long long), ctx->stream));
+    CUC(cudaStreamSynchronize(ctx->stream));
     for (int codec = 0; codec < 4; ++codec) {
         for (int soft = 0; soft < 3; ++soft) {
             for (int mode = 0; mode < (soft == 2 ? 1 : 2); ++mode) {
@@ -1838,6 +1849,16 @@ void mbe_b200_destroy(mbe_b200_ctx* ctx) {
         }
         cudaFree(ctx->d_desc[i]);
     }
+    if (ctx->kt_ev) {
+        for (int i = 0; i < 2 * KT_MAX; ++i) {
+            if (ctx->kt_ev[i]) {
+                cudaEventDestroy(ctx->kt_ev[i]);
+            }
+        }
+        free(ctx->kt_ev);
+    }
+    free(ctx->kt_kind);
+    cudaFree(ctx->d_cnt);
     cudaFree(ctx->d_state);
     cudaFree(ctx->d_dbg);
     cudaFree(ctx->d_tab);
@@ -1857,6 +1878,7 @@ int mbe_b200_debug_stage_cycles(mbe_b200_ctx* ctx, unsigned long long* out16, in
     CU(cudaMemcpy(out16, ctx->d_dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     if (reset) {
         CU(cudaMemset(ctx->d_dbg, 0, 16 * sizeof(unsigned long long)));
+        CU(cudaDeviceSynchronize());
     }
     return 0;
 }
@@ -1971,6 +1993,25 @@ int mbe_b200_import_rng(mbe_b200_ctx* ctx, int first, int count, const uint32_t*
     return state_xfer(ctx, first, count, const_cast<uint32_t*>(rng_words4), RNG_WORDS, 3 * PARMS_WORDS, 0);
 }
 
+// event pair around one kernel launch when a timing session is on (kind: 0 parameter / fused, 1 bank, 2 unvoiced)
+struct KernelTimer {
+    mbe_b200_ctx* ctx;
+    cudaStream_t st;
+    int slot;
+    KernelTimer(mbe_b200_ctx* c, int kind, cudaStream_t s) : ctx(c), st(s), slot(-1) {
+        if (c->kt_on && c->kt_ev && c->kt_n < KT_MAX) {
+            slot = c->kt_n++;
+            c->kt_kind[slot] = (unsigned char)kind;
+            cudaEventRecord(c->kt_ev[2 * slot], s);
+        }
+    }
+    ~KernelTimer() {
+        if (slot >= 0) {
+            cudaEventRecord(ctx->kt_ev[2 * slot + 1], st);
+        }
+    }
+};
+
 static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaStream_t st) {
     LaunchArgs a = a_in;
     a.pcmf_scale = ctx->normalized_float ? (7.0f / 32768.0f) : 1.0f;
@@ -1984,7 +2025,10 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaS
     }
     if (!ctx->split) {
         const int blocks = (a.n_streams + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-        pick_stream_kernel(a.codec, a.soft, a.mode)<<<blocks, WARPS_PER_BLOCK * 32, stream_kernel_smem(), st>>>(a);
+        {
+            KernelTimer kt(ctx, 0, st);
+            pick_stream_kernel(a.codec, a.soft, a.mode)<<<blocks, WARPS_PER_BLOCK * 32, stream_kernel_smem(), st>>>(a);
+        }
         ctx->launches++;
         CU(cudaGetLastError());
         return 0;
@@ -2039,7 +2083,10 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaS
         a.io_base = a_in.io_base + o;
         a.n_streams = ns;
         a.desc = (uint32_t*)ctx->d_desc[slot];
-        pk<<<(ns + pw - 1) / pw, pw * 32, parm_kernel_smem(a.soft), ss>>>(a);
+        {
+            KernelTimer kt(ctx, 0, ss);
+            pk<<<(ns + pw - 1) / pw, pw * 32, parm_kernel_smem(a.soft), ss>>>(a);
+        }
         ctx->launches++;
         CU(cudaGetLastError());
         SynthArgs sa;
@@ -2053,16 +2100,23 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaS
         sa.pcmf_scale = a.pcmf_scale;
         sa.state = a.state;
         sa.tab = a.tab;
+        sa.counters = ctx->kt_on ? ctx->d_cnt : nullptr;
         const long long groups = ((long long)ns * a.n_frames + BG - 1) / BG;
         long long bank_blocks = (groups + B_WARPS - 1) / B_WARPS;
         const long long resident = (long long)g_sm_count.load() * B_MINB;   // grid-stride warps: one resident wave is enough
         if (bank_blocks > resident) {
             bank_blocks = resident;
         }
-        mbe_split_bank_kernel<<<(unsigned)bank_blocks, B_WARPS * 32, bank_kernel_smem(), ss>>>(sa);
+        {
+            KernelTimer kt(ctx, 1, ss);
+            mbe_split_bank_kernel<<<(unsigned)bank_blocks, B_WARPS * 32, bank_kernel_smem(), ss>>>(sa);
+        }
         ctx->launches++;
         CU(cudaGetLastError());
-        mbe_split_unvoiced_kernel<<<(ns + U_WARPS - 1) / U_WARPS, U_WARPS * 32, unvoiced_kernel_smem(), ss>>>(sa);
+        {
+            KernelTimer kt(ctx, 2, ss);
+            mbe_split_unvoiced_kernel<<<(ns + U_WARPS - 1) / U_WARPS, U_WARPS * 32, unvoiced_kernel_smem(), ss>>>(sa);
+        }
         ctx->launches++;
         CU(cudaGetLastError());
         CU(cudaEventRecord(ctx->ev_desc[slot], ss));
@@ -2089,6 +2143,59 @@ int mbe_b200_set_kernel_path(mbe_b200_ctx* ctx, int path) {
 }
 
 int mbe_b200_kernel_path(const mbe_b200_ctx* ctx) { return ctx ? ctx->split : MBE_B200_E_ARG; }
+
+int mbe_b200_set_kernel_timing(mbe_b200_ctx* ctx, int enable) {
+    if (!ctx) {
+        return MBE_B200_E_ARG;
+    }
+    CU(cudaSetDevice(ctx->device));
+    if (enable && !ctx->kt_ev) {
+        ctx->kt_ev = (cudaEvent_t*)calloc(2 * KT_MAX, sizeof(cudaEvent_t));
+        ctx->kt_kind = (unsigned char*)calloc(KT_MAX, 1);
+        if (!ctx->kt_ev || !ctx->kt_kind) {
+            return fail(ctx, MBE_B200_E_ARG, "set_kernel_timing: out of host memory", cudaSuccess);
+        }
+        for (int i = 0; i < 2 * KT_MAX; ++i) {
+            CU(cudaEventCreate(&ctx->kt_ev[i]));
+        }
+        CU(cudaMalloc(&ctx->d_cnt, 4 * sizeof(unsigned long long)));
+    }
+    if (enable) {
+        CU(cudaDeviceSynchronize());
+        CU(cudaMemsetAsync(ctx->d_cnt, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->kt_n = 0;
+    }
+    ctx->kt_on = enable ? 1 : 0;
+    return 0;
+}
+
+int mbe_b200_kernel_timing(mbe_b200_ctx* ctx, double ms[3], long long launches[3], unsigned long long counters[4]) {
+    if (!ctx || !ms || !launches || !counters) {
+        return MBE_B200_E_ARG;
+    }
+    for (int i = 0; i < 3; ++i) {
+        ms[i] = 0.0;
+        launches[i] = 0;
+    }
+    for (int i = 0; i < 4; ++i) {
+        counters[i] = 0;
+    }
+    if (!ctx->kt_ev) {
+        return 0;
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    for (int i = 0; i < ctx->kt_n; ++i) {
+        float t = 0.0f;
+        CU(cudaEventElapsedTime(&t, ctx->kt_ev[2 * i], ctx->kt_ev[2 * i + 1]));
+        const int k = ctx->kt_kind[i] < 3 ? ctx->kt_kind[i] : 0;
+        ms[k] += (double)t;
+        launches[k]++;
+    }
+    CU(cudaMemcpy(counters, ctx->d_cnt, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
 
 // input kinds of the frame entry points: 0 = one byte per hard bit, 1 = mbe_soft_bit pairs, 2 = hard bits packed
 static int frames_dev_impl(mbe_b200_ctx* ctx, int codec, int kind, int first_stream, int n_streams, int n_frames,
@@ -2151,7 +2258,8 @@ int mbe_b200_set_channel_map(mbe_b200_ctx* ctx, int codec, const uint16_t* map, 
     }
     CU(cudaSetDevice(ctx->device));
     CU(cudaDeviceSynchronize());  // configuration call: no launch of this device may still be reading the old map
-    CU(cudaMemcpy(&ctx->d_tab->chan_src[codec][0], src, sizeof(src), cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(&ctx->d_tab->chan_src[codec][0], src, sizeof(src), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // (the pipeline streams are non-blocking: the upload must have landed)
     ctx->chan_bits[codec] = n_bits;
     return 0;
 }

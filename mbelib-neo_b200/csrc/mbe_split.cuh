@@ -47,7 +47,7 @@ constexpr int DESC_WORDS = 768;
 static_assert(D_SD + 112 <= DESC_WORDS && D_VOICED + NS <= D_S, "descriptor layout");
 
 #ifndef MBE_BG
-#define MBE_BG 4
+#define MBE_BG 3
 #endif
 #ifndef MBE_BWARPS
 #define MBE_BWARPS 8
@@ -234,6 +234,8 @@ struct SynthArgs {
     float pcmf_scale;
     uint32_t* state;        // [max_streams][STATE_WORDS]: only the previousUw words are touched
     const DevTables* tab;
+    unsigned long long* counters;   // profiling (may be null): [0] oscillator slots run, [1] of them interpolated harmonics,
+                                    // [2] frames synthesised
 };
 
 // Oscillator tile of the bank kernel: 32 samples x 32 slots, rows padded to 36 words: phase A (lane = slot, one row per
@@ -302,6 +304,7 @@ __global__ void __launch_bounds__(B_WARPS * 32, B_MINB) mbe_split_bank_kernel(co
             }
         }
 
+        int n_k2 = 0;   // interpolated harmonics of the group (profiling counter)
 #pragma unroll 1
         for (int base = 0; base < total; base += 32) {
             const int k = base + lane;
@@ -336,6 +339,7 @@ __global__ void __launch_bounds__(B_WARPS * 32, B_MINB) mbe_split_bank_kernel(co
             }
             const bool k2lane = (kind == 2);
             const unsigned k2mask = __ballot_sync(FULL, k2lane);
+            n_k2 += __popc(k2mask);
             const float* Wb = vwin + ((kind == 0) ? WIN_PREV : 0);
             const float gg = k2lane ? 0.0f : g;   // interpolated slots are written by whoever renders them
             const float rec_c = c, rec_s = s;     // (the recurrence below rotates c and s on every lane)
@@ -421,6 +425,16 @@ __global__ void __launch_bounds__(B_WARPS * 32, B_MINB) mbe_split_bank_kernel(co
                 }
                 __syncwarp();
             }
+        }
+        if (A.counters && lane == 0) {
+            int slots = 0;
+#pragma unroll
+            for (int q = 0; q < BG; ++q) {
+                slots += cnt[q];
+            }
+            atomicAdd(&A.counters[0], (unsigned long long)slots);
+            atomicAdd(&A.counters[1], (unsigned long long)n_k2);
+            atomicAdd(&A.counters[2], (unsigned long long)__popc(go_mask));
         }
         // the frames' voiced samples replace their (now dead) slot records
 #pragma unroll
