@@ -8,7 +8,10 @@
  * Build (host C only):
  *     gcc -std=c99 -O2 -Iinclude examples/mbe_pool_demo.c -Lmbelib-neo_b200 -lmbe_b200 \
  *         -Wl,-rpath,'$ORIGIN/../mbelib-neo_b200' -o examples/mbe_pool_demo
- * Run:  examples/mbe_pool_demo [streams=262144] [frames=50] [devices=0 (all)]
+ * Run:  examples/mbe_pool_demo [streams=262144] [frames=50] [devices=0 (all)] [pageable]
+ *
+ * The frame and PCM arrays come from mbe_b200_host_alloc (page-locked, portable across the pool's devices): the caller does
+ * not link the CUDA runtime.  A fourth argument "pageable" uses malloc instead, to show what that costs.
  */
 #define _POSIX_C_SOURCE 199309L
 #include <stdio.h>
@@ -35,6 +38,7 @@ int main(int argc, char** argv) {
     const int S = argc > 1 ? atoi(argv[1]) : 262144;
     const int F = argc > 2 ? atoi(argv[2]) : 50;
     const int ndev = argc > 3 ? atoi(argv[3]) : 0;
+    const int pageable = argc > 4 && strcmp(argv[4], "pageable") == 0;
     const int codec = MBE_B200_AMBE3600X2450;
     const size_t fbytes = (size_t)mbe_b200_packed_frame_bytes(codec);
 
@@ -44,8 +48,16 @@ int main(int argc, char** argv) {
         fprintf(stderr, "mbe_b200_pool_create: %s\n", mbe_b200_pool_last_error(NULL));
         return 1; /* no GPU, no decode: there is no CPU fallback */
     }
-    uint8_t* frames = (uint8_t*)malloc((size_t)S * F * fbytes);
-    int16_t* pcm = (int16_t*)malloc((size_t)S * F * MBE_B200_SAMPLES_PER_FRAME * sizeof(int16_t));
+    const size_t frame_bytes = (size_t)S * F * fbytes, pcm_bytes = (size_t)S * F * MBE_B200_SAMPLES_PER_FRAME * sizeof(int16_t);
+    uint8_t* frames = NULL;
+    int16_t* pcm = NULL;
+    if (pageable) {
+        frames = (uint8_t*)malloc(frame_bytes);
+        pcm = (int16_t*)malloc(pcm_bytes);
+    } else if (mbe_b200_host_alloc((void**)&frames, frame_bytes) != 0 || mbe_b200_host_alloc((void**)&pcm, pcm_bytes) != 0) {
+        fprintf(stderr, "mbe_b200_host_alloc: %s\n", mbe_b200_last_error(NULL));
+        return 1;
+    }
     uint32_t* seeds = (uint32_t*)malloc((size_t)S * sizeof(uint32_t));
     if (!frames || !pcm || !seeds) {
         fprintf(stderr, "out of host memory\n");
@@ -83,11 +95,18 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < (size_t)S * F * MBE_B200_SAMPLES_PER_FRAME * sizeof(int16_t); ++i) {
         h = (h ^ b[i]) * 16777619u;
     }
-    printf("{\"shards\": %d, \"streams\": %d, \"frames\": %d, \"seconds\": %.4f, \"frames_per_s\": %.4g, \"pcm_fnv1a32\": \"%08x\"}\n",
-           mbe_b200_pool_shards(pool), S, F, best, (double)S * F / best, h);
+    printf("{\"shards\": %d, \"streams\": %d, \"frames\": %d, \"host_memory\": \"%s\", \"seconds\": %.4f, \"frames_per_s\": %.4g, "
+           "\"pcm_fnv1a32\": \"%08x\"}\n",
+           mbe_b200_pool_shards(pool), S, F, pageable ? "pageable (malloc)" : "pinned (mbe_b200_host_alloc)", best,
+           (double)S * F / best, h);
     mbe_b200_pool_destroy(pool);
-    free(frames);
-    free(pcm);
+    if (pageable) {
+        free(frames);
+        free(pcm);
+    } else {
+        mbe_b200_host_free(frames);
+        mbe_b200_host_free(pcm);
+    }
     free(seeds);
     return 0;
 }

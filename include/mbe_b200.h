@@ -76,6 +76,15 @@ MBE_B200_API const char* mbe_b200_last_error(const mbe_b200_ctx* ctx); /* ctx ma
 MBE_B200_API const char* mbe_b200_version(void);
 MBE_B200_API int mbe_b200_geometry(int codec, int* frame_bits, int* param_bits); /* 184/168/96/96, 88/88/49/49 */
 MBE_B200_API int mbe_b200_device_count(void); /* usable CUDA devices (0 when there is none or the driver is missing) */
+/* Pinned (page-locked) host memory.  The reference's contract is "the caller owns every buffer" (mbelib.h:28-30); the
+ * host-pointer entry points below accept any host pointer, but only page-locked buffers move at full link speed and overlap
+ * with the kernels (a pageable 1 GB PCM buffer costs 3x on one GPU).  A plain-C caller that does not link the CUDA runtime
+ * allocates its frame / PCM / result arrays here, or registers arrays it already owns.  Portable: valid for every device
+ * of the process (mbe_b200_pool_*).  No context needed; errors: mbe_b200_last_error(NULL). */
+MBE_B200_API int mbe_b200_host_alloc(void** out, size_t bytes);
+MBE_B200_API int mbe_b200_host_free(void* p);
+MBE_B200_API int mbe_b200_host_register(void* p, size_t bytes);
+MBE_B200_API int mbe_b200_host_unregister(void* p);
 /* kernel launches issued by this context so far (bench.py reports it as gpu_launches) */
 MBE_B200_API long long mbe_b200_launch_count(const mbe_b200_ctx* ctx);
 /* Kernel path of the frame entry points (process_frames*, process_data*): 0 = one fused kernel per batch, 1 = a parameter

@@ -40,7 +40,8 @@ _EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b
             "mbe_b200_device_count", "mbe_b200_pool_create", "mbe_b200_pool_destroy", "mbe_b200_pool_last_error",
             "mbe_b200_pool_shards", "mbe_b200_pool_shard", "mbe_b200_pool_init_streams", "mbe_b200_pool_export_state",
             "mbe_b200_pool_import_state", "mbe_b200_pool_process_frames", "mbe_b200_pool_process_frames_packed",
-            "mbe_b200_set_kernel_path", "mbe_b200_kernel_path", "mbe_b200_set_kernel_timing", "mbe_b200_kernel_timing"]
+            "mbe_b200_set_kernel_path", "mbe_b200_kernel_path", "mbe_b200_set_kernel_timing", "mbe_b200_kernel_timing",
+            "mbe_b200_host_alloc", "mbe_b200_host_free", "mbe_b200_host_register", "mbe_b200_host_unregister"]
 
 _lib = None
 
@@ -82,6 +83,10 @@ def load_library():
         lib.mbe_b200_set_kernel_path.argtypes = [vp, ci]
         lib.mbe_b200_kernel_path.argtypes = [vp]
         lib.mbe_b200_set_kernel_timing.argtypes = [vp, ci]
+        lib.mbe_b200_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+        lib.mbe_b200_host_free.argtypes = [vp]
+        lib.mbe_b200_host_register.argtypes = [vp, ctypes.c_size_t]
+        lib.mbe_b200_host_unregister.argtypes = [vp]
         lib.mbe_b200_kernel_timing.argtypes = [vp, vp, vp, vp]
         lib.mbe_b200_packed_frame_bytes.argtypes = [ci]
         lib.mbe_b200_pipeline_plan.argtypes = [ci, ctypes.POINTER(ci), ci]
@@ -142,6 +147,31 @@ def _p(a):
     if isinstance(a, int):
         return ctypes.c_void_p(a)
     return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def host_alloc(shape, dtype):
+    """numpy array in page-locked host memory from mbe_b200_host_alloc (freed with host_free(array))."""
+    lib = load_library()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = ctypes.c_void_p()
+    rc = lib.mbe_b200_host_alloc(ctypes.byref(p), max(n, 1))
+    if rc != 0:
+        raise MbeB200Error("mbe_b200_host_alloc failed (%d): %s" % (rc, lib.mbe_b200_last_error(None).decode()))
+    buf = (ctypes.c_uint8 * max(n, 1)).from_address(p.value)
+    a = np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
+    a.flags.writeable = True
+    _pinned[a.__array_interface__["data"][0]] = p.value
+    return a
+
+
+_pinned = {}
+
+
+def host_free(a):
+    lib = load_library()
+    p = _pinned.pop(a.__array_interface__["data"][0], None)
+    if p is not None:
+        lib.mbe_b200_host_free(ctypes.c_void_p(p))
 
 
 class Pool:

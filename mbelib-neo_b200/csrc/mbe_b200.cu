@@ -1681,6 +1681,46 @@ int mbe_b200_device_count(void) {
     return n;
 }
 
+// ---- pinned host memory for plain-C callers (no CUDA runtime on their side) -------------------------------------------
+static int host_fail(const char* what, cudaError_t ce) {
+    snprintf(g_create_err, sizeof(g_create_err), "%s: %s", what, cudaGetErrorString(ce));
+    cudaGetLastError();
+    return (ce == cudaErrorNoDevice || ce == cudaErrorInsufficientDriver) ? MBE_B200_E_NOGPU : MBE_B200_E_CUDA;
+}
+
+int mbe_b200_host_alloc(void** out, size_t bytes) {
+    if (!out || bytes == 0) {
+        return MBE_B200_E_ARG;
+    }
+    *out = nullptr;
+    const cudaError_t ce = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    return ce == cudaSuccess ? 0 : host_fail("mbe_b200_host_alloc", ce);
+}
+
+int mbe_b200_host_free(void* p) {
+    if (!p) {
+        return 0;
+    }
+    const cudaError_t ce = cudaFreeHost(p);
+    return ce == cudaSuccess ? 0 : host_fail("mbe_b200_host_free", ce);
+}
+
+int mbe_b200_host_register(void* p, size_t bytes) {
+    if (!p || bytes == 0) {
+        return MBE_B200_E_ARG;
+    }
+    const cudaError_t ce = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    return ce == cudaSuccess ? 0 : host_fail("mbe_b200_host_register", ce);
+}
+
+int mbe_b200_host_unregister(void* p) {
+    if (!p) {
+        return 0;
+    }
+    const cudaError_t ce = cudaHostUnregister(p);
+    return ce == cudaSuccess ? 0 : host_fail("mbe_b200_host_unregister", ce);
+}
+
 int mbe_b200_geometry(int codec, int* frame_bits, int* param_bits) {
     if (codec < 0 || codec > 3) {
         return MBE_B200_E_ARG;

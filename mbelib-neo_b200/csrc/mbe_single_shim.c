@@ -6,7 +6,14 @@
  *
  * State mapping per call: {cur_mp, prev_mp, prev_mp_enhanced} -> stream slot 0 (mbe_b200_import_state), the calling
  * thread's RNG words (the reference's thread-locals, src/core/mbe_adaptive.c:29-30, src/core/mbe_unvoiced_fft.c:29-30)
- * -> mbe_b200_import_rng; one frame; both exported back.  One process-wide context guarded by a mutex.
+ * -> mbe_b200_import_rng; one frame; both exported back.
+ *
+ * Re-entrancy (mbelib.h:28-30: "re-entrant per stream, the caller owns every buffer"): every calling thread gets its OWN
+ * context (one stream slot, own CUDA streams), created on first use and destroyed when the thread exits - no lock is held
+ * around a call, threads decode side by side.
+ * Failure (no CUDA device, a CUDA error): never abort().  The reference's int functions report MBE_STATUS_INVALID_ARGUMENT,
+ * its void helpers leave silence / their arguments untouched (mbelib.c:1048-1055); the shim does the same and says why on
+ * stderr once per thread.
  */
 #include <pthread.h>
 #include <stdio.h>
@@ -18,34 +25,56 @@
 
 #define NSAMP 160
 
-static mbe_b200_ctx* g_ctx;
-static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static __thread mbe_b200_ctx* t_ctx;
+static __thread int t_ctx_tried;   /* creation failed once: do not retry (and do not repeat the message) on every frame */
+static __thread int t_failed;      /* a C-ABI call of the current shim call failed */
+static __thread int t_warned;
 static __thread uint32_t t_rng[4];
 static __thread int t_rng_ready;
+static pthread_key_t g_key;
+static pthread_once_t g_key_once = PTHREAD_ONCE_INIT;
 
-/* the shared context, created on first use; no GPU = no product path: say so and stop */
-static mbe_b200_ctx* ctx_locked(void) {
-    if (!g_ctx) {
+static void ctx_destructor(void* p) { mbe_b200_destroy((mbe_b200_ctx*)p); }
+static void key_make(void) { pthread_key_create(&g_key, ctx_destructor); }
+
+/* the calling thread's context, created on first use; NULL (and t_failed set) when there is no usable GPU: the product has
+ * no CPU path, so the call then fails the way the reference's argument checks fail */
+static mbe_b200_ctx* shim_ctx(void) {
+    t_failed = 0;
+    if (!t_ctx && !t_ctx_tried) {
+        t_ctx_tried = 1;
         const char* dev = getenv("MBE_B200_DEVICE");
-        const int rc = mbe_b200_create(&g_ctx, dev ? atoi(dev) : 0, 1);
+        const int rc = mbe_b200_create(&t_ctx, dev ? atoi(dev) : 0, 1);
         if (rc != 0) {
-            fprintf(stderr, "libmbe-neo-b200shim: mbe_b200_create failed (%d): %s - there is no CPU fallback\n", rc,
-                    mbe_b200_last_error(NULL));
-            abort();
+            fprintf(stderr, "libmbe-neo-b200shim: mbe_b200_create failed (%d): %s - there is no CPU fallback; calls on this "
+                            "thread return MBE_STATUS_INVALID_ARGUMENT / silence\n", rc, mbe_b200_last_error(NULL));
+            t_ctx = NULL;
+        } else {
+            pthread_once(&g_key_once, key_make);
+            pthread_setspecific(g_key, t_ctx);
         }
     }
-    return g_ctx;
+    if (!t_ctx) {
+        t_failed = 1;
+    }
+    return t_ctx;
 }
 
-static void die(mbe_b200_ctx* c, const char* what, int rc) {
-    fprintf(stderr, "libmbe-neo-b200shim: %s failed (%d): %s\n", what, rc, mbe_b200_last_error(c));
-    abort();
+static void note_failure(mbe_b200_ctx* c, const char* what, int rc) {
+    t_failed = 1;
+    if (!t_warned) {
+        t_warned = 1;
+        fprintf(stderr, "libmbe-neo-b200shim: %s failed (%d): %s\n", what, rc, mbe_b200_last_error(c));
+    }
 }
+/* one C-ABI call; skipped once an earlier call of the same shim call has failed */
 #define CK(call)                                                                                                      \
     do {                                                                                                              \
-        const int rc_ = (call);                                                                                       \
-        if (rc_ != 0) {                                                                                               \
-            die(c, #call, rc_);                                                                                       \
+        if (!t_failed) {                                                                                              \
+            const int rc_ = (call);                                                                                   \
+            if (rc_ != 0) {                                                                                           \
+                note_failure(c, #call, rc_);                                                                          \
+            }                                                                                                         \
         }                                                                                                             \
     } while (0)
 
@@ -54,7 +83,7 @@ static void rng_ready_locked(mbe_b200_ctx* c) {
     if (!t_rng_ready) {
         CK(mbe_b200_init_streams(c, 0, 1, NULL));
         CK(mbe_b200_export_rng(c, 0, 1, t_rng));
-        t_rng_ready = 1;
+        t_rng_ready = !t_failed;
     }
 }
 
@@ -160,12 +189,12 @@ void mbe_synthesizeSilence(short* aout_buf) { /* mbelib.c:874-880 */
 
 /* ---- state ------------------------------------------------------------------------------------------------- */
 void mbe_setThreadRngSeed(uint32_t seed) { /* mbelib.c:173-181: the device derives both generators from the seed */
-    pthread_mutex_lock(&g_mu);
-    mbe_b200_ctx* c = ctx_locked();
+    mbe_b200_ctx* c = shim_ctx();
     CK(mbe_b200_init_streams(c, 0, 1, &seed));
     CK(mbe_b200_export_rng(c, 0, 1, t_rng));
-    t_rng_ready = 1;
-    pthread_mutex_unlock(&g_mu);
+    if (!t_failed) {
+        t_rng_ready = 1;
+    }
 }
 
 void mbe_initMbeParms(mbe_parms* cur_mp, mbe_parms* prev_mp, mbe_parms* prev_mp_enhanced) { /* mbelib.c:367-410 */
@@ -173,12 +202,13 @@ void mbe_initMbeParms(mbe_parms* cur_mp, mbe_parms* prev_mp, mbe_parms* prev_mp_
         return;
     }
     mbe_parms t[3];
-    pthread_mutex_lock(&g_mu);
-    mbe_b200_ctx* c = ctx_locked();
+    mbe_b200_ctx* c = shim_ctx();
     rng_ready_locked(c);  /* (before the slot is reset, so a fresh thread's defaults are captured once) */
     CK(mbe_b200_init_streams(c, 0, 1, NULL));
     CK(mbe_b200_export_state(c, 0, 1, t));
-    pthread_mutex_unlock(&g_mu);
+    if (t_failed) {
+        return;   /* the caller's structs stay as they were */
+    }
     *cur_mp = t[0];
     *prev_mp = t[1];
     *prev_mp_enhanced = t[2];
@@ -209,6 +239,9 @@ static void slot_out(mbe_b200_ctx* c, mbe_parms* cur, mbe_parms* prev, mbe_parms
     mbe_parms t[3];
     CK(mbe_b200_export_state(c, 0, 1, t));
     CK(mbe_b200_export_rng(c, 0, 1, t_rng));
+    if (t_failed) {
+        return;
+    }
     *cur = t[0];
     *prev = t[1];
     *enh = t[2];
@@ -224,10 +257,12 @@ static int shim_decode(int codec, int soft, const void* fr, char* d, mbe_process
     }
     uint8_t bits[88];
     mbe_b200_result r;
-    pthread_mutex_lock(&g_mu);
-    mbe_b200_ctx* c = ctx_locked();
+    mbe_b200_ctx* c = shim_ctx();
+    memset(&r, 0, sizeof(r));
     CK(mbe_b200_decode_frames(c, codec, soft, 1, (const uint8_t*)fr, bits, &r));
-    pthread_mutex_unlock(&g_mu);
+    if (t_failed) {
+        return MBE_STATUS_INVALID_ARGUMENT;
+    }
     if (r.status < 0) {
         return r.status;
     }
@@ -257,15 +292,17 @@ static int shim_frame(int codec, int soft, float* outf, short* outs, int want_sh
     float pf[NSAMP];
     int16_t ps[NSAMP];
     mbe_b200_result r;
-    pthread_mutex_lock(&g_mu);
-    mbe_b200_ctx* c = ctx_locked();
+    memset(&r, 0, sizeof(r));
+    mbe_b200_ctx* c = shim_ctx();
     slot_in(c, cur, prev, enh);
     CK(mbe_b200_process_frames(c, codec, soft, 0, 1, 1, (const uint8_t*)fr, want_short ? ps : NULL, want_short ? NULL : pf,
                                &r, bits));
-    if (r.status >= 0) {
+    if (!t_failed && r.status >= 0) {
         slot_out(c, cur, prev, enh);
     }
-    pthread_mutex_unlock(&g_mu);
+    if (t_failed) {
+        return MBE_STATUS_INVALID_ARGUMENT;  /* device failure: outputs and state untouched */
+    }
     if (r.status < 0) {
         return r.status;  /* nothing but the (reset) result has been touched, like the reference's early return */
     }
@@ -301,14 +338,15 @@ static int shim_data(int codec, float* outf, short* outs, int want_short, mbe_pr
     }
     float pf[NSAMP];
     int16_t ps[NSAMP];
-    pthread_mutex_lock(&g_mu);
-    mbe_b200_ctx* c = ctx_locked();
+    mbe_b200_ctx* c = shim_ctx();
     slot_in(c, cur, prev, enh);
     CK(mbe_b200_process_data(c, codec, 0, 1, 1, (const uint8_t*)d, &r, want_short ? ps : NULL, want_short ? NULL : pf));
-    if (r.status >= 0) {
+    if (!t_failed && r.status >= 0) {
         slot_out(c, cur, prev, enh);
     }
-    pthread_mutex_unlock(&g_mu);
+    if (t_failed) {
+        return MBE_STATUS_INVALID_ARGUMENT;
+    }
     if (r.status < 0) {
         return r.status;
     }
@@ -372,11 +410,9 @@ static int shim_decode_parms(int codec, const char* d, mbe_parms* cur, mbe_parms
         return MBE_STATUS_INVALID_ARGUMENT;  /* imbe7200x4400.c:596-602: state pointers, then the bit array */
     }
     int32_t st = 0;
-    pthread_mutex_lock(&g_mu);
-    mbe_b200_ctx* c = ctx_locked();
+    mbe_b200_ctx* c = shim_ctx();
     CK(mbe_b200_decode_parms(c, codec, 1, (const uint8_t*)d, cur, prev, &st));
-    pthread_mutex_unlock(&g_mu);
-    return st;
+    return t_failed ? MBE_STATUS_INVALID_ARGUMENT : st;
 }
 int mbe_decodeImbe4400Parms(const char* imbe_d, mbe_parms* cur_mp, mbe_parms* prev_mp) {
     return shim_decode_parms(MBE_B200_IMBE7200X4400, imbe_d, cur_mp, prev_mp);
@@ -392,20 +428,16 @@ void mbe_spectralAmpEnhance(mbe_parms* cur_mp) { /* mbelib.c:663-666 */
     if (!cur_mp) {
         return;
     }
-    pthread_mutex_lock(&g_mu);
-    mbe_b200_ctx* c = ctx_locked();
+    mbe_b200_ctx* c = shim_ctx();
     CK(mbe_b200_spectral_amp_enhance(c, 1, cur_mp, NULL));
-    pthread_mutex_unlock(&g_mu);
 }
 
 void mbe_applyAdaptiveSmoothing(mbe_parms* cur_mp, const mbe_parms* prev_mp) { /* mbe_adaptive.c:266-276 */
     if (!cur_mp || !prev_mp) {
         return;
     }
-    pthread_mutex_lock(&g_mu);
-    mbe_b200_ctx* c = ctx_locked();
+    mbe_b200_ctx* c = shim_ctx();
     CK(mbe_b200_adaptive_smoothing(c, 1, cur_mp, prev_mp));
-    pthread_mutex_unlock(&g_mu);
 }
 
 /* host-only predicates on a parameter set (mbe_adaptive.c:70-107) */
@@ -419,11 +451,9 @@ static int shim_step(int codec, int step, char* fr, char* d) {
         return MBE_STATUS_INVALID_ARGUMENT;
     }
     int32_t st = 0;
-    pthread_mutex_lock(&g_mu);
-    mbe_b200_ctx* c = ctx_locked();
+    mbe_b200_ctx* c = shim_ctx();
     CK(mbe_b200_channel_step(c, codec, step, 1, (uint8_t*)fr, (uint8_t*)d, &st));
-    pthread_mutex_unlock(&g_mu);
-    return st;
+    return t_failed ? MBE_STATUS_INVALID_ARGUMENT : st;
 }
 #define STEP_FN(name, codec, R, C)                                                                                    \
     int mbe_ecc##name##C0(char fr[R][C]) { return shim_step(codec, 0, (char*)fr, NULL); }                             \
@@ -446,10 +476,11 @@ static void shim_tone(float* aout_buf, const char* ambe_d, mbe_parms* cur_mp, co
         mbe_synthesizeSilencef(aout_buf);  /* mbelib.c:771-774,826-829 */
         return;
     }
-    pthread_mutex_lock(&g_mu);
-    mbe_b200_ctx* c = ctx_locked();
+    mbe_b200_ctx* c = shim_ctx();
     CK(mbe_b200_synthesize_tone(c, 1, dstar_id ? NULL : (const uint8_t*)ambe_d, dstar_id, cur_mp, aout_buf));
-    pthread_mutex_unlock(&g_mu);
+    if (t_failed) {
+        mbe_synthesizeSilencef(aout_buf);
+    }
 }
 void mbe_synthesizeTonef(float* aout_buf, const char* ambe_d, mbe_parms* cur_mp) { shim_tone(aout_buf, ambe_d, cur_mp, NULL); }
 void mbe_synthesizeTonefdstar(float* aout_buf, const char* ambe_d, mbe_parms* cur_mp, int ID1) {
@@ -462,11 +493,12 @@ void mbe_synthesizeComfortNoisef(float* aout_buf) { /* mbe_adaptive.c:116-131: a
     if (!aout_buf) {
         return;
     }
-    pthread_mutex_lock(&g_mu);
-    mbe_b200_ctx* c = ctx_locked();
+    mbe_b200_ctx* c = shim_ctx();
     rng_ready_locked(c);
     CK(mbe_b200_comfort_noise(c, 1, t_rng, aout_buf));
-    pthread_mutex_unlock(&g_mu);
+    if (t_failed) {
+        mbe_synthesizeSilencef(aout_buf);
+    }
 }
 void mbe_synthesizeComfortNoise(short* aout_buf) { /* mbe_adaptive.c:133-149 */
     float f[NSAMP];
@@ -544,10 +576,11 @@ static int shim_ecc(int code, int soft, const void* in, char* out, int len) {
     uint8_t o[23];
     int32_t st = 0;
     memcpy(o, out, (size_t)len);
-    pthread_mutex_lock(&g_mu);
-    mbe_b200_ctx* c = ctx_locked();
+    mbe_b200_ctx* c = shim_ctx();
     CK(mbe_b200_ecc_blocks(c, code, soft, 1, (const uint8_t*)in, o, &st));
-    pthread_mutex_unlock(&g_mu);
+    if (t_failed) {
+        return MBE_STATUS_INVALID_ARGUMENT;
+    }
     if (st >= 0) {
         memcpy(out, o, (size_t)len);
     }
@@ -592,11 +625,17 @@ static void shim_synth(float* outf, short* outs, mbe_parms* cur, mbe_parms* prev
     if ((!outf && !outs) || !cur || !prev) {
         return;
     }
-    pthread_mutex_lock(&g_mu);
-    mbe_b200_ctx* c = ctx_locked();
+    mbe_b200_ctx* c = shim_ctx();
     rng_ready_locked(c);
     CK(mbe_b200_synthesize_speech_rng(c, 1, cur, prev, t_rng, outf, (int16_t*)outs));
-    pthread_mutex_unlock(&g_mu);
+    if (t_failed) {   /* like mbe_synthesizeSpeechCore on unusable arguments: silence (mbelib.c:1048-1055) */
+        if (outf) {
+            mbe_synthesizeSilencef(outf);
+        }
+        if (outs) {
+            mbe_synthesizeSilence(outs);
+        }
+    }
 }
 
 void mbe_synthesizeSpeechf(float* aout_buf, mbe_parms* cur_mp, mbe_parms* prev_mp) {
@@ -611,8 +650,9 @@ void mbe_floattoshort(const float* float_buf, short* aout_buf) { /* mbelib.c:114
     if (!float_buf || !aout_buf) {
         return;
     }
-    pthread_mutex_lock(&g_mu);
-    mbe_b200_ctx* c = ctx_locked();
+    mbe_b200_ctx* c = shim_ctx();
     CK(mbe_b200_floattoshort(c, 1, float_buf, (int16_t*)aout_buf));
-    pthread_mutex_unlock(&g_mu);
+    if (t_failed) {
+        mbe_synthesizeSilence(aout_buf);
+    }
 }

@@ -158,3 +158,33 @@ def test_contexts_release_their_device_memory(pkg):
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info(0)
     assert free0 - free1 < 64 << 20, "device memory not released: %d MB" % ((free0 - free1) >> 20)
+
+
+def test_pinned_host_buffers_from_the_c_abi(pkg):
+    """mbe_b200_host_alloc / host_register: a plain-C caller gets page-locked frame and PCM arrays without linking the CUDA
+    runtime (the reference's "caller owns every buffer" contract, mbelib.h:28-30).  Results do not depend on
+    where the host buffers live; a registered pageable array works the same and unregisters cleanly."""
+    import ctypes
+    lib = pkg.load_library()
+    codec, S, F = 0, 300, 5
+    frames = T.random_hard_frames(codec, S, F, 0xA110C)
+    seeds = T.stream_seeds(S, 3)
+    dec = pkg.Decoder(max_streams=S, device=0)
+    dec.init_streams(0, S, seeds)
+    want = dec.process_frames(codec, frames)
+    h_fr = pkg.host_alloc(frames.shape, np.uint8)
+    h_pcm = pkg.host_alloc((S, F, 160), np.int16)
+    h_fr[...] = frames
+    dec.init_streams(0, S, seeds)
+    got = dec.process_frames(codec, h_fr, out_pcm=h_pcm)
+    assert got["pcm"] is h_pcm and np.array_equal(h_pcm, want["pcm"])
+    pkg.host_free(h_fr)
+    pkg.host_free(h_pcm)
+    own = np.zeros((S, F, 160), np.int16)
+    assert lib.mbe_b200_host_register(own.ctypes.data_as(ctypes.c_void_p), own.nbytes) == 0
+    dec.init_streams(0, S, seeds)
+    dec.process_frames(codec, frames, out_pcm=own)
+    assert lib.mbe_b200_host_unregister(own.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert np.array_equal(own, want["pcm"])
+    assert lib.mbe_b200_host_alloc(None, 16) != 0        # bad argument: error code, no crash
+    dec.close()

@@ -119,3 +119,54 @@ def test_two_threads_keep_their_own_rng_state():
         frames, pcm = out[codec]
         want = T.run_cpu(T.load_oracle().mbo_run, codec, 0, frames, np.array([seed], np.uint32))
         assert np.array_equal(pcm, want["pcm"][0]), T.CODEC_NAMES[codec]
+
+
+def test_sixteen_threads_decode_side_by_side():
+    """The reference is re-entrant per stream (mbelib.h:28-30).  Every calling thread of the shim owns its context, so 16
+    threads decoding 16 different streams at once (1) each equal the oracle's run of their stream and (2) finish in well
+    under 16x the time one thread needs for one stream (a process-wide lock would serialise them)."""
+    import threading
+    import time
+    shim = ctypes.CDLL(SHIM)
+    vp = ctypes.c_void_p
+    shim.mbe_setThreadRngSeed.argtypes = [ctypes.c_uint32]
+    shim.mbe_initMbeParms.argtypes = [vp, vp, vp]
+    codec, F, N = 3, 40, 16
+    fn = getattr(shim, FRAME_FN[codec] + "Frame")
+    fn.argtypes = [vp] * 7
+    out = {}
+
+    def work(i):
+        seed = 0x5EED0 + i
+        frames = T.random_hard_frames(codec, 1, F, seed)
+        trip = np.zeros((3, T.PARMS_BYTES), np.uint8)
+        pcm = np.zeros((F, 160), np.int16)
+        bits = np.zeros(T.PARAM_BITS[codec], np.uint8)
+        shim.mbe_setThreadRngSeed(seed)
+        shim.mbe_initMbeParms(trip[0].ctypes.data, trip[1].ctypes.data, trip[2].ctypes.data)
+        t0 = time.perf_counter()
+        for f in range(F):
+            fr = np.ascontiguousarray(frames[0, f])
+            rc = fn(pcm[f].ctypes.data, None, fr.ctypes.data, bits.ctypes.data, trip[0].ctypes.data, trip[1].ctypes.data,
+                    trip[2].ctypes.data)
+            assert rc >= 0
+        out[i] = (frames, pcm, seed, time.perf_counter() - t0)
+
+    work(100)                                  # warm-up (context creation, first launches) and the single-thread time
+    work(101)
+    t_one = out[101][3]
+    th = [threading.Thread(target=work, args=(i,)) for i in range(N)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    t_all = time.perf_counter() - t0
+    for i in range(N):
+        frames, pcm, seed, _ = out[i]
+        want = T.run_cpu(T.load_oracle().mbo_run, codec, 0, frames, np.array([seed], np.uint32))
+        assert np.array_equal(pcm, want["pcm"][0]), i
+    # includes 16 context creations; a serialised shim would need >= 16 x t_one for the frames alone
+    print("one thread %.3f s, 16 threads %.3f s (%.1fx one)" % (t_one, t_all, t_all / t_one))
+    steady = max(out[i][3] for i in range(N))
+    assert steady < 8.0 * t_one, "16 threads took %.1fx the single-thread time: calls are being serialised" % (steady / t_one)
