@@ -1,15 +1,19 @@
 #!/usr/bin/env python
 """Extract the per-frame constants bench.py quotes and the pipe metrics DESIGN.md cites from `ncu --set full` captures.
 
-    python tools/ncu_constants.py <tag> gpurun_out/<tag>_<codec>_<kind>.ncu-rep ...      (run where ncu is installed, no GPU needed)
+    python tools/ncu_constants.py <tag> gpurun_out/<tag>_<codec>_<kind>_<kernel>_s<streams>x<frames>.ncu-rep ...
+                                                                           (run where ncu is installed, no GPU needed)
 
-For every capture (one launch of the stream kernel over FRAMES = streams x frames, both read from the capture's grid and the
-file name `..._s<streams>x<frames>.ncu-rep`, default 16576 x 50) it writes
-  profiles/<tag>_<codec>_<kind>_ncu_raw.txt   the raw-page metrics that matter (pipes, FP32 op counts, wavefronts, DRAM, issue)
+<kernel> is parameter | bank | unvoiced (the three kernels of the multi-kernel path, tools/gpu_ncu_all.sh) or fused.  For every
+capture (one launch over FRAMES = streams x frames, from the file name) it writes
+  profiles/<tag>_<codec>_<kind>_<kernel>_ncu_raw.txt   the raw-page metrics that matter (pipes, FP32 op counts, wavefronts,
+                                                       DRAM, issue, stalls)
 and merges into
-  profiles/ncu_constants.json                 {"<codec>/<kind>": {warp_instr_per_frame, fp32_thread_ops_per_frame,
-                                               dram_bytes_per_frame, pipe_fma_pct, pipe_alu_pct, pipe_lsu_pct, pipe_xu_pct,
-                                               issue_active_pct, source}}
+  profiles/ncu_constants.json     {"<codec>/<kind>": {warp_instr_per_frame, dram_bytes_per_frame, fp32_thread_ops_per_frame
+                                   (sums over the path's kernels), "kernels": {<kernel>: {warp_instr_per_frame,
+                                   fp32_thread_ops_per_frame, dram_bytes_per_frame, pipe_fma_pct, pipe_alu_pct, pipe_lsu_pct,
+                                   pipe_xu_pct, issue_active_pct, launch_ms_under_ncu, source}}}}
+bench.py reads the sums (roofline.traffic, roofline.issue_slots).
 """
 import csv
 import json
@@ -61,16 +65,17 @@ def main():
     consts = json.load(open(cpath)) if os.path.exists(cpath) else {}
     for rep in reps:
         base = os.path.basename(rep)[:-len(".ncu-rep")]
-        m = re.match(r"(?:.*?_)?(imbe7200x4400|imbe7100x4400|ambe3600x2400|ambe3600x2450|synth)_(\w+?)(?:_s(\d+)x(\d+))?$", base)
+        m = re.match(r"(?:.*?_)?(imbe7200x4400|imbe7100x4400|ambe3600x2400|ambe3600x2450)_(hard|soft|softch|tones)_"
+                     r"(parameter|bank|unvoiced|fused)_s(\d+)x(\d+)$", base)
         if not m:
-            print("skip (name does not say codec_kind):", rep)
+            print("skip (name does not say codec_kind_kernel_s<streams>x<frames>):", rep)
             continue
-        codec, kind = m.group(1), m.group(2)
-        streams, frames = int(m.group(3) or 16576), int(m.group(4) or 50)
+        codec, kind, kname = m.group(1), m.group(2), m.group(3)
+        streams, frames = int(m.group(4)), int(m.group(5))
         met = raw_page(rep)
         n = float(streams * frames)
         kernel = met.get("Kernel Name", ("", "?"))[1]
-        out = os.path.join(ROOT, "profiles", "%s_%s_%s_ncu_raw.txt" % (tag, codec, kind))
+        out = os.path.join(ROOT, "profiles", "%s_%s_%s_%s_ncu_raw.txt" % (tag, codec, kind, kname))
         with open(out, "w") as f:
             f.write("# ncu --set full --clock-control none, one launch: %s\n# %s: %d streams x %d frames (%s)\n" % (kernel, base, streams, frames, rep))
             for k in sorted(met):
@@ -91,12 +96,22 @@ def main():
                  "pipe_lsu_pct": num(met, "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", None),
                  "pipe_xu_pct": num(met, "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", None),
                  "issue_active_pct": num(met, "smsp__issue_active.avg.pct_of_peak_sustained_active", None),
+                 "warps_active_pct": num(met, "sm__warps_active.avg.pct_of_peak_sustained_active", None),
                  "launch_ms_under_ncu": num(met, "gpu__time_duration.sum") if met.get("gpu__time_duration.sum", ("", ""))[0] == "ms" else None,
                  "frames_in_capture": int(n), "kernel": kernel,
-                 "source": "profiles/%s_%s_%s_ncu_raw.txt" % (tag, codec, kind)}
-        consts["%s/%s" % (codec, kind)] = entry
-        print("%s/%s: %.0f warp-instr/frame, %.0f FP32 thread-ops/frame, %.0f DRAM B/frame, fma %.1f%% alu %.1f%% lsu %.1f%% xu %.1f%% issue %.1f%%" % (
-            codec, kind, entry["warp_instr_per_frame"], entry["fp32_thread_ops_per_frame"], entry["dram_bytes_per_frame"],
+                 "source": "profiles/%s_%s_%s_%s_ncu_raw.txt" % (tag, codec, kind, kname)}
+        part = consts.setdefault("%s/%s" % (codec, kind), {})
+        part.setdefault("kernels", {})
+        if kname == "fused":
+            part["fused"] = entry
+        else:
+            part["kernels"][kname] = entry
+            ks = part["kernels"]
+            for key in ("warp_instr_per_frame", "fp32_thread_ops_per_frame", "dram_bytes_per_frame"):
+                part[key] = sum(ks[k][key] for k in ks)
+            part["kernels_summed"] = sorted(ks)
+        print("%s/%s %s: %.0f warp-instr/frame, %.0f FP32 thread-ops/frame, %.0f DRAM B/frame, fma %.1f%% alu %.1f%% lsu %.1f%% xu %.1f%% issue %.1f%%" % (
+            codec, kind, kname, entry["warp_instr_per_frame"], entry["fp32_thread_ops_per_frame"], entry["dram_bytes_per_frame"],
             entry["pipe_fma_pct"] or -1, entry["pipe_alu_pct"] or -1, entry["pipe_lsu_pct"] or -1, entry["pipe_xu_pct"] or -1,
             entry["issue_active_pct"] or -1))
     with open(cpath, "w") as f:
