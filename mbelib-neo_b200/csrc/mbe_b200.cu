@@ -2092,8 +2092,15 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaS
     } else if (cap_streams < (size_t)WARPS_PER_BLOCK) {
         cap_streams = WARPS_PER_BLOCK;
     }
-    const int sub = (int)(cap_streams < (size_t)a.n_streams ? cap_streams : (size_t)a.n_streams);
+    int sub = (int)(cap_streams < (size_t)a.n_streams ? cap_streams : (size_t)a.n_streams);
     const int n_sub = (a.n_streams + sub - 1) / sub;
+    if (n_sub > 1) {
+        // equal ranges (whole blocks of the parameter kernel) instead of full ones and a small remainder
+        const int even = ((a.n_streams + n_sub - 1) / n_sub + pw - 1) / pw * pw;
+        if (even < sub) {
+            sub = even;
+        }
+    }
     int n_aux = knobs().aux_streams;
     if (n_aux < 1 || n_aux > MAX_AUX) {
         n_aux = MAX_AUX;
