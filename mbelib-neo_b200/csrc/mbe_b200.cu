@@ -556,10 +556,12 @@ struct StreamShape {
     static constexpr bool SMALL = SPLIT && SOFT != 1;
     static constexpr int WARPS = SMALL ? P_WARPS : WARPS_PER_BLOCK;
     static constexpr size_t STRIDE = SMALL ? WS_STRIDE_SMALL : sizeof(WarpWS);
+    static constexpr int MINB = SMALL ? P_MINB : MIN_BLOCKS_PER_SM;
 };
 
 template <int CODEC, int SOFT, int MODE, bool SPLIT>
-__global__ void __launch_bounds__(StreamShape<SOFT, SPLIT>::WARPS * 32, MIN_BLOCKS_PER_SM) mbe_stream_kernel(const LaunchArgs A) {
+__global__ void __launch_bounds__(StreamShape<SOFT, SPLIT>::WARPS * 32, StreamShape<SOFT, SPLIT>::MINB)
+mbe_stream_kernel(const LaunchArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Shape = StreamShape<SOFT, SPLIT>;
     BlockTables* bt = reinterpret_cast<BlockTables*>(smem_raw);
@@ -2086,7 +2088,7 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaS
     const size_t per_stream = (size_t)a.n_frames * DESC_WORDS * sizeof(uint32_t);
     size_t cap_streams = ((size_t)knobs().desc_mb << 20) / per_stream;
     const int pw = parm_kernel_warps(a.soft);
-    const size_t gran = (size_t)g_sm_count.load() * pw * MIN_BLOCKS_PER_SM;   // one wave of the parameter kernel
+    const size_t gran = (size_t)g_sm_count.load() * pw * (parm_kernel_small(a.soft) ? P_MINB : MIN_BLOCKS_PER_SM);   // one wave
     if (cap_streams >= gran) {
         cap_streams -= cap_streams % gran;
     } else if (cap_streams < (size_t)WARPS_PER_BLOCK) {

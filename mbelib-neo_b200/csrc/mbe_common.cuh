@@ -311,7 +311,11 @@ constexpr size_t WS_STRIDE_SMALL = offsetof(WarpWS, u) + WS_DEC_BYTES;
 #ifndef MBE_PWPB
 #define MBE_PWPB 18
 #endif
-constexpr int P_WARPS = MBE_PWPB;   // warps per block of that kernel (64 registers per thread at two blocks per SM)
+#ifndef MBE_PMINB
+#define MBE_PMINB 2
+#endif
+constexpr int P_WARPS = MBE_PWPB;   // warps per block of that kernel (56 registers per thread at two blocks of 18 warps per SM)
+constexpr int P_MINB = MBE_PMINB;
 
 struct BlockShared {
     int cnt[2][WARPS_PER_BLOCK + 2];      // per stream: component count of the current frame (double-buffered by frame parity)

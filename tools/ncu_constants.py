@@ -42,7 +42,12 @@ UNIT = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
 
 
 def raw_page(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """rep: an .ncu-rep, or the `ncu -i rep --page raw --csv` text of one (tools/gpu_ncu_all.sh keeps only that: a report with
+    imported sources is ~17 MB and gpurun brings back 64 MiB per call)"""
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     names, units, vals = rows[hdr], rows[hdr + 1], rows[hdr + 2]
@@ -64,7 +69,8 @@ def main():
     cpath = os.path.join(ROOT, "profiles", "ncu_constants.json")
     consts = json.load(open(cpath)) if os.path.exists(cpath) else {}
     for rep in reps:
-        base = os.path.basename(rep)[:-len(".ncu-rep")]
+        base = os.path.basename(rep)
+        base = base[:-len(".ncu-rep")] if base.endswith(".ncu-rep") else base[:-len(".raw.csv")]
         m = re.match(r"(?:.*?_)?(imbe7200x4400|imbe7100x4400|ambe3600x2400|ambe3600x2450)_(hard|soft|softch|tones)_"
                      r"(parameter|bank|unvoiced|fused)_s(\d+)x(\d+)$", base)
         if not m:
