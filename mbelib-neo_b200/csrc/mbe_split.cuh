@@ -343,14 +343,12 @@ __global__ void __launch_bounds__(B_WARPS * 32, B_MINB) mbe_split_bank_kernel(co
             const float* Wb = vwin + ((kind == 0) ? WIN_PREV : 0);
             const float gg = k2lane ? 0.0f : g;   // interpolated slots are written by whoever renders them
             const float rec_c = c, rec_s = s;     // (the recurrence below rotates c and s on every lane)
-            // this pass's part of every frame of the group, in four-slot groups of the tile: [glo, ghi)
-            int glo[BG], ghi[BG];
-#pragma unroll
-            for (int t = 0; t < BG; ++t) {
-                const int lo = max(off[t], base), hi = min(off[t] + ((cnt[t] + 3) & ~3), base + 32);
-                glo[t] = (lo - base) >> 2;
-                ghi[t] = (hi > lo) ? ((hi - base) >> 2) : glo[t];
-            }
+            // phase B's map of the pass: which frame owns each four-slot group of the tile (a frame's slots start at a multiple
+            // of four, so a group never straddles frames): bit 4g of (fq0, fq1) = frame of group g, fchg = groups where it changes
+            static_assert(BG <= 4, "two bits per group");
+            const unsigned fq0 = __ballot_sync(FULL, (q & 1) != 0), fq1 = __ballot_sync(FULL, (q & 2) != 0);
+            const unsigned fchg = (fq0 ^ (fq0 << 4)) | (fq1 ^ (fq1 << 4));
+            const int ng = min(8, (total - base) >> 2);   // groups of this pass that hold slots
 #pragma unroll 1
             for (int ch = 0; ch < 5; ++ch) {
                 // phase A: 32 oscillator steps, sixteen per loop body (the body stays in the L0 instruction cache)
@@ -392,36 +390,28 @@ __global__ void __launch_bounds__(B_WARPS * 32, B_MINB) mbe_split_bank_kernel(co
                     }
                 }
                 __syncwarp();
-                // phase B: every frame with slots in this pass adds them in list order, lane = sample
+                // phase B: lane = sample; the tile's groups in order, each added to the running sum of the frame that owns it
+                // (list order = the reference's summation order); the sum moves to the next frame's row where the owner changes
                 {
                     const float4* row = reinterpret_cast<const float4*>(tile + lane * BT_STRIDE);
+                    float* op = &ws.out[(fq0 & 1u) | ((fq1 & 1u) << 1)][32 * ch + lane];
+                    float a = *op;
 #pragma unroll
-                    for (int t = 0; t < BG; ++t) {
-                        if (ghi[t] > glo[t]) {
-                            float a = ws.out[t][32 * ch + lane];
-                            const float4* p = row + glo[t];
-                            const float4* const pe = row + ghi[t];
-#pragma unroll 1
-                            for (; p + 4 <= pe; p += 4) {
-                                const float4 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
-                                a += v0.x; a += v0.y; a += v0.z; a += v0.w;
-                                a += v1.x; a += v1.y; a += v1.z; a += v1.w;
-                                a += v2.x; a += v2.y; a += v2.z; a += v2.w;
-                                a += v3.x; a += v3.y; a += v3.z; a += v3.w;
+                    for (int gi = 0; gi < 8; ++gi) {
+                        if (gi < ng) {
+                            if (gi > 0 && ((fchg >> (4 * gi)) & 1u)) {
+                                *op = a;
+                                op = &ws.out[((fq0 >> (4 * gi)) & 1u) | (((fq1 >> (4 * gi)) & 1u) << 1)][32 * ch + lane];
+                                a = *op;
                             }
-                            if (p + 2 <= pe) {
-                                const float4 v0 = p[0], v1 = p[1];
-                                a += v0.x; a += v0.y; a += v0.z; a += v0.w;
-                                a += v1.x; a += v1.y; a += v1.z; a += v1.w;
-                                p += 2;
-                            }
-                            if (p < pe) {
-                                const float4 v = p[0];
-                                a += v.x; a += v.y; a += v.z; a += v.w;
-                            }
-                            ws.out[t][32 * ch + lane] = a;
+                            const float4 v = row[gi];
+                            a += v.x;
+                            a += v.y;
+                            a += v.z;
+                            a += v.w;
                         }
                     }
+                    *op = a;
                 }
                 __syncwarp();
             }
