@@ -1574,6 +1574,8 @@ struct Knobs {
     int aux_streams;  // MBE_B200_AUX: internal streams a multi-kernel launch forks its stream ranges over
     int split;        // MBE_B200_SPLIT: default kernel path of new contexts (0 fused, 1 parameter + synthesis kernels)
     long desc_mb;     // MBE_B200_DESC_MB: descriptor buffer budget per launch, MiB
+    int skip_kernels; // MBE_B200_SKIP_KERNELS (timing experiments only, results are wrong): 1 parameter (after the first use of
+                      // a descriptor buffer), 2 bank, 4 unvoiced kernel launches are skipped
 };
 static Knobs g_knobs;
 static std::once_flag g_knobs_once;
@@ -1592,6 +1594,8 @@ static const Knobs& knobs() {
         g_knobs.aux_streams = e ? atoi(e) : 0;
         e = getenv("MBE_B200_SPLIT");
         g_knobs.split = e ? atoi(e) : MBE_SPLIT_DEFAULT;
+        e = getenv("MBE_B200_SKIP_KERNELS");
+        g_knobs.skip_kernels = e ? atoi(e) : 0;
         e = getenv("MBE_B200_DESC_MB");
         g_knobs.desc_mb = e ? atol(e) : 2048;
         if (g_knobs.desc_mb < 1) {
@@ -2132,7 +2136,8 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaS
         a.io_base = a_in.io_base + o;
         a.n_streams = ns;
         a.desc = (uint32_t*)ctx->d_desc[slot];
-        {
+        const int skip = knobs().skip_kernels;
+        if (!(skip & 1) || ctx->launches < 64) {
             KernelTimer kt(ctx, 0, ss);
             pk<<<(ns + pw - 1) / pw, pw * 32, parm_kernel_smem(a.soft), ss>>>(a);
         }
@@ -2156,13 +2161,13 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaS
         if (bank_blocks > resident) {
             bank_blocks = resident;
         }
-        {
+        if (!(skip & 2)) {
             KernelTimer kt(ctx, 1, ss);
             mbe_split_bank_kernel<<<(unsigned)bank_blocks, B_WARPS * 32, bank_kernel_smem(), ss>>>(sa);
         }
         ctx->launches++;
         CU(cudaGetLastError());
-        {
+        if (!(skip & 4)) {
             KernelTimer kt(ctx, 2, ss);
             mbe_split_unvoiced_kernel<<<(ns + U_WARPS - 1) / U_WARPS, U_WARPS * 32, unvoiced_kernel_smem(), ss>>>(sa);
         }
