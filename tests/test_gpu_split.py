@@ -89,3 +89,38 @@ def test_split_descriptor_buffer_ranges(pkg, monkeypatch):
     assert np.array_equal(res[0][0]["pcmf"].view(np.uint32), res[1][0]["pcmf"].view(np.uint32))
     assert np.array_equal(res[0][0]["results"], res[1][0]["results"])
     assert np.array_equal(res[0][1], res[1][1])
+
+
+def test_kernel_timing_and_bank_counters(pkg):
+    """mbe_b200_set_kernel_timing / kernel_timing (bench.py's roofline source): per kernel kind launches and device time, and
+    the bank kernel's own work counters.  Voice frames of valid AMBE+2 parameters all run the synthesis, so the frame counter
+    is exact; the slot counter must lie between one and 112 per synthesised frame; the fused path reports one kind only."""
+    codec, S, F = 3, 200, 10
+    rng = np.random.default_rng(77)
+    frames = np.zeros((S, F, 96), np.uint8)
+    for s in range(S):
+        for f in range(F):
+            p = rng.integers(0, 2, size=49, dtype=np.uint8)
+            p[0] = 0                                    # b0 < 64: a voice frame, never a tone / erasure signature
+            frames[s, f] = T.encode_ambe_frame(p).reshape(-1)
+    dec = pkg.Decoder(max_streams=S, device=0)
+    for path in (1, 0):
+        dec.set_kernel_path(path)
+        dec.init_streams(0, S, T.stream_seeds(S, 1))
+        dec.set_kernel_timing(True)
+        got = dec.process_frames(codec, frames)
+        kinds, work = dec.kernel_timing()
+        dec.set_kernel_timing(False)
+        assert (got["results"]["status"] >= 0).all()
+        if path == 1:
+            assert all(kinds[k][1] >= 1 and kinds[k][0] > 0.0 for k in ("parameter", "bank", "unvoiced")), kinds
+            muted = int(((got["results"]["flags"] & 0x80) != 0).sum())
+            assert S * F - muted <= work["frames"] <= S * F
+            assert work["frames"] <= work["slots"] <= 112 * work["frames"]
+            assert 0 <= work["interpolated"] <= 7 * work["frames"]
+        else:
+            assert kinds["parameter"][1] >= 1 and kinds["bank"][1] == 0 and kinds["unvoiced"][1] == 0
+            assert work == dict(slots=0, interpolated=0, frames=0)
+    with pytest.raises(pkg.MbeB200Error):
+        dec.set_kernel_path(2)
+    dec.close()
