@@ -345,9 +345,10 @@ __global__ void __launch_bounds__(B_WARPS * 32, B_MINB) mbe_split_bank_kernel(co
             const float rec_c = c, rec_s = s;     // (the recurrence below rotates c and s on every lane)
             // phase B's map of the pass: which frame owns each four-slot group of the tile (a frame's slots start at a multiple
             // of four, so a group never straddles frames): bit 4g of (fq0, fq1) = frame of group g, fchg = groups where it changes
-            static_assert(BG <= 4, "two bits per group");
+            static_assert(BG <= 8, "three bits per group");
             const unsigned fq0 = __ballot_sync(FULL, (q & 1) != 0), fq1 = __ballot_sync(FULL, (q & 2) != 0);
-            const unsigned fchg = (fq0 ^ (fq0 << 4)) | (fq1 ^ (fq1 << 4));
+            const unsigned fq2 = (BG > 4) ? __ballot_sync(FULL, (q & 4) != 0) : 0u;
+            const unsigned fchg = (fq0 ^ (fq0 << 4)) | (fq1 ^ (fq1 << 4)) | (fq2 ^ (fq2 << 4));
             const int ng = min(8, (total - base) >> 2);   // groups of this pass that hold slots
 #pragma unroll 1
             for (int ch = 0; ch < 5; ++ch) {
@@ -394,14 +395,15 @@ __global__ void __launch_bounds__(B_WARPS * 32, B_MINB) mbe_split_bank_kernel(co
                 // (list order = the reference's summation order); the sum moves to the next frame's row where the owner changes
                 {
                     const float4* row = reinterpret_cast<const float4*>(tile + lane * BT_STRIDE);
-                    float* op = &ws.out[(fq0 & 1u) | ((fq1 & 1u) << 1)][32 * ch + lane];
+                    float* op = &ws.out[(fq0 & 1u) | ((fq1 & 1u) << 1) | ((fq2 & 1u) << 2)][32 * ch + lane];
                     float a = *op;
 #pragma unroll
                     for (int gi = 0; gi < 8; ++gi) {
                         if (gi < ng) {
                             if (gi > 0 && ((fchg >> (4 * gi)) & 1u)) {
                                 *op = a;
-                                op = &ws.out[((fq0 >> (4 * gi)) & 1u) | (((fq1 >> (4 * gi)) & 1u) << 1)][32 * ch + lane];
+                                op = &ws.out[((fq0 >> (4 * gi)) & 1u) | (((fq1 >> (4 * gi)) & 1u) << 1) |
+                                             (((fq2 >> (4 * gi)) & 1u) << 2)][32 * ch + lane];
                                 a = *op;
                             }
                             const float4 v = row[gi];
