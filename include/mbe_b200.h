@@ -87,6 +87,16 @@ MBE_B200_API int mbe_b200_host_register(void* p, size_t bytes);
 MBE_B200_API int mbe_b200_host_unregister(void* p);
 /* kernel launches issued by this context so far (bench.py reports it as gpu_launches) */
 MBE_B200_API long long mbe_b200_launch_count(const mbe_b200_ctx* ctx);
+/* One stream, one frame, caller-owned state - the reference's call shape (mbe_process<Codec>[Soft]Frame[f] / Data[f]) in one
+ * call: the {cur_mp, prev_mp, prev_mp_enhanced} triplet (3 x 2604 bytes) and the calling thread's four RNG words go to stream
+ * slot `stream`, ONE frame is decoded and synthesised, both come back - one upload, one download, one synchronisation.
+ * kind: 0 hard channel frame, 1 soft channel frame (mbe_soft_bit pairs), 2 parameter bits (`result` is then the IN/OUT decode
+ * context of mbe_process<Codec>Data).  result->status < 0 (invalid bits / argument): nothing else is written, like the
+ * reference's early return.  At least one of pcm / pcmf; bits may be NULL.  This is what the single-stream shim is built on;
+ * throughput callers use the batched entry points. */
+MBE_B200_API int mbe_b200_single_frame(mbe_b200_ctx* ctx, int codec, int kind, int stream, const void* frame,
+                                       void* parms_triplet, uint32_t* rng_words4, int16_t* pcm, float* pcmf,
+                                       mbe_b200_result* result, uint8_t* bits);
 /* Kernel path of the frame entry points (process_frames*, process_data*): 0 = one fused kernel per batch, 1 = a parameter
  * kernel (ECC, decode, state machine, enhancement) that leaves a descriptor per frame + a synthesis kernel (oscillator
  * bank, FFT / overlap-add, PCM: a bank kernel and an unvoiced kernel) - DESIGN 4.5.  Results are bit-identical; the

@@ -41,7 +41,8 @@ _EXPORTS = ["mbe_b200_create", "mbe_b200_destroy", "mbe_b200_last_error", "mbe_b
             "mbe_b200_pool_shards", "mbe_b200_pool_shard", "mbe_b200_pool_init_streams", "mbe_b200_pool_export_state",
             "mbe_b200_pool_import_state", "mbe_b200_pool_process_frames", "mbe_b200_pool_process_frames_packed",
             "mbe_b200_set_kernel_path", "mbe_b200_kernel_path", "mbe_b200_set_kernel_timing", "mbe_b200_kernel_timing",
-            "mbe_b200_host_alloc", "mbe_b200_host_free", "mbe_b200_host_register", "mbe_b200_host_unregister"]
+            "mbe_b200_host_alloc", "mbe_b200_host_free", "mbe_b200_host_register", "mbe_b200_host_unregister",
+            "mbe_b200_single_frame"]
 
 _lib = None
 
@@ -85,6 +86,7 @@ def load_library():
         lib.mbe_b200_set_kernel_timing.argtypes = [vp, ci]
         lib.mbe_b200_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
         lib.mbe_b200_host_free.argtypes = [vp]
+        lib.mbe_b200_single_frame.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp]
         lib.mbe_b200_host_register.argtypes = [vp, ctypes.c_size_t]
         lib.mbe_b200_host_unregister.argtypes = [vp]
         lib.mbe_b200_kernel_timing.argtypes = [vp, vp, vp, vp]

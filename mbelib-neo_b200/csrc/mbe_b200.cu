@@ -1284,6 +1284,19 @@ __global__ void mbe_state_xfer_kernel(uint32_t* state, int first, int count, uin
     }
 }
 
+// single-frame call (mbe_b200_single_frame): one stream's {cur, prev, enh} triplet + RNG words between a dense blob and its slot
+__global__ void mbe_single_io_kernel(uint32_t* state, int stream, uint32_t* blob, int to_blob) {
+    uint32_t* g = state + (size_t)stream * STATE_WORDS;
+    constexpr int N = 3 * PARMS_WORDS + RNG_WORDS;   // the slot's first words are exactly these
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        if (to_blob) {
+            blob[i] = g[i];
+        } else {
+            g[i] = blob[i];
+        }
+    }
+}
+
 }  // namespace mbe
 
 // =====================================================================================================
@@ -1330,6 +1343,10 @@ struct mbe_b200_ctx {
     cudaStream_t s_aux[MAX_AUX];
     cudaEvent_t ev_fork, ev_join[MAX_AUX];
     // per-kernel device time (mbe_b200_set_kernel_timing): an event pair around every launch of the frame kernels
+    // mbe_b200_single_frame: one pinned host blob and its device twin (state + RNG + frame in, PCM + result + bits out)
+    unsigned char* h_one;
+    unsigned char* d_one;
+    int force_fused;       // the single-frame call runs the fused kernel (one launch instead of three + fork / join)
     int kt_on, kt_n;
     cudaEvent_t* kt_ev;               // [2 * KT_MAX]
     unsigned char* kt_kind;           // [KT_MAX]: 0 parameter (or fused) kernel, 1 bank kernel, 2 unvoiced kernel
@@ -1905,6 +1922,10 @@ void mbe_b200_destroy(mbe_b200_ctx* ctx) {
     }
     free(ctx->kt_kind);
     cudaFree(ctx->d_cnt);
+    if (ctx->h_one) {
+        cudaFreeHost(ctx->h_one);
+    }
+    cudaFree(ctx->d_one);
     cudaFree(ctx->d_state);
     cudaFree(ctx->d_dbg);
     cudaFree(ctx->d_tab);
@@ -2069,7 +2090,7 @@ static int launch_stream_kernel(mbe_b200_ctx* ctx, const LaunchArgs& a_in, cudaS
         CU(cudaGetLastError());
         return 0;
     }
-    if (!ctx->split) {
+    if (!ctx->split || ctx->force_fused) {
         const int blocks = (a.n_streams + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
         {
             KernelTimer kt(ctx, 0, st);
@@ -2388,6 +2409,95 @@ int mbe_b200_process_data_dev(mbe_b200_ctx* ctx, int codec, int first_stream, in
     a.state = ctx->d_state;
     a.tab = ctx->d_tab;
     return launch_stream_kernel(ctx, a, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream);
+}
+
+// ---- one stream, one frame, caller-owned state: what the single-stream shim needs, as ONE upload, three kernels, ONE
+// download and ONE synchronisation (the generic calls - import_state, import_rng, process_frames, export_state, export_rng -
+// are ~40 runtime calls and ten synchronisations per frame, and the CUDA driver serialises the runtime calls of a process)
+constexpr size_t ONE_STATE = (size_t)(3 * PARMS_WORDS + RNG_WORDS) * sizeof(uint32_t);   // triplet + RNG words
+constexpr size_t ONE_FRAME = (ONE_STATE + 15) & ~(size_t)15;    // channel frame (<= 368 bytes) or parameter bits
+constexpr size_t ONE_RES = ONE_FRAME + 384;                    // mbe_b200_result in / out
+constexpr size_t ONE_IN_END = ONE_RES + 32;
+constexpr size_t ONE_BITS = ONE_IN_END;                        // parameter bits out (<= 88)
+constexpr size_t ONE_PCM = ONE_BITS + 96;                      // int16[160]
+constexpr size_t ONE_PCMF = ONE_PCM + 320;                     // float[160]
+constexpr size_t ONE_BYTES = ONE_PCMF + 640;
+static_assert(ONE_FRAME % 16 == 0 && ONE_RES % 8 == 0 && ONE_PCM % 16 == 0 && ONE_PCMF % 16 == 0, "blob alignment");
+
+int mbe_b200_single_frame(mbe_b200_ctx* ctx, int codec, int kind, int stream, const void* frame, void* parms_triplet,
+                          uint32_t* rng_words4, int16_t* pcm, float* pcmf, mbe_b200_result* result, uint8_t* bits) {
+    int rc = check_range(ctx, stream, 1);
+    if (rc < 0) {
+        return rc;
+    }
+    if (check_idle(ctx, "single_frame") < 0) {
+        return MBE_B200_E_ARG;
+    }
+    int fb = 0, pb = 0;
+    if (mbe_b200_geometry(codec, &fb, &pb) != 0 || kind < 0 || kind > 2 || !frame || !parms_triplet || !rng_words4 || (!pcm && !pcmf)) {
+        return fail(ctx, MBE_B200_E_ARG, "single_frame: bad argument", cudaSuccess);
+    }
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->h_one) {
+        CU(cudaHostAlloc((void**)&ctx->h_one, ONE_BYTES, cudaHostAllocDefault));
+        CU(cudaMalloc((void**)&ctx->d_one, ONE_BYTES));
+    }
+    const size_t in_bytes = kind == 2 ? (size_t)pb : (size_t)fb * (kind == 1 ? 2u : 1u);
+    unsigned char* h = ctx->h_one;
+    unsigned char* d = ctx->d_one;
+    memcpy(h, parms_triplet, 3 * sizeof(Parms));
+    memcpy(h + 3 * sizeof(Parms), rng_words4, RNG_WORDS * sizeof(uint32_t));
+    memcpy(h + ONE_FRAME, frame, in_bytes);
+    mbe_b200_result rin;
+    memset(&rin, 0, sizeof(rin));
+    if (kind == 2 && result) {
+        rin = *result;
+    }
+    memcpy(h + ONE_RES, &rin, sizeof(rin));
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(d, h, ONE_IN_END, cudaMemcpyHostToDevice, st));
+    mbe_single_io_kernel<<<1, 256, 0, st>>>(ctx->d_state, stream, (uint32_t*)d, 0);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    ctx->force_fused = 1;
+    if (kind == 2) {
+        rc = mbe_b200_process_data_dev(ctx, codec, stream, 1, 1, d + ONE_FRAME, (mbe_b200_result*)(d + ONE_RES),
+                                       pcm ? (int16_t*)(d + ONE_PCM) : nullptr, pcmf ? (float*)(d + ONE_PCMF) : nullptr, st);
+    } else {
+        rc = mbe_b200_process_frames_dev(ctx, codec, kind, stream, 1, 1, d + ONE_FRAME, pcm ? (int16_t*)(d + ONE_PCM) : nullptr,
+                                         pcmf ? (float*)(d + ONE_PCMF) : nullptr, (mbe_b200_result*)(d + ONE_RES),
+                                         d + ONE_BITS, st);
+    }
+    ctx->force_fused = 0;
+    if (rc < 0) {
+        cudaStreamSynchronize(st);
+        return rc;
+    }
+    mbe_single_io_kernel<<<1, 256, 0, st>>>(ctx->d_state, stream, (uint32_t*)d, 1);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h, d, ONE_BYTES, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    mbe_b200_result rout;
+    memcpy(&rout, h + ONE_RES, sizeof(rout));
+    if (result) {
+        *result = rout;
+    }
+    if (rout.status < 0) {
+        return 0;   // the reference returns before it touches the state, the bit vector or the samples
+    }
+    memcpy(parms_triplet, h, 3 * sizeof(Parms));
+    memcpy(rng_words4, h + 3 * sizeof(Parms), RNG_WORDS * sizeof(uint32_t));
+    if (bits && kind != 2) {
+        memcpy(bits, h + ONE_BITS, (size_t)pb);
+    }
+    if (pcm) {
+        memcpy(pcm, h + ONE_PCM, NS * sizeof(int16_t));
+    }
+    if (pcmf) {
+        memcpy(pcmf, h + ONE_PCMF, NS * sizeof(float));
+    }
+    return 0;
 }
 
 int mbe_b200_decode_frames_dev(mbe_b200_ctx* ctx, int codec, int soft, int n, const uint8_t* d_frames, uint8_t* d_bits,

@@ -225,28 +225,6 @@ static void result_out(mbe_process_result* result, const mbe_b200_result* r) {
     }
 }
 
-static void slot_in(mbe_b200_ctx* c, const mbe_parms* cur, const mbe_parms* prev, const mbe_parms* enh) {
-    mbe_parms t[3];
-    t[0] = *cur;
-    t[1] = *prev;
-    t[2] = *enh;
-    rng_ready_locked(c);
-    CK(mbe_b200_import_state(c, 0, 1, t));
-    CK(mbe_b200_import_rng(c, 0, 1, t_rng));
-}
-
-static void slot_out(mbe_b200_ctx* c, mbe_parms* cur, mbe_parms* prev, mbe_parms* enh) {
-    mbe_parms t[3];
-    CK(mbe_b200_export_state(c, 0, 1, t));
-    CK(mbe_b200_export_rng(c, 0, 1, t_rng));
-    if (t_failed) {
-        return;
-    }
-    *cur = t[0];
-    *prev = t[1];
-    *enh = t[2];
-}
-
 /* mbe_decode<Codec>[Soft]Frame: the result is reset first, then the arguments are checked (imbe7200x4400.c:709-744) */
 static int shim_decode(int codec, int soft, const void* fr, char* d, mbe_process_result* result) {
     int fbits = 0, pbits = 0;
@@ -293,15 +271,21 @@ static int shim_frame(int codec, int soft, float* outf, short* outs, int want_sh
     int16_t ps[NSAMP];
     mbe_b200_result r;
     memset(&r, 0, sizeof(r));
+    mbe_parms t[3];
+    t[0] = *cur;
+    t[1] = *prev;
+    t[2] = *enh;
     mbe_b200_ctx* c = shim_ctx();
-    slot_in(c, cur, prev, enh);
-    CK(mbe_b200_process_frames(c, codec, soft, 0, 1, 1, (const uint8_t*)fr, want_short ? ps : NULL, want_short ? NULL : pf,
-                               &r, bits));
-    if (!t_failed && r.status >= 0) {
-        slot_out(c, cur, prev, enh);
-    }
+    rng_ready_locked(c);
+    /* state in, one frame, state out: one upload, one download, one synchronisation (mbe_b200_single_frame) */
+    CK(mbe_b200_single_frame(c, codec, soft ? 1 : 0, 0, fr, t, t_rng, want_short ? ps : NULL, want_short ? NULL : pf, &r, bits));
     if (t_failed) {
         return MBE_STATUS_INVALID_ARGUMENT;  /* device failure: outputs and state untouched */
+    }
+    if (r.status >= 0) {
+        *cur = t[0];
+        *prev = t[1];
+        *enh = t[2];
     }
     if (r.status < 0) {
         return r.status;  /* nothing but the (reset) result has been touched, like the reference's early return */
@@ -338,14 +322,20 @@ static int shim_data(int codec, float* outf, short* outs, int want_short, mbe_pr
     }
     float pf[NSAMP];
     int16_t ps[NSAMP];
+    mbe_parms t[3];
+    t[0] = *cur;
+    t[1] = *prev;
+    t[2] = *enh;
     mbe_b200_ctx* c = shim_ctx();
-    slot_in(c, cur, prev, enh);
-    CK(mbe_b200_process_data(c, codec, 0, 1, 1, (const uint8_t*)d, &r, want_short ? ps : NULL, want_short ? NULL : pf));
-    if (!t_failed && r.status >= 0) {
-        slot_out(c, cur, prev, enh);
-    }
+    rng_ready_locked(c);
+    CK(mbe_b200_single_frame(c, codec, 2, 0, d, t, t_rng, want_short ? ps : NULL, want_short ? NULL : pf, &r, NULL));
     if (t_failed) {
         return MBE_STATUS_INVALID_ARGUMENT;
+    }
+    if (r.status >= 0) {
+        *cur = t[0];
+        *prev = t[1];
+        *enh = t[2];
     }
     if (r.status < 0) {
         return r.status;
