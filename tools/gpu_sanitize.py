@@ -53,3 +53,22 @@ dec.synthesize_tone(cur, dstar_id=np.arange(8, dtype=np.int32) + 3)
 dec.comfort_noise(dec.export_rng(0, 8))
 print("stage entry points ok")
 dec.close()
+# the single-frame call of the shim (mbe_b200_single_frame): caller-owned state in, one frame, state out
+import ctypes
+dec = pkg.Decoder(max_streams=2, device=0)
+lib = dec.lib
+for codec in (0, 3):
+    fr = T.random_hard_frames(codec, 1, 4, 31 + codec)
+    trip = dec.export_state(0, 1)[0].copy()
+    rng4 = dec.export_rng(0, 1)[0].copy()
+    pcm = np.zeros(160, np.int16)
+    res = np.zeros(1, pkg.RESULT_DTYPE)
+    bits = np.zeros(pkg.PARAM_BITS[codec], np.uint8)
+    for f in range(4):
+        frame = np.ascontiguousarray(fr[0, f])
+        rc = lib.mbe_b200_single_frame(dec.h, codec, 0, 0, frame.ctypes.data_as(ctypes.c_void_p), trip.ctypes.data_as(ctypes.c_void_p),
+                                       rng4.ctypes.data_as(ctypes.c_void_p), pcm.ctypes.data_as(ctypes.c_void_p), None,
+                                       res.ctypes.data_as(ctypes.c_void_p), bits.ctypes.data_as(ctypes.c_void_p))
+        assert rc == 0 and res["status"][0] >= 0
+print("single-frame call ok")
+dec.close()
