@@ -2450,6 +2450,8 @@ int mbe_b200_single_frame(mbe_b200_ctx* ctx, int codec, int kind, int stream, co
     if (!ctx->h_one) {
         CU(cudaHostAlloc((void**)&ctx->h_one, ONE_BYTES, cudaHostAllocDefault));
         CU(cudaMalloc((void**)&ctx->d_one, ONE_BYTES));
+        CU(cudaMemsetAsync(ctx->d_one, 0, ONE_BYTES, ctx->stream));   // (the whole blob is copied back: no uninitialised words)
+        memset(ctx->h_one, 0, ONE_BYTES);
     }
     const size_t in_bytes = kind == 2 ? (size_t)pb : (size_t)fb * (kind == 1 ? 2u : 1u);
     unsigned char* h = ctx->h_one;
