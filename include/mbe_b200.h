@@ -166,7 +166,9 @@ MBE_B200_API int mbe_b200_packed_frame_bytes(int codec);
  * chunk; large ones are about 32 chunks of whole blocks-per-SM multiples, with pieces that double from / halve towards
  * the two ends so that the copy-in ahead of the first kernel and the copy-out behind the last one stay small.
  * MBE_B200_CHUNKS / MBE_B200_TAPER / MBE_B200_KSTREAMS (environment) override chunk count, smallest piece in blocks
- * (0 = no taper) and the number of compute streams; they are tuning knobs, results do not depend on them. */
+ * (0 = no taper) and the number of compute streams; they are tuning knobs, results do not depend on them.  (On the
+ * multi-kernel path a context rounds the body chunks of very large batches - a chunk of at least one full stream range -
+ * to whole stream ranges; the plan reported here is the context-free one.) */
 MBE_B200_API int mbe_b200_pipeline_plan(int n_streams, int* sizes, int cap);
 /* Channel map (on-device de-interleave): by default packed bit k is frame position k.  With a map,
  * the packed frame holds the n_bits transmitted bits of the air interface in transmission order (MSB first, n_bits <=
