@@ -19,6 +19,9 @@ from __graft_entry__ import load_package  # noqa: E402
 def main():
     pkg = load_package()
     S, F, fb, codec = 65536, 50, 96, 3
+    if len(sys.argv) > 2:      # python tools/gpu_e2e_probe.py <codec 0..3> <streams>
+        codec, S = int(sys.argv[1]), int(sys.argv[2])
+        fb = {0: 184, 1: 168, 2: 96, 3: 96}[codec]
     dev = torch.device("cuda", 0)
     dec = pkg.Decoder(max_streams=S, device=0)
     dec.init_streams(0, S, np.arange(S, dtype=np.uint32) + 0xC0FFEE)
@@ -55,7 +58,7 @@ def main():
     t_res = timed(lambda: host(None, pr))
     t_d2h = timed(lambda: h_pcm.copy_(d_pcm, non_blocking=True))
     print("shape k=%s taper=%s chunks=%s | device-resident %.2f ms | host call pcm+results %.2f ms | results only %.2f ms | "
-          "plain 1.05 GB d2h %.2f ms" % (os.environ.get("MBE_B200_KSTREAMS", "-"), os.environ.get("MBE_B200_TAPER", "-"),
+          "plain PCM d2h %.2f ms" % (os.environ.get("MBE_B200_KSTREAMS", "-"), os.environ.get("MBE_B200_TAPER", "-"),
                                          os.environ.get("MBE_B200_CHUNKS", "-"), t_dev, t_full, t_res, t_d2h))
 
 
