@@ -449,7 +449,7 @@ __device__ __forceinline__ void store_pcm(const LaunchArgs& A, const WarpWS& ws,
         const size_t o = frame_idx * NS + 32 * ch + lane;
         const float v = ws.out[32 * ch + lane];
         if (A.pcmf) {
-            A.pcmf[o] = v * A.pcmf_scale;  // x 1.0f is exact: the default is the reference's float scale
+            A.pcmf[o] = ref_nan(v * A.pcmf_scale);  // x 1.0f is exact: the default is the reference's float scale
         }
         if (A.pcm) {
             A.pcm[o] = float_to_short(v);
@@ -879,10 +879,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MIN_BLOCKS_PER_SM) mbe_s
         __syncwarp();
         store_pcm(A, ws, (size_t)s, lane);
         for (int i = lane; i < HEAD_WORDS; i += 32) {
-            gc[i] = c[i];
+            gc[i] = ref_nan_parms_word(i, c[i]);
         }
         for (int j = lane; j < ENH_WORDS; j += 32) {
-            gp[enh_word(j)] = e[j];
+            gp[enh_word(j)] = ref_nan_parms_word(enh_word(j), e[j]);
         }
         if (lane == 0) {
             gc[SEED_WORD] = c[HEAD_WORDS];
@@ -924,7 +924,7 @@ mbe_stage_kernel(int op, int n, const uint8_t* __restrict__ bits, uint32_t* cur,
         __syncwarp();
         comfort_noise(ws, T, lane);
         for (int i = lane; i < NS; i += 32) {
-            pcmf[(size_t)s * NS + i] = ws.out[i];
+            pcmf[(size_t)s * NS + i] = ref_nan(ws.out[i]);
         }
         if (lane == 0) {
             r[0] = (uint32_t)(ws.rng.comfort & 0xffffffffULL);
@@ -1023,14 +1023,14 @@ mbe_stage_kernel(int op, int n, const uint8_t* __restrict__ bits, uint32_t* cur,
         }
         render_tone(ws, ok ? f1 : 0.0f, f2, amp, lane);
         for (int i = lane; i < NS; i += 32) {
-            pcmf[(size_t)s * NS + i] = ws.out[i];
+            pcmf[(size_t)s * NS + i] = ref_nan(ws.out[i]);
         }
     } else {
         adaptive_smoothing(ws.cur, ws.enh, 0, 0.0f, lane);
     }
     __syncwarp();
     for (int i = lane; i < HEAD_WORDS; i += 32) {
-        gc[i] = c[i];
+        gc[i] = ref_nan_parms_word(i, c[i]);
     }
     if (op <= STAGE_PARMS_A2450) {  // the decoders extend / touch prev_mp's magnitudes (SURVEY 8(a) trap T3)
         for (int j = lane; j < PREV_WORDS - 1; j += 32) {
@@ -1277,7 +1277,8 @@ __global__ void mbe_state_xfer_kernel(uint32_t* state, int first, int count, uin
         const size_t s = i / words, w = i % words;
         uint32_t* g = state + (size_t)(first + s) * STATE_WORDS + offset + w;
         if (to_dense) {
-            dense[i] = *g;
+            // exported mbe_parms images carry the reference's NaN pattern (the RNG words are integers: untouched)
+            dense[i] = (words == 3 * PARMS_WORDS) ? ref_nan_parms_word((int)(w % PARMS_WORDS), *g) : *g;
         } else {
             *g = dense[i];
         }
@@ -1290,7 +1291,7 @@ __global__ void mbe_single_io_kernel(uint32_t* state, int stream, uint32_t* blob
     constexpr int N = 3 * PARMS_WORDS + RNG_WORDS;   // the slot's first words are exactly these
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         if (to_blob) {
-            blob[i] = g[i];
+            blob[i] = (i < 3 * PARMS_WORDS) ? ref_nan_parms_word(i % PARMS_WORDS, g[i]) : g[i];
         } else {
             g[i] = blob[i];
         }

@@ -131,6 +131,17 @@ static_assert(offsetof(Parms, previousUw) == UW_WORD * 4 && offsetof(Parms, nois
                   offsetof(Parms, noiseOverlap) == OVERLAP_WORD * 4 && offsetof(Parms, mutingThreshold) == 297 * 4,
               "mbe_parms offsets");
 constexpr int PARMS_WORDS = sizeof(Parms) / 4;            // 651
+// NaN bit patterns at the library's boundary.  Every NaN the reference can produce on its x86-64 target comes from an invalid
+// operation (0/0 in the enhancement of an erasure model, 0 * inf, ...) and is the SSE default NaN 0xffc00000, which then
+// propagates unchanged; the GPU's arithmetic produces (and propagates) its canonical NaN 0x7fffffff instead.  Both decode
+// identically afterwards; only the bit pattern a caller sees differs, so float words that leave the library - exported
+// mbe_parms images, float PCM - carry the reference's pattern.  (NaNs with other payloads, i.e. imported ones, are left alone.)
+__host__ __device__ constexpr bool parms_word_is_float(int w) {
+    return w == 0 || (w >= 60 && w <= 288) || w == 291 || w == 293 || w >= 297;
+}
+__device__ __forceinline__ uint32_t ref_nan_word(uint32_t v) { return v == 0x7fffffffu ? 0xffc00000u : v; }
+__device__ __forceinline__ float ref_nan(float x) { return __uint_as_float(ref_nan_word(__float_as_uint(x))); }
+__device__ __forceinline__ uint32_t ref_nan_parms_word(int w, uint32_t v) { return parms_word_is_float(w) ? ref_nan_word(v) : v; }
 constexpr int RNG_WORDS = 4;                              // comfort lo, comfort hi, uv seed, uv override
 constexpr int SPILL_WORD = 3 * PARMS_WORDS + RNG_WORDS;   // a fourth mbe_parms image: scratch of the AMBE+2 replay path
 constexpr int STATE_WORDS = 4 * PARMS_WORDS + RNG_WORDS;  // per stream in HBM: cur, prev, enh, rng, scratch (10432 B)

@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(U_WARPS * 32, U_MINB) mbe_split_unvoiced_kerne
                     }
                     const size_t o = idx * NS + n;
                     if (A.pcmf) {
-                        A.pcmf[o] = v * A.pcmf_scale;
+                        A.pcmf[o] = ref_nan(v * A.pcmf_scale);
                     }
                     if (A.pcm) {
                         A.pcm[o] = float_to_short(v);

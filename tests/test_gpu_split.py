@@ -124,3 +124,64 @@ def test_kernel_timing_and_bank_counters(pkg):
     with pytest.raises(pkg.MbeB200Error):
         dec.set_kernel_path(2)
     dec.close()
+
+
+@pytest.mark.parametrize("codec", [0, 1, 2, 3])
+def test_state_machine_fuzz_against_the_oracle(pkg, codec):
+    """Differential fuzz of the frame state machines on the default (multi-kernel) path: 4096 streams x 24 frames per codec,
+    every frame drawn at random from {random bits, a fresh valid frame, the previous valid frame held, a valid frame with
+    1-8 % flipped bits, an AMBE tone / erasure signature, a frame with a non-binary bit}, so that repeats, headroom resets,
+    mutes, re-initialisation, erasures, replays and tones follow each other in every order - which is what the descriptor's
+    previousUw op codes have to replay exactly.  Everything against the oracle: bits, results, int16 / float PCM, final
+    triplets."""
+    rng = np.random.default_rng(0xF022 + codec)
+    S, F = 4096, 24
+    fb, pb = T.FRAME_BITS[codec], T.PARAM_BITS[codec]
+    enc = {0: T.encode_imbe7200_frame, 1: T.encode_imbe7100_frame}.get(codec, T.encode_ambe_frame)
+    P = 96
+    pool = np.zeros((P, fb), np.uint8)
+    for i in range(P):
+        p = rng.integers(0, 2, size=pb, dtype=np.uint8)
+        if codec <= 1:
+            p[codec] = 0
+        elif i % 6 == 0:
+            p[0:6] = 1                      # tone / erasure signatures
+            if i % 12 == 0:
+                p[45:49] = 0
+        pool[i] = enc(p).reshape(-1)
+    kind = rng.choice(6, size=(S, F), p=[0.22, 0.30, 0.22, 0.18, 0.06, 0.02])
+    pick = rng.integers(0, P, size=(S, F))
+    frames = np.zeros((S, F, fb), np.uint8)
+    last = pool[pick[:, 0]]
+    for f in range(F):
+        k = kind[:, f]
+        fresh = pool[pick[:, f]]
+        cur = np.where((k == 2)[:, None], last, fresh)                 # held frame
+        last = np.where(((k == 1) | (k == 2) | (k == 3))[:, None], cur, last)
+        noisy = cur ^ (rng.random((S, fb)) < rng.uniform(0.01, 0.08, size=(S, 1))).astype(np.uint8)
+        rnd = rng.integers(0, 2, size=(S, fb), dtype=np.uint8)
+        out = np.where((k == 0)[:, None], rnd, np.where((k == 3)[:, None], noisy, cur))
+        sig = pool[(pick[:, f] // 6) * 6 % P]                          # a signature frame (AMBE) / a valid frame (IMBE)
+        out = np.where((k == 4)[:, None], sig, out)
+        bad = out.copy()
+        bad[:, 7] = 2
+        frames[:, f] = np.where((k == 5)[:, None], bad, out)
+    seeds = T.stream_seeds(S, 0xF0 + codec)
+    want = T.run_cpu(T.load_oracle().mbo_run, codec, 0, frames, seeds, n_threads=16)
+    dec = pkg.Decoder(max_streams=S, device=0)
+    assert dec.kernel_path() == 1
+    dec.init_streams(0, S, seeds)
+    got = dec.process_frames(codec, frames, want_float=True)
+    res = got["results"]
+    assert np.array_equal(res["status"], want["results"][..., 0])
+    ok = want["results"][..., 0] >= 0
+    assert np.array_equal(got["bits"][ok], want["bits"][ok])
+    assert np.array_equal(res["total_errors"][ok], want["results"][..., 4][ok])
+    assert np.array_equal(res["flags"][ok].astype(np.int64), want["results"][..., 5][ok].astype(np.int64) & 0xffffffff)
+    assert np.array_equal(got["pcmf"].view(np.uint32), want["pcmf"].view(np.uint32))
+    assert np.array_equal(got["pcm"], want["pcm"])
+    assert np.array_equal(dec.export_state(0, S), want["state"])
+    flags = res["flags"][ok]
+    print(T.CODEC_NAMES[codec], "frames", int(ok.sum()), "rejected", int((~ok).sum()), "repeat", int((flags & 0x40 != 0).sum()),
+          "mute", int((flags & 0x80 != 0).sum()), "tone", int((flags & 0x10 != 0).sum()), "erasure", int((flags & 0x20 != 0).sum()))
+    dec.close()
