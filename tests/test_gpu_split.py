@@ -126,16 +126,18 @@ def test_kernel_timing_and_bank_counters(pkg):
     dec.close()
 
 
+@pytest.mark.parametrize("soft", [0, 1], ids=["hard", "soft"])
 @pytest.mark.parametrize("codec", [0, 1, 2, 3])
-def test_state_machine_fuzz_against_the_oracle(pkg, codec):
+def test_state_machine_fuzz_against_the_oracle(pkg, codec, soft):
     """Differential fuzz of the frame state machines on the default (multi-kernel) path: 4096 streams x 24 frames per codec,
     every frame drawn at random from {random bits, a fresh valid frame, the previous valid frame held, a valid frame with
     1-8 % flipped bits, an AMBE tone / erasure signature, a frame with a non-binary bit}, so that repeats, headroom resets,
     mutes, re-initialisation, erasures, replays and tones follow each other in every order - which is what the descriptor's
     previousUw op codes have to replay exactly.  Everything against the oracle: bits, results, int16 / float PCM, final
-    triplets."""
-    rng = np.random.default_rng(0xF022 + codec)
-    S, F = 4096, 24
+    triplets.  Soft-decision input: the same mixture with seeded flips and reliabilities (fewer streams: the oracle's
+    exhaustive soft decoders are slow), decoded in three launches of different lengths."""
+    rng = np.random.default_rng(0xF022 + codec + 16 * soft)
+    S, F = (4096, 24) if not soft else (384, 18)
     fb, pb = T.FRAME_BITS[codec], T.PARAM_BITS[codec]
     enc = {0: T.encode_imbe7200_frame, 1: T.encode_imbe7100_frame}.get(codec, T.encode_ambe_frame)
     P = 96
@@ -167,11 +169,19 @@ def test_state_machine_fuzz_against_the_oracle(pkg, codec):
         bad[:, 7] = 2
         frames[:, f] = np.where((k == 5)[:, None], bad, out)
     seeds = T.stream_seeds(S, 0xF0 + codec)
-    want = T.run_cpu(T.load_oracle().mbo_run, codec, 0, frames, seeds, n_threads=16)
+    if soft:
+        frames = T.soften(frames, rng, flip_p=0.03)
+        frames[..., 0] = np.where(kind[..., None] == 5, np.where(np.arange(fb) == 7, 2, frames[..., 0]), frames[..., 0])
+    want = T.run_cpu(T.load_oracle().mbo_run, codec, soft, frames, seeds, n_threads=16)
     dec = pkg.Decoder(max_streams=S, device=0)
     assert dec.kernel_path() == 1
     dec.init_streams(0, S, seeds)
-    got = dec.process_frames(codec, frames, want_float=True)
+    if soft:
+        parts = [dec.process_frames(codec, np.ascontiguousarray(frames[:, a:b]), soft=True, want_float=True)
+                 for a, b in ((0, 1), (1, 7), (7, F))]
+        got = {k: np.concatenate([p[k] for p in parts], axis=1) for k in ("bits", "results", "pcm", "pcmf")}
+    else:
+        got = dec.process_frames(codec, frames, want_float=True)
     res = got["results"]
     assert np.array_equal(res["status"], want["results"][..., 0])
     ok = want["results"][..., 0] >= 0
