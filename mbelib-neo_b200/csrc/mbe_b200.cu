@@ -1034,7 +1034,7 @@ mbe_stage_kernel(int op, int n, const uint8_t* __restrict__ bits, uint32_t* cur,
     }
     if (op <= STAGE_PARMS_A2450) {  // the decoders extend / touch prev_mp's magnitudes (SURVEY 8(a) trap T3)
         for (int j = lane; j < PREV_WORDS - 1; j += 32) {
-            gp[prev_word(j)] = p[j];
+            gp[prev_word(j)] = ref_nan_parms_word(prev_word(j), p[j]);
         }
     }
     if (status && lane == 0) {
