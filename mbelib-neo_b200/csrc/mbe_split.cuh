@@ -242,6 +242,10 @@ struct SynthArgs {
 // store) and phase B (lane = sample, LDS.128 over four consecutive slots) are both bank-conflict free, and every access is
 // a base register + immediate offset (no swizzle arithmetic in the loops)
 constexpr int BT_STRIDE = 36;
+#ifndef MBE_BANK_STEPS
+#define MBE_BANK_STEPS 16
+#endif
+constexpr int BANK_STEPS = MBE_BANK_STEPS;   // oscillator steps per loop body of phase A (8 / 16 / 32)
 struct __align__(16) BankWS {
     float tile[32 * BT_STRIDE];
     float out[BG][NS];      // voiced samples of the group's frames (lane i owns i, 32 + i, ...)
@@ -356,15 +360,15 @@ __global__ void __launch_bounds__(B_WARPS * 32, B_MINB) mbe_split_bank_kernel(co
                 const float4* W4 = reinterpret_cast<const float4*>(Wb) + 8 * ch;
                 float* tp = tile + lane;
 #pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < 32 / BANK_STEPS; ++h) {
 #pragma unroll
-                    for (int n4 = 0; n4 < 4; ++n4) {
-                        const float4 w4 = W4[4 * h + n4];
+                    for (int n4 = 0; n4 < BANK_STEPS / 4; ++n4) {
+                        const float4 w4 = W4[(BANK_STEPS / 4) * h + n4];
                         const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             if (!k2lane) {
-                                tp[(4 * n4 + i) * BT_STRIDE] = (gg * wv[i]) * c;   // row n = 16 h + 4 n4 + i
+                                tp[(4 * n4 + i) * BT_STRIDE] = (gg * wv[i]) * c;   // row n = BANK_STEPS h + 4 n4 + i
                             }
                             const float cn = (c * cd) - (s * sd);
                             const float sn = (s * cd) + (c * sd);
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(B_WARPS * 32, B_MINB) mbe_split_bank_kernel(co
                             s = sn;
                         }
                     }
-                    tp += 16 * BT_STRIDE;
+                    tp += BANK_STEPS * BT_STRIDE;
                 }
                 // phase-interpolated harmonics of this pass: lane = sample (mbelib.c:953-968); the slot's lane holds its record
                 if (k2mask) {
